@@ -1,0 +1,90 @@
+"""Loader of the in-tree C-ABI shared library (foldcomp_b200/csrc/libfcz_engine.so).
+
+The library is built by `__graft_entry__.build()` / `make -C foldcomp_b200/csrc`.  There is NO
+fallback: if the library is missing the import fails loudly (the product path is CUDA only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfcz_engine.so")
+
+# every symbol include/fcz_engine.h declares
+SYMBOLS = [
+    "fcz_engine_create",
+    "fcz_engine_destroy",
+    "fcz_engine_set_opts",
+    "fcz_encode_bound",
+    "fcz_encode_batch",
+    "fcz_decode_plan",
+    "fcz_decode_batch",
+    "fcz_engine_sync",
+    "fcz_engine_launch_count",
+    "fcz_strerror",
+    "fcz_last_error",
+    "fcz_type_natoms",
+    "fcz_type_name3",
+    "fcz_type_atom_name",
+    "fcz_type_alt_slot",
+    "fcz_type_pred",
+    "fcz_type_bond_length",
+    "fcz_type_bond_angle",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the CUDA engine first "
+            "(python -c 'import __graft_entry__ as g; g.build()' or make -C foldcomp_b200/csrc). "
+            "foldcomp_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    lib.fcz_engine_create.restype = C.c_void_p
+    lib.fcz_engine_create.argtypes = [C.c_int, P(abi.FczOpts)]
+    lib.fcz_engine_destroy.restype = None
+    lib.fcz_engine_destroy.argtypes = [C.c_void_p]
+    lib.fcz_engine_set_opts.restype = C.c_int
+    lib.fcz_engine_set_opts.argtypes = [C.c_void_p, P(abi.FczOpts)]
+    lib.fcz_encode_bound.restype = C.c_uint64
+    lib.fcz_encode_bound.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32]
+    lib.fcz_encode_batch.restype = C.c_int
+    lib.fcz_encode_batch.argtypes = [C.c_void_p, P(abi.FczChainBatch), P(abi.FczBlobBatch)]
+    lib.fcz_decode_plan.restype = C.c_int
+    lib.fcz_decode_plan.argtypes = [C.c_void_p, P(abi.FczBlobBatch), P(abi.FczChainBatch), P(abi.FczSizes)]
+    lib.fcz_decode_batch.restype = C.c_int
+    lib.fcz_decode_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), P(abi.FczChainBatch)]
+    lib.fcz_engine_sync.restype = C.c_int
+    lib.fcz_engine_sync.argtypes = [C.c_void_p]
+    lib.fcz_engine_launch_count.restype = C.c_uint64
+    lib.fcz_engine_launch_count.argtypes = [C.c_void_p]
+    lib.fcz_strerror.restype = C.c_char_p
+    lib.fcz_strerror.argtypes = [C.c_int]
+    lib.fcz_last_error.restype = C.c_char_p
+    lib.fcz_last_error.argtypes = [C.c_void_p]
+    lib.fcz_type_natoms.restype = C.c_int
+    lib.fcz_type_natoms.argtypes = [C.c_int]
+    lib.fcz_type_name3.restype = C.c_char_p
+    lib.fcz_type_name3.argtypes = [C.c_int]
+    lib.fcz_type_atom_name.restype = C.c_char_p
+    lib.fcz_type_atom_name.argtypes = [C.c_int, C.c_int]
+    lib.fcz_type_alt_slot.restype = C.c_int
+    lib.fcz_type_alt_slot.argtypes = [C.c_int, C.c_int]
+    lib.fcz_type_pred.restype = C.c_int
+    lib.fcz_type_pred.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.fcz_type_bond_length.restype = C.c_float
+    lib.fcz_type_bond_length.argtypes = [C.c_int, C.c_int]
+    lib.fcz_type_bond_angle.restype = C.c_float
+    lib.fcz_type_bond_angle.argtypes = [C.c_int, C.c_int]
+    _lib = lib
+    return lib

@@ -1,0 +1,153 @@
+/* include/fcz_engine.h -- C ABI of the B200 FCZ encode/decode engine.
+ *
+ * This is the drop-in boundary for Foldcomp's per-chain codec.  The
+ * reference has no FFI for this path; its seam is the C++ class `Foldcomp`
+ * (/root/reference/src/foldcomp.h:267-402) that the CLI lambdas (src/main.cpp:438-536 encode,
+ * 612-689 decode) and the CPython module (foldcomp/foldcomp.cxx:197-220, 253-293) call once per
+ * chain.  The entry points below replace, for a BATCH of chains at once:
+ *
+ *   fcz_encode_batch   <-  Foldcomp::compress()   src/foldcomp.cpp:562-606  (+ preprocess 450-559)
+ *                          Foldcomp::writeStream() src/foldcomp.cpp:1038-1109
+ *   fcz_decode_plan    <-  the header part of Foldcomp::read()  src/foldcomp.cpp:904-924
+ *   fcz_decode_batch   <-  Foldcomp::read()        src/foldcomp.cpp:904-1036
+ *                          Foldcomp::decompress()  src/foldcomp.cpp:779-902
+ *   per-chain status   <-  read()'s int return (0 ok, -1 bad magic, src/foldcomp.cpp:911-915),
+ *                          ValidityError (src/foldcomp.h:59-67), and the std::out_of_range that
+ *                          escapes AAS.at() for residue names outside the table (src/sidechain.cpp:177)
+ *
+ * Chains are exchanged in a string-free canonical SoA layout: every residue carries a 5-bit type
+ * code (src/utility.h:133-205) and its heavy atoms in the fixed slot order of the reference's
+ * AminoAcid::atoms table (src/amino_acid.h:69-406; N, CA, C, O, CB, ...), FCZ_NATOMS[code] atoms
+ * per residue, a missing atom given as (0,0,0) exactly as findFirstAtomCoords() returns it
+ * (src/sidechain.cpp:140-147).  The host adapter (foldcomp_b200/csrc/foldcomp_gpu.h) converts
+ * std::vector<AtomCoordinate>-style records to and from this layout.
+ *
+ * All pointers inside a batch live in ONE memory space, named by `mem`:
+ *   FCZ_MEM_HOST    host memory (pageable or pinned); the call copies in/out and returns when the
+ *                   results are on the host.
+ *   FCZ_MEM_DEVICE  device memory of the engine's GPU; the call only enqueues work on the
+ *                   engine's stream and returns (results are valid after the stream syncs).
+ * Buffers are caller-owned; the engine owns its stream-ordered scratch.  One engine per GPU; calls
+ * on one engine must be serialised by the caller, different engines are independent.
+ */
+#ifndef FCZ_ENGINE_H
+#define FCZ_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCZ_MEM_HOST 0
+#define FCZ_MEM_DEVICE 1
+
+/* return / status codes */
+#define FCZ_OK 0
+#define FCZ_E_MAGIC (-1)         /* blob does not start with "FCMP"        (read() == -1)        */
+#define FCZ_E_TRUNCATED (-2)     /* blob shorter than its header implies                          */
+#define FCZ_E_RESIDUE (-3)       /* residue code outside the 20 amino acids + UNK (AAS.at throws) */
+#define FCZ_E_LIMIT (-4)         /* nResidue/nAtom > 65535, nAnchor > 255 (src/foldcomp.h:118-131) or L < 2 */
+#define FCZ_E_CAPACITY (-5)      /* an output buffer is too small                                 */
+#define FCZ_E_CUDA (-6)          /* CUDA runtime error (see fcz_last_error)                       */
+#define FCZ_E_ARG (-7)           /* bad argument                                                  */
+
+typedef struct fcz_engine fcz_engine;
+
+typedef struct fcz_opts {
+    int32_t anchor_threshold;   /* Foldcomp::anchorThreshold, CLI -b/--break; default 25 (src/foldcomp.h:56) */
+    int32_t use_alt_atom_order; /* Foldcomp::useAltAtomOrder, CLI -a/--alt (decode only)          */
+    void* stream;               /* cudaStream_t to enqueue on; NULL = engine-owned stream         */
+} fcz_opts;
+
+/* Per-chain scalars that the reference keeps in Foldcomp members / CompressedFileHeader
+ * (src/foldcomp.h:118-136). */
+typedef struct fcz_chain_meta {
+    uint16_t n_atom;      /* header nAtom: atom count of the ORIGINAL input incl. OXT            */
+    uint16_t idx_residue; /* residue number of the first residue                                 */
+    uint16_t idx_atom;    /* serial of the first atom                                            */
+    uint8_t chain;        /* chain id character                                                  */
+    uint8_t has_oxt;      /* 1 when the input ended with an OXT atom (src/foldcomp.cpp:473-481)  */
+    float oxt[3];         /* its coordinates, zeros otherwise                                    */
+} fcz_chain_meta;
+
+/* A batch of chains in canonical slot order.  Input of encode, output of decode. */
+typedef struct fcz_chain_batch {
+    uint32_t n_chains;
+    int32_t mem;          /* FCZ_MEM_HOST | FCZ_MEM_DEVICE for every pointer below               */
+    uint32_t* res_off;    /* [n_chains+1] first residue of each chain                            */
+    uint64_t* atom_off;   /* [n_chains+1] first atom of each chain (sum of FCZ_NATOMS)           */
+    uint32_t* title_off;  /* [n_chains+1] first title byte of each chain                         */
+    uint8_t* res_type;    /* [n_res]   5-bit residue codes                                       */
+    float* bfactor;       /* [n_res]   B-factor / pLDDT of the residue's CA                      */
+    float* xyz;           /* [3*n_atoms] x,y,z per atom, residue-major, slot order               */
+    char* titles;         /* [n_title_bytes] concatenated titles, no terminators                 */
+    fcz_chain_meta* meta; /* [n_chains]                                                          */
+    int32_t* status;      /* [n_chains] per-chain status written by decode (may be NULL on encode input) */
+    /* capacities (elements) of res_type/bfactor, xyz/3 and titles when used as decode output     */
+    uint64_t res_cap, atom_cap, title_cap;
+} fcz_chain_batch;
+
+/* A batch of FCZ blobs, tightly concatenated.  Output of encode, input of decode. */
+typedef struct fcz_blob_batch {
+    uint32_t n_chains;
+    int32_t mem;
+    uint64_t* blob_off; /* [n_chains+1] byte offset of each blob in `bytes`                      */
+    uint8_t* bytes;
+    int32_t* status;    /* [n_chains] per-chain status written by encode (may be NULL on decode input) */
+    uint64_t bytes_cap; /* capacity of `bytes` when used as encode output                        */
+} fcz_blob_batch;
+
+/* totals returned by the planning calls */
+typedef struct fcz_sizes {
+    uint64_t n_res, n_atoms, n_title_bytes, n_blob_bytes;
+} fcz_sizes;
+
+fcz_engine* fcz_engine_create(int device, const fcz_opts* opts);
+void fcz_engine_destroy(fcz_engine* e);
+int fcz_engine_set_opts(fcz_engine* e, const fcz_opts* opts);
+
+/* Upper bound of the encoded size of a batch, from totals only (host arithmetic, no GPU work):
+ * sum over chains of 97 + 40*nAnchor + lenTitle + 8*L + (atoms - 3*L) + L  (SURVEY.md Appendix A). */
+uint64_t fcz_encode_bound(uint64_t n_chains, uint64_t n_res, uint64_t n_atoms,
+                          uint64_t n_title_bytes, int32_t anchor_threshold);
+
+/* Encode every chain of `in` into `out`.  Fills out->blob_off[0..n], out->bytes and out->status.
+ * Blobs are byte-identical to the reference's writeStream() output except that the four padding
+ * bytes of CompressedFileHeader (file offsets 14,15,22,23), which the reference leaves
+ * uninitialised, are written as zero.  A chain with a non-zero status gets an empty blob. */
+int fcz_encode_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch* out);
+
+/* Read the blob headers and fill out->res_off, out->atom_off, out->title_off (n_chains+1 each)
+ * and out->status.  `totals` (host memory) receives the sizes the caller must provide to
+ * fcz_decode_batch; this call synchronises the engine's stream. */
+int fcz_decode_plan(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out, fcz_sizes* totals);
+
+/* Decode every blob of `in` into `out` (whose offset arrays were filled by fcz_decode_plan and
+ * whose data arrays have at least the planned capacities).  Atom order inside a residue is the
+ * canonical slot order, or FCZ_ALT order when opts.use_alt_atom_order is set. */
+int fcz_decode_batch(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out);
+
+/* Block until everything enqueued on the engine's stream has finished. */
+int fcz_engine_sync(fcz_engine* e);
+
+/* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
+uint64_t fcz_engine_launch_count(const fcz_engine* e);
+
+const char* fcz_strerror(int code);
+const char* fcz_last_error(const fcz_engine* e);
+
+/* Residue tables (foldcomp_b200/csrc/fcz_tables.h) for host code that cannot include the header. */
+int fcz_type_natoms(int code);
+const char* fcz_type_name3(int code);
+const char* fcz_type_atom_name(int code, int slot);
+int fcz_type_alt_slot(int code, int pos);
+int fcz_type_pred(int code, int slot, int which);
+float fcz_type_bond_length(int code, int slot);
+float fcz_type_bond_angle(int code, int slot);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCZ_ENGINE_H */

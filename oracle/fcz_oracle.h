@@ -1,0 +1,46 @@
+/* oracle/fcz_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C, scalar, CPU restatement of the reference's FCZ encode/decode algorithm
+ * (steineggerlab/foldcomp @ 30496eb), used ONLY as the parity checker by tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg.  The product path
+ * (foldcomp_b200/) never links, imports or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_ref.py checks this restatement against the
+ * unmodified reference compiled in this container (oracle/_ref/libfoldcomp_ref.so): FCZ bytes
+ * bit-identical (modulo the four uninitialised header padding bytes), decoded coordinates
+ * bit-identical; tests/test_oracle_golden.py repeats it against committed fixtures
+ * (tests/golden/) generated from the reference by tests/golden/make_golden.py.
+ */
+#ifndef FCZ_ORACLE_H
+#define FCZ_ORACLE_H
+#include "../include/fcz_engine.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Encode one chain (canonical slot layout).  Returns blob size, or a negative FCZ_E_* code.
+ * out may be NULL to query the size. */
+int64_t fcz_oracle_encode_chain(const uint8_t* res_type, uint32_t L, const float* xyz,
+                                const float* bfactor, const fcz_chain_meta* meta, const char* title,
+                                uint32_t title_len, int32_t anchor_threshold, uint8_t* out,
+                                uint64_t cap);
+
+/* Header peek: residues, decoded atoms (sum of table atoms + OXT), title length. */
+int fcz_oracle_peek(const uint8_t* blob, uint64_t len, uint32_t* L, uint64_t* n_atoms,
+                    uint32_t* title_len);
+
+/* Decode one blob.  xyz gets n_atoms*3 floats (OXT last if present), res_type/bfactor L entries. */
+int fcz_oracle_decode_chain(const uint8_t* blob, uint64_t len, int use_alt, uint8_t* res_type,
+                            float* bfactor, float* xyz, fcz_chain_meta* meta, char* title);
+
+/* Batch versions over host-memory batches (same structs as the engine ABI); OpenMP over chains. */
+int fcz_oracle_encode_batch(const fcz_chain_batch* in, fcz_blob_batch* out, int32_t anchor_threshold,
+                            int n_threads);
+int fcz_oracle_decode_plan(const fcz_blob_batch* in, fcz_chain_batch* out, fcz_sizes* totals);
+int fcz_oracle_decode_batch(const fcz_blob_batch* in, fcz_chain_batch* out, int use_alt, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,76 @@
+// tests/emu/fcz_emu.cpp -- TEST HARNESS (not product, not a fallback).
+// Instantiates the per-chain codec of foldcomp_b200/csrc/fcz_codec.h with a ONE-THREAD execution
+// context so the algorithm the CUDA kernels run (phases, indexing, stitch decomposition, bit
+// packing) can be checked against the oracle on a machine without a GPU.  It shares no code with
+// oracle/; what it cannot check (barriers, TMA staging, device libm) is covered by the -m gpu tests.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../foldcomp_b200/csrc/fcz_codec.h"
+
+using namespace fcz;
+
+struct HostCtx {
+    int tid = 0, nthr = 1, lane = 0, warp = 0, nwarps = 1;
+    void sync() {}
+    void stage_wait() {}
+    uint32_t excl_scan(uint32_t) { return 0; }
+    float wmin(float v) { return v; }
+    float wmax(float v) { return v; }
+};
+
+static const Tables* tables() {
+    static Tables t;
+    static bool init = false;
+    if (!init) { build_tables(&t); init = true; }
+    return &t;
+}
+
+extern "C" {
+
+int64_t emu_encode_chain(const uint8_t* res_type, uint32_t L, const float* xyz, const float* bfac,
+                         const fcz_chain_meta* meta, const char* title, uint32_t title_len, int32_t b,
+                         uint8_t* out, uint64_t cap) {
+    const Tables* tb = tables();
+    uint32_t A = 0;
+    for (uint32_t r = 0; r < L; r++) {
+        if (res_type[r] >= FCZ_NUM_CODES || tb->natoms[res_type[r]] == 0) return FCZ_E_RESIDUE;
+        A += tb->natoms[res_type[r]];
+    }
+    if (L < 2 || L > 65535 || b < 1 || anchor_count(L, b) > 255) return FCZ_E_LIMIT;
+    Layout y = make_layout(L, A - 3 * L, title_len, (uint32_t)anchor_count(L, b));
+    if (!out) return y.size;
+    if (y.size > cap) return FCZ_E_CAPACITY;
+    std::vector<uint32_t> aoff(L + 1);
+    std::vector<uint16_t> ares(A);
+    std::vector<float> ang(6 * (size_t)L), red(FCZ_RED_FLOATS(1));
+    EncChain ch;
+    ch.L = L; ch.A = A; ch.title_len = title_len; ch.b = b;
+    ch.type = res_type; ch.bfac = bfac; ch.X = xyz; ch.title = title; ch.meta = meta; ch.B = out;
+    ch.aoff = aoff.data(); ch.ares = ares.data(); ch.ang = ang.data(); ch.red = red.data();
+    HostCtx cx;
+    encode_chain(cx, tb, ch);
+    return y.size;
+}
+
+int emu_decode_chain(const uint8_t* blob, uint64_t len, int use_alt, uint8_t* res_type, float* bfac,
+                     float* xyz, fcz_chain_meta* meta, char* title) {
+    const Tables* tb = tables();
+    if (len < HDR_BYTES || memcmp(blob, "FCMP", 4) != 0) return FCZ_E_MAGIC;
+    uint32_t L = get_u16(blob + OFF_NRES);
+    Layout y = make_layout(L, get_u32(blob + OFF_NSC), get_u32(blob + OFF_LENTITLE), blob[OFF_NANCHOR]);
+    if (y.size > len || L < 2 || y.n_anchor < 2) return FCZ_E_TRUNCATED;
+    std::vector<uint32_t> aoff(L + 1);
+    std::vector<cs> tor(3 * (size_t)L), ang(3 * (size_t)L);
+    std::vector<float> seg((size_t)(y.n_anchor - 1) * FCZ_SEG_FLOATS);
+    DecChain ch;
+    ch.blob = blob; ch.y = y; ch.use_alt = use_alt;
+    ch.out_xyz = xyz; ch.out_type = res_type; ch.out_bfac = bfac; ch.out_meta = meta; ch.out_title = title;
+    ch.aoff = aoff.data(); ch.tor = tor.data(); ch.ang = ang.data(); ch.seg = seg.data();
+    HostCtx cx;
+    decode_chain(cx, tb, ch);
+    return FCZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+"""ctypes wrappers of the CHECKERS used by the tests:
+  * oracle/libfcz_oracle.so       -- plain-C restatement (fcz_oracle.c)
+  * oracle/_ref/libfoldcomp_ref.so -- the unmodified reference compiled in place (ref_shim.cpp)
+  * tests/emu/libfcz_emu.so       -- one-thread host instantiation of the product codec header
+None of this is product code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from foldcomp_b200 import abi  # noqa: E402
+from foldcomp_b200.abi import HostBlobBatch, HostChainBatch  # noqa: E402
+from foldcomp_b200.tables import tables  # noqa: E402
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "libfcz_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libfoldcomp_ref.so")
+EMU_SO = os.path.join(ROOT, "tests", "emu", "libfcz_emu.so")
+REFERENCE_DIR = "/root/reference"
+MASK = (14, 15, 22, 23)  # uninitialised CompressedFileHeader padding in the reference
+
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libfcz_oracle.so"])
+    if os.path.isdir(os.path.join(REFERENCE_DIR, "src")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+
+
+def build_emu():
+    src = os.path.join(ROOT, "tests", "emu", "fcz_emu.cpp")
+    deps = [src] + [os.path.join(ROOT, "foldcomp_b200", "csrc", f) for f in ("fcz_codec.h", "fcz_math.h", "fcz_format.h", "fcz_tables.h")]
+    if not os.path.exists(EMU_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMU_SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", EMU_SO, src])
+
+
+_cache = {}
+
+
+def oracle():
+    if "oracle" not in _cache:
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        lib = C.CDLL(ORACLE_SO)
+        lib.fcz_oracle_encode_chain.restype = C.c_int64
+        lib.fcz_oracle_encode_chain.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_uint64]
+        lib.fcz_oracle_peek.restype = C.c_int
+        lib.fcz_oracle_peek.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        lib.fcz_oracle_decode_chain.restype = C.c_int
+        lib.fcz_oracle_decode_chain.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.fcz_oracle_encode_batch.restype = C.c_int
+        lib.fcz_oracle_encode_batch.argtypes = [C.POINTER(abi.FczChainBatch), C.POINTER(abi.FczBlobBatch), C.c_int32, C.c_int]
+        lib.fcz_oracle_decode_plan.restype = C.c_int
+        lib.fcz_oracle_decode_plan.argtypes = [C.POINTER(abi.FczBlobBatch), C.POINTER(abi.FczChainBatch), C.POINTER(abi.FczSizes)]
+        lib.fcz_oracle_decode_batch.restype = C.c_int
+        lib.fcz_oracle_decode_batch.argtypes = [C.POINTER(abi.FczBlobBatch), C.POINTER(abi.FczChainBatch), C.c_int, C.c_int]
+        _cache["oracle"] = lib
+    return _cache["oracle"]
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    if "ref" not in _cache:
+        lib = C.CDLL(REF_SO)
+        lib.ref_compress.restype = C.c_int
+        lib.ref_compress.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_char, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        lib.ref_decompress.restype = C.c_int
+        lib.ref_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.ref_roundtrip_batch.restype = C.c_int
+        lib.ref_roundtrip_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.ref_max_threads.restype = C.c_int
+        lib.ref_type_natoms.restype = C.c_int
+        lib.ref_type_natoms.argtypes = [C.c_int]
+        _cache["ref"] = lib
+    return _cache["ref"]
+
+
+def emu():
+    if "emu" not in _cache:
+        build_emu()
+        lib = C.CDLL(EMU_SO)
+        lib.emu_encode_chain.restype = C.c_int64
+        lib.emu_encode_chain.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_uint64]
+        lib.emu_decode_chain.restype = C.c_int
+        lib.emu_decode_chain.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _cache["emu"] = lib
+    return _cache["emu"]
+
+
+# --------------------------------------------------------------------------- per-chain convenience
+
+
+def _chain_args(b: HostChainBatch, c: int):
+    r0, r1 = int(b.res_off[c]), int(b.res_off[c + 1])
+    a0, a1 = int(b.atom_off[c]), int(b.atom_off[c + 1])
+    t0, t1 = int(b.title_off[c]), int(b.title_off[c + 1])
+    rt = np.ascontiguousarray(b.res_type[r0:r1])
+    bf = np.ascontiguousarray(b.bfactor[r0:r1])
+    xyz = np.ascontiguousarray(b.xyz[a0:a1])
+    title = bytes(b.titles[t0:t1])
+    meta = np.ascontiguousarray(b.meta[c : c + 1])
+    return rt, bf, xyz, title, meta
+
+
+def _encode_with(fn, b: HostChainBatch, c: int, anchor: int):
+    rt, bf, xyz, title, meta = _chain_args(b, c)
+    cap = abi.encode_bound(1, len(rt), len(xyz), len(title), anchor) + 64
+    out = np.zeros(cap, np.uint8)
+    n = fn(rt.ctypes.data, len(rt), xyz.ctypes.data, bf.ctypes.data, meta.ctypes.data, title, len(title), anchor, out.ctypes.data, cap)
+    if n < 0:
+        return int(n)
+    return bytes(out[:n])
+
+
+def oracle_encode(b: HostChainBatch, c: int = 0, anchor: int = 25):
+    return _encode_with(oracle().fcz_oracle_encode_chain, b, c, anchor)
+
+
+def emu_encode(b: HostChainBatch, c: int = 0, anchor: int = 25):
+    return _encode_with(emu().emu_encode_chain, b, c, anchor)
+
+
+def ref_encode(b: HostChainBatch, c: int = 0, anchor: int = 25):
+    rt, bf, xyz, title, meta = _chain_args(b, c)
+    m = meta[0]
+    cap = abi.encode_bound(1, len(rt), len(xyz), len(title), anchor) + 64
+    out = np.zeros(cap, np.uint8)
+    n = C.c_size_t(0)
+    oxt = np.ascontiguousarray(m["oxt"], np.float32)
+    rc = ref().ref_compress(rt.ctypes.data, len(rt), xyz.ctypes.data, bf.ctypes.data, int(m["has_oxt"]), oxt.ctypes.data,
+                            int(m["idx_residue"]), int(m["idx_atom"]), bytes([int(m["chain"])]), title, len(title), anchor,
+                            out.ctypes.data, cap, C.byref(n))
+    if rc != 0:
+        return rc
+    return bytes(out[: n.value])
+
+
+class Decoded:
+    def __init__(self, res_type, bfac, xyz, meta, title):
+        self.res_type, self.bfactor, self.xyz, self.meta, self.title = res_type, bfac, xyz, meta, title
+
+
+def _peek(blob: bytes):
+    L, na, tl = C.c_uint32(), C.c_uint64(), C.c_uint32()
+    buf = np.frombuffer(blob, np.uint8)
+    rc = oracle().fcz_oracle_peek(buf.ctypes.data, len(blob), C.byref(L), C.byref(na), C.byref(tl))
+    return rc, L.value, na.value, tl.value
+
+
+def _decode_with(fn, blob: bytes, use_alt: bool = False):
+    rc, L, na, tl = _peek(blob)
+    if rc:
+        return rc
+    buf = np.frombuffer(blob, np.uint8)
+    rt = np.zeros(L, np.uint8)
+    bf = np.zeros(L, np.float32)
+    xyz = np.zeros((na, 3), np.float32)
+    meta = np.zeros(1, abi.META_DTYPE)
+    title = np.zeros(max(tl, 1), np.uint8)
+    rc = fn(buf.ctypes.data, len(blob), int(use_alt), rt.ctypes.data, bf.ctypes.data, xyz.ctypes.data, meta.ctypes.data, title.ctypes.data)
+    if rc:
+        return rc
+    return Decoded(rt, bf, xyz, meta[0], bytes(title[:tl]))
+
+
+def oracle_decode(blob: bytes, use_alt: bool = False):
+    return _decode_with(oracle().fcz_oracle_decode_chain, blob, use_alt)
+
+
+def emu_decode(blob: bytes, use_alt: bool = False):
+    return _decode_with(emu().emu_decode_chain, blob, use_alt)
+
+
+def ref_decode(blob: bytes, use_alt: bool = False):
+    rc, L, na, tl = _peek(blob)
+    if rc:
+        return rc
+    buf = np.frombuffer(blob, np.uint8)
+    xyz = np.zeros((na + 1, 3), np.float32)
+    bf = np.zeros(L, np.float32)
+    rt = np.zeros(L, np.uint8)
+    n_atoms, n_res, has_oxt = C.c_int(), C.c_int(), C.c_int()
+    rc = ref().ref_decompress(buf.ctypes.data, len(blob), int(use_alt), xyz.ctypes.data, na + 1, C.byref(n_atoms), bf.ctypes.data,
+                              rt.ctypes.data, L, C.byref(n_res), C.byref(has_oxt))
+    if rc:
+        return rc
+    n = n_atoms.value - (1 if has_oxt.value else 0)
+    meta = np.zeros(1, abi.META_DTYPE)[0]
+    meta["has_oxt"] = has_oxt.value
+    if has_oxt.value:
+        meta["oxt"] = xyz[n]
+    return Decoded(rt, bf, xyz[:n].copy(), meta, b"")
+
+
+def masked(blob: bytes) -> bytes:
+    b = bytearray(blob)
+    for i in MASK:
+        if i < len(b):
+            b[i] = 0
+    return bytes(b)
+
+
+def rmsd(a: np.ndarray, b: np.ndarray) -> float:
+    d = a.astype(np.float64) - b.astype(np.float64)
+    return float(np.sqrt((d * d).sum(axis=1).mean()))
+
+
+def max_dev(a: np.ndarray, b: np.ndarray) -> float:
+    d = a.astype(np.float64) - b.astype(np.float64)
+    return float(np.sqrt((d * d).sum(axis=1)).max())
+
+
+def backbone_mask(res_type: np.ndarray) -> np.ndarray:
+    tb = tables()
+    m = []
+    for c in res_type:
+        n = int(tb.natoms[int(c)])
+        m += [True, True, True] + [False] * (n - 3)
+    return np.array(m, bool)
