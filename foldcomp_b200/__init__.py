@@ -1,0 +1,69 @@
+"""foldcomp_b200 -- B200-native FCZ encode/decode engine (drop-in for Foldcomp's per-chain codec).
+
+The Python surface mirrors the reference's CPython module for this path
+(/root/reference/foldcomp/foldcomp.cxx:702-709):
+
+    compress(name, pdb_content, *, anchor_residue_threshold=25) -> bytes     (foldcomp.cxx:295-328)
+    decompress(fcz_bytes) -> (name, pdb_str)                                 (foldcomp.cxx:222-239)
+
+Both go through the CUDA engine (include/fcz_engine.h); text parsing/formatting is host code
+(pdbio.py).  Batch entry points live in `engine.Engine`.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from . import abi
+from .abi import HostBlobBatch, HostChainBatch
+
+__all__ = ["compress", "decompress", "error", "Engine", "HostChainBatch", "HostBlobBatch"]
+
+
+class error(Exception):
+    """foldcomp.error (foldcomp.cxx:737-741)."""
+
+
+_engine = None
+
+
+def _get_engine():
+    global _engine
+    if _engine is None:
+        from .engine import Engine
+
+        _engine = Engine(0)
+    return _engine
+
+
+def __getattr__(name):
+    if name == "Engine":
+        from .engine import Engine
+
+        return Engine
+    raise AttributeError(name)
+
+
+def compress(name: str, pdb_content: str, *, anchor_residue_threshold: int = abi.DEFAULT_ANCHOR_THRESHOLD) -> bytes:
+    from .pdbio import PdbError, parse_pdb_chain
+
+    if not isinstance(anchor_residue_threshold, int):
+        raise TypeError("anchor_residue_threshold must be an integer")
+    try:
+        batch = parse_pdb_chain(pdb_content, name)
+    except PdbError as e:
+        raise error(str(e)) from None
+    eng = _get_engine()
+    eng.set_opts(anchor_threshold=anchor_residue_threshold)
+    out = eng.encode_host(batch)
+    if int(out.status[0]) != abi.FCZ_OK:
+        raise error("Error compressing")
+    return out.blob(0)
+
+
+def decompress(fcz: bytes):
+    from .pdbio import format_pdb
+
+    eng = _get_engine()
+    blobs = HostBlobBatch.from_blobs([bytes(fcz)])
+    out = eng.decode_host(blobs)
+    if int(out.status[0]) != abi.FCZ_OK:
+        raise error("Error decompressing.")
+    return out.title(0), format_pdb(out, 0)

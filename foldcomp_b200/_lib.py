@@ -24,6 +24,8 @@ SYMBOLS = [
     "fcz_decode_batch",
     "fcz_engine_sync",
     "fcz_engine_launch_count",
+    "fcz_engine_set_profiling",
+    "fcz_engine_get_profile",
     "fcz_strerror",
     "fcz_last_error",
     "fcz_type_natoms",
@@ -68,6 +70,10 @@ def load() -> C.CDLL:
     lib.fcz_engine_sync.argtypes = [C.c_void_p]
     lib.fcz_engine_launch_count.restype = C.c_uint64
     lib.fcz_engine_launch_count.argtypes = [C.c_void_p]
+    lib.fcz_engine_set_profiling.restype = C.c_int
+    lib.fcz_engine_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.fcz_engine_get_profile.restype = C.c_int
+    lib.fcz_engine_get_profile.argtypes = [C.c_void_p, P(abi.FczProfile)]
     lib.fcz_strerror.restype = C.c_char_p
     lib.fcz_strerror.argtypes = [C.c_int]
     lib.fcz_last_error.restype = C.c_char_p

@@ -93,6 +93,15 @@ class FczSizes(C.Structure):
     ]
 
 
+class FczProfile(C.Structure):
+    _fields_ = [
+        ("encode_kernel_ms", C.c_double),
+        ("decode_kernel_ms", C.c_double),
+        ("encode_launches", C.c_uint64),
+        ("decode_launches", C.c_uint64),
+    ]
+
+
 def _ptr(a: np.ndarray | None):
     if a is None:
         return None
@@ -210,6 +219,29 @@ def concat_chains(parts) -> HostChainBatch:
         xyz=cat(2, np.float32, (-1, 3)),
         titles=cat(3, np.uint8, (-1,)),
         meta=np.ascontiguousarray(np.concatenate([p[4] for p in parts])) if n else np.zeros(0, META_DTYPE),
+    )
+
+
+def concat_batches(batches) -> HostChainBatch:
+    """Concatenate whole batches (vectorised; offsets are re-based)."""
+    batches = list(batches)
+    if len(batches) == 1:
+        return batches[0]
+    if not batches:
+        return HostChainBatch.empty(0)
+
+    def offs(name, dt):
+        out, base = [np.zeros(1, dt)], 0
+        for b in batches:
+            o = getattr(b, name).astype(np.int64)
+            out.append((o[1:] + base).astype(dt))
+            base += int(o[-1])
+        return np.concatenate(out)
+
+    cat = lambda name: np.ascontiguousarray(np.concatenate([getattr(b, name) for b in batches]))
+    return HostChainBatch(
+        res_off=offs("res_off", np.uint32), atom_off=offs("atom_off", np.uint64), title_off=offs("title_off", np.uint32),
+        res_type=cat("res_type"), bfactor=cat("bfactor"), xyz=cat("xyz"), titles=cat("titles"), meta=cat("meta"),
     )
 
 

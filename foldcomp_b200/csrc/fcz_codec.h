@@ -25,6 +25,7 @@ namespace fcz {
 // Device-friendly copy of the residue tables (built once from fcz_tables.h).
 struct Tables {
     uint8_t natoms[FCZ_NUM_CODES];
+    uint8_t name1[FCZ_NUM_CODES];  // one-letter codes (header firstResidue / lastResidue)
     uint8_t alt[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
     uint16_t pred[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
     float blen[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
@@ -36,6 +37,7 @@ struct Tables {
 inline void build_tables(Tables* t) {
     for (int c = 0; c < FCZ_NUM_CODES; c++) {
         t->natoms[c] = FCZ_NATOMS[c];
+        t->name1[c] = (uint8_t)FCZ_NAME1[c];
         for (int k = 0; k < FCZ_MAX_ATOMS; k++) {
             t->alt[c][k] = FCZ_ALT[c][k];
             t->pred[c][k] = FCZ_PRED[c][k];
@@ -195,8 +197,8 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
         B[OFF_CHAIN] = ch.meta->chain;
         B[14] = 0; B[15] = 0;  // struct padding: uninitialised in the reference, zero here
         put_u32(B + OFF_NSC, y.n_sc);
-        B[OFF_FIRSTRES] = (uint8_t)FCZ_NAME1[ch.type[0]];      // src/foldcomp.cpp:467
-        B[OFF_LASTRES] = (uint8_t)FCZ_NAME1[ch.type[L - 1u]];  // src/foldcomp.cpp:468
+        B[OFF_FIRSTRES] = tb->name1[ch.type[0]];      // src/foldcomp.cpp:467
+        B[OFF_LASTRES] = tb->name1[ch.type[L - 1u]];  // src/foldcomp.cpp:468
         B[22] = 0; B[23] = 0;
         put_u32(B + OFF_LENTITLE, ch.title_len);
         for (int k = 0; k < 6; k++) {

@@ -1,0 +1,1109 @@
+// foldcomp_b200/csrc/fcz_engine.cu -- B200 (sm_100a) FCZ encode/decode engine behind include/fcz_engine.h.
+//
+// Execution model:
+//   * one CTA works on one chain at a time; the chain's coordinates (encode) or blob (decode) are
+//     pulled from HBM into shared memory with ONE bulk async copy (cp.async.bulk + mbarrier, the
+//     1-D TMA path) and every intermediate array (atom offsets, angles, sin/cos tables, the output
+//     blob / coordinates) lives in shared memory; results leave with coalesced 128-bit stores;
+//   * chains are binned by size into TIERS on the device (k_*_plan); each tier is one persistent
+//     launch (grid = SMs x CTAs/SM for that tier's shared-memory footprint) whose CTAs pull chains
+//     from the tier's list through an atomic ticket;
+//   * output offsets are exclusive scans over per-chain sizes (k_scan_*), so blobs and coordinates
+//     are tightly packed in chain order regardless of the order CTAs finish;
+//   * the per-chain algorithm itself is fcz_codec.h (shared with the CPU model used by the tests).
+// No tensor cores: there is no dense contraction on this path.
+// Compile with -fmad=false: the encode arithmetic must not be contracted into FMAs.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "fcz_codec.h"
+
+using namespace fcz;
+
+// ============================================================================================ tiers
+
+struct TierCfg {
+    uint32_t max_res;    // residues
+    uint32_t max_atoms;  // atoms
+    uint32_t max_blob;   // blob bytes
+    uint32_t max_seg;    // anchor segments (decode)
+    uint32_t staged;     // 1: chain data staged in smem; 0: large tier, data stays in global memory
+    uint32_t threads;
+    uint32_t smem;       // dynamic shared memory bytes
+};
+
+#define FCZ_NTIER 7
+static const uint32_t kTierRes[FCZ_NTIER] = {64, 128, 256, 384, 640, 1280, 3072};
+
+__host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// ---- shared memory carve-up (offsets are computed identically on host and device)
+struct EncSmem {
+    uint32_t o_tab, o_misc, o_red, o_type, o_aoff, o_ares, o_ang, o_x, o_b, total;
+};
+__host__ __device__ inline EncSmem enc_smem(const TierCfg& t) {
+    EncSmem s;
+    uint32_t o = 0;
+    s.o_tab = o;  o += align16((uint32_t)offsetof(Tables, blen));
+    s.o_misc = o; o += 256;  // mbarrier, ticket, warp sums
+    s.o_red = o;  o += align16(4u * FCZ_RED_FLOATS(32));
+    s.o_type = o; o += t.staged ? align16(t.max_res) : 0u;
+    s.o_aoff = o; o += align16(4u * (t.max_res + 1u));
+    s.o_ares = o; o += align16(2u * t.max_atoms);
+    s.o_ang = o;  o += align16(24u * t.max_res);
+    s.o_x = o;    o += t.staged ? align16(12u * t.max_atoms) + 32u : 0u;
+    s.o_b = o;    o += t.staged ? align16(t.max_blob) + 32u : 0u;
+    s.total = o;
+    return s;
+}
+struct DecSmem {
+    uint32_t o_tab, o_misc, o_aoff, o_tor, o_ang, o_seg, o_blob, o_out, total;
+};
+__host__ __device__ inline DecSmem dec_smem(const TierCfg& t) {
+    DecSmem s;
+    uint32_t o = 0;
+    s.o_tab = o;  o += align16((uint32_t)sizeof(Tables));
+    s.o_misc = o; o += 256;
+    s.o_aoff = o; o += align16(4u * (t.max_res + 1u));
+    s.o_tor = o;  o += align16(24u * t.max_res);
+    s.o_ang = o;  o += align16(24u * t.max_res);
+    s.o_seg = o;  o += align16(4u * FCZ_SEG_FLOATS * t.max_seg);
+    s.o_blob = o; o += t.staged ? align16(t.max_blob) + 32u : 0u;
+    s.o_out = o;  o += t.staged ? align16(12u * t.max_atoms) + 32u : 0u;
+    s.total = o;
+    return s;
+}
+
+static void make_tiers(TierCfg* enc, TierCfg* dec) {
+    for (int i = 0; i < FCZ_NTIER; i++) {
+        TierCfg t;
+        t.max_res = kTierRes[i];
+        t.staged = (i < FCZ_NTIER - 1) ? 1u : 0u;
+        t.max_atoms = t.staged ? 9u * t.max_res : 65535u * 2u / 3u;  // large tier: bounded by smem of ares only
+        t.max_blob = 17u * t.max_res + 1280u;
+        t.max_seg = t.max_res / 8u + 8u;
+        if (t.max_seg > 254u) t.max_seg = 254u;
+        t.threads = (t.max_res <= 128u) ? 128u : 256u;
+        if (!t.staged) {
+            t.max_atoms = 10u * t.max_res;
+            t.max_blob = 0xFFFFFFFFu;
+            t.max_seg = 254u;
+            t.threads = 512u;
+        }
+        TierCfg e = t, d = t;
+        e.smem = enc_smem(e).total;
+        d.smem = dec_smem(d).total;
+        enc[i] = e;
+        dec[i] = d;
+    }
+}
+
+// ======================================================================================= device ctx
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 22)) __trap();  // a lost bulk copy must fail loudly, never hang the GPU
+    }
+}
+// 1-D bulk async copy global -> shared (TMA engine), completion counted on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct DevCtx {
+    int tid, nthr, lane, warp, nwarps;
+    uint32_t* wsum;   // [32] warp sums for the block scan
+    uint64_t* bar;    // staging mbarrier
+    uint32_t parity;  // its current phase
+    bool staged;      // a bulk copy is in flight for this chain
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void stage_wait() {
+        if (staged) mbar_wait(bar, parity);
+    }
+    __device__ __forceinline__ uint32_t excl_scan(uint32_t v) {
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t yv = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += yv;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < warp; w++) base += wsum[w];
+        __syncthreads();
+        return base + x - v;
+    }
+    __device__ __forceinline__ float wmin(float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    __device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+};
+
+// Stage `bytes` bytes starting at global address `src` into shared memory so that the copy has
+// the same 16-byte phase as the source: returns the shared address of byte 0.  The 16-byte
+// aligned interior goes through ONE bulk async copy (issued by thread 0, completion on cx.bar);
+// the <16-byte head and tail are fetched with plain loads.  buf must be 16-byte aligned and hold
+// bytes + 32.
+__device__ __forceinline__ uint8_t* stage_in(DevCtx& cx, uint8_t* buf, const uint8_t* src, uint32_t bytes) {
+    const uint32_t mis = (uint32_t)((uintptr_t)src & 15u);
+    uint8_t* dst0 = buf + mis;
+    const uint32_t head = (16u - mis) & 15u;
+    uint32_t body = 0;
+    if (bytes > head) body = (bytes - head) & ~15u;
+    if (cx.tid == 0) {
+        // order this CTA's earlier generic-proxy accesses to the buffer before the async-proxy write
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (body) {
+            mbar_expect_tx(cx.bar, body);
+            bulk_g2s(dst0 + head, src + head, body, cx.bar);
+        } else {
+            mbar_arrive(cx.bar);
+        }
+    }
+    const uint32_t hb = head < bytes ? head : bytes;
+    for (uint32_t i = cx.tid; i < hb; i += cx.nthr) dst0[i] = src[i];
+    for (uint32_t i = hb + body + cx.tid; i < bytes; i += cx.nthr) dst0[i] = src[i];
+    cx.staged = true;
+    return dst0;
+}
+
+// Copy `bytes` bytes from shared (same 16-byte phase as dst, see stage buffers) to global with
+// 128-bit stores for the aligned interior.
+__device__ __forceinline__ void copy_out(const DevCtx& cx, uint8_t* dst, const uint8_t* src, uint32_t bytes) {
+    const uint32_t mis = (uint32_t)((uintptr_t)dst & 15u);
+    const uint32_t head = (16u - mis) & 15u;
+    const uint32_t hb = head < bytes ? head : bytes;
+    uint32_t body = 0;
+    if (bytes > head) body = (bytes - head) & ~15u;
+    for (uint32_t i = cx.tid; i < hb; i += cx.nthr) dst[i] = src[i];
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    for (uint32_t i = cx.tid; i < (body >> 4); i += cx.nthr) d4[i] = s4[i];
+    for (uint32_t i = hb + body + cx.tid; i < bytes; i += cx.nthr) dst[i] = src[i];
+}
+
+// ========================================================================================== encode
+
+struct EncArgs {
+    const uint32_t* res_off;
+    const uint64_t* atom_off;
+    const uint32_t* title_off;
+    const uint8_t* res_type;
+    const float* bfactor;
+    const float* xyz;
+    const char* titles;
+    const fcz_chain_meta* meta;
+    const uint64_t* blob_off;
+    uint8_t* bytes;
+    const uint32_t* list;   // chains of this tier
+    const uint32_t* count;  // their number
+    uint32_t* ticket;
+    const Tables* tables;
+    int32_t b;
+    TierCfg cfg;
+};
+
+// Plan: one warp per chain.  Validates the chain, computes its blob size and tier.
+struct PlanOut {
+    uint32_t* v0;          // per-chain value 0 (encode: blob bytes; decode: residues)
+    uint32_t* v1;          // decode: atoms
+    uint32_t* v2;          // decode: title bytes
+    int32_t* status;       // per-chain status (engine copy)
+    uint32_t* tier_count;  // [FCZ_NTIER]
+    uint32_t* tier_list;   // [FCZ_NTIER][n]
+};
+
+struct TierTable {
+    TierCfg t[FCZ_NTIER];
+};
+
+__device__ __forceinline__ int pick_tier(const TierTable& tt, uint32_t L, uint32_t A, uint32_t blob, uint32_t nseg) {
+    for (int i = 0; i < FCZ_NTIER; i++) {
+        const TierCfg& t = tt.t[i];
+        if (L <= t.max_res && A <= t.max_atoms && blob <= t.max_blob && nseg <= t.max_seg) return i;
+    }
+    return -1;
+}
+
+__global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* atom_off, const uint32_t* title_off,
+                           const uint8_t* res_type, int32_t b, const Tables* tb, TierTable tt, PlanOut po) {
+    const uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= n) return;
+    const uint32_t r0 = res_off[c], L = res_off[c + 1] - r0;
+    const uint64_t A = atom_off[c + 1] - atom_off[c];
+    const uint32_t T = title_off[c + 1] - title_off[c];
+    int status = FCZ_OK;
+    uint32_t sum = 0, bad = 0;
+    for (uint32_t r = lane; r < L; r += 32) {
+        uint32_t code = res_type[r0 + r];
+        uint32_t na = code < FCZ_NUM_CODES ? tb->natoms[code] : 0u;
+        bad |= (na == 0u);
+        sum += na;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    uint32_t size = 0;
+    int tier = -1;
+    if (L < 2u || L > 65535u || b < 1) status = FCZ_E_LIMIT;
+    else if (bad) status = FCZ_E_RESIDUE;
+    else if ((uint64_t)sum != A) status = FCZ_E_ARG;
+    else {
+        const int na = anchor_count(L, b);
+        if (na > 255) status = FCZ_E_LIMIT;
+        else {
+            Layout y = make_layout(L, sum - 3u * L, T, (uint32_t)na);
+            size = y.size;
+            tier = pick_tier(tt, L, sum, size, (uint32_t)na - 1u);
+            if (tier < 0) { status = FCZ_E_LIMIT; size = 0; }
+        }
+    }
+    if (lane == 0) {
+        po.v0[c] = size;
+        po.status[c] = status;
+        if (tier >= 0) {
+            uint32_t pos = atomicAdd(&po.tier_count[tier], 1u);
+            po.tier_list[(size_t)tier * n + pos] = c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512) k_encode(EncArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const EncSmem so = enc_smem(a.cfg);
+    Tables* tb = reinterpret_cast<Tables*>(smem + so.o_tab);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + so.o_misc);
+    uint32_t* s_ticket = reinterpret_cast<uint32_t*>(smem + so.o_misc + 8);
+    DevCtx cx;
+    cx.tid = threadIdx.x; cx.nthr = blockDim.x; cx.lane = threadIdx.x & 31; cx.warp = threadIdx.x >> 5;
+    cx.nwarps = blockDim.x >> 5;
+    cx.wsum = reinterpret_cast<uint32_t*>(smem + so.o_misc + 64);
+    cx.bar = bar; cx.parity = 0; cx.staged = false;
+    // tables prefix (natoms, alt, pred) -> shared
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tb);
+        for (uint32_t i = cx.tid; i < (uint32_t)offsetof(Tables, blen) / 4u; i += cx.nthr) dst[i] = src[i];
+    }
+    if (cx.tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    const uint32_t count = *a.count;
+    for (;;) {
+        if (cx.tid == 0) *s_ticket = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const uint32_t t = *s_ticket;
+        if (t >= count) break;
+        const uint32_t c = a.list[t];
+        const uint32_t r0 = a.res_off[c], L = a.res_off[c + 1] - r0;
+        const uint64_t a0 = a.atom_off[c];
+        const uint32_t A = (uint32_t)(a.atom_off[c + 1] - a0);
+        const uint32_t t0 = a.title_off[c], T = a.title_off[c + 1] - t0;
+        const uint64_t b0 = a.blob_off[c];
+        const uint32_t size = (uint32_t)(a.blob_off[c + 1] - b0);
+
+        EncChain ch;
+        ch.L = L; ch.A = A; ch.title_len = T; ch.b = a.b;
+        ch.bfac = a.bfactor + r0;
+        ch.title = a.titles + t0;
+        ch.meta = a.meta + c;
+        ch.aoff = reinterpret_cast<uint32_t*>(smem + so.o_aoff);
+        ch.ares = reinterpret_cast<uint16_t*>(smem + so.o_ares);
+        ch.ang = reinterpret_cast<float*>(smem + so.o_ang);
+        ch.red = reinterpret_cast<float*>(smem + so.o_red);
+        uint8_t* gdst = a.bytes + b0;
+        uint8_t* sB = nullptr;
+        if (a.cfg.staged) {
+            const uint8_t* gx = reinterpret_cast<const uint8_t*>(a.xyz + 3u * a0);
+            ch.X = reinterpret_cast<const float*>(stage_in(cx, smem + so.o_x, gx, 12u * A));
+            uint8_t* st = smem + so.o_type;
+            for (uint32_t i = cx.tid; i < L; i += cx.nthr) st[i] = a.res_type[r0 + i];
+            ch.type = st;
+            sB = smem + so.o_b + ((uintptr_t)gdst & 15u);
+            ch.B = sB;
+            __syncthreads();  // staged types visible before phase 1
+        } else {
+            ch.X = a.xyz + 3u * a0;
+            ch.type = a.res_type + r0;
+            ch.B = gdst;
+            cx.staged = false;
+        }
+        encode_chain(cx, tb, ch);
+        if (a.cfg.staged) {
+            copy_out(cx, gdst, sB, size);
+            cx.parity ^= 1u;
+            cx.staged = false;
+        }
+        __syncthreads();  // shared buffers free for the next chain
+    }
+}
+
+// ========================================================================================== decode
+
+struct DecArgs {
+    const uint64_t* blob_off;
+    const uint8_t* bytes;
+    const uint32_t* res_off;
+    const uint64_t* atom_off;
+    const uint32_t* title_off;
+    uint8_t* res_type;
+    float* bfactor;
+    float* xyz;
+    char* titles;
+    fcz_chain_meta* meta;
+    const uint32_t* list;
+    const uint32_t* count;
+    uint32_t* ticket;
+    const Tables* tables;
+    int32_t use_alt;
+    TierCfg cfg;
+};
+
+// Plan: one warp per blob.  Validates the header (Foldcomp::read, src/foldcomp.cpp:904-924 and the
+// count checks of checkValidity, 1492-1561), sums the decoded atom count, picks the tier.
+__global__ void k_dec_plan(uint32_t n, const uint64_t* blob_off, const uint8_t* bytes, const Tables* tb, TierTable tt,
+                           PlanOut po) {
+    const uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= n) return;
+    const uint8_t* blob = bytes + blob_off[c];
+    const uint64_t len = blob_off[c + 1] - blob_off[c];
+    int status = FCZ_OK;
+    uint32_t L = 0, A = 0, T = 0;
+    int tier = -1;
+    if (len < HDR_BYTES || blob[0] != 'F' || blob[1] != 'C' || blob[2] != 'M' || blob[3] != 'P') {
+        status = FCZ_E_MAGIC;
+    } else {
+        L = get_u16(blob + OFF_NRES);
+        T = get_u32(blob + OFF_LENTITLE);
+        const uint32_t nsc = get_u32(blob + OFF_NSC), na = blob[OFF_NANCHOR];
+        Layout y = make_layout(L, nsc, T, na);
+        if (L < 2u || na < 2u || (uint64_t)T > len || (uint64_t)nsc > len || (uint64_t)y.size > len) {
+            status = FCZ_E_TRUNCATED;
+        } else {
+            uint32_t sum = 0, bad = 0;
+            for (uint32_t r = lane; r < L; r += 32) {
+                uint32_t nat = tb->natoms[blob[y.o_rec + 8u * r] >> 3];
+                bad |= (nat == 0u);
+                sum += nat;
+            }
+            // anchors: 0 = first, non-decreasing, last = L-1
+            for (uint32_t i = lane; i < na; i += 32) {
+                uint32_t ai = get_u32(blob + y.o_aidx + 4u * i);
+                uint32_t prev = i ? get_u32(blob + y.o_aidx + 4u * (i - 1u)) : 0u;
+                if (ai < prev || ai >= L || (i == 0u && ai != 0u) || (i == na - 1u && ai != L - 1u)) bad |= 2u;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+            }
+            if (bad & 1u) status = FCZ_E_RESIDUE;
+            else if ((bad & 2u) || sum - 3u * L != nsc) status = FCZ_E_TRUNCATED;
+            else {
+                A = sum;
+                tier = pick_tier(tt, L, A, y.size, na - 1u);
+                if (tier < 0) status = FCZ_E_LIMIT;
+            }
+        }
+    }
+    if (status != FCZ_OK) { L = 0; A = 0; T = 0; }
+    if (lane == 0) {
+        po.v0[c] = L; po.v1[c] = A; po.v2[c] = T;
+        po.status[c] = status;
+        if (tier >= 0) {
+            uint32_t pos = atomicAdd(&po.tier_count[tier], 1u);
+            po.tier_list[(size_t)tier * n + pos] = c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512) k_decode(DecArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const DecSmem so = dec_smem(a.cfg);
+    Tables* tb = reinterpret_cast<Tables*>(smem + so.o_tab);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + so.o_misc);
+    uint32_t* s_ticket = reinterpret_cast<uint32_t*>(smem + so.o_misc + 8);
+    DevCtx cx;
+    cx.tid = threadIdx.x; cx.nthr = blockDim.x; cx.lane = threadIdx.x & 31; cx.warp = threadIdx.x >> 5;
+    cx.nwarps = blockDim.x >> 5;
+    cx.wsum = reinterpret_cast<uint32_t*>(smem + so.o_misc + 64);
+    cx.bar = bar; cx.parity = 0; cx.staged = false;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tb);
+        for (uint32_t i = cx.tid; i < (uint32_t)sizeof(Tables) / 4u; i += cx.nthr) dst[i] = src[i];
+    }
+    if (cx.tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    const uint32_t count = *a.count;
+    for (;;) {
+        if (cx.tid == 0) *s_ticket = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const uint32_t t = *s_ticket;
+        if (t >= count) break;
+        const uint32_t c = a.list[t];
+        const uint64_t b0 = a.blob_off[c];
+        const uint32_t blen = (uint32_t)(a.blob_off[c + 1] - b0);
+        const uint32_t r0 = a.res_off[c];
+        const uint64_t a0 = a.atom_off[c];
+        const uint32_t A = (uint32_t)(a.atom_off[c + 1] - a0);
+        const uint8_t* gblob = a.bytes + b0;
+
+        DecChain ch;
+        ch.use_alt = a.use_alt;
+        ch.out_type = a.res_type + r0;
+        ch.out_bfac = a.bfactor + r0;
+        ch.out_meta = a.meta + c;
+        ch.out_title = a.titles ? a.titles + a.title_off[c] : nullptr;
+        ch.aoff = reinterpret_cast<uint32_t*>(smem + so.o_aoff);
+        ch.tor = reinterpret_cast<cs*>(smem + so.o_tor);
+        ch.ang = reinterpret_cast<cs*>(smem + so.o_ang);
+        ch.seg = reinterpret_cast<float*>(smem + so.o_seg);
+        float* gout = a.xyz + 3u * a0;
+        uint8_t* sout = nullptr;
+        if (a.cfg.staged) {
+            ch.blob = stage_in(cx, smem + so.o_blob, gblob, blen);
+            sout = smem + so.o_out + ((uintptr_t)gout & 15u);
+            ch.out_xyz = reinterpret_cast<float*>(sout);
+            cx.stage_wait();
+            __syncthreads();
+        } else {
+            ch.blob = gblob;
+            ch.out_xyz = gout;
+        }
+        const uint8_t* hb = ch.blob;
+        ch.y = make_layout(get_u16(hb + OFF_NRES), get_u32(hb + OFF_NSC), get_u32(hb + OFF_LENTITLE), hb[OFF_NANCHOR]);
+        decode_chain(cx, tb, ch);
+        if (a.cfg.staged) {
+            copy_out(cx, reinterpret_cast<uint8_t*>(gout), sout, 12u * A);
+            cx.parity ^= 1u;
+            cx.staged = false;
+        }
+        __syncthreads();
+    }
+}
+
+// ============================================================================================ scans
+// Exclusive scans of up to three per-chain u32 arrays into offsets (u32/u64), tile = 2048 chains.
+
+#define SCAN_TILE 2048
+#define SCAN_THREADS 256
+#define SCAN_ITEMS (SCAN_TILE / SCAN_THREADS)
+
+struct ScanArgs {
+    uint32_t n;
+    int narr;
+    const uint32_t* in[3];
+    void* out[3];       // [n+1]
+    int out64[3];       // 1: uint64 output, 0: uint32
+    uint64_t* partial;  // [ntiles*3]
+    uint64_t* totals;   // [3]
+};
+
+__device__ __forceinline__ uint64_t block_sum64(uint64_t v, uint64_t* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint64_t s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sh[w];
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(ScanArgs a) {
+    __shared__ uint64_t sh[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    for (int j = 0; j < a.narr; j++) {
+        uint64_t s = 0;
+        for (int i = 0; i < SCAN_ITEMS; i++)
+            if (base + i < a.n) s += a.in[j][base + i];
+        s = block_sum64(s, sh);
+        if (threadIdx.x == 0) a.partial[blockIdx.x * 3 + j] = s;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(ScanArgs a) {
+    __shared__ uint64_t sh[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = 0; j < a.narr; j++) {
+        uint64_t pre = 0;
+        for (uint32_t t = threadIdx.x; t < blockIdx.x; t += blockDim.x) pre += a.partial[t * 3 + j];
+        pre = block_sum64(pre, sh);
+        uint32_t v[SCAN_ITEMS];
+        uint64_t s = 0;
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            v[i] = (base + i < a.n) ? a.in[j][base + i] : 0u;
+            s += v[i];
+        }
+        uint64_t x = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t yv = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += yv;
+        }
+        if (lane == 31) sh[warp] = x;
+        __syncthreads();
+        uint64_t wb = 0;
+        for (int w = 0; w < warp; w++) wb += sh[w];
+        uint64_t tile_total = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) tile_total += sh[w];
+        __syncthreads();
+        uint64_t off = pre + wb + x - s;
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            if (base + i < a.n) {
+                if (a.out64[j]) ((uint64_t*)a.out[j])[base + i] = off;
+                else ((uint32_t*)a.out[j])[base + i] = (uint32_t)off;
+            }
+            off += v[i];
+        }
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+            uint64_t tot = pre + tile_total;
+            if (a.out64[j]) ((uint64_t*)a.out[j])[a.n] = tot;
+            else ((uint32_t*)a.out[j])[a.n] = (uint32_t)tot;
+            a.totals[j] = tot;
+        }
+    }
+}
+
+// ============================================================================================ engine
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct fcz_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    fcz_opts opts;
+    int num_sms = 148;
+    TierCfg enc_tier[FCZ_NTIER], dec_tier[FCZ_NTIER];
+    int enc_occ[FCZ_NTIER], dec_occ[FCZ_NTIER];
+    Tables* d_tables = nullptr;
+    // plan scratch
+    DevBuf v0, v1, v2, status, tier_list, partial;
+    uint32_t* d_counters = nullptr;  // [FCZ_NTIER] counts, [FCZ_NTIER] tickets
+    uint64_t* d_totals = nullptr;    // [3]
+    uint32_t* h_counters = nullptr;  // pinned mirror
+    uint64_t* h_totals = nullptr;
+    // staging for host-memory batches
+    DevBuf d_res_off, d_atom_off, d_title_off, d_res_type, d_bfactor, d_xyz, d_titles, d_meta, d_blob_off, d_bytes, d_status;
+    uint64_t launches = 0;
+    // optional per-kernel event timing
+    bool profiling = false;
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;            // recorded since the last get_profile
+    std::vector<cudaEvent_t> free_events;
+    char err[512];
+};
+
+static cudaEvent_t take_event(fcz_engine* e) {
+    cudaEvent_t ev = nullptr;
+    if (!e->free_events.empty()) { ev = e->free_events.back(); e->free_events.pop_back(); }
+    else cudaEventCreate(&ev);
+    return ev;
+}
+struct ProfSpan {  // RAII: events around one kernel launch when profiling is on
+    fcz_engine* e; cudaEvent_t a = nullptr, b = nullptr; int kind;
+    ProfSpan(fcz_engine* e_, int kind_) : e(e_), kind(kind_) {
+        if (e->profiling) { a = take_event(e); b = take_event(e); cudaEventRecord(a, e->stream); }
+    }
+    ~ProfSpan() {
+        if (a) { cudaEventRecord(b, e->stream); e->spans.push_back({a, b, kind}); }
+    }
+};
+
+static int fail(fcz_engine* e, int code, const char* fmt, ...) {
+    if (e) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(e->err, sizeof e->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t _e = (call);                                                                          \
+        if (_e != cudaSuccess) return fail(e, FCZ_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static int ensure(fcz_engine* e, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return FCZ_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t cap = bytes + bytes / 8 + 256;
+    CK(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return FCZ_OK;
+}
+
+extern "C" {
+
+fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
+    fcz_engine* e = new (std::nothrow) fcz_engine();
+    if (!e) return nullptr;
+    e->err[0] = 0;
+    e->device = device;
+    e->opts.anchor_threshold = 25;
+    e->opts.use_alt_atom_order = 0;
+    e->opts.stream = nullptr;
+    if (opts) e->opts = *opts;
+    if (e->opts.anchor_threshold < 1) e->opts.anchor_threshold = 25;
+    if (cudaSetDevice(device) != cudaSuccess) { delete e; return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; return nullptr; }
+    e->num_sms = prop.multiProcessorCount;
+    if (e->opts.stream) {
+        e->stream = (cudaStream_t)e->opts.stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return nullptr; }
+        e->own_stream = true;
+    }
+    make_tiers(e->enc_tier, e->dec_tier);
+    bool ok = true;
+    for (int i = 0; i < FCZ_NTIER && ok; i++) {
+        ok &= cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        int occ = 0;
+        ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, (int)e->enc_tier[i].threads, e->enc_tier[i].smem) == cudaSuccess;
+        e->enc_occ[i] = occ > 0 ? occ : 1;
+        ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decode, (int)e->dec_tier[i].threads, e->dec_tier[i].smem) == cudaSuccess;
+        e->dec_occ[i] = occ > 0 ? occ : 1;
+    }
+    Tables h;
+    build_tables(&h);
+    ok &= cudaMalloc(&e->d_tables, sizeof(Tables)) == cudaSuccess;
+    ok &= cudaMalloc(&e->d_counters, sizeof(uint32_t) * 2 * FCZ_NTIER) == cudaSuccess;
+    ok &= cudaMalloc(&e->d_totals, sizeof(uint64_t) * 3) == cudaSuccess;
+    ok &= cudaMallocHost(&e->h_counters, sizeof(uint32_t) * 2 * FCZ_NTIER) == cudaSuccess;
+    ok &= cudaMallocHost(&e->h_totals, sizeof(uint64_t) * 3) == cudaSuccess;
+    if (ok) ok &= cudaMemcpy(e->d_tables, &h, sizeof(Tables), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        fprintf(stderr, "fcz_engine_create: %s\n", cudaGetErrorString(cudaGetLastError()));
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+
+void fcz_engine_destroy(fcz_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
+                      &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
+                      &e->d_blob_off, &e->d_bytes, &e->d_status};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (e->d_tables) cudaFree(e->d_tables);
+    if (e->d_counters) cudaFree(e->d_counters);
+    if (e->d_totals) cudaFree(e->d_totals);
+    if (e->h_counters) cudaFreeHost(e->h_counters);
+    if (e->h_totals) cudaFreeHost(e->h_totals);
+    for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto ev : e->free_events) cudaEventDestroy(ev);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int fcz_engine_set_opts(fcz_engine* e, const fcz_opts* opts) {
+    if (!e || !opts) return FCZ_E_ARG;
+    if (opts->anchor_threshold < 1) return fail(e, FCZ_E_ARG, "anchor_threshold must be >= 1");
+    e->opts.anchor_threshold = opts->anchor_threshold;
+    e->opts.use_alt_atom_order = opts->use_alt_atom_order;
+    if (opts->stream != e->opts.stream) {
+        if (e->own_stream) {
+            cudaStreamSynchronize(e->stream);
+            cudaStreamDestroy(e->stream);
+            e->own_stream = false;
+        }
+        if (opts->stream) {
+            e->stream = (cudaStream_t)opts->stream;
+        } else {
+            if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(e, FCZ_E_CUDA, "stream");
+            e->own_stream = true;
+        }
+        e->opts.stream = opts->stream;
+    }
+    return FCZ_OK;
+}
+
+uint64_t fcz_encode_bound(uint64_t n_chains, uint64_t n_res, uint64_t n_atoms, uint64_t n_title_bytes, int32_t b) {
+    if (b < 1) b = 1;
+    return 97ull * n_chains + 40ull * (n_res / (uint64_t)b + 2ull * n_chains) + n_title_bytes + 6ull * n_res + n_atoms;
+}
+
+int fcz_engine_sync(fcz_engine* e) {
+    if (!e) return FCZ_E_ARG;
+    CK(cudaStreamSynchronize(e->stream));
+    return FCZ_OK;
+}
+
+uint64_t fcz_engine_launch_count(const fcz_engine* e) { return e ? e->launches : 0; }
+
+int fcz_engine_set_profiling(fcz_engine* e, int enabled) {
+    if (!e) return FCZ_E_ARG;
+    e->profiling = enabled != 0;
+    return FCZ_OK;
+}
+
+int fcz_engine_get_profile(fcz_engine* e, fcz_profile* out) {
+    if (!e || !out) return FCZ_E_ARG;
+    CK(cudaStreamSynchronize(e->stream));
+    memset(out, 0, sizeof *out);
+    for (auto& s : e->spans) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s.a, s.b));
+        if (s.kind == 0) { out->encode_kernel_ms += ms; out->encode_launches++; }
+        else { out->decode_kernel_ms += ms; out->decode_launches++; }
+        e->free_events.push_back(s.a);
+        e->free_events.push_back(s.b);
+    }
+    e->spans.clear();
+    return FCZ_OK;
+}
+
+const char* fcz_strerror(int code) {
+    switch (code) {
+        case FCZ_OK: return "ok";
+        case FCZ_E_MAGIC: return "not an FCZ blob (bad magic)";
+        case FCZ_E_TRUNCATED: return "blob truncated or inconsistent with its header";
+        case FCZ_E_RESIDUE: return "residue code outside the 20 amino acids + UNK";
+        case FCZ_E_LIMIT: return "chain exceeds a format or engine limit";
+        case FCZ_E_CAPACITY: return "output buffer too small";
+        case FCZ_E_CUDA: return "CUDA error";
+        case FCZ_E_ARG: return "bad argument";
+        default: return "unknown error";
+    }
+}
+const char* fcz_last_error(const fcz_engine* e) { return e ? e->err : "no engine"; }
+
+int fcz_type_natoms(int c) { return (c >= 0 && c < FCZ_NUM_CODES) ? FCZ_NATOMS[c] : 0; }
+const char* fcz_type_name3(int c) { return (c >= 0 && c < FCZ_NUM_CODES) ? FCZ_NAME3[c] : ""; }
+const char* fcz_type_atom_name(int c, int k) {
+    return (c >= 0 && c < FCZ_NUM_CODES && k >= 0 && k < FCZ_MAX_ATOMS) ? FCZ_ATOM_NAME[c][k] : "";
+}
+int fcz_type_alt_slot(int c, int k) { return (c >= 0 && c < FCZ_NUM_CODES && k >= 0 && k < FCZ_MAX_ATOMS) ? FCZ_ALT[c][k] : 0; }
+int fcz_type_pred(int c, int k, int w) {
+    if (c < 0 || c >= FCZ_NUM_CODES || k < 0 || k >= FCZ_MAX_ATOMS || w < 0 || w > 2) return 0;
+    return (FCZ_PRED[c][k] >> (4 * w)) & 15;
+}
+float fcz_type_bond_length(int c, int k) { return (c >= 0 && c < FCZ_NUM_CODES && k >= 0 && k < FCZ_MAX_ATOMS) ? FCZ_BLEN[c][k] : 0.f; }
+float fcz_type_bond_angle(int c, int k) { return (c >= 0 && c < FCZ_NUM_CODES && k >= 0 && k < FCZ_MAX_ATOMS) ? FCZ_BANG[c][k] : 0.f; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ plan helpers
+
+static int plan_buffers(fcz_engine* e, uint32_t n) {
+    int rc;
+    if ((rc = ensure(e, e->v0, 4ull * n + 4))) return rc;
+    if ((rc = ensure(e, e->v1, 4ull * n + 4))) return rc;
+    if ((rc = ensure(e, e->v2, 4ull * n + 4))) return rc;
+    if ((rc = ensure(e, e->status, 4ull * n + 4))) return rc;
+    if ((rc = ensure(e, e->tier_list, 4ull * n * FCZ_NTIER + 4))) return rc;
+    uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if ((rc = ensure(e, e->partial, 24ull * (ntiles + 1)))) return rc;
+    CK(cudaMemsetAsync(e->d_counters, 0, sizeof(uint32_t) * 2 * FCZ_NTIER, e->stream));
+    return FCZ_OK;
+}
+
+static int run_scan(fcz_engine* e, ScanArgs& sa) {
+    uint32_t ntiles = (sa.n + SCAN_TILE - 1) / SCAN_TILE;
+    if (ntiles == 0) ntiles = 1;
+    sa.partial = (uint64_t*)e->partial.p;
+    sa.totals = e->d_totals;
+    k_scan_partials<<<ntiles, SCAN_THREADS, 0, e->stream>>>(sa);
+    k_scan_final<<<ntiles, SCAN_THREADS, 0, e->stream>>>(sa);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    return FCZ_OK;
+}
+
+// counters + totals -> pinned host, then wait for them
+static int fetch_plan(fcz_engine* e) {
+    CK(cudaMemcpyAsync(e->h_counters, e->d_counters, sizeof(uint32_t) * FCZ_NTIER, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_totals, e->d_totals, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return FCZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------- encode
+
+static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch* out, uint64_t* total_bytes) {
+    const uint32_t n = in->n_chains;
+    int rc;
+    if ((rc = plan_buffers(e, n))) return rc;
+    TierTable tt;
+    for (int i = 0; i < FCZ_NTIER; i++) tt.t[i] = e->enc_tier[i];
+    PlanOut po;
+    po.v0 = (uint32_t*)e->v0.p; po.v1 = nullptr; po.v2 = nullptr;
+    po.status = out->status ? out->status : (int32_t*)e->status.p;
+    po.tier_count = e->d_counters;
+    po.tier_list = (uint32_t*)e->tier_list.p;
+    if (n) {
+        k_enc_plan<<<(n + 7) / 8, 256, 0, e->stream>>>(n, in->res_off, in->atom_off, in->title_off, in->res_type,
+                                                       e->opts.anchor_threshold, e->d_tables, tt, po);
+        e->launches++;
+    }
+    ScanArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.n = n; sa.narr = 1;
+    sa.in[0] = po.v0; sa.out[0] = out->blob_off; sa.out64[0] = 1;
+    if ((rc = run_scan(e, sa))) return rc;
+    if ((rc = fetch_plan(e))) return rc;
+    *total_bytes = e->h_totals[0];
+    if (*total_bytes > out->bytes_cap) return fail(e, FCZ_E_CAPACITY, "encode needs %llu bytes, capacity %llu",
+                                                   (unsigned long long)*total_bytes, (unsigned long long)out->bytes_cap);
+    for (int i = 0; i < FCZ_NTIER; i++) {
+        const uint32_t cnt = e->h_counters[i];
+        if (!cnt) continue;
+        EncArgs a;
+        a.res_off = in->res_off; a.atom_off = in->atom_off; a.title_off = in->title_off;
+        a.res_type = in->res_type; a.bfactor = in->bfactor; a.xyz = in->xyz; a.titles = in->titles; a.meta = in->meta;
+        a.blob_off = out->blob_off; a.bytes = out->bytes;
+        a.list = (uint32_t*)e->tier_list.p + (size_t)i * n;
+        a.count = e->d_counters + i;
+        a.ticket = e->d_counters + FCZ_NTIER + i;
+        a.tables = e->d_tables;
+        a.b = e->opts.anchor_threshold;
+        a.cfg = e->enc_tier[i];
+        uint32_t grid = (uint32_t)(e->num_sms * e->enc_occ[i]);
+        if (grid > cnt) grid = cnt;
+        {
+            ProfSpan ps(e, 0);
+            k_encode<<<grid, a.cfg.threads, a.cfg.smem, e->stream>>>(a);
+        }
+        e->launches++;
+    }
+    CK(cudaGetLastError());
+    return FCZ_OK;
+}
+
+#define H2D(buf, src, bytes)                                                                   \
+    do {                                                                                       \
+        if ((rc = ensure(e, buf, (bytes) + 16))) return rc;                                    \
+        if (bytes) CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, e->stream)); \
+    } while (0)
+
+extern "C" int fcz_encode_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch* out) {
+    if (!e || !in || !out) return FCZ_E_ARG;
+    if (in->mem != out->mem) return fail(e, FCZ_E_ARG, "input and output batches must live in the same memory space");
+    CK(cudaSetDevice(e->device));
+    out->n_chains = in->n_chains;
+    const uint32_t n = in->n_chains;
+    uint64_t total = 0;
+    if (in->mem == FCZ_MEM_DEVICE) return encode_device(e, in, out, &total);
+    // host batch: copy in, run, copy out
+    int rc;
+    const uint64_t n_res = in->res_off[n], n_atoms = in->atom_off[n], n_title = in->title_off[n];
+    H2D(e->d_res_off, in->res_off, 4ull * (n + 1));
+    H2D(e->d_atom_off, in->atom_off, 8ull * (n + 1));
+    H2D(e->d_title_off, in->title_off, 4ull * (n + 1));
+    H2D(e->d_res_type, in->res_type, n_res);
+    H2D(e->d_bfactor, in->bfactor, 4ull * n_res);
+    H2D(e->d_xyz, in->xyz, 12ull * n_atoms);
+    H2D(e->d_titles, in->titles, n_title);
+    H2D(e->d_meta, in->meta, sizeof(fcz_chain_meta) * (uint64_t)n);
+    const uint64_t bound = fcz_encode_bound(n, n_res, n_atoms, n_title, e->opts.anchor_threshold);
+    if ((rc = ensure(e, e->d_bytes, bound + 64))) return rc;
+    if ((rc = ensure(e, e->d_blob_off, 8ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_status, 4ull * n + 4))) return rc;
+    fcz_chain_batch din = *in;
+    din.mem = FCZ_MEM_DEVICE;
+    din.res_off = (uint32_t*)e->d_res_off.p; din.atom_off = (uint64_t*)e->d_atom_off.p;
+    din.title_off = (uint32_t*)e->d_title_off.p; din.res_type = (uint8_t*)e->d_res_type.p;
+    din.bfactor = (float*)e->d_bfactor.p; din.xyz = (float*)e->d_xyz.p; din.titles = (char*)e->d_titles.p;
+    din.meta = (fcz_chain_meta*)e->d_meta.p;
+    fcz_blob_batch dout;
+    dout.n_chains = n; dout.mem = FCZ_MEM_DEVICE;
+    dout.blob_off = (uint64_t*)e->d_blob_off.p; dout.bytes = (uint8_t*)e->d_bytes.p;
+    dout.status = (int32_t*)e->d_status.p; dout.bytes_cap = bound + 64;
+    if ((rc = encode_device(e, &din, &dout, &total))) return rc;
+    if (total > out->bytes_cap) return fail(e, FCZ_E_CAPACITY, "encode needs %llu bytes, capacity %llu",
+                                            (unsigned long long)total, (unsigned long long)out->bytes_cap);
+    CK(cudaMemcpyAsync(out->blob_off, dout.blob_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+    if (total) CK(cudaMemcpyAsync(out->bytes, dout.bytes, total, cudaMemcpyDeviceToHost, e->stream));
+    if (out->status && n) CK(cudaMemcpyAsync(out->status, dout.status, 4ull * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return FCZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------- decode
+
+static int decode_plan_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out, fcz_sizes* totals) {
+    const uint32_t n = in->n_chains;
+    int rc;
+    if ((rc = plan_buffers(e, n))) return rc;
+    TierTable tt;
+    for (int i = 0; i < FCZ_NTIER; i++) tt.t[i] = e->dec_tier[i];
+    PlanOut po;
+    po.v0 = (uint32_t*)e->v0.p; po.v1 = (uint32_t*)e->v1.p; po.v2 = (uint32_t*)e->v2.p;
+    po.status = out->status ? out->status : (int32_t*)e->status.p;
+    po.tier_count = e->d_counters;
+    po.tier_list = (uint32_t*)e->tier_list.p;
+    if (n) {
+        k_dec_plan<<<(n + 7) / 8, 256, 0, e->stream>>>(n, in->blob_off, in->bytes, e->d_tables, tt, po);
+        e->launches++;
+    }
+    ScanArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.n = n; sa.narr = 3;
+    sa.in[0] = po.v0; sa.out[0] = out->res_off; sa.out64[0] = 0;
+    sa.in[1] = po.v1; sa.out[1] = out->atom_off; sa.out64[1] = 1;
+    sa.in[2] = po.v2; sa.out[2] = out->title_off; sa.out64[2] = 0;
+    if ((rc = run_scan(e, sa))) return rc;
+    if ((rc = fetch_plan(e))) return rc;
+    totals->n_res = e->h_totals[0];
+    totals->n_atoms = e->h_totals[1];
+    totals->n_title_bytes = e->h_totals[2];
+    totals->n_blob_bytes = 0;
+    return FCZ_OK;
+}
+
+static int decode_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out) {
+    // uses the tier lists / counters left by the last decode_plan_device on this engine
+    const uint32_t n = in->n_chains;
+    if (e->h_totals[0] > out->res_cap || e->h_totals[1] > out->atom_cap || (out->titles && e->h_totals[2] > out->title_cap))
+        return fail(e, FCZ_E_CAPACITY, "decode output capacity too small (need %llu residues, %llu atoms, %llu title bytes)",
+                    (unsigned long long)e->h_totals[0], (unsigned long long)e->h_totals[1], (unsigned long long)e->h_totals[2]);
+    CK(cudaMemsetAsync(e->d_counters + FCZ_NTIER, 0, sizeof(uint32_t) * FCZ_NTIER, e->stream));
+    for (int i = 0; i < FCZ_NTIER; i++) {
+        const uint32_t cnt = e->h_counters[i];
+        if (!cnt) continue;
+        DecArgs a;
+        a.blob_off = in->blob_off; a.bytes = in->bytes;
+        a.res_off = out->res_off; a.atom_off = out->atom_off; a.title_off = out->title_off;
+        a.res_type = out->res_type; a.bfactor = out->bfactor; a.xyz = out->xyz; a.titles = out->titles; a.meta = out->meta;
+        a.list = (uint32_t*)e->tier_list.p + (size_t)i * n;
+        a.count = e->d_counters + i;
+        a.ticket = e->d_counters + FCZ_NTIER + i;
+        a.tables = e->d_tables;
+        a.use_alt = e->opts.use_alt_atom_order;
+        a.cfg = e->dec_tier[i];
+        uint32_t grid = (uint32_t)(e->num_sms * e->dec_occ[i]);
+        if (grid > cnt) grid = cnt;
+        {
+            ProfSpan ps(e, 1);
+            k_decode<<<grid, a.cfg.threads, a.cfg.smem, e->stream>>>(a);
+        }
+        e->launches++;
+    }
+    CK(cudaGetLastError());
+    return FCZ_OK;
+}
+
+extern "C" int fcz_decode_plan(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out, fcz_sizes* totals) {
+    if (!e || !in || !out || !totals) return FCZ_E_ARG;
+    if (in->mem != out->mem) return fail(e, FCZ_E_ARG, "input and output batches must live in the same memory space");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    out->n_chains = n;
+    int rc;
+    if (in->mem == FCZ_MEM_DEVICE) {
+        rc = decode_plan_device(e, in, out, totals);
+        return rc;
+    }
+    const uint64_t nbytes = in->blob_off[n];
+    H2D(e->d_blob_off, in->blob_off, 8ull * (n + 1));
+    H2D(e->d_bytes, in->bytes, nbytes);
+    if ((rc = ensure(e, e->d_res_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_atom_off, 8ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_title_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_status, 4ull * n + 4))) return rc;
+    fcz_blob_batch din = *in;
+    din.mem = FCZ_MEM_DEVICE; din.blob_off = (uint64_t*)e->d_blob_off.p; din.bytes = (uint8_t*)e->d_bytes.p;
+    fcz_chain_batch dout = *out;
+    dout.mem = FCZ_MEM_DEVICE;
+    dout.res_off = (uint32_t*)e->d_res_off.p; dout.atom_off = (uint64_t*)e->d_atom_off.p;
+    dout.title_off = (uint32_t*)e->d_title_off.p; dout.status = (int32_t*)e->d_status.p;
+    if ((rc = decode_plan_device(e, &din, &dout, totals))) return rc;
+    totals->n_blob_bytes = nbytes;
+    CK(cudaMemcpyAsync(out->res_off, dout.res_off, 4ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(out->atom_off, dout.atom_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(out->title_off, dout.title_off, 4ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+    if (out->status && n) CK(cudaMemcpyAsync(out->status, dout.status, 4ull * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return FCZ_OK;
+}
+
+extern "C" int fcz_decode_batch(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out) {
+    if (!e || !in || !out) return FCZ_E_ARG;
+    if (in->mem != out->mem) return fail(e, FCZ_E_ARG, "input and output batches must live in the same memory space");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    int rc;
+    if (in->mem == FCZ_MEM_DEVICE) return decode_device(e, in, out);
+    // host batch: blobs and offsets are still resident from fcz_decode_plan on this engine
+    const uint64_t n_res = out->res_off[n], n_atoms = out->atom_off[n], n_title = out->title_off[n];
+    if (n_res > out->res_cap || n_atoms > out->atom_cap || (out->titles && n_title > out->title_cap))
+        return fail(e, FCZ_E_CAPACITY, "decode output capacity too small");
+    if ((rc = ensure(e, e->d_res_type, n_res + 16))) return rc;
+    if ((rc = ensure(e, e->d_bfactor, 4ull * n_res + 16))) return rc;
+    if ((rc = ensure(e, e->d_xyz, 12ull * n_atoms + 16))) return rc;
+    if ((rc = ensure(e, e->d_titles, n_title + 16))) return rc;
+    if ((rc = ensure(e, e->d_meta, sizeof(fcz_chain_meta) * (uint64_t)n + 16))) return rc;
+    fcz_blob_batch din = *in;
+    din.mem = FCZ_MEM_DEVICE; din.blob_off = (uint64_t*)e->d_blob_off.p; din.bytes = (uint8_t*)e->d_bytes.p;
+    fcz_chain_batch dout = *out;
+    dout.mem = FCZ_MEM_DEVICE;
+    dout.res_off = (uint32_t*)e->d_res_off.p; dout.atom_off = (uint64_t*)e->d_atom_off.p;
+    dout.title_off = (uint32_t*)e->d_title_off.p; dout.res_type = (uint8_t*)e->d_res_type.p;
+    dout.bfactor = (float*)e->d_bfactor.p; dout.xyz = (float*)e->d_xyz.p;
+    dout.titles = out->titles ? (char*)e->d_titles.p : nullptr;
+    dout.meta = (fcz_chain_meta*)e->d_meta.p; dout.status = (int32_t*)e->d_status.p;
+    if ((rc = decode_device(e, &din, &dout))) return rc;
+    if (n_res) {
+        CK(cudaMemcpyAsync(out->res_type, dout.res_type, n_res, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(out->bfactor, dout.bfactor, 4ull * n_res, cudaMemcpyDeviceToHost, e->stream));
+    }
+    if (n_atoms) CK(cudaMemcpyAsync(out->xyz, dout.xyz, 12ull * n_atoms, cudaMemcpyDeviceToHost, e->stream));
+    if (out->titles && n_title) CK(cudaMemcpyAsync(out->titles, dout.titles, n_title, cudaMemcpyDeviceToHost, e->stream));
+    if (n) CK(cudaMemcpyAsync(out->meta, dout.meta, sizeof(fcz_chain_meta) * (uint64_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return FCZ_OK;
+}

@@ -50,12 +50,24 @@ def mixed_lengths(rng: np.random.Generator, n: int, lo: int = 50, hi: int = 2000
     return np.clip(np.rint(np.exp(rng.normal(np.log(280.0), 0.75, n))), lo, hi).astype(np.int64)
 
 
+CHUNK = 500  # chains generated per vectorised pass (bounds the float64 temporaries to ~100 MB)
+
+
 def generate(n_chains: int, length=350, seed: int = SEED, first_index: int = 0) -> HostChainBatch:
-    """`length` is an int (all chains equal) or an array of per-chain lengths."""
-    tb = tables()
-    rng = np.random.Generator(np.random.Philox(key=seed + 7919 * first_index))
+    """`length` is an int (all chains equal) or an array of per-chain lengths.  Chains are generated in
+    chunks of CHUNK with a Philox stream keyed by (seed, index of the chunk's first chain)."""
+    from .abi import concat_batches
+
     lens = np.full(n_chains, int(length), np.int64) if np.isscalar(length) else np.asarray(length, np.int64)
-    assert len(lens) == n_chains and lens.min() >= 2
+    assert len(lens) == n_chains and (n_chains == 0 or lens.min() >= 2)
+    parts = [_generate_chunk(lens[s : s + CHUNK], seed, first_index + s) for s in range(0, n_chains, CHUNK)]
+    return concat_batches(parts)
+
+
+def _generate_chunk(lens: np.ndarray, seed: int, first_index: int) -> HostChainBatch:
+    tb = tables()
+    n_chains = len(lens)
+    rng = np.random.Generator(np.random.Philox(key=seed + 7919 * first_index))
     Lm = int(lens.max())
     n = n_chains
     types = rng.choice(20, size=(n, Lm), p=_FREQ / _FREQ.sum()).astype(np.uint8)

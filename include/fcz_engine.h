@@ -135,6 +135,17 @@ int fcz_engine_sync(fcz_engine* e);
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 uint64_t fcz_engine_launch_count(const fcz_engine* e);
 
+/* Optional per-kernel timing with CUDA events recorded on the engine's stream around every launch of
+ * the two hot kernels (k_encode, k_decode).  fcz_engine_get_profile synchronises the stream, returns
+ * the accumulated device times since the last call and resets them.  bench.py uses it for the
+ * roofline of the dominant kernel. */
+typedef struct fcz_profile {
+    double encode_kernel_ms, decode_kernel_ms; /* summed device time of k_encode / k_decode launches */
+    uint64_t encode_launches, decode_launches; /* how many launches that is                       */
+} fcz_profile;
+int fcz_engine_set_profiling(fcz_engine* e, int enabled);
+int fcz_engine_get_profile(fcz_engine* e, fcz_profile* out);
+
 const char* fcz_strerror(int code);
 const char* fcz_last_error(const fcz_engine* e);
 

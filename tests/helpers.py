@@ -230,3 +230,65 @@ def backbone_mask(res_type: np.ndarray) -> np.ndarray:
         n = int(tb.natoms[int(c)])
         m += [True, True, True] + [False] * (n - 3)
     return np.array(m, bool)
+
+
+# --------------------------------------------------------------------------- batch (OpenMP) oracle
+
+
+def oracle_encode_batch(b: HostChainBatch, anchor: int = 25, threads: int = 0) -> HostBlobBatch:
+    cap = abi.encode_bound(b.n_chains, b.n_res, b.n_atoms, len(b.titles), anchor) + 64
+    out = HostBlobBatch.empty(b.n_chains, cap)
+    sin, sout = b.as_struct(), out.as_struct()
+    rc = oracle().fcz_oracle_encode_batch(C.byref(sin), C.byref(sout), anchor, threads)
+    assert rc == 0, rc
+    out.bytes = out.bytes[: int(out.blob_off[-1])]
+    return out
+
+
+def oracle_decode_batch(blobs: HostBlobBatch, use_alt: bool = False, threads: int = 0) -> HostChainBatch:
+    n = blobs.n_chains
+    plan = HostChainBatch.empty(n)
+    sizes = abi.FczSizes()
+    sin, sp = blobs.as_struct(), plan.as_struct()
+    rc = oracle().fcz_oracle_decode_plan(C.byref(sin), C.byref(sp), C.byref(sizes))
+    assert rc == 0
+    out = HostChainBatch(
+        res_off=plan.res_off, atom_off=plan.atom_off, title_off=plan.title_off,
+        res_type=np.zeros(sizes.n_res, np.uint8), bfactor=np.zeros(sizes.n_res, np.float32),
+        xyz=np.zeros((sizes.n_atoms, 3), np.float32), titles=np.zeros(sizes.n_title_bytes, np.uint8),
+        meta=np.zeros(n, abi.META_DTYPE), status=plan.status,
+    )
+    so = out.as_struct()
+    rc = oracle().fcz_oracle_decode_batch(C.byref(sin), C.byref(so), int(use_alt), threads)
+    assert rc == 0
+    return out
+
+
+def per_chain_deviation(a: HostChainBatch, b: HostChainBatch):
+    """(worst backbone RMSD, worst all-atom RMSD, worst max deviation) over chains of two decoded batches."""
+    assert np.array_equal(a.atom_off, b.atom_off) and np.array_equal(a.res_off, b.res_off)
+    d2 = ((a.xyz.astype(np.float64) - b.xyz.astype(np.float64)) ** 2).sum(axis=1)
+    bb = backbone_mask_fast(a.res_type)
+    aoff = a.atom_off.astype(np.int64)
+    worst_bb = worst_all = worst_max = 0.0
+    cs_all = np.concatenate([[0.0], np.cumsum(d2)])
+    cs_bb = np.concatenate([[0.0], np.cumsum(d2 * bb)])
+    cnt_bb = np.concatenate([[0], np.cumsum(bb)])
+    for c in range(a.n_chains):
+        lo, hi = aoff[c], aoff[c + 1]
+        if hi == lo:
+            continue
+        worst_all = max(worst_all, np.sqrt((cs_all[hi] - cs_all[lo]) / (hi - lo)))
+        worst_bb = max(worst_bb, np.sqrt((cs_bb[hi] - cs_bb[lo]) / max(cnt_bb[hi] - cnt_bb[lo], 1)))
+    worst_max = float(np.sqrt(d2.max())) if len(d2) else 0.0
+    return float(worst_bb), float(worst_all), worst_max
+
+
+def backbone_mask_fast(res_type: np.ndarray) -> np.ndarray:
+    tb = tables()
+    nat = tb.natoms[res_type.astype(np.int64)]
+    starts = np.concatenate([[0], np.cumsum(nat)])[:-1]
+    m = np.zeros(int(nat.sum()), bool)
+    for k in range(3):
+        m[starts + k] = True
+    return m

@@ -1,0 +1,65 @@
+"""The product's per-chain codec (foldcomp_b200/csrc/fcz_codec.h) instantiated with a one-thread
+host context (tests/emu/) against the oracle: this checks, without a GPU, the algorithm the CUDA
+kernels run -- phase structure, indexing, bit packing and the anchor-segment stitch decomposition.
+Encode must be byte-identical; decode within the BASELINE.md tolerances (backbone RMSD <= 0.01 A,
+max deviation <= 0.05 A, all-atom RMSD <= 0.02 A -- measured values are ~1e-4 A)."""
+import numpy as np
+
+import helpers as H
+from foldcomp_b200 import synth
+
+TOL_BB_RMSD, TOL_MAX, TOL_ALL_RMSD = 0.01, 0.05, 0.02
+
+
+def test_model_encode_matches_golden(golden):
+    for b in golden.anchors:
+        blobs = golden.blobs(b)
+        for c, name in enumerate(golden.names):
+            assert H.emu_encode(golden.batch, c, b) == blobs[c], (name, b)
+
+
+def test_model_decode_within_tolerance_of_reference(golden):
+    worst = 0.0
+    for b in golden.anchors:
+        blobs = golden.blobs(b)
+        for c, name in enumerate(golden.names):
+            dec = H.emu_decode(blobs[c])
+            xyz, bf = golden.decoded(b, c)
+            bb = H.backbone_mask(dec.res_type)
+            assert H.rmsd(dec.xyz[bb], xyz[bb]) <= TOL_BB_RMSD, (name, b)
+            assert H.max_dev(dec.xyz, xyz) <= TOL_MAX, (name, b)
+            assert H.rmsd(dec.xyz, xyz) <= TOL_ALL_RMSD, (name, b)
+            assert np.array_equal(dec.bfactor, bf)
+            worst = max(worst, H.max_dev(dec.xyz, xyz))
+    assert worst < 5e-3  # calibration: the decomposition costs ~1e-4 A, not 1e-2
+
+
+def test_model_decodes_upstream_example_db(golden):
+    a = 0
+    for blob in golden.db_blobs:
+        dec = H.emu_decode(blob)
+        n = len(dec.xyz)
+        assert H.max_dev(dec.xyz, golden.db_xyz[a : a + n]) <= TOL_MAX
+        a += n
+
+
+def test_model_vs_oracle_synthetic_mixed():
+    rng = np.random.default_rng(11)
+    lens = synth.mixed_lengths(rng, 60, lo=2, hi=1200)
+    batch = synth.generate(len(lens), lens, seed=3)
+    for c in range(batch.n_chains):
+        for b in (25, 10, 50, 200):
+            o = H.oracle_encode(batch, c, b)
+            assert H.emu_encode(batch, c, b) == o, (c, b)
+            do, de = H.oracle_decode(o), H.emu_decode(o)
+            bb = H.backbone_mask(do.res_type)
+            assert H.rmsd(de.xyz[bb], do.xyz[bb]) <= TOL_BB_RMSD
+            assert H.max_dev(de.xyz, do.xyz) <= TOL_MAX
+            assert de.title == do.title and de.meta == do.meta
+
+
+def test_model_alt_order(golden):
+    c = golden.names.index("test.pdb")
+    blob = golden.blobs(25)[c]
+    do, de = H.oracle_decode(blob, use_alt=True), H.emu_decode(blob, use_alt=True)
+    assert H.max_dev(de.xyz, do.xyz) <= TOL_MAX
