@@ -236,8 +236,9 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
 
 // ------------------------------------------------------------------------------------------ decode
 
-// floats of per-segment scratch: S[9] actual start atoms, T[12] rigid transform, tail[9] local tail,
-// F[12] local frame (3 axes + origin)
+// floats of per-segment scratch: S[9] true start atoms, T[12] rigid transform local->true, TAIL[9] local
+// coordinates of the segment's last residue, F[12] frame after the first placed residue in local
+// coordinates (bcn, nbc, n) + its origin (the C atom)
 #define FCZ_SEG_FLOATS 42
 enum { SEG_S = 0, SEG_T = 9, SEG_TAIL = 21, SEG_F = 30 };
 
@@ -256,31 +257,22 @@ struct DecChain {
     cs* tor;              // [3(L-1)] (cos,sin) of psi,omega,phi per record
     cs* ang;              // [3(L-1)] (cos,sin) of CA-C-N, C-N-CA, N-CA-C per record
     float* seg;           // [(n_anchor-1) * FCZ_SEG_FLOATS]
+    uint16_t* order;      // [L] residues sorted by atom count, descending
+    uint32_t* bins;       // [2*16] counting-sort bins
 };
 
-// orthonormal frame of a triangle (p0,p1,p2): e1 along p0->p1, e3 normal, e2 = e3 x e1
-struct Frame {
-    f3 e1, e2, e3;
-};
-FCZ_HD f3 scale3(f3 v, float s) { return mk3(v.x * s, v.y * s, v.z * s); }
-FCZ_HD float dot3(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-FCZ_HD Frame make_frame(f3 p0, f3 p1, f3 p2) {
-    Frame f;
-    f3 u = sub3(p1, p0);
-    f.e1 = scale3(u, 1.0f / norm3(u));
-    f3 n = cross3(f.e1, sub3(p2, p1));
-    f.e3 = scale3(n, 1.0f / norm3(n));
-    f.e2 = cross3(f.e3, f.e1);
-    return f;
-}
-// x -> R (x - o_loc) + o_act with R = F_act F_loc^T, evaluated as sum_j e_act_j * (e_loc_j . (x - o_loc))
+// y = R x + t, T = rows of R (9) then t (3)
 FCZ_HD f3 xform(const float* T, f3 x) {
-    // T: rows of R (9), then t (3):  y = R x + t
-    return mk3(((T[0] * x.x + T[1] * x.y) + T[2] * x.z) + T[9], ((T[3] * x.x + T[4] * x.y) + T[5] * x.z) + T[10],
-               ((T[6] * x.x + T[7] * x.y) + T[8] * x.z) + T[11]);
+    return mk3(fma_(T[2], x.z, fma_(T[1], x.y, fma_(T[0], x.x, T[9]))), fma_(T[5], x.z, fma_(T[4], x.y, fma_(T[3], x.x, T[10]))),
+               fma_(T[8], x.z, fma_(T[7], x.y, fma_(T[6], x.x, T[11]))));
 }
-
+FCZ_HD f3 get_f3(const uint8_t* p) { return mk3(get_f32(p), get_f32(p + 4), get_f32(p + 8)); }
 FCZ_HD float n_ca_len(unsigned code) { return code == FCZ_CODE_PRO ? FCZ_PRO_N_TO_CA : FCZ_N_TO_CA; }
+
+// weightedAverage (src/atom_coordinate.cpp:145-163): atom i of n: (fwd*(n-i) + rev*i) / n
+FCZ_HD f3 blend(f3 fwd, f3 rev, float wf, float wr, float inv_n) {
+    return mk3(fma_(rev.x, wr, fwd.x * wf) * inv_n, fma_(rev.y, wr, fwd.y * wf) * inv_n, fma_(rev.z, wr, fwd.z * wf) * inv_n);
+}
 
 template <class Ctx>
 FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
@@ -291,11 +283,14 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     const int n_seg = (int)y.n_anchor - 1;
     const uint32_t nT = 3u * L - 3u;
 
-    // ---- phase 1: records -> residue codes, atom offsets (exclusive scan), (cos,sin) of the
-    // continuised angles (convertBytesToBackboneChain src/foldcomp.cpp:60-77, decompressBackboneChain
-    // 122-153, _continuize 155-158; the deg->rad and sincos of Nerf::place_atom src/nerf.cpp:63-70
-    // are hoisted here so the recurrences below carry no transcendental)
+    // ---- phase 1: records -> residue codes, atom offsets (exclusive scan), residues sorted by atom
+    // count (for the level-synchronous side-chain pass), (cos,sin) of the continuised angles
+    // (convertBytesToBackboneChain src/foldcomp.cpp:60-77, decompressBackboneChain 122-153,
+    // _continuize 155-158; the deg->rad and sincos of Nerf::place_atom src/nerf.cpp:63-70 are hoisted
+    // here so the recurrences below carry no transcendental)
     {
+        for (uint32_t i = cx.tid; i < 32u; i += cx.nthr) ch.bins[i] = 0u;
+        cx.sync();
         float mins[6], cfs[6];
         for (int k = 0; k < 6; k++) {
             mins[k] = get_f32(blob + OFF_MINS + 4 * k);
@@ -305,13 +300,27 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
         uint32_t r0 = cx.tid * chunk; if (r0 > L) r0 = L;
         uint32_t r1 = r0 + chunk; if (r1 > L) r1 = L;
         uint32_t sum = 0;
-        for (uint32_t r = r0; r < r1; r++) sum += tb->natoms[rec[8u * r] >> 3];
-        uint32_t base = cx.excl_scan(sum);
+        for (uint32_t r = r0; r < r1; r++) {
+            uint32_t na = tb->natoms[rec[8u * r] >> 3];
+            sum += na;
+            cx.atomic_add(&ch.bins[na & 15u], 1u);
+        }
+        uint32_t base = cx.excl_scan(sum);  // (block barrier inside: bins complete afterwards)
         for (uint32_t r = r0; r < r1; r++) {
             ch.aoff[r] = base;
             base += tb->natoms[rec[8u * r] >> 3];
         }
         if (r1 == L) ch.aoff[L] = base;
+        // bins[16+na] = first position of residues with `na` atoms in the descending order
+        if (cx.tid == 0) {
+            uint32_t pos = 0;
+            for (int na = 15; na >= 0; na--) { ch.bins[16 + na] = pos; pos += ch.bins[na]; }
+        }
+        cx.sync();
+        for (uint32_t r = r0; r < r1; r++) {
+            uint32_t na = tb->natoms[rec[8u * r] >> 3];
+            ch.order[cx.atomic_add(&ch.bins[16u + (na & 15u)], 1u)] = (uint16_t)r;
+        }
         const float tmin = get_f32(blob + y.o_temp), tcf = get_f32(blob + y.o_temp + 4);
         for (uint32_t r = cx.tid; r < L; r += cx.nthr) {
             Record q = unpack_record(rec + 8u * r);
@@ -353,21 +362,18 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
         float* sg = ch.seg + s * FCZ_SEG_FLOATS;
         const uint32_t a0 = get_u32(blob + y.o_aidx + 4u * s), a1 = get_u32(blob + y.o_aidx + 4u * (s + 1));
         const uint8_t* anc = blob + y.o_anchor + 36u * s;
-        f3 p0 = mk3(get_f32(anc), get_f32(anc + 4), get_f32(anc + 8));
-        f3 p1 = mk3(get_f32(anc + 12), get_f32(anc + 16), get_f32(anc + 20));
-        f3 p2 = mk3(get_f32(anc + 24), get_f32(anc + 28), get_f32(anc + 32));
+        f3 p0 = get_f3(anc), p1 = get_f3(anc + 12), p2 = get_f3(anc + 24);
+        NerfFrame f = frame_from(p0, p1, p2);
         for (uint32_t r = a0; r < a1; r++) {
             const uint32_t t = 3u * r;
-            f3 n = place_atom(p0, p1, p2, FCZ_C_TO_N, ch.ang[t], ch.tor[t]);
-            f3 ca = place_atom(p1, p2, n, n_ca_len(rec[8u * r] >> 3), ch.ang[t + 1u], ch.tor[t + 1u]);
-            f3 c = place_atom(p2, n, ca, FCZ_CA_TO_C, ch.ang[t + 2u], ch.tor[t + 2u]);
+            p0 = nerf_step(f, p2, FCZ_C_TO_N, ch.ang[t], ch.tor[t]);                             // N
+            p1 = nerf_step(f, p0, n_ca_len(rec[8u * r] >> 3), ch.ang[t + 1u], ch.tor[t + 1u]);  // CA
+            p2 = nerf_step(f, p1, FCZ_CA_TO_C, ch.ang[t + 2u], ch.tor[t + 2u]);                  // C
             float* o = ch.out_xyz + 3u * ch.aoff[r + 1u];
-            st3(o, n); st3(o + 3, ca); st3(o + 6, c);
-            if (r == a0) {  // local frame of the first placed residue
-                Frame f = make_frame(n, ca, c);
-                st3(sg + SEG_F, f.e1); st3(sg + SEG_F + 3, f.e2); st3(sg + SEG_F + 6, f.e3); st3(sg + SEG_F + 9, n);
+            st3(o, p0); st3(o + 3, p1); st3(o + 6, p2);
+            if (r == a0) {  // frame carried by the first placed residue, origin at its C
+                st3(sg + SEG_F, f.bcn); st3(sg + SEG_F + 3, f.nbc); st3(sg + SEG_F + 6, f.n); st3(sg + SEG_F + 9, p2);
             }
-            p0 = n; p1 = ca; p2 = c;
         }
         st3(sg + SEG_TAIL, p0); st3(sg + SEG_TAIL + 3, p1); st3(sg + SEG_TAIL + 6, p2);
     }
@@ -375,57 +381,49 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
 
     // ---- phase 3: stitch.  Serial over segments (the only cross-segment dependency of the
     // reference, src/foldcomp.cpp:855-857: the blended tail of segment s seeds segment s+1).  Per
-    // segment: place N',CA',C' from the true start atoms, derive the rigid transform local->true,
-    // move the local tail, blend it with the stored anchor (weightedAverage,
+    // segment: place N',CA',C' from the true start atoms, derive the rigid transform local->true
+    // from the two frames, move the local tail, blend it with the stored anchor (weightedAverage,
     // src/atom_coordinate.cpp:145-163, last three atoms only).
     if (cx.tid == 0) {
-        f3 s0, s1, s2;
-        {
-            const uint8_t* anc = blob + y.o_anchor;
-            s0 = mk3(get_f32(anc), get_f32(anc + 4), get_f32(anc + 8));
-            s1 = mk3(get_f32(anc + 12), get_f32(anc + 16), get_f32(anc + 20));
-            s2 = mk3(get_f32(anc + 24), get_f32(anc + 28), get_f32(anc + 32));
-        }
+        const uint8_t* anc0 = blob + y.o_anchor;
+        f3 s0 = get_f3(anc0), s1 = get_f3(anc0 + 12), s2 = get_f3(anc0 + 24);
         for (int s = 0; s < n_seg; s++) {
             float* sg = ch.seg + s * FCZ_SEG_FLOATS;
             st3(sg + SEG_S, s0); st3(sg + SEG_S + 3, s1); st3(sg + SEG_S + 6, s2);
             const uint32_t a0 = get_u32(blob + y.o_aidx + 4u * s), a1 = get_u32(blob + y.o_aidx + 4u * (s + 1));
             const uint8_t* anc = blob + y.o_anchor + 36u * (s + 1);
-            f3 e0 = mk3(get_f32(anc), get_f32(anc + 4), get_f32(anc + 8));
-            f3 e1 = mk3(get_f32(anc + 12), get_f32(anc + 16), get_f32(anc + 20));
-            f3 e2 = mk3(get_f32(anc + 24), get_f32(anc + 28), get_f32(anc + 32));
+            const f3 e0 = get_f3(anc), e1 = get_f3(anc + 12), e2 = get_f3(anc + 24);
             f3 t0 = s0, t1 = s1, t2 = s2;  // forward tail in true coordinates
             if (a1 > a0) {
                 const uint32_t t = 3u * a0;
-                f3 n = place_atom(s0, s1, s2, FCZ_C_TO_N, ch.ang[t], ch.tor[t]);
-                f3 ca = place_atom(s1, s2, n, n_ca_len(rec[8u * a0] >> 3), ch.ang[t + 1u], ch.tor[t + 1u]);
-                f3 c = place_atom(s2, n, ca, FCZ_CA_TO_C, ch.ang[t + 2u], ch.tor[t + 2u]);
-                Frame fa = make_frame(n, ca, c);
-                f3 l1 = ld3(sg + SEG_F), l2 = ld3(sg + SEG_F + 3), l3 = ld3(sg + SEG_F + 6), lo = ld3(sg + SEG_F + 9);
+                NerfFrame fa = frame_from(s0, s1, s2);
+                f3 n = nerf_step(fa, s2, FCZ_C_TO_N, ch.ang[t], ch.tor[t]);
+                f3 ca = nerf_step(fa, n, n_ca_len(rec[8u * a0] >> 3), ch.ang[t + 1u], ch.tor[t + 1u]);
+                f3 c = nerf_step(fa, ca, FCZ_CA_TO_C, ch.ang[t + 2u], ch.tor[t + 2u]);
+                const f3 l1 = ld3(sg + SEG_F), l2 = ld3(sg + SEG_F + 3), l3 = ld3(sg + SEG_F + 6), lo = ld3(sg + SEG_F + 9);
                 float* T = sg + SEG_T;
-                // R = e_act1 l1^T + e_act2 l2^T + e_act3 l3^T
-                T[0] = (fa.e1.x * l1.x + fa.e2.x * l2.x) + fa.e3.x * l3.x;
-                T[1] = (fa.e1.x * l1.y + fa.e2.x * l2.y) + fa.e3.x * l3.y;
-                T[2] = (fa.e1.x * l1.z + fa.e2.x * l2.z) + fa.e3.x * l3.z;
-                T[3] = (fa.e1.y * l1.x + fa.e2.y * l2.x) + fa.e3.y * l3.x;
-                T[4] = (fa.e1.y * l1.y + fa.e2.y * l2.y) + fa.e3.y * l3.y;
-                T[5] = (fa.e1.y * l1.z + fa.e2.y * l2.z) + fa.e3.y * l3.z;
-                T[6] = (fa.e1.z * l1.x + fa.e2.z * l2.x) + fa.e3.z * l3.x;
-                T[7] = (fa.e1.z * l1.y + fa.e2.z * l2.y) + fa.e3.z * l3.y;
-                T[8] = (fa.e1.z * l1.z + fa.e2.z * l2.z) + fa.e3.z * l3.z;
-                // t = o_act - R o_loc
-                T[9] = n.x - ((T[0] * lo.x + T[1] * lo.y) + T[2] * lo.z);
-                T[10] = n.y - ((T[3] * lo.x + T[4] * lo.y) + T[5] * lo.z);
-                T[11] = n.z - ((T[6] * lo.x + T[7] * lo.y) + T[8] * lo.z);
+                // R = bcn_a bcn_l^T + nbc_a nbc_l^T + n_a n_l^T ;  t = c_true - R c_local
+                T[0] = fma_(fa.n.x, l3.x, fma_(fa.nbc.x, l2.x, fa.bcn.x * l1.x));
+                T[1] = fma_(fa.n.x, l3.y, fma_(fa.nbc.x, l2.y, fa.bcn.x * l1.y));
+                T[2] = fma_(fa.n.x, l3.z, fma_(fa.nbc.x, l2.z, fa.bcn.x * l1.z));
+                T[3] = fma_(fa.n.y, l3.x, fma_(fa.nbc.y, l2.x, fa.bcn.y * l1.x));
+                T[4] = fma_(fa.n.y, l3.y, fma_(fa.nbc.y, l2.y, fa.bcn.y * l1.y));
+                T[5] = fma_(fa.n.y, l3.z, fma_(fa.nbc.y, l2.z, fa.bcn.y * l1.z));
+                T[6] = fma_(fa.n.z, l3.x, fma_(fa.nbc.z, l2.x, fa.bcn.z * l1.x));
+                T[7] = fma_(fa.n.z, l3.y, fma_(fa.nbc.z, l2.y, fa.bcn.z * l1.y));
+                T[8] = fma_(fa.n.z, l3.z, fma_(fa.nbc.z, l2.z, fa.bcn.z * l1.z));
+                T[9] = c.x - fma_(T[2], lo.z, fma_(T[1], lo.y, T[0] * lo.x));
+                T[10] = c.y - fma_(T[5], lo.z, fma_(T[4], lo.y, T[3] * lo.x));
+                T[11] = c.z - fma_(T[8], lo.z, fma_(T[7], lo.y, T[6] * lo.x));
                 t0 = xform(T, ld3(sg + SEG_TAIL));
                 t1 = xform(T, ld3(sg + SEG_TAIL + 3));
                 t2 = xform(T, ld3(sg + SEG_TAIL + 6));
             }
             const float nf = (float)(3u * (a1 - a0 + 1u));  // atoms in the segment
-            const float w0 = nf - 3.0f, w1 = nf - 2.0f, w2 = nf - 1.0f;  // index i of the tail atoms
-            s0 = mk3((t0.x * 3.0f + e0.x * w0) / nf, (t0.y * 3.0f + e0.y * w0) / nf, (t0.z * 3.0f + e0.z * w0) / nf);
-            s1 = mk3((t1.x * 2.0f + e1.x * w1) / nf, (t1.y * 2.0f + e1.y * w1) / nf, (t1.z * 2.0f + e1.z * w1) / nf);
-            s2 = mk3((t2.x * 1.0f + e2.x * w2) / nf, (t2.y * 1.0f + e2.y * w2) / nf, (t2.z * 1.0f + e2.z * w2) / nf);
+            const float inv = 1.0f / nf;
+            s0 = blend(t0, e0, 3.0f, nf - 3.0f, inv);
+            s1 = blend(t1, e1, 2.0f, nf - 2.0f, inv);
+            s2 = blend(t2, e2, 1.0f, nf - 1.0f, inv);
         }
         // blended tail of the last segment = final coordinates of the last residue (src/foldcomp.cpp:851-853)
         float* o = ch.out_xyz + 3u * ch.aoff[L - 1u];
@@ -435,60 +433,65 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
 
     // ---- phase 4: reverse pass + blend, one lane per segment (reconstructBackboneReverse,
     // src/foldcomp.cpp:248-273; Nerf::reconstructWithReversed src/nerf.cpp:342-379 with forward
-    // indices; bond angles recomputed from the FORWARD atoms as getBondAngles src/nerf.cpp:495-508
-    // does; bond lengths by atom kind, never the Pro length, src/nerf.h:37-43).
+    // indices; bond angles taken from the FORWARD atoms as getBondAngles src/nerf.cpp:495-508 does;
+    // bond lengths by atom kind, never the Pro length, src/nerf.h:37-43).
     for (int s = cx.tid; s < n_seg; s += cx.nthr) {
         const float* sg = ch.seg + s * FCZ_SEG_FLOATS;
         const float* T = sg + SEG_T;
         const uint32_t a0 = get_u32(blob + y.o_aidx + 4u * s), a1 = get_u32(blob + y.o_aidx + 4u * (s + 1));
         if (a1 <= a0) continue;  // empty segment: nothing to emit (its three atoms belong to the next one)
         const int n = (int)(3u * (a1 - a0 + 1u));
-        const float nf = (float)n;
+        const float inv = 1.0f / (float)n;
         const uint8_t* anc = blob + y.o_anchor + 36u * (s + 1);
-        // reversed chain window (atoms q+3, q+2, q+1) starts as the stored anchor C, CA, N
-        f3 r1 = mk3(get_f32(anc), get_f32(anc + 4), get_f32(anc + 8));
-        f3 r2 = mk3(get_f32(anc + 12), get_f32(anc + 16), get_f32(anc + 20));
-        f3 r3 = mk3(get_f32(anc + 24), get_f32(anc + 28), get_f32(anc + 32));
+        // reversed chain starts as the stored anchor: a = C, b = CA, c = N
+        f3 rc = get_f3(anc);
+        NerfFrame f = frame_from(get_f3(anc + 24), get_f3(anc + 12), rc);
         // forward window (atoms q+1, q+2) starts as the moved local tail
         f3 f1 = xform(T, ld3(sg + SEG_TAIL)), f2 = xform(T, ld3(sg + SEG_TAIL + 3));
         for (int q = n - 4; q >= 0; q--) {
             const uint32_t r = a0 + (uint32_t)q / 3u, k = (uint32_t)q % 3u;
             float* slot = ch.out_xyz + 3u * (ch.aoff[r] + k);
-            f3 f0 = (q < 3) ? ld3(sg + SEG_S + 3 * q) : xform(T, ld3(slot));
-            cs ba = cossin_deg(bond_angle_deg(f0, f1, f2));  // angle at forward atom q+1
+            const f3 f0 = (q < 3) ? ld3(sg + SEG_S + 3 * q) : xform(T, ld3(slot));
+            const cs ba = cossin_angle(f0, f1, f2);  // angle at forward atom q+1
             const float bl = (k == 0u) ? FCZ_N_TO_CA : (k == 1u ? FCZ_CA_TO_C : FCZ_C_TO_N);
             uint32_t ti = 3u * a0 + (uint32_t)q;
             if (ti >= nT) ti = nT - 1u;
-            f3 nw = place_atom(r3, r2, r1, bl, ba, ch.tor[ti]);
-            const float wf = (float)(n - q), wr = (float)q;
-            st3(slot, mk3((f0.x * wf + nw.x * wr) / nf, (f0.y * wf + nw.y * wr) / nf, (f0.z * wf + nw.z * wr) / nf));
-            r3 = r2; r2 = r1; r1 = nw;
+            rc = nerf_step(f, rc, bl, ba, ch.tor[ti]);
+            st3(slot, blend(f0, rc, (float)(n - q), (float)q, inv));
             f2 = f1; f1 = f0;
         }
     }
     cx.sync();
 
-    // ---- phase 5: side chains, one lane per residue (Nerf::reconstructAminoAcid
-    // src/nerf.cpp:106-155; torsion = FixedAngleDiscretizer(255).continuize(byte),
-    // src/foldcomp.cpp:338-369).  Atoms are built in place in the output area: predecessors of an
-    // atom always have lower slots in the same residue.
+    // ---- phase 5: side chains, level-synchronous: level k places slot k of every residue that has
+    // one (residues sorted by atom count, so the active ones are a prefix and warps stay full).
+    // Nerf::reconstructAminoAcid src/nerf.cpp:106-155; torsion = FixedAngleDiscretizer(255)
+    // .continuize(byte), src/foldcomp.cpp:338-369.  Atoms are built in place in the output area:
+    // predecessors of an atom always have lower slots in the same residue.
     {
         const float mn = sc_min(), cf = sc_cont_f();
         const uint8_t* sc = blob + y.o_sc;
-        for (uint32_t r = cx.tid; r < L; r += cx.nthr) {
-            const unsigned code = rec[8u * r] >> 3;
-            const uint32_t a0 = ch.aoff[r];
-            const uint32_t na = tb->natoms[code];
-            float* R = ch.out_xyz + 3u * a0;
-            const uint8_t* tb_sc = sc + (a0 - 3u * r);
-            for (uint32_t k = 3u; k < na; k++) {
-                unsigned pr = tb->pred[code][k];
-                cs to = cossin_deg(continuize(tb_sc[k - 3u], mn, cf));
-                f3 v = place_atom(ld3(R + 3u * (pr & 15u)), ld3(R + 3u * ((pr >> 4) & 15u)),
-                                  ld3(R + 3u * ((pr >> 8) & 15u)), tb->blen[code][k], tb->bang[code][k], to);
-                st3(R + 3u * k, v);
+        uint32_t active = L;  // residues with more than k atoms
+        for (uint32_t k = 3u; k < FCZ_MAX_ATOMS; k++) {
+            active -= ch.bins[k];  // bins[k] = residues with exactly k atoms (bins[3] = UNK)
+            if (active == 0u) break;
+            for (uint32_t i = cx.tid; i < active; i += cx.nthr) {
+                const uint32_t r = ch.order[i];
+                const unsigned code = rec[8u * r] >> 3;
+                const uint32_t a0 = ch.aoff[r];
+                float* R = ch.out_xyz + 3u * a0;
+                const unsigned pr = tb->pred[code][k];
+                const cs to = cossin_deg(continuize(sc[a0 - 3u * r + k - 3u], mn, cf));
+                st3(R + 3u * k, place_from(ld3(R + 3u * (pr & 15u)), ld3(R + 3u * ((pr >> 4) & 15u)),
+                                           ld3(R + 3u * ((pr >> 8) & 15u)), tb->blen[code][k], tb->bang[code][k], to));
             }
-            if (ch.use_alt) {  // _reorderAtoms, src/foldcomp.cpp:1563-1577
+            cx.sync();
+        }
+        if (ch.use_alt) {  // _reorderAtoms, src/foldcomp.cpp:1563-1577
+            for (uint32_t r = cx.tid; r < L; r += cx.nthr) {
+                const unsigned code = rec[8u * r] >> 3;
+                const uint32_t na = tb->natoms[code];
+                float* R = ch.out_xyz + 3u * ch.aoff[r];
                 f3 tmp[FCZ_MAX_ATOMS];
                 for (uint32_t k = 0; k < na; k++) tmp[k] = ld3(R + 3u * k);
                 for (uint32_t k = 0; k < na; k++) st3(R + 3u * k, tmp[tb->alt[code][k]]);

@@ -39,7 +39,10 @@ struct TierCfg {
 };
 
 #define FCZ_NTIER 7
-static const uint32_t kTierRes[FCZ_NTIER] = {64, 128, 256, 384, 640, 1280, 3072};
+// residue caps per tier; decode carries more per-residue state in shared memory (198 B vs 175 B), so its
+// last staged tier is smaller.  The last tier keeps chain data in global memory.
+static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 256, 384, 640, 1280, 3072};
+static const uint32_t kDecTierRes[FCZ_NTIER] = {64, 128, 256, 384, 640, 1024, 3072};
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
@@ -63,14 +66,15 @@ __host__ __device__ inline EncSmem enc_smem(const TierCfg& t) {
     return s;
 }
 struct DecSmem {
-    uint32_t o_tab, o_misc, o_aoff, o_tor, o_ang, o_seg, o_blob, o_out, total;
+    uint32_t o_tab, o_misc, o_aoff, o_order, o_tor, o_ang, o_seg, o_blob, o_out, total;
 };
 __host__ __device__ inline DecSmem dec_smem(const TierCfg& t) {
     DecSmem s;
     uint32_t o = 0;
     s.o_tab = o;  o += align16((uint32_t)sizeof(Tables));
-    s.o_misc = o; o += 256;
+    s.o_misc = o; o += 384;  // mbarrier, ticket, warp sums (+64), counting-sort bins (+192)
     s.o_aoff = o; o += align16(4u * (t.max_res + 1u));
+    s.o_order = o; o += align16(2u * t.max_res);
     s.o_tor = o;  o += align16(24u * t.max_res);
     s.o_ang = o;  o += align16(24u * t.max_res);
     s.o_seg = o;  o += align16(4u * FCZ_SEG_FLOATS * t.max_seg);
@@ -80,27 +84,30 @@ __host__ __device__ inline DecSmem dec_smem(const TierCfg& t) {
     return s;
 }
 
+static TierCfg make_tier(uint32_t max_res, bool staged) {
+    TierCfg t;
+    t.max_res = max_res;
+    t.staged = staged ? 1u : 0u;
+    t.max_atoms = 9u * max_res;
+    t.max_blob = 17u * max_res + 1280u;
+    t.max_seg = max_res / 8u + 8u;
+    if (t.max_seg > 254u) t.max_seg = 254u;
+    t.threads = (max_res <= 128u) ? 128u : 256u;
+    if (!staged) {
+        t.max_atoms = 10u * max_res;
+        t.max_blob = 0xFFFFFFFFu;
+        t.max_seg = 254u;
+        t.threads = 512u;
+    }
+    t.smem = 0;
+    return t;
+}
 static void make_tiers(TierCfg* enc, TierCfg* dec) {
     for (int i = 0; i < FCZ_NTIER; i++) {
-        TierCfg t;
-        t.max_res = kTierRes[i];
-        t.staged = (i < FCZ_NTIER - 1) ? 1u : 0u;
-        t.max_atoms = t.staged ? 9u * t.max_res : 65535u * 2u / 3u;  // large tier: bounded by smem of ares only
-        t.max_blob = 17u * t.max_res + 1280u;
-        t.max_seg = t.max_res / 8u + 8u;
-        if (t.max_seg > 254u) t.max_seg = 254u;
-        t.threads = (t.max_res <= 128u) ? 128u : 256u;
-        if (!t.staged) {
-            t.max_atoms = 10u * t.max_res;
-            t.max_blob = 0xFFFFFFFFu;
-            t.max_seg = 254u;
-            t.threads = 512u;
-        }
-        TierCfg e = t, d = t;
-        e.smem = enc_smem(e).total;
-        d.smem = dec_smem(d).total;
-        enc[i] = e;
-        dec[i] = d;
+        enc[i] = make_tier(kEncTierRes[i], i < FCZ_NTIER - 1);
+        dec[i] = make_tier(kDecTierRes[i], i < FCZ_NTIER - 1);
+        enc[i].smem = enc_smem(enc[i]).total;
+        dec[i].smem = dec_smem(dec[i]).total;
     }
 }
 
@@ -163,6 +170,7 @@ struct DevCtx {
         __syncthreads();
         return base + x - v;
     }
+    __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
     __device__ __forceinline__ float wmin(float v) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -498,6 +506,8 @@ __global__ void __launch_bounds__(512) k_decode(DecArgs a) {
         ch.tor = reinterpret_cast<cs*>(smem + so.o_tor);
         ch.ang = reinterpret_cast<cs*>(smem + so.o_ang);
         ch.seg = reinterpret_cast<float*>(smem + so.o_seg);
+        ch.order = reinterpret_cast<uint16_t*>(smem + so.o_order);
+        ch.bins = reinterpret_cast<uint32_t*>(smem + so.o_misc + 192);
         float* gout = a.xyz + 3u * a0;
         uint8_t* sout = nullptr;
         if (a.cfg.staged) {
@@ -705,6 +715,13 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     }
     make_tiers(e->enc_tier, e->dec_tier);
     bool ok = true;
+    for (int i = 0; i < FCZ_NTIER; i++) {
+        if (e->enc_tier[i].smem > 227u * 1024u || e->dec_tier[i].smem > 227u * 1024u) {
+            fprintf(stderr, "fcz_engine_create: tier %d needs %u / %u bytes of shared memory (> 227 KB)\n", i,
+                    e->enc_tier[i].smem, e->dec_tier[i].smem);
+            ok = false;
+        }
+    }
     for (int i = 0; i < FCZ_NTIER && ok; i++) {
         ok &= cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         ok &= cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;

@@ -79,10 +79,37 @@ FCZ_HD float dihedral_deg(f3 a1, f3 a2, f3 a3, f3 a4) {
     return t;
 }
 
-// degrees -> radians exactly as src/nerf.cpp:63-64 (double multiply, double divide, to float)
-FCZ_HD float deg2rad(float deg) { return (float)((double)deg * M_PI / 180.0); }
+// ---------------------------------------------------------------- decode-side NeRF (tolerance parity)
+// Decoding cannot be bit-identical to the reference (its sincosf comes from glibc), so it is held to
+// the BASELINE.md tolerance instead and is free to use fused multiply-adds, rsqrt and a propagated
+// frame.  Everything below is exact-arithmetic equivalent to Nerf::place_atom (src/nerf.cpp:39-104).
 
-// (cos, sin) of an angle given in degrees, the pair place_atom needs
+FCZ_HD float fma_(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+FCZ_HD float rsqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+FCZ_HD float dotf(f3 a, f3 b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
+FCZ_HD f3 crossf(f3 a, f3 b) {
+    return mk3(fma_(a.y, b.z, -(b.y * a.z)), fma_(a.z, b.x, -(b.z * a.x)), fma_(a.x, b.y, -(b.x * a.y)));
+}
+FCZ_HD f3 scalef(f3 v, float s) { return mk3(v.x * s, v.y * s, v.z * s); }
+// a + s*v
+FCZ_HD f3 axpy(float s, f3 v, f3 a) { return mk3(fma_(s, v.x, a.x), fma_(s, v.y, a.y), fma_(s, v.z, a.z)); }
+
+// degrees -> radians: one double multiply (src/nerf.cpp:63-64 does x*M_PI/180.0 in double)
+FCZ_HD float deg2rad(float deg) { return (float)((double)deg * (M_PI / 180.0)); }
+
+// (cos, sin) of an angle
 struct cs {
     float c, s;
 };
@@ -97,26 +124,53 @@ FCZ_HD cs cossin_deg(float deg) {
 #endif
     return o;
 }
+// (cos, sin) of the angle at b between a and c, straight from the coordinates -- what the
+// reference gets by acos -> degrees -> radians -> sincosf (src/float3d.h:55-65, src/nerf.cpp:63-70)
+FCZ_HD cs cossin_angle(f3 a, f3 b, f3 c) {
+    f3 u = sub3(a, b), v = sub3(c, b);
+    cs o;
+    o.c = dotf(u, v) * rsqrt_(dotf(u, u) * dotf(v, v));
+    float s2 = fma_(-o.c, o.c, 1.0f);
+    o.s = s2 > 0.0f ? sqrtf(s2) : 0.0f;
+    return o;
+}
 
-// reference: Nerf::place_atom, src/nerf.cpp:39-104, with the trigonometry hoisted out:
-// ang = (cos, sin) of the bond angle, tor = (cos, sin) of the torsion.  Operation order of the
-// remaining float arithmetic is the reference's.
-FCZ_HD f3 place_atom(f3 a, f3 b, f3 c, float len, cs ang, cs tor) {
+// The local frame Nerf::place_atom builds from three atoms (a, b, c): bcn along b->c, n normal to
+// the a-b-c plane, nbc = n x bcn (src/nerf.cpp:52-85).
+struct NerfFrame {
+    f3 bcn, n, nbc;
+};
+FCZ_HD NerfFrame frame_from(f3 a, f3 b, f3 c) {
+    NerfFrame f;
     f3 ab = sub3(b, a), bc = sub3(c, b);
-    float bc_norm = norm3(bc);
-    f3 bcn = mk3(bc.x / bc_norm, bc.y / bc_norm, bc.z / bc_norm);
-    float d2x = (-1 * len) * ang.c;
-    float d2y = (len * tor.c) * ang.s;
-    float d2z = (len * tor.s) * ang.s;
-    f3 n = cross3(ab, bcn);
-    float n_norm = norm3(n);
-    n = mk3(n.x / n_norm, n.y / n_norm, n.z / n_norm);
-    f3 nbc = cross3(n, bcn);
-    f3 d;
-    d.x = ((bcn.x * d2x + nbc.x * d2y) + n.x * d2z) + c.x;
-    d.y = ((bcn.y * d2x + nbc.y * d2y) + n.y * d2z) + c.y;
-    d.z = ((bcn.z * d2x + nbc.z * d2y) + n.z * d2z) + c.z;
-    return d;
+    f.bcn = scalef(bc, rsqrt_(dotf(bc, bc)));
+    f3 n = crossf(ab, f.bcn);
+    f.n = scalef(n, rsqrt_(dotf(n, n)));
+    f.nbc = crossf(f.n, f.bcn);
+    return f;
+}
+// Place the next atom of a chain from the frame of the previous three and advance the frame:
+//   D      = c + len * (-cos(th) bcn + cos(tau) sin(th) nbc + sin(tau) sin(th) n)     (nerf.cpp:66-98)
+//   bcn'   = (D - c) / len
+//   n'     = normalise((c - b) x bcn') =             - sin(tau) nbc + cos(tau) n
+//   nbc'   = n' x bcn'                 = -sin(th) bcn - cos(tau) cos(th) nbc - sin(tau) cos(th) n
+// i.e. the frame place_atom would rebuild from (b, c, D), obtained by ROTATING the old frame with an
+// orthogonal 3x3 matrix: no square root, no division, and -- unlike recomputing nbc' as a cross
+// product, which multiplies the vectors' norm errors and blows up exponentially -- rounding errors
+// only add up linearly along the chain.
+FCZ_HD f3 nerf_step(NerfFrame& f, f3 c, float len, cs ang, cs tor) {
+    const float x = -ang.c, y = tor.c * ang.s, z = tor.s * ang.s;
+    const float u = -ang.s, v = -(tor.c * ang.c), w = -(tor.s * ang.c);
+    const f3 b0 = f.bcn, b1 = f.nbc, b2 = f.n;
+    f.bcn = mk3(fma_(z, b2.x, fma_(y, b1.x, x * b0.x)), fma_(z, b2.y, fma_(y, b1.y, x * b0.y)), fma_(z, b2.z, fma_(y, b1.z, x * b0.z)));
+    f.nbc = mk3(fma_(w, b2.x, fma_(v, b1.x, u * b0.x)), fma_(w, b2.y, fma_(v, b1.y, u * b0.y)), fma_(w, b2.z, fma_(v, b1.z, u * b0.z)));
+    f.n = mk3(fma_(tor.c, b2.x, -(tor.s * b1.x)), fma_(tor.c, b2.y, -(tor.s * b1.y)), fma_(tor.c, b2.z, -(tor.s * b1.z)));
+    return axpy(len, f.bcn, c);
+}
+// One-off placement from three arbitrary predecessor atoms (side chains, src/nerf.cpp:106-155)
+FCZ_HD f3 place_from(f3 a, f3 b, f3 c, float len, cs ang, cs tor) {
+    NerfFrame f = frame_from(a, b, c);
+    return nerf_step(f, c, len, ang, tor);
 }
 
 // ------------------------------------------------------------------ discretiser (src/discretizer.cpp)

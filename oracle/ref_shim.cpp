@@ -40,11 +40,11 @@ struct TypeInfo {
 };
 
 const TypeInfo& type_info(int code) {
-    static std::vector<TypeInfo> tab;
-    if (tab.empty()) {
-        tab.resize(24);
+    // thread-safe one-time initialisation (C++11 magic static): ref_roundtrip_batch calls this from OpenMP threads
+    static const std::vector<TypeInfo> tab = [] {
+        std::vector<TypeInfo> v(24);
         for (int c = 0; c < 24; c++) {
-            TypeInfo& t = tab[c];
+            TypeInfo& t = v[c];
             t.name3 = convertIntToThreeLetterCode((unsigned)c);
             auto it = aas().find(t.name3);
             if (it != aas().end() && !it->second.atoms.empty()) {
@@ -53,7 +53,8 @@ const TypeInfo& type_info(int code) {
                 t.atoms = {"N", "CA", "C"};
             }
         }
-    }
+        return v;
+    }();
     return tab[code];
 }
 

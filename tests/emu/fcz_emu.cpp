@@ -16,6 +16,7 @@ struct HostCtx {
     void sync() {}
     void stage_wait() {}
     uint32_t excl_scan(uint32_t) { return 0; }
+    uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
     float wmin(float v) { return v; }
     float wmax(float v) { return v; }
 };
@@ -64,10 +65,12 @@ int emu_decode_chain(const uint8_t* blob, uint64_t len, int use_alt, uint8_t* re
     std::vector<uint32_t> aoff(L + 1);
     std::vector<cs> tor(3 * (size_t)L), ang(3 * (size_t)L);
     std::vector<float> seg((size_t)(y.n_anchor - 1) * FCZ_SEG_FLOATS);
+    std::vector<uint16_t> order(L);
+    uint32_t bins[32];
     DecChain ch;
     ch.blob = blob; ch.y = y; ch.use_alt = use_alt;
     ch.out_xyz = xyz; ch.out_type = res_type; ch.out_bfac = bfac; ch.out_meta = meta; ch.out_title = title;
-    ch.aoff = aoff.data(); ch.tor = tor.data(); ch.ang = ang.data(); ch.seg = seg.data();
+    ch.aoff = aoff.data(); ch.tor = tor.data(); ch.ang = ang.data(); ch.seg = seg.data(); ch.order = order.data(); ch.bins = bins;
     HostCtx cx;
     decode_chain(cx, tb, ch);
     return FCZ_OK;
