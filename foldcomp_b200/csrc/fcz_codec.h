@@ -101,41 +101,73 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
     cx.stage_wait();  // coordinates staged by the caller are now visible
     cx.sync();
 
-    // ---- phase 2: one dihedral per atom.  Side-chain atoms (slot >= 3) give the side-chain byte
-    // (src/sidechain.cpp:149-168 + FixedAngleDiscretizer, src/foldcomp.cpp:532-538); backbone
-    // atom j = 3r+k gives backbone torsion j (src/torsion_angle.cpp:49-94): k=0 psi, 1 omega, 2 phi
-    // (src/foldcomp.cpp:488-492).
+    // ---- phases 2+3: ONE loop over all angle items of the chain so that the expensive double-precision
+    // tail (sqrt, divide, acos, *180/pi) exists once and runs with full warps:
+    //   items 0 .. A-1     one dihedral per atom.  Side-chain atoms (slot >= 3) give the side-chain byte
+    //                      (src/sidechain.cpp:149-168 + FixedAngleDiscretizer, src/foldcomp.cpp:532-538);
+    //                      backbone atom j = 3r+k gives backbone torsion j (src/torsion_angle.cpp:49-94):
+    //                      k=0 psi, 1 omega, 2 phi (src/foldcomp.cpp:488-492);
+    //   items A .. A+3L-4  backbone bond angles at atoms m = 2 .. 3L-2 (src/nerf.cpp:495-508; split by
+    //                      index%3 at src/foldcomp.cpp:496-505: m%3==2 CA-C-N[m/3], 0 C-N-CA[m/3-1],
+    //                      1 N-CA-C[m/3-1]).
+    // The arithmetic of each item is exactly dihedral_deg / bond_angle_deg of fcz_math.h.
     {
         const float mn = sc_min(), df = sc_disc_f();
         const uint32_t nT = 3u * L - 3u;
-        for (uint32_t a = cx.tid; a < A; a += cx.nthr) {
-            uint32_t r = ch.ares[a];
-            uint32_t a0 = ch.aoff[r];
-            uint32_t k = a - a0;
-            if (k >= 3u) {
-                unsigned pr = tb->pred[ch.type[r]][k];
-                const float* R = ch.X + 3u * a0;
-                float t = dihedral_deg(ld3(R + 3u * (pr & 15u)), ld3(R + 3u * ((pr >> 4) & 15u)),
-                                       ld3(R + 3u * ((pr >> 8) & 15u)), ld3(R + 3u * k));
-                B[y.o_sc + (a - 3u * (r + 1u))] = (uint8_t)disc_trunc(t, mn, df);
-            } else {
-                uint32_t j = 3u * r + k;
-                if (j < nT) {
-                    float t = dihedral_deg(bb_atom(ch, j), bb_atom(ch, j + 1), bb_atom(ch, j + 2), bb_atom(ch, j + 3));
-                    int arr = (k == 0) ? A_PSI : (k == 1 ? A_OMEGA : A_PHI);
-                    ch.ang[arr * L + r] = t;
+        const uint32_t W = A + nT;
+        for (uint32_t w = cx.tid; w < W; w += cx.nthr) {
+            f3 v1, v2;          // the two vectors whose angle is taken
+            bool neg = false;   // dihedral sign
+            bool valid = true;
+            int kind;           // 0 side-chain byte, 1 backbone torsion, 2 bond angle
+            uint32_t dst;       // destination index (byte offset in B, or index into ch.ang)
+            if (w < A) {
+                const uint32_t r = ch.ares[w];
+                const uint32_t a0 = ch.aoff[r];
+                const uint32_t k = w - a0;
+                uint32_t i0, i1, i2, i3;
+                if (k >= 3u) {
+                    const unsigned pr = tb->pred[ch.type[r]][k];
+                    i0 = a0 + (pr & 15u); i1 = a0 + ((pr >> 4) & 15u); i2 = a0 + ((pr >> 8) & 15u); i3 = w;
+                    kind = 0;
+                    dst = y.o_sc + (w - 3u * (r + 1u));
+                } else {
+                    const uint32_t j = 3u * r + k;
+                    valid = j < nT;
+                    const uint32_t a1 = valid ? ch.aoff[r + 1u] : a0;
+                    // backbone atoms j .. j+3 = (r,k) (r,k+1) ... wrapping into residue r+1
+                    i0 = a0 + k;
+                    i1 = (k < 2u) ? a0 + k + 1u : a1;
+                    i2 = (k < 1u) ? a0 + 2u : a1 + (k - 1u);
+                    i3 = a1 + k;
+                    kind = 1;
+                    dst = (k == 0u ? (uint32_t)A_PSI : (k == 1u ? (uint32_t)A_OMEGA : (uint32_t)A_PHI)) * L + r;
                 }
+                const f3 p0 = ld3(ch.X + 3u * i0), p1 = ld3(ch.X + 3u * i1), p2 = ld3(ch.X + 3u * i2), p3 = ld3(ch.X + 3u * i3);
+                const f3 d1 = sub3(p1, p0), d2 = sub3(p2, p1), d3 = sub3(p3, p2);
+                v1 = cross3(d1, d2);
+                v2 = cross3(d2, d3);
+                const f3 pb = cross3(v2, d2);  // torsion_angle.cpp:87-92
+                neg = (v1.x * pb.x) + (v1.y * pb.y) + (v1.z * pb.z) < 0;
+            } else {
+                const uint32_t m = 2u + (w - A);
+                const uint32_t q = m / 3u, k = m - 3u * q;
+                const f3 pm = bb_atom(ch, m);
+                v1 = sub3(bb_atom(ch, m - 1u), pm);
+                v2 = sub3(bb_atom(ch, m + 1u), pm);
+                kind = 2;
+                dst = (k == 2u) ? (uint32_t)A_CACN * L + q : (k == 0u ? (uint32_t)A_CNCA * L + q - 1u : (uint32_t)A_NCAC * L + q - 1u);
             }
+            const float c = cos_theta(v1, v2);
+            const double ac = acos((double)c);
+            float deg = (float)(ac * 180.0 / M_PI);
+            if (kind != 2) {
+                if (ac != ac) deg = (c < 0) ? 180.0f : 0.0f;  // torsion_angle.cpp:74-79
+                if (neg) deg = -deg;
+            }
+            if (kind == 0) B[dst] = (uint8_t)disc_trunc(deg, mn, df);
+            else if (valid) ch.ang[dst] = deg;
         }
-    }
-    // ---- phase 3: backbone bond angles at atoms m = 2 .. 3L-2 (src/nerf.cpp:495-508; split by
-    // index%3 at src/foldcomp.cpp:496-505: m%3==2 CA-C-N[m/3], 0 C-N-CA[m/3-1], 1 N-CA-C[m/3-1])
-    for (uint32_t m = 2u + cx.tid; m + 1u < 3u * L; m += cx.nthr) {
-        float v = bond_angle_deg(bb_atom(ch, m - 1), bb_atom(ch, m), bb_atom(ch, m + 1));
-        uint32_t q = m / 3u, k = m - 3u * q;
-        if (k == 2u) ch.ang[A_CACN * L + q] = v;
-        else if (k == 0u) ch.ang[A_CNCA * L + q - 1u] = v;
-        else ch.ang[A_NCAC * L + q - 1u] = v;
     }
     cx.sync();
 
@@ -238,9 +270,10 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
 
 // floats of per-segment scratch: S[9] true start atoms, T[12] rigid transform local->true, TAIL[9] local
 // coordinates of the segment's last residue, F[12] frame after the first placed residue in local
-// coordinates (bcn, nbc, n) + its origin (the C atom)
-#define FCZ_SEG_FLOATS 42
-enum { SEG_S = 0, SEG_T = 9, SEG_TAIL = 21, SEG_F = 30 };
+// coordinates (bcn, nbc, n) + its origin (the C atom), HEAD[6] local N',CA' of the first placed residue,
+// RF[12] frame (bcn, nbc, n) and last atom of the reverse pass once it has placed atom 3
+#define FCZ_SEG_FLOATS 60
+enum { SEG_S = 0, SEG_T = 9, SEG_TAIL = 21, SEG_F = 30, SEG_HEAD = 42, SEG_RF = 48 };
 
 struct DecChain {
     const uint8_t* blob;  // staged copy or global
@@ -258,6 +291,8 @@ struct DecChain {
     cs* ang;              // [3(L-1)] (cos,sin) of CA-C-N, C-N-CA, N-CA-C per record
     float* seg;           // [(n_anchor-1) * FCZ_SEG_FLOATS]
     uint16_t* order;      // [L] residues sorted by atom count, descending
+    float* rev;           // [9L] reverse-pass backbone atoms (true coordinates)
+    uint8_t* segid;       // [L] anchor segment that owns (emits) each residue
     uint32_t* bins;       // [2*16] counting-sort bins
 };
 
@@ -352,30 +387,56 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     }
     cx.sync();
 
-    // ---- phase 2: forward NeRF pass of every anchor segment, one lane per segment, in the
-    // segment's LOCAL frame: it starts from the STORED anchor instead of the blended tail of the
-    // previous segment (which is not known yet).  From its 4th placed atom on a forward pass is a
-    // rigid body hanging off its first placed residue (N',CA',C'), so the true pass is this one
-    // moved by a rigid transform that phase 3 determines.  (reconstructBackboneAtoms,
-    // src/foldcomp.cpp:167-246; Pro N-CA length taken from the record being consumed, 204-212.)
-    for (int s = cx.tid; s < n_seg; s += cx.nthr) {
+    // ---- phase 2: both NeRF passes of every anchor segment, TWO lanes per segment.
+    //  even lane: FORWARD pass (reconstructBackboneAtoms, src/foldcomp.cpp:167-246; Pro N-CA length taken
+    //   from the record being consumed, 204-212) in the segment's LOCAL frame: it starts from the STORED
+    //   anchor instead of the blended tail of the previous segment (not known yet).  From its 4th placed
+    //   atom on a forward pass is a rigid body hanging off its first placed residue (N',CA',C'), so the
+    //   true pass is this one moved by a rigid transform that phase 3 determines.
+    //  odd lane: REVERSE pass (reconstructBackboneReverse src/foldcomp.cpp:248-273, Nerf::reconstructWithReversed
+    //   src/nerf.cpp:342-379 with forward indices) from the stored anchor s+1, in true coordinates, for atoms
+    //   n-4 .. 3.  The reference feeds it the bond angles re-measured on the forward atoms (getBondAngles,
+    //   src/nerf.cpp:495-508); for atoms 4.. those are the stored angles the forward pass was built with
+    //   (up to float noise), so the stored values are used and the pass does not wait for the forward one.
+    //   Bond lengths by atom kind, never the Pro length (src/nerf.h:37-43).  The last three reverse atoms
+    //   depend on the true start atoms and are finished in phase 4.
+    for (int ln = cx.tid; ln < 2 * n_seg; ln += cx.nthr) {
+        const int s = ln >> 1;
         float* sg = ch.seg + s * FCZ_SEG_FLOATS;
         const uint32_t a0 = get_u32(blob + y.o_aidx + 4u * s), a1 = get_u32(blob + y.o_aidx + 4u * (s + 1));
-        const uint8_t* anc = blob + y.o_anchor + 36u * s;
-        f3 p0 = get_f3(anc), p1 = get_f3(anc + 12), p2 = get_f3(anc + 24);
-        NerfFrame f = frame_from(p0, p1, p2);
-        for (uint32_t r = a0; r < a1; r++) {
-            const uint32_t t = 3u * r;
-            p0 = nerf_step(f, p2, FCZ_C_TO_N, ch.ang[t], ch.tor[t]);                             // N
-            p1 = nerf_step(f, p0, n_ca_len(rec[8u * r] >> 3), ch.ang[t + 1u], ch.tor[t + 1u]);  // CA
-            p2 = nerf_step(f, p1, FCZ_CA_TO_C, ch.ang[t + 2u], ch.tor[t + 2u]);                  // C
-            float* o = ch.out_xyz + 3u * ch.aoff[r + 1u];
-            st3(o, p0); st3(o + 3, p1); st3(o + 6, p2);
-            if (r == a0) {  // frame carried by the first placed residue, origin at its C
-                st3(sg + SEG_F, f.bcn); st3(sg + SEG_F + 3, f.nbc); st3(sg + SEG_F + 6, f.n); st3(sg + SEG_F + 9, p2);
+        if ((ln & 1) == 0) {
+            const uint8_t* anc = blob + y.o_anchor + 36u * s;
+            f3 p0 = get_f3(anc), p1 = get_f3(anc + 12), p2 = get_f3(anc + 24);
+            NerfFrame f = frame_from(p0, p1, p2);
+            for (uint32_t r = a0; r < a1; r++) {
+                const uint32_t t = 3u * r;
+                p0 = nerf_step(f, p2, FCZ_C_TO_N, ch.ang[t], ch.tor[t]);                             // N
+                p1 = nerf_step(f, p0, n_ca_len(rec[8u * r] >> 3), ch.ang[t + 1u], ch.tor[t + 1u]);  // CA
+                p2 = nerf_step(f, p1, FCZ_CA_TO_C, ch.ang[t + 2u], ch.tor[t + 2u]);                  // C
+                float* o = ch.out_xyz + 3u * ch.aoff[r + 1u];
+                st3(o, p0); st3(o + 3, p1); st3(o + 6, p2);
+                ch.segid[r] = (uint8_t)s;
+                if (r == a0) {  // frame carried by the first placed residue, origin at its C
+                    st3(sg + SEG_F, f.bcn); st3(sg + SEG_F + 3, f.nbc); st3(sg + SEG_F + 6, f.n); st3(sg + SEG_F + 9, p2);
+                    st3(sg + SEG_HEAD, p0); st3(sg + SEG_HEAD + 3, p1);
+                }
             }
+            st3(sg + SEG_TAIL, p0); st3(sg + SEG_TAIL + 3, p1); st3(sg + SEG_TAIL + 6, p2);
+        } else if (a1 > a0) {
+            const int n = (int)(3u * (a1 - a0 + 1u));
+            const uint8_t* anc = blob + y.o_anchor + 36u * (s + 1);
+            // reversed chain starts as the stored anchor: a = C, b = CA, c = N
+            f3 rc = get_f3(anc);
+            NerfFrame f = frame_from(get_f3(anc + 24), get_f3(anc + 12), rc);
+            for (int q = n - 4; q >= 3; q--) {
+                const uint32_t g = 3u * a0 + (uint32_t)q;  // backbone atom index in the chain
+                const uint32_t k = (uint32_t)q % 3u;
+                const float bl = (k == 0u) ? FCZ_N_TO_CA : (k == 1u ? FCZ_CA_TO_C : FCZ_C_TO_N);
+                rc = nerf_step(f, rc, bl, ch.ang[g - 1u], ch.tor[g]);  // angle at atom g+1, torsion g
+                st3(ch.rev + 3u * g, rc);
+            }
+            st3(sg + SEG_RF, f.bcn); st3(sg + SEG_RF + 3, f.nbc); st3(sg + SEG_RF + 6, f.n); st3(sg + SEG_RF + 9, rc);
         }
-        st3(sg + SEG_TAIL, p0); st3(sg + SEG_TAIL + 3, p1); st3(sg + SEG_TAIL + 6, p2);
     }
     cx.sync();
 
@@ -431,10 +492,10 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     }
     cx.sync();
 
-    // ---- phase 4: reverse pass + blend, one lane per segment (reconstructBackboneReverse,
-    // src/foldcomp.cpp:248-273; Nerf::reconstructWithReversed src/nerf.cpp:342-379 with forward
-    // indices; bond angles taken from the FORWARD atoms as getBondAngles src/nerf.cpp:495-508 does;
-    // bond lengths by atom kind, never the Pro length, src/nerf.h:37-43).
+    // ---- phase 4: blend (weightedAverage, src/atom_coordinate.cpp:145-163).
+    //  (a) one lane per segment finishes the reverse pass: atoms 2,1,0 need the bond angles at the true
+    //      atoms 3,2,1 (which involve the start atoms S) and emits the blended first residue;
+    //  (b) every other backbone atom, one per thread: forward = local atom moved by T, reverse from phase 2.
     for (int s = cx.tid; s < n_seg; s += cx.nthr) {
         const float* sg = ch.seg + s * FCZ_SEG_FLOATS;
         const float* T = sg + SEG_T;
@@ -442,24 +503,35 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
         if (a1 <= a0) continue;  // empty segment: nothing to emit (its three atoms belong to the next one)
         const int n = (int)(3u * (a1 - a0 + 1u));
         const float inv = 1.0f / (float)n;
-        const uint8_t* anc = blob + y.o_anchor + 36u * (s + 1);
-        // reversed chain starts as the stored anchor: a = C, b = CA, c = N
-        f3 rc = get_f3(anc);
-        NerfFrame f = frame_from(get_f3(anc + 24), get_f3(anc + 12), rc);
-        // forward window (atoms q+1, q+2) starts as the moved local tail
-        f3 f1 = xform(T, ld3(sg + SEG_TAIL)), f2 = xform(T, ld3(sg + SEG_TAIL + 3));
-        for (int q = n - 4; q >= 0; q--) {
-            const uint32_t r = a0 + (uint32_t)q / 3u, k = (uint32_t)q % 3u;
-            float* slot = ch.out_xyz + 3u * (ch.aoff[r] + k);
-            const f3 f0 = (q < 3) ? ld3(sg + SEG_S + 3 * q) : xform(T, ld3(slot));
-            const cs ba = cossin_angle(f0, f1, f2);  // angle at forward atom q+1
-            const float bl = (k == 0u) ? FCZ_N_TO_CA : (k == 1u ? FCZ_CA_TO_C : FCZ_C_TO_N);
+        NerfFrame f;
+        f.bcn = ld3(sg + SEG_RF); f.nbc = ld3(sg + SEG_RF + 3); f.n = ld3(sg + SEG_RF + 6);
+        f3 rc = ld3(sg + SEG_RF + 9);
+        // forward window: true atoms 3 and 4 (N', CA' of the first placed residue; the tail when n == 6)
+        f3 f1 = xform(T, ld3(sg + SEG_HEAD)), f2 = xform(T, ld3(sg + SEG_HEAD + 3));
+        float* slot = ch.out_xyz + 3u * ch.aoff[a0];
+        for (int q = 2; q >= 0; q--) {
+            const f3 f0 = ld3(sg + SEG_S + 3 * q);
+            const cs ba = cossin_angle(f0, f1, f2);  // angle at true atom q+1
+            const float bl = (q == 0) ? FCZ_N_TO_CA : (q == 1 ? FCZ_CA_TO_C : FCZ_C_TO_N);
             uint32_t ti = 3u * a0 + (uint32_t)q;
             if (ti >= nT) ti = nT - 1u;
             rc = nerf_step(f, rc, bl, ba, ch.tor[ti]);
-            st3(slot, blend(f0, rc, (float)(n - q), (float)q, inv));
+            st3(slot + 3 * q, blend(f0, rc, (float)(n - q), (float)q, inv));
             f2 = f1; f1 = f0;
         }
+    }
+    for (uint32_t g = 3u + cx.tid; g < 3u * L - 3u; g += cx.nthr) {
+        const uint32_t r = g / 3u, k = g - 3u * r;
+        const int s = ch.segid[r - 1u];  // residue r was placed while consuming record r-1
+        const uint32_t a0 = get_u32(blob + y.o_aidx + 4u * s), a1 = get_u32(blob + y.o_aidx + 4u * (s + 1));
+        if (r == a0 || r >= a1) {
+            // first residue of the NEXT segment (emitted by (a)) -- or the chain's last residue (phase 3)
+            continue;
+        }
+        const float* T = ch.seg + s * FCZ_SEG_FLOATS + SEG_T;
+        const int q = (int)(g - 3u * a0), n = (int)(3u * (a1 - a0 + 1u));
+        float* slot = ch.out_xyz + 3u * (ch.aoff[r] + k);
+        st3(slot, blend(xform(T, ld3(slot)), ld3(ch.rev + 3u * g), (float)(n - q), (float)q, 1.0f / (float)n));
     }
     cx.sync();
 

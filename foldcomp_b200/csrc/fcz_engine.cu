@@ -41,8 +41,10 @@ struct TierCfg {
 #define FCZ_NTIER 7
 // residue caps per tier; decode carries more per-residue state in shared memory (198 B vs 175 B), so its
 // last staged tier is smaller.  The last tier keeps chain data in global memory.
-static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 256, 384, 640, 1280, 3072};
-static const uint32_t kDecTierRes[FCZ_NTIER] = {64, 128, 256, 384, 640, 1024, 3072};
+// Caps are chosen at the occupancy steps of the per-residue shared-memory footprint (encode ~172 B/residue,
+// decode ~240 B/residue): 350-residue chains run 3 CTAs/SM in encode and 2 CTAs/SM in decode.
+static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 296, 408, 632, 1280, 2800};
+static const uint32_t kDecTierRes[FCZ_NTIER] = {64, 128, 192, 272, 432, 896, 2800};
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
@@ -66,7 +68,7 @@ __host__ __device__ inline EncSmem enc_smem(const TierCfg& t) {
     return s;
 }
 struct DecSmem {
-    uint32_t o_tab, o_misc, o_aoff, o_order, o_tor, o_ang, o_seg, o_blob, o_out, total;
+    uint32_t o_tab, o_misc, o_aoff, o_order, o_segid, o_tor, o_ang, o_seg, o_rev, o_blob, o_out, total;
 };
 __host__ __device__ inline DecSmem dec_smem(const TierCfg& t) {
     DecSmem s;
@@ -75,9 +77,11 @@ __host__ __device__ inline DecSmem dec_smem(const TierCfg& t) {
     s.o_misc = o; o += 384;  // mbarrier, ticket, warp sums (+64), counting-sort bins (+192)
     s.o_aoff = o; o += align16(4u * (t.max_res + 1u));
     s.o_order = o; o += align16(2u * t.max_res);
+    s.o_segid = o; o += align16(t.max_res);
     s.o_tor = o;  o += align16(24u * t.max_res);
     s.o_ang = o;  o += align16(24u * t.max_res);
     s.o_seg = o;  o += align16(4u * FCZ_SEG_FLOATS * t.max_seg);
+    s.o_rev = o;  o += t.staged ? align16(36u * t.max_res) : 0u;  // large tier: reverse atoms live in global scratch
     s.o_blob = o; o += t.staged ? align16(t.max_blob) + 32u : 0u;
     s.o_out = o;  o += t.staged ? align16(12u * t.max_atoms) + 32u : 0u;
     s.total = o;
@@ -90,7 +94,7 @@ static TierCfg make_tier(uint32_t max_res, bool staged) {
     t.staged = staged ? 1u : 0u;
     t.max_atoms = 9u * max_res;
     t.max_blob = 17u * max_res + 1280u;
-    t.max_seg = max_res / 8u + 8u;
+    t.max_seg = max_res / 10u + 8u;
     if (t.max_seg > 254u) t.max_seg = 254u;
     t.threads = (max_res <= 128u) ? 128u : 256u;
     if (!staged) {
@@ -402,6 +406,7 @@ struct DecArgs {
     uint32_t* ticket;
     const Tables* tables;
     int32_t use_alt;
+    float* large_scratch;  // [gridDim.x][9 * cfg.max_res] reverse atoms of the large (unstaged) tier
     TierCfg cfg;
 };
 
@@ -507,6 +512,8 @@ __global__ void __launch_bounds__(512) k_decode(DecArgs a) {
         ch.ang = reinterpret_cast<cs*>(smem + so.o_ang);
         ch.seg = reinterpret_cast<float*>(smem + so.o_seg);
         ch.order = reinterpret_cast<uint16_t*>(smem + so.o_order);
+        ch.segid = smem + so.o_segid;
+        ch.rev = a.cfg.staged ? reinterpret_cast<float*>(smem + so.o_rev) : a.large_scratch + (size_t)blockIdx.x * 9u * a.cfg.max_res;
         ch.bins = reinterpret_cast<uint32_t*>(smem + so.o_misc + 192);
         float* gout = a.xyz + 3u * a0;
         uint8_t* sout = nullptr;
@@ -633,7 +640,7 @@ struct fcz_engine {
     int enc_occ[FCZ_NTIER], dec_occ[FCZ_NTIER];
     Tables* d_tables = nullptr;
     // plan scratch
-    DevBuf v0, v1, v2, status, tier_list, partial;
+    DevBuf v0, v1, v2, status, tier_list, partial, large_scratch;
     uint32_t* d_counters = nullptr;  // [FCZ_NTIER] counts, [FCZ_NTIER] tickets
     uint64_t* d_totals = nullptr;    // [3]
     uint32_t* h_counters = nullptr;  // pinned mirror
@@ -751,7 +758,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
+    DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->status, &e->tier_list, &e->partial, &e->large_scratch, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
                       &e->d_blob_off, &e->d_bytes, &e->d_status};
     for (DevBuf* b : bufs)
@@ -1044,6 +1051,12 @@ static int decode_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batc
         a.cfg = e->dec_tier[i];
         uint32_t grid = (uint32_t)(e->num_sms * e->dec_occ[i]);
         if (grid > cnt) grid = cnt;
+        a.large_scratch = nullptr;
+        if (!a.cfg.staged) {
+            int rc = ensure(e, e->large_scratch, (size_t)grid * 36u * a.cfg.max_res);
+            if (rc) return rc;
+            a.large_scratch = (float*)e->large_scratch.p;
+        }
         {
             ProfSpan ps(e, 1);
             k_decode<<<grid, a.cfg.threads, a.cfg.smem, e->stream>>>(a);
