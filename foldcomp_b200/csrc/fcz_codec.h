@@ -30,6 +30,7 @@ struct Tables {
     uint16_t pred[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
     float blen[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
     cs bang[FCZ_NUM_CODES][FCZ_MAX_ATOMS];  // (cos, sin) of the table bond angle
+    cs sc_tor[256];  // (cos, sin) of every side-chain torsion byte: FixedAngleDiscretizer(255).continuize(b)
 };
 
 // Filled on the host with host libm: the table angles are compile-time constants of the format,
@@ -46,6 +47,11 @@ inline void build_tables(Tables* t) {
             t->bang[c][k].c = cosf(r);
             t->bang[c][k].s = sinf(r);
         }
+    }
+    for (int b = 0; b < 256; b++) {  // src/foldcomp.cpp:338-369 + src/nerf.cpp:64,66-70
+        float r = deg2rad(continuize((unsigned)b, sc_min(), sc_cont_f()));
+        t->sc_tor[b].c = cosf(r);
+        t->sc_tor[b].s = sinf(r);
     }
 }
 
@@ -100,6 +106,7 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
     }
     cx.stage_wait();  // coordinates staged by the caller are now visible
     cx.sync();
+    cx.mark(0);  // E_SCAN
 
     // ---- phases 2+3: ONE loop over all angle items of the chain so that the expensive double-precision
     // tail (sqrt, divide, acos, *180/pi) exists once and runs with full warps:
@@ -170,6 +177,7 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
         }
     }
     cx.sync();
+    cx.mark(1);  // E_ANGLES
 
     // ---- phase 4: min / max of the six arrays (L-1 values) and of the B-factors (L values)
     // (Discretizer::Discretizer, src/discretizer.cpp:22-33)
@@ -215,6 +223,7 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
             prm[2] = cont_factor(lo, hi, nb);
         }
         cx.sync();
+        cx.mark(2);  // E_MINMAX
     }
     const float* prm = ch.red + cx.nwarps * 14 + 14;
 
@@ -264,6 +273,7 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
         B[y.o_temp + 8u + r] = (uint8_t)disc_round(ch.bfac[r], prm[18], prm[19]);
     }
     cx.sync();
+    cx.mark(3);  // E_PACK
 }
 
 // ------------------------------------------------------------------------------------------ decode
@@ -272,8 +282,10 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
 // coordinates of the segment's last residue, F[12] frame after the first placed residue in local
 // coordinates (bcn, nbc, n) + its origin (the C atom), HEAD[6] local N',CA' of the first placed residue,
 // RF[12] frame (bcn, nbc, n) and last atom of the reverse pass once it has placed atom 3
-#define FCZ_SEG_FLOATS 60
-enum { SEG_S = 0, SEG_T = 9, SEG_TAIL = 21, SEG_F = 30, SEG_HEAD = 42, SEG_RF = 48 };
+// A[9] the stored anchor that opens the segment (as aligned floats), I[3] first / last residue index of
+// the segment (uint32 bits) and 1/(atoms in the segment).  Slot n_seg holds only A (the closing anchor).
+#define FCZ_SEG_FLOATS 72
+enum { SEG_S = 0, SEG_T = 9, SEG_TAIL = 21, SEG_F = 30, SEG_HEAD = 42, SEG_RF = 48, SEG_A = 60, SEG_I = 69 };
 
 struct DecChain {
     const uint8_t* blob;  // staged copy or global
@@ -289,7 +301,7 @@ struct DecChain {
     uint32_t* aoff;       // [L+1]
     cs* tor;              // [3(L-1)] (cos,sin) of psi,omega,phi per record
     cs* ang;              // [3(L-1)] (cos,sin) of CA-C-N, C-N-CA, N-CA-C per record
-    float* seg;           // [(n_anchor-1) * FCZ_SEG_FLOATS]
+    float* seg;           // [n_anchor * FCZ_SEG_FLOATS]
     uint16_t* order;      // [L] residues sorted by atom count, descending
     float* rev;           // [9L] reverse-pass backbone atoms (true coordinates)
     uint8_t* segid;       // [L] anchor segment that owns (emits) each residue
@@ -302,6 +314,8 @@ FCZ_HD f3 xform(const float* T, f3 x) {
                fma_(T[8], x.z, fma_(T[7], x.y, fma_(T[6], x.x, T[11]))));
 }
 FCZ_HD f3 get_f3(const uint8_t* p) { return mk3(get_f32(p), get_f32(p + 4), get_f32(p + 8)); }
+FCZ_HD uint32_t seg_a0(const float* sg) { return f2u(sg[SEG_I]); }
+FCZ_HD uint32_t seg_a1(const float* sg) { return f2u(sg[SEG_I + 1]); }
 FCZ_HD float n_ca_len(unsigned code) { return code == FCZ_CODE_PRO ? FCZ_PRO_N_TO_CA : FCZ_N_TO_CA; }
 
 // weightedAverage (src/atom_coordinate.cpp:145-163): atom i of n: (fwd*(n-i) + rev*i) / n
@@ -370,6 +384,19 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
                 ch.ang[3u * r + 2u] = cossin_deg(continuize(q.nca, mins[A_NCAC], cfs[A_NCAC]));
             }
         }
+        // anchors as aligned floats and the segment bounds, so that the serial phases never touch the
+        // unaligned blob bytes (anchor atoms: src/foldcomp.cpp:925-953)
+        for (uint32_t e = cx.tid; e < 9u * y.n_anchor; e += cx.nthr) {
+            const uint32_t i = e / 9u;
+            ch.seg[i * FCZ_SEG_FLOATS + SEG_A + (e - 9u * i)] = get_f32(blob + y.o_anchor + 4u * e);
+        }
+        for (uint32_t i = cx.tid; i + 1u < y.n_anchor; i += cx.nthr) {
+            const uint32_t a0 = get_u32(blob + y.o_aidx + 4u * i), a1 = get_u32(blob + y.o_aidx + 4u * (i + 1u));
+            float* sg = ch.seg + i * FCZ_SEG_FLOATS;
+            sg[SEG_I] = u2f(a0);
+            sg[SEG_I + 1] = u2f(a1);
+            sg[SEG_I + 2] = 1.0f / (float)(3u * (a1 - a0 + 1u));
+        }
         if (cx.tid == 0) {
             fcz_chain_meta m;
             m.n_atom = (uint16_t)get_u16(blob + OFF_NATOM);
@@ -386,6 +413,7 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
             for (uint32_t i = cx.tid; i < y.title_len; i += cx.nthr) ch.out_title[i] = (char)blob[y.o_title + i];
     }
     cx.sync();
+    cx.mark(8);  // D_UNPACK
 
     // ---- phase 2: both NeRF passes of every anchor segment, TWO lanes per segment.
     //  even lane: FORWARD pass (reconstructBackboneAtoms, src/foldcomp.cpp:167-246; Pro N-CA length taken
@@ -400,13 +428,15 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     //   (up to float noise), so the stored values are used and the pass does not wait for the forward one.
     //   Bond lengths by atom kind, never the Pro length (src/nerf.h:37-43).  The last three reverse atoms
     //   depend on the true start atoms and are finished in phase 4.
-    for (int ln = cx.tid; ln < 2 * n_seg; ln += cx.nthr) {
-        const int s = ln >> 1;
+    // (forward and reverse lanes sit in DIFFERENT warps: lanes of one warp would serialise the two loops)
+    const int n_grp = (n_seg + cx.wsize - 1) / cx.wsize;
+    for (int idx = cx.warp; idx < 2 * n_grp; idx += cx.nwarps) {
+        const int s = (idx >> 1) * cx.wsize + cx.lane;
+        if (s >= n_seg) continue;
         float* sg = ch.seg + s * FCZ_SEG_FLOATS;
-        const uint32_t a0 = get_u32(blob + y.o_aidx + 4u * s), a1 = get_u32(blob + y.o_aidx + 4u * (s + 1));
-        if ((ln & 1) == 0) {
-            const uint8_t* anc = blob + y.o_anchor + 36u * s;
-            f3 p0 = get_f3(anc), p1 = get_f3(anc + 12), p2 = get_f3(anc + 24);
+        const uint32_t a0 = seg_a0(sg), a1 = seg_a1(sg);
+        if ((idx & 1) == 0) {
+            f3 p0 = ld3(sg + SEG_A), p1 = ld3(sg + SEG_A + 3), p2 = ld3(sg + SEG_A + 6);
             NerfFrame f = frame_from(p0, p1, p2);
             for (uint32_t r = a0; r < a1; r++) {
                 const uint32_t t = 3u * r;
@@ -424,21 +454,28 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
             st3(sg + SEG_TAIL, p0); st3(sg + SEG_TAIL + 3, p1); st3(sg + SEG_TAIL + 6, p2);
         } else if (a1 > a0) {
             const int n = (int)(3u * (a1 - a0 + 1u));
-            const uint8_t* anc = blob + y.o_anchor + 36u * (s + 1);
+            const float* anc = sg + FCZ_SEG_FLOATS + SEG_A;
             // reversed chain starts as the stored anchor: a = C, b = CA, c = N
-            f3 rc = get_f3(anc);
-            NerfFrame f = frame_from(get_f3(anc + 24), get_f3(anc + 12), rc);
-            for (int q = n - 4; q >= 3; q--) {
-                const uint32_t g = 3u * a0 + (uint32_t)q;  // backbone atom index in the chain
-                const uint32_t k = (uint32_t)q % 3u;
-                const float bl = (k == 0u) ? FCZ_N_TO_CA : (k == 1u ? FCZ_CA_TO_C : FCZ_C_TO_N);
-                rc = nerf_step(f, rc, bl, ch.ang[g - 1u], ch.tor[g]);  // angle at atom g+1, torsion g
-                st3(ch.rev + 3u * g, rc);
+            f3 rc = ld3(anc);
+            NerfFrame f = frame_from(ld3(anc + 6), ld3(anc + 3), rc);
+            // residue-wise (three placements per trip, so the six table loads of a trip issue together):
+            // atoms q = n-4 .. 3 are C, CA, N of residues a1-1 .. a0+1; g = backbone atom index in the chain
+            for (uint32_t r = a1 - 1u; r > a0; r--) {
+                const uint32_t g = 3u * r;
+                const cs b2 = ch.ang[g + 1u], b1 = ch.ang[g], b0 = ch.ang[g - 1u];  // angle at atom g+k+1
+                const cs t2 = ch.tor[g + 2u], t1 = ch.tor[g + 1u], t0 = ch.tor[g];  // torsion g+k
+                const f3 c = nerf_step(f, rc, FCZ_C_TO_N, b2, t2);
+                const f3 ca = nerf_step(f, c, FCZ_CA_TO_C, b1, t1);
+                rc = nerf_step(f, ca, FCZ_N_TO_CA, b0, t0);
+                float* o = ch.rev + 3u * g;
+                st3(o, rc); st3(o + 3, ca); st3(o + 6, c);
             }
+            (void)n;
             st3(sg + SEG_RF, f.bcn); st3(sg + SEG_RF + 3, f.nbc); st3(sg + SEG_RF + 6, f.n); st3(sg + SEG_RF + 9, rc);
         }
     }
     cx.sync();
+    cx.mark(9);  // D_PASSES
 
     // ---- phase 3: stitch.  Serial over segments (the only cross-segment dependency of the
     // reference, src/foldcomp.cpp:855-857: the blended tail of segment s seeds segment s+1).  Per
@@ -446,23 +483,28 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     // from the two frames, move the local tail, blend it with the stored anchor (weightedAverage,
     // src/atom_coordinate.cpp:145-163, last three atoms only).
     if (cx.tid == 0) {
-        const uint8_t* anc0 = blob + y.o_anchor;
-        f3 s0 = get_f3(anc0), s1 = get_f3(anc0 + 12), s2 = get_f3(anc0 + 24);
+        f3 s0 = ld3(ch.seg + SEG_A), s1 = ld3(ch.seg + SEG_A + 3), s2 = ld3(ch.seg + SEG_A + 6);
         for (int s = 0; s < n_seg; s++) {
             float* sg = ch.seg + s * FCZ_SEG_FLOATS;
             st3(sg + SEG_S, s0); st3(sg + SEG_S + 3, s1); st3(sg + SEG_S + 6, s2);
-            const uint32_t a0 = get_u32(blob + y.o_aidx + 4u * s), a1 = get_u32(blob + y.o_aidx + 4u * (s + 1));
-            const uint8_t* anc = blob + y.o_anchor + 36u * (s + 1);
-            const f3 e0 = get_f3(anc), e1 = get_f3(anc + 12), e2 = get_f3(anc + 24);
+            const uint32_t a0 = seg_a0(sg), a1 = seg_a1(sg);
+            const float* anc = sg + FCZ_SEG_FLOATS + SEG_A;
+            // all inputs of this step first (independent of the serial chain), then the chain itself
+            const f3 e0 = ld3(anc), e1 = ld3(anc + 3), e2 = ld3(anc + 6);
+            const f3 l1 = ld3(sg + SEG_F), l2 = ld3(sg + SEG_F + 3), l3 = ld3(sg + SEG_F + 6), lo = ld3(sg + SEG_F + 9);
+            const f3 q0 = ld3(sg + SEG_TAIL), q1 = ld3(sg + SEG_TAIL + 3), q2 = ld3(sg + SEG_TAIL + 6);
+            const uint32_t t = 3u * a0;
+            const uint32_t tt = (a1 > a0) ? t : 0u;
+            const cs b0 = ch.ang[tt], b1 = ch.ang[tt + 1u], b2 = ch.ang[tt + 2u];
+            const cs w0 = ch.tor[tt], w1 = ch.tor[tt + 1u], w2 = ch.tor[tt + 2u];
+            const float l_nca = n_ca_len(rec[8u * a0] >> 3);
             f3 t0 = s0, t1 = s1, t2 = s2;  // forward tail in true coordinates
             if (a1 > a0) {
-                const uint32_t t = 3u * a0;
                 NerfFrame fa = frame_from(s0, s1, s2);
-                f3 n = nerf_step(fa, s2, FCZ_C_TO_N, ch.ang[t], ch.tor[t]);
-                f3 ca = nerf_step(fa, n, n_ca_len(rec[8u * a0] >> 3), ch.ang[t + 1u], ch.tor[t + 1u]);
-                f3 c = nerf_step(fa, ca, FCZ_CA_TO_C, ch.ang[t + 2u], ch.tor[t + 2u]);
-                const f3 l1 = ld3(sg + SEG_F), l2 = ld3(sg + SEG_F + 3), l3 = ld3(sg + SEG_F + 6), lo = ld3(sg + SEG_F + 9);
-                float* T = sg + SEG_T;
+                f3 n = nerf_step(fa, s2, FCZ_C_TO_N, b0, w0);
+                f3 ca = nerf_step(fa, n, l_nca, b1, w1);
+                f3 c = nerf_step(fa, ca, FCZ_CA_TO_C, b2, w2);
+                float T[12];
                 // R = bcn_a bcn_l^T + nbc_a nbc_l^T + n_a n_l^T ;  t = c_true - R c_local
                 T[0] = fma_(fa.n.x, l3.x, fma_(fa.nbc.x, l2.x, fa.bcn.x * l1.x));
                 T[1] = fma_(fa.n.x, l3.y, fma_(fa.nbc.x, l2.y, fa.bcn.x * l1.y));
@@ -476,12 +518,13 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
                 T[9] = c.x - fma_(T[2], lo.z, fma_(T[1], lo.y, T[0] * lo.x));
                 T[10] = c.y - fma_(T[5], lo.z, fma_(T[4], lo.y, T[3] * lo.x));
                 T[11] = c.z - fma_(T[8], lo.z, fma_(T[7], lo.y, T[6] * lo.x));
-                t0 = xform(T, ld3(sg + SEG_TAIL));
-                t1 = xform(T, ld3(sg + SEG_TAIL + 3));
-                t2 = xform(T, ld3(sg + SEG_TAIL + 6));
+                t0 = xform(T, q0);
+                t1 = xform(T, q1);
+                t2 = xform(T, q2);
+                for (int i = 0; i < 12; i++) sg[SEG_T + i] = T[i];
             }
             const float nf = (float)(3u * (a1 - a0 + 1u));  // atoms in the segment
-            const float inv = 1.0f / nf;
+            const float inv = sg[SEG_I + 2];
             s0 = blend(t0, e0, 3.0f, nf - 3.0f, inv);
             s1 = blend(t1, e1, 2.0f, nf - 2.0f, inv);
             s2 = blend(t2, e2, 1.0f, nf - 1.0f, inv);
@@ -491,6 +534,7 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
         st3(o, s0); st3(o + 3, s1); st3(o + 6, s2);
     }
     cx.sync();
+    cx.mark(10);  // D_STITCH
 
     // ---- phase 4: blend (weightedAverage, src/atom_coordinate.cpp:145-163).
     //  (a) one lane per segment finishes the reverse pass: atoms 2,1,0 need the bond angles at the true
@@ -499,10 +543,10 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     for (int s = cx.tid; s < n_seg; s += cx.nthr) {
         const float* sg = ch.seg + s * FCZ_SEG_FLOATS;
         const float* T = sg + SEG_T;
-        const uint32_t a0 = get_u32(blob + y.o_aidx + 4u * s), a1 = get_u32(blob + y.o_aidx + 4u * (s + 1));
+        const uint32_t a0 = seg_a0(sg), a1 = seg_a1(sg);
         if (a1 <= a0) continue;  // empty segment: nothing to emit (its three atoms belong to the next one)
         const int n = (int)(3u * (a1 - a0 + 1u));
-        const float inv = 1.0f / (float)n;
+        const float inv = sg[SEG_I + 2];
         NerfFrame f;
         f.bcn = ld3(sg + SEG_RF); f.nbc = ld3(sg + SEG_RF + 3); f.n = ld3(sg + SEG_RF + 6);
         f3 rc = ld3(sg + SEG_RF + 9);
@@ -523,17 +567,18 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     for (uint32_t g = 3u + cx.tid; g < 3u * L - 3u; g += cx.nthr) {
         const uint32_t r = g / 3u, k = g - 3u * r;
         const int s = ch.segid[r - 1u];  // residue r was placed while consuming record r-1
-        const uint32_t a0 = get_u32(blob + y.o_aidx + 4u * s), a1 = get_u32(blob + y.o_aidx + 4u * (s + 1));
+        const float* sg = ch.seg + s * FCZ_SEG_FLOATS;
+        const uint32_t a0 = seg_a0(sg), a1 = seg_a1(sg);
         if (r == a0 || r >= a1) {
             // first residue of the NEXT segment (emitted by (a)) -- or the chain's last residue (phase 3)
             continue;
         }
-        const float* T = ch.seg + s * FCZ_SEG_FLOATS + SEG_T;
         const int q = (int)(g - 3u * a0), n = (int)(3u * (a1 - a0 + 1u));
         float* slot = ch.out_xyz + 3u * (ch.aoff[r] + k);
-        st3(slot, blend(xform(T, ld3(slot)), ld3(ch.rev + 3u * g), (float)(n - q), (float)q, 1.0f / (float)n));
+        st3(slot, blend(xform(sg + SEG_T, ld3(slot)), ld3(ch.rev + 3u * g), (float)(n - q), (float)q, sg[SEG_I + 2]));
     }
     cx.sync();
+    cx.mark(11);  // D_BLEND
 
     // ---- phase 5: side chains, level-synchronous: level k places slot k of every residue that has
     // one (residues sorted by atom count, so the active ones are a prefix and warps stay full).
@@ -541,21 +586,30 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     // .continuize(byte), src/foldcomp.cpp:338-369.  Atoms are built in place in the output area:
     // predecessors of an atom always have lower slots in the same residue.
     {
-        const float mn = sc_min(), cf = sc_cont_f();
         const uint8_t* sc = blob + y.o_sc;
         uint32_t active = L;  // residues with more than k atoms
         for (uint32_t k = 3u; k < FCZ_MAX_ATOMS; k++) {
             active -= ch.bins[k];  // bins[k] = residues with exactly k atoms (bins[3] = UNK)
             if (active == 0u) break;
-            for (uint32_t i = cx.tid; i < active; i += cx.nthr) {
-                const uint32_t r = ch.order[i];
-                const unsigned code = rec[8u * r] >> 3;
-                const uint32_t a0 = ch.aoff[r];
-                float* R = ch.out_xyz + 3u * a0;
-                const unsigned pr = tb->pred[code][k];
-                const cs to = cossin_deg(continuize(sc[a0 - 3u * r + k - 3u], mn, cf));
-                st3(R + 3u * k, place_from(ld3(R + 3u * (pr & 15u)), ld3(R + 3u * ((pr >> 4) & 15u)),
-                                           ld3(R + 3u * ((pr >> 8) & 15u)), tb->blen[code][k], tb->bang[code][k], to));
+            // two residues per thread per trip: their placements are independent, which doubles the
+            // instruction-level parallelism of this latency-bound level
+            for (uint32_t i = cx.tid; i < active; i += 2u * cx.nthr) {
+                const uint32_t i2 = i + cx.nthr;
+                const bool two = i2 < active;
+                const uint32_t rA = ch.order[i], rB = ch.order[two ? i2 : i];
+                const unsigned cA = rec[8u * rA] >> 3, cB = rec[8u * rB] >> 3;
+                const uint32_t oA = ch.aoff[rA], oB = ch.aoff[rB];
+                float* RA = ch.out_xyz + 3u * oA;
+                float* RB = ch.out_xyz + 3u * oB;
+                const unsigned pA = tb->pred[cA][k], pB = tb->pred[cB][k];
+                const cs tA = tb->sc_tor[sc[oA - 3u * rA + k - 3u]];  // 256 possible torsions: table lookup
+                const cs tB = tb->sc_tor[sc[oB - 3u * rB + k - 3u]];
+                const f3 vA = place_from(ld3(RA + 3u * (pA & 15u)), ld3(RA + 3u * ((pA >> 4) & 15u)), ld3(RA + 3u * ((pA >> 8) & 15u)),
+                                         tb->blen[cA][k], tb->bang[cA][k], tA);
+                const f3 vB = place_from(ld3(RB + 3u * (pB & 15u)), ld3(RB + 3u * ((pB >> 4) & 15u)), ld3(RB + 3u * ((pB >> 8) & 15u)),
+                                         tb->blen[cB][k], tb->bang[cB][k], tB);
+                st3(RA + 3u * k, vA);
+                if (two) st3(RB + 3u * k, vB);
             }
             cx.sync();
         }
@@ -571,6 +625,7 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
         }
     }
     cx.sync();
+    cx.mark(12);  // D_SIDE
 }
 
 }  // namespace fcz

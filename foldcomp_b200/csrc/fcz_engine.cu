@@ -43,8 +43,8 @@ struct TierCfg {
 // last staged tier is smaller.  The last tier keeps chain data in global memory.
 // Caps are chosen at the occupancy steps of the per-residue shared-memory footprint (encode ~172 B/residue,
 // decode ~240 B/residue): 350-residue chains run 3 CTAs/SM in encode and 2 CTAs/SM in decode.
-static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 296, 408, 632, 1280, 2800};
-static const uint32_t kDecTierRes[FCZ_NTIER] = {64, 128, 192, 272, 432, 896, 2800};
+static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 296, 408, 632, 1280, 2720};
+static const uint32_t kDecTierRes[FCZ_NTIER] = {64, 128, 184, 256, 416, 864, 2720};
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
@@ -80,7 +80,7 @@ __host__ __device__ inline DecSmem dec_smem(const TierCfg& t) {
     s.o_segid = o; o += align16(t.max_res);
     s.o_tor = o;  o += align16(24u * t.max_res);
     s.o_ang = o;  o += align16(24u * t.max_res);
-    s.o_seg = o;  o += align16(4u * FCZ_SEG_FLOATS * t.max_seg);
+    s.o_seg = o;  o += align16(4u * FCZ_SEG_FLOATS * (t.max_seg + 1u));
     s.o_rev = o;  o += t.staged ? align16(36u * t.max_res) : 0u;  // large tier: reverse atoms live in global scratch
     s.o_blob = o; o += t.staged ? align16(t.max_blob) + 32u : 0u;
     s.o_out = o;  o += t.staged ? align16(12u * t.max_atoms) + 32u : 0u;
@@ -101,7 +101,7 @@ static TierCfg make_tier(uint32_t max_res, bool staged) {
         t.max_atoms = 10u * max_res;
         t.max_blob = 0xFFFFFFFFu;
         t.max_seg = 254u;
-        t.threads = 512u;
+        t.threads = 256u;
     }
     t.smem = 0;
     return t;
@@ -150,8 +150,29 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+#ifdef FCZ_PHASE_TIMING
+// Debug build only (libfcz_engine_timing.so): cycles spent between phase marks, summed over chains.
+// ids: 0-3 encode phases, 4 encode stage/copy-out, 8-12 decode phases, 13 decode stage-in, 14 decode copy-out
+__device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long g_phase_count[16];
+#endif
+
 struct DevCtx {
     int tid, nthr, lane, warp, nwarps;
+    static constexpr int wsize = 32;
+#ifdef FCZ_PHASE_TIMING
+    long long t_last;
+    __device__ __forceinline__ void mark(int id) {
+        if (tid == 0) {
+            long long t = clock64();
+            atomicAdd(&g_phase_cycles[id], (unsigned long long)(t - t_last));
+            atomicAdd(&g_phase_count[id], 1ull);
+            t_last = t;
+        }
+    }
+#else
+    __device__ __forceinline__ void mark(int) {}
+#endif
     uint32_t* wsum;   // [32] warp sums for the block scan
     uint64_t* bar;    // staging mbarrier
     uint32_t parity;  // its current phase
@@ -319,7 +340,7 @@ __global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* 
     }
 }
 
-__global__ void __launch_bounds__(512) k_encode(EncArgs a) {
+__global__ void __launch_bounds__(256, 3) k_encode(EncArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncSmem so = enc_smem(a.cfg);
     Tables* tb = reinterpret_cast<Tables*>(smem + so.o_tab);
@@ -344,6 +365,9 @@ __global__ void __launch_bounds__(512) k_encode(EncArgs a) {
         __syncthreads();
         const uint32_t t = *s_ticket;
         if (t >= count) break;
+#ifdef FCZ_PHASE_TIMING
+        cx.t_last = clock64();
+#endif
         const uint32_t c = a.list[t];
         const uint32_t r0 = a.res_off[c], L = a.res_off[c + 1] - r0;
         const uint64_t a0 = a.atom_off[c];
@@ -378,9 +402,22 @@ __global__ void __launch_bounds__(512) k_encode(EncArgs a) {
             ch.B = gdst;
             cx.staged = false;
         }
-        encode_chain(cx, tb, ch);
+        __builtin_assume(__isShared(tb));
+        __builtin_assume(__isShared(ch.aoff));
+        __builtin_assume(__isShared(ch.ares));
+        __builtin_assume(__isShared(ch.ang));
+        __builtin_assume(__isShared(ch.red));
+        if (a.cfg.staged) {
+            __builtin_assume(__isShared(ch.X));
+            __builtin_assume(__isShared(ch.type));
+            __builtin_assume(__isShared(ch.B));
+            encode_chain(cx, tb, ch);
+        } else {
+            encode_chain(cx, tb, ch);
+        }
         if (a.cfg.staged) {
             copy_out(cx, gdst, sB, size);
+            cx.mark(4);
             cx.parity ^= 1u;
             cx.staged = false;
         }
@@ -469,7 +506,7 @@ __global__ void k_dec_plan(uint32_t n, const uint64_t* blob_off, const uint8_t* 
     }
 }
 
-__global__ void __launch_bounds__(512) k_decode(DecArgs a) {
+__global__ void __launch_bounds__(256, 2) k_decode(DecArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const DecSmem so = dec_smem(a.cfg);
     Tables* tb = reinterpret_cast<Tables*>(smem + so.o_tab);
@@ -493,6 +530,9 @@ __global__ void __launch_bounds__(512) k_decode(DecArgs a) {
         __syncthreads();
         const uint32_t t = *s_ticket;
         if (t >= count) break;
+#ifdef FCZ_PHASE_TIMING
+        cx.t_last = clock64();
+#endif
         const uint32_t c = a.list[t];
         const uint64_t b0 = a.blob_off[c];
         const uint32_t blen = (uint32_t)(a.blob_off[c + 1] - b0);
@@ -523,15 +563,33 @@ __global__ void __launch_bounds__(512) k_decode(DecArgs a) {
             ch.out_xyz = reinterpret_cast<float*>(sout);
             cx.stage_wait();
             __syncthreads();
+            cx.mark(13);
         } else {
             ch.blob = gblob;
             ch.out_xyz = gout;
         }
         const uint8_t* hb = ch.blob;
         ch.y = make_layout(get_u16(hb + OFF_NRES), get_u32(hb + OFF_NSC), get_u32(hb + OFF_LENTITLE), hb[OFF_NANCHOR]);
-        decode_chain(cx, tb, ch);
+        // the workspace is always shared memory; tell the compiler so it emits LDS/STS instead of generic LD/ST
+        __builtin_assume(__isShared(tb));
+        __builtin_assume(__isShared(ch.aoff));
+        __builtin_assume(__isShared(ch.tor));
+        __builtin_assume(__isShared(ch.ang));
+        __builtin_assume(__isShared(ch.seg));
+        __builtin_assume(__isShared(ch.order));
+        __builtin_assume(__isShared(ch.segid));
+        __builtin_assume(__isShared(ch.bins));
+        if (a.cfg.staged) {
+            __builtin_assume(__isShared(ch.blob));
+            __builtin_assume(__isShared(ch.out_xyz));
+            __builtin_assume(__isShared(ch.rev));
+            decode_chain(cx, tb, ch);
+        } else {
+            decode_chain(cx, tb, ch);
+        }
         if (a.cfg.staged) {
             copy_out(cx, reinterpret_cast<uint8_t*>(gout), sout, 12u * A);
+            cx.mark(14);
             cx.parity ^= 1u;
             cx.staged = false;
         }
@@ -808,6 +866,19 @@ int fcz_engine_sync(fcz_engine* e) {
 }
 
 uint64_t fcz_engine_launch_count(const fcz_engine* e) { return e ? e->launches : 0; }
+
+#ifdef FCZ_PHASE_TIMING
+// debug-only export: out[0..15] cycles, out[16..31] counts; resets the counters
+int fcz_debug_phase_cycles(fcz_engine* e, unsigned long long* out) {
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16));
+    CK(cudaMemcpyFromSymbol(out + 16, g_phase_count, sizeof(unsigned long long) * 16));
+    unsigned long long z[16] = {0};
+    CK(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z));
+    CK(cudaMemcpyToSymbol(g_phase_count, z, sizeof z));
+    return FCZ_OK;
+}
+#endif
 
 int fcz_engine_set_profiling(fcz_engine* e, int enabled) {
     if (!e) return FCZ_E_ARG;

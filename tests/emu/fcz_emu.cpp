@@ -12,8 +12,9 @@
 using namespace fcz;
 
 struct HostCtx {
-    int tid = 0, nthr = 1, lane = 0, warp = 0, nwarps = 1;
+    int tid = 0, nthr = 1, lane = 0, warp = 0, nwarps = 1, wsize = 1;
     void sync() {}
+    void mark(int) {}
     void stage_wait() {}
     uint32_t excl_scan(uint32_t) { return 0; }
     uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
@@ -64,7 +65,7 @@ int emu_decode_chain(const uint8_t* blob, uint64_t len, int use_alt, uint8_t* re
     if (y.size > len || L < 2 || y.n_anchor < 2) return FCZ_E_TRUNCATED;
     std::vector<uint32_t> aoff(L + 1);
     std::vector<cs> tor(3 * (size_t)L), ang(3 * (size_t)L);
-    std::vector<float> seg((size_t)(y.n_anchor - 1) * FCZ_SEG_FLOATS);
+    std::vector<float> seg((size_t)y.n_anchor * FCZ_SEG_FLOATS);
     std::vector<uint16_t> order(L);
     std::vector<float> rev(9 * (size_t)L);
     std::vector<uint8_t> segid(L);
