@@ -313,9 +313,11 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     e2e_value = world * n_res * args.steps / (float(ms_e.item()) * 1e-3)
     assert not hout.status.any() and np.array_equal(hout.res_type, batch.res_type)
-    off_bytes = 16 * (batch.n_chains + 1)
-    h2d = 12 * n_atoms + 5 * n_res + n_title + 20 * batch.n_chains + off_bytes + fcz_bytes + 8 * (batch.n_chains + 1)
-    d2h = fcz_bytes + 8 * (batch.n_chains + 1) + 4 * batch.n_chains + 12 * n_atoms + 5 * n_res + n_title + 20 * batch.n_chains + off_bytes + 4 * batch.n_chains
+    nc = batch.n_chains
+    # bytes the host-pointer path moves per step (foldcomp_b200/csrc/fcz_engine.cu: encode_host / decode_host)
+    h2d = (12 * n_atoms + 5 * n_res + n_title + 20 * nc + 16 * (nc + 1) + 8 * (nc + 1) + 4 * nc) \
+        + (fcz_bytes + 24 * (nc + 1) + 8 * nc)
+    d2h = fcz_bytes + (12 * n_atoms + 5 * n_res + n_title + 20 * nc + 4 * nc)
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None

@@ -265,7 +265,8 @@ struct EncArgs {
     const uint64_t* blob_off;
     uint8_t* bytes;
     const uint32_t* list;   // chains of this tier
-    const uint32_t* count;  // their number
+    const uint32_t* count;  // their number (device-planned batches) ...
+    uint32_t count_val;     // ... or by value when count == nullptr (host-planned batches)
     uint32_t* ticket;
     const Tables* tables;
     int32_t b;
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(256, 3) k_encode(EncArgs a) {
     }
     if (cx.tid == 0) mbar_init(bar, 1);
     __syncthreads();
-    const uint32_t count = *a.count;
+    const uint32_t count = a.count ? *a.count : a.count_val;
     for (;;) {
         if (cx.tid == 0) *s_ticket = atomicAdd(a.ticket, 1u);
         __syncthreads();
@@ -440,6 +441,8 @@ struct DecArgs {
     fcz_chain_meta* meta;
     const uint32_t* list;
     const uint32_t* count;
+    uint32_t count_val;
+    const int32_t* status;  // host-planned batches: chains flagged by the validation pass are skipped
     uint32_t* ticket;
     const Tables* tables;
     int32_t use_alt;
@@ -449,11 +452,14 @@ struct DecArgs {
 
 // Plan: one warp per blob.  Validates the header (Foldcomp::read, src/foldcomp.cpp:904-924 and the
 // count checks of checkValidity, 1492-1561), sums the decoded atom count, picks the tier.
-__global__ void k_dec_plan(uint32_t n, const uint64_t* blob_off, const uint8_t* bytes, const Tables* tb, TierTable tt,
-                           PlanOut po) {
-    const uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// validate_only: host-planned batches -- chains [c0, n) are checked, only po.status is written (and only
+// for chains the host has not already rejected).
+__global__ void k_dec_plan(uint32_t c0, uint32_t n, const uint64_t* blob_off, const uint8_t* bytes, const Tables* tb, TierTable tt,
+                           PlanOut po, int validate_only) {
+    const uint32_t c = c0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= n) return;
+    if (validate_only && po.status[c] != FCZ_OK) return;
     const uint8_t* blob = bytes + blob_off[c];
     const uint64_t len = blob_off[c + 1] - blob_off[c];
     int status = FCZ_OK;
@@ -496,6 +502,10 @@ __global__ void k_dec_plan(uint32_t n, const uint64_t* blob_off, const uint8_t* 
         }
     }
     if (status != FCZ_OK) { L = 0; A = 0; T = 0; }
+    if (validate_only) {
+        if (lane == 0 && status != FCZ_OK) po.status[c] = status;
+        return;
+    }
     if (lane == 0) {
         po.v0[c] = L; po.v1[c] = A; po.v2[c] = T;
         po.status[c] = status;
@@ -524,7 +534,7 @@ __global__ void __launch_bounds__(256, 2) k_decode(DecArgs a) {
     }
     if (cx.tid == 0) mbar_init(bar, 1);
     __syncthreads();
-    const uint32_t count = *a.count;
+    const uint32_t count = a.count ? *a.count : a.count_val;
     for (;;) {
         if (cx.tid == 0) *s_ticket = atomicAdd(a.ticket, 1u);
         __syncthreads();
@@ -534,6 +544,7 @@ __global__ void __launch_bounds__(256, 2) k_decode(DecArgs a) {
         cx.t_last = clock64();
 #endif
         const uint32_t c = a.list[t];
+        if (a.status && a.status[c] != FCZ_OK) { __syncthreads(); continue; }
         const uint64_t b0 = a.blob_off[c];
         const uint32_t blen = (uint32_t)(a.blob_off[c + 1] - b0);
         const uint32_t r0 = a.res_off[c];
@@ -692,6 +703,8 @@ struct fcz_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined host-memory path
+    std::vector<cudaEvent_t> ev_pool;              // events of that path, reused across calls
     fcz_opts opts;
     int num_sms = 148;
     TierCfg enc_tier[FCZ_NTIER], dec_tier[FCZ_NTIER];
@@ -705,6 +718,16 @@ struct fcz_engine {
     uint64_t* h_totals = nullptr;
     // staging for host-memory batches
     DevBuf d_res_off, d_atom_off, d_title_off, d_res_type, d_bfactor, d_xyz, d_titles, d_meta, d_blob_off, d_bytes, d_status;
+    DevBuf d_list, d_tickets;
+    // plan made on the host by fcz_decode_plan(host) for the following fcz_decode_batch(host)
+    struct Launch { uint32_t chunk, tier, first, count; };
+    struct HostPlan {
+        uint32_t n = 0;
+        std::vector<uint32_t> chunk_c0;   // [nchunks+1] chain ranges
+        std::vector<uint32_t> list;       // chains grouped by (chunk, tier)
+        std::vector<Launch> launches;
+        std::vector<int32_t> status;
+    } hplan;
     uint64_t launches = 0;
     // optional per-kernel event timing
     bool profiling = false;
@@ -780,6 +803,8 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     }
     make_tiers(e->enc_tier, e->dec_tier);
     bool ok = true;
+    ok &= cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) == cudaSuccess;
+    ok &= cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < FCZ_NTIER; i++) {
         if (e->enc_tier[i].smem > 227u * 1024u || e->dec_tier[i].smem > 227u * 1024u) {
             fprintf(stderr, "fcz_engine_create: tier %d needs %u / %u bytes of shared memory (> 227 KB)\n", i,
@@ -818,7 +843,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->status, &e->tier_list, &e->partial, &e->large_scratch, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
-                      &e->d_blob_off, &e->d_bytes, &e->d_status};
+                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (e->d_tables) cudaFree(e->d_tables);
@@ -828,6 +853,9 @@ void fcz_engine_destroy(fcz_engine* e) {
     if (e->h_totals) cudaFreeHost(e->h_totals);
     for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto ev : e->free_events) cudaEventDestroy(ev);
+    for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -1003,6 +1031,7 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
         a.blob_off = out->blob_off; a.bytes = out->bytes;
         a.list = (uint32_t*)e->tier_list.p + (size_t)i * n;
         a.count = e->d_counters + i;
+        a.count_val = 0;
         a.ticket = e->d_counters + FCZ_NTIER + i;
         a.tables = e->d_tables;
         a.b = e->opts.anchor_threshold;
@@ -1016,6 +1045,346 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
         e->launches++;
     }
     CK(cudaGetLastError());
+    return FCZ_OK;
+}
+
+
+// ------------------------------------------------------------------- pipelined host-memory path
+// Host batches are planned ON THE HOST (sizes, offsets, tiers: the offset arrays are host memory
+// anyway) and processed in chunks so that the H2D copy of chunk k+1, the kernels of chunk k and the
+// D2H copy of chunk k-1 overlap on three streams (PCIe is full duplex; the kernels hide behind it).
+
+static int host_pick_tier(const TierCfg* tiers, uint32_t L, uint64_t A, uint64_t blob, uint32_t nseg) {
+    for (int i = 0; i < FCZ_NTIER; i++) {
+        const TierCfg& t = tiers[i];
+        if (L <= t.max_res && A <= t.max_atoms && blob <= t.max_blob && nseg <= t.max_seg) return i;
+    }
+    return -1;
+}
+
+static cudaEvent_t pool_event(fcz_engine* e, size_t i) {
+    while (e->ev_pool.size() <= i) {
+        cudaEvent_t ev = nullptr;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        e->ev_pool.push_back(ev);
+    }
+    return e->ev_pool[i];
+}
+
+// chain ranges of ~equal payload; chunk_c0 has nchunks+1 entries
+static void make_chunks(uint32_t n, const uint64_t* weight_prefix /* [n+1] */, std::vector<uint32_t>& chunk_c0) {
+    const uint64_t total = weight_prefix[n] - weight_prefix[0];
+    uint32_t nchunks = (uint32_t)(total / (24ull << 20)) + 1u;  // ~24 MB of payload per chunk
+    if (nchunks > 16u) nchunks = 16u;
+    if (nchunks > n) nchunks = n ? n : 1u;
+    chunk_c0.assign(1, 0u);
+    uint32_t c = 0;
+    for (uint32_t k = 1; k < nchunks; k++) {
+        const uint64_t target = weight_prefix[0] + total * k / nchunks;
+        while (c < n && weight_prefix[c] < target) c++;
+        if (c > chunk_c0.back()) chunk_c0.push_back(c);
+    }
+    chunk_c0.push_back(n);
+}
+
+// group chains by (chunk, tier): fills plan.list and plan.launches from per-chain tiers (-1 = skipped)
+static void group_launches(fcz_engine::HostPlan& plan, const std::vector<int8_t>& tier) {
+    plan.list.clear();
+    plan.launches.clear();
+    const uint32_t nchunks = (uint32_t)plan.chunk_c0.size() - 1u;
+    for (uint32_t k = 0; k < nchunks; k++) {
+        for (int t = 0; t < FCZ_NTIER; t++) {
+            const uint32_t first = (uint32_t)plan.list.size();
+            for (uint32_t c = plan.chunk_c0[k]; c < plan.chunk_c0[k + 1]; c++)
+                if (tier[c] == t) plan.list.push_back(c);
+            const uint32_t cnt = (uint32_t)plan.list.size() - first;
+            if (cnt) plan.launches.push_back({k, (uint32_t)t, first, cnt});
+        }
+    }
+}
+
+#define COPY(dst, src, bytes, kind, st)                                                \
+    do {                                                                               \
+        if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, kind, st));                     \
+    } while (0)
+
+static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch* out) {
+    const uint32_t n = in->n_chains;
+    int rc;
+    const uint64_t n_res = in->res_off[n], n_atoms = in->atom_off[n], n_title = in->title_off[n];
+    const int32_t b = e->opts.anchor_threshold;
+    if ((rc = ensure(e, e->d_res_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_atom_off, 8ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_title_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_res_type, n_res + 16))) return rc;
+    if ((rc = ensure(e, e->d_bfactor, 4ull * n_res + 16))) return rc;
+    if ((rc = ensure(e, e->d_xyz, 12ull * n_atoms + 16))) return rc;
+    if ((rc = ensure(e, e->d_titles, n_title + 16))) return rc;
+    if ((rc = ensure(e, e->d_meta, sizeof(fcz_chain_meta) * (uint64_t)n + 16))) return rc;
+    if ((rc = ensure(e, e->d_blob_off, 8ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_list, 4ull * n + 16))) return rc;
+    if ((rc = ensure(e, e->d_tickets, 4ull * 16 * FCZ_NTIER))) return rc;
+
+    fcz_engine::HostPlan plan;
+    plan.n = n;
+    make_chunks(n, in->atom_off, plan.chunk_c0);
+    const uint32_t nchunks = (uint32_t)plan.chunk_c0.size() - 1u;
+
+    // 1. start moving the inputs (copy stream), chunk by chunk
+    size_t evi = 0;
+    cudaEvent_t ev0 = pool_event(e, evi++);
+    CK(cudaEventRecord(ev0, e->stream));
+    CK(cudaStreamWaitEvent(e->s_in, ev0, 0));
+    CK(cudaStreamWaitEvent(e->s_out, ev0, 0));
+    COPY(e->d_res_off.p, in->res_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_atom_off.p, in->atom_off, 8ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_title_off.p, in->title_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_meta.p, in->meta, sizeof(fcz_chain_meta) * (uint64_t)n, cudaMemcpyHostToDevice, e->s_in);
+    std::vector<cudaEvent_t> ev_in(nchunks);
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t c0 = plan.chunk_c0[k], c1 = plan.chunk_c0[k + 1];
+        const uint64_t r0 = in->res_off[c0], r1 = in->res_off[c1], a0 = in->atom_off[c0], a1 = in->atom_off[c1];
+        const uint64_t t0 = in->title_off[c0], t1 = in->title_off[c1];
+        COPY((uint8_t*)e->d_res_type.p + r0, in->res_type + r0, r1 - r0, cudaMemcpyHostToDevice, e->s_in);
+        COPY((float*)e->d_bfactor.p + r0, in->bfactor + r0, 4ull * (r1 - r0), cudaMemcpyHostToDevice, e->s_in);
+        COPY((float*)e->d_xyz.p + 3ull * a0, in->xyz + 3ull * a0, 12ull * (a1 - a0), cudaMemcpyHostToDevice, e->s_in);
+        COPY((char*)e->d_titles.p + t0, in->titles + t0, t1 - t0, cudaMemcpyHostToDevice, e->s_in);
+        ev_in[k] = pool_event(e, evi++);
+        CK(cudaEventRecord(ev_in[k], e->s_in));
+    }
+
+    // 2. meanwhile plan on the host: validate (what k_enc_plan does on the device), sizes, offsets, tiers
+    uint8_t nat_lut[256];
+    for (int i = 0; i < 256; i++) nat_lut[i] = i < FCZ_NUM_CODES ? FCZ_NATOMS[i] : 0;
+    std::vector<int8_t> tier(n, -1);
+    plan.status.assign(n, FCZ_OK);
+    out->blob_off[0] = 0;
+    for (uint32_t c = 0; c < n; c++) {
+        const uint32_t r0 = in->res_off[c], L = in->res_off[c + 1] - r0;
+        const uint64_t A = in->atom_off[c + 1] - in->atom_off[c];
+        const uint32_t T = in->title_off[c + 1] - in->title_off[c];
+        int st = FCZ_OK;
+        uint64_t size = 0;
+        uint32_t sum = 0, bad = 0;
+        const uint8_t* rt = in->res_type + r0;
+        for (uint32_t r = 0; r < L; r++) { const uint32_t na = nat_lut[rt[r]]; sum += na; bad |= (na == 0u); }
+        if (L < 2u || L > 65535u || b < 1) st = FCZ_E_LIMIT;
+        else if (bad) st = FCZ_E_RESIDUE;
+        else if ((uint64_t)sum != A) st = FCZ_E_ARG;
+        else {
+            const int na = anchor_count(L, b);
+            if (na > 255) st = FCZ_E_LIMIT;
+            else {
+                size = make_layout(L, sum - 3u * L, T, (uint32_t)na).size;
+                const int t = host_pick_tier(e->enc_tier, L, sum, size, (uint32_t)na - 1u);
+                if (t < 0) { st = FCZ_E_LIMIT; size = 0; }
+                else tier[c] = (int8_t)t;
+            }
+        }
+        plan.status[c] = st;
+        if (out->status) out->status[c] = st;
+        out->blob_off[c + 1] = out->blob_off[c] + size;
+    }
+    const uint64_t total = out->blob_off[n];
+    if (total > out->bytes_cap) {
+        cudaStreamSynchronize(e->s_in);
+        return fail(e, FCZ_E_CAPACITY, "encode needs %llu bytes, capacity %llu", (unsigned long long)total,
+                    (unsigned long long)out->bytes_cap);
+    }
+    if ((rc = ensure(e, e->d_bytes, total + 64))) return rc;
+    group_launches(plan, tier);
+    COPY(e->d_blob_off.p, out->blob_off, 8ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_list.p, plan.list.data(), 4ull * plan.list.size(), cudaMemcpyHostToDevice, e->s_in);
+    cudaEvent_t ev_plan = pool_event(e, evi++);
+    CK(cudaEventRecord(ev_plan, e->s_in));
+    CK(cudaMemsetAsync(e->d_tickets.p, 0, 4ull * 16 * FCZ_NTIER, e->stream));
+    CK(cudaStreamWaitEvent(e->stream, ev_plan, 0));
+
+    // 3. kernels per chunk (main stream) and the blobs back (out stream)
+    size_t li = 0;
+    for (uint32_t k = 0; k < nchunks; k++) {
+        CK(cudaStreamWaitEvent(e->stream, ev_in[k], 0));
+        for (; li < plan.launches.size() && plan.launches[li].chunk == k; li++) {
+            const fcz_engine::Launch& ln = plan.launches[li];
+            EncArgs a;
+            a.res_off = (uint32_t*)e->d_res_off.p; a.atom_off = (uint64_t*)e->d_atom_off.p; a.title_off = (uint32_t*)e->d_title_off.p;
+            a.res_type = (uint8_t*)e->d_res_type.p; a.bfactor = (float*)e->d_bfactor.p; a.xyz = (float*)e->d_xyz.p;
+            a.titles = (char*)e->d_titles.p; a.meta = (fcz_chain_meta*)e->d_meta.p;
+            a.blob_off = (uint64_t*)e->d_blob_off.p; a.bytes = (uint8_t*)e->d_bytes.p;
+            a.list = (uint32_t*)e->d_list.p + ln.first;
+            a.count = nullptr; a.count_val = ln.count;
+            a.ticket = (uint32_t*)e->d_tickets.p + k * FCZ_NTIER + ln.tier;
+            a.tables = e->d_tables; a.b = b; a.cfg = e->enc_tier[ln.tier];
+            uint32_t grid = (uint32_t)(e->num_sms * e->enc_occ[ln.tier]);
+            if (grid > ln.count) grid = ln.count;
+            {
+                ProfSpan ps(e, 0);
+                k_encode<<<grid, a.cfg.threads, a.cfg.smem, e->stream>>>(a);
+            }
+            e->launches++;
+        }
+        cudaEvent_t ev_k = pool_event(e, evi++);
+        CK(cudaEventRecord(ev_k, e->stream));
+        CK(cudaStreamWaitEvent(e->s_out, ev_k, 0));
+        const uint64_t b0 = out->blob_off[plan.chunk_c0[k]], b1 = out->blob_off[plan.chunk_c0[k + 1]];
+        COPY(out->bytes + b0, (uint8_t*)e->d_bytes.p + b0, b1 - b0, cudaMemcpyDeviceToHost, e->s_out);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->s_out));
+    CK(cudaStreamSynchronize(e->stream));
+    return FCZ_OK;
+}
+
+// Blob headers are parsed on the host (Foldcomp::read, src/foldcomp.cpp:904-924): sizes, offsets, tiers.
+// The per-residue checks (codes, anchors, side-chain count) run on the device before the decode kernels.
+static int decode_plan_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out, fcz_sizes* totals) {
+    const uint32_t n = in->n_chains;
+    fcz_engine::HostPlan& plan = e->hplan;
+    plan.n = n;
+    plan.status.assign(n, FCZ_OK);
+    std::vector<int8_t> tier(n, -1);
+    out->res_off[0] = 0; out->atom_off[0] = 0; out->title_off[0] = 0;
+    for (uint32_t c = 0; c < n; c++) {
+        const uint8_t* blob = in->bytes + in->blob_off[c];
+        const uint64_t len = in->blob_off[c + 1] - in->blob_off[c];
+        int st = FCZ_OK;
+        uint32_t L = 0, T = 0;
+        uint64_t A = 0;
+        if (len < HDR_BYTES || memcmp(blob, "FCMP", 4) != 0) st = FCZ_E_MAGIC;
+        else {
+            L = get_u16(blob + OFF_NRES);
+            T = get_u32(blob + OFF_LENTITLE);
+            const uint32_t nsc = get_u32(blob + OFF_NSC), na = blob[OFF_NANCHOR];
+            const Layout y = make_layout(L, nsc, T, na);
+            if (L < 2u || na < 2u || (uint64_t)T > len || (uint64_t)nsc > len || (uint64_t)y.size > len) st = FCZ_E_TRUNCATED;
+            else {
+                A = (uint64_t)nsc + 3ull * L;  // = sum of table atoms when the blob is consistent (checked on the device)
+                const int t = host_pick_tier(e->dec_tier, L, A, y.size, na - 1u);
+                if (t < 0) st = FCZ_E_LIMIT;
+                else tier[c] = (int8_t)t;
+            }
+        }
+        if (st != FCZ_OK) { L = 0; A = 0; T = 0; }
+        plan.status[c] = st;
+        if (out->status) out->status[c] = st;
+        out->res_off[c + 1] = out->res_off[c] + L;
+        out->atom_off[c + 1] = out->atom_off[c] + A;
+        out->title_off[c + 1] = out->title_off[c] + T;
+    }
+    make_chunks(n, out->atom_off, plan.chunk_c0);
+    group_launches(plan, tier);
+    totals->n_res = out->res_off[n];
+    totals->n_atoms = out->atom_off[n];
+    totals->n_title_bytes = out->title_off[n];
+    totals->n_blob_bytes = in->blob_off[n];
+    return FCZ_OK;
+}
+
+static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out) {
+    const uint32_t n = in->n_chains;
+    fcz_engine::HostPlan& plan = e->hplan;
+    if (plan.n != n || plan.chunk_c0.empty()) return fail(e, FCZ_E_ARG, "fcz_decode_batch(host) needs a preceding fcz_decode_plan on the same batch");
+    int rc;
+    const uint64_t n_res = out->res_off[n], n_atoms = out->atom_off[n], n_title = out->title_off[n], n_bytes = in->blob_off[n];
+    if (n_res > out->res_cap || n_atoms > out->atom_cap || (out->titles && n_title > out->title_cap))
+        return fail(e, FCZ_E_CAPACITY, "decode output capacity too small");
+    if ((rc = ensure(e, e->d_blob_off, 8ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_bytes, n_bytes + 64))) return rc;
+    if ((rc = ensure(e, e->d_res_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_atom_off, 8ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_title_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_status, 4ull * n + 4))) return rc;
+    if ((rc = ensure(e, e->d_res_type, n_res + 16))) return rc;
+    if ((rc = ensure(e, e->d_bfactor, 4ull * n_res + 16))) return rc;
+    if ((rc = ensure(e, e->d_xyz, 12ull * n_atoms + 16))) return rc;
+    if ((rc = ensure(e, e->d_titles, n_title + 16))) return rc;
+    if ((rc = ensure(e, e->d_meta, sizeof(fcz_chain_meta) * (uint64_t)n + 16))) return rc;
+    if ((rc = ensure(e, e->d_list, 4ull * n + 16))) return rc;
+    if ((rc = ensure(e, e->d_tickets, 4ull * 16 * FCZ_NTIER))) return rc;
+    const uint32_t nchunks = (uint32_t)plan.chunk_c0.size() - 1u;
+    uint32_t max_grid_large = 0;
+    for (auto& ln : plan.launches)
+        if (!e->dec_tier[ln.tier].staged) {
+            uint32_t g = (uint32_t)(e->num_sms * e->dec_occ[ln.tier]);
+            if (g > ln.count) g = ln.count;
+            if (g > max_grid_large) max_grid_large = g;
+        }
+    if (max_grid_large && (rc = ensure(e, e->large_scratch, (size_t)max_grid_large * 36u * e->dec_tier[FCZ_NTIER - 1].max_res))) return rc;
+
+    size_t evi = 0;
+    cudaEvent_t ev0 = pool_event(e, evi++);
+    CK(cudaEventRecord(ev0, e->stream));
+    CK(cudaStreamWaitEvent(e->s_in, ev0, 0));
+    CK(cudaStreamWaitEvent(e->s_out, ev0, 0));
+    COPY(e->d_blob_off.p, in->blob_off, 8ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_res_off.p, out->res_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_atom_off.p, out->atom_off, 8ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_title_off.p, out->title_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_status.p, plan.status.data(), 4ull * n, cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_list.p, plan.list.data(), 4ull * plan.list.size(), cudaMemcpyHostToDevice, e->s_in);
+    std::vector<cudaEvent_t> ev_in(nchunks);
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint64_t b0 = in->blob_off[plan.chunk_c0[k]], b1 = in->blob_off[plan.chunk_c0[k + 1]];
+        COPY((uint8_t*)e->d_bytes.p + b0, in->bytes + b0, b1 - b0, cudaMemcpyHostToDevice, e->s_in);
+        ev_in[k] = pool_event(e, evi++);
+        CK(cudaEventRecord(ev_in[k], e->s_in));
+    }
+    CK(cudaMemsetAsync(e->d_tickets.p, 0, 4ull * 16 * FCZ_NTIER, e->stream));
+    TierTable tt;
+    for (int i = 0; i < FCZ_NTIER; i++) tt.t[i] = e->dec_tier[i];
+    PlanOut po;
+    memset(&po, 0, sizeof po);
+    po.status = (int32_t*)e->d_status.p;
+    size_t li = 0;
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t c0 = plan.chunk_c0[k], c1 = plan.chunk_c0[k + 1];
+        CK(cudaStreamWaitEvent(e->stream, ev_in[k], 0));
+        if (c1 > c0) {
+            k_dec_plan<<<(c1 - c0 + 7) / 8, 256, 0, e->stream>>>(c0, c1, (uint64_t*)e->d_blob_off.p, (uint8_t*)e->d_bytes.p, e->d_tables, tt, po, 1);
+            e->launches++;
+        }
+        for (; li < plan.launches.size() && plan.launches[li].chunk == k; li++) {
+            const fcz_engine::Launch& ln = plan.launches[li];
+            DecArgs a;
+            a.blob_off = (uint64_t*)e->d_blob_off.p; a.bytes = (uint8_t*)e->d_bytes.p;
+            a.res_off = (uint32_t*)e->d_res_off.p; a.atom_off = (uint64_t*)e->d_atom_off.p; a.title_off = (uint32_t*)e->d_title_off.p;
+            a.res_type = (uint8_t*)e->d_res_type.p; a.bfactor = (float*)e->d_bfactor.p; a.xyz = (float*)e->d_xyz.p;
+            a.titles = out->titles ? (char*)e->d_titles.p : nullptr; a.meta = (fcz_chain_meta*)e->d_meta.p;
+            a.list = (uint32_t*)e->d_list.p + ln.first;
+            a.count = nullptr; a.count_val = ln.count;
+            a.status = (int32_t*)e->d_status.p;
+            a.ticket = (uint32_t*)e->d_tickets.p + k * FCZ_NTIER + ln.tier;
+            a.tables = e->d_tables; a.use_alt = e->opts.use_alt_atom_order;
+            a.large_scratch = (float*)e->large_scratch.p;
+            a.cfg = e->dec_tier[ln.tier];
+            uint32_t grid = (uint32_t)(e->num_sms * e->dec_occ[ln.tier]);
+            if (grid > ln.count) grid = ln.count;
+            {
+                ProfSpan ps(e, 1);
+                k_decode<<<grid, a.cfg.threads, a.cfg.smem, e->stream>>>(a);
+            }
+            e->launches++;
+        }
+        cudaEvent_t ev_k = pool_event(e, evi++);
+        CK(cudaEventRecord(ev_k, e->stream));
+        CK(cudaStreamWaitEvent(e->s_out, ev_k, 0));
+        const uint64_t r0 = out->res_off[c0], r1 = out->res_off[c1], a0 = out->atom_off[c0], a1 = out->atom_off[c1];
+        const uint64_t t0 = out->title_off[c0], t1 = out->title_off[c1];
+        COPY(out->xyz + 3ull * a0, (float*)e->d_xyz.p + 3ull * a0, 12ull * (a1 - a0), cudaMemcpyDeviceToHost, e->s_out);
+        COPY(out->res_type + r0, (uint8_t*)e->d_res_type.p + r0, r1 - r0, cudaMemcpyDeviceToHost, e->s_out);
+        COPY(out->bfactor + r0, (float*)e->d_bfactor.p + r0, 4ull * (r1 - r0), cudaMemcpyDeviceToHost, e->s_out);
+        if (out->titles) COPY(out->titles + t0, (char*)e->d_titles.p + t0, t1 - t0, cudaMemcpyDeviceToHost, e->s_out);
+        COPY(out->meta + c0, (fcz_chain_meta*)e->d_meta.p + c0, sizeof(fcz_chain_meta) * (uint64_t)(c1 - c0), cudaMemcpyDeviceToHost, e->s_out);
+    }
+    if (out->status) {
+        cudaEvent_t ev_done = pool_event(e, evi++);
+        CK(cudaEventRecord(ev_done, e->stream));
+        CK(cudaStreamWaitEvent(e->s_out, ev_done, 0));
+        COPY(out->status, e->d_status.p, 4ull * n, cudaMemcpyDeviceToHost, e->s_out);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->s_out));
+    CK(cudaStreamSynchronize(e->stream));
     return FCZ_OK;
 }
 
@@ -1033,39 +1402,7 @@ extern "C" int fcz_encode_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_bl
     const uint32_t n = in->n_chains;
     uint64_t total = 0;
     if (in->mem == FCZ_MEM_DEVICE) return encode_device(e, in, out, &total);
-    // host batch: copy in, run, copy out
-    int rc;
-    const uint64_t n_res = in->res_off[n], n_atoms = in->atom_off[n], n_title = in->title_off[n];
-    H2D(e->d_res_off, in->res_off, 4ull * (n + 1));
-    H2D(e->d_atom_off, in->atom_off, 8ull * (n + 1));
-    H2D(e->d_title_off, in->title_off, 4ull * (n + 1));
-    H2D(e->d_res_type, in->res_type, n_res);
-    H2D(e->d_bfactor, in->bfactor, 4ull * n_res);
-    H2D(e->d_xyz, in->xyz, 12ull * n_atoms);
-    H2D(e->d_titles, in->titles, n_title);
-    H2D(e->d_meta, in->meta, sizeof(fcz_chain_meta) * (uint64_t)n);
-    const uint64_t bound = fcz_encode_bound(n, n_res, n_atoms, n_title, e->opts.anchor_threshold);
-    if ((rc = ensure(e, e->d_bytes, bound + 64))) return rc;
-    if ((rc = ensure(e, e->d_blob_off, 8ull * (n + 1)))) return rc;
-    if ((rc = ensure(e, e->d_status, 4ull * n + 4))) return rc;
-    fcz_chain_batch din = *in;
-    din.mem = FCZ_MEM_DEVICE;
-    din.res_off = (uint32_t*)e->d_res_off.p; din.atom_off = (uint64_t*)e->d_atom_off.p;
-    din.title_off = (uint32_t*)e->d_title_off.p; din.res_type = (uint8_t*)e->d_res_type.p;
-    din.bfactor = (float*)e->d_bfactor.p; din.xyz = (float*)e->d_xyz.p; din.titles = (char*)e->d_titles.p;
-    din.meta = (fcz_chain_meta*)e->d_meta.p;
-    fcz_blob_batch dout;
-    dout.n_chains = n; dout.mem = FCZ_MEM_DEVICE;
-    dout.blob_off = (uint64_t*)e->d_blob_off.p; dout.bytes = (uint8_t*)e->d_bytes.p;
-    dout.status = (int32_t*)e->d_status.p; dout.bytes_cap = bound + 64;
-    if ((rc = encode_device(e, &din, &dout, &total))) return rc;
-    if (total > out->bytes_cap) return fail(e, FCZ_E_CAPACITY, "encode needs %llu bytes, capacity %llu",
-                                            (unsigned long long)total, (unsigned long long)out->bytes_cap);
-    CK(cudaMemcpyAsync(out->blob_off, dout.blob_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
-    if (total) CK(cudaMemcpyAsync(out->bytes, dout.bytes, total, cudaMemcpyDeviceToHost, e->stream));
-    if (out->status && n) CK(cudaMemcpyAsync(out->status, dout.status, 4ull * n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    return FCZ_OK;
+    return encode_host(e, in, out);
 }
 
 // ------------------------------------------------------------------------------------------- decode
@@ -1082,7 +1419,7 @@ static int decode_plan_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain
     po.tier_count = e->d_counters;
     po.tier_list = (uint32_t*)e->tier_list.p;
     if (n) {
-        k_dec_plan<<<(n + 7) / 8, 256, 0, e->stream>>>(n, in->blob_off, in->bytes, e->d_tables, tt, po);
+        k_dec_plan<<<(n + 7) / 8, 256, 0, e->stream>>>(0u, n, in->blob_off, in->bytes, e->d_tables, tt, po, 0);
         e->launches++;
     }
     ScanArgs sa;
@@ -1116,6 +1453,8 @@ static int decode_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batc
         a.res_type = out->res_type; a.bfactor = out->bfactor; a.xyz = out->xyz; a.titles = out->titles; a.meta = out->meta;
         a.list = (uint32_t*)e->tier_list.p + (size_t)i * n;
         a.count = e->d_counters + i;
+        a.count_val = 0;
+        a.status = nullptr;
         a.ticket = e->d_counters + FCZ_NTIER + i;
         a.tables = e->d_tables;
         a.use_alt = e->opts.use_alt_atom_order;
@@ -1149,27 +1488,8 @@ extern "C" int fcz_decode_plan(fcz_engine* e, const fcz_blob_batch* in, fcz_chai
         rc = decode_plan_device(e, in, out, totals);
         return rc;
     }
-    const uint64_t nbytes = in->blob_off[n];
-    H2D(e->d_blob_off, in->blob_off, 8ull * (n + 1));
-    H2D(e->d_bytes, in->bytes, nbytes);
-    if ((rc = ensure(e, e->d_res_off, 4ull * (n + 1)))) return rc;
-    if ((rc = ensure(e, e->d_atom_off, 8ull * (n + 1)))) return rc;
-    if ((rc = ensure(e, e->d_title_off, 4ull * (n + 1)))) return rc;
-    if ((rc = ensure(e, e->d_status, 4ull * n + 4))) return rc;
-    fcz_blob_batch din = *in;
-    din.mem = FCZ_MEM_DEVICE; din.blob_off = (uint64_t*)e->d_blob_off.p; din.bytes = (uint8_t*)e->d_bytes.p;
-    fcz_chain_batch dout = *out;
-    dout.mem = FCZ_MEM_DEVICE;
-    dout.res_off = (uint32_t*)e->d_res_off.p; dout.atom_off = (uint64_t*)e->d_atom_off.p;
-    dout.title_off = (uint32_t*)e->d_title_off.p; dout.status = (int32_t*)e->d_status.p;
-    if ((rc = decode_plan_device(e, &din, &dout, totals))) return rc;
-    totals->n_blob_bytes = nbytes;
-    CK(cudaMemcpyAsync(out->res_off, dout.res_off, 4ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(out->atom_off, dout.atom_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(out->title_off, dout.title_off, 4ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
-    if (out->status && n) CK(cudaMemcpyAsync(out->status, dout.status, 4ull * n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    return FCZ_OK;
+    (void)rc;
+    return decode_plan_host(e, in, out, totals);
 }
 
 extern "C" int fcz_decode_batch(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out) {
@@ -1179,32 +1499,6 @@ extern "C" int fcz_decode_batch(fcz_engine* e, const fcz_blob_batch* in, fcz_cha
     const uint32_t n = in->n_chains;
     int rc;
     if (in->mem == FCZ_MEM_DEVICE) return decode_device(e, in, out);
-    // host batch: blobs and offsets are still resident from fcz_decode_plan on this engine
-    const uint64_t n_res = out->res_off[n], n_atoms = out->atom_off[n], n_title = out->title_off[n];
-    if (n_res > out->res_cap || n_atoms > out->atom_cap || (out->titles && n_title > out->title_cap))
-        return fail(e, FCZ_E_CAPACITY, "decode output capacity too small");
-    if ((rc = ensure(e, e->d_res_type, n_res + 16))) return rc;
-    if ((rc = ensure(e, e->d_bfactor, 4ull * n_res + 16))) return rc;
-    if ((rc = ensure(e, e->d_xyz, 12ull * n_atoms + 16))) return rc;
-    if ((rc = ensure(e, e->d_titles, n_title + 16))) return rc;
-    if ((rc = ensure(e, e->d_meta, sizeof(fcz_chain_meta) * (uint64_t)n + 16))) return rc;
-    fcz_blob_batch din = *in;
-    din.mem = FCZ_MEM_DEVICE; din.blob_off = (uint64_t*)e->d_blob_off.p; din.bytes = (uint8_t*)e->d_bytes.p;
-    fcz_chain_batch dout = *out;
-    dout.mem = FCZ_MEM_DEVICE;
-    dout.res_off = (uint32_t*)e->d_res_off.p; dout.atom_off = (uint64_t*)e->d_atom_off.p;
-    dout.title_off = (uint32_t*)e->d_title_off.p; dout.res_type = (uint8_t*)e->d_res_type.p;
-    dout.bfactor = (float*)e->d_bfactor.p; dout.xyz = (float*)e->d_xyz.p;
-    dout.titles = out->titles ? (char*)e->d_titles.p : nullptr;
-    dout.meta = (fcz_chain_meta*)e->d_meta.p; dout.status = (int32_t*)e->d_status.p;
-    if ((rc = decode_device(e, &din, &dout))) return rc;
-    if (n_res) {
-        CK(cudaMemcpyAsync(out->res_type, dout.res_type, n_res, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaMemcpyAsync(out->bfactor, dout.bfactor, 4ull * n_res, cudaMemcpyDeviceToHost, e->stream));
-    }
-    if (n_atoms) CK(cudaMemcpyAsync(out->xyz, dout.xyz, 12ull * n_atoms, cudaMemcpyDeviceToHost, e->stream));
-    if (out->titles && n_title) CK(cudaMemcpyAsync(out->titles, dout.titles, n_title, cudaMemcpyDeviceToHost, e->stream));
-    if (n) CK(cudaMemcpyAsync(out->meta, dout.meta, sizeof(fcz_chain_meta) * (uint64_t)n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    return FCZ_OK;
+    (void)n; (void)rc;
+    return decode_host(e, in, out);
 }
