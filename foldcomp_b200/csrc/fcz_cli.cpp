@@ -1,0 +1,105 @@
+// foldcomp_b200/csrc/fcz_cli.cpp -- minimal `compress` / `decompress` front end over FoldcompGpu, shaped
+// like the per-entry lambdas of the reference CLI (src/main.cpp:438-536, 612-689): one single-chain PDB
+// file <-> one .fcz file.  ATOM records are read with the fixed columns the reference's CPython module
+// uses (foldcomp/foldcomp.cxx:253-293) and written like writeAtomCoordinatesToPDB
+// (src/atom_coordinate.cpp:220-291).  Host text I/O only; the codec runs on the GPU.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "foldcomp_gpu.h"
+
+using namespace fczgpu;
+
+static std::string trim(const std::string& s) {
+    size_t a = s.find_first_not_of(" \t"), b = s.find_last_not_of(" \t");
+    return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+}
+
+static int read_pdb(const std::string& path, std::vector<AtomCoordinate>& atoms) {
+    std::ifstream f(path);
+    if (!f) return 1;
+    std::string line, chain;
+    while (std::getline(f, line)) {
+        if (line.compare(0, 4, "ATOM") != 0 || line.size() < 66) continue;
+        if (chain.empty()) chain = line.substr(21, 1);
+        if (line.substr(21, 1) != chain) return 2;  // multiple chains (foldcomp.cxx:266-268)
+        AtomCoordinate a;
+        a.atom = trim(line.substr(12, 4)); a.residue = trim(line.substr(17, 3)); a.chain = chain;
+        a.atom_index = std::stoi(line.substr(6, 5)); a.residue_index = std::stoi(line.substr(22, 4));
+        a.coordinate.x = std::stof(line.substr(30, 8)); a.coordinate.y = std::stof(line.substr(38, 8));
+        a.coordinate.z = std::stof(line.substr(46, 8));
+        a.occupancy = std::stof(line.substr(54, 6)); a.tempFactor = std::stof(line.substr(60, 6));
+        if (!atoms.empty() && atoms.back().atom == a.atom) continue;  // removeAlternativePosition
+        atoms.push_back(a);
+    }
+    return atoms.empty() ? 1 : 0;
+}
+
+static void write_pdb(std::ostream& os, const std::vector<AtomCoordinate>& atoms, const std::string& title) {
+    char buf[128];
+    if (!title.empty()) { snprintf(buf, sizeof buf, "TITLE     %.70s\n", title.c_str()); os << buf; }
+    for (size_t i = 0; i < atoms.size(); i++) {
+        const AtomCoordinate& a = atoms[i];
+        char name[8];
+        if (a.atom.size() == 4) snprintf(name, sizeof name, "%-4s", a.atom.c_str());
+        else snprintf(name, sizeof name, " %-3s", a.atom.c_str());
+        snprintf(buf, sizeof buf, "ATOM  %5d %s %3s %s%4d    %8.3f%8.3f%8.3f  1.00%6.2f          %2c  \n", a.atom_index, name,
+                 a.residue.c_str(), a.chain.c_str(), a.residue_index, a.coordinate.x, a.coordinate.y, a.coordinate.z, a.tempFactor,
+                 a.atom[0]);
+        os << buf;
+    }
+    if (!atoms.empty()) {
+        const AtomCoordinate& a = atoms.back();
+        snprintf(buf, sizeof buf, "TER   %5d      %3s %s%4d\n", a.atom_index + 1, a.residue.c_str(), a.chain.c_str(), a.residue_index);
+        os << buf;
+    }
+}
+
+int main(int argc, char** argv) {
+    if (argc < 4) {
+        fprintf(stderr, "usage: fcz_cli compress [-b N] in.pdb out.fcz | decompress [-a] in.fcz out.pdb\n");
+        return 2;
+    }
+    const std::string mode = argv[1];
+    int ai = 2, b = 25;
+    bool alt = false;
+    while (ai < argc && argv[ai][0] == '-') {
+        if (!strcmp(argv[ai], "-b") && ai + 1 < argc) { b = atoi(argv[ai + 1]); ai += 2; }
+        else if (!strcmp(argv[ai], "-a")) { alt = true; ai++; }
+        else break;
+    }
+    if (ai + 2 > argc) return 2;
+    const std::string in = argv[ai], out = argv[ai + 1];
+    try {
+        Engine eng(0);
+        FoldcompGpu comp(eng);
+        if (mode == "compress") {
+            std::vector<AtomCoordinate> atoms;
+            int rc = read_pdb(in, atoms);
+            if (rc) { fprintf(stderr, "[Error] %s\n", rc == 2 ? "multiple chains" : "no atoms found"); return 1; }
+            std::string base = out.substr(out.find_last_of('/') == std::string::npos ? 0 : out.find_last_of('/') + 1);
+            comp.strTitle = base.substr(0, base.find_last_of('.'));  // main.cpp:451-465: output basename without extension
+            comp.anchorThreshold = b;
+            if ((rc = comp.compress(atoms))) { fprintf(stderr, "[Error] compress: %s\n", fcz_strerror(rc)); return 1; }
+            std::ofstream os(out, std::ios::binary);
+            comp.writeStream(os);
+        } else if (mode == "decompress") {
+            std::ifstream is(in, std::ios::binary);
+            if (!is || comp.read(is) != 0) { fprintf(stderr, "[Error] not an FCZ file\n"); return 1; }
+            comp.useAltAtomOrder = alt;
+            std::vector<AtomCoordinate> atoms;
+            int rc = comp.decompress(atoms);
+            if (rc) { fprintf(stderr, "[Error] decompress: %s\n", fcz_strerror(rc)); return 1; }
+            std::ofstream os(out);
+            write_pdb(os, atoms, comp.strTitle);
+        } else return 2;
+    } catch (const std::exception& ex) {
+        fprintf(stderr, "[Error] %s\n", ex.what());
+        return 1;
+    }
+    return 0;
+}
