@@ -17,6 +17,8 @@
 #ifndef FCZ_CODEC_H
 #define FCZ_CODEC_H
 
+#include <string.h>
+
 #include "../../include/fcz_engine.h"
 #include "fcz_format.h"
 
@@ -28,14 +30,70 @@ struct Tables {
     uint8_t name1[FCZ_NUM_CODES];  // one-letter codes (header firstResidue / lastResidue)
     uint8_t alt[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
     uint16_t pred[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
+    // side-chain byte as a step function of cos(torsion) (see build_tables), both tables increasing:
+    // non-negated torsion: byte = 127 + #{i: -c >= sc_pos[i]};  negated torsion: byte = #{i: c >= sc_neg[i]}
+    float sc_pos[128];
+    float sc_neg[128];
     float blen[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
     cs bang[FCZ_NUM_CODES][FCZ_MAX_ATOMS];  // (cos, sin) of the table bond angle
     cs sc_tor[256];  // (cos, sin) of every side-chain torsion byte: FixedAngleDiscretizer(255).continuize(b)
 };
 
+// The side-chain byte the reference stores for a torsion whose cosine is the float c
+// (src/torsion_angle.cpp:70-92, src/discretizer.cpp:55-57 via src/foldcomp.cpp:532-538), host libm.
+inline unsigned sc_byte_of_cos(float c, bool neg) {
+    double ac = acos((double)c);
+    float t = (ac != ac) ? ((c < 0) ? 180.0f : 0.0f) : (float)(ac * 180.0 / M_PI);
+    if (neg) t = -t;
+    return disc_trunc(t, sc_min(), sc_disc_f()) & 0xFFu;
+}
+inline float float_from_ordered(int32_t k) {  // monotone bijection int32 <-> float (excluding NaN)
+    uint32_t u = k >= 0 ? (uint32_t)k : ~((uint32_t)k) ^ 0x80000000u;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+inline int32_t ordered_from_float(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? (int32_t)~(u ^ 0x80000000u) : (int32_t)u;
+}
+
 // Filled on the host with host libm: the table angles are compile-time constants of the format,
 // so their (cos,sin) are computed once, exactly as cossin_deg would.
 inline void build_tables(Tables* t) {
+    // Side-chain thresholds in cos-space.  The byte is a monotone step function of the float c (acos is
+    // strictly monotone at float-input granularity, every later step is monotone), so each step's boundary
+    // is found by bisection over the floats in [-2, 2] (|c| > 1 takes the reference's NaN branch).
+    {
+        const int64_t lo0 = ordered_from_float(-2.0f), hi0 = ordered_from_float(2.0f);
+        for (int i = 0; i < 128; i++) {
+            // non-negated torsion: byte >= 128+i holds for small c; find the LARGEST such c
+            const unsigned j = 128u + (unsigned)i;
+            if (sc_byte_of_cos(-2.0f, false) < j) t->sc_pos[i] = 3.0f;
+            else if (sc_byte_of_cos(2.0f, false) >= j) t->sc_pos[i] = -3.0f;
+            else {
+                int64_t lo = lo0, hi = hi0;  // predicate true at lo, false at hi
+                while (hi - lo > 1) {
+                    int64_t mid = lo + (hi - lo) / 2;
+                    if (sc_byte_of_cos(float_from_ordered((int32_t)mid), false) >= j) lo = mid; else hi = mid;
+                }
+                t->sc_pos[i] = -float_from_ordered((int32_t)lo);
+            }
+            // negated torsion: byte >= 1+i holds for large c; find the SMALLEST such c
+            const unsigned jn = 1u + (unsigned)i;
+            if (i == 127 || sc_byte_of_cos(2.0f, true) < jn) t->sc_neg[i] = 3.0f;
+            else if (sc_byte_of_cos(-2.0f, true) >= jn) t->sc_neg[i] = -3.0f;
+            else {
+                int64_t lo = lo0, hi = hi0;  // predicate false at lo, true at hi
+                while (hi - lo > 1) {
+                    int64_t mid = lo + (hi - lo) / 2;
+                    if (sc_byte_of_cos(float_from_ordered((int32_t)mid), true) >= jn) hi = mid; else lo = mid;
+                }
+                t->sc_neg[i] = float_from_ordered((int32_t)hi);
+            }
+        }
+    }
     for (int c = 0; c < FCZ_NUM_CODES; c++) {
         t->natoms[c] = FCZ_NATOMS[c];
         t->name1[c] = (uint8_t)FCZ_NAME1[c];
@@ -71,10 +129,41 @@ struct EncChain {
     uint8_t* B;              // blob destination (staged copy or global), Layout.size bytes
     // workspace
     uint32_t* aoff;          // [L+1] first atom of each residue, relative to the chain
-    uint16_t* ares;          // [A]   residue of each atom
+    uint16_t* sres;          // [A-3L] residue of each side-chain atom (= side-chain torsion)
     float* ang;              // [6*L] the six backbone arrays, header order, stride L
     float* red;              // [FCZ_RED_FLOATS(nwarps)]
 };
+
+// Side-chain byte from the parts of cos(torsion) and the torsion's sign (see encode_chain phase 2).
+// The count of thresholds <= z is found from a cheap estimate (a 4-term arccosine, good to 0.003 degrees,
+// run through the reference's own byte formula) corrected against the table, so it is exact whatever the
+// estimate's quality; the table lookup is certified against the error G of the single-precision cosine.
+FCZ_HD uint8_t sc_byte_fast(const Tables* tb, DotParts dp, bool neg) {
+    const float G = 5e-7f;  // > 4 ulp of a cosine: bound on |inner * rsqrt(p) - reference cosine|
+    float c = dp.inner * rsqrt_(dp.p);
+    const float* tz = neg ? tb->sc_neg : tb->sc_pos;
+    bool ok = dp.p >= 1e-30f && dp.p <= 1e30f;
+    int n = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        if (c != c) c = 2.0f;  // NaN cosine: the reference's acos is NaN and c < 0 is false -> 0 degrees
+        c = c > 2.0f ? 2.0f : (c < -2.0f ? -2.0f : c);  // |c| > 1 all take the NaN branch: the table spans [-2, 2]
+        const float z = neg ? c : -c;
+        // estimate (Abramowitz & Stegun 4.4.45): acos(x) ~ sqrt(1-x) (a0 + a1 x + a2 x^2 + a3 x^3), 0 <= x <= 1
+        const float x = fminf(fabsf(c), 1.0f);
+        float a = sqrtf(1.0f - x) * (1.5707288f + x * (-0.2121144f + x * (0.0742610f + x * -0.0187293f))) * 57.29578f;
+        if (c < 0.0f) a = 180.0f - a;
+        n = (int)(((neg ? -a : a) + 180.0f) * sc_disc_f()) - (neg ? 0 : 127);
+        n = n < 0 ? 0 : (n > 128 ? 128 : n);
+        while (n > 0 && !(z >= tz[n - 1])) n--;   // exact count of thresholds <= z (tables increase)
+        while (n < 128 && z >= tz[n]) n++;
+        if (ok && n > 0 && !(z - G >= tz[n - 1])) ok = false;
+        if (ok && n < 128 && !(z + G < tz[n])) ok = false;
+        if (ok) break;
+        c = cos_exact(dp);  // the reference's own sequence; the second pass needs no guard
+        ok = true;
+    }
+    return (uint8_t)(neg ? n : 127 + n);
+}
 
 FCZ_HD f3 bb_atom(const EncChain& ch, uint32_t j) {  // j-th backbone atom (N,CA,C = slots 0..2)
     uint32_t r = j / 3u, k = j - 3u * r;
@@ -88,7 +177,7 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
     const Layout y = make_layout(L, A - 3u * L, ch.title_len, (uint32_t)n_anchor);
     uint8_t* B = ch.B;
 
-    // ---- phase 1: residue -> first atom (exclusive scan of table atom counts), atom -> residue
+    // ---- phase 1: residue -> first atom (exclusive scan of table atom counts), side-chain atom -> residue
     {
         const uint32_t chunk = (L + cx.nthr - 1) / cx.nthr;
         uint32_t r0 = cx.tid * chunk; if (r0 > L) r0 = L;
@@ -99,7 +188,7 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
         for (uint32_t r = r0; r < r1; r++) {
             ch.aoff[r] = base;
             uint32_t n = tb->natoms[ch.type[r]];
-            for (uint32_t k = 0; k < n; k++) ch.ares[base + k] = (uint16_t)r;
+            for (uint32_t k = 3u; k < n; k++) ch.sres[base - 3u * r + (k - 3u)] = (uint16_t)r;
             base += n;
         }
         if (r1 == L) ch.aoff[L] = base;
@@ -108,76 +197,72 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
     cx.sync();
     cx.mark(0);  // E_SCAN
 
-    // ---- phases 2+3: ONE loop over all angle items of the chain so that the expensive double-precision
-    // tail (sqrt, divide, acos, *180/pi) exists once and runs with full warps:
-    //   items 0 .. A-1     one dihedral per atom.  Side-chain atoms (slot >= 3) give the side-chain byte
-    //                      (src/sidechain.cpp:149-168 + FixedAngleDiscretizer, src/foldcomp.cpp:532-538);
-    //                      backbone atom j = 3r+k gives backbone torsion j (src/torsion_angle.cpp:49-94):
-    //                      k=0 psi, 1 omega, 2 phi (src/foldcomp.cpp:488-492);
-    //   items A .. A+3L-4  backbone bond angles at atoms m = 2 .. 3L-2 (src/nerf.cpp:495-508; split by
-    //                      index%3 at src/foldcomp.cpp:496-505: m%3==2 CA-C-N[m/3], 0 C-N-CA[m/3-1],
-    //                      1 N-CA-C[m/3-1]).
-    // The arithmetic of each item is exactly dihedral_deg / bond_angle_deg of fcz_math.h.
+    // ---- phase 2: side-chain bytes, one dihedral per side-chain atom (src/sidechain.cpp:149-168 +
+    // FixedAngleDiscretizer, src/foldcomp.cpp:532-538).  The stored byte is a monotone step function of
+    // cos(torsion), so it is read off a 128-entry threshold table in cos-space (Tables::sc_pos/sc_neg, built
+    // with the host's libm exactly as the reference evaluates it): no acos at all.  The cosine itself is
+    // first taken in single precision (inner * rsqrt(p), within 4 ulp of the reference's float); only when
+    // that lands within the error of a threshold is the reference's exact double sqrt/divide evaluated.
     {
-        const float mn = sc_min(), df = sc_disc_f();
+        const uint32_t S = A - 3u * L;
+        for (uint32_t t = cx.tid; t < S; t += cx.nthr) {
+            const uint32_t r = ch.sres[t];
+            const uint32_t a0 = ch.aoff[r];
+            const uint32_t k = 3u + (t - (a0 - 3u * r));
+            const uint32_t w = a0 + k;
+            const unsigned pr = tb->pred[ch.type[r]][k];
+            const f3 p0 = ld3(ch.X + 3u * (a0 + (pr & 15u))), p1 = ld3(ch.X + 3u * (a0 + ((pr >> 4) & 15u)));
+            const f3 p2 = ld3(ch.X + 3u * (a0 + ((pr >> 8) & 15u))), p3 = ld3(ch.X + 3u * w);
+            const f3 d1 = sub3(p1, p0), d2 = sub3(p2, p1), d3 = sub3(p3, p2);
+            const f3 u1 = cross3(d1, d2), u2 = cross3(d2, d3);
+            const f3 pb = cross3(u2, d2);  // torsion_angle.cpp:87-92
+            const bool neg = (u1.x * pb.x) + (u1.y * pb.y) + (u1.z * pb.z) < 0;
+            B[y.o_sc + t] = sc_byte_fast(tb, dot_parts(u1, u2), neg);
+        }
+    }
+    cx.mark(1);  // E_SIDE (no barrier: timing only)
+    // ---- phase 3: backbone torsions j = 0 .. 3L-4 (src/torsion_angle.cpp:49-94; j%3 = 0 psi, 1 omega,
+    // 2 phi of residue j/3, src/foldcomp.cpp:488-492) and bond angles at backbone atoms m = 2 .. 3L-2
+    // (src/nerf.cpp:495-508; m%3 = 2 CA-C-N[m/3], 0 C-N-CA[m/3-1], 1 N-CA-C[m/3-1], src/foldcomp.cpp:496-505)
+    // in ONE loop, so that the double-precision tail (cosine, acos, degrees) exists once.
+    {
         const uint32_t nT = 3u * L - 3u;
-        const uint32_t W = A + nT;
-        for (uint32_t w = cx.tid; w < W; w += cx.nthr) {
-            f3 v1, v2;          // the two vectors whose angle is taken
-            bool neg = false;   // dihedral sign
-            bool valid = true;
-            int kind;           // 0 side-chain byte, 1 backbone torsion, 2 bond angle
-            uint32_t dst;       // destination index (byte offset in B, or index into ch.ang)
-            if (w < A) {
-                const uint32_t r = ch.ares[w];
-                const uint32_t a0 = ch.aoff[r];
-                const uint32_t k = w - a0;
-                uint32_t i0, i1, i2, i3;
-                if (k >= 3u) {
-                    const unsigned pr = tb->pred[ch.type[r]][k];
-                    i0 = a0 + (pr & 15u); i1 = a0 + ((pr >> 4) & 15u); i2 = a0 + ((pr >> 8) & 15u); i3 = w;
-                    kind = 0;
-                    dst = y.o_sc + (w - 3u * (r + 1u));
-                } else {
-                    const uint32_t j = 3u * r + k;
-                    valid = j < nT;
-                    const uint32_t a1 = valid ? ch.aoff[r + 1u] : a0;
-                    // backbone atoms j .. j+3 = (r,k) (r,k+1) ... wrapping into residue r+1
-                    i0 = a0 + k;
-                    i1 = (k < 2u) ? a0 + k + 1u : a1;
-                    i2 = (k < 1u) ? a0 + 2u : a1 + (k - 1u);
-                    i3 = a1 + k;
-                    kind = 1;
-                    dst = (k == 0u ? (uint32_t)A_PSI : (k == 1u ? (uint32_t)A_OMEGA : (uint32_t)A_PHI)) * L + r;
-                }
+        for (uint32_t w = cx.tid; w < 2u * nT; w += cx.nthr) {
+            f3 v1, v2;
+            bool neg = false;
+            const bool is_tor = w < nT;
+            uint32_t dst;
+            if (is_tor) {
+                const uint32_t r = w / 3u, k = w - 3u * r;
+                const uint32_t a0 = ch.aoff[r], a1 = ch.aoff[r + 1u];
+                // backbone atoms j .. j+3 = (r,k) (r,k+1) ... wrapping into residue r+1
+                const uint32_t i0 = a0 + k, i1 = (k < 2u) ? a0 + k + 1u : a1, i2 = (k < 1u) ? a0 + 2u : a1 + (k - 1u), i3 = a1 + k;
                 const f3 p0 = ld3(ch.X + 3u * i0), p1 = ld3(ch.X + 3u * i1), p2 = ld3(ch.X + 3u * i2), p3 = ld3(ch.X + 3u * i3);
                 const f3 d1 = sub3(p1, p0), d2 = sub3(p2, p1), d3 = sub3(p3, p2);
                 v1 = cross3(d1, d2);
                 v2 = cross3(d2, d3);
-                const f3 pb = cross3(v2, d2);  // torsion_angle.cpp:87-92
+                const f3 pb = cross3(v2, d2);
                 neg = (v1.x * pb.x) + (v1.y * pb.y) + (v1.z * pb.z) < 0;
+                dst = (k == 0u ? (uint32_t)A_PSI : (k == 1u ? (uint32_t)A_OMEGA : (uint32_t)A_PHI)) * L + r;
             } else {
-                const uint32_t m = 2u + (w - A);
+                const uint32_t m = 2u + (w - nT);
                 const uint32_t q = m / 3u, k = m - 3u * q;
                 const f3 pm = bb_atom(ch, m);
                 v1 = sub3(bb_atom(ch, m - 1u), pm);
                 v2 = sub3(bb_atom(ch, m + 1u), pm);
-                kind = 2;
                 dst = (k == 2u) ? (uint32_t)A_CACN * L + q : (k == 0u ? (uint32_t)A_CNCA * L + q - 1u : (uint32_t)A_NCAC * L + q - 1u);
             }
-            const float c = cos_theta(v1, v2);
+            const float c = cos_ref(dot_parts(v1, v2));
             const double ac = acos((double)c);
-            float deg = (float)(ac * 180.0 / M_PI);
-            if (kind != 2) {
+            float deg = deg_ref(ac);
+            if (is_tor) {
                 if (ac != ac) deg = (c < 0) ? 180.0f : 0.0f;  // torsion_angle.cpp:74-79
                 if (neg) deg = -deg;
             }
-            if (kind == 0) B[dst] = (uint8_t)disc_trunc(deg, mn, df);
-            else if (valid) ch.ang[dst] = deg;
+            ch.ang[dst] = deg;
         }
     }
     cx.sync();
-    cx.mark(1);  // E_ANGLES
 
     // ---- phase 4: min / max of the six arrays (L-1 values) and of the B-factors (L values)
     // (Discretizer::Discretizer, src/discretizer.cpp:22-33)

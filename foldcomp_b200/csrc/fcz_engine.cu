@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256, 3) k_encode(EncArgs a) {
         ch.title = a.titles + t0;
         ch.meta = a.meta + c;
         ch.aoff = reinterpret_cast<uint32_t*>(smem + so.o_aoff);
-        ch.ares = reinterpret_cast<uint16_t*>(smem + so.o_ares);
+        ch.sres = reinterpret_cast<uint16_t*>(smem + so.o_ares);
         ch.ang = reinterpret_cast<float*>(smem + so.o_ang);
         ch.red = reinterpret_cast<float*>(smem + so.o_red);
         uint8_t* gdst = a.bytes + b0;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256, 3) k_encode(EncArgs a) {
         }
         __builtin_assume(__isShared(tb));
         __builtin_assume(__isShared(ch.aoff));
-        __builtin_assume(__isShared(ch.ares));
+        __builtin_assume(__isShared(ch.sres));
         __builtin_assume(__isShared(ch.ang));
         __builtin_assume(__isShared(ch.red));
         if (a.cfg.staged) {

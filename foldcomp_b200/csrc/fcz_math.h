@@ -56,6 +56,51 @@ FCZ_HD float cos_theta(f3 v1, f3 v2) {
     return (float)((double)inner / sqrt((double)(s1 * s2)));
 }
 
+// ---- the same quantities, split so that the expensive double-precision steps can be CERTIFIED
+// shortcuts: a cheaper evaluation is used only when it provably rounds to the same float as the
+// reference's sequence; otherwise the reference's exact sequence runs.  Results are identical always.
+struct DotParts {
+    float inner, p;  // inner product and float product of the squared sizes, exactly as getCosineTheta forms them
+};
+FCZ_HD DotParts dot_parts(f3 v1, f3 v2) {
+    DotParts d;
+    d.inner = (v1.x * v2.x) + (v1.y * v2.y) + (v1.z * v2.z);
+    float s1 = v1.x * v1.x + v1.y * v1.y + v1.z * v1.z;
+    float s2 = v2.x * v2.x + v2.y * v2.y + v2.z * v2.z;
+    d.p = s1 * s2;
+    return d;
+}
+FCZ_HD float cos_exact(DotParts d) { return (float)((double)d.inner / sqrt((double)d.p)); }
+
+FCZ_HD double drsqrt_(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+// Both roundings of an interval [v(1-2^-46), v(1+2^-46)] agree  =>  every double in it rounds to that float.
+FCZ_HD bool same_float(double v, float* f) {
+    const float lo = (float)(v * (1.0 - 0x1p-46)), hi = (float)(v * (1.0 + 0x1p-46));
+    *f = lo;
+    return lo == hi;  // false for NaN
+}
+// cos(theta) as the reference rounds it.  Fast path: inner * rsqrt(p) in double is within 2^-50 (relative)
+// of the reference's RN(inner / RN(sqrt(p))) -- rsqrt <= 1 ulp, one multiply -- so if the whole 2^-46
+// interval around it rounds to one float, that float is the reference's.  Fails with probability ~2^-21.
+FCZ_HD float cos_ref(DotParts d) {
+    float c;
+    if (d.p >= 1e-30f && d.p <= 1e30f && same_float((double)d.inner * drsqrt_((double)d.p), &c)) return c;
+    return cos_exact(d);
+}
+// degrees of an arccosine as the reference rounds them: (float)(ac * 180.0 / M_PI) is within 2^-50.5 of
+// ac * RN(180/pi); certified the same way.
+FCZ_HD float deg_ref(double ac) {
+    float g;
+    if (same_float(ac * 57.29577951308232, &g)) return g;
+    return (float)(ac * 180.0 / M_PI);
+}
+
 // reference: angle, src/float3d.h:55-65 -- bond angle at a2 in degrees (double acos).
 FCZ_HD float bond_angle_deg(f3 a1, f3 a2, f3 a3) {
     float c = cos_theta(sub3(a1, a2), sub3(a3, a2));

@@ -50,7 +50,7 @@ int64_t emu_encode_chain(const uint8_t* res_type, uint32_t L, const float* xyz, 
     EncChain ch;
     ch.L = L; ch.A = A; ch.title_len = title_len; ch.b = b;
     ch.type = res_type; ch.bfac = bfac; ch.X = xyz; ch.title = title; ch.meta = meta; ch.B = out;
-    ch.aoff = aoff.data(); ch.ares = ares.data(); ch.ang = ang.data(); ch.red = red.data();
+    ch.aoff = aoff.data(); ch.sres = ares.data(); ch.ang = ang.data(); ch.red = red.data();
     HostCtx cx;
     encode_chain(cx, tb, ch);
     return y.size;
@@ -77,6 +77,36 @@ int emu_decode_chain(const uint8_t* blob, uint64_t len, int use_alt, uint8_t* re
     HostCtx cx;
     decode_chain(cx, tb, ch);
     return FCZ_OK;
+}
+
+// --- the certified shortcuts of the encode path, exposed for exhaustive comparison with the exact formulas
+void emu_sc_bytes(const float* inner, const float* p, const uint8_t* neg, uint32_t n, uint8_t* fast, uint8_t* exact) {
+    const Tables* tb = tables();
+    for (uint32_t i = 0; i < n; i++) {
+        DotParts d; d.inner = inner[i]; d.p = p[i];
+        fast[i] = sc_byte_fast(tb, d, neg[i] != 0);
+        exact[i] = (uint8_t)sc_byte_of_cos(cos_exact(d), neg[i] != 0);
+    }
+}
+void emu_thresholds(float* pos, float* neg) {
+    const Tables* tb = tables();
+    memcpy(pos, tb->sc_pos, sizeof tb->sc_pos);
+    memcpy(neg, tb->sc_neg, sizeof tb->sc_neg);
+}
+uint64_t emu_cos_deg_mismatches(const float* inner, const float* p, uint32_t n, uint64_t* fallbacks) {
+    uint64_t bad = 0, fb = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        DotParts d; d.inner = inner[i]; d.p = p[i];
+        const float ce = cos_exact(d), cr = cos_ref(d);
+        float tmp;
+        if (!(d.p >= 1e-30f && d.p <= 1e30f && same_float((double)d.inner * drsqrt_((double)d.p), &tmp))) fb++;
+        if (memcmp(&ce, &cr, 4) != 0 && !(ce != ce && cr != cr)) bad++;
+        const double ac = acos((double)ce);
+        const float de = (float)(ac * 180.0 / M_PI), dr = deg_ref(ac);
+        if (memcmp(&de, &dr, 4) != 0 && !(de != de && dr != dr)) bad++;
+    }
+    *fallbacks = fb;
+    return bad;
 }
 
 }  // extern "C"

@@ -21,7 +21,7 @@ f.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
 for it in range(3):
     eng.encode_device(db, bl); eng.decode_plan_device(bl, do); eng.decode_device(bl, do)
     f(eng.h, out)
-names = {0: "enc scan+stage wait", 1: "enc angle items", 2: "enc min/max", 3: "enc pack", 4: "enc copy-out", 8: "dec unpack", 9: "dec fwd/rev passes",
+names = {0: "enc scan+stage wait", 1: "enc side-chain bytes", 2: "enc backbone angles+min/max", 3: "enc pack", 4: "enc copy-out", 8: "dec unpack", 9: "dec fwd/rev passes",
          10: "dec stitch", 11: "dec blend", 12: "dec side chains", 13: "dec stage-in wait", 14: "dec copy-out"}
 for k in sorted(names):
     if out[16 + k]:
