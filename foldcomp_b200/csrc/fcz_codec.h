@@ -387,10 +387,8 @@ struct DecChain {
     cs* tor;              // [3(L-1)] (cos,sin) of psi,omega,phi per record
     cs* ang;              // [3(L-1)] (cos,sin) of CA-C-N, C-N-CA, N-CA-C per record
     float* seg;           // [n_anchor * FCZ_SEG_FLOATS]
-    uint16_t* order;      // [L] residues sorted by atom count, descending
     float* rev;           // [9L] reverse-pass backbone atoms (true coordinates)
     uint8_t* segid;       // [L] anchor segment that owns (emits) each residue
-    uint32_t* bins;       // [2*16] counting-sort bins
 };
 
 // y = R x + t, T = rows of R (9) then t (3)
@@ -417,14 +415,11 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     const int n_seg = (int)y.n_anchor - 1;
     const uint32_t nT = 3u * L - 3u;
 
-    // ---- phase 1: records -> residue codes, atom offsets (exclusive scan), residues sorted by atom
-    // count (for the level-synchronous side-chain pass), (cos,sin) of the continuised angles
+    // ---- phase 1: records -> residue codes, atom offsets (exclusive scan), (cos,sin) of the continuised angles
     // (convertBytesToBackboneChain src/foldcomp.cpp:60-77, decompressBackboneChain 122-153,
     // _continuize 155-158; the deg->rad and sincos of Nerf::place_atom src/nerf.cpp:63-70 are hoisted
     // here so the recurrences below carry no transcendental)
     {
-        for (uint32_t i = cx.tid; i < 32u; i += cx.nthr) ch.bins[i] = 0u;
-        cx.sync();
         float mins[6], cfs[6];
         for (int k = 0; k < 6; k++) {
             mins[k] = get_f32(blob + OFF_MINS + 4 * k);
@@ -435,26 +430,14 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
         uint32_t r1 = r0 + chunk; if (r1 > L) r1 = L;
         uint32_t sum = 0;
         for (uint32_t r = r0; r < r1; r++) {
-            uint32_t na = tb->natoms[rec[8u * r] >> 3];
-            sum += na;
-            cx.atomic_add(&ch.bins[na & 15u], 1u);
+            sum += tb->natoms[rec[8u * r] >> 3];
         }
-        uint32_t base = cx.excl_scan(sum);  // (block barrier inside: bins complete afterwards)
+        uint32_t base = cx.excl_scan(sum);
         for (uint32_t r = r0; r < r1; r++) {
             ch.aoff[r] = base;
             base += tb->natoms[rec[8u * r] >> 3];
         }
         if (r1 == L) ch.aoff[L] = base;
-        // bins[16+na] = first position of residues with `na` atoms in the descending order
-        if (cx.tid == 0) {
-            uint32_t pos = 0;
-            for (int na = 15; na >= 0; na--) { ch.bins[16 + na] = pos; pos += ch.bins[na]; }
-        }
-        cx.sync();
-        for (uint32_t r = r0; r < r1; r++) {
-            uint32_t na = tb->natoms[rec[8u * r] >> 3];
-            ch.order[cx.atomic_add(&ch.bins[16u + (na & 15u)], 1u)] = (uint16_t)r;
-        }
         const float tmin = get_f32(blob + y.o_temp), tcf = get_f32(blob + y.o_temp + 4);
         for (uint32_t r = cx.tid; r < L; r += cx.nthr) {
             Record q = unpack_record(rec + 8u * r);
@@ -514,7 +497,10 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     //   Bond lengths by atom kind, never the Pro length (src/nerf.h:37-43).  The last three reverse atoms
     //   depend on the true start atoms and are finished in phase 4.
     // (forward and reverse lanes sit in DIFFERENT warps: lanes of one warp would serialise the two loops)
+    // When all segments fit one warp (the common case) the stitch of phase 3 starts as soon as the forward
+    // lanes of warp 0 are done and overlaps with the reverse lanes running in warp 1.
     const int n_grp = (n_seg + cx.wsize - 1) / cx.wsize;
+    const bool fused = n_grp == 1 && cx.nwarps >= 2;
     for (int idx = cx.warp; idx < 2 * n_grp; idx += cx.nwarps) {
         const int s = (idx >> 1) * cx.wsize + cx.lane;
         if (s >= n_seg) continue;
@@ -559,8 +545,12 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
             st3(sg + SEG_RF, f.bcn); st3(sg + SEG_RF + 3, f.nbc); st3(sg + SEG_RF + 6, f.n); st3(sg + SEG_RF + 9, rc);
         }
     }
-    cx.sync();
-    cx.mark(9);  // D_PASSES
+    if (!fused) {
+        cx.sync();
+        cx.mark(9);  // D_PASSES
+    } else if (cx.warp == 0) {
+        cx.wsync();  // the forward lanes (all in warp 0) have published SEG_F / SEG_TAIL
+    }
 
     // ---- phase 3: stitch.  Serial over segments (the only cross-segment dependency of the
     // reference, src/foldcomp.cpp:855-857: the blended tail of segment s seeds segment s+1).  Per
@@ -665,39 +655,35 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     cx.sync();
     cx.mark(11);  // D_BLEND
 
-    // ---- phase 5: side chains, level-synchronous: level k places slot k of every residue that has
-    // one (residues sorted by atom count, so the active ones are a prefix and warps stay full).
-    // Nerf::reconstructAminoAcid src/nerf.cpp:106-155; torsion = FixedAngleDiscretizer(255)
-    // .continuize(byte), src/foldcomp.cpp:338-369.  Atoms are built in place in the output area:
-    // predecessors of an atom always have lower slots in the same residue.
+    // ---- phase 5: side chains, one thread per PAIR of neighbouring residues (two independent dependency
+    // chains per thread hide the latency of a placement; no barrier is needed because an atom's predecessors
+    // are lower slots of the same residue).  Nerf::reconstructAminoAcid src/nerf.cpp:106-155; torsion =
+    // FixedAngleDiscretizer(255).continuize(byte), src/foldcomp.cpp:338-369, read from a 256-entry table.
     {
         const uint8_t* sc = blob + y.o_sc;
-        uint32_t active = L;  // residues with more than k atoms
-        for (uint32_t k = 3u; k < FCZ_MAX_ATOMS; k++) {
-            active -= ch.bins[k];  // bins[k] = residues with exactly k atoms (bins[3] = UNK)
-            if (active == 0u) break;
-            // two residues per thread per trip: their placements are independent, which doubles the
-            // instruction-level parallelism of this latency-bound level
-            for (uint32_t i = cx.tid; i < active; i += 2u * cx.nthr) {
-                const uint32_t i2 = i + cx.nthr;
-                const bool two = i2 < active;
-                const uint32_t rA = ch.order[i], rB = ch.order[two ? i2 : i];
-                const unsigned cA = rec[8u * rA] >> 3, cB = rec[8u * rB] >> 3;
-                const uint32_t oA = ch.aoff[rA], oB = ch.aoff[rB];
-                float* RA = ch.out_xyz + 3u * oA;
-                float* RB = ch.out_xyz + 3u * oB;
-                const unsigned pA = tb->pred[cA][k], pB = tb->pred[cB][k];
-                const cs tA = tb->sc_tor[sc[oA - 3u * rA + k - 3u]];  // 256 possible torsions: table lookup
-                const cs tB = tb->sc_tor[sc[oB - 3u * rB + k - 3u]];
+        for (uint32_t i = cx.tid; 2u * i < L; i += cx.nthr) {
+            const uint32_t rA = 2u * i, rB = (2u * i + 1u < L) ? 2u * i + 1u : rA;
+            const unsigned cA = rec[8u * rA] >> 3, cB = rec[8u * rB] >> 3;
+            const uint32_t oA = ch.aoff[rA], oB = ch.aoff[rB];
+            const uint32_t nA = tb->natoms[cA], nB = (rB != rA) ? tb->natoms[cB] : 0u;
+            float* RA = ch.out_xyz + 3u * oA;
+            float* RB = ch.out_xyz + 3u * oB;
+            const uint8_t* sA = sc + (oA - 3u * rA);
+            const uint8_t* sB = sc + (oB - 3u * rB);
+            const uint32_t nmax = nA > nB ? nA : nB;
+            for (uint32_t k = 3u; k < nmax; k++) {
+                const bool doA = k < nA, doB = k < nB;
+                const uint32_t kA = doA ? k : 3u, kB = doB ? k : 3u;  // idle side re-places slot 3 (result discarded)
+                const unsigned pA = tb->pred[cA][kA], pB = tb->pred[cB][kB];
                 const f3 vA = place_from(ld3(RA + 3u * (pA & 15u)), ld3(RA + 3u * ((pA >> 4) & 15u)), ld3(RA + 3u * ((pA >> 8) & 15u)),
-                                         tb->blen[cA][k], tb->bang[cA][k], tA);
+                                         tb->blen[cA][kA], tb->bang[cA][kA], tb->sc_tor[sA[kA - 3u]]);
                 const f3 vB = place_from(ld3(RB + 3u * (pB & 15u)), ld3(RB + 3u * ((pB >> 4) & 15u)), ld3(RB + 3u * ((pB >> 8) & 15u)),
-                                         tb->blen[cB][k], tb->bang[cB][k], tB);
-                st3(RA + 3u * k, vA);
-                if (two) st3(RB + 3u * k, vB);
+                                         tb->blen[cB][kB], tb->bang[cB][kB], tb->sc_tor[sB[kB - 3u]]);
+                if (doA) st3(RA + 3u * k, vA);
+                if (doB) st3(RB + 3u * k, vB);
             }
-            cx.sync();
         }
+        cx.sync();
         if (ch.use_alt) {  // _reorderAtoms, src/foldcomp.cpp:1563-1577
             for (uint32_t r = cx.tid; r < L; r += cx.nthr) {
                 const unsigned code = rec[8u * r] >> 3;

@@ -68,7 +68,7 @@ __host__ __device__ inline EncSmem enc_smem(const TierCfg& t) {
     return s;
 }
 struct DecSmem {
-    uint32_t o_tab, o_misc, o_aoff, o_order, o_segid, o_tor, o_ang, o_seg, o_rev, o_blob, o_out, total;
+    uint32_t o_tab, o_misc, o_aoff, o_segid, o_tor, o_ang, o_seg, o_rev, o_blob, o_out, total;
 };
 __host__ __device__ inline DecSmem dec_smem(const TierCfg& t) {
     DecSmem s;
@@ -76,7 +76,6 @@ __host__ __device__ inline DecSmem dec_smem(const TierCfg& t) {
     s.o_tab = o;  o += align16((uint32_t)sizeof(Tables));
     s.o_misc = o; o += 384;  // mbarrier, ticket, warp sums (+64), counting-sort bins (+192)
     s.o_aoff = o; o += align16(4u * (t.max_res + 1u));
-    s.o_order = o; o += align16(2u * t.max_res);
     s.o_segid = o; o += align16(t.max_res);
     s.o_tor = o;  o += align16(24u * t.max_res);
     s.o_ang = o;  o += align16(24u * t.max_res);
@@ -178,6 +177,7 @@ struct DevCtx {
     uint32_t parity;  // its current phase
     bool staged;      // a bulk copy is in flight for this chain
     __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void wsync() { __syncwarp(); }
     __device__ __forceinline__ void stage_wait() {
         if (staged) mbar_wait(bar, parity);
     }
@@ -195,7 +195,6 @@ struct DevCtx {
         __syncthreads();
         return base + x - v;
     }
-    __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
     __device__ __forceinline__ float wmin(float v) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -562,10 +561,8 @@ __global__ void __launch_bounds__(256, 2) k_decode(DecArgs a) {
         ch.tor = reinterpret_cast<cs*>(smem + so.o_tor);
         ch.ang = reinterpret_cast<cs*>(smem + so.o_ang);
         ch.seg = reinterpret_cast<float*>(smem + so.o_seg);
-        ch.order = reinterpret_cast<uint16_t*>(smem + so.o_order);
         ch.segid = smem + so.o_segid;
         ch.rev = a.cfg.staged ? reinterpret_cast<float*>(smem + so.o_rev) : a.large_scratch + (size_t)blockIdx.x * 9u * a.cfg.max_res;
-        ch.bins = reinterpret_cast<uint32_t*>(smem + so.o_misc + 192);
         float* gout = a.xyz + 3u * a0;
         uint8_t* sout = nullptr;
         if (a.cfg.staged) {
@@ -587,9 +584,7 @@ __global__ void __launch_bounds__(256, 2) k_decode(DecArgs a) {
         __builtin_assume(__isShared(ch.tor));
         __builtin_assume(__isShared(ch.ang));
         __builtin_assume(__isShared(ch.seg));
-        __builtin_assume(__isShared(ch.order));
         __builtin_assume(__isShared(ch.segid));
-        __builtin_assume(__isShared(ch.bins));
         if (a.cfg.staged) {
             __builtin_assume(__isShared(ch.blob));
             __builtin_assume(__isShared(ch.out_xyz));

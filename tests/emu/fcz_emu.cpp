@@ -14,10 +14,10 @@ using namespace fcz;
 struct HostCtx {
     int tid = 0, nthr = 1, lane = 0, warp = 0, nwarps = 1, wsize = 1;
     void sync() {}
+    void wsync() {}
     void mark(int) {}
     void stage_wait() {}
     uint32_t excl_scan(uint32_t) { return 0; }
-    uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
     float wmin(float v) { return v; }
     float wmax(float v) { return v; }
 };
@@ -66,14 +66,12 @@ int emu_decode_chain(const uint8_t* blob, uint64_t len, int use_alt, uint8_t* re
     std::vector<uint32_t> aoff(L + 1);
     std::vector<cs> tor(3 * (size_t)L), ang(3 * (size_t)L);
     std::vector<float> seg((size_t)y.n_anchor * FCZ_SEG_FLOATS);
-    std::vector<uint16_t> order(L);
     std::vector<float> rev(9 * (size_t)L);
     std::vector<uint8_t> segid(L);
-    uint32_t bins[32];
     DecChain ch;
     ch.blob = blob; ch.y = y; ch.use_alt = use_alt;
     ch.out_xyz = xyz; ch.out_type = res_type; ch.out_bfac = bfac; ch.out_meta = meta; ch.out_title = title;
-    ch.aoff = aoff.data(); ch.tor = tor.data(); ch.ang = ang.data(); ch.seg = seg.data(); ch.order = order.data(); ch.bins = bins; ch.rev = rev.data(); ch.segid = segid.data();
+    ch.aoff = aoff.data(); ch.tor = tor.data(); ch.ang = ang.data(); ch.seg = seg.data(); ch.rev = rev.data(); ch.segid = segid.data();
     HostCtx cx;
     decode_chain(cx, tb, ch);
     return FCZ_OK;
