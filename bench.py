@@ -97,7 +97,7 @@ def cpu_sample_size(batch, threads, target_s):
     return n
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     if rank != 0:
         return
     from foldcomp_b200 import synth
@@ -125,7 +125,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
 
 
 # --------------------------------------------------------------------------------------- clocks
@@ -182,7 +182,7 @@ def pinned_like(arr):
     return t.numpy().view(arr.dtype).reshape(arr.shape), t
 
 
-def run_ours(args, rank, world, local_rank):
+def run_ours(args, rank, world, local_rank, out):
     import torch
 
     from foldcomp_b200 import abi, synth
@@ -272,9 +272,15 @@ def run_ours(args, rank, world, local_rank):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     kname, kms, kbytes = ("k_encode", enc_ms, enc_bytes) if enc_ms >= dec_ms else ("k_decode", dec_ms, dec_bytes)
     achieved = kbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kname]
+        traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src, "ms_per_launch": kms, "algorithmic_bytes_per_launch": kbytes,
+        "traffic": traffic, "peak_source": peak_src, "ms_per_launch": kms, "algorithmic_bytes_per_launch": kbytes,
         "kernels": {"k_encode": {"ms_per_launch": enc_ms, "algorithmic_bytes": enc_bytes, "gbs": enc_bytes / max(enc_ms, 1e-9) / 1e6},
                     "k_decode": {"ms_per_launch": dec_ms, "algorithmic_bytes": dec_bytes, "gbs": dec_bytes / max(dec_ms, 1e-9) / 1e6}},
         "round_trip_bytes_per_residue": (enc_bytes + dec_bytes) / n_res,
@@ -339,14 +345,24 @@ def run_ours(args, rank, world, local_rank):
                     "ms_per_step": float(ms_e.item()) / args.steps},
             "gpu_launches": launches, "fcz_bytes_per_step": fcz_bytes, "roundtrip_rmsd_vs_input": dev_rt,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
 
 
+def _quiet_stdout():
+    """Libraries (NCCL's version banner) print to fd 1; the contract is ONE JSON line on stdout.  Route fd 1 to
+    stderr for the run and return a file on the real stdout for the JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -357,9 +373,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
     else:
-        run_ours(args, rank, world, local_rank)
+        run_ours(args, rank, world, local_rank, out)
 
 
 if __name__ == "__main__":

@@ -159,7 +159,7 @@ FCZ_HD uint8_t sc_byte_fast(const Tables* tb, DotParts dp, bool neg) {
         if (ok && n > 0 && !(z - G >= tz[n - 1])) ok = false;
         if (ok && n < 128 && !(z + G < tz[n])) ok = false;
         if (ok) break;
-        c = cos_exact(dp);  // the reference's own sequence; the second pass needs no guard
+        c = cos_exact_slow(dp.inner, dp.p);  // the reference's own sequence; the second pass needs no guard
         ok = true;
     }
     return (uint8_t)(neg ? n : 127 + n);
@@ -253,12 +253,9 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
                 dst = (k == 2u) ? (uint32_t)A_CACN * L + q : (k == 0u ? (uint32_t)A_CNCA * L + q - 1u : (uint32_t)A_NCAC * L + q - 1u);
             }
             const float c = cos_ref(dot_parts(v1, v2));
-            const double ac = acos((double)c);
-            float deg = deg_ref(ac);
-            if (is_tor) {
-                if (ac != ac) deg = (c < 0) ? 180.0f : 0.0f;  // torsion_angle.cpp:74-79
-                if (neg) deg = -deg;
-            }
+            float deg;
+            if (!acos_deg_certified(c, &deg)) deg = angle_deg_slow(c, is_tor);  // ~2e-6 of items, and |c| > 1
+            if (is_tor && neg) deg = -deg;
             ch.ang[dst] = deg;
         }
     }

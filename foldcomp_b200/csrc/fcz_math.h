@@ -12,8 +12,10 @@
 
 #if defined(__CUDACC__)
 #define FCZ_HD __host__ __device__ __forceinline__
+#define FCZ_HD_SLOW __host__ __device__ __noinline__  // rare exact fallbacks: keep them out of the hot instruction stream
 #else
 #define FCZ_HD inline
+#define FCZ_HD_SLOW inline
 #endif
 
 #ifndef M_PI
@@ -71,6 +73,10 @@ FCZ_HD DotParts dot_parts(f3 v1, f3 v2) {
     return d;
 }
 FCZ_HD float cos_exact(DotParts d) { return (float)((double)d.inner / sqrt((double)d.p)); }
+// the same, as a real call: used where the exact sequence is a rare fallback (otherwise the compiler
+// speculates its first ~40 instructions into every iteration)
+static FCZ_HD_SLOW float cos_exact_slow(float inner, float p) { return (float)((double)inner / sqrt((double)p)); }
+static FCZ_HD_SLOW float deg_exact_slow(double ac) { return (float)(ac * 180.0 / M_PI); }
 
 FCZ_HD double drsqrt_(double x) {
 #if defined(__CUDA_ARCH__)
@@ -91,13 +97,60 @@ FCZ_HD bool same_float(double v, float* f) {
 FCZ_HD float cos_ref(DotParts d) {
     float c;
     if (d.p >= 1e-30f && d.p <= 1e30f && same_float((double)d.inner * drsqrt_((double)d.p), &c)) return c;
-    return cos_exact(d);
+    return cos_exact_slow(d.inner, d.p);
 }
 // degrees of an arccosine as the reference rounds them: (float)(ac * 180.0 / M_PI) is within 2^-50.5 of
 // ac * RN(180/pi); certified the same way.
 FCZ_HD float deg_ref(double ac) {
     float g;
     if (same_float(ac * 57.29577951308232, &g)) return g;
+    return deg_exact_slow(ac);
+}
+
+// acos(c) in DEGREES for a float c, |relative error| <= 2^-46 over every float in [-1, 1] (verified
+// exhaustively on the host, tests/emu: the function uses only IEEE operations -- fma, *, +, sqrt -- in a fixed
+// order, so the device computes bit-identical values); NaN for |c| > 1 or NaN.  ~30 double instructions
+// against ~105 for the library acos.  asin(s) = s + s z P(z), z = s^2 <= 1/4, P a degree-10 fit.
+FCZ_HD double acos_deg_fast(float c) {
+    const double x = (double)c, ax = fabs(x);
+    const bool big = ax > 0.5;
+    const double z = big ? (1.0 - ax) * 0.5 : x * x;  // exact for a float c
+    const double s = big ? sqrt(z) : x;
+    const double C[11] = {
+        0x1.55555555555c8p-3,
+        0x1.33333332ff5fap-4,
+        0x1.6db6dbad27a33p-5,
+        0x1.f1c6fe1e214e6p-6,
+        0x1.6e8f5826053ccp-6,
+        0x1.1c0b647b67e48p-6,
+        0x1.cf844e5f3bc52p-7,
+        0x1.5058ab6f69f19p-7,
+        0x1.fcea21358375cp-7,
+        -0x1.c9afa6dfde62cp-8,
+        0x1.cac497b043fe3p-6};
+    double p = C[10];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 9; i >= 0; i--) p = fma(p, z, C[i]);
+    const double r = fma(s * z, p, s);
+    const double a = big ? (x < 0 ? 3.141592653589793 - 2.0 * r : 2.0 * r) : 1.5707963267948966 - r;
+    return a * 57.29577951308232;
+}
+// float degrees of acos(c) exactly as the reference rounds them ((float)(acos((double)c) * 180.0 / M_PI) with the
+// library acos), or false when the fast evaluation cannot certify the rounding (then the caller takes the
+// reference's own sequence).  The reference's double is within 2^-50 of the true value, acos_deg_fast within
+// 2^-46: if the whole 2^-44 interval rounds to one float, that float is the reference's.
+FCZ_HD bool acos_deg_certified(float c, float* deg) {
+    const double v = acos_deg_fast(c);
+    const float lo = (float)(v * (1.0 - 0x1p-44)), hi = (float)(v * (1.0 + 0x1p-44));
+    *deg = lo;
+    return lo == hi;  // false for NaN
+}
+// the reference's sequence for one angle, incl. the NaN rule of torsions (torsion_angle.cpp:74-79)
+static FCZ_HD_SLOW float angle_deg_slow(float c, bool is_torsion) {
+    const double ac = acos((double)c);
+    if (is_torsion && ac != ac) return (c < 0) ? 180.0f : 0.0f;
     return (float)(ac * 180.0 / M_PI);
 }
 

@@ -108,3 +108,32 @@ uint64_t emu_cos_deg_mismatches(const float* inner, const float* p, uint32_t n, 
 }
 
 }  // extern "C"
+
+// Exhaustive (stride = 1) or sampled check of acos_deg_fast against long double over the floats in [-1, 1]:
+// returns the maximum relative error as a base-2 exponent * 1000 (e.g. -46500 = 2^-46.5) and counts the inputs
+// whose certified float differs from the reference's float (must be 0) and the uncertified ones.
+extern "C" long emu_acos_check(uint32_t stride, uint64_t* n_wrong, uint64_t* n_uncertified) {
+    double worst = 0;
+    uint64_t wrong = 0, unc = 0;
+    const uint32_t one = 0x3f800000u;
+#pragma omp parallel for reduction(max : worst) reduction(+ : wrong, unc) schedule(static)
+    for (int64_t k = 0; k <= (int64_t)one; k += stride) {
+        for (int sgn = 0; sgn < 2; sgn++) {
+            uint32_t u = (uint32_t)k | (sgn ? 0x80000000u : 0u);
+            float c;
+            memcpy(&c, &u, 4);
+            const long double ref = acosl((long double)c) * 180.0L / 3.14159265358979323846264338327950288L;
+            const double v = fcz::acos_deg_fast(c);
+            if (ref != 0) {
+                const double rel = (double)fabsl(((long double)v - ref) / ref);
+                if (rel > worst) worst = rel;
+            } else if (v != 0) worst = 1;
+            float f;
+            const float want = (float)(acos((double)c) * 180.0 / M_PI);
+            if (fcz::acos_deg_certified(c, &f)) { if (memcmp(&f, &want, 4) != 0) wrong++; } else unc++;
+        }
+    }
+    *n_wrong = wrong;
+    *n_uncertified = unc;
+    return worst > 0 ? (long)(1000.0 * log2(worst)) : -99999;
+}
