@@ -403,15 +403,20 @@ FCZ_HD f3 blend(f3 fwd, f3 rev, float wf, float wr, float inv_n) {
     return mk3(fma_(rev.x, wr, fwd.x * wf) * inv_n, fma_(rev.y, wr, fwd.y * wf) * inv_n, fma_(rev.z, wr, fwd.z * wf) * inv_n);
 }
 
+// The decode of one chain is five phases.  decode_chain() runs them back to back inside one CTA (block
+// barriers in between); the batch-wide decoder of fcz_engine.cu runs each phase as its own kernel over all
+// chains of a sub-batch, with the workspace in global memory (L2-resident), so that the serial phases cost
+// their latency once per batch instead of once per CTA wave.
+
 template <class Ctx>
-FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
+FCZ_HD void dec_unpack(Ctx& cx, const Tables* tb, const DecChain& ch) {
     const Layout& y = ch.y;
     const uint32_t L = y.L;
     const uint8_t* blob = ch.blob;
     const uint8_t* rec = blob + y.o_rec;
     const int n_seg = (int)y.n_anchor - 1;
     const uint32_t nT = 3u * L - 3u;
-
+    (void)L; (void)rec; (void)n_seg; (void)nT; (void)blob; (void)tb;
     // ---- phase 1: records -> residue codes, atom offsets (exclusive scan), (cos,sin) of the continuised angles
     // (convertBytesToBackboneChain src/foldcomp.cpp:60-77, decompressBackboneChain 122-153,
     // _continuize 155-158; the deg->rad and sincos of Nerf::place_atom src/nerf.cpp:63-70 are hoisted
@@ -477,9 +482,17 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
         if (ch.out_title)
             for (uint32_t i = cx.tid; i < y.title_len; i += cx.nthr) ch.out_title[i] = (char)blob[y.o_title + i];
     }
-    cx.sync();
-    cx.mark(8);  // D_UNPACK
+}
 
+template <class Ctx>
+FCZ_HD void dec_passes(Ctx& cx, const Tables* tb, const DecChain& ch) {
+    const Layout& y = ch.y;
+    const uint32_t L = y.L;
+    const uint8_t* blob = ch.blob;
+    const uint8_t* rec = blob + y.o_rec;
+    const int n_seg = (int)y.n_anchor - 1;
+    const uint32_t nT = 3u * L - 3u;
+    (void)L; (void)rec; (void)n_seg; (void)nT; (void)blob; (void)tb;
     // ---- phase 2: both NeRF passes of every anchor segment, TWO lanes per segment.
     //  even lane: FORWARD pass (reconstructBackboneAtoms, src/foldcomp.cpp:167-246; Pro N-CA length taken
     //   from the record being consumed, 204-212) in the segment's LOCAL frame: it starts from the STORED
@@ -494,10 +507,7 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
     //   Bond lengths by atom kind, never the Pro length (src/nerf.h:37-43).  The last three reverse atoms
     //   depend on the true start atoms and are finished in phase 4.
     // (forward and reverse lanes sit in DIFFERENT warps: lanes of one warp would serialise the two loops)
-    // When all segments fit one warp (the common case) the stitch of phase 3 starts as soon as the forward
-    // lanes of warp 0 are done and overlaps with the reverse lanes running in warp 1.
     const int n_grp = (n_seg + cx.wsize - 1) / cx.wsize;
-    const bool fused = n_grp == 1 && cx.nwarps >= 2;
     for (int idx = cx.warp; idx < 2 * n_grp; idx += cx.nwarps) {
         const int s = (idx >> 1) * cx.wsize + cx.lane;
         if (s >= n_seg) continue;
@@ -542,13 +552,17 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
             st3(sg + SEG_RF, f.bcn); st3(sg + SEG_RF + 3, f.nbc); st3(sg + SEG_RF + 6, f.n); st3(sg + SEG_RF + 9, rc);
         }
     }
-    if (!fused) {
-        cx.sync();
-        cx.mark(9);  // D_PASSES
-    } else if (cx.warp == 0) {
-        cx.wsync();  // the forward lanes (all in warp 0) have published SEG_F / SEG_TAIL
-    }
+}
 
+template <class Ctx>
+FCZ_HD void dec_stitch(Ctx& cx, const Tables* tb, const DecChain& ch) {
+    const Layout& y = ch.y;
+    const uint32_t L = y.L;
+    const uint8_t* blob = ch.blob;
+    const uint8_t* rec = blob + y.o_rec;
+    const int n_seg = (int)y.n_anchor - 1;
+    const uint32_t nT = 3u * L - 3u;
+    (void)L; (void)rec; (void)n_seg; (void)nT; (void)blob; (void)tb;
     // ---- phase 3: stitch.  Serial over segments (the only cross-segment dependency of the
     // reference, src/foldcomp.cpp:855-857: the blended tail of segment s seeds segment s+1).  Per
     // segment: place N',CA',C' from the true start atoms, derive the rigid transform local->true
@@ -605,9 +619,17 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
         float* o = ch.out_xyz + 3u * ch.aoff[L - 1u];
         st3(o, s0); st3(o + 3, s1); st3(o + 6, s2);
     }
-    cx.sync();
-    cx.mark(10);  // D_STITCH
+}
 
+template <class Ctx>
+FCZ_HD void dec_blend(Ctx& cx, const Tables* tb, const DecChain& ch) {
+    const Layout& y = ch.y;
+    const uint32_t L = y.L;
+    const uint8_t* blob = ch.blob;
+    const uint8_t* rec = blob + y.o_rec;
+    const int n_seg = (int)y.n_anchor - 1;
+    const uint32_t nT = 3u * L - 3u;
+    (void)L; (void)rec; (void)n_seg; (void)nT; (void)blob; (void)tb;
     // ---- phase 4: blend (weightedAverage, src/atom_coordinate.cpp:145-163).
     //  (a) one lane per segment finishes the reverse pass: atoms 2,1,0 need the bond angles at the true
     //      atoms 3,2,1 (which involve the start atoms S) and emits the blended first residue;
@@ -649,9 +671,17 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
         float* slot = ch.out_xyz + 3u * (ch.aoff[r] + k);
         st3(slot, blend(xform(sg + SEG_T, ld3(slot)), ld3(ch.rev + 3u * g), (float)(n - q), (float)q, sg[SEG_I + 2]));
     }
-    cx.sync();
-    cx.mark(11);  // D_BLEND
+}
 
+template <class Ctx>
+FCZ_HD void dec_side(Ctx& cx, const Tables* tb, const DecChain& ch) {
+    const Layout& y = ch.y;
+    const uint32_t L = y.L;
+    const uint8_t* blob = ch.blob;
+    const uint8_t* rec = blob + y.o_rec;
+    const int n_seg = (int)y.n_anchor - 1;
+    const uint32_t nT = 3u * L - 3u;
+    (void)L; (void)rec; (void)n_seg; (void)nT; (void)blob; (void)tb;
     // ---- phase 5: side chains, one thread per PAIR of neighbouring residues (two independent dependency
     // chains per thread hide the latency of a placement; no barrier is needed because an atom's predecessors
     // are lower slots of the same residue).  Nerf::reconstructAminoAcid src/nerf.cpp:106-155; torsion =
@@ -692,6 +722,31 @@ FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
             }
         }
     }
+}
+
+template <class Ctx>
+FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
+    const int n_seg = (int)ch.y.n_anchor - 1;
+    dec_unpack(cx, tb, ch);
+    cx.sync();
+    cx.mark(8);  // D_UNPACK
+    // When all segments fit one warp (the common case) the stitch starts as soon as the forward lanes of warp 0
+    // are done and overlaps with the reverse lanes running in warp 1.
+    const bool fused = (n_seg + cx.wsize - 1) / cx.wsize == 1 && cx.nwarps >= 2;
+    dec_passes(cx, tb, ch);
+    if (!fused) {
+        cx.sync();
+        cx.mark(9);  // D_PASSES
+    } else if (cx.warp == 0) {
+        cx.wsync();  // the forward lanes (all in warp 0) have published SEG_F / SEG_TAIL
+    }
+    dec_stitch(cx, tb, ch);
+    cx.sync();
+    cx.mark(10);  // D_STITCH
+    dec_blend(cx, tb, ch);
+    cx.sync();
+    cx.mark(11);  // D_BLEND
+    dec_side(cx, tb, ch);
     cx.sync();
     cx.mark(12);  // D_SIDE
 }

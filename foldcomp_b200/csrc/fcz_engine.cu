@@ -39,12 +39,13 @@ struct TierCfg {
 };
 
 #define FCZ_NTIER 7
+#define FCZ_MAX_CHUNKS 4096       // decode sub-batches per call
+#define FCZ_SUB_RESIDUES 525000u  // residues per decode sub-batch: workspace (~101 B/residue) + output stay in the 126 MB L2
 // residue caps per tier; decode carries more per-residue state in shared memory (198 B vs 175 B), so its
 // last staged tier is smaller.  The last tier keeps chain data in global memory.
 // Caps are chosen at the occupancy steps of the per-residue shared-memory footprint (encode ~172 B/residue,
-// decode ~240 B/residue): 350-residue chains run 3 CTAs/SM in encode and 2 CTAs/SM in decode.
+// 350-residue chains run 3 CTAs/SM).  Decode has no tiers: it is batch-wide (see below).
 static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 296, 408, 632, 1280, 2720};
-static const uint32_t kDecTierRes[FCZ_NTIER] = {64, 128, 184, 256, 416, 864, 2720};
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
@@ -67,26 +68,6 @@ __host__ __device__ inline EncSmem enc_smem(const TierCfg& t) {
     s.total = o;
     return s;
 }
-struct DecSmem {
-    uint32_t o_tab, o_misc, o_aoff, o_segid, o_tor, o_ang, o_seg, o_rev, o_blob, o_out, total;
-};
-__host__ __device__ inline DecSmem dec_smem(const TierCfg& t) {
-    DecSmem s;
-    uint32_t o = 0;
-    s.o_tab = o;  o += align16((uint32_t)sizeof(Tables));
-    s.o_misc = o; o += 384;  // mbarrier, ticket, warp sums (+64), counting-sort bins (+192)
-    s.o_aoff = o; o += align16(4u * (t.max_res + 1u));
-    s.o_segid = o; o += align16(t.max_res);
-    s.o_tor = o;  o += align16(24u * t.max_res);
-    s.o_ang = o;  o += align16(24u * t.max_res);
-    s.o_seg = o;  o += align16(4u * FCZ_SEG_FLOATS * (t.max_seg + 1u));
-    s.o_rev = o;  o += t.staged ? align16(36u * t.max_res) : 0u;  // large tier: reverse atoms live in global scratch
-    s.o_blob = o; o += t.staged ? align16(t.max_blob) + 32u : 0u;
-    s.o_out = o;  o += t.staged ? align16(12u * t.max_atoms) + 32u : 0u;
-    s.total = o;
-    return s;
-}
-
 static TierCfg make_tier(uint32_t max_res, bool staged) {
     TierCfg t;
     t.max_res = max_res;
@@ -105,12 +86,10 @@ static TierCfg make_tier(uint32_t max_res, bool staged) {
     t.smem = 0;
     return t;
 }
-static void make_tiers(TierCfg* enc, TierCfg* dec) {
+static void make_tiers(TierCfg* enc) {
     for (int i = 0; i < FCZ_NTIER; i++) {
         enc[i] = make_tier(kEncTierRes[i], i < FCZ_NTIER - 1);
-        dec[i] = make_tier(kDecTierRes[i], i < FCZ_NTIER - 1);
         enc[i].smem = enc_smem(enc[i]).total;
-        dec[i].smem = dec_smem(dec[i]).total;
     }
 }
 
@@ -277,6 +256,7 @@ struct PlanOut {
     uint32_t* v0;          // per-chain value 0 (encode: blob bytes; decode: residues)
     uint32_t* v1;          // decode: atoms
     uint32_t* v2;          // decode: title bytes
+    uint32_t* v3;          // decode: anchors (segment scratch slots)
     int32_t* status;       // per-chain status (engine copy)
     uint32_t* tier_count;  // [FCZ_NTIER]
     uint32_t* tier_list;   // [FCZ_NTIER][n]
@@ -427,30 +407,6 @@ __global__ void __launch_bounds__(256, 3) k_encode(EncArgs a) {
 
 // ========================================================================================== decode
 
-struct DecArgs {
-    const uint64_t* blob_off;
-    const uint8_t* bytes;
-    const uint32_t* res_off;
-    const uint64_t* atom_off;
-    const uint32_t* title_off;
-    uint8_t* res_type;
-    float* bfactor;
-    float* xyz;
-    char* titles;
-    fcz_chain_meta* meta;
-    const uint32_t* list;
-    const uint32_t* count;
-    uint32_t count_val;
-    const int32_t* status;  // host-planned batches: chains flagged by the validation pass are skipped
-    uint32_t* ticket;
-    const Tables* tables;
-    int32_t use_alt;
-    float* large_scratch;  // [gridDim.x][9 * cfg.max_res] reverse atoms of the large (unstaged) tier
-    TierCfg cfg;
-};
-
-// Plan: one warp per blob.  Validates the header (Foldcomp::read, src/foldcomp.cpp:904-924 and the
-// count checks of checkValidity, 1492-1561), sums the decoded atom count, picks the tier.
 // validate_only: host-planned batches -- chains [c0, n) are checked, only po.status is written (and only
 // for chains the host has not already rejected).
 __global__ void k_dec_plan(uint32_t c0, uint32_t n, const uint64_t* blob_off, const uint8_t* bytes, const Tables* tb, TierTable tt,
@@ -463,7 +419,6 @@ __global__ void k_dec_plan(uint32_t c0, uint32_t n, const uint64_t* blob_off, co
     const uint64_t len = blob_off[c + 1] - blob_off[c];
     int status = FCZ_OK;
     uint32_t L = 0, A = 0, T = 0;
-    int tier = -1;
     if (len < HDR_BYTES || blob[0] != 'F' || blob[1] != 'C' || blob[2] != 'M' || blob[3] != 'P') {
         status = FCZ_E_MAGIC;
     } else {
@@ -495,8 +450,6 @@ __global__ void k_dec_plan(uint32_t c0, uint32_t n, const uint64_t* blob_off, co
             else if ((bad & 2u) || sum - 3u * L != nsc) status = FCZ_E_TRUNCATED;
             else {
                 A = sum;
-                tier = pick_tier(tt, L, A, y.size, na - 1u);
-                if (tier < 0) status = FCZ_E_LIMIT;
             }
         }
     }
@@ -507,99 +460,128 @@ __global__ void k_dec_plan(uint32_t c0, uint32_t n, const uint64_t* blob_off, co
     }
     if (lane == 0) {
         po.v0[c] = L; po.v1[c] = A; po.v2[c] = T;
+        po.v3[c] = (status == FCZ_OK) ? (uint32_t)blob[OFF_NANCHOR] : 0u;
         po.status[c] = status;
-        if (tier >= 0) {
-            uint32_t pos = atomicAdd(&po.tier_count[tier], 1u);
-            po.tier_list[(size_t)tier * n + pos] = c;
-        }
     }
 }
 
-__global__ void __launch_bounds__(256, 2) k_decode(DecArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const DecSmem so = dec_smem(a.cfg);
-    Tables* tb = reinterpret_cast<Tables*>(smem + so.o_tab);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + so.o_misc);
-    uint32_t* s_ticket = reinterpret_cast<uint32_t*>(smem + so.o_misc + 8);
+// ============================================================================= batch-wide decode
+// The decoder that is used: each phase of fcz_codec.h's decode is its own kernel over all chains of a
+// sub-batch, workspace in global memory.  No shared-memory staging: the per-chain working set (~56 KB)
+// allows only two resident chains per SM, and a CTA that walks a chain through its serial phases (stitch:
+// one thread; passes: <= 2 lanes per segment) leaves the SM idle; run batch-wide, those phases cost their
+// latency once per sub-batch.  Sub-batches are sized so workspace + output stay L2-resident.
+
+struct Dec2Args {
+    const uint64_t* blob_off;
+    const uint8_t* bytes;
+    const uint32_t* res_off;
+    const uint64_t* atom_off;
+    const uint32_t* title_off;
+    const uint32_t* seg_off;  // [n+1] prefix of anchors per chain = first segment-scratch slot
+    uint8_t* res_type;
+    float* bfactor;
+    float* xyz;
+    char* titles;
+    fcz_chain_meta* meta;
+    const int32_t* status;
+    const Tables* tables;
+    int32_t use_alt;
+    uint32_t c0, c1;          // chains of this sub-batch
+    uint32_t r_base, s_base;  // res_off[c0], seg_off[c0]
+    uint32_t* aoff;           // workspace, indexed from the sub-batch's first residue / segment slot
+    uint8_t* segid;
+    cs* tor;
+    cs* ang;
+    float* rev;
+    float* seg;
+};
+
+__device__ __forceinline__ bool dec2_chain(const Dec2Args& a, uint32_t c, DecChain& ch) {
+    if (a.status[c] != FCZ_OK) return false;
+    const uint8_t* blob = a.bytes + a.blob_off[c];
+    ch.blob = blob;
+    ch.y = make_layout(get_u16(blob + OFF_NRES), get_u32(blob + OFF_NSC), get_u32(blob + OFF_LENTITLE), blob[OFF_NANCHOR]);
+    ch.use_alt = a.use_alt;
+    const uint32_t r0 = a.res_off[c], rr = r0 - a.r_base;
+    ch.out_xyz = a.xyz + 3u * a.atom_off[c];
+    ch.out_type = a.res_type + r0;
+    ch.out_bfac = a.bfactor + r0;
+    ch.out_meta = a.meta + c;
+    ch.out_title = a.titles ? a.titles + a.title_off[c] : nullptr;
+    ch.aoff = a.aoff + rr + (c - a.c0);
+    ch.segid = a.segid + rr;
+    ch.tor = a.tor + 3u * (size_t)rr;
+    ch.ang = a.ang + 3u * (size_t)rr;
+    ch.rev = a.rev + 9u * (size_t)rr;
+    ch.seg = a.seg + (size_t)(a.seg_off[c] - a.s_base) * FCZ_SEG_FLOATS;
+    return true;
+}
+
+struct ThreadCtx {  // one thread = one chain (stitch)
+    static constexpr int tid = 0, nthr = 1, lane = 0, warp = 0, nwarps = 1, wsize = 1;
+    __device__ __forceinline__ void sync() {}
+    __device__ __forceinline__ void wsync() {}
+};
+
+__device__ __forceinline__ DevCtx block_ctx(uint32_t* wsum) {
     DevCtx cx;
     cx.tid = threadIdx.x; cx.nthr = blockDim.x; cx.lane = threadIdx.x & 31; cx.warp = threadIdx.x >> 5;
     cx.nwarps = blockDim.x >> 5;
-    cx.wsum = reinterpret_cast<uint32_t*>(smem + so.o_misc + 64);
-    cx.bar = bar; cx.parity = 0; cx.staged = false;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(tb);
-        for (uint32_t i = cx.tid; i < (uint32_t)sizeof(Tables) / 4u; i += cx.nthr) dst[i] = src[i];
-    }
-    if (cx.tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    const uint32_t count = a.count ? *a.count : a.count_val;
-    for (;;) {
-        if (cx.tid == 0) *s_ticket = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const uint32_t t = *s_ticket;
-        if (t >= count) break;
-#ifdef FCZ_PHASE_TIMING
-        cx.t_last = clock64();
-#endif
-        const uint32_t c = a.list[t];
-        if (a.status && a.status[c] != FCZ_OK) { __syncthreads(); continue; }
-        const uint64_t b0 = a.blob_off[c];
-        const uint32_t blen = (uint32_t)(a.blob_off[c + 1] - b0);
-        const uint32_t r0 = a.res_off[c];
-        const uint64_t a0 = a.atom_off[c];
-        const uint32_t A = (uint32_t)(a.atom_off[c + 1] - a0);
-        const uint8_t* gblob = a.bytes + b0;
+    cx.wsum = wsum; cx.bar = nullptr; cx.parity = 0; cx.staged = false;
+    return cx;
+}
 
-        DecChain ch;
-        ch.use_alt = a.use_alt;
-        ch.out_type = a.res_type + r0;
-        ch.out_bfac = a.bfactor + r0;
-        ch.out_meta = a.meta + c;
-        ch.out_title = a.titles ? a.titles + a.title_off[c] : nullptr;
-        ch.aoff = reinterpret_cast<uint32_t*>(smem + so.o_aoff);
-        ch.tor = reinterpret_cast<cs*>(smem + so.o_tor);
-        ch.ang = reinterpret_cast<cs*>(smem + so.o_ang);
-        ch.seg = reinterpret_cast<float*>(smem + so.o_seg);
-        ch.segid = smem + so.o_segid;
-        ch.rev = a.cfg.staged ? reinterpret_cast<float*>(smem + so.o_rev) : a.large_scratch + (size_t)blockIdx.x * 9u * a.cfg.max_res;
-        float* gout = a.xyz + 3u * a0;
-        uint8_t* sout = nullptr;
-        if (a.cfg.staged) {
-            ch.blob = stage_in(cx, smem + so.o_blob, gblob, blen);
-            sout = smem + so.o_out + ((uintptr_t)gout & 15u);
-            ch.out_xyz = reinterpret_cast<float*>(sout);
-            cx.stage_wait();
-            __syncthreads();
-            cx.mark(13);
-        } else {
-            ch.blob = gblob;
-            ch.out_xyz = gout;
-        }
-        const uint8_t* hb = ch.blob;
-        ch.y = make_layout(get_u16(hb + OFF_NRES), get_u32(hb + OFF_NSC), get_u32(hb + OFF_LENTITLE), hb[OFF_NANCHOR]);
-        // the workspace is always shared memory; tell the compiler so it emits LDS/STS instead of generic LD/ST
-        __builtin_assume(__isShared(tb));
-        __builtin_assume(__isShared(ch.aoff));
-        __builtin_assume(__isShared(ch.tor));
-        __builtin_assume(__isShared(ch.ang));
-        __builtin_assume(__isShared(ch.seg));
-        __builtin_assume(__isShared(ch.segid));
-        if (a.cfg.staged) {
-            __builtin_assume(__isShared(ch.blob));
-            __builtin_assume(__isShared(ch.out_xyz));
-            __builtin_assume(__isShared(ch.rev));
-            decode_chain(cx, tb, ch);
-        } else {
-            decode_chain(cx, tb, ch);
-        }
-        if (a.cfg.staged) {
-            copy_out(cx, reinterpret_cast<uint8_t*>(gout), sout, 12u * A);
-            cx.mark(14);
-            cx.parity ^= 1u;
-            cx.staged = false;
-        }
-        __syncthreads();
+__global__ void __launch_bounds__(256) k_dec_unpack(Dec2Args a) {  // block per chain
+    __shared__ uint32_t wsum[32];
+    DecChain ch;
+    if (!dec2_chain(a, a.c0 + blockIdx.x, ch)) return;
+    DevCtx cx = block_ctx(wsum);
+    dec_unpack(cx, a.tables, ch);
+}
+__global__ void __launch_bounds__(64) k_dec_passes(Dec2Args a) {  // two warps per chain: forward lanes, reverse lanes
+    DecChain ch;
+    if (!dec2_chain(a, a.c0 + blockIdx.x, ch)) return;
+    DevCtx cx = block_ctx(nullptr);
+    dec_passes(cx, a.tables, ch);
+}
+__global__ void __launch_bounds__(128) k_dec_stitch(Dec2Args a) {  // thread per chain
+    const uint32_t c = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.c1) return;
+    DecChain ch;
+    if (!dec2_chain(a, c, ch)) return;
+    ThreadCtx cx;
+    dec_stitch(cx, a.tables, ch);
+}
+__global__ void __launch_bounds__(128) k_dec_blend(Dec2Args a) {  // block per chain, thread per backbone atom
+    DecChain ch;
+    if (!dec2_chain(a, a.c0 + blockIdx.x, ch)) return;
+    DevCtx cx = block_ctx(nullptr);
+    dec_blend(cx, a.tables, ch);
+}
+__global__ void __launch_bounds__(192) k_dec_side(Dec2Args a) {  // block per chain, thread per residue pair
+    DecChain ch;
+    if (!dec2_chain(a, a.c0 + blockIdx.x, ch)) return;
+    DevCtx cx = block_ctx(nullptr);
+    dec_side(cx, a.tables, ch);
+}
+
+// Sub-batch bounds for device-planned batches: ~FCZ_SUB_RESIDUES residues each, equal chain counts; written to
+// pinned host memory together with the residue / segment-slot prefix at every bound.
+__global__ void k_plan_chunks(uint32_t n, const uint32_t* res_off, const uint32_t* seg_off, uint32_t* out) {
+    if (threadIdx.x || blockIdx.x) return;
+    const uint64_t R = res_off[n];
+    uint64_t per = n ? ((uint64_t)FCZ_SUB_RESIDUES * n + (R ? R - 1 : 0)) / (R ? R : 1) : 1;
+    if (per < 1) per = 1;
+    uint64_t nch = n ? (n + per - 1) / per : 0;
+    if (nch > FCZ_MAX_CHUNKS) { per = (n + FCZ_MAX_CHUNKS - 1) / FCZ_MAX_CHUNKS; nch = (n + per - 1) / per; }
+    out[0] = (uint32_t)nch;
+    for (uint32_t k = 0; k <= nch; k++) {
+        uint64_t c = (uint64_t)k * per;
+        if (c > n) c = n;
+        out[1 + 3 * k] = (uint32_t)c;
+        out[2 + 3 * k] = res_off[c];
+        out[3 + 3 * k] = seg_off[c];
     }
 }
 
@@ -613,11 +595,11 @@ __global__ void __launch_bounds__(256, 2) k_decode(DecArgs a) {
 struct ScanArgs {
     uint32_t n;
     int narr;
-    const uint32_t* in[3];
-    void* out[3];       // [n+1]
-    int out64[3];       // 1: uint64 output, 0: uint32
-    uint64_t* partial;  // [ntiles*3]
-    uint64_t* totals;   // [3]
+    const uint32_t* in[4];
+    void* out[4];       // [n+1]
+    int out64[4];       // 1: uint64 output, 0: uint32
+    uint64_t* partial;  // [ntiles*4]
+    uint64_t* totals;   // [4]
 };
 
 __device__ __forceinline__ uint64_t block_sum64(uint64_t v, uint64_t* sh) {
@@ -639,7 +621,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(ScanArgs a) {
         for (int i = 0; i < SCAN_ITEMS; i++)
             if (base + i < a.n) s += a.in[j][base + i];
         s = block_sum64(s, sh);
-        if (threadIdx.x == 0) a.partial[blockIdx.x * 3 + j] = s;
+        if (threadIdx.x == 0) a.partial[blockIdx.x * 4 + j] = s;
     }
 }
 
@@ -649,7 +631,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(ScanArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int j = 0; j < a.narr; j++) {
         uint64_t pre = 0;
-        for (uint32_t t = threadIdx.x; t < blockIdx.x; t += blockDim.x) pre += a.partial[t * 3 + j];
+        for (uint32_t t = threadIdx.x; t < blockIdx.x; t += blockDim.x) pre += a.partial[t * 4 + j];
         pre = block_sum64(pre, sh);
         uint32_t v[SCAN_ITEMS];
         uint64_t s = 0;
@@ -702,18 +684,20 @@ struct fcz_engine {
     std::vector<cudaEvent_t> ev_pool;              // events of that path, reused across calls
     fcz_opts opts;
     int num_sms = 148;
-    TierCfg enc_tier[FCZ_NTIER], dec_tier[FCZ_NTIER];
-    int enc_occ[FCZ_NTIER], dec_occ[FCZ_NTIER];
+    TierCfg enc_tier[FCZ_NTIER];
+    int enc_occ[FCZ_NTIER];
     Tables* d_tables = nullptr;
     // plan scratch
-    DevBuf v0, v1, v2, status, tier_list, partial, large_scratch;
+    DevBuf v0, v1, v2, v3, status, tier_list, partial;
     uint32_t* d_counters = nullptr;  // [FCZ_NTIER] counts, [FCZ_NTIER] tickets
     uint64_t* d_totals = nullptr;    // [3]
     uint32_t* h_counters = nullptr;  // pinned mirror
     uint64_t* h_totals = nullptr;
+    uint32_t* h_bounds = nullptr;    // pinned: [0] nchunks, then chain / residue / segment-slot bounds of the decode sub-batches
     // staging for host-memory batches
     DevBuf d_res_off, d_atom_off, d_title_off, d_res_type, d_bfactor, d_xyz, d_titles, d_meta, d_blob_off, d_bytes, d_status;
     DevBuf d_list, d_tickets;
+    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg;  // batch-wide decoder: segment offsets + L2-resident workspace
     // plan made on the host by fcz_decode_plan(host) for the following fcz_decode_batch(host)
     struct Launch { uint32_t chunk, tier, first, count; };
     struct HostPlan {
@@ -722,6 +706,7 @@ struct fcz_engine {
         std::vector<uint32_t> list;       // chains grouped by (chunk, tier)
         std::vector<Launch> launches;
         std::vector<int32_t> status;
+        std::vector<uint32_t> seg_off;    // decode: [n+1] prefix of anchors (segment-scratch slots)
     } hplan;
     uint64_t launches = 0;
     // optional per-kernel event timing
@@ -796,33 +781,30 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
         if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return nullptr; }
         e->own_stream = true;
     }
-    make_tiers(e->enc_tier, e->dec_tier);
+    make_tiers(e->enc_tier);
     bool ok = true;
     ok &= cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) == cudaSuccess;
     ok &= cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < FCZ_NTIER; i++) {
-        if (e->enc_tier[i].smem > 227u * 1024u || e->dec_tier[i].smem > 227u * 1024u) {
-            fprintf(stderr, "fcz_engine_create: tier %d needs %u / %u bytes of shared memory (> 227 KB)\n", i,
-                    e->enc_tier[i].smem, e->dec_tier[i].smem);
+        if (e->enc_tier[i].smem > 227u * 1024u) {
+            fprintf(stderr, "fcz_engine_create: tier %d needs %u bytes of shared memory (> 227 KB)\n", i, e->enc_tier[i].smem);
             ok = false;
         }
     }
     for (int i = 0; i < FCZ_NTIER && ok; i++) {
         ok &= cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         int occ = 0;
         ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, (int)e->enc_tier[i].threads, e->enc_tier[i].smem) == cudaSuccess;
         e->enc_occ[i] = occ > 0 ? occ : 1;
-        ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decode, (int)e->dec_tier[i].threads, e->dec_tier[i].smem) == cudaSuccess;
-        e->dec_occ[i] = occ > 0 ? occ : 1;
     }
     Tables h;
     build_tables(&h);
     ok &= cudaMalloc(&e->d_tables, sizeof(Tables)) == cudaSuccess;
     ok &= cudaMalloc(&e->d_counters, sizeof(uint32_t) * 2 * FCZ_NTIER) == cudaSuccess;
-    ok &= cudaMalloc(&e->d_totals, sizeof(uint64_t) * 3) == cudaSuccess;
+    ok &= cudaMalloc(&e->d_totals, sizeof(uint64_t) * 4) == cudaSuccess;
     ok &= cudaMallocHost(&e->h_counters, sizeof(uint32_t) * 2 * FCZ_NTIER) == cudaSuccess;
-    ok &= cudaMallocHost(&e->h_totals, sizeof(uint64_t) * 3) == cudaSuccess;
+    ok &= cudaMallocHost(&e->h_totals, sizeof(uint64_t) * 4) == cudaSuccess;
+    ok &= cudaMallocHost(&e->h_bounds, sizeof(uint32_t) * (3 * (FCZ_MAX_CHUNKS + 1) + 1)) == cudaSuccess;
     if (ok) ok &= cudaMemcpy(e->d_tables, &h, sizeof(Tables), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         fprintf(stderr, "fcz_engine_create: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -836,9 +818,10 @@ void fcz_engine_destroy(fcz_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->status, &e->tier_list, &e->partial, &e->large_scratch, &e->d_res_off, &e->d_atom_off,
+    DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->v3, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
-                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets};
+                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets,
+                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (e->d_tables) cudaFree(e->d_tables);
@@ -846,6 +829,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     if (e->d_totals) cudaFree(e->d_totals);
     if (e->h_counters) cudaFreeHost(e->h_counters);
     if (e->h_totals) cudaFreeHost(e->h_totals);
+    if (e->h_bounds) cudaFreeHost(e->h_bounds);
     for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto ev : e->free_events) cudaEventDestroy(ev);
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
@@ -962,10 +946,11 @@ static int plan_buffers(fcz_engine* e, uint32_t n) {
     if ((rc = ensure(e, e->v0, 4ull * n + 4))) return rc;
     if ((rc = ensure(e, e->v1, 4ull * n + 4))) return rc;
     if ((rc = ensure(e, e->v2, 4ull * n + 4))) return rc;
+    if ((rc = ensure(e, e->v3, 4ull * n + 4))) return rc;
     if ((rc = ensure(e, e->status, 4ull * n + 4))) return rc;
     if ((rc = ensure(e, e->tier_list, 4ull * n * FCZ_NTIER + 4))) return rc;
     uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    if ((rc = ensure(e, e->partial, 24ull * (ntiles + 1)))) return rc;
+    if ((rc = ensure(e, e->partial, 32ull * (ntiles + 1)))) return rc;
     CK(cudaMemsetAsync(e->d_counters, 0, sizeof(uint32_t) * 2 * FCZ_NTIER, e->stream));
     return FCZ_OK;
 }
@@ -985,7 +970,7 @@ static int run_scan(fcz_engine* e, ScanArgs& sa) {
 // counters + totals -> pinned host, then wait for them
 static int fetch_plan(fcz_engine* e) {
     CK(cudaMemcpyAsync(e->h_counters, e->d_counters, sizeof(uint32_t) * FCZ_NTIER, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(e->h_totals, e->d_totals, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_totals, e->d_totals, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return FCZ_OK;
 }
@@ -1230,44 +1215,94 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
     return FCZ_OK;
 }
 
-// Blob headers are parsed on the host (Foldcomp::read, src/foldcomp.cpp:904-924): sizes, offsets, tiers.
+#define H2D(buf, src, bytes)                                                                   \
+    do {                                                                                       \
+        if ((rc = ensure(e, buf, (bytes) + 16))) return rc;                                    \
+        if (bytes) CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, e->stream)); \
+    } while (0)
+
+extern "C" int fcz_encode_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch* out) {
+    if (!e || !in || !out) return FCZ_E_ARG;
+    if (in->mem != out->mem) return fail(e, FCZ_E_ARG, "input and output batches must live in the same memory space");
+    CK(cudaSetDevice(e->device));
+    out->n_chains = in->n_chains;
+    const uint32_t n = in->n_chains;
+    uint64_t total = 0;
+    if (in->mem == FCZ_MEM_DEVICE) return encode_device(e, in, out, &total);
+    return encode_host(e, in, out);
+}
+
+// ------------------------------------------------------------------------------------------- decode
+
+struct Dec2Sub { uint32_t c0, c1, r0, r1, s0, s1; };  // chains, residues, segment slots of one sub-batch
+
+static int dec2_workspace(fcz_engine* e, const Dec2Sub* subs, size_t nsub) {
+    uint64_t mr = 0, ms = 0, mc = 0;
+    for (size_t k = 0; k < nsub; k++) {
+        if ((uint64_t)(subs[k].r1 - subs[k].r0) > mr) mr = subs[k].r1 - subs[k].r0;
+        if ((uint64_t)(subs[k].s1 - subs[k].s0) > ms) ms = subs[k].s1 - subs[k].s0;
+        if ((uint64_t)(subs[k].c1 - subs[k].c0) > mc) mc = subs[k].c1 - subs[k].c0;
+    }
+    int rc;
+    if ((rc = ensure(e, e->sc_aoff, 4ull * (mr + mc + 1)))) return rc;
+    if ((rc = ensure(e, e->sc_segid, mr + 16))) return rc;
+    if ((rc = ensure(e, e->sc_tor, 24ull * mr + 16))) return rc;
+    if ((rc = ensure(e, e->sc_ang, 24ull * mr + 16))) return rc;
+    if ((rc = ensure(e, e->sc_rev, 36ull * mr + 16))) return rc;
+    if ((rc = ensure(e, e->sc_seg, 4ull * FCZ_SEG_FLOATS * (ms + 1)))) return rc;
+    return FCZ_OK;
+}
+
+// the five phase kernels over one sub-batch (a carries the batch pointers)
+static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb) {
+    const uint32_t nch = sb.c1 - sb.c0;
+    if (!nch) return FCZ_OK;
+    a.c0 = sb.c0; a.c1 = sb.c1; a.r_base = sb.r0; a.s_base = sb.s0;
+    a.aoff = (uint32_t*)e->sc_aoff.p; a.segid = (uint8_t*)e->sc_segid.p; a.tor = (cs*)e->sc_tor.p; a.ang = (cs*)e->sc_ang.p;
+    a.rev = (float*)e->sc_rev.p; a.seg = (float*)e->sc_seg.p;
+    k_dec_unpack<<<nch, 256, 0, e->stream>>>(a);
+    k_dec_passes<<<nch, 64, 0, e->stream>>>(a);
+    k_dec_stitch<<<(nch + 127) / 128, 128, 0, e->stream>>>(a);
+    k_dec_blend<<<nch, 128, 0, e->stream>>>(a);
+    k_dec_side<<<nch, 192, 0, e->stream>>>(a);
+    e->launches += 5;
+    return FCZ_OK;
+}
+
+// Blob headers are parsed on the host (Foldcomp::read, src/foldcomp.cpp:904-924): sizes and offsets.
 // The per-residue checks (codes, anchors, side-chain count) run on the device before the decode kernels.
 static int decode_plan_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out, fcz_sizes* totals) {
     const uint32_t n = in->n_chains;
     fcz_engine::HostPlan& plan = e->hplan;
     plan.n = n;
     plan.status.assign(n, FCZ_OK);
-    std::vector<int8_t> tier(n, -1);
+    plan.seg_off.assign(n + 1, 0u);
     out->res_off[0] = 0; out->atom_off[0] = 0; out->title_off[0] = 0;
     for (uint32_t c = 0; c < n; c++) {
         const uint8_t* blob = in->bytes + in->blob_off[c];
         const uint64_t len = in->blob_off[c + 1] - in->blob_off[c];
         int st = FCZ_OK;
-        uint32_t L = 0, T = 0;
+        uint32_t L = 0, T = 0, na = 0;
         uint64_t A = 0;
         if (len < HDR_BYTES || memcmp(blob, "FCMP", 4) != 0) st = FCZ_E_MAGIC;
         else {
             L = get_u16(blob + OFF_NRES);
             T = get_u32(blob + OFF_LENTITLE);
-            const uint32_t nsc = get_u32(blob + OFF_NSC), na = blob[OFF_NANCHOR];
+            const uint32_t nsc = get_u32(blob + OFF_NSC);
+            na = blob[OFF_NANCHOR];
             const Layout y = make_layout(L, nsc, T, na);
             if (L < 2u || na < 2u || (uint64_t)T > len || (uint64_t)nsc > len || (uint64_t)y.size > len) st = FCZ_E_TRUNCATED;
-            else {
-                A = (uint64_t)nsc + 3ull * L;  // = sum of table atoms when the blob is consistent (checked on the device)
-                const int t = host_pick_tier(e->dec_tier, L, A, y.size, na - 1u);
-                if (t < 0) st = FCZ_E_LIMIT;
-                else tier[c] = (int8_t)t;
-            }
+            else A = (uint64_t)nsc + 3ull * L;  // = sum of table atoms when the blob is consistent (checked on the device)
         }
-        if (st != FCZ_OK) { L = 0; A = 0; T = 0; }
+        if (st != FCZ_OK) { L = 0; A = 0; T = 0; na = 0; }
         plan.status[c] = st;
         if (out->status) out->status[c] = st;
         out->res_off[c + 1] = out->res_off[c] + L;
         out->atom_off[c + 1] = out->atom_off[c] + A;
         out->title_off[c + 1] = out->title_off[c] + T;
+        plan.seg_off[c + 1] = plan.seg_off[c] + na;
     }
     make_chunks(n, out->atom_off, plan.chunk_c0);
-    group_launches(plan, tier);
     totals->n_res = out->res_off[n];
     totals->n_atoms = out->atom_off[n];
     totals->n_title_bytes = out->title_off[n];
@@ -1278,7 +1313,8 @@ static int decode_plan_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_b
 static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out) {
     const uint32_t n = in->n_chains;
     fcz_engine::HostPlan& plan = e->hplan;
-    if (plan.n != n || plan.chunk_c0.empty()) return fail(e, FCZ_E_ARG, "fcz_decode_batch(host) needs a preceding fcz_decode_plan on the same batch");
+    if (plan.n != n || plan.chunk_c0.empty() || plan.seg_off.size() != (size_t)n + 1)
+        return fail(e, FCZ_E_ARG, "fcz_decode_batch(host) needs a preceding fcz_decode_plan on the same batch");
     int rc;
     const uint64_t n_res = out->res_off[n], n_atoms = out->atom_off[n], n_title = out->title_off[n], n_bytes = in->blob_off[n];
     if (n_res > out->res_cap || n_atoms > out->atom_cap || (out->titles && n_title > out->title_cap))
@@ -1288,23 +1324,20 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
     if ((rc = ensure(e, e->d_res_off, 4ull * (n + 1)))) return rc;
     if ((rc = ensure(e, e->d_atom_off, 8ull * (n + 1)))) return rc;
     if ((rc = ensure(e, e->d_title_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_seg_off, 4ull * (n + 1)))) return rc;
     if ((rc = ensure(e, e->d_status, 4ull * n + 4))) return rc;
     if ((rc = ensure(e, e->d_res_type, n_res + 16))) return rc;
     if ((rc = ensure(e, e->d_bfactor, 4ull * n_res + 16))) return rc;
     if ((rc = ensure(e, e->d_xyz, 12ull * n_atoms + 16))) return rc;
     if ((rc = ensure(e, e->d_titles, n_title + 16))) return rc;
     if ((rc = ensure(e, e->d_meta, sizeof(fcz_chain_meta) * (uint64_t)n + 16))) return rc;
-    if ((rc = ensure(e, e->d_list, 4ull * n + 16))) return rc;
-    if ((rc = ensure(e, e->d_tickets, 4ull * 16 * FCZ_NTIER))) return rc;
     const uint32_t nchunks = (uint32_t)plan.chunk_c0.size() - 1u;
-    uint32_t max_grid_large = 0;
-    for (auto& ln : plan.launches)
-        if (!e->dec_tier[ln.tier].staged) {
-            uint32_t g = (uint32_t)(e->num_sms * e->dec_occ[ln.tier]);
-            if (g > ln.count) g = ln.count;
-            if (g > max_grid_large) max_grid_large = g;
-        }
-    if (max_grid_large && (rc = ensure(e, e->large_scratch, (size_t)max_grid_large * 36u * e->dec_tier[FCZ_NTIER - 1].max_res))) return rc;
+    std::vector<Dec2Sub> subs(nchunks);
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t c0 = plan.chunk_c0[k], c1 = plan.chunk_c0[k + 1];
+        subs[k] = {c0, c1, out->res_off[c0], out->res_off[c1], plan.seg_off[c0], plan.seg_off[c1]};
+    }
+    if ((rc = dec2_workspace(e, subs.data(), subs.size()))) return rc;
 
     size_t evi = 0;
     cudaEvent_t ev0 = pool_event(e, evi++);
@@ -1315,8 +1348,8 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
     COPY(e->d_res_off.p, out->res_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
     COPY(e->d_atom_off.p, out->atom_off, 8ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
     COPY(e->d_title_off.p, out->title_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_seg_off.p, plan.seg_off.data(), 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
     COPY(e->d_status.p, plan.status.data(), 4ull * n, cudaMemcpyHostToDevice, e->s_in);
-    COPY(e->d_list.p, plan.list.data(), 4ull * plan.list.size(), cudaMemcpyHostToDevice, e->s_in);
     std::vector<cudaEvent_t> ev_in(nchunks);
     for (uint32_t k = 0; k < nchunks; k++) {
         const uint64_t b0 = in->blob_off[plan.chunk_c0[k]], b1 = in->blob_off[plan.chunk_c0[k + 1]];
@@ -1324,41 +1357,27 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
         ev_in[k] = pool_event(e, evi++);
         CK(cudaEventRecord(ev_in[k], e->s_in));
     }
-    CK(cudaMemsetAsync(e->d_tickets.p, 0, 4ull * 16 * FCZ_NTIER, e->stream));
     TierTable tt;
-    for (int i = 0; i < FCZ_NTIER; i++) tt.t[i] = e->dec_tier[i];
+    memset(&tt, 0, sizeof tt);
     PlanOut po;
     memset(&po, 0, sizeof po);
     po.status = (int32_t*)e->d_status.p;
-    size_t li = 0;
+    Dec2Args a;
+    memset(&a, 0, sizeof a);
+    a.blob_off = (uint64_t*)e->d_blob_off.p; a.bytes = (uint8_t*)e->d_bytes.p;
+    a.res_off = (uint32_t*)e->d_res_off.p; a.atom_off = (uint64_t*)e->d_atom_off.p; a.title_off = (uint32_t*)e->d_title_off.p;
+    a.seg_off = (uint32_t*)e->d_seg_off.p;
+    a.res_type = (uint8_t*)e->d_res_type.p; a.bfactor = (float*)e->d_bfactor.p; a.xyz = (float*)e->d_xyz.p;
+    a.titles = out->titles ? (char*)e->d_titles.p : nullptr; a.meta = (fcz_chain_meta*)e->d_meta.p;
+    a.status = (int32_t*)e->d_status.p; a.tables = e->d_tables; a.use_alt = e->opts.use_alt_atom_order;
     for (uint32_t k = 0; k < nchunks; k++) {
-        const uint32_t c0 = plan.chunk_c0[k], c1 = plan.chunk_c0[k + 1];
+        const uint32_t c0 = subs[k].c0, c1 = subs[k].c1;
         CK(cudaStreamWaitEvent(e->stream, ev_in[k], 0));
         if (c1 > c0) {
             k_dec_plan<<<(c1 - c0 + 7) / 8, 256, 0, e->stream>>>(c0, c1, (uint64_t*)e->d_blob_off.p, (uint8_t*)e->d_bytes.p, e->d_tables, tt, po, 1);
             e->launches++;
-        }
-        for (; li < plan.launches.size() && plan.launches[li].chunk == k; li++) {
-            const fcz_engine::Launch& ln = plan.launches[li];
-            DecArgs a;
-            a.blob_off = (uint64_t*)e->d_blob_off.p; a.bytes = (uint8_t*)e->d_bytes.p;
-            a.res_off = (uint32_t*)e->d_res_off.p; a.atom_off = (uint64_t*)e->d_atom_off.p; a.title_off = (uint32_t*)e->d_title_off.p;
-            a.res_type = (uint8_t*)e->d_res_type.p; a.bfactor = (float*)e->d_bfactor.p; a.xyz = (float*)e->d_xyz.p;
-            a.titles = out->titles ? (char*)e->d_titles.p : nullptr; a.meta = (fcz_chain_meta*)e->d_meta.p;
-            a.list = (uint32_t*)e->d_list.p + ln.first;
-            a.count = nullptr; a.count_val = ln.count;
-            a.status = (int32_t*)e->d_status.p;
-            a.ticket = (uint32_t*)e->d_tickets.p + k * FCZ_NTIER + ln.tier;
-            a.tables = e->d_tables; a.use_alt = e->opts.use_alt_atom_order;
-            a.large_scratch = (float*)e->large_scratch.p;
-            a.cfg = e->dec_tier[ln.tier];
-            uint32_t grid = (uint32_t)(e->num_sms * e->dec_occ[ln.tier]);
-            if (grid > ln.count) grid = ln.count;
-            {
-                ProfSpan ps(e, 1);
-                k_decode<<<grid, a.cfg.threads, a.cfg.smem, e->stream>>>(a);
-            }
-            e->launches++;
+            ProfSpan ps(e, 1);
+            if ((rc = dec2_launch(e, a, subs[k]))) return rc;
         }
         cudaEvent_t ev_k = pool_event(e, evi++);
         CK(cudaEventRecord(ev_k, e->stream));
@@ -1383,33 +1402,15 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
     return FCZ_OK;
 }
 
-#define H2D(buf, src, bytes)                                                                   \
-    do {                                                                                       \
-        if ((rc = ensure(e, buf, (bytes) + 16))) return rc;                                    \
-        if (bytes) CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, e->stream)); \
-    } while (0)
-
-extern "C" int fcz_encode_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch* out) {
-    if (!e || !in || !out) return FCZ_E_ARG;
-    if (in->mem != out->mem) return fail(e, FCZ_E_ARG, "input and output batches must live in the same memory space");
-    CK(cudaSetDevice(e->device));
-    out->n_chains = in->n_chains;
-    const uint32_t n = in->n_chains;
-    uint64_t total = 0;
-    if (in->mem == FCZ_MEM_DEVICE) return encode_device(e, in, out, &total);
-    return encode_host(e, in, out);
-}
-
-// ------------------------------------------------------------------------------------------- decode
-
 static int decode_plan_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out, fcz_sizes* totals) {
     const uint32_t n = in->n_chains;
     int rc;
     if ((rc = plan_buffers(e, n))) return rc;
+    if ((rc = ensure(e, e->d_seg_off, 4ull * (n + 1)))) return rc;
     TierTable tt;
-    for (int i = 0; i < FCZ_NTIER; i++) tt.t[i] = e->dec_tier[i];
+    memset(&tt, 0, sizeof tt);
     PlanOut po;
-    po.v0 = (uint32_t*)e->v0.p; po.v1 = (uint32_t*)e->v1.p; po.v2 = (uint32_t*)e->v2.p;
+    po.v0 = (uint32_t*)e->v0.p; po.v1 = (uint32_t*)e->v1.p; po.v2 = (uint32_t*)e->v2.p; po.v3 = (uint32_t*)e->v3.p;
     po.status = out->status ? out->status : (int32_t*)e->status.p;
     po.tier_count = e->d_counters;
     po.tier_list = (uint32_t*)e->tier_list.p;
@@ -1419,11 +1420,14 @@ static int decode_plan_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain
     }
     ScanArgs sa;
     memset(&sa, 0, sizeof sa);
-    sa.n = n; sa.narr = 3;
+    sa.n = n; sa.narr = 4;
     sa.in[0] = po.v0; sa.out[0] = out->res_off; sa.out64[0] = 0;
     sa.in[1] = po.v1; sa.out[1] = out->atom_off; sa.out64[1] = 1;
     sa.in[2] = po.v2; sa.out[2] = out->title_off; sa.out64[2] = 0;
+    sa.in[3] = po.v3; sa.out[3] = e->d_seg_off.p; sa.out64[3] = 0;
     if ((rc = run_scan(e, sa))) return rc;
+    k_plan_chunks<<<1, 32, 0, e->stream>>>(n, out->res_off, (uint32_t*)e->d_seg_off.p, e->h_bounds);
+    e->launches++;
     if ((rc = fetch_plan(e))) return rc;
     totals->n_res = e->h_totals[0];
     totals->n_atoms = e->h_totals[1];
@@ -1433,40 +1437,29 @@ static int decode_plan_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain
 }
 
 static int decode_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out) {
-    // uses the tier lists / counters left by the last decode_plan_device on this engine
-    const uint32_t n = in->n_chains;
+    // uses the sub-batch bounds left in pinned memory by the last decode_plan_device on this engine
     if (e->h_totals[0] > out->res_cap || e->h_totals[1] > out->atom_cap || (out->titles && e->h_totals[2] > out->title_cap))
         return fail(e, FCZ_E_CAPACITY, "decode output capacity too small (need %llu residues, %llu atoms, %llu title bytes)",
                     (unsigned long long)e->h_totals[0], (unsigned long long)e->h_totals[1], (unsigned long long)e->h_totals[2]);
-    CK(cudaMemsetAsync(e->d_counters + FCZ_NTIER, 0, sizeof(uint32_t) * FCZ_NTIER, e->stream));
-    for (int i = 0; i < FCZ_NTIER; i++) {
-        const uint32_t cnt = e->h_counters[i];
-        if (!cnt) continue;
-        DecArgs a;
-        a.blob_off = in->blob_off; a.bytes = in->bytes;
-        a.res_off = out->res_off; a.atom_off = out->atom_off; a.title_off = out->title_off;
-        a.res_type = out->res_type; a.bfactor = out->bfactor; a.xyz = out->xyz; a.titles = out->titles; a.meta = out->meta;
-        a.list = (uint32_t*)e->tier_list.p + (size_t)i * n;
-        a.count = e->d_counters + i;
-        a.count_val = 0;
-        a.status = nullptr;
-        a.ticket = e->d_counters + FCZ_NTIER + i;
-        a.tables = e->d_tables;
-        a.use_alt = e->opts.use_alt_atom_order;
-        a.cfg = e->dec_tier[i];
-        uint32_t grid = (uint32_t)(e->num_sms * e->dec_occ[i]);
-        if (grid > cnt) grid = cnt;
-        a.large_scratch = nullptr;
-        if (!a.cfg.staged) {
-            int rc = ensure(e, e->large_scratch, (size_t)grid * 36u * a.cfg.max_res);
-            if (rc) return rc;
-            a.large_scratch = (float*)e->large_scratch.p;
-        }
-        {
-            ProfSpan ps(e, 1);
-            k_decode<<<grid, a.cfg.threads, a.cfg.smem, e->stream>>>(a);
-        }
-        e->launches++;
+    const uint32_t nsub = e->h_bounds[0];
+    std::vector<Dec2Sub> subs(nsub);
+    for (uint32_t k = 0; k < nsub; k++) {
+        const uint32_t* b = e->h_bounds + 1 + 3 * k;
+        subs[k] = {b[0], b[3], b[1], b[4], b[2], b[5]};
+    }
+    int rc;
+    if ((rc = dec2_workspace(e, subs.data(), subs.size()))) return rc;
+    Dec2Args a;
+    memset(&a, 0, sizeof a);
+    a.blob_off = in->blob_off; a.bytes = in->bytes;
+    a.res_off = out->res_off; a.atom_off = out->atom_off; a.title_off = out->title_off; a.seg_off = (uint32_t*)e->d_seg_off.p;
+    a.res_type = out->res_type; a.bfactor = out->bfactor; a.xyz = out->xyz; a.titles = out->titles; a.meta = out->meta;
+    a.status = out->status ? out->status : (int32_t*)e->status.p;
+    a.tables = e->d_tables; a.use_alt = e->opts.use_alt_atom_order;
+    {
+        ProfSpan ps(e, 1);
+        for (uint32_t k = 0; k < nsub; k++)
+            if ((rc = dec2_launch(e, a, subs[k]))) return rc;
     }
     CK(cudaGetLastError());
     return FCZ_OK;
