@@ -366,8 +366,10 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
 // RF[12] frame (bcn, nbc, n) and last atom of the reverse pass once it has placed atom 3
 // A[9] the stored anchor that opens the segment (as aligned floats), I[3] first / last residue index of
 // the segment (uint32 bits) and 1/(atoms in the segment).  Slot n_seg holds only A (the closing anchor).
-#define FCZ_SEG_FLOATS 72
-enum { SEG_S = 0, SEG_T = 9, SEG_TAIL = 21, SEG_F = 30, SEG_HEAD = 42, SEG_RF = 48, SEG_A = 60, SEG_I = 69 };
+// CS[13] (cos,sin) of the bond angles and torsions of the segment's first record + its N-CA length (so that
+// the stitch needs nothing but this scratch).
+#define FCZ_SEG_FLOATS 88
+enum { SEG_S = 0, SEG_T = 9, SEG_TAIL = 21, SEG_F = 30, SEG_HEAD = 42, SEG_RF = 48, SEG_A = 60, SEG_I = 69, SEG_CS = 72 };
 
 struct DecChain {
     const uint8_t* blob;  // staged copy or global
@@ -385,6 +387,7 @@ struct DecChain {
     cs* ang;              // [3(L-1)] (cos,sin) of CA-C-N, C-N-CA, N-CA-C per record
     float* seg;           // [n_anchor * FCZ_SEG_FLOATS]
     float* rev;           // [9L] reverse-pass backbone atoms (true coordinates)
+    const float* loc;     // [9L] forward-pass (local) backbone atoms when they do not live in out_xyz, else NULL
     uint8_t* segid;       // [L] anchor segment that owns (emits) each residue
 };
 
@@ -527,6 +530,11 @@ FCZ_HD void dec_passes(Ctx& cx, const Tables* tb, const DecChain& ch) {
                 if (r == a0) {  // frame carried by the first placed residue, origin at its C
                     st3(sg + SEG_F, f.bcn); st3(sg + SEG_F + 3, f.nbc); st3(sg + SEG_F + 6, f.n); st3(sg + SEG_F + 9, p2);
                     st3(sg + SEG_HEAD, p0); st3(sg + SEG_HEAD + 3, p1);
+                    for (int j = 0; j < 3; j++) {  // what the stitch needs of the first record
+                        sg[SEG_CS + 2 * j] = ch.ang[t + j].c; sg[SEG_CS + 2 * j + 1] = ch.ang[t + j].s;
+                        sg[SEG_CS + 6 + 2 * j] = ch.tor[t + j].c; sg[SEG_CS + 6 + 2 * j + 1] = ch.tor[t + j].s;
+                    }
+                    sg[SEG_CS + 12] = n_ca_len(rec[8u * r] >> 3);
                 }
             }
             st3(sg + SEG_TAIL, p0); st3(sg + SEG_TAIL + 3, p1); st3(sg + SEG_TAIL + 6, p2);
@@ -554,71 +562,93 @@ FCZ_HD void dec_passes(Ctx& cx, const Tables* tb, const DecChain& ch) {
     }
 }
 
+// ---- phase 3: stitch.  Serial over segments (the only cross-segment dependency of the reference,
+// src/foldcomp.cpp:855-857: the blended tail of segment s seeds segment s+1).  Per segment: place N',CA',C'
+// from the true start atoms, derive the rigid transform local->true from the two frames, move the local tail,
+// blend it with the stored anchor (weightedAverage, src/atom_coordinate.cpp:145-163, last three atoms only).
+// Works on the segment scratch alone; element (slot s, field f) sits at seg[(s*FCZ_SEG_FLOATS + f) * stride]:
+// stride 1 = one chain's scratch, stride C = structure-of-arrays over the C chains of a sub-batch (one thread
+// per chain, coalesced across the warp).
+// M maps the fields: SegFull = the scratch as the other phases see it; SegPacked = only what the stitch reads, with
+// its outputs S, T overwriting TAIL, F of the same slot (dead once the step has loaded them).
+struct SegFull { enum { S = SEG_S, T = SEG_T, TAIL = SEG_TAIL, F = SEG_F, A = SEG_A, I = SEG_I, CS = SEG_CS, N = FCZ_SEG_FLOATS }; };
+struct SegPacked { enum { I = 0, F = 3, T = 3, TAIL = 15, S = 15, A = 24, CS = 33, N = 46 }; };
+template <class M>
+FCZ_HD void dec_stitch_core(float* seg, size_t stride, int n_seg) {
+#define SEG_S M::S
+#define SEG_T M::T
+#define SEG_TAIL M::TAIL
+#define SEG_F M::F
+#define SEG_A M::A
+#define SEG_I M::I
+#define SEG_CS M::CS
+#define SG(s_, f_) seg[((size_t)(s_) * M::N + (size_t)(f_)) * stride]
+#define LD3(s_, f_) mk3(SG(s_, f_), SG(s_, (f_) + 1), SG(s_, (f_) + 2))
+#define ST3(s_, f_, v_) do { const f3 v__ = (v_); SG(s_, f_) = v__.x; SG(s_, (f_) + 1) = v__.y; SG(s_, (f_) + 2) = v__.z; } while (0)
+    f3 s0 = LD3(0, SEG_A), s1 = LD3(0, SEG_A + 3), s2 = LD3(0, SEG_A + 6);
+    for (int s = 0; s < n_seg; s++) {
+        // all inputs of this step first (independent of the serial chain), then the chain itself
+        const uint32_t a0 = f2u(SG(s, SEG_I)), a1 = f2u(SG(s, SEG_I + 1));
+        const float inv = SG(s, SEG_I + 2);
+        const f3 e0 = LD3(s + 1, SEG_A), e1 = LD3(s + 1, SEG_A + 3), e2 = LD3(s + 1, SEG_A + 6);
+        const f3 l1 = LD3(s, SEG_F), l2 = LD3(s, SEG_F + 3), l3 = LD3(s, SEG_F + 6), lo = LD3(s, SEG_F + 9);
+        const f3 q0 = LD3(s, SEG_TAIL), q1 = LD3(s, SEG_TAIL + 3), q2 = LD3(s, SEG_TAIL + 6);
+        cs b[3], w[3];
+        for (int j = 0; j < 3; j++) {
+            b[j].c = SG(s, SEG_CS + 2 * j); b[j].s = SG(s, SEG_CS + 2 * j + 1);
+            w[j].c = SG(s, SEG_CS + 6 + 2 * j); w[j].s = SG(s, SEG_CS + 6 + 2 * j + 1);
+        }
+        const float l_nca = SG(s, SEG_CS + 12);
+        ST3(s, SEG_S, s0); ST3(s, SEG_S + 3, s1); ST3(s, SEG_S + 6, s2);
+        f3 t0 = s0, t1 = s1, t2 = s2;  // forward tail in true coordinates
+        if (a1 > a0) {
+            NerfFrame fa = frame_from(s0, s1, s2);
+            f3 n = nerf_step(fa, s2, FCZ_C_TO_N, b[0], w[0]);
+            f3 ca = nerf_step(fa, n, l_nca, b[1], w[1]);
+            f3 c = nerf_step(fa, ca, FCZ_CA_TO_C, b[2], w[2]);
+            float T[12];
+            // R = bcn_a bcn_l^T + nbc_a nbc_l^T + n_a n_l^T ;  t = c_true - R c_local
+            T[0] = fma_(fa.n.x, l3.x, fma_(fa.nbc.x, l2.x, fa.bcn.x * l1.x));
+            T[1] = fma_(fa.n.x, l3.y, fma_(fa.nbc.x, l2.y, fa.bcn.x * l1.y));
+            T[2] = fma_(fa.n.x, l3.z, fma_(fa.nbc.x, l2.z, fa.bcn.x * l1.z));
+            T[3] = fma_(fa.n.y, l3.x, fma_(fa.nbc.y, l2.x, fa.bcn.y * l1.x));
+            T[4] = fma_(fa.n.y, l3.y, fma_(fa.nbc.y, l2.y, fa.bcn.y * l1.y));
+            T[5] = fma_(fa.n.y, l3.z, fma_(fa.nbc.y, l2.z, fa.bcn.y * l1.z));
+            T[6] = fma_(fa.n.z, l3.x, fma_(fa.nbc.z, l2.x, fa.bcn.z * l1.x));
+            T[7] = fma_(fa.n.z, l3.y, fma_(fa.nbc.z, l2.y, fa.bcn.z * l1.y));
+            T[8] = fma_(fa.n.z, l3.z, fma_(fa.nbc.z, l2.z, fa.bcn.z * l1.z));
+            T[9] = c.x - fma_(T[2], lo.z, fma_(T[1], lo.y, T[0] * lo.x));
+            T[10] = c.y - fma_(T[5], lo.z, fma_(T[4], lo.y, T[3] * lo.x));
+            T[11] = c.z - fma_(T[8], lo.z, fma_(T[7], lo.y, T[6] * lo.x));
+            t0 = xform(T, q0);
+            t1 = xform(T, q1);
+            t2 = xform(T, q2);
+            for (int i = 0; i < 12; i++) SG(s, SEG_T + i) = T[i];
+        }
+        const float nf = (float)(3u * (a1 - a0 + 1u));  // atoms in the segment
+        s0 = blend(t0, e0, 3.0f, nf - 3.0f, inv);
+        s1 = blend(t1, e1, 2.0f, nf - 2.0f, inv);
+        s2 = blend(t2, e2, 1.0f, nf - 1.0f, inv);
+    }
+    // blended tail of the last segment = final coordinates of the last residue (src/foldcomp.cpp:851-853);
+    // parked in the S field of the closing anchor's slot, emitted by dec_blend
+    ST3(n_seg, SEG_S, s0); ST3(n_seg, SEG_S + 3, s1); ST3(n_seg, SEG_S + 6, s2);
+#undef SG
+#undef LD3
+#undef ST3
+#undef SEG_S
+#undef SEG_T
+#undef SEG_TAIL
+#undef SEG_F
+#undef SEG_A
+#undef SEG_I
+#undef SEG_CS
+}
+
 template <class Ctx>
 FCZ_HD void dec_stitch(Ctx& cx, const Tables* tb, const DecChain& ch) {
-    const Layout& y = ch.y;
-    const uint32_t L = y.L;
-    const uint8_t* blob = ch.blob;
-    const uint8_t* rec = blob + y.o_rec;
-    const int n_seg = (int)y.n_anchor - 1;
-    const uint32_t nT = 3u * L - 3u;
-    (void)L; (void)rec; (void)n_seg; (void)nT; (void)blob; (void)tb;
-    // ---- phase 3: stitch.  Serial over segments (the only cross-segment dependency of the
-    // reference, src/foldcomp.cpp:855-857: the blended tail of segment s seeds segment s+1).  Per
-    // segment: place N',CA',C' from the true start atoms, derive the rigid transform local->true
-    // from the two frames, move the local tail, blend it with the stored anchor (weightedAverage,
-    // src/atom_coordinate.cpp:145-163, last three atoms only).
-    if (cx.tid == 0) {
-        f3 s0 = ld3(ch.seg + SEG_A), s1 = ld3(ch.seg + SEG_A + 3), s2 = ld3(ch.seg + SEG_A + 6);
-        for (int s = 0; s < n_seg; s++) {
-            float* sg = ch.seg + s * FCZ_SEG_FLOATS;
-            st3(sg + SEG_S, s0); st3(sg + SEG_S + 3, s1); st3(sg + SEG_S + 6, s2);
-            const uint32_t a0 = seg_a0(sg), a1 = seg_a1(sg);
-            const float* anc = sg + FCZ_SEG_FLOATS + SEG_A;
-            // all inputs of this step first (independent of the serial chain), then the chain itself
-            const f3 e0 = ld3(anc), e1 = ld3(anc + 3), e2 = ld3(anc + 6);
-            const f3 l1 = ld3(sg + SEG_F), l2 = ld3(sg + SEG_F + 3), l3 = ld3(sg + SEG_F + 6), lo = ld3(sg + SEG_F + 9);
-            const f3 q0 = ld3(sg + SEG_TAIL), q1 = ld3(sg + SEG_TAIL + 3), q2 = ld3(sg + SEG_TAIL + 6);
-            const uint32_t t = 3u * a0;
-            const uint32_t tt = (a1 > a0) ? t : 0u;
-            const cs b0 = ch.ang[tt], b1 = ch.ang[tt + 1u], b2 = ch.ang[tt + 2u];
-            const cs w0 = ch.tor[tt], w1 = ch.tor[tt + 1u], w2 = ch.tor[tt + 2u];
-            const float l_nca = n_ca_len(rec[8u * a0] >> 3);
-            f3 t0 = s0, t1 = s1, t2 = s2;  // forward tail in true coordinates
-            if (a1 > a0) {
-                NerfFrame fa = frame_from(s0, s1, s2);
-                f3 n = nerf_step(fa, s2, FCZ_C_TO_N, b0, w0);
-                f3 ca = nerf_step(fa, n, l_nca, b1, w1);
-                f3 c = nerf_step(fa, ca, FCZ_CA_TO_C, b2, w2);
-                float T[12];
-                // R = bcn_a bcn_l^T + nbc_a nbc_l^T + n_a n_l^T ;  t = c_true - R c_local
-                T[0] = fma_(fa.n.x, l3.x, fma_(fa.nbc.x, l2.x, fa.bcn.x * l1.x));
-                T[1] = fma_(fa.n.x, l3.y, fma_(fa.nbc.x, l2.y, fa.bcn.x * l1.y));
-                T[2] = fma_(fa.n.x, l3.z, fma_(fa.nbc.x, l2.z, fa.bcn.x * l1.z));
-                T[3] = fma_(fa.n.y, l3.x, fma_(fa.nbc.y, l2.x, fa.bcn.y * l1.x));
-                T[4] = fma_(fa.n.y, l3.y, fma_(fa.nbc.y, l2.y, fa.bcn.y * l1.y));
-                T[5] = fma_(fa.n.y, l3.z, fma_(fa.nbc.y, l2.z, fa.bcn.y * l1.z));
-                T[6] = fma_(fa.n.z, l3.x, fma_(fa.nbc.z, l2.x, fa.bcn.z * l1.x));
-                T[7] = fma_(fa.n.z, l3.y, fma_(fa.nbc.z, l2.y, fa.bcn.z * l1.y));
-                T[8] = fma_(fa.n.z, l3.z, fma_(fa.nbc.z, l2.z, fa.bcn.z * l1.z));
-                T[9] = c.x - fma_(T[2], lo.z, fma_(T[1], lo.y, T[0] * lo.x));
-                T[10] = c.y - fma_(T[5], lo.z, fma_(T[4], lo.y, T[3] * lo.x));
-                T[11] = c.z - fma_(T[8], lo.z, fma_(T[7], lo.y, T[6] * lo.x));
-                t0 = xform(T, q0);
-                t1 = xform(T, q1);
-                t2 = xform(T, q2);
-                for (int i = 0; i < 12; i++) sg[SEG_T + i] = T[i];
-            }
-            const float nf = (float)(3u * (a1 - a0 + 1u));  // atoms in the segment
-            const float inv = sg[SEG_I + 2];
-            s0 = blend(t0, e0, 3.0f, nf - 3.0f, inv);
-            s1 = blend(t1, e1, 2.0f, nf - 2.0f, inv);
-            s2 = blend(t2, e2, 1.0f, nf - 1.0f, inv);
-        }
-        // blended tail of the last segment = final coordinates of the last residue (src/foldcomp.cpp:851-853)
-        float* o = ch.out_xyz + 3u * ch.aoff[L - 1u];
-        st3(o, s0); st3(o + 3, s1); st3(o + 6, s2);
-    }
+    (void)tb;
+    if (cx.tid == 0) dec_stitch_core<SegFull>(ch.seg, 1, (int)ch.y.n_anchor - 1);
 }
 
 template <class Ctx>
@@ -634,6 +664,11 @@ FCZ_HD void dec_blend(Ctx& cx, const Tables* tb, const DecChain& ch) {
     //  (a) one lane per segment finishes the reverse pass: atoms 2,1,0 need the bond angles at the true
     //      atoms 3,2,1 (which involve the start atoms S) and emits the blended first residue;
     //  (b) every other backbone atom, one per thread: forward = local atom moved by T, reverse from phase 2.
+    if (cx.tid == cx.nthr - 1) {  // last residue: the blended tail of the last segment (parked by the stitch)
+        const float* sl = ch.seg + n_seg * FCZ_SEG_FLOATS + SEG_S;
+        float* o = ch.out_xyz + 3u * ch.aoff[L - 1u];
+        st3(o, ld3(sl)); st3(o + 3, ld3(sl + 3)); st3(o + 6, ld3(sl + 6));
+    }
     for (int s = cx.tid; s < n_seg; s += cx.nthr) {
         const float* sg = ch.seg + s * FCZ_SEG_FLOATS;
         const float* T = sg + SEG_T;
@@ -651,9 +686,9 @@ FCZ_HD void dec_blend(Ctx& cx, const Tables* tb, const DecChain& ch) {
             const f3 f0 = ld3(sg + SEG_S + 3 * q);
             const cs ba = cossin_angle(f0, f1, f2);  // angle at true atom q+1
             const float bl = (q == 0) ? FCZ_N_TO_CA : (q == 1 ? FCZ_CA_TO_C : FCZ_C_TO_N);
-            uint32_t ti = 3u * a0 + (uint32_t)q;
-            if (ti >= nT) ti = nT - 1u;
-            rc = nerf_step(f, rc, bl, ba, ch.tor[ti]);
+            // torsion 3*a0+q: of the segment's first record (kept in the scratch by the forward lane)
+            const cs tq = {sg[SEG_CS + 6 + 2 * q], sg[SEG_CS + 7 + 2 * q]};
+            rc = nerf_step(f, rc, bl, ba, tq);
             st3(slot + 3 * q, blend(f0, rc, (float)(n - q), (float)q, inv));
             f2 = f1; f1 = f0;
         }
@@ -669,7 +704,8 @@ FCZ_HD void dec_blend(Ctx& cx, const Tables* tb, const DecChain& ch) {
         }
         const int q = (int)(g - 3u * a0), n = (int)(3u * (a1 - a0 + 1u));
         float* slot = ch.out_xyz + 3u * (ch.aoff[r] + k);
-        st3(slot, blend(xform(sg + SEG_T, ld3(slot)), ld3(ch.rev + 3u * g), (float)(n - q), (float)q, sg[SEG_I + 2]));
+        const f3 local = ch.loc ? ld3(ch.loc + 3u * g) : ld3(slot);
+        st3(slot, blend(xform(sg + SEG_T, local), ld3(ch.rev + 3u * g), (float)(n - q), (float)q, sg[SEG_I + 2]));
     }
 }
 

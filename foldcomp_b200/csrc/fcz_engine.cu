@@ -40,7 +40,7 @@ struct TierCfg {
 
 #define FCZ_NTIER 7
 #define FCZ_MAX_CHUNKS 4096       // decode sub-batches per call
-#define FCZ_SUB_RESIDUES 525000u  // residues per decode sub-batch: workspace (~101 B/residue) + output stay in the 126 MB L2
+#define FCZ_SUB_RESIDUES 8000000u  // residues per decode sub-batch (bounds the workspace: ~80 B/residue)
 // residue caps per tier; decode carries more per-residue state in shared memory (198 B vs 175 B), so its
 // last staged tier is smaller.  The last tier keeps chain data in global memory.
 // Caps are chosen at the occupancy steps of the per-residue shared-memory footprint (encode ~172 B/residue,
@@ -495,6 +495,10 @@ struct Dec2Args {
     cs* ang;
     float* rev;
     float* seg;
+    // shared-memory path (k_dec_front / k_dec_stitch_soa / k_dec_back)
+    float* loc;               // [9 * residues] forward-pass backbone atoms in segment-local coordinates
+    uint32_t stitch_group;    // chains per block of k_dec_stitch_t
+    uint32_t max_L, max_anchor, max_blob, max_atoms;  // of the sub-batch: shared-memory carve-up
 };
 
 __device__ __forceinline__ bool dec2_chain(const Dec2Args& a, uint32_t c, DecChain& ch) {
@@ -514,6 +518,7 @@ __device__ __forceinline__ bool dec2_chain(const Dec2Args& a, uint32_t c, DecCha
     ch.tor = a.tor + 3u * (size_t)rr;
     ch.ang = a.ang + 3u * (size_t)rr;
     ch.rev = a.rev + 9u * (size_t)rr;
+    ch.loc = nullptr;
     ch.seg = a.seg + (size_t)(a.seg_off[c] - a.s_base) * FCZ_SEG_FLOATS;
     return true;
 }
@@ -566,22 +571,255 @@ __global__ void __launch_bounds__(192) k_dec_side(Dec2Args a) {  // block per ch
     dec_side(cx, a.tables, ch);
 }
 
-// Sub-batch bounds for device-planned batches: ~FCZ_SUB_RESIDUES residues each, equal chain counts; written to
-// pinned host memory together with the residue / segment-slot prefix at every bound.
-__global__ void k_plan_chunks(uint32_t n, const uint32_t* res_off, const uint32_t* seg_off, uint32_t* out) {
-    if (threadIdx.x || blockIdx.x) return;
+// ---------------------------------------------------------------- shared-memory decode, three kernels
+// front (block per chain): blob staged by one bulk copy; unpack + both NeRF passes with records, (cos,sin)
+//   tables and segment scratch in shared memory; hands over the local/reverse backbone atoms and the atom
+//   offsets in global memory and the segment scratch as a structure-of-arrays over the sub-batch's chains.
+// stitch (thread per chain): the serial walk over segments, coalesced over chains, paid once per sub-batch.
+// back (block per chain): blend + side chains into a shared-memory image of the chain's coordinates, then
+//   one 128-bit copy-out.
+struct FrontSmem { uint32_t o_seg, o_tor, o_ang, o_aoff, o_segid, o_blob, total; };
+__host__ __device__ inline uint32_t up16(uint32_t v) { return (v + 15u) & ~15u; }
+__host__ __device__ inline FrontSmem front_smem(uint32_t max_L, uint32_t max_anchor, uint32_t max_blob) {
+    FrontSmem o;
+    uint32_t p = 256;  // mbarrier + warp sums
+    o.o_seg = p; p += up16(4u * FCZ_SEG_FLOATS * (max_anchor + 1u));
+    o.o_tor = p; p += up16(24u * max_L);
+    o.o_ang = p; p += up16(24u * max_L);
+    o.o_aoff = p; p += up16(4u * (max_L + 1u));
+    o.o_segid = p; p += up16(max_L);
+    o.o_blob = p; p += up16(max_blob) + 32u;
+    o.total = p;
+    return o;
+}
+struct BackSmem { uint32_t o_seg, o_aoff, o_segid, o_out, total; };
+__host__ __device__ inline BackSmem back_smem(uint32_t max_L, uint32_t max_anchor, uint32_t max_atoms) {
+    BackSmem o;
+    uint32_t p = 0;
+    o.o_seg = p; p += up16(4u * FCZ_SEG_FLOATS * (max_anchor + 1u));
+    o.o_aoff = p; p += up16(4u * (max_L + 1u));
+    o.o_segid = p; p += up16(max_L);
+    o.o_out = p; p += up16(12u * max_atoms) + 32u;
+    o.total = p;
+    return o;
+}
+
+__global__ void __launch_bounds__(128) k_dec_front(Dec2Args a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t c = a.c0 + blockIdx.x;
+    if (a.status[c] != FCZ_OK) return;
+    const FrontSmem so = front_smem(a.max_L, a.max_anchor, a.max_blob);
+    DevCtx cx = block_ctx(reinterpret_cast<uint32_t*>(smem + 64));
+    cx.bar = reinterpret_cast<uint64_t*>(smem);
+#ifdef FCZ_PHASE_TIMING
+    cx.t_last = clock64();
+#endif
+    if (cx.tid == 0) mbar_init(cx.bar, 1);
+    __syncthreads();
+    const uint8_t* gblob = a.bytes + a.blob_off[c];
+    const uint32_t len = (uint32_t)(a.blob_off[c + 1] - a.blob_off[c]);
+    DecChain ch;
+    ch.y = make_layout(get_u16(gblob + OFF_NRES), get_u32(gblob + OFF_NSC), get_u32(gblob + OFF_LENTITLE), gblob[OFF_NANCHOR]);
+    const uint32_t size = ch.y.size < len ? ch.y.size : len;
+    ch.blob = stage_in(cx, smem + so.o_blob, gblob, size);
+    ch.use_alt = a.use_alt;
+    const uint32_t r0 = a.res_off[c], rr = r0 - a.r_base, L = ch.y.L, nA = ch.y.n_anchor;
+    ch.out_type = a.res_type + r0;
+    ch.out_bfac = a.bfactor + r0;
+    ch.out_meta = a.meta + c;
+    ch.out_title = a.titles ? a.titles + a.title_off[c] : nullptr;
+    ch.aoff = reinterpret_cast<uint32_t*>(smem + so.o_aoff);
+    ch.segid = smem + so.o_segid;
+    ch.tor = reinterpret_cast<cs*>(smem + so.o_tor);
+    ch.ang = reinterpret_cast<cs*>(smem + so.o_ang);
+    ch.seg = reinterpret_cast<float*>(smem + so.o_seg);
+    ch.rev = a.rev + 9u * (size_t)rr;
+    ch.out_xyz = a.loc + 9u * (size_t)rr;  // forward atoms of residue r at 9r: see the offsets below
+    ch.loc = nullptr;
+    __builtin_assume(__isShared(ch.blob));
+    __builtin_assume(__isShared(ch.aoff));
+    __builtin_assume(__isShared(ch.segid));
+    __builtin_assume(__isShared(ch.tor));
+    __builtin_assume(__isShared(ch.ang));
+    __builtin_assume(__isShared(ch.seg));
+    cx.stage_wait();
+    cx.mark(13);
+    dec_unpack(cx, a.tables, ch);
+    __syncthreads();
+    uint32_t* g_aoff = a.aoff + rr + (c - a.c0);
+    for (uint32_t r = cx.tid; r <= L; r += cx.nthr) g_aoff[r] = ch.aoff[r];
+    __syncthreads();
+    for (uint32_t r = cx.tid; r <= L; r += cx.nthr) ch.aoff[r] = 3u * r;  // compact backbone-only slots for the passes
+    __syncthreads();
+    cx.mark(8);
+    dec_passes(cx, a.tables, ch);
+    __syncthreads();
+    cx.mark(9);
+    float4* gseg = reinterpret_cast<float4*>(a.seg + (size_t)(a.seg_off[c] - a.s_base) * FCZ_SEG_FLOATS);
+    const float4* sseg = reinterpret_cast<const float4*>(ch.seg);
+    for (uint32_t e = cx.tid; e < nA * (FCZ_SEG_FLOATS / 4u); e += cx.nthr) gseg[e] = sseg[e];
+    cx.mark(14);
+}
+
+// stitch: block = stitch_group chains, one thread per chain walks the segments.  The fields it reads are first
+// gathered (all threads, coalesced over each chain's scratch) into shared memory, packed 46 floats per slot with
+// an odd per-chain stride (conflict-free for thread-per-chain access); S and T come back the same way.
+__global__ void __launch_bounds__(256) k_dec_stitch_t(Dec2Args a) {
+    extern __shared__ __align__(16) float sm[];
+    const uint32_t G = a.stitch_group, cstride = (a.max_anchor * SegPacked::N) | 1u;
+    const uint32_t cb = a.c0 + blockIdx.x * G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t j = warp; j < G; j += nwarps) {
+        const uint32_t c = cb + j;
+        if (c >= a.c1 || a.status[c] != FCZ_OK) continue;
+        const uint32_t s0 = a.seg_off[c], nA = a.seg_off[c + 1] - s0;
+        const float* src = a.seg + (size_t)(s0 - a.s_base) * FCZ_SEG_FLOATS;
+        float* dst = sm + (size_t)j * cstride;
+        const uint32_t ne = nA * SegPacked::N;
+        for (uint32_t base = lane; base < ne; base += 32u * 8u) {  // eight loads in flight per lane
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t e = base + 32u * u;
+                const uint32_t s = e / SegPacked::N, k = e - s * SegPacked::N;
+                // packed order: I[3] F[12] TAIL[9] A[9] CS[13]
+                const uint32_t f = k < 3u ? SEG_I + k : (k < 15u ? SEG_F + (k - 3u) : (k < 24u ? SEG_TAIL + (k - 15u) : (k < 33u ? SEG_A + (k - 24u) : SEG_CS + (k - 33u))));
+                v[u] = e < ne ? __ldg(src + s * FCZ_SEG_FLOATS + f) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t e = base + 32u * u;
+                if (e < ne) dst[e] = v[u];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const uint32_t c = cb + threadIdx.x;
+        if (c < a.c1 && a.status[c] == FCZ_OK)
+            dec_stitch_core<SegPacked>(sm + (size_t)threadIdx.x * cstride, 1, (int)(a.seg_off[c + 1] - a.seg_off[c]) - 1);
+    }
+    __syncthreads();
+    for (uint32_t j = warp; j < G; j += nwarps) {
+        const uint32_t c = cb + j;
+        if (c >= a.c1 || a.status[c] != FCZ_OK) continue;
+        const uint32_t s0 = a.seg_off[c], nA = a.seg_off[c + 1] - s0;
+        float* out = a.seg + (size_t)(s0 - a.s_base) * FCZ_SEG_FLOATS;
+        const float* srcp = sm + (size_t)j * cstride;
+        for (uint32_t e = lane; e < nA * 21u; e += 32) {  // S[9] T[12] are adjacent in the full layout
+            const uint32_t s = e / 21u, k = e - s * 21u;
+            out[s * FCZ_SEG_FLOATS + k] = srcp[s * SegPacked::N + (k < 9u ? SegPacked::S + k : SegPacked::T + (k - 9u))];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(192) k_dec_back(Dec2Args a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint32_t wsum[32];
+    const uint32_t c = a.c0 + blockIdx.x;
+    if (a.status[c] != FCZ_OK) return;
+    const BackSmem so = back_smem(a.max_L, a.max_anchor, a.max_atoms);
+    DevCtx cx = block_ctx(wsum);
+#ifdef FCZ_PHASE_TIMING
+    cx.t_last = clock64();
+#endif
+    const uint8_t* blob = a.bytes + a.blob_off[c];
+    DecChain ch;
+    ch.blob = blob;
+    ch.y = make_layout(get_u16(blob + OFF_NRES), get_u32(blob + OFF_NSC), get_u32(blob + OFF_LENTITLE), blob[OFF_NANCHOR]);
+    ch.use_alt = a.use_alt;
+    const uint32_t r0 = a.res_off[c], rr = r0 - a.r_base, L = ch.y.L, nA = ch.y.n_anchor;
+    const uint64_t a0 = a.atom_off[c];
+    const uint32_t A = (uint32_t)(a.atom_off[c + 1] - a0);
+    uint8_t* gdst = reinterpret_cast<uint8_t*>(a.xyz + 3u * a0);
+    uint8_t* sdst = smem + so.o_out + ((uintptr_t)gdst & 15u);
+    ch.out_xyz = reinterpret_cast<float*>(sdst);
+    ch.out_type = nullptr; ch.out_bfac = nullptr; ch.out_meta = nullptr; ch.out_title = nullptr;
+    ch.aoff = reinterpret_cast<uint32_t*>(smem + so.o_aoff);
+    ch.segid = smem + so.o_segid;
+    ch.tor = nullptr; ch.ang = nullptr;
+    ch.seg = reinterpret_cast<float*>(smem + so.o_seg);
+    ch.rev = a.rev + 9u * (size_t)rr;
+    ch.loc = a.loc + 9u * (size_t)rr;
+    __builtin_assume(__isShared(ch.out_xyz));
+    __builtin_assume(__isShared(ch.aoff));
+    __builtin_assume(__isShared(ch.segid));
+    __builtin_assume(__isShared(ch.seg));
+    const uint32_t* g_aoff = a.aoff + rr + (c - a.c0);
+    for (uint32_t r = cx.tid; r <= L; r += cx.nthr) ch.aoff[r] = g_aoff[r];
+    {
+        const float4* gseg = reinterpret_cast<const float4*>(a.seg + (size_t)(a.seg_off[c] - a.s_base) * FCZ_SEG_FLOATS);
+        float4* sseg = reinterpret_cast<float4*>(ch.seg);
+        for (uint32_t e = cx.tid; e < nA * (FCZ_SEG_FLOATS / 4u); e += cx.nthr) sseg[e] = gseg[e];
+    }
+    __syncthreads();
+    for (uint32_t s = cx.tid; s + 1u < nA; s += cx.nthr) {
+        const float* sg = ch.seg + s * FCZ_SEG_FLOATS;
+        for (uint32_t r = seg_a0(sg); r < seg_a1(sg); r++) ch.segid[r] = (uint8_t)s;
+    }
+    __syncthreads();
+    cx.mark(13);
+    dec_blend(cx, a.tables, ch);
+    __syncthreads();
+    cx.mark(11);
+    dec_side(cx, a.tables, ch);
+    __syncthreads();
+    cx.mark(12);
+    copy_out(cx, gdst, sdst, 12u * A);
+    cx.mark(14);
+}
+
+// Sub-batch bounds for device-planned batches: ~sub_res residues each, equal chain counts; written to pinned
+// host memory: [0] count, then per bound k (chain, residue, segment-slot prefix), then per sub-batch the
+// maxima (residues, anchors, blob bytes, atoms) over its chains that size the shared-memory kernels.
+// One thread per chain; maxima through device atomics in dmax (all zero on entry and on exit), published by
+// the last block to finish.
+__global__ void __launch_bounds__(256) k_plan_chunks(uint32_t n, uint32_t sub_res, const uint32_t* res_off, const uint32_t* seg_off,
+                                                     const uint64_t* atom_off, const uint64_t* blob_off, uint32_t* dmax, uint32_t* out) {
+    __shared__ uint32_t s_last;
     const uint64_t R = res_off[n];
-    uint64_t per = n ? ((uint64_t)FCZ_SUB_RESIDUES * n + (R ? R - 1 : 0)) / (R ? R : 1) : 1;
-    if (per < 1) per = 1;
-    uint64_t nch = n ? (n + per - 1) / per : 0;
-    if (nch > FCZ_MAX_CHUNKS) { per = (n + FCZ_MAX_CHUNKS - 1) / FCZ_MAX_CHUNKS; nch = (n + per - 1) / per; }
-    out[0] = (uint32_t)nch;
-    for (uint32_t k = 0; k <= nch; k++) {
-        uint64_t c = (uint64_t)k * per;
-        if (c > n) c = n;
-        out[1 + 3 * k] = (uint32_t)c;
-        out[2 + 3 * k] = res_off[c];
-        out[3 + 3 * k] = seg_off[c];
+    uint64_t per64 = n ? ((uint64_t)sub_res * n + (R ? R - 1 : 0)) / (R ? R : 1) : 1;
+    if (per64 < 1) per64 = 1;
+    uint64_t nch64 = n ? (n + per64 - 1) / per64 : 0;
+    if (nch64 > FCZ_MAX_CHUNKS) { per64 = (n + FCZ_MAX_CHUNKS - 1) / FCZ_MAX_CHUNKS; nch64 = (n + per64 - 1) / per64; }
+    const uint32_t per = (uint32_t)per64, nch = (uint32_t)nch64;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) out[0] = nch;
+        for (uint32_t k = threadIdx.x; k <= nch; k += blockDim.x) {
+            uint64_t c = (uint64_t)k * per;
+            if (c > n) c = n;
+            out[1 + 3 * k] = (uint32_t)c;
+            out[2 + 3 * k] = res_off[c];
+            out[3 + 3 * k] = seg_off[c];
+        }
+    }
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) {
+        const uint32_t k = c / per;
+        uint32_t m[4] = {res_off[c + 1] - res_off[c], seg_off[c + 1] - seg_off[c], (uint32_t)(blob_off[c + 1] - blob_off[c]),
+                         (uint32_t)(atom_off[c + 1] - atom_off[c])};
+        const unsigned mask = __activemask();
+        const uint32_t k0 = __shfl_sync(mask, k, __ffs(mask) - 1);
+        if (__all_sync(mask, k == k0)) {
+            for (int j = 0; j < 4; j++) {
+                const uint32_t v = __reduce_max_sync(mask, m[j]);
+                if ((int)(threadIdx.x & 31) == __ffs(mask) - 1) atomicMax(&dmax[4 * k + j], v);
+            }
+        } else {
+            for (int j = 0; j < 4; j++) atomicMax(&dmax[4 * k + j], m[j]);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&dmax[4 * FCZ_MAX_CHUNKS], 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        uint32_t* mx = out + 1 + 3 * (nch + 1);
+        for (uint32_t i = threadIdx.x; i < 4u * nch; i += blockDim.x) {
+            mx[i] = atomicExch(&dmax[i], 0u);
+        }
+        if (threadIdx.x == 0) dmax[4 * FCZ_MAX_CHUNKS] = 0u;
     }
 }
 
@@ -693,11 +931,12 @@ struct fcz_engine {
     uint64_t* d_totals = nullptr;    // [3]
     uint32_t* h_counters = nullptr;  // pinned mirror
     uint64_t* h_totals = nullptr;
+    uint32_t dec_sub_res = FCZ_SUB_RESIDUES;  // residues per decode sub-batch (FCZ_DEC_SUB_RESIDUES overrides)
     uint32_t* h_bounds = nullptr;    // pinned: [0] nchunks, then chain / residue / segment-slot bounds of the decode sub-batches
     // staging for host-memory batches
     DevBuf d_res_off, d_atom_off, d_title_off, d_res_type, d_bfactor, d_xyz, d_titles, d_meta, d_blob_off, d_bytes, d_status;
     DevBuf d_list, d_tickets;
-    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg;  // batch-wide decoder: segment offsets + L2-resident workspace
+    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax;  // batch-wide decoder: segment offsets + L2-resident workspace
     // plan made on the host by fcz_decode_plan(host) for the following fcz_decode_batch(host)
     struct Launch { uint32_t chunk, tier, first, count; };
     struct HostPlan {
@@ -793,6 +1032,10 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     }
     for (int i = 0; i < FCZ_NTIER && ok; i++) {
         ok &= cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(k_dec_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(k_dec_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(k_dec_stitch_t, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        if (const char* v = getenv("FCZ_DEC_SUB_RESIDUES")) { long q = atol(v); if (q > 0) e->dec_sub_res = (uint32_t)q; }
         int occ = 0;
         ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, (int)e->enc_tier[i].threads, e->enc_tier[i].smem) == cudaSuccess;
         e->enc_occ[i] = occ > 0 ? occ : 1;
@@ -804,8 +1047,10 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     ok &= cudaMalloc(&e->d_totals, sizeof(uint64_t) * 4) == cudaSuccess;
     ok &= cudaMallocHost(&e->h_counters, sizeof(uint32_t) * 2 * FCZ_NTIER) == cudaSuccess;
     ok &= cudaMallocHost(&e->h_totals, sizeof(uint64_t) * 4) == cudaSuccess;
-    ok &= cudaMallocHost(&e->h_bounds, sizeof(uint32_t) * (3 * (FCZ_MAX_CHUNKS + 1) + 1)) == cudaSuccess;
+    ok &= cudaMallocHost(&e->h_bounds, sizeof(uint32_t) * (7 * (FCZ_MAX_CHUNKS + 1) + 1)) == cudaSuccess;
     if (ok) ok &= cudaMemcpy(e->d_tables, &h, sizeof(Tables), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMalloc(&e->d_submax.p, sizeof(uint32_t) * (4 * FCZ_MAX_CHUNKS + 1)) == cudaSuccess;  // k_plan_chunks keeps it zero
+    if (ok) { e->d_submax.cap = sizeof(uint32_t) * (4 * FCZ_MAX_CHUNKS + 1); ok &= cudaMemset(e->d_submax.p, 0, e->d_submax.cap) == cudaSuccess; }
     if (!ok) {
         fprintf(stderr, "fcz_engine_create: %s\n", cudaGetErrorString(cudaGetLastError()));
         delete e;
@@ -821,7 +1066,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->v3, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
                       &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets,
-                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg};
+                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (e->d_tables) cudaFree(e->d_tables);
@@ -1234,32 +1479,74 @@ extern "C" int fcz_encode_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_bl
 
 // ------------------------------------------------------------------------------------------- decode
 
-struct Dec2Sub { uint32_t c0, c1, r0, r1, s0, s1; };  // chains, residues, segment slots of one sub-batch
+struct Dec2Sub {
+    uint32_t c0, c1, r0, r1, s0, s1;                  // chains, residues, segment slots of one sub-batch
+    uint32_t max_L, max_anchor, max_blob, max_atoms;  // maxima over its chains
+    bool smem;                                        // runs the shared-memory kernels
+};
 
-static int dec2_workspace(fcz_engine* e, const Dec2Sub* subs, size_t nsub) {
-    uint64_t mr = 0, ms = 0, mc = 0;
+#define FCZ_SMEM_LIMIT (227u * 1024u)
+
+static uint32_t stitch_chain_bytes(uint32_t max_anchor) { return 4u * ((max_anchor * (uint32_t)SegPacked::N) | 1u); }
+
+static void dec2_classify(Dec2Sub& sb) {
+    const FrontSmem fs = front_smem(sb.max_L, sb.max_anchor, sb.max_blob);
+    const BackSmem bs = back_smem(sb.max_L, sb.max_anchor, sb.max_atoms);
+    sb.smem = fs.total <= FCZ_SMEM_LIMIT && bs.total <= FCZ_SMEM_LIMIT && stitch_chain_bytes(sb.max_anchor) <= FCZ_SMEM_LIMIT &&
+              getenv("FCZ_DEC_GLOBAL") == nullptr;
+}
+
+static int dec2_workspace(fcz_engine* e, Dec2Sub* subs, size_t nsub) {
+    uint64_t mr = 0, ms = 0, mc = 0, mrs = 0;
+    bool any_global = false;
     for (size_t k = 0; k < nsub; k++) {
-        if ((uint64_t)(subs[k].r1 - subs[k].r0) > mr) mr = subs[k].r1 - subs[k].r0;
+        dec2_classify(subs[k]);
+        const uint64_t nr = subs[k].r1 - subs[k].r0, nc = subs[k].c1 - subs[k].c0;
+        if (nc > mc) mc = nc;
+        if (nr > mr) mr = nr;
         if ((uint64_t)(subs[k].s1 - subs[k].s0) > ms) ms = subs[k].s1 - subs[k].s0;
-        if ((uint64_t)(subs[k].c1 - subs[k].c0) > mc) mc = subs[k].c1 - subs[k].c0;
+        if (subs[k].smem) { if (nr > mrs) mrs = nr; }
+        else any_global = true;
     }
     int rc;
     if ((rc = ensure(e, e->sc_aoff, 4ull * (mr + mc + 1)))) return rc;
-    if ((rc = ensure(e, e->sc_segid, mr + 16))) return rc;
-    if ((rc = ensure(e, e->sc_tor, 24ull * mr + 16))) return rc;
-    if ((rc = ensure(e, e->sc_ang, 24ull * mr + 16))) return rc;
     if ((rc = ensure(e, e->sc_rev, 36ull * mr + 16))) return rc;
     if ((rc = ensure(e, e->sc_seg, 4ull * FCZ_SEG_FLOATS * (ms + 1)))) return rc;
+    if (mrs && (rc = ensure(e, e->sc_loc, 36ull * mrs + 16))) return rc;
+    if (any_global) {
+        if ((rc = ensure(e, e->sc_segid, mr + 16))) return rc;
+        if ((rc = ensure(e, e->sc_tor, 24ull * mr + 16))) return rc;
+        if ((rc = ensure(e, e->sc_ang, 24ull * mr + 16))) return rc;
+    }
     return FCZ_OK;
 }
 
-// the five phase kernels over one sub-batch (a carries the batch pointers)
+// the phase kernels over one sub-batch (a carries the batch pointers)
 static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb) {
     const uint32_t nch = sb.c1 - sb.c0;
     if (!nch) return FCZ_OK;
     a.c0 = sb.c0; a.c1 = sb.c1; a.r_base = sb.r0; a.s_base = sb.s0;
-    a.aoff = (uint32_t*)e->sc_aoff.p; a.segid = (uint8_t*)e->sc_segid.p; a.tor = (cs*)e->sc_tor.p; a.ang = (cs*)e->sc_ang.p;
-    a.rev = (float*)e->sc_rev.p; a.seg = (float*)e->sc_seg.p;
+    a.aoff = (uint32_t*)e->sc_aoff.p; a.rev = (float*)e->sc_rev.p; a.seg = (float*)e->sc_seg.p;
+    if (sb.smem) {
+        a.loc = (float*)e->sc_loc.p;
+        a.max_L = sb.max_L; a.max_anchor = sb.max_anchor; a.max_blob = sb.max_blob; a.max_atoms = sb.max_atoms;
+        const FrontSmem fs = front_smem(sb.max_L, sb.max_anchor, sb.max_blob);
+        const BackSmem bs = back_smem(sb.max_L, sb.max_anchor, sb.max_atoms);
+        // stitch: one wave when it fits -- chains per block = ceil(chains / SMs), bounded by shared memory
+        const uint32_t cbytes = stitch_chain_bytes(sb.max_anchor);
+        uint32_t G = (nch + (uint32_t)e->num_sms - 1u) / (uint32_t)e->num_sms;
+        const uint32_t gmax = (FCZ_SMEM_LIMIT - 1024u) / cbytes;
+        if (G > gmax) G = gmax;
+        if (G > 256u) G = 256u;
+        if (G < 1u) G = 1u;
+        a.stitch_group = G;
+        k_dec_front<<<nch, 128, fs.total, e->stream>>>(a);
+        k_dec_stitch_t<<<(nch + G - 1u) / G, 256, G * cbytes, e->stream>>>(a);
+        k_dec_back<<<nch, 192, bs.total, e->stream>>>(a);
+        e->launches += 3;
+        return FCZ_OK;
+    }
+    a.segid = (uint8_t*)e->sc_segid.p; a.tor = (cs*)e->sc_tor.p; a.ang = (cs*)e->sc_ang.p;
     k_dec_unpack<<<nch, 256, 0, e->stream>>>(a);
     k_dec_passes<<<nch, 64, 0, e->stream>>>(a);
     k_dec_stitch<<<(nch + 127) / 128, 128, 0, e->stream>>>(a);
@@ -1335,7 +1622,13 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
     std::vector<Dec2Sub> subs(nchunks);
     for (uint32_t k = 0; k < nchunks; k++) {
         const uint32_t c0 = plan.chunk_c0[k], c1 = plan.chunk_c0[k + 1];
-        subs[k] = {c0, c1, out->res_off[c0], out->res_off[c1], plan.seg_off[c0], plan.seg_off[c1]};
+        subs[k] = {c0, c1, out->res_off[c0], out->res_off[c1], plan.seg_off[c0], plan.seg_off[c1], 0, 0, 0, 0, false};
+        for (uint32_t c = c0; c < c1; c++) {
+            subs[k].max_L = std::max(subs[k].max_L, out->res_off[c + 1] - out->res_off[c]);
+            subs[k].max_anchor = std::max(subs[k].max_anchor, plan.seg_off[c + 1] - plan.seg_off[c]);
+            subs[k].max_blob = std::max(subs[k].max_blob, (uint32_t)(in->blob_off[c + 1] - in->blob_off[c]));
+            subs[k].max_atoms = std::max(subs[k].max_atoms, (uint32_t)(out->atom_off[c + 1] - out->atom_off[c]));
+        }
     }
     if ((rc = dec2_workspace(e, subs.data(), subs.size()))) return rc;
 
@@ -1426,7 +1719,8 @@ static int decode_plan_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain
     sa.in[2] = po.v2; sa.out[2] = out->title_off; sa.out64[2] = 0;
     sa.in[3] = po.v3; sa.out[3] = e->d_seg_off.p; sa.out64[3] = 0;
     if ((rc = run_scan(e, sa))) return rc;
-    k_plan_chunks<<<1, 32, 0, e->stream>>>(n, out->res_off, (uint32_t*)e->d_seg_off.p, e->h_bounds);
+    k_plan_chunks<<<n / 256 + 1, 256, 0, e->stream>>>(n, e->dec_sub_res, out->res_off, (uint32_t*)e->d_seg_off.p, out->atom_off, in->blob_off,
+                                                  (uint32_t*)e->d_submax.p, e->h_bounds);
     e->launches++;
     if ((rc = fetch_plan(e))) return rc;
     totals->n_res = e->h_totals[0];
@@ -1445,7 +1739,8 @@ static int decode_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batc
     std::vector<Dec2Sub> subs(nsub);
     for (uint32_t k = 0; k < nsub; k++) {
         const uint32_t* b = e->h_bounds + 1 + 3 * k;
-        subs[k] = {b[0], b[3], b[1], b[4], b[2], b[5]};
+        const uint32_t* m = e->h_bounds + 1 + 3 * (nsub + 1) + 4 * k;
+        subs[k] = {b[0], b[3], b[1], b[4], b[2], b[5], m[0], m[1], m[2], m[3], false};
     }
     int rc;
     if ((rc = dec2_workspace(e, subs.data(), subs.size()))) return rc;
