@@ -389,6 +389,9 @@ struct DecChain {
     float* rev;           // [9L] reverse-pass backbone atoms (true coordinates)
     const float* loc;     // [9L] forward-pass (local) backbone atoms when they do not live in out_xyz, else NULL
     uint8_t* segid;       // [L] anchor segment that owns (emits) each residue
+    uint16_t* order;      // [L] residues sorted by atom count (side chains), with bins[32] u32 of scratch; or NULL
+    uint32_t* bins;
+    const uint8_t* codes;  // [L] residue codes when a copy is at hand (else read from the records), or NULL
 };
 
 // y = R x + t, T = rows of R (9) then t (3)
@@ -487,6 +490,60 @@ FCZ_HD void dec_unpack(Ctx& cx, const Tables* tb, const DecChain& ch) {
     }
 }
 
+// One work item of phase 2: component k of the forward (dir 0) or reverse (dir 1) pass of segment s; see dec_passes.
+FCZ_HD void dec_pass_item(const Tables* tb, const DecChain& ch, int dir, int s, int k) {
+    (void)tb;
+    const uint8_t* rec = ch.blob + ch.y.o_rec;
+    float* sg = ch.seg + s * FCZ_SEG_FLOATS;
+    const uint32_t a0 = seg_a0(sg), a1 = seg_a1(sg);
+    if (dir == 0) {
+        const f3 p0 = ld3(sg + SEG_A), p1 = ld3(sg + SEG_A + 3), p2 = ld3(sg + SEG_A + 6);
+        const NerfFrame F = frame_from(p0, p1, p2);
+        NerfFrame1 f = {comp3(F.bcn, k), comp3(F.nbc, k), comp3(F.n, k)};
+        float q0 = comp3(p0, k), q1 = comp3(p1, k), q2 = comp3(p2, k);
+        for (uint32_t r = a0; r < a1; r++) {
+            const uint32_t t = 3u * r;
+            q0 = nerf_step1(f, q2, FCZ_C_TO_N, ch.ang[t], ch.tor[t]);                             // N
+            q1 = nerf_step1(f, q0, n_ca_len(rec[8u * r] >> 3), ch.ang[t + 1u], ch.tor[t + 1u]);  // CA
+            q2 = nerf_step1(f, q1, FCZ_CA_TO_C, ch.ang[t + 2u], ch.tor[t + 2u]);                  // C
+            float* o = ch.out_xyz + 3u * ch.aoff[r + 1u] + k;
+            o[0] = q0; o[3] = q1; o[6] = q2;
+            if (k == 0) ch.segid[r] = (uint8_t)s;
+            if (r == a0) {  // frame carried by the first placed residue, origin at its C
+                sg[SEG_F + k] = f.bcn; sg[SEG_F + 3 + k] = f.nbc; sg[SEG_F + 6 + k] = f.n; sg[SEG_F + 9 + k] = q2;
+                sg[SEG_HEAD + k] = q0; sg[SEG_HEAD + 3 + k] = q1;
+                if (k == 0) {
+                    for (int j = 0; j < 3; j++) {  // what the stitch needs of the first record
+                        sg[SEG_CS + 2 * j] = ch.ang[t + j].c; sg[SEG_CS + 2 * j + 1] = ch.ang[t + j].s;
+                        sg[SEG_CS + 6 + 2 * j] = ch.tor[t + j].c; sg[SEG_CS + 6 + 2 * j + 1] = ch.tor[t + j].s;
+                    }
+                    sg[SEG_CS + 12] = n_ca_len(rec[8u * r] >> 3);
+                }
+            }
+        }
+        sg[SEG_TAIL + k] = q0; sg[SEG_TAIL + 3 + k] = q1; sg[SEG_TAIL + 6 + k] = q2;
+    } else if (a1 > a0) {
+        const float* anc = sg + FCZ_SEG_FLOATS + SEG_A;
+        // reversed chain starts as the stored anchor: a = C, b = CA, c = N
+        const f3 pn = ld3(anc);
+        const NerfFrame F = frame_from(ld3(anc + 6), ld3(anc + 3), pn);
+        NerfFrame1 f = {comp3(F.bcn, k), comp3(F.nbc, k), comp3(F.n, k)};
+        float rc = comp3(pn, k);
+        // atoms q = n-4 .. 3 are C, CA, N of residues a1-1 .. a0+1; g = backbone atom index in the chain
+        for (uint32_t r = a1 - 1u; r > a0; r--) {
+            const uint32_t g = 3u * r;
+            const cs b2 = ch.ang[g + 1u], b1 = ch.ang[g], b0 = ch.ang[g - 1u];  // angle at atom g+k+1
+            const cs t2 = ch.tor[g + 2u], t1 = ch.tor[g + 1u], t0 = ch.tor[g];  // torsion g+k
+            const float c = nerf_step1(f, rc, FCZ_C_TO_N, b2, t2);
+            const float ca = nerf_step1(f, c, FCZ_CA_TO_C, b1, t1);
+            rc = nerf_step1(f, ca, FCZ_N_TO_CA, b0, t0);
+            float* o = ch.rev + 3u * g + k;
+            o[0] = rc; o[3] = ca; o[6] = c;
+        }
+        sg[SEG_RF + k] = f.bcn; sg[SEG_RF + 3 + k] = f.nbc; sg[SEG_RF + 6 + k] = f.n; sg[SEG_RF + 9 + k] = rc;
+    }
+}
+
 template <class Ctx>
 FCZ_HD void dec_passes(Ctx& cx, const Tables* tb, const DecChain& ch) {
     const Layout& y = ch.y;
@@ -510,55 +567,17 @@ FCZ_HD void dec_passes(Ctx& cx, const Tables* tb, const DecChain& ch) {
     //   Bond lengths by atom kind, never the Pro length (src/nerf.h:37-43).  The last three reverse atoms
     //   depend on the true start atoms and are finished in phase 4.
     // (forward and reverse lanes sit in DIFFERENT warps: lanes of one warp would serialise the two loops)
-    const int n_grp = (n_seg + cx.wsize - 1) / cx.wsize;
-    for (int idx = cx.warp; idx < 2 * n_grp; idx += cx.nwarps) {
-        const int s = (idx >> 1) * cx.wsize + cx.lane;
-        if (s >= n_seg) continue;
-        float* sg = ch.seg + s * FCZ_SEG_FLOATS;
-        const uint32_t a0 = seg_a0(sg), a1 = seg_a1(sg);
-        if ((idx & 1) == 0) {
-            f3 p0 = ld3(sg + SEG_A), p1 = ld3(sg + SEG_A + 3), p2 = ld3(sg + SEG_A + 6);
-            NerfFrame f = frame_from(p0, p1, p2);
-            for (uint32_t r = a0; r < a1; r++) {
-                const uint32_t t = 3u * r;
-                p0 = nerf_step(f, p2, FCZ_C_TO_N, ch.ang[t], ch.tor[t]);                             // N
-                p1 = nerf_step(f, p0, n_ca_len(rec[8u * r] >> 3), ch.ang[t + 1u], ch.tor[t + 1u]);  // CA
-                p2 = nerf_step(f, p1, FCZ_CA_TO_C, ch.ang[t + 2u], ch.tor[t + 2u]);                  // C
-                float* o = ch.out_xyz + 3u * ch.aoff[r + 1u];
-                st3(o, p0); st3(o + 3, p1); st3(o + 6, p2);
-                ch.segid[r] = (uint8_t)s;
-                if (r == a0) {  // frame carried by the first placed residue, origin at its C
-                    st3(sg + SEG_F, f.bcn); st3(sg + SEG_F + 3, f.nbc); st3(sg + SEG_F + 6, f.n); st3(sg + SEG_F + 9, p2);
-                    st3(sg + SEG_HEAD, p0); st3(sg + SEG_HEAD + 3, p1);
-                    for (int j = 0; j < 3; j++) {  // what the stitch needs of the first record
-                        sg[SEG_CS + 2 * j] = ch.ang[t + j].c; sg[SEG_CS + 2 * j + 1] = ch.ang[t + j].s;
-                        sg[SEG_CS + 6 + 2 * j] = ch.tor[t + j].c; sg[SEG_CS + 6 + 2 * j + 1] = ch.tor[t + j].s;
-                    }
-                    sg[SEG_CS + 12] = n_ca_len(rec[8u * r] >> 3);
-                }
-            }
-            st3(sg + SEG_TAIL, p0); st3(sg + SEG_TAIL + 3, p1); st3(sg + SEG_TAIL + 6, p2);
-        } else if (a1 > a0) {
-            const int n = (int)(3u * (a1 - a0 + 1u));
-            const float* anc = sg + FCZ_SEG_FLOATS + SEG_A;
-            // reversed chain starts as the stored anchor: a = C, b = CA, c = N
-            f3 rc = ld3(anc);
-            NerfFrame f = frame_from(ld3(anc + 6), ld3(anc + 3), rc);
-            // residue-wise (three placements per trip, so the six table loads of a trip issue together):
-            // atoms q = n-4 .. 3 are C, CA, N of residues a1-1 .. a0+1; g = backbone atom index in the chain
-            for (uint32_t r = a1 - 1u; r > a0; r--) {
-                const uint32_t g = 3u * r;
-                const cs b2 = ch.ang[g + 1u], b1 = ch.ang[g], b0 = ch.ang[g - 1u];  // angle at atom g+k+1
-                const cs t2 = ch.tor[g + 2u], t1 = ch.tor[g + 1u], t0 = ch.tor[g];  // torsion g+k
-                const f3 c = nerf_step(f, rc, FCZ_C_TO_N, b2, t2);
-                const f3 ca = nerf_step(f, c, FCZ_CA_TO_C, b1, t1);
-                rc = nerf_step(f, ca, FCZ_N_TO_CA, b0, t0);
-                float* o = ch.rev + 3u * g;
-                st3(o, rc); st3(o + 3, ca); st3(o + 6, c);
-            }
-            (void)n;
-            st3(sg + SEG_RF, f.bcn); st3(sg + SEG_RF + 3, f.nbc); st3(sg + SEG_RF + 6, f.n); st3(sg + SEG_RF + 9, rc);
-        }
+    // Each pass of a segment is shared by THREE lanes, one per Cartesian component (nerf_step1): work items
+    // (direction, segment, component); the first half of the warps takes the forward items, the rest the reverse.
+    const int items = 3 * n_seg;
+    if (cx.nwarps >= 2) {
+        const int half = cx.nwarps / 2;
+        const int dir = cx.warp >= half ? 1 : 0;
+        const int w = dir ? cx.warp - half : cx.warp, nw = dir ? cx.nwarps - half : half;
+        for (int i = w * cx.wsize + cx.lane; i < items; i += nw * cx.wsize) dec_pass_item(tb, ch, dir, i / 3, i - 3 * (i / 3));
+    } else {
+        for (int dir = 0; dir < 2; dir++)
+            for (int i = cx.tid; i < items; i += cx.nthr) dec_pass_item(tb, ch, dir, i / 3, i - 3 * (i / 3));
     }
 }
 
@@ -693,8 +712,14 @@ FCZ_HD void dec_blend(Ctx& cx, const Tables* tb, const DecChain& ch) {
             f2 = f1; f1 = f0;
         }
     }
+    const float* locp = ch.loc ? ch.loc : nullptr;
+#pragma unroll 3
     for (uint32_t g = 3u + cx.tid; g < 3u * L - 3u; g += cx.nthr) {
         const uint32_t r = g / 3u, k = g - 3u * r;
+        // both inputs first (global memory on the three-kernel path): their latency overlaps across the unrolled trips
+        const f3 rv = ld3(ch.rev + 3u * g);
+        float* slot = ch.out_xyz + 3u * (ch.aoff[r] + k);
+        const f3 local = locp ? ld3(locp + 3u * g) : ld3(slot);
         const int s = ch.segid[r - 1u];  // residue r was placed while consuming record r-1
         const float* sg = ch.seg + s * FCZ_SEG_FLOATS;
         const uint32_t a0 = seg_a0(sg), a1 = seg_a1(sg);
@@ -703,9 +728,7 @@ FCZ_HD void dec_blend(Ctx& cx, const Tables* tb, const DecChain& ch) {
             continue;
         }
         const int q = (int)(g - 3u * a0), n = (int)(3u * (a1 - a0 + 1u));
-        float* slot = ch.out_xyz + 3u * (ch.aoff[r] + k);
-        const f3 local = ch.loc ? ld3(ch.loc + 3u * g) : ld3(slot);
-        st3(slot, blend(xform(sg + SEG_T, local), ld3(ch.rev + 3u * g), (float)(n - q), (float)q, sg[SEG_I + 2]));
+        st3(slot, blend(xform(sg + SEG_T, local), rv, (float)(n - q), (float)q, sg[SEG_I + 2]));
     }
 }
 
@@ -724,26 +747,40 @@ FCZ_HD void dec_side(Ctx& cx, const Tables* tb, const DecChain& ch) {
     // FixedAngleDiscretizer(255).continuize(byte), src/foldcomp.cpp:338-369, read from a 256-entry table.
     {
         const uint8_t* sc = blob + y.o_sc;
-        for (uint32_t i = cx.tid; 2u * i < L; i += cx.nthr) {
-            const uint32_t rA = 2u * i, rB = (2u * i + 1u < L) ? 2u * i + 1u : rA;
-            const unsigned cA = rec[8u * rA] >> 3, cB = rec[8u * rB] >> 3;
-            const uint32_t oA = ch.aoff[rA], oB = ch.aoff[rB];
-            const uint32_t nA = tb->natoms[cA], nB = (rB != rA) ? tb->natoms[cB] : 0u;
-            float* RA = ch.out_xyz + 3u * oA;
-            float* RB = ch.out_xyz + 3u * oB;
-            const uint8_t* sA = sc + (oA - 3u * rA);
-            const uint8_t* sB = sc + (oB - 3u * rB);
-            const uint32_t nmax = nA > nB ? nA : nB;
-            for (uint32_t k = 3u; k < nmax; k++) {
-                const bool doA = k < nA, doB = k < nB;
-                const uint32_t kA = doA ? k : 3u, kB = doB ? k : 3u;  // idle side re-places slot 3 (result discarded)
-                const unsigned pA = tb->pred[cA][kA], pB = tb->pred[cB][kB];
-                const f3 vA = place_from(ld3(RA + 3u * (pA & 15u)), ld3(RA + 3u * ((pA >> 4) & 15u)), ld3(RA + 3u * ((pA >> 8) & 15u)),
-                                         tb->blen[cA][kA], tb->bang[cA][kA], tb->sc_tor[sA[kA - 3u]]);
-                const f3 vB = place_from(ld3(RB + 3u * (pB & 15u)), ld3(RB + 3u * ((pB >> 4) & 15u)), ld3(RB + 3u * ((pB >> 8) & 15u)),
-                                         tb->blen[cB][kB], tb->bang[cB][kB], tb->sc_tor[sB[kB - 3u]]);
-                if (doA) st3(RA + 3u * k, vA);
-                if (doB) st3(RB + 3u * k, vB);
+        // Residues sorted by atom count (counting sort, longest first) so that the lanes of a warp -- and the two
+        // residues of a pair -- run the same number of placements: a warp costs its longest lane.
+        const uint16_t* ord = nullptr;
+        if (ch.order) {
+            uint32_t* bins = ch.bins;  // [0,16) counts by atom count, [16,32) write cursors
+            for (uint32_t i = cx.tid; i < 32u; i += cx.nthr) bins[i] = 0u;
+            cx.sync();
+            for (uint32_t r = cx.tid; r < L; r += cx.nthr) cx.atomic_add(&bins[(ch.aoff[r + 1u] - ch.aoff[r]) & 15u], 1u);
+            cx.sync();
+            if (cx.tid == 0) {
+                uint32_t acc = 0;
+                for (int k = 15; k >= 0; k--) { bins[16 + k] = acc; acc += bins[k]; }
+            }
+            cx.sync();
+            for (uint32_t r = cx.tid; r < L; r += cx.nthr) ch.order[cx.atomic_add(&bins[16u + ((ch.aoff[r + 1u] - ch.aoff[r]) & 15u)], 1u)] = (uint16_t)r;
+            cx.sync();
+            ord = ch.order;
+        }
+        // one lane per residue; warp-sized runs of the sorted order are dealt to the warps boustrophedon
+        // (0..n-1, n-1..0, ...) so that every warp gets long and short runs
+        const uint32_t runs = (L + cx.wsize - 1u) / cx.wsize;
+        for (uint32_t cyc = 0; cyc * cx.nwarps < runs; cyc++) {
+            const uint32_t j = cyc * cx.nwarps + ((cyc & 1u) ? (uint32_t)(cx.nwarps - 1 - cx.warp) : (uint32_t)cx.warp);
+            const uint32_t i = j * cx.wsize + cx.lane;
+            if (j >= runs || i >= L) continue;
+            const uint32_t r = ord ? ord[i] : i;
+            const unsigned code = ch.codes ? ch.codes[r] : (unsigned)(rec[8u * r] >> 3);
+            const uint32_t o = ch.aoff[r], n = ch.aoff[r + 1u] - o;
+            float* R = ch.out_xyz + 3u * o;
+            const uint8_t* sb = sc + (o - 3u * r);
+            for (uint32_t k = 3u; k < n; k++) {
+                const unsigned pp = tb->pred[code][k];
+                st3(R + 3u * k, place_from(ld3(R + 3u * (pp & 15u)), ld3(R + 3u * ((pp >> 4) & 15u)), ld3(R + 3u * ((pp >> 8) & 15u)),
+                                           tb->blen[code][k], tb->bang[code][k], tb->sc_tor[sb[k - 3u]]));
             }
         }
         cx.sync();
@@ -762,20 +799,12 @@ FCZ_HD void dec_side(Ctx& cx, const Tables* tb, const DecChain& ch) {
 
 template <class Ctx>
 FCZ_HD void decode_chain(Ctx& cx, const Tables* tb, const DecChain& ch) {
-    const int n_seg = (int)ch.y.n_anchor - 1;
     dec_unpack(cx, tb, ch);
     cx.sync();
     cx.mark(8);  // D_UNPACK
-    // When all segments fit one warp (the common case) the stitch starts as soon as the forward lanes of warp 0
-    // are done and overlaps with the reverse lanes running in warp 1.
-    const bool fused = (n_seg + cx.wsize - 1) / cx.wsize == 1 && cx.nwarps >= 2;
     dec_passes(cx, tb, ch);
-    if (!fused) {
-        cx.sync();
-        cx.mark(9);  // D_PASSES
-    } else if (cx.warp == 0) {
-        cx.wsync();  // the forward lanes (all in warp 0) have published SEG_F / SEG_TAIL
-    }
+    cx.sync();
+    cx.mark(9);  // D_PASSES
     dec_stitch(cx, tb, ch);
     cx.sync();
     cx.mark(10);  // D_STITCH

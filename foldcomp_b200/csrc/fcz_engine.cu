@@ -128,6 +128,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 #ifdef FCZ_PHASE_TIMING
 // Debug build only (libfcz_engine_timing.so): cycles spent between phase marks, summed over chains.
 // ids: 0-3 encode phases, 4 encode stage/copy-out, 8-12 decode phases, 13 decode stage-in, 14 decode copy-out
@@ -157,6 +165,7 @@ struct DevCtx {
     bool staged;      // a bulk copy is in flight for this chain
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ void wsync() { __syncwarp(); }
+    __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
     __device__ __forceinline__ void stage_wait() {
         if (staged) mbar_wait(bar, parity);
     }
@@ -519,6 +528,7 @@ __device__ __forceinline__ bool dec2_chain(const Dec2Args& a, uint32_t c, DecCha
     ch.ang = a.ang + 3u * (size_t)rr;
     ch.rev = a.rev + 9u * (size_t)rr;
     ch.loc = nullptr;
+    ch.order = nullptr; ch.bins = nullptr; ch.codes = nullptr;
     ch.seg = a.seg + (size_t)(a.seg_off[c] - a.s_base) * FCZ_SEG_FLOATS;
     return true;
 }
@@ -544,7 +554,7 @@ __global__ void __launch_bounds__(256) k_dec_unpack(Dec2Args a) {  // block per 
     DevCtx cx = block_ctx(wsum);
     dec_unpack(cx, a.tables, ch);
 }
-__global__ void __launch_bounds__(64) k_dec_passes(Dec2Args a) {  // two warps per chain: forward lanes, reverse lanes
+__global__ void __launch_bounds__(128) k_dec_passes(Dec2Args a) {  // block per chain: forward items in two warps, reverse items in two
     DecChain ch;
     if (!dec2_chain(a, a.c0 + blockIdx.x, ch)) return;
     DevCtx cx = block_ctx(nullptr);
@@ -592,13 +602,15 @@ __host__ __device__ inline FrontSmem front_smem(uint32_t max_L, uint32_t max_anc
     o.total = p;
     return o;
 }
-struct BackSmem { uint32_t o_seg, o_aoff, o_segid, o_out, total; };
+struct BackSmem { uint32_t o_seg, o_aoff, o_segid, o_codes, o_order, o_out, total; };
 __host__ __device__ inline BackSmem back_smem(uint32_t max_L, uint32_t max_anchor, uint32_t max_atoms) {
     BackSmem o;
     uint32_t p = 0;
     o.o_seg = p; p += up16(4u * FCZ_SEG_FLOATS * (max_anchor + 1u));
     o.o_aoff = p; p += up16(4u * (max_L + 1u));
     o.o_segid = p; p += up16(max_L);
+    o.o_codes = p; p += up16(max_L);
+    o.o_order = p; p += up16(2u * max_L) + 128u;  // sorted residues + 32 bins
     o.o_out = p; p += up16(12u * max_atoms) + 32u;
     o.total = p;
     return o;
@@ -607,7 +619,15 @@ __host__ __device__ inline BackSmem back_smem(uint32_t max_L, uint32_t max_ancho
 __global__ void __launch_bounds__(128) k_dec_front(Dec2Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t c = a.c0 + blockIdx.x;
-    if (a.status[c] != FCZ_OK) return;
+    // everything about the chain from the offset arrays (independent loads, one round trip): the plan has
+    // already checked them against the blob header
+    const int32_t st = a.status[c];
+    const uint64_t b0 = a.blob_off[c], b1 = a.blob_off[c + 1];
+    const uint32_t r0 = a.res_off[c], L = a.res_off[c + 1] - r0;
+    const uint32_t A = (uint32_t)(a.atom_off[c + 1] - a.atom_off[c]);
+    const uint32_t t0 = a.title_off[c], T = a.title_off[c + 1] - t0;
+    const uint32_t g0 = a.seg_off[c], nA = a.seg_off[c + 1] - g0;
+    if (st != FCZ_OK) return;
     const FrontSmem so = front_smem(a.max_L, a.max_anchor, a.max_blob);
     DevCtx cx = block_ctx(reinterpret_cast<uint32_t*>(smem + 64));
     cx.bar = reinterpret_cast<uint64_t*>(smem);
@@ -616,18 +636,18 @@ __global__ void __launch_bounds__(128) k_dec_front(Dec2Args a) {
 #endif
     if (cx.tid == 0) mbar_init(cx.bar, 1);
     __syncthreads();
-    const uint8_t* gblob = a.bytes + a.blob_off[c];
-    const uint32_t len = (uint32_t)(a.blob_off[c + 1] - a.blob_off[c]);
+    const uint8_t* gblob = a.bytes + b0;
+    const uint32_t len = (uint32_t)(b1 - b0);
     DecChain ch;
-    ch.y = make_layout(get_u16(gblob + OFF_NRES), get_u32(gblob + OFF_NSC), get_u32(gblob + OFF_LENTITLE), gblob[OFF_NANCHOR]);
+    ch.y = make_layout(L, A - 3u * L, T, nA);
     const uint32_t size = ch.y.size < len ? ch.y.size : len;
     ch.blob = stage_in(cx, smem + so.o_blob, gblob, size);
     ch.use_alt = a.use_alt;
-    const uint32_t r0 = a.res_off[c], rr = r0 - a.r_base, L = ch.y.L, nA = ch.y.n_anchor;
+    const uint32_t rr = r0 - a.r_base;
     ch.out_type = a.res_type + r0;
     ch.out_bfac = a.bfactor + r0;
     ch.out_meta = a.meta + c;
-    ch.out_title = a.titles ? a.titles + a.title_off[c] : nullptr;
+    ch.out_title = a.titles ? a.titles + t0 : nullptr;
     ch.aoff = reinterpret_cast<uint32_t*>(smem + so.o_aoff);
     ch.segid = smem + so.o_segid;
     ch.tor = reinterpret_cast<cs*>(smem + so.o_tor);
@@ -636,6 +656,7 @@ __global__ void __launch_bounds__(128) k_dec_front(Dec2Args a) {
     ch.rev = a.rev + 9u * (size_t)rr;
     ch.out_xyz = a.loc + 9u * (size_t)rr;  // forward atoms of residue r at 9r: see the offsets below
     ch.loc = nullptr;
+    ch.order = nullptr; ch.bins = nullptr; ch.codes = nullptr;
     __builtin_assume(__isShared(ch.blob));
     __builtin_assume(__isShared(ch.aoff));
     __builtin_assume(__isShared(ch.segid));
@@ -655,7 +676,7 @@ __global__ void __launch_bounds__(128) k_dec_front(Dec2Args a) {
     dec_passes(cx, a.tables, ch);
     __syncthreads();
     cx.mark(9);
-    float4* gseg = reinterpret_cast<float4*>(a.seg + (size_t)(a.seg_off[c] - a.s_base) * FCZ_SEG_FLOATS);
+    float4* gseg = reinterpret_cast<float4*>(a.seg + (size_t)(g0 - a.s_base) * FCZ_SEG_FLOATS);
     const float4* sseg = reinterpret_cast<const float4*>(ch.seg);
     for (uint32_t e = cx.tid; e < nA * (FCZ_SEG_FLOATS / 4u); e += cx.nthr) gseg[e] = sseg[e];
     cx.mark(14);
@@ -664,7 +685,7 @@ __global__ void __launch_bounds__(128) k_dec_front(Dec2Args a) {
 // stitch: block = stitch_group chains, one thread per chain walks the segments.  The fields it reads are first
 // gathered (all threads, coalesced over each chain's scratch) into shared memory, packed 46 floats per slot with
 // an odd per-chain stride (conflict-free for thread-per-chain access); S and T come back the same way.
-__global__ void __launch_bounds__(256) k_dec_stitch_t(Dec2Args a) {
+__global__ void __launch_bounds__(1024) k_dec_stitch_t(Dec2Args a) {
     extern __shared__ __align__(16) float sm[];
     const uint32_t G = a.stitch_group, cstride = (a.max_anchor * SegPacked::N) | 1u;
     const uint32_t cb = a.c0 + blockIdx.x * G;
@@ -717,20 +738,25 @@ __global__ void __launch_bounds__(192) k_dec_back(Dec2Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t wsum[32];
     const uint32_t c = a.c0 + blockIdx.x;
-    if (a.status[c] != FCZ_OK) return;
+    const int32_t st = a.status[c];
+    const uint64_t b0 = a.blob_off[c];
+    const uint32_t r0 = a.res_off[c], L = a.res_off[c + 1] - r0;
+    const uint64_t a0 = a.atom_off[c];
+    const uint32_t A = (uint32_t)(a.atom_off[c + 1] - a0);
+    const uint32_t T = a.title_off[c + 1] - a.title_off[c];
+    const uint32_t g0 = a.seg_off[c], nA = a.seg_off[c + 1] - g0;
+    if (st != FCZ_OK) return;
     const BackSmem so = back_smem(a.max_L, a.max_anchor, a.max_atoms);
     DevCtx cx = block_ctx(wsum);
 #ifdef FCZ_PHASE_TIMING
     cx.t_last = clock64();
 #endif
-    const uint8_t* blob = a.bytes + a.blob_off[c];
+    const uint8_t* blob = a.bytes + b0;
     DecChain ch;
     ch.blob = blob;
-    ch.y = make_layout(get_u16(blob + OFF_NRES), get_u32(blob + OFF_NSC), get_u32(blob + OFF_LENTITLE), blob[OFF_NANCHOR]);
+    ch.y = make_layout(L, A - 3u * L, T, nA);
     ch.use_alt = a.use_alt;
-    const uint32_t r0 = a.res_off[c], rr = r0 - a.r_base, L = ch.y.L, nA = ch.y.n_anchor;
-    const uint64_t a0 = a.atom_off[c];
-    const uint32_t A = (uint32_t)(a.atom_off[c + 1] - a0);
+    const uint32_t rr = r0 - a.r_base;
     uint8_t* gdst = reinterpret_cast<uint8_t*>(a.xyz + 3u * a0);
     uint8_t* sdst = smem + so.o_out + ((uintptr_t)gdst & 15u);
     ch.out_xyz = reinterpret_cast<float*>(sdst);
@@ -738,6 +764,8 @@ __global__ void __launch_bounds__(192) k_dec_back(Dec2Args a) {
     ch.aoff = reinterpret_cast<uint32_t*>(smem + so.o_aoff);
     ch.segid = smem + so.o_segid;
     ch.tor = nullptr; ch.ang = nullptr;
+    ch.order = reinterpret_cast<uint16_t*>(smem + so.o_order + 128u);
+    ch.bins = reinterpret_cast<uint32_t*>(smem + so.o_order);
     ch.seg = reinterpret_cast<float*>(smem + so.o_seg);
     ch.rev = a.rev + 9u * (size_t)rr;
     ch.loc = a.loc + 9u * (size_t)rr;
@@ -745,12 +773,20 @@ __global__ void __launch_bounds__(192) k_dec_back(Dec2Args a) {
     __builtin_assume(__isShared(ch.aoff));
     __builtin_assume(__isShared(ch.segid));
     __builtin_assume(__isShared(ch.seg));
-    const uint32_t* g_aoff = a.aoff + rr + (c - a.c0);
-    for (uint32_t r = cx.tid; r <= L; r += cx.nthr) ch.aoff[r] = g_aoff[r];
+    __builtin_assume(__isShared(ch.order));
+    __builtin_assume(__isShared(ch.bins));
+    // inputs of the first phases: asynchronous copies straight into shared memory, all in flight together
     {
-        const float4* gseg = reinterpret_cast<const float4*>(a.seg + (size_t)(a.seg_off[c] - a.s_base) * FCZ_SEG_FLOATS);
+        const uint32_t* g_aoff = a.aoff + rr + (c - a.c0);
+        for (uint32_t r = cx.tid; r <= L; r += cx.nthr) cp_async4(ch.aoff + r, g_aoff + r);
+        const float4* gseg = reinterpret_cast<const float4*>(a.seg + (size_t)(g0 - a.s_base) * FCZ_SEG_FLOATS);
         float4* sseg = reinterpret_cast<float4*>(ch.seg);
-        for (uint32_t e = cx.tid; e < nA * (FCZ_SEG_FLOATS / 4u); e += cx.nthr) sseg[e] = gseg[e];
+        for (uint32_t e = cx.tid; e < nA * (FCZ_SEG_FLOATS / 4u); e += cx.nthr) cp_async16(sseg + e, gseg + e);
+        uint8_t* codes = smem + so.o_codes;
+        const uint8_t* gtype = a.res_type + r0;  // written by the front kernel
+        for (uint32_t r = cx.tid; r < L; r += cx.nthr) codes[r] = gtype[r];
+        ch.codes = codes;
+        cp_async_wait_all();
     }
     __syncthreads();
     for (uint32_t s = cx.tid; s + 1u < nA; s += cx.nthr) {
@@ -1541,14 +1577,14 @@ static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb) {
         if (G < 1u) G = 1u;
         a.stitch_group = G;
         k_dec_front<<<nch, 128, fs.total, e->stream>>>(a);
-        k_dec_stitch_t<<<(nch + G - 1u) / G, 256, G * cbytes, e->stream>>>(a);
+        k_dec_stitch_t<<<(nch + G - 1u) / G, 1024, G * cbytes, e->stream>>>(a);
         k_dec_back<<<nch, 192, bs.total, e->stream>>>(a);
         e->launches += 3;
         return FCZ_OK;
     }
     a.segid = (uint8_t*)e->sc_segid.p; a.tor = (cs*)e->sc_tor.p; a.ang = (cs*)e->sc_ang.p;
     k_dec_unpack<<<nch, 256, 0, e->stream>>>(a);
-    k_dec_passes<<<nch, 64, 0, e->stream>>>(a);
+    k_dec_passes<<<nch, 128, 0, e->stream>>>(a);
     k_dec_stitch<<<(nch + 127) / 128, 128, 0, e->stream>>>(a);
     k_dec_blend<<<nch, 128, 0, e->stream>>>(a);
     k_dec_side<<<nch, 192, 0, e->stream>>>(a);

@@ -211,7 +211,7 @@ FCZ_HD float deg2rad(float deg) { return (float)((double)deg * (M_PI / 180.0)); 
 struct cs {
     float c, s;
 };
-FCZ_HD cs cossin_deg(float deg) {
+FCZ_HD_SLOW cs cossin_deg_slow(float deg) {
     float r = deg2rad(deg);
     cs o;
 #if defined(__CUDA_ARCH__)
@@ -222,8 +222,26 @@ FCZ_HD cs cossin_deg(float deg) {
 #endif
     return o;
 }
-// (cos, sin) of the angle at b between a and c, straight from the coordinates -- what the
-// reference gets by acos -> degrees -> radians -> sincosf (src/float3d.h:55-65, src/nerf.cpp:63-70)
+// Decode only (the encoder never takes a sine or cosine of an angle).  Quadrant reduction in DEGREES, where it is
+// exact: q = rint(deg/90), r = deg - 90q in [-45, 45] without rounding; then the classic single-precision
+// minimax polynomials on |x| <= pi/4 (absolute error < 1.2e-7, the same as sincosf gives on a rounded radian
+// argument; checked against double in tests/test_fastpath.py).
+FCZ_HD cs cossin_deg(float deg) {
+    if (!(fabsf(deg) <= 720.0f)) return cossin_deg_slow(deg);  // never for a blob written by an encoder
+    const float q = rintf(deg * (1.0f / 90.0f));
+    const float r = fma_(q, -90.0f, deg);
+    const float x = r * 0.017453292519943295f;
+    const float z = x * x;
+    const float sp = fma_(fma_(fma_(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), z * x, x);
+    const float cp = fma_(fma_(fma_(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z * z, fma_(-0.5f, z, 1.0f));
+    const int k = (int)q & 3;
+    cs o;
+    o.s = (k & 1) ? cp : sp;
+    o.c = (k & 1) ? sp : cp;
+    if (k & 2) o.s = -o.s;
+    if ((k + 1) & 2) o.c = -o.c;
+    return o;
+}
 FCZ_HD cs cossin_angle(f3 a, f3 b, f3 c) {
     f3 u = sub3(a, b), v = sub3(c, b);
     cs o;
@@ -264,6 +282,21 @@ FCZ_HD f3 nerf_step(NerfFrame& f, f3 c, float len, cs ang, cs tor) {
     f.nbc = mk3(fma_(w, b2.x, fma_(v, b1.x, u * b0.x)), fma_(w, b2.y, fma_(v, b1.y, u * b0.y)), fma_(w, b2.z, fma_(v, b1.z, u * b0.z)));
     f.n = mk3(fma_(tor.c, b2.x, -(tor.s * b1.x)), fma_(tor.c, b2.y, -(tor.s * b1.y)), fma_(tor.c, b2.z, -(tor.s * b1.z)));
     return axpy(len, f.bcn, c);
+}
+// The same step for ONE Cartesian component: the update combines the frame vectors with scalar coefficients,
+// so x, y and z evolve independently and three lanes can share a chain (bit-identical to nerf_step).
+struct NerfFrame1 {
+    float bcn, nbc, n;
+};
+FCZ_HD float comp3(f3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+FCZ_HD float nerf_step1(NerfFrame1& f, float c, float len, cs ang, cs tor) {
+    const float x = -ang.c, y = tor.c * ang.s, z = tor.s * ang.s;
+    const float u = -ang.s, v = -(tor.c * ang.c), w = -(tor.s * ang.c);
+    const float b0 = f.bcn, b1 = f.nbc, b2 = f.n;
+    f.bcn = fma_(z, b2, fma_(y, b1, x * b0));
+    f.nbc = fma_(w, b2, fma_(v, b1, u * b0));
+    f.n = fma_(tor.c, b2, -(tor.s * b1));
+    return fma_(len, f.bcn, c);
 }
 // One-off placement from three arbitrary predecessor atoms (side chains, src/nerf.cpp:106-155)
 FCZ_HD f3 place_from(f3 a, f3 b, f3 c, float len, cs ang, cs tor) {

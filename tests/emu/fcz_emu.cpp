@@ -20,6 +20,7 @@ struct HostCtx {
     uint32_t excl_scan(uint32_t) { return 0; }
     float wmin(float v) { return v; }
     float wmax(float v) { return v; }
+    uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 };
 
 static const Tables* tables() {
@@ -72,6 +73,8 @@ int emu_decode_chain(const uint8_t* blob, uint64_t len, int use_alt, uint8_t* re
     ch.blob = blob; ch.y = y; ch.use_alt = use_alt;
     ch.out_xyz = xyz; ch.out_type = res_type; ch.out_bfac = bfac; ch.out_meta = meta; ch.out_title = title;
     ch.aoff = aoff.data(); ch.tor = tor.data(); ch.ang = ang.data(); ch.seg = seg.data(); ch.rev = rev.data(); ch.segid = segid.data(); ch.loc = nullptr;
+    std::vector<uint16_t> order(L); std::vector<uint32_t> bins(32);
+    ch.order = order.data(); ch.bins = bins.data(); ch.codes = nullptr;
     HostCtx cx;
     decode_chain(cx, tb, ch);
     return FCZ_OK;
@@ -136,4 +139,19 @@ extern "C" long emu_acos_check(uint32_t stride, uint64_t* n_wrong, uint64_t* n_u
     *n_wrong = wrong;
     *n_uncertified = unc;
     return worst > 0 ? (long)(1000.0 * log2(worst)) : -99999;
+}
+
+// cossin_deg (decode) against double sin/cos: n points evenly over [lo, hi] degrees; returns the maximum
+// absolute error of either component in units of 1e-9.
+extern "C" long emu_cossin_check(double lo, double hi, uint64_t n) {
+    double worst = 0;
+#pragma omp parallel for reduction(max : worst) schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const float deg = (float)(lo + (hi - lo) * (double)i / (double)(n - 1));
+        const fcz::cs v = fcz::cossin_deg(deg);
+        const double r = (double)deg * (M_PI / 180.0);
+        const double e = fmax(fabs((double)v.c - cos(r)), fabs((double)v.s - sin(r)));
+        if (e > worst) worst = e;
+    }
+    return (long)(worst * 1e9);
 }

@@ -100,3 +100,14 @@ def test_fast_acos_sampled():
     assert e <= -46000, e
     assert wrong.value == 0
     assert unc.value < 2000
+
+
+def test_decode_cossin_deg():
+    """The decoder's degree-domain sincos: absolute error vs double below 1.2e-7 over [-720, 720] degrees
+    (20 M points) and sane on the slow path beyond."""
+    lib = _lib()
+    lib.emu_cossin_check.restype = C.c_long
+    lib.emu_cossin_check.argtypes = [C.c_double, C.c_double, C.c_uint64]
+    assert lib.emu_cossin_check(-720.0, 720.0, 20_000_001) <= 120
+    assert lib.emu_cossin_check(-181.0, 181.0, 20_000_001) <= 120
+    assert lib.emu_cossin_check(721.0, 5000.0, 1_000_001) <= 8000  # float radians: half an ulp of 87 rad is 3.8e-6
