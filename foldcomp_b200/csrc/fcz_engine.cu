@@ -76,7 +76,7 @@ static TierCfg make_tier(uint32_t max_res, bool staged) {
     t.max_blob = 17u * max_res + 1280u;
     t.max_seg = max_res / 10u + 8u;
     if (t.max_seg > 254u) t.max_seg = 254u;
-    t.threads = (max_res <= 128u) ? 128u : 256u;
+    t.threads = (max_res <= 128u) ? 128u : 320u;
     if (!staged) {
         t.max_atoms = 10u * max_res;
         t.max_blob = 0xFFFFFFFFu;
@@ -134,6 +134,7 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 #ifdef FCZ_PHASE_TIMING
@@ -329,7 +330,7 @@ __global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* 
     }
 }
 
-__global__ void __launch_bounds__(256, 3) k_encode(EncArgs a) {
+__global__ void __launch_bounds__(320, 3) k_encode(EncArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncSmem so = enc_smem(a.cfg);
     Tables* tb = reinterpret_cast<Tables*>(smem + so.o_tab);
@@ -775,7 +776,13 @@ __global__ void __launch_bounds__(192) k_dec_back(Dec2Args a) {
     __builtin_assume(__isShared(ch.seg));
     __builtin_assume(__isShared(ch.order));
     __builtin_assume(__isShared(ch.bins));
-    // inputs of the first phases: asynchronous copies straight into shared memory, all in flight together
+    // inputs of the first phases: asynchronous copies straight into shared memory, all in flight together;
+    // the blend's inputs (written by the front kernel a whole batch ago, i.e. in HBM) are pulled towards L2 meanwhile
+    {
+        const char* pl = reinterpret_cast<const char*>(ch.loc);
+        const char* pv = reinterpret_cast<const char*>(ch.rev);
+        for (uint32_t off = cx.tid * 128u; off < 36u * L; off += cx.nthr * 128u) { prefetch_l2(pl + off); prefetch_l2(pv + off); }
+    }
     {
         const uint32_t* g_aoff = a.aoff + rr + (c - a.c0);
         for (uint32_t r = cx.tid; r <= L; r += cx.nthr) cp_async4(ch.aoff + r, g_aoff + r);
