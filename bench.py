@@ -37,15 +37,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_CHAINS, LENGTH, ANCHOR = 10000, 350, 25
+WORKLOAD_NOTE = ""
 METRIC = "residues/sec compress+decompress round-trip"
 UNIT = "residues/s"
 
 
+def _len_desc():
+    return int(LENGTH) if np.isscalar(LENGTH) else round(float(np.mean(LENGTH)), 1)
+
+
 def workload_config(n_gpus):
     return {
-        "workload": f"BASELINE.json configs[1]: {N_CHAINS} synthetic single chains x {LENGTH} residues per GPU, -b {ANCHOR}, "
-                    "compress -> decompress round trip",
-        "chains_per_gpu": N_CHAINS, "residues_per_chain": LENGTH, "anchor_threshold": ANCHOR,
+        "workload": f"BASELINE.json configs[1]: {N_CHAINS} synthetic single chains x {_len_desc()} residues per GPU, -b {ANCHOR}, "
+                    "compress -> decompress round trip" + WORKLOAD_NOTE,
+        "chains_per_gpu": N_CHAINS, "residues_per_chain": _len_desc(), "anchor_threshold": ANCHOR,
         "parallelism": f"chains sharded over {n_gpus} GPU(s), no collective on the data path",
         "l2": "per step the kernels stream ~346 MB of coordinates in, 56 MB of FCZ and ~343 MB of coordinates out "
               "(> 126 MB L2), so inputs come from HBM every step; no explicit flush",
@@ -93,7 +98,7 @@ def cpu_sample_size(batch, threads, target_s):
     cpu_roundtrip(batch, 128, threads)  # first call pays library load and thread start-up
     dt, kind, nres = cpu_roundtrip(batch, min(batch.n_chains, 512), threads)
     rate = nres / dt
-    n = int(max(128, min(batch.n_chains, rate * target_s / LENGTH)))
+    n = int(max(128, min(batch.n_chains, rate * target_s / float(np.mean(LENGTH)))))
     return n
 
 
@@ -103,7 +108,7 @@ def run_reference(args, rank, world, out):
     from foldcomp_b200 import synth
 
     threads = os.cpu_count() or 1
-    batch = synth.generate(N_CHAINS, LENGTH, seed=synth.SEED)
+    batch = synth.generate(N_CHAINS, LENGTH, seed=synth.SEED)  # LENGTH: int or per-chain array
     n = cpu_sample_size(batch, threads, 3.0)
     for _ in range(args.warmup):
         cpu_roundtrip(batch, n, threads)
@@ -259,7 +264,7 @@ def run_ours(args, rank, world, local_rank, out):
     fcz_bytes = int(dblob.blob_off[-1].item())
 
     # ---- roofline of the dominant kernel
-    enc_ms = prof.encode_kernel_ms / max(prof.encode_launches, 1)
+    enc_ms = prof.encode_kernel_ms / max(prof.encode_launches, 1)  # one span per call: all tier launches, fork to join
     dec_ms = prof.decode_kernel_ms / max(prof.decode_launches, 1)
     enc_bytes = 12 * n_atoms + 5 * n_res + fcz_bytes
     dec_bytes = fcz_bytes + 12 * n_atoms + 4 * n_res
@@ -368,7 +373,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lengths", default="fixed", choices=["fixed", "mixed"],
+                    help="fixed = the headline workload (BASELINE.json configs[1]); mixed = the same number of chains with the "
+                         "clipped log-normal lengths of configs[4] (AFDB proxy, 50..2000 residues) -- a secondary measurement")
     args = ap.parse_args()
+    global LENGTH, WORKLOAD_NOTE
+    from foldcomp_b200 import synth
+    if args.lengths == "mixed":
+        LENGTH = synth.mixed_lengths(np.random.default_rng(synth.SEED), N_CHAINS)
+        WORKLOAD_NOTE = " [--lengths mixed: log-normal lengths 50..2000, median 280 -- NOT the headline workload]"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -90,6 +90,7 @@ static void make_tiers(TierCfg* enc) {
     for (int i = 0; i < FCZ_NTIER; i++) {
         enc[i] = make_tier(kEncTierRes[i], i < FCZ_NTIER - 1);
         enc[i].smem = enc_smem(enc[i]).total;
+        enc[i].threads = 128u;  // settled at engine creation from the occupancy the footprint allows
     }
 }
 
@@ -330,7 +331,7 @@ __global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* 
     }
 }
 
-__global__ void __launch_bounds__(320, 3) k_encode(EncArgs a) {
+__global__ void __launch_bounds__(1024) k_encode(EncArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncSmem so = enc_smem(a.cfg);
     Tables* tb = reinterpret_cast<Tables*>(smem + so.o_tab);
@@ -498,6 +499,8 @@ struct Dec2Args {
     const Tables* tables;
     int32_t use_alt;
     uint32_t c0, c1;          // chains of this sub-batch
+    const uint32_t* list;     // chains of this launch: a length tier of the sub-batch (block i = list[i])
+    uint32_t count;
     uint32_t r_base, s_base;  // res_off[c0], seg_off[c0]
     uint32_t* aoff;           // workspace, indexed from the sub-batch's first residue / segment slot
     uint8_t* segid;
@@ -551,33 +554,25 @@ __device__ __forceinline__ DevCtx block_ctx(uint32_t* wsum) {
 __global__ void __launch_bounds__(256) k_dec_unpack(Dec2Args a) {  // block per chain
     __shared__ uint32_t wsum[32];
     DecChain ch;
-    if (!dec2_chain(a, a.c0 + blockIdx.x, ch)) return;
+    if (!dec2_chain(a, a.list[blockIdx.x], ch)) return;
     DevCtx cx = block_ctx(wsum);
     dec_unpack(cx, a.tables, ch);
 }
 __global__ void __launch_bounds__(128) k_dec_passes(Dec2Args a) {  // block per chain: forward items in two warps, reverse items in two
     DecChain ch;
-    if (!dec2_chain(a, a.c0 + blockIdx.x, ch)) return;
+    if (!dec2_chain(a, a.list[blockIdx.x], ch)) return;
     DevCtx cx = block_ctx(nullptr);
     dec_passes(cx, a.tables, ch);
 }
-__global__ void __launch_bounds__(128) k_dec_stitch(Dec2Args a) {  // thread per chain
-    const uint32_t c = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.c1) return;
-    DecChain ch;
-    if (!dec2_chain(a, c, ch)) return;
-    ThreadCtx cx;
-    dec_stitch(cx, a.tables, ch);
-}
 __global__ void __launch_bounds__(128) k_dec_blend(Dec2Args a) {  // block per chain, thread per backbone atom
     DecChain ch;
-    if (!dec2_chain(a, a.c0 + blockIdx.x, ch)) return;
+    if (!dec2_chain(a, a.list[blockIdx.x], ch)) return;
     DevCtx cx = block_ctx(nullptr);
     dec_blend(cx, a.tables, ch);
 }
 __global__ void __launch_bounds__(192) k_dec_side(Dec2Args a) {  // block per chain, thread per residue pair
     DecChain ch;
-    if (!dec2_chain(a, a.c0 + blockIdx.x, ch)) return;
+    if (!dec2_chain(a, a.list[blockIdx.x], ch)) return;
     DevCtx cx = block_ctx(nullptr);
     dec_side(cx, a.tables, ch);
 }
@@ -617,9 +612,9 @@ __host__ __device__ inline BackSmem back_smem(uint32_t max_L, uint32_t max_ancho
     return o;
 }
 
-__global__ void __launch_bounds__(128) k_dec_front(Dec2Args a) {
+__global__ void __launch_bounds__(1024) k_dec_front(Dec2Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t c = a.c0 + blockIdx.x;
+    const uint32_t c = a.list[blockIdx.x];
     // everything about the chain from the offset arrays (independent loads, one round trip): the plan has
     // already checked them against the blob header
     const int32_t st = a.status[c];
@@ -689,11 +684,11 @@ __global__ void __launch_bounds__(128) k_dec_front(Dec2Args a) {
 __global__ void __launch_bounds__(1024) k_dec_stitch_t(Dec2Args a) {
     extern __shared__ __align__(16) float sm[];
     const uint32_t G = a.stitch_group, cstride = (a.max_anchor * SegPacked::N) | 1u;
-    const uint32_t cb = a.c0 + blockIdx.x * G;
+    const uint32_t ib = blockIdx.x * G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (uint32_t j = warp; j < G; j += nwarps) {
-        const uint32_t c = cb + j;
-        if (c >= a.c1 || a.status[c] != FCZ_OK) continue;
+        if (ib + j >= a.count) continue;
+        const uint32_t c = a.list[ib + j];
         const uint32_t s0 = a.seg_off[c], nA = a.seg_off[c + 1] - s0;
         const float* src = a.seg + (size_t)(s0 - a.s_base) * FCZ_SEG_FLOATS;
         float* dst = sm + (size_t)j * cstride;
@@ -716,15 +711,14 @@ __global__ void __launch_bounds__(1024) k_dec_stitch_t(Dec2Args a) {
         }
     }
     __syncthreads();
-    if (threadIdx.x < G) {
-        const uint32_t c = cb + threadIdx.x;
-        if (c < a.c1 && a.status[c] == FCZ_OK)
-            dec_stitch_core<SegPacked>(sm + (size_t)threadIdx.x * cstride, 1, (int)(a.seg_off[c + 1] - a.seg_off[c]) - 1);
+    if (threadIdx.x < G && ib + threadIdx.x < a.count) {
+        const uint32_t c = a.list[ib + threadIdx.x];
+        dec_stitch_core<SegPacked>(sm + (size_t)threadIdx.x * cstride, 1, (int)(a.seg_off[c + 1] - a.seg_off[c]) - 1);
     }
     __syncthreads();
     for (uint32_t j = warp; j < G; j += nwarps) {
-        const uint32_t c = cb + j;
-        if (c >= a.c1 || a.status[c] != FCZ_OK) continue;
+        if (ib + j >= a.count) continue;
+        const uint32_t c = a.list[ib + j];
         const uint32_t s0 = a.seg_off[c], nA = a.seg_off[c + 1] - s0;
         float* out = a.seg + (size_t)(s0 - a.s_base) * FCZ_SEG_FLOATS;
         const float* srcp = sm + (size_t)j * cstride;
@@ -735,10 +729,10 @@ __global__ void __launch_bounds__(1024) k_dec_stitch_t(Dec2Args a) {
     }
 }
 
-__global__ void __launch_bounds__(192) k_dec_back(Dec2Args a) {
+__global__ void __launch_bounds__(1024) k_dec_back(Dec2Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t wsum[32];
-    const uint32_t c = a.c0 + blockIdx.x;
+    const uint32_t c = a.list[blockIdx.x];
     const int32_t st = a.status[c];
     const uint64_t b0 = a.blob_off[c];
     const uint32_t r0 = a.res_off[c], L = a.res_off[c + 1] - r0;
@@ -812,13 +806,19 @@ __global__ void __launch_bounds__(192) k_dec_back(Dec2Args a) {
     cx.mark(14);
 }
 
-// Sub-batch bounds for device-planned batches: ~sub_res residues each, equal chain counts; written to pinned
-// host memory: [0] count, then per bound k (chain, residue, segment-slot prefix), then per sub-batch the
-// maxima (residues, anchors, blob bytes, atoms) over its chains that size the shared-memory kernels.
-// One thread per chain; maxima through device atomics in dmax (all zero on entry and on exit), published by
-// the last block to finish.
+// Decode launch plan for device-planned batches.  Sub-batches of ~sub_res residues (equal chain counts) bound the
+// workspace; inside a sub-batch chains are binned by length into FCZ_DEC_TIERS tiers, each launched on its own
+// with shared memory sized by the tier's actual maxima, so a few long chains do not cost the short ones their
+// occupancy.  Written to pinned host memory: [0] count, then per bound k (chain, residue, segment-slot prefix),
+// then per (sub-batch, tier) five words: chains, max residues, max anchors, max blob bytes, max atoms.
+// list[t * n + c0_k + i] = i-th chain of tier t in sub-batch k.  One thread per chain; counts and maxima through
+// device atomics in dmax (all zero on entry and on exit), published by the last block to finish.
+#define FCZ_DEC_TIERS 4
+__host__ __device__ inline uint32_t dec_tier_of(uint32_t L) { return L <= 384u ? 0u : (L <= 768u ? 1u : (L <= 1536u ? 2u : 3u)); }
+
 __global__ void __launch_bounds__(256) k_plan_chunks(uint32_t n, uint32_t sub_res, const uint32_t* res_off, const uint32_t* seg_off,
-                                                     const uint64_t* atom_off, const uint64_t* blob_off, uint32_t* dmax, uint32_t* out) {
+                                                     const uint64_t* atom_off, const uint64_t* blob_off, const int32_t* status,
+                                                     uint32_t* list, uint32_t* dmax, uint32_t* out) {
     __shared__ uint32_t s_last;
     const uint64_t R = res_off[n];
     uint64_t per64 = n ? ((uint64_t)sub_res * n + (R ? R - 1 : 0)) / (R ? R : 1) : 1;
@@ -837,32 +837,50 @@ __global__ void __launch_bounds__(256) k_plan_chunks(uint32_t n, uint32_t sub_re
         }
     }
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n) {
-        const uint32_t k = c / per;
-        uint32_t m[4] = {res_off[c + 1] - res_off[c], seg_off[c + 1] - seg_off[c], (uint32_t)(blob_off[c + 1] - blob_off[c]),
-                         (uint32_t)(atom_off[c + 1] - atom_off[c])};
-        const unsigned mask = __activemask();
-        const uint32_t k0 = __shfl_sync(mask, k, __ffs(mask) - 1);
-        if (__all_sync(mask, k == k0)) {
-            for (int j = 0; j < 4; j++) {
-                const uint32_t v = __reduce_max_sync(mask, m[j]);
-                if ((int)(threadIdx.x & 31) == __ffs(mask) - 1) atomicMax(&dmax[4 * k + j], v);
-            }
-        } else {
-            for (int j = 0; j < 4; j++) atomicMax(&dmax[4 * k + j], m[j]);
+    const bool valid = c < n && status[c] == FCZ_OK;
+    uint32_t k = 0, t = 0, m[4] = {0, 0, 0, 0};
+    if (valid) {
+        k = c / per;
+        m[0] = res_off[c + 1] - res_off[c];
+        m[1] = seg_off[c + 1] - seg_off[c];
+        m[2] = (uint32_t)(blob_off[c + 1] - blob_off[c]);
+        m[3] = (uint32_t)(atom_off[c + 1] - atom_off[c]);
+        t = dec_tier_of(m[0]);
+    }
+    // a block whose chains all sit in one sub-batch (the usual case) aggregates in shared memory first
+    const uint32_t cf = blockIdx.x * blockDim.x, cl = (cf + blockDim.x < n ? cf + blockDim.x : n) - 1u;
+    if (cf < n && cf / per == cl / per) {
+        __shared__ uint32_t s_agg[FCZ_DEC_TIERS][6];  // count, four maxima, base
+        if (threadIdx.x < FCZ_DEC_TIERS * 6) (&s_agg[0][0])[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t pos = 0;
+        if (valid) {
+            pos = atomicAdd(&s_agg[t][0], 1u);
+            for (int j = 0; j < 4; j++) atomicMax(&s_agg[t][1 + j], m[j]);
         }
+        __syncthreads();
+        if (threadIdx.x < FCZ_DEC_TIERS && s_agg[threadIdx.x][0]) {
+            uint32_t* d = dmax + 5u * (FCZ_DEC_TIERS * (cf / per) + threadIdx.x);
+            s_agg[threadIdx.x][5] = atomicAdd(&d[0], s_agg[threadIdx.x][0]);
+            for (int j = 0; j < 4; j++) atomicMax(&d[1 + j], s_agg[threadIdx.x][1 + j]);
+        }
+        __syncthreads();
+        if (valid) list[(size_t)t * n + (size_t)k * per + s_agg[t][5] + pos] = c;
+    } else if (valid) {
+        uint32_t* d = dmax + 5u * (FCZ_DEC_TIERS * k + t);
+        const uint32_t pos = atomicAdd(&d[0], 1u);
+        list[(size_t)t * n + (size_t)k * per + pos] = c;
+        for (int j = 0; j < 4; j++) atomicMax(&d[1 + j], m[j]);
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&dmax[4 * FCZ_MAX_CHUNKS], 1u) == gridDim.x - 1u);
+    if (threadIdx.x == 0) s_last = (atomicAdd(&dmax[5 * FCZ_DEC_TIERS * FCZ_MAX_CHUNKS], 1u) == gridDim.x - 1u);
     __syncthreads();
     if (s_last) {
         __threadfence();
         uint32_t* mx = out + 1 + 3 * (nch + 1);
-        for (uint32_t i = threadIdx.x; i < 4u * nch; i += blockDim.x) {
-            mx[i] = atomicExch(&dmax[i], 0u);
-        }
-        if (threadIdx.x == 0) dmax[4 * FCZ_MAX_CHUNKS] = 0u;
+        for (uint32_t i = threadIdx.x; i < 5u * FCZ_DEC_TIERS * nch; i += blockDim.x) mx[i] = atomicExch(&dmax[i], 0u);
+        if (threadIdx.x == 0) dmax[5 * FCZ_DEC_TIERS * FCZ_MAX_CHUNKS] = 0u;
     }
 }
 
@@ -962,6 +980,8 @@ struct fcz_engine {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined host-memory path
+    cudaStream_t s_tier[8] = {};  // length tiers (encode: FCZ_NTIER, decode: FCZ_DEC_TIERS) run side by side
+    cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
     std::vector<cudaEvent_t> ev_pool;              // events of that path, reused across calls
     fcz_opts opts;
     int num_sms = 148;
@@ -979,7 +999,7 @@ struct fcz_engine {
     // staging for host-memory batches
     DevBuf d_res_off, d_atom_off, d_title_off, d_res_type, d_bfactor, d_xyz, d_titles, d_meta, d_blob_off, d_bytes, d_status;
     DevBuf d_list, d_tickets;
-    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax;  // batch-wide decoder: segment offsets + L2-resident workspace
+    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax, d_dec_list;  // batch-wide decoder: segment offsets + L2-resident workspace
     // plan made on the host by fcz_decode_plan(host) for the following fcz_decode_batch(host)
     struct Launch { uint32_t chunk, tier, first, count; };
     struct HostPlan {
@@ -1067,6 +1087,11 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     bool ok = true;
     ok &= cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) == cudaSuccess;
     ok &= cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8; i++) {
+        ok &= cudaStreamCreateWithFlags(&e->s_tier[i], cudaStreamNonBlocking) == cudaSuccess;
+        ok &= cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok &= cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < FCZ_NTIER; i++) {
         if (e->enc_tier[i].smem > 227u * 1024u) {
             fprintf(stderr, "fcz_engine_create: tier %d needs %u bytes of shared memory (> 227 KB)\n", i, e->enc_tier[i].smem);
@@ -1079,7 +1104,12 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
         ok &= cudaFuncSetAttribute(k_dec_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         ok &= cudaFuncSetAttribute(k_dec_stitch_t, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         if (const char* v = getenv("FCZ_DEC_SUB_RESIDUES")) { long q = atol(v); if (q > 0) e->dec_sub_res = (uint32_t)q; }
+        // 64 registers per thread = 1024 threads per SM, shared between the CTAs the shared-memory footprint lets in
         int occ = 0;
+        ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, 128, e->enc_tier[i].smem) == cudaSuccess;
+        if (occ < 1) occ = 1;
+        uint32_t thr = (1024u / (uint32_t)occ) & ~31u;
+        e->enc_tier[i].threads = thr < 128u ? 128u : thr;
         ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, (int)e->enc_tier[i].threads, e->enc_tier[i].smem) == cudaSuccess;
         e->enc_occ[i] = occ > 0 ? occ : 1;
     }
@@ -1090,10 +1120,10 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     ok &= cudaMalloc(&e->d_totals, sizeof(uint64_t) * 4) == cudaSuccess;
     ok &= cudaMallocHost(&e->h_counters, sizeof(uint32_t) * 2 * FCZ_NTIER) == cudaSuccess;
     ok &= cudaMallocHost(&e->h_totals, sizeof(uint64_t) * 4) == cudaSuccess;
-    ok &= cudaMallocHost(&e->h_bounds, sizeof(uint32_t) * (7 * (FCZ_MAX_CHUNKS + 1) + 1)) == cudaSuccess;
+    ok &= cudaMallocHost(&e->h_bounds, sizeof(uint32_t) * ((3 + 5 * FCZ_DEC_TIERS) * (FCZ_MAX_CHUNKS + 1) + 1)) == cudaSuccess;
     if (ok) ok &= cudaMemcpy(e->d_tables, &h, sizeof(Tables), cudaMemcpyHostToDevice) == cudaSuccess;
-    ok &= cudaMalloc(&e->d_submax.p, sizeof(uint32_t) * (4 * FCZ_MAX_CHUNKS + 1)) == cudaSuccess;  // k_plan_chunks keeps it zero
-    if (ok) { e->d_submax.cap = sizeof(uint32_t) * (4 * FCZ_MAX_CHUNKS + 1); ok &= cudaMemset(e->d_submax.p, 0, e->d_submax.cap) == cudaSuccess; }
+    ok &= cudaMalloc(&e->d_submax.p, sizeof(uint32_t) * (5 * FCZ_DEC_TIERS * FCZ_MAX_CHUNKS + 1)) == cudaSuccess;  // k_plan_chunks keeps it zero
+    if (ok) { e->d_submax.cap = sizeof(uint32_t) * (5 * FCZ_DEC_TIERS * FCZ_MAX_CHUNKS + 1); ok &= cudaMemset(e->d_submax.p, 0, e->d_submax.cap) == cudaSuccess; }
     if (!ok) {
         fprintf(stderr, "fcz_engine_create: %s\n", cudaGetErrorString(cudaGetLastError()));
         delete e;
@@ -1109,7 +1139,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->v3, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
                       &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets,
-                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax};
+                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (e->d_tables) cudaFree(e->d_tables);
@@ -1121,6 +1151,11 @@ void fcz_engine_destroy(fcz_engine* e) {
     for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto ev : e->free_events) cudaEventDestroy(ev);
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+    for (int i = 0; i < 8; i++) {
+        if (e->s_tier[i]) cudaStreamDestroy(e->s_tier[i]);
+        if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
     if (e->own_stream) cudaStreamDestroy(e->stream);
@@ -1290,9 +1325,17 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
     *total_bytes = e->h_totals[0];
     if (*total_bytes > out->bytes_cap) return fail(e, FCZ_E_CAPACITY, "encode needs %llu bytes, capacity %llu",
                                                    (unsigned long long)*total_bytes, (unsigned long long)out->bytes_cap);
+    int ntier = 0;
+    for (int i = 0; i < FCZ_NTIER; i++) ntier += e->h_counters[i] ? 1 : 0;
+    // tiers run side by side on their own streams (the long-chain tiers have few, long-running blocks)
+    const bool fork = ntier > 1;
+    ProfSpan ps(e, 0);
+    if (fork) CK(cudaEventRecord(e->ev_fork, e->stream));
     for (int i = 0; i < FCZ_NTIER; i++) {
         const uint32_t cnt = e->h_counters[i];
         if (!cnt) continue;
+        cudaStream_t st = fork ? e->s_tier[i] : e->stream;
+        if (fork) CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
         EncArgs a;
         a.res_off = in->res_off; a.atom_off = in->atom_off; a.title_off = in->title_off;
         a.res_type = in->res_type; a.bfactor = in->bfactor; a.xyz = in->xyz; a.titles = in->titles; a.meta = in->meta;
@@ -1306,11 +1349,12 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
         a.cfg = e->enc_tier[i];
         uint32_t grid = (uint32_t)(e->num_sms * e->enc_occ[i]);
         if (grid > cnt) grid = cnt;
-        {
-            ProfSpan ps(e, 0);
-            k_encode<<<grid, a.cfg.threads, a.cfg.smem, e->stream>>>(a);
-        }
+        k_encode<<<grid, a.cfg.threads, a.cfg.smem, st>>>(a);
         e->launches++;
+        if (fork) {
+            CK(cudaEventRecord(e->ev_join[i], st));
+            CK(cudaStreamWaitEvent(e->stream, e->ev_join[i], 0));
+        }
     }
     CK(cudaGetLastError());
     return FCZ_OK;
@@ -1522,40 +1566,43 @@ extern "C" int fcz_encode_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_bl
 
 // ------------------------------------------------------------------------------------------- decode
 
+struct Dec2Tier {
+    uint32_t count, max_L, max_anchor, max_blob, max_atoms;  // chains and maxima over them
+    size_t list_off;                                         // first entry in the device chain list
+    bool smem;                                               // runs the shared-memory kernels
+};
 struct Dec2Sub {
-    uint32_t c0, c1, r0, r1, s0, s1;                  // chains, residues, segment slots of one sub-batch
-    uint32_t max_L, max_anchor, max_blob, max_atoms;  // maxima over its chains
-    bool smem;                                        // runs the shared-memory kernels
+    uint32_t c0, c1, r0, r1, s0, s1;  // chains, residues, segment slots of one sub-batch
+    Dec2Tier tier[FCZ_DEC_TIERS];
 };
 
 #define FCZ_SMEM_LIMIT (227u * 1024u)
 
 static uint32_t stitch_chain_bytes(uint32_t max_anchor) { return 4u * ((max_anchor * (uint32_t)SegPacked::N) | 1u); }
 
-static void dec2_classify(Dec2Sub& sb) {
-    const FrontSmem fs = front_smem(sb.max_L, sb.max_anchor, sb.max_blob);
-    const BackSmem bs = back_smem(sb.max_L, sb.max_anchor, sb.max_atoms);
-    sb.smem = fs.total <= FCZ_SMEM_LIMIT && bs.total <= FCZ_SMEM_LIMIT && stitch_chain_bytes(sb.max_anchor) <= FCZ_SMEM_LIMIT &&
-              getenv("FCZ_DEC_GLOBAL") == nullptr;
-}
-
 static int dec2_workspace(fcz_engine* e, Dec2Sub* subs, size_t nsub) {
-    uint64_t mr = 0, ms = 0, mc = 0, mrs = 0;
-    bool any_global = false;
+    uint64_t mr = 0, ms = 0, mc = 0;
+    bool any_global = false, any_smem = false;
+    const bool force_global = getenv("FCZ_DEC_GLOBAL") != nullptr;
     for (size_t k = 0; k < nsub; k++) {
-        dec2_classify(subs[k]);
         const uint64_t nr = subs[k].r1 - subs[k].r0, nc = subs[k].c1 - subs[k].c0;
         if (nc > mc) mc = nc;
         if (nr > mr) mr = nr;
         if ((uint64_t)(subs[k].s1 - subs[k].s0) > ms) ms = subs[k].s1 - subs[k].s0;
-        if (subs[k].smem) { if (nr > mrs) mrs = nr; }
-        else any_global = true;
+        for (int t = 0; t < FCZ_DEC_TIERS; t++) {
+            Dec2Tier& tr = subs[k].tier[t];
+            if (!tr.count) continue;
+            const FrontSmem fs = front_smem(tr.max_L, tr.max_anchor, tr.max_blob);
+            const BackSmem bs = back_smem(tr.max_L, tr.max_anchor, tr.max_atoms);
+            tr.smem = fs.total <= FCZ_SMEM_LIMIT && bs.total <= FCZ_SMEM_LIMIT && !force_global;
+            (tr.smem ? any_smem : any_global) = true;
+        }
     }
     int rc;
     if ((rc = ensure(e, e->sc_aoff, 4ull * (mr + mc + 1)))) return rc;
     if ((rc = ensure(e, e->sc_rev, 36ull * mr + 16))) return rc;
     if ((rc = ensure(e, e->sc_seg, 4ull * FCZ_SEG_FLOATS * (ms + 1)))) return rc;
-    if (mrs && (rc = ensure(e, e->sc_loc, 36ull * mrs + 16))) return rc;
+    if (any_smem && (rc = ensure(e, e->sc_loc, 36ull * mr + 16))) return rc;
     if (any_global) {
         if ((rc = ensure(e, e->sc_segid, mr + 16))) return rc;
         if ((rc = ensure(e, e->sc_tor, 24ull * mr + 16))) return rc;
@@ -1564,38 +1611,63 @@ static int dec2_workspace(fcz_engine* e, Dec2Sub* subs, size_t nsub) {
     return FCZ_OK;
 }
 
-// the phase kernels over one sub-batch (a carries the batch pointers)
-static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb) {
+// the phase kernels over one sub-batch (a carries the batch pointers, list = device chain list)
+static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb, const uint32_t* list) {
     const uint32_t nch = sb.c1 - sb.c0;
     if (!nch) return FCZ_OK;
     a.c0 = sb.c0; a.c1 = sb.c1; a.r_base = sb.r0; a.s_base = sb.s0;
     a.aoff = (uint32_t*)e->sc_aoff.p; a.rev = (float*)e->sc_rev.p; a.seg = (float*)e->sc_seg.p;
-    if (sb.smem) {
-        a.loc = (float*)e->sc_loc.p;
-        a.max_L = sb.max_L; a.max_anchor = sb.max_anchor; a.max_blob = sb.max_blob; a.max_atoms = sb.max_atoms;
-        const FrontSmem fs = front_smem(sb.max_L, sb.max_anchor, sb.max_blob);
-        const BackSmem bs = back_smem(sb.max_L, sb.max_anchor, sb.max_atoms);
+    a.loc = (float*)e->sc_loc.p;
+    a.segid = (uint8_t*)e->sc_segid.p; a.tor = (cs*)e->sc_tor.p; a.ang = (cs*)e->sc_ang.p;
+    int ntier = 0;
+    for (int t = 0; t < FCZ_DEC_TIERS; t++)
+        if (sb.tier[t].count) ntier++;
+    if (!ntier) return FCZ_OK;  // no valid chain
+    // Each tier is its own three-kernel pipeline; tiers run side by side on their own streams (a tier of long
+    // chains has few, long-running blocks): fork from the engine's stream, join at the end.
+    const bool fork = ntier > 1;
+    if (fork) CK(cudaEventRecord(e->ev_fork, e->stream));
+    for (int t = 0; t < FCZ_DEC_TIERS; t++) {
+        const Dec2Tier& tr = sb.tier[t];
+        if (!tr.count) continue;
+        cudaStream_t st = fork ? e->s_tier[t] : e->stream;
+        if (fork) CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
+        a.list = list + tr.list_off; a.count = tr.count;
+        a.max_L = tr.max_L; a.max_anchor = tr.max_anchor; a.max_blob = tr.max_blob; a.max_atoms = tr.max_atoms;
         // stitch: one wave when it fits -- chains per block = ceil(chains / SMs), bounded by shared memory
-        const uint32_t cbytes = stitch_chain_bytes(sb.max_anchor);
-        uint32_t G = (nch + (uint32_t)e->num_sms - 1u) / (uint32_t)e->num_sms;
+        const uint32_t cbytes = stitch_chain_bytes(tr.max_anchor);
+        uint32_t G = (tr.count + (uint32_t)e->num_sms - 1u) / (uint32_t)e->num_sms;
         const uint32_t gmax = (FCZ_SMEM_LIMIT - 1024u) / cbytes;
         if (G > gmax) G = gmax;
-        if (G > 256u) G = 256u;
+        if (G > 1024u) G = 1024u;
         if (G < 1u) G = 1u;
         a.stitch_group = G;
-        k_dec_front<<<nch, 128, fs.total, e->stream>>>(a);
-        k_dec_stitch_t<<<(nch + G - 1u) / G, 1024, G * cbytes, e->stream>>>(a);
-        k_dec_back<<<nch, 192, bs.total, e->stream>>>(a);
-        e->launches += 3;
-        return FCZ_OK;
+        uint32_t sthr = 32u * G;  // enough warps to gather the group's scratch with deep queues
+        sthr = sthr < 256u ? 256u : (sthr > 1024u ? 1024u : sthr);
+        if (tr.smem) {
+            // front: three lanes per segment and direction -- enough warps that the passes take one trip
+            uint32_t thr = (6u * tr.max_anchor + 31u) & ~31u;
+            thr = thr < 128u ? 128u : (thr > 1024u ? 1024u : thr);
+            k_dec_front<<<tr.count, thr, front_smem(tr.max_L, tr.max_anchor, tr.max_blob).total, st>>>(a);
+            k_dec_stitch_t<<<(tr.count + G - 1u) / G, sthr, G * cbytes, st>>>(a);
+            // back: about one thread per two residues (side chains take two trips), whole warps
+            thr = ((tr.max_L * 35u) / 64u + 31u) & ~31u;
+            thr = thr < 192u ? 192u : (thr > 1024u ? 1024u : thr);
+            k_dec_back<<<tr.count, thr, back_smem(tr.max_L, tr.max_anchor, tr.max_atoms).total, st>>>(a);
+            e->launches += 3;
+        } else {
+            k_dec_unpack<<<tr.count, 256, 0, st>>>(a);
+            k_dec_passes<<<tr.count, 128, 0, st>>>(a);
+            k_dec_stitch_t<<<(tr.count + G - 1u) / G, sthr, G * cbytes, st>>>(a);
+            k_dec_blend<<<tr.count, 128, 0, st>>>(a);
+            k_dec_side<<<tr.count, 192, 0, st>>>(a);
+            e->launches += 5;
+        }
+        if (fork) {
+            CK(cudaEventRecord(e->ev_join[t], st));
+            CK(cudaStreamWaitEvent(e->stream, e->ev_join[t], 0));
+        }
     }
-    a.segid = (uint8_t*)e->sc_segid.p; a.tor = (cs*)e->sc_tor.p; a.ang = (cs*)e->sc_ang.p;
-    k_dec_unpack<<<nch, 256, 0, e->stream>>>(a);
-    k_dec_passes<<<nch, 128, 0, e->stream>>>(a);
-    k_dec_stitch<<<(nch + 127) / 128, 128, 0, e->stream>>>(a);
-    k_dec_blend<<<nch, 128, 0, e->stream>>>(a);
-    k_dec_side<<<nch, 192, 0, e->stream>>>(a);
-    e->launches += 5;
     return FCZ_OK;
 }
 
@@ -1663,16 +1735,31 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
     if ((rc = ensure(e, e->d_meta, sizeof(fcz_chain_meta) * (uint64_t)n + 16))) return rc;
     const uint32_t nchunks = (uint32_t)plan.chunk_c0.size() - 1u;
     std::vector<Dec2Sub> subs(nchunks);
+    plan.list.assign(n, 0u);  // chains grouped by (chunk, length tier)
     for (uint32_t k = 0; k < nchunks; k++) {
         const uint32_t c0 = plan.chunk_c0[k], c1 = plan.chunk_c0[k + 1];
-        subs[k] = {c0, c1, out->res_off[c0], out->res_off[c1], plan.seg_off[c0], plan.seg_off[c1], 0, 0, 0, 0, false};
+        Dec2Sub& sb = subs[k];
+        memset(&sb, 0, sizeof sb);
+        sb.c0 = c0; sb.c1 = c1; sb.r0 = out->res_off[c0]; sb.r1 = out->res_off[c1]; sb.s0 = plan.seg_off[c0]; sb.s1 = plan.seg_off[c1];
         for (uint32_t c = c0; c < c1; c++) {
-            subs[k].max_L = std::max(subs[k].max_L, out->res_off[c + 1] - out->res_off[c]);
-            subs[k].max_anchor = std::max(subs[k].max_anchor, plan.seg_off[c + 1] - plan.seg_off[c]);
-            subs[k].max_blob = std::max(subs[k].max_blob, (uint32_t)(in->blob_off[c + 1] - in->blob_off[c]));
-            subs[k].max_atoms = std::max(subs[k].max_atoms, (uint32_t)(out->atom_off[c + 1] - out->atom_off[c]));
+            if (plan.status[c] != FCZ_OK) continue;
+            Dec2Tier& tr = sb.tier[dec_tier_of(out->res_off[c + 1] - out->res_off[c])];
+            tr.count++;
+            tr.max_L = std::max(tr.max_L, out->res_off[c + 1] - out->res_off[c]);
+            tr.max_anchor = std::max(tr.max_anchor, plan.seg_off[c + 1] - plan.seg_off[c]);
+            tr.max_blob = std::max(tr.max_blob, (uint32_t)(in->blob_off[c + 1] - in->blob_off[c]));
+            tr.max_atoms = std::max(tr.max_atoms, (uint32_t)(out->atom_off[c + 1] - out->atom_off[c]));
+        }
+        size_t off = c0;
+        uint32_t cur[FCZ_DEC_TIERS];
+        for (int t = 0; t < FCZ_DEC_TIERS; t++) { sb.tier[t].list_off = off; cur[t] = 0; off += sb.tier[t].count; }
+        for (uint32_t c = c0; c < c1; c++) {
+            if (plan.status[c] != FCZ_OK) continue;
+            const uint32_t t = dec_tier_of(out->res_off[c + 1] - out->res_off[c]);
+            plan.list[sb.tier[t].list_off + cur[t]++] = c;
         }
     }
+    if ((rc = ensure(e, e->d_dec_list, 4ull * n + 16))) return rc;
     if ((rc = dec2_workspace(e, subs.data(), subs.size()))) return rc;
 
     size_t evi = 0;
@@ -1686,6 +1773,7 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
     COPY(e->d_title_off.p, out->title_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
     COPY(e->d_seg_off.p, plan.seg_off.data(), 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
     COPY(e->d_status.p, plan.status.data(), 4ull * n, cudaMemcpyHostToDevice, e->s_in);
+    if (n) COPY(e->d_dec_list.p, plan.list.data(), 4ull * n, cudaMemcpyHostToDevice, e->s_in);
     std::vector<cudaEvent_t> ev_in(nchunks);
     for (uint32_t k = 0; k < nchunks; k++) {
         const uint64_t b0 = in->blob_off[plan.chunk_c0[k]], b1 = in->blob_off[plan.chunk_c0[k + 1]];
@@ -1713,7 +1801,7 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
             k_dec_plan<<<(c1 - c0 + 7) / 8, 256, 0, e->stream>>>(c0, c1, (uint64_t*)e->d_blob_off.p, (uint8_t*)e->d_bytes.p, e->d_tables, tt, po, 1);
             e->launches++;
             ProfSpan ps(e, 1);
-            if ((rc = dec2_launch(e, a, subs[k]))) return rc;
+            if ((rc = dec2_launch(e, a, subs[k], (const uint32_t*)e->d_dec_list.p))) return rc;
         }
         cudaEvent_t ev_k = pool_event(e, evi++);
         CK(cudaEventRecord(ev_k, e->stream));
@@ -1762,8 +1850,9 @@ static int decode_plan_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain
     sa.in[2] = po.v2; sa.out[2] = out->title_off; sa.out64[2] = 0;
     sa.in[3] = po.v3; sa.out[3] = e->d_seg_off.p; sa.out64[3] = 0;
     if ((rc = run_scan(e, sa))) return rc;
+    if ((rc = ensure(e, e->d_dec_list, 4ull * FCZ_DEC_TIERS * n + 16))) return rc;
     k_plan_chunks<<<n / 256 + 1, 256, 0, e->stream>>>(n, e->dec_sub_res, out->res_off, (uint32_t*)e->d_seg_off.p, out->atom_off, in->blob_off,
-                                                  (uint32_t*)e->d_submax.p, e->h_bounds);
+                                                  po.status, (uint32_t*)e->d_dec_list.p, (uint32_t*)e->d_submax.p, e->h_bounds);
     e->launches++;
     if ((rc = fetch_plan(e))) return rc;
     totals->n_res = e->h_totals[0];
@@ -1778,12 +1867,20 @@ static int decode_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batc
     if (e->h_totals[0] > out->res_cap || e->h_totals[1] > out->atom_cap || (out->titles && e->h_totals[2] > out->title_cap))
         return fail(e, FCZ_E_CAPACITY, "decode output capacity too small (need %llu residues, %llu atoms, %llu title bytes)",
                     (unsigned long long)e->h_totals[0], (unsigned long long)e->h_totals[1], (unsigned long long)e->h_totals[2]);
-    const uint32_t nsub = e->h_bounds[0];
+    const uint32_t nsub = e->h_bounds[0], n = in->n_chains;
     std::vector<Dec2Sub> subs(nsub);
+    uint32_t per = nsub ? e->h_bounds[4] - e->h_bounds[1] : 0u;  // chains per sub-batch (the last may be shorter)
     for (uint32_t k = 0; k < nsub; k++) {
         const uint32_t* b = e->h_bounds + 1 + 3 * k;
-        const uint32_t* m = e->h_bounds + 1 + 3 * (nsub + 1) + 4 * k;
-        subs[k] = {b[0], b[3], b[1], b[4], b[2], b[5], m[0], m[1], m[2], m[3], false};
+        const uint32_t* m = e->h_bounds + 1 + 3 * (nsub + 1) + 5 * FCZ_DEC_TIERS * k;
+        Dec2Sub& sb = subs[k];
+        memset(&sb, 0, sizeof sb);
+        sb.c0 = b[0]; sb.c1 = b[3]; sb.r0 = b[1]; sb.r1 = b[4]; sb.s0 = b[2]; sb.s1 = b[5];
+        for (int t = 0; t < FCZ_DEC_TIERS; t++) {
+            Dec2Tier& tr = sb.tier[t];
+            tr.count = m[5 * t]; tr.max_L = m[5 * t + 1]; tr.max_anchor = m[5 * t + 2]; tr.max_blob = m[5 * t + 3]; tr.max_atoms = m[5 * t + 4];
+            tr.list_off = (size_t)t * n + (size_t)k * per;
+        }
     }
     int rc;
     if ((rc = dec2_workspace(e, subs.data(), subs.size()))) return rc;
@@ -1797,7 +1894,7 @@ static int decode_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batc
     {
         ProfSpan ps(e, 1);
         for (uint32_t k = 0; k < nsub; k++)
-            if ((rc = dec2_launch(e, a, subs[k]))) return rc;
+            if ((rc = dec2_launch(e, a, subs[k], (const uint32_t*)e->d_dec_list.p))) return rc;
     }
     CK(cudaGetLastError());
     return FCZ_OK;
