@@ -11,10 +11,12 @@ fcz_decode_batch on BASELINE.json configs[1] (10 000 synthetic single chains of 
   value      whole-job residues/s with the batch resident in HBM (device-pointer C ABI), K steps
              between two CUDA events on the engine's stream, max over ranks;
   e2e        the same round trip through the host-pointer C ABI (pinned host buffers; H2D of the
-             coordinates and D2H of blobs and decoded coordinates inside the timed region);
-  roofline   the slower of the two hot kernels (k_encode / k_decode): algorithmic bytes per launch
-             (SURVEY.md 8d / BASELINE.md 5) over its mean device time (CUDA events recorded by the
-             engine around each launch, same timed region), against MEASURED_PEAKS.json hbm_gbs;
+             coordinates and D2H of blobs and decoded coordinates inside the timed region), encode and
+             decode on two engines so that their PCIe directions overlap; wall clock;
+  roofline   the dominant hot kernel (longest device time per step among k_encode, k_dec_front,
+             k_dec_stitch_t, k_dec_back): its algorithmic bytes per launch (SURVEY.md 8d / BASELINE.md 5)
+             over its mean launch duration (CUDA events the engine records around each launch on the
+             launching stream, same timed region as `value`), against MEASURED_PEAKS.json hbm_gbs;
   cpu_baseline  the reference's own CPU path (oracle/_ref: unmodified sources compiled in place;
              Foldcomp::compress+writeStream+read+decompress per chain under OpenMP) on a bounded
              sample of the same workload, all host cores, rank 0 at N=1 only;
@@ -37,6 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_CHAINS, LENGTH, ANCHOR = 10000, 350, 25
+E2E_PARTS = 4  # sub-batches per step on the end-to-end path
 WORKLOAD_NOTE = ""
 METRIC = "residues/sec compress+decompress round-trip"
 UNIT = "residues/s"
@@ -263,19 +266,42 @@ def run_ours(args, rank, world, local_rank, out):
     assert dev_rt < 0.2, dev_rt
     fcz_bytes = int(dblob.blob_off[-1].item())
 
-    # ---- roofline of the dominant kernel
-    enc_ms = prof.encode_kernel_ms / max(prof.encode_launches, 1)  # one span per call: all tier launches, fork to join
-    dec_ms = prof.decode_kernel_ms / max(prof.decode_launches, 1)
+    # ---- roofline of the dominant kernel: the single kernel with the longest mean launch among the four hot
+    # kernels, each timed by CUDA events recorded on its own launch stream inside the timed region above
     enc_bytes = 12 * n_atoms + 5 * n_res + fcz_bytes
     dec_bytes = fcz_bytes + 12 * n_atoms + 4 * n_res
+    # algorithmic bytes per kernel (SURVEY.md 8d / BASELINE.md 5): encode reads coordinates+types+B-factors and
+    # writes FCZ; decode as a whole reads FCZ and writes coordinates+types+B-factors -- of that, the front kernel
+    # owns the FCZ read and the 5 B/residue it emits, the back kernel the coordinates it writes (it re-reads the
+    # side-chain bytes); the stitch kernel moves no algorithmic bytes at all (segment scratch only).
+    kalg = {"k_encode": enc_bytes, "k_dec_front": fcz_bytes + 5 * n_res, "k_dec_stitch_t": 0, "k_dec_back": 12 * n_atoms + (n_atoms - 3 * n_res)}
+    kernels = {}
+    for name, kind in abi.PROF_KINDS.items():
+        n_l = int(prof.kernel_launches[kind])
+        ms_l = float(prof.kernel_ms[kind]) / max(n_l, 1)
+        entry = {"ms_per_launch": ms_l, "launches_per_step": n_l / args.steps}
+        if name in kalg:
+            entry["algorithmic_bytes"] = kalg[name]
+            entry["gbs"] = kalg[name] / max(ms_l, 1e-9) / 1e6
+        elif name == "encode_span":
+            entry["algorithmic_bytes"] = enc_bytes
+            entry["gbs"] = enc_bytes / max(ms_l, 1e-9) / 1e6
+        elif name == "decode_span":
+            entry["algorithmic_bytes"] = dec_bytes
+            entry["gbs"] = dec_bytes / max(ms_l, 1e-9) / 1e6
+        kernels[name] = entry
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    kname, kms, kbytes = ("k_encode", enc_ms, enc_bytes) if enc_ms >= dec_ms else ("k_decode", dec_ms, dec_bytes)
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # launches per step > 1 (length tiers) -> total time per step of that kernel decides dominance
+    per_step = {k: kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"] for k in kalg}
+    kname = max(per_step, key=per_step.get)
+    kms = kernels[kname]["ms_per_launch"]
+    kbytes = kalg[kname] / max(kernels[kname]["launches_per_step"], 1.0)
     achieved = kbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
@@ -286,12 +312,25 @@ def run_ours(args, rank, world, local_rank, out):
     roofline = {
         "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src, "ms_per_launch": kms, "algorithmic_bytes_per_launch": kbytes,
-        "kernels": {"k_encode": {"ms_per_launch": enc_ms, "algorithmic_bytes": enc_bytes, "gbs": enc_bytes / max(enc_ms, 1e-9) / 1e6},
-                    "k_decode": {"ms_per_launch": dec_ms, "algorithmic_bytes": dec_bytes, "gbs": dec_bytes / max(dec_ms, 1e-9) / 1e6}},
-        "round_trip_bytes_per_residue": (enc_bytes + dec_bytes) / n_res,
+        "kernels": kernels, "round_trip_bytes_per_residue": (enc_bytes + dec_bytes) / n_res,
+        "round_trip_frac": (enc_bytes + dec_bytes) * args.steps / (ms * 1e-3) / 1e9 / peak,
     }
 
-    # ---- e2e: host-pointer C ABI, pinned buffers, copies inside the timed region
+    if args.kernels_only:  # profiling runs (ncu --set full): the device-resident region above is all that is needed
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": ms_max / args.steps,
+                              "roofline": roofline, "gpu_launches": launches, "note": "--kernels-only: no e2e / cpu_baseline legs"}), file=out, flush=True)
+        eng.close()
+        return
+
+    # ---- e2e: host-pointer C ABI, pinned host buffers, every copy inside the timed region.  The batch goes
+    # through in E2E_PARTS sub-batches on TWO engines driven by two host threads: one calls fcz_encode_batch,
+    # the other fcz_decode_plan + fcz_decode_batch on the blobs the first produced, so the encode's H2D traffic
+    # and the decode's D2H traffic share the full-duplex PCIe link (a compress job and a decompress job side
+    # by side, as the reference's CLI runs them under OpenMP).  Every step round-trips every chain; a blob
+    # buffer is reused only after its decode has finished.
+    import threading
+
     keep = []
 
     def pin(a):
@@ -299,36 +338,110 @@ def run_ours(args, rank, world, local_rank, out):
         keep.append(t)
         return v
 
-    hb = HostChainBatch(pin(batch.res_off), pin(batch.atom_off), pin(batch.title_off), pin(batch.res_type), pin(batch.bfactor),
-                        pin(batch.xyz), pin(batch.titles), pin(batch.meta), pin(np.zeros(batch.n_chains, np.int32)))
-    hblob = HostBlobBatch(pin(np.zeros(batch.n_chains + 1, np.uint64)), pin(np.zeros(cap, np.uint8)), pin(np.zeros(batch.n_chains, np.int32)))
-    hout = HostChainBatch(pin(np.zeros(batch.n_chains + 1, np.uint32)), pin(np.zeros(batch.n_chains + 1, np.uint64)),
-                          pin(np.zeros(batch.n_chains + 1, np.uint32)), pin(np.zeros(n_res, np.uint8)), pin(np.zeros(n_res, np.float32)),
-                          pin(np.zeros((n_atoms, 3), np.float32)), pin(np.zeros(max(n_title, 1), np.uint8)), pin(np.zeros(batch.n_chains, abi.META_DTYPE)),
-                          pin(np.zeros(batch.n_chains, np.int32)))
+    def pinned_chain_batch(b):
+        return HostChainBatch(pin(b.res_off), pin(b.atom_off), pin(b.title_off), pin(b.res_type), pin(b.bfactor),
+                              pin(b.xyz), pin(b.titles), pin(b.meta), pin(np.zeros(b.n_chains, np.int32)))
 
-    def e2e_step():
-        eng.encode_host(hb, hblob)
-        eng.decode_host(hblob, out=hout)
+    def pinned_out_batch(b):
+        nt = len(b.titles)
+        return HostChainBatch(pin(np.zeros(b.n_chains + 1, np.uint32)), pin(np.zeros(b.n_chains + 1, np.uint64)),
+                              pin(np.zeros(b.n_chains + 1, np.uint32)), pin(np.zeros(b.n_res, np.uint8)), pin(np.zeros(b.n_res, np.float32)),
+                              pin(np.zeros((b.n_atoms, 3), np.float32)), pin(np.zeros(max(nt, 1), np.uint8)),
+                              pin(np.zeros(b.n_chains, abi.META_DTYPE)), pin(np.zeros(b.n_chains, np.int32)))
 
-    for _ in range(3):
-        e2e_step()
+    def pinned_blob_batch(b):
+        c = abi.encode_bound(b.n_chains, b.n_res, b.n_atoms, len(b.titles), ANCHOR)
+        return HostBlobBatch(pin(np.zeros(b.n_chains + 1, np.uint64)), pin(np.zeros(c, np.uint8)), pin(np.zeros(b.n_chains, np.int32)))
+
+    bounds = [round(i * batch.n_chains / E2E_PARTS) for i in range(E2E_PARTS + 1)]
+    parts = [batch.select(range(bounds[i], bounds[i + 1])) for i in range(E2E_PARTS)]
+    h_in = [pinned_chain_batch(p) for p in parts]
+    h_blob = [pinned_blob_batch(p) for p in parts]
+    h_out = [pinned_out_batch(p) for p in parts]
+    eng_enc = Engine(local_rank, anchor_threshold=ANCHOR)
+    eng_dec = Engine(local_rank, anchor_threshold=ANCHOR)
+
+    def e2e_run(steps):
+        ready = [threading.Semaphore(0) for _ in range(E2E_PARTS)]
+        free = [threading.Semaphore(1) for _ in range(E2E_PARTS)]
+        errs = []
+
+        def enc_loop():
+            try:
+                for _ in range(steps):
+                    for j in range(E2E_PARTS):
+                        free[j].acquire()
+                        eng_enc.encode_host(h_in[j], h_blob[j])
+                        ready[j].release()
+            except Exception as ex:  # surface in the main thread
+                errs.append(ex)
+                for sem in ready:
+                    sem.release()
+
+        def dec_loop():
+            try:
+                for _ in range(steps):
+                    for j in range(E2E_PARTS):
+                        ready[j].acquire()
+                        if errs:
+                            return
+                        eng_dec.decode_host(h_blob[j], out=h_out[j])
+                        free[j].release()
+            except Exception as ex:
+                errs.append(ex)
+                for sem in free:
+                    sem.release()
+
+        th = [threading.Thread(target=enc_loop), threading.Thread(target=dec_loop)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if errs:
+            raise errs[0]
+        return dt
+
+    e2e_run(3)
     barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        e2e_step()
-    ev1.record(stream)
+    l1 = eng_enc.launch_count() + eng_dec.launch_count()
+    dt_e = e2e_run(args.steps)
+    e2e_launches = eng_enc.launch_count() + eng_dec.launch_count() - l1
     barrier()
-    ms_e = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    ms_e = torch.tensor([dt_e * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     e2e_value = world * n_res * args.steps / (float(ms_e.item()) * 1e-3)
-    assert not hout.status.any() and np.array_equal(hout.res_type, batch.res_type)
+    for p, o in zip(parts, h_out):
+        assert not o.status.any() and np.array_equal(o.res_type, p.res_type)
+        rt = float(np.sqrt(((o.xyz[:5000] - p.xyz[:5000]) ** 2).sum(1).mean()))
+        assert rt < 0.2, rt
     nc = batch.n_chains
     # bytes the host-pointer path moves per step (foldcomp_b200/csrc/fcz_engine.cu: encode_host / decode_host)
     h2d = (12 * n_atoms + 5 * n_res + n_title + 20 * nc + 16 * (nc + 1) + 8 * (nc + 1) + 4 * nc) \
         + (fcz_bytes + 24 * (nc + 1) + 8 * nc)
     d2h = fcz_bytes + (12 * n_atoms + 5 * n_res + n_title + 20 * nc + 4 * nc)
+
+    # the same round trip on ONE engine, one call after the other (no encode/decode overlap), for comparison
+    hb_all, hblob_all, hout_all = pinned_chain_batch(batch), pinned_blob_batch(batch), pinned_out_batch(batch)
+
+    def serial_step():
+        eng.encode_host(hb_all, hblob_all)
+        eng.decode_host(hblob_all, out=hout_all)
+
+    for _ in range(2):
+        serial_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        serial_step()
+    torch.cuda.synchronize(dev)
+    e2e_serial = n_res * args.steps / (time.perf_counter() - t0)
+    assert not hout_all.status.any() and np.array_equal(hout_all.res_type, batch.res_type)
+    eng_enc.close()
+    eng_dec.close()
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
@@ -347,7 +460,13 @@ def run_ours(args, rank, world, local_rank, out):
             "dtype": "f32+f64", "data": "synthetic", "config": workload_config(world), "roofline": roofline,
             "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(ms_e.item()) / args.steps},
+                    "ms_per_step": float(ms_e.item()) / args.steps, "gpu_launches": e2e_launches,
+                    "pcie_gbs_each_way": max(h2d, d2h) / (float(ms_e.item()) / args.steps) / 1e6,
+                    "how": f"host-pointer C ABI, pinned buffers, {E2E_PARTS} sub-batches per step, encode and decode on two "
+                           "engines from two host threads (H2D of encode overlaps D2H of decode); wall clock around K steps "
+                           "with a device synchronize on both sides, max over ranks",
+                    "serial_one_engine": {"value": world * e2e_serial, "unit": UNIT,
+                                          "how": "one engine, fcz_encode_batch then fcz_decode_batch on the whole batch, no overlap"}},
             "gpu_launches": launches, "fcz_bytes_per_step": fcz_bytes, "roundtrip_rmsd_vs_input": dev_rt,
         }
         print(json.dumps(line), file=out, flush=True)
@@ -373,6 +492,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernels-only", action="store_true", help="profiling aid: stop after the device-resident timed region")
     ap.add_argument("--lengths", default="fixed", choices=["fixed", "mixed"],
                     help="fixed = the headline workload (BASELINE.json configs[1]); mixed = the same number of chains with the "
                          "clipped log-normal lengths of configs[4] (AFDB proxy, 50..2000 residues) -- a secondary measurement")

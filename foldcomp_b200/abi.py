@@ -99,7 +99,12 @@ class FczProfile(C.Structure):
         ("decode_kernel_ms", C.c_double),
         ("encode_launches", C.c_uint64),
         ("decode_launches", C.c_uint64),
+        ("kernel_ms", C.c_double * 8),
+        ("kernel_launches", C.c_uint64 * 8),
     ]
+
+
+PROF_KINDS = {"encode_span": 0, "decode_span": 1, "k_encode": 2, "k_dec_front": 3, "k_dec_stitch_t": 4, "k_dec_back": 5}
 
 
 def _ptr(a: np.ndarray | None):

@@ -34,18 +34,20 @@ struct TierCfg {
     uint32_t max_blob;   // blob bytes
     uint32_t max_seg;    // anchor segments (decode)
     uint32_t staged;     // 1: chain data staged in smem; 0: large tier, data stays in global memory
+    uint32_t gws;        // 1: the workspace (atom offsets, angle arrays) lives in global memory too (k_encode_long)
     uint32_t threads;
     uint32_t smem;       // dynamic shared memory bytes
 };
 
-#define FCZ_NTIER 7
+#define FCZ_NTIER 8
 #define FCZ_MAX_CHUNKS 4096       // decode sub-batches per call
 #define FCZ_SUB_RESIDUES 8000000u  // residues per decode sub-batch (bounds the workspace: ~80 B/residue)
 // residue caps per tier; decode carries more per-residue state in shared memory (198 B vs 175 B), so its
-// last staged tier is smaller.  The last tier keeps chain data in global memory.
+// last staged tier is smaller.  Tier 6 keeps chain data in global memory, tier 7 (up to the format's 65535
+// residues) its workspace as well.
 // Caps are chosen at the occupancy steps of the per-residue shared-memory footprint (encode ~172 B/residue,
 // 350-residue chains run 3 CTAs/SM).  Decode has no tiers: it is batch-wide (see below).
-static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 296, 408, 632, 1280, 2720};
+static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 296, 408, 632, 1280, 2720, 65535};
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
@@ -60,25 +62,26 @@ __host__ __device__ inline EncSmem enc_smem(const TierCfg& t) {
     s.o_misc = o; o += 256;  // mbarrier, ticket, warp sums
     s.o_red = o;  o += align16(4u * FCZ_RED_FLOATS(32));
     s.o_type = o; o += t.staged ? align16(t.max_res) : 0u;
-    s.o_aoff = o; o += align16(4u * (t.max_res + 1u));
-    s.o_ares = o; o += align16(2u * t.max_atoms);
-    s.o_ang = o;  o += align16(24u * t.max_res);
+    s.o_aoff = o; o += t.gws ? 0u : align16(4u * (t.max_res + 1u));
+    s.o_ares = o; o += t.gws ? 0u : align16(2u * t.max_atoms);
+    s.o_ang = o;  o += t.gws ? 0u : align16(24u * t.max_res);
     s.o_x = o;    o += t.staged ? align16(12u * t.max_atoms) + 32u : 0u;
     s.o_b = o;    o += t.staged ? align16(t.max_blob) + 32u : 0u;
     s.total = o;
     return s;
 }
-static TierCfg make_tier(uint32_t max_res, bool staged) {
+static TierCfg make_tier(uint32_t max_res, bool staged, bool gws) {
     TierCfg t;
     t.max_res = max_res;
     t.staged = staged ? 1u : 0u;
+    t.gws = gws ? 1u : 0u;
     t.max_atoms = 9u * max_res;
     t.max_blob = 17u * max_res + 1280u;
     t.max_seg = max_res / 10u + 8u;
     if (t.max_seg > 254u) t.max_seg = 254u;
     t.threads = (max_res <= 128u) ? 128u : 320u;
     if (!staged) {
-        t.max_atoms = 10u * max_res;
+        t.max_atoms = gws ? FCZ_MAX_ATOMS * max_res : 10u * max_res;
         t.max_blob = 0xFFFFFFFFu;
         t.max_seg = 254u;
         t.threads = 256u;
@@ -88,7 +91,7 @@ static TierCfg make_tier(uint32_t max_res, bool staged) {
 }
 static void make_tiers(TierCfg* enc) {
     for (int i = 0; i < FCZ_NTIER; i++) {
-        enc[i] = make_tier(kEncTierRes[i], i < FCZ_NTIER - 1);
+        enc[i] = make_tier(kEncTierRes[i], i < FCZ_NTIER - 2, i == FCZ_NTIER - 1);
         enc[i].smem = enc_smem(enc[i]).total;
         enc[i].threads = 128u;  // settled at engine creation from the occupancy the footprint allows
     }
@@ -260,6 +263,9 @@ struct EncArgs {
     const Tables* tables;
     int32_t b;
     TierCfg cfg;
+    uint8_t* gws;         // k_encode_long: per-block workspace in global memory, gws_stride bytes each
+    uint64_t gws_stride;
+    uint32_t gws_max_res; // residues the workspace was sized for
 };
 
 // Plan: one warp per chain.  Validates the chain, computes its blob size and tier.
@@ -327,6 +333,7 @@ __global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* 
         if (tier >= 0) {
             uint32_t pos = atomicAdd(&po.tier_count[tier], 1u);
             po.tier_list[(size_t)tier * n + pos] = c;
+            if (tt.t[tier].gws) atomicMax(&po.tier_count[2 * FCZ_NTIER], L);  // sizes the long tier's global workspace
         }
     }
 }
@@ -413,6 +420,56 @@ __global__ void __launch_bounds__(1024) k_encode(EncArgs a) {
             cx.staged = false;
         }
         __syncthreads();  // shared buffers free for the next chain
+    }
+}
+
+// The long tier (2721 .. 65535 residues): chain data AND workspace stay in global memory (per-block slices of
+// a.gws, sized for the tier's longest chain); otherwise the same persistent ticket loop as k_encode.
+__host__ __device__ inline uint64_t enc_gws_bytes(uint32_t max_res) {
+    return (uint64_t)align16(4u * (max_res + 1u)) + align16(2u * (FCZ_MAX_ATOMS - 3u) * max_res) + align16(24u * max_res);
+}
+__global__ void __launch_bounds__(1024) k_encode_long(EncArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const EncSmem so = enc_smem(a.cfg);
+    Tables* tb = reinterpret_cast<Tables*>(smem + so.o_tab);
+    uint32_t* s_ticket = reinterpret_cast<uint32_t*>(smem + so.o_misc + 8);
+    DevCtx cx;
+    cx.tid = threadIdx.x; cx.nthr = blockDim.x; cx.lane = threadIdx.x & 31; cx.warp = threadIdx.x >> 5;
+    cx.nwarps = blockDim.x >> 5;
+    cx.wsum = reinterpret_cast<uint32_t*>(smem + so.o_misc + 64);
+    cx.bar = nullptr; cx.parity = 0; cx.staged = false;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tb);
+        for (uint32_t i = cx.tid; i < (uint32_t)offsetof(Tables, blen) / 4u; i += cx.nthr) dst[i] = src[i];
+    }
+    __syncthreads();
+    uint8_t* ws = a.gws + (uint64_t)blockIdx.x * a.gws_stride;
+    const uint32_t count = a.count ? *a.count : a.count_val;
+    for (;;) {
+        if (cx.tid == 0) *s_ticket = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const uint32_t t = *s_ticket;
+        if (t >= count) break;
+        const uint32_t c = a.list[t];
+        const uint32_t r0 = a.res_off[c], L = a.res_off[c + 1] - r0;
+        const uint64_t a0 = a.atom_off[c];
+        const uint32_t t0 = a.title_off[c];
+        if (L > a.gws_max_res) __trap();  // the plan sized the workspace from these very chains
+        EncChain ch;
+        ch.L = L; ch.A = (uint32_t)(a.atom_off[c + 1] - a0); ch.title_len = a.title_off[c + 1] - t0; ch.b = a.b;
+        ch.bfac = a.bfactor + r0;
+        ch.title = a.titles + t0;
+        ch.meta = a.meta + c;
+        ch.aoff = reinterpret_cast<uint32_t*>(ws);
+        ch.sres = reinterpret_cast<uint16_t*>(ws + align16(4u * (a.gws_max_res + 1u)));
+        ch.ang = reinterpret_cast<float*>(ws + align16(4u * (a.gws_max_res + 1u)) + align16(2u * (FCZ_MAX_ATOMS - 3u) * a.gws_max_res));
+        ch.red = reinterpret_cast<float*>(smem + so.o_red);
+        ch.X = a.xyz + 3u * a0;
+        ch.type = a.res_type + r0;
+        ch.B = a.bytes + a.blob_off[c];
+        encode_chain(cx, tb, ch);
+        __syncthreads();
     }
 }
 
@@ -998,7 +1055,7 @@ struct fcz_engine {
     uint32_t* h_bounds = nullptr;    // pinned: [0] nchunks, then chain / residue / segment-slot bounds of the decode sub-batches
     // staging for host-memory batches
     DevBuf d_res_off, d_atom_off, d_title_off, d_res_type, d_bfactor, d_xyz, d_titles, d_meta, d_blob_off, d_bytes, d_status;
-    DevBuf d_list, d_tickets;
+    DevBuf d_list, d_tickets, enc_gws;
     DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax, d_dec_list;  // batch-wide decoder: segment offsets + L2-resident workspace
     // plan made on the host by fcz_decode_plan(host) for the following fcz_decode_batch(host)
     struct Launch { uint32_t chunk, tier, first, count; };
@@ -1025,13 +1082,13 @@ static cudaEvent_t take_event(fcz_engine* e) {
     else cudaEventCreate(&ev);
     return ev;
 }
-struct ProfSpan {  // RAII: events around one kernel launch when profiling is on
-    fcz_engine* e; cudaEvent_t a = nullptr, b = nullptr; int kind;
-    ProfSpan(fcz_engine* e_, int kind_) : e(e_), kind(kind_) {
-        if (e->profiling) { a = take_event(e); b = take_event(e); cudaEventRecord(a, e->stream); }
+struct ProfSpan {  // RAII: events around one kernel launch (or one fork-to-join span) when profiling is on
+    fcz_engine* e; cudaEvent_t a = nullptr, b = nullptr; int kind; cudaStream_t st;
+    ProfSpan(fcz_engine* e_, int kind_, cudaStream_t st_ = nullptr) : e(e_), kind(kind_), st(st_ ? st_ : e_->stream) {
+        if (e->profiling) { a = take_event(e); b = take_event(e); cudaEventRecord(a, st); }
     }
     ~ProfSpan() {
-        if (a) { cudaEventRecord(b, e->stream); e->spans.push_back({a, b, kind}); }
+        if (a) { cudaEventRecord(b, st); e->spans.push_back({a, b, kind}); }
     }
 };
 
@@ -1100,6 +1157,7 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     }
     for (int i = 0; i < FCZ_NTIER && ok; i++) {
         ok &= cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(k_encode_long, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         ok &= cudaFuncSetAttribute(k_dec_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         ok &= cudaFuncSetAttribute(k_dec_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         ok &= cudaFuncSetAttribute(k_dec_stitch_t, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
@@ -1112,13 +1170,14 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
         e->enc_tier[i].threads = thr < 128u ? 128u : thr;
         ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, (int)e->enc_tier[i].threads, e->enc_tier[i].smem) == cudaSuccess;
         e->enc_occ[i] = occ > 0 ? occ : 1;
+        if (e->enc_tier[i].gws) { e->enc_tier[i].threads = 1024u; e->enc_occ[i] = 1; }  // one wide block per SM walks a long chain
     }
     Tables h;
     build_tables(&h);
     ok &= cudaMalloc(&e->d_tables, sizeof(Tables)) == cudaSuccess;
-    ok &= cudaMalloc(&e->d_counters, sizeof(uint32_t) * 2 * FCZ_NTIER) == cudaSuccess;
+    ok &= cudaMalloc(&e->d_counters, sizeof(uint32_t) * (2 * FCZ_NTIER + 2)) == cudaSuccess;
     ok &= cudaMalloc(&e->d_totals, sizeof(uint64_t) * 4) == cudaSuccess;
-    ok &= cudaMallocHost(&e->h_counters, sizeof(uint32_t) * 2 * FCZ_NTIER) == cudaSuccess;
+    ok &= cudaMallocHost(&e->h_counters, sizeof(uint32_t) * (2 * FCZ_NTIER + 2)) == cudaSuccess;
     ok &= cudaMallocHost(&e->h_totals, sizeof(uint64_t) * 4) == cudaSuccess;
     ok &= cudaMallocHost(&e->h_bounds, sizeof(uint32_t) * ((3 + 5 * FCZ_DEC_TIERS) * (FCZ_MAX_CHUNKS + 1) + 1)) == cudaSuccess;
     if (ok) ok &= cudaMemcpy(e->d_tables, &h, sizeof(Tables), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -1138,7 +1197,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->v3, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
-                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets,
+                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets, &e->enc_gws,
                       &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -1223,8 +1282,9 @@ int fcz_engine_get_profile(fcz_engine* e, fcz_profile* out) {
     for (auto& s : e->spans) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, s.a, s.b));
-        if (s.kind == 0) { out->encode_kernel_ms += ms; out->encode_launches++; }
-        else { out->decode_kernel_ms += ms; out->decode_launches++; }
+        if (s.kind == FCZ_PROF_ENCODE) { out->encode_kernel_ms += ms; out->encode_launches++; }
+        else if (s.kind == FCZ_PROF_DECODE) { out->decode_kernel_ms += ms; out->decode_launches++; }
+        if (s.kind >= 0 && s.kind < FCZ_PROF_KINDS) { out->kernel_ms[s.kind] += ms; out->kernel_launches[s.kind]++; }
         e->free_events.push_back(s.a);
         e->free_events.push_back(s.b);
     }
@@ -1274,7 +1334,7 @@ static int plan_buffers(fcz_engine* e, uint32_t n) {
     if ((rc = ensure(e, e->tier_list, 4ull * n * FCZ_NTIER + 4))) return rc;
     uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if ((rc = ensure(e, e->partial, 32ull * (ntiles + 1)))) return rc;
-    CK(cudaMemsetAsync(e->d_counters, 0, sizeof(uint32_t) * 2 * FCZ_NTIER, e->stream));
+    CK(cudaMemsetAsync(e->d_counters, 0, sizeof(uint32_t) * (2 * FCZ_NTIER + 2), e->stream));
     return FCZ_OK;
 }
 
@@ -1292,13 +1352,36 @@ static int run_scan(fcz_engine* e, ScanArgs& sa) {
 
 // counters + totals -> pinned host, then wait for them
 static int fetch_plan(fcz_engine* e) {
-    CK(cudaMemcpyAsync(e->h_counters, e->d_counters, sizeof(uint32_t) * FCZ_NTIER, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_counters, e->d_counters, sizeof(uint32_t) * (2 * FCZ_NTIER + 2), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(e->h_totals, e->d_totals, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return FCZ_OK;
 }
 
 // ------------------------------------------------------------------------------------------- encode
+
+// one tier's persistent launch: k_encode, or k_encode_long with its global workspace for the long tier
+static int launch_encode(fcz_engine* e, EncArgs& a, int tier, uint32_t cnt, uint32_t long_max_res, cudaStream_t st) {
+    a.cfg = e->enc_tier[tier];
+    a.gws = nullptr; a.gws_stride = 0; a.gws_max_res = 0;
+    uint32_t grid = (uint32_t)(e->num_sms * e->enc_occ[tier]);
+    if (grid > cnt) grid = cnt;
+    ProfSpan pk(e, FCZ_PROF_K_ENCODE, st);
+    if (a.cfg.gws) {
+        if (grid > (uint32_t)e->num_sms) grid = (uint32_t)e->num_sms;
+        if (long_max_res < 1u || long_max_res > a.cfg.max_res) long_max_res = a.cfg.max_res;
+        a.gws_stride = enc_gws_bytes(long_max_res);
+        a.gws_max_res = long_max_res;
+        int rc;
+        if ((rc = ensure(e, e->enc_gws, a.gws_stride * grid))) return rc;  // stream-ordered reuse: launches on one engine are serialised
+        a.gws = (uint8_t*)e->enc_gws.p;
+        k_encode_long<<<grid, a.cfg.threads, a.cfg.smem, st>>>(a);
+    } else {
+        k_encode<<<grid, a.cfg.threads, a.cfg.smem, st>>>(a);
+    }
+    e->launches++;
+    return FCZ_OK;
+}
 
 static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch* out, uint64_t* total_bytes) {
     const uint32_t n = in->n_chains;
@@ -1329,7 +1412,7 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
     for (int i = 0; i < FCZ_NTIER; i++) ntier += e->h_counters[i] ? 1 : 0;
     // tiers run side by side on their own streams (the long-chain tiers have few, long-running blocks)
     const bool fork = ntier > 1;
-    ProfSpan ps(e, 0);
+    ProfSpan ps(e, FCZ_PROF_ENCODE);
     if (fork) CK(cudaEventRecord(e->ev_fork, e->stream));
     for (int i = 0; i < FCZ_NTIER; i++) {
         const uint32_t cnt = e->h_counters[i];
@@ -1346,11 +1429,7 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
         a.ticket = e->d_counters + FCZ_NTIER + i;
         a.tables = e->d_tables;
         a.b = e->opts.anchor_threshold;
-        a.cfg = e->enc_tier[i];
-        uint32_t grid = (uint32_t)(e->num_sms * e->enc_occ[i]);
-        if (grid > cnt) grid = cnt;
-        k_encode<<<grid, a.cfg.threads, a.cfg.smem, st>>>(a);
-        e->launches++;
+        if ((rc = launch_encode(e, a, i, cnt, e->h_counters[2 * FCZ_NTIER], st))) return rc;
         if (fork) {
             CK(cudaEventRecord(e->ev_join[i], st));
             CK(cudaStreamWaitEvent(e->stream, e->ev_join[i], 0));
@@ -1469,6 +1548,7 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
     uint8_t nat_lut[256];
     for (int i = 0; i < 256; i++) nat_lut[i] = i < FCZ_NUM_CODES ? FCZ_NATOMS[i] : 0;
     std::vector<int8_t> tier(n, -1);
+    uint32_t long_max_res = 0;  // longest chain of the long tier: sizes its global workspace
     plan.status.assign(n, FCZ_OK);
     out->blob_off[0] = 0;
     for (uint32_t c = 0; c < n; c++) {
@@ -1490,7 +1570,10 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
                 size = make_layout(L, sum - 3u * L, T, (uint32_t)na).size;
                 const int t = host_pick_tier(e->enc_tier, L, sum, size, (uint32_t)na - 1u);
                 if (t < 0) { st = FCZ_E_LIMIT; size = 0; }
-                else tier[c] = (int8_t)t;
+                else {
+                    tier[c] = (int8_t)t;
+                    if (e->enc_tier[t].gws && L > long_max_res) long_max_res = L;
+                }
             }
         }
         plan.status[c] = st;
@@ -1526,14 +1609,11 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
             a.list = (uint32_t*)e->d_list.p + ln.first;
             a.count = nullptr; a.count_val = ln.count;
             a.ticket = (uint32_t*)e->d_tickets.p + k * FCZ_NTIER + ln.tier;
-            a.tables = e->d_tables; a.b = b; a.cfg = e->enc_tier[ln.tier];
-            uint32_t grid = (uint32_t)(e->num_sms * e->enc_occ[ln.tier]);
-            if (grid > ln.count) grid = ln.count;
+            a.tables = e->d_tables; a.b = b;
             {
-                ProfSpan ps(e, 0);
-                k_encode<<<grid, a.cfg.threads, a.cfg.smem, e->stream>>>(a);
+                ProfSpan ps(e, FCZ_PROF_ENCODE);
+                if ((rc = launch_encode(e, a, (int)ln.tier, ln.count, long_max_res, e->stream))) return rc;
             }
-            e->launches++;
         }
         cudaEvent_t ev_k = pool_event(e, evi++);
         CK(cudaEventRecord(ev_k, e->stream));
@@ -1648,12 +1728,21 @@ static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb, const uint3
             // front: three lanes per segment and direction -- enough warps that the passes take one trip
             uint32_t thr = (6u * tr.max_anchor + 31u) & ~31u;
             thr = thr < 128u ? 128u : (thr > 1024u ? 1024u : thr);
-            k_dec_front<<<tr.count, thr, front_smem(tr.max_L, tr.max_anchor, tr.max_blob).total, st>>>(a);
-            k_dec_stitch_t<<<(tr.count + G - 1u) / G, sthr, G * cbytes, st>>>(a);
+            {
+                ProfSpan pk(e, FCZ_PROF_K_DEC_FRONT, st);
+                k_dec_front<<<tr.count, thr, front_smem(tr.max_L, tr.max_anchor, tr.max_blob).total, st>>>(a);
+            }
+            {
+                ProfSpan pk(e, FCZ_PROF_K_DEC_STITCH, st);
+                k_dec_stitch_t<<<(tr.count + G - 1u) / G, sthr, G * cbytes, st>>>(a);
+            }
             // back: about one thread per two residues (side chains take two trips), whole warps
             thr = ((tr.max_L * 35u) / 64u + 31u) & ~31u;
             thr = thr < 192u ? 192u : (thr > 1024u ? 1024u : thr);
-            k_dec_back<<<tr.count, thr, back_smem(tr.max_L, tr.max_anchor, tr.max_atoms).total, st>>>(a);
+            {
+                ProfSpan pk(e, FCZ_PROF_K_DEC_BACK, st);
+                k_dec_back<<<tr.count, thr, back_smem(tr.max_L, tr.max_anchor, tr.max_atoms).total, st>>>(a);
+            }
             e->launches += 3;
         } else {
             k_dec_unpack<<<tr.count, 256, 0, st>>>(a);
@@ -1800,7 +1889,7 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
         if (c1 > c0) {
             k_dec_plan<<<(c1 - c0 + 7) / 8, 256, 0, e->stream>>>(c0, c1, (uint64_t*)e->d_blob_off.p, (uint8_t*)e->d_bytes.p, e->d_tables, tt, po, 1);
             e->launches++;
-            ProfSpan ps(e, 1);
+            ProfSpan ps(e, FCZ_PROF_DECODE);
             if ((rc = dec2_launch(e, a, subs[k], (const uint32_t*)e->d_dec_list.p))) return rc;
         }
         cudaEvent_t ev_k = pool_event(e, evi++);
@@ -1892,7 +1981,7 @@ static int decode_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batc
     a.status = out->status ? out->status : (int32_t*)e->status.p;
     a.tables = e->d_tables; a.use_alt = e->opts.use_alt_atom_order;
     {
-        ProfSpan ps(e, 1);
+        ProfSpan ps(e, FCZ_PROF_DECODE);
         for (uint32_t k = 0; k < nsub; k++)
             if ((rc = dec2_launch(e, a, subs[k], (const uint32_t*)e->d_dec_list.p))) return rc;
     }

@@ -60,8 +60,18 @@ def generate(n_chains: int, length=350, seed: int = SEED, first_index: int = 0) 
 
     lens = np.full(n_chains, int(length), np.int64) if np.isscalar(length) else np.asarray(length, np.int64)
     assert len(lens) == n_chains and (n_chains == 0 or lens.min() >= 2)
-    parts = [_generate_chunk(lens[s : s + CHUNK], seed, first_index + s) for s in range(0, n_chains, CHUNK)]
-    return concat_batches(parts)
+    if n_chains == 0 or lens.min() == lens.max():
+        parts = [_generate_chunk(lens[s : s + CHUNK], seed, first_index + s) for s in range(0, n_chains, CHUNK)]
+        return concat_batches(parts)
+    # ragged: a chunk costs its LONGEST chain, so chunks are cut from the length-sorted order and the chains put
+    # back in the requested order afterwards (titles follow the final position)
+    order = np.argsort(lens, kind="stable")
+    parts = [_generate_chunk(lens[order[s : s + CHUNK]], seed, first_index + s) for s in range(0, n_chains, CHUNK)]
+    inv = np.empty(n_chains, np.int64)
+    inv[order] = np.arange(n_chains)
+    out = concat_batches(parts).select(inv)
+    out.titles = np.frombuffer(b"".join(b"syn_%07d" % (first_index + i) for i in range(n_chains)), np.uint8).copy()
+    return out
 
 
 def _generate_chunk(lens: np.ndarray, seed: int, first_index: int) -> HostChainBatch:

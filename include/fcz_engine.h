@@ -135,13 +135,23 @@ int fcz_engine_sync(fcz_engine* e);
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 uint64_t fcz_engine_launch_count(const fcz_engine* e);
 
-/* Optional per-kernel timing with CUDA events recorded on the engine's stream around every launch of
- * the two hot kernels (k_encode, k_decode).  fcz_engine_get_profile synchronises the stream, returns
- * the accumulated device times since the last call and resets them.  bench.py uses it for the
- * roofline of the dominant kernel. */
+/* Optional timing with CUDA events recorded around every launch, on the stream the kernel is launched on.
+ * fcz_engine_get_profile synchronises the engine's stream, returns the accumulated device times since the
+ * last call and resets them.  bench.py uses it for the roofline of the dominant kernel.
+ *   encode_kernel_ms / decode_kernel_ms   whole hot-path spans: every tier's launches, fork to join
+ *   kernel_ms[k] / kernel_launches[k]     the same per kind k (FCZ_PROF_*): the two spans and each kernel alone */
+#define FCZ_PROF_ENCODE 0        /* span: all k_encode launches of one fcz_encode_batch                        */
+#define FCZ_PROF_DECODE 1        /* span: front + stitch + back of every tier of one fcz_decode_batch          */
+#define FCZ_PROF_K_ENCODE 2      /* one k_encode launch                                                        */
+#define FCZ_PROF_K_DEC_FRONT 3   /* one k_dec_front launch (unpack + NeRF passes)                              */
+#define FCZ_PROF_K_DEC_STITCH 4  /* one k_dec_stitch_t launch (serial walk over anchor segments)               */
+#define FCZ_PROF_K_DEC_BACK 5    /* one k_dec_back launch (blend + side chains + copy-out)                     */
+#define FCZ_PROF_KINDS 8
 typedef struct fcz_profile {
-    double encode_kernel_ms, decode_kernel_ms; /* summed device time of k_encode / k_decode launches */
-    uint64_t encode_launches, decode_launches; /* how many launches that is                       */
+    double encode_kernel_ms, decode_kernel_ms;
+    uint64_t encode_launches, decode_launches;
+    double kernel_ms[FCZ_PROF_KINDS];
+    uint64_t kernel_launches[FCZ_PROF_KINDS];
 } fcz_profile;
 int fcz_engine_set_profiling(fcz_engine* e, int enabled);
 int fcz_engine_get_profile(fcz_engine* e, fcz_profile* out);

@@ -292,3 +292,24 @@ def backbone_mask_fast(res_type: np.ndarray) -> np.ndarray:
     for k in range(3):
         m[starts + k] = True
     return m
+
+
+def long_chain(L: int, seed: int = 0) -> HostChainBatch:
+    """One chain of L residues made by joining 350-residue synthetic chains end to end (seconds even for the
+    format's maximum of 65535 residues; the generator's serial NeRF walk would take a minute).  The joints have
+    arbitrary geometry, which is fine: encode parity is bit-exact on any coordinates and decode parity compares
+    two decoders on the same blob."""
+    from foldcomp_b200 import synth
+
+    nparts = (L + 349) // 350
+    src = synth.generate(nparts, 350, seed=4242 + seed)
+    # shift part i so that the chain does not fold back onto itself
+    xyz = src.xyz.copy()
+    for i in range(nparts):
+        a0, a1 = int(src.atom_off[i]), int(src.atom_off[i + 1])
+        xyz[a0:a1] += np.float32(3.8) * i
+    rt = src.res_type[:L]
+    A = int(tables().natoms[rt].sum())
+    meta = src.meta[:1].copy()
+    meta["n_atom"] = np.uint16((A + int(meta["has_oxt"][0])) & 0xFFFF)  # the header field is 16 bits (src/foldcomp.h:118-131)
+    return abi.concat_chains([(rt, src.bfactor[:L], xyz[:A], np.frombuffer(f"long_{L}".encode(), np.uint8), meta)])

@@ -63,3 +63,14 @@ def test_model_alt_order(golden):
     blob = golden.blobs(25)[c]
     do, de = H.oracle_decode(blob, use_alt=True), H.emu_decode(blob, use_alt=True)
     assert H.max_dev(de.xyz, do.xyz) <= TOL_MAX
+
+
+def test_model_long_chains_up_to_format_maximum():
+    """Chains beyond the shared-memory tiers, up to the format's 16-bit residue count (src/foldcomp.h:118-131)."""
+    for L, b in ((2721, 25), (6200, 25), (50000, 200), (65535, 300)):
+        batch = H.long_chain(L)
+        o = H.oracle_encode(batch, 0, b)
+        assert H.emu_encode(batch, 0, b) == o, (L, b)
+        do, de = H.oracle_decode(o), H.emu_decode(o)
+        bb = H.backbone_mask(do.res_type)
+        assert H.rmsd(de.xyz[bb], do.xyz[bb]) <= TOL_BB_RMSD and H.max_dev(de.xyz, do.xyz) <= TOL_MAX, (L, b)

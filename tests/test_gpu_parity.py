@@ -147,14 +147,22 @@ def test_edge_cases(engine):
     assert out.n_chains == 0 and int(out.blob_off[0]) == 0
     dec = engine.decode_host(HostBlobBatch.from_blobs([]))
     assert dec.n_chains == 0
-    # shortest chains, ragged batch with one invalid residue code and one chain that is too long
+    # shortest chains, ragged batch with one invalid residue code and one chain with more anchors than the
+    # header's 8-bit nAnchor can hold (3100/10 + 2 = 312 > 255, src/foldcomp.h:118-131)
     lens = np.array([2, 3, 5, 40, 3100])
     batch = synth.generate(len(lens), lens, seed=9)
     r = int(batch.res_off[3]) + 7
     batch.res_type[r] = 20  # ASX has no table entry: the reference throws (AAS.at), we report FCZ_E_RESIDUE
+    engine.set_opts(anchor_threshold=10)
+    try:
+        got = engine.encode_host(batch)
+        assert list(got.status) == [0, 0, 0, abi.FCZ_E_RESIDUE, abi.FCZ_E_LIMIT]
+        assert got.blob(3) == b"" and got.blob(4) == b""
+    finally:
+        engine.set_opts(anchor_threshold=25)
     got = engine.encode_host(batch)
-    assert list(got.status) == [0, 0, 0, abi.FCZ_E_RESIDUE, abi.FCZ_E_LIMIT]
-    assert got.blob(3) == b"" and got.blob(4) == b""
+    assert list(got.status) == [0, 0, 0, abi.FCZ_E_RESIDUE, 0]
+    assert got.blob(3) == b"" and got.blob(4) == H.oracle_encode(batch, 4, 25)
     for c in range(3):
         assert got.blob(c) == H.oracle_encode(batch, c, 25)
     # decode: bad magic, truncated blob, good blob in one batch
@@ -209,6 +217,45 @@ def test_long_titles_and_unaligned_offsets(engine):
     _assert_decoded_close(dec, H.oracle_decode_batch(want))
 
 
+@pytest.mark.parametrize("device_api", [False, True])
+def test_long_chains_up_to_format_maximum(engine, device_api):
+    """Chains beyond the shared-memory tiers (k_encode_long, the global-workspace decode kernels), up to the
+    format's 16-bit residue count; mixed into one batch with short chains so every tier launches side by side."""
+    import torch
+
+    from foldcomp_b200.engine import DeviceBlobBatch, DeviceChainBatch
+
+    for b, lens in ((25, (2721, 3400, 6200)), (200, (20000, 50000)), (300, (65535,))):
+        parts = [H.long_chain(L, seed=i) for i, L in enumerate(lens)] + [synth.generate(12, np.array([2, 60, 350] * 4), seed=3)]
+        batch = abi.concat_batches(parts)
+        engine.set_opts(anchor_threshold=b)
+        try:
+            want = H.oracle_encode_batch(batch, b)
+            if device_api:
+                dev = torch.device("cuda:0")
+                dbatch = DeviceChainBatch.from_host(batch, dev)
+                dblob = DeviceBlobBatch(batch.n_chains, abi.encode_bound(batch.n_chains, batch.n_res, batch.n_atoms, len(batch.titles), b), dev)
+                torch.cuda.synchronize()
+                engine.encode_device(dbatch, dblob)
+                engine.sync()
+                got = dblob.to_host()
+                dout = DeviceChainBatch(batch.n_chains, batch.n_res, batch.n_atoms, len(batch.titles), dev)
+                engine.decode_plan_device(dblob, dout)
+                engine.decode_device(dblob, dout)
+                engine.sync()
+                dec = dout.to_host()
+            else:
+                got = engine.encode_host(batch)
+                dec = engine.decode_host(HostBlobBatch(want.blob_off, want.bytes))
+            assert not got.status.any(), (b, list(got.status))
+            assert np.array_equal(got.blob_off, want.blob_off)
+            bad = [c for c in range(batch.n_chains) if got.blob(c) != want.blob(c)]
+            assert not bad, (b, bad)
+            _assert_decoded_close(dec, H.oracle_decode_batch(want))
+        finally:
+            engine.set_opts(anchor_threshold=25)
+
+
 # ------------------------------------------------------------------------------ full-size config 2
 
 
@@ -236,3 +283,80 @@ def test_config2_10k_chains_350(engine):
                                                           dec.bfactor, batch.xyz, batch.titles, batch.meta))
     assert rb <= 0.1, rb  # north-star ceiling; typical 0.03-0.05 at -b 25
     print(f"config2: decode vs oracle bb_rmsd={bb:.2e} all={allr:.2e} max={mx:.2e}; round trip bb={rb:.3f} all={ra:.3f}")
+
+
+# ------------------------------------------------------------------------------ full-size config 3
+
+
+def test_config3_542k_chain_db_decode(engine):
+    """BASELINE.json configs[2]: a 542 378-chain (afdb_swissprot_v4-scale) FCZ database decoded in ONE call on one
+    GPU.  The database is 4 000 mixed-length chains (50..2000 residues, config 5's distribution) encoded by the
+    engine -- bytes checked against the oracle -- and replicated on the device.  Checks: every chain decodes with
+    status 0 and the planned sizes; every replica is bit-identical to the first (decode is deterministic and
+    independent of a chain's position in the batch); the first replica matches the oracle's decode on every
+    40th chain within the BASELINE.md tolerances."""
+    import torch
+
+    from foldcomp_b200.engine import DeviceBlobBatch, DeviceChainBatch
+
+    N_DB, N_BASE = 542378, 4000
+    engine.set_opts(anchor_threshold=25)
+    rng = np.random.default_rng(3)
+    lens = synth.mixed_lengths(rng, N_BASE)
+    base = synth.generate(N_BASE, lens, seed=303)
+    blobs = engine.encode_host(base)
+    assert not blobs.status.any()
+    sample = list(range(0, N_BASE, 40))
+    want = H.oracle_encode_batch(base.select(sample), 25)
+    for i, c in enumerate(sample):
+        assert blobs.blob(c) == want.blob(i), c
+    dev = torch.device("cuda:0")
+    total = int(blobs.blob_off[-1])
+    reps = (N_DB + N_BASE - 1) // N_BASE
+    off1 = torch.from_numpy(blobs.blob_off[:-1].astype(np.int64)).to(dev)
+    off = (off1[None, :] + total * torch.arange(reps, device=dev, dtype=torch.int64)[:, None]).reshape(-1)[:N_DB]
+    last = N_DB - (reps - 1) * N_BASE  # chains in the final, partial replica
+    end = total * (reps - 1) + int(blobs.blob_off[last])
+    dblob = DeviceBlobBatch(N_DB, 16, dev)
+    dblob.blob_off = torch.cat([off, torch.tensor([end], device=dev, dtype=torch.int64)])
+    dblob.bytes = torch.from_numpy(blobs.bytes[:total]).to(dev).repeat(reps)
+    n_res = int(base.n_res) * (reps - 1) + int(base.res_off[last])
+    n_atoms = int(base.n_atoms) * (reps - 1) + int(base.atom_off[last])
+    n_title = len(base.titles) * (reps - 1) + int(base.title_off[last])
+    dout = DeviceChainBatch(N_DB, n_res, n_atoms, n_title, dev)
+    torch.cuda.synchronize()
+    sizes = engine.decode_plan_device(dblob, dout)
+    assert (sizes.n_res, sizes.n_atoms, sizes.n_title_bytes) == (n_res, n_atoms, n_title)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    engine.sync()
+    s = torch.cuda.current_stream()
+    ev0.record(s)
+    torch.cuda.synchronize()
+    engine.decode_device(dblob, dout)
+    engine.sync()
+    ev1.record(s)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    assert int(dout.status.count_nonzero().item()) == 0
+    # replicas identical to the first one (device-side comparison: the output is ~19 GB)
+    A1, R1 = int(base.n_atoms), int(base.n_res)
+    first_xyz, first_bf, first_rt = dout.xyz[:A1], dout.bfactor[:R1], dout.res_type[:R1]
+    for k in range(1, reps):
+        na = A1 if k < reps - 1 else int(base.atom_off[last])
+        nr = R1 if k < reps - 1 else int(base.res_off[last])
+        assert torch.equal(dout.xyz[k * A1 : k * A1 + na], first_xyz[:na]), k
+        assert torch.equal(dout.bfactor[k * R1 : k * R1 + nr], first_bf[:nr]), k
+        assert torch.equal(dout.res_type[k * R1 : k * R1 + nr], first_rt[:nr]), k
+    # first replica against the oracle on every 100th chain, and against the original coordinates on all
+    got_xyz = first_xyz.cpu().numpy()
+    ref = H.oracle_decode_batch(want)
+    for i, c in enumerate(sample):
+        a0, a1 = int(base.atom_off[c]), int(base.atom_off[c + 1])
+        r = ref.chain(i)
+        bbm = H.backbone_mask(r.res_type)
+        g = got_xyz[a0:a1]
+        assert H.rmsd(g[bbm], r.xyz[bbm]) <= TOL_BB_RMSD and H.max_dev(g, r.xyz) <= TOL_MAX, c
+    rt_all = float(np.sqrt(((got_xyz - base.xyz) ** 2).sum(1).mean()))
+    assert rt_all <= 0.2, rt_all
+    print(f"config3: {N_DB} chains, {n_res} residues decoded in {ms:.1f} ms wall ({n_res / ms / 1e6:.2f} G res/s incl. launch overheads); "
+          f"all-atom round-trip RMSD vs input {rt_all:.3f} A")

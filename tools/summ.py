@@ -4,7 +4,9 @@ import json, csv, collections, os
 try:
     j = json.load(open("gpurun_out/bench.json"))
     print("value %.3f G res/s  step %.4f ms  kernels %s  e2e %.1f M res/s" % (j["value"] / 1e9, j["ms_per_step"],
-          {k: round(v["ms_per_launch"], 4) for k, v in j["roofline"]["kernels"].items()}, j["e2e"]["value"] / 1e6))
+          {k: round(v["ms_per_launch"] * v.get("launches_per_step", 1), 4) for k, v in j["roofline"]["kernels"].items()}, j["e2e"]["value"] / 1e6))
+    print("roofline", j["roofline"]["kernel"], round(j["roofline"]["frac"], 4), "e2e serial %.1f M" % (j["e2e"].get("serial_one_engine", {}).get("value", 0) / 1e6),
+          "pcie %.1f GB/s" % j["e2e"].get("pcie_gbs_each_way", 0), "cpu", j.get("cpu_baseline"))
 except Exception as ex:
     print("bench.json:", ex)
 if os.path.exists("gpurun_out/launches.csv"):
