@@ -22,6 +22,9 @@ SYMBOLS = [
     "fcz_encode_batch",
     "fcz_decode_plan",
     "fcz_decode_batch",
+    "fcz_pdb_text_plan",
+    "fcz_pdb_text_batch",
+    "fcz_extract_batch",
     "fcz_engine_sync",
     "fcz_engine_launch_count",
     "fcz_engine_set_profiling",
@@ -66,6 +69,12 @@ def load() -> C.CDLL:
     lib.fcz_decode_plan.argtypes = [C.c_void_p, P(abi.FczBlobBatch), P(abi.FczChainBatch), P(abi.FczSizes)]
     lib.fcz_decode_batch.restype = C.c_int
     lib.fcz_decode_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), P(abi.FczChainBatch)]
+    lib.fcz_pdb_text_plan.restype = C.c_int
+    lib.fcz_pdb_text_plan.argtypes = [C.c_void_p, P(abi.FczChainBatch), P(abi.FczTextBatch), P(C.c_uint64)]
+    lib.fcz_pdb_text_batch.restype = C.c_int
+    lib.fcz_pdb_text_batch.argtypes = [C.c_void_p, P(abi.FczChainBatch), P(abi.FczTextBatch)]
+    lib.fcz_extract_batch.restype = C.c_int
+    lib.fcz_extract_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), C.c_int32, C.c_int32, P(abi.FczTextBatch), P(C.c_uint64)]
     lib.fcz_engine_sync.restype = C.c_int
     lib.fcz_engine_sync.argtypes = [C.c_void_p]
     lib.fcz_engine_launch_count.restype = C.c_uint64

@@ -84,6 +84,16 @@ class FczBlobBatch(C.Structure):
     ]
 
 
+class FczTextBatch(C.Structure):
+    _fields_ = [
+        ("n_chains", C.c_uint32),
+        ("mem", C.c_int32),
+        ("text_off", C.c_void_p),
+        ("bytes", C.c_void_p),
+        ("bytes_cap", C.c_uint64),
+    ]
+
+
 class FczSizes(C.Structure):
     _fields_ = [
         ("n_res", C.c_uint64),
@@ -105,6 +115,7 @@ class FczProfile(C.Structure):
 
 
 PROF_KINDS = {"encode_span": 0, "decode_span": 1, "k_encode": 2, "k_dec_front": 3, "k_dec_stitch_t": 4, "k_dec_back": 5}
+PROF_TEXT_KINDS = {"k_pdb_plan": 6, "k_pdb_emit": 7}
 
 
 def _ptr(a: np.ndarray | None):
@@ -298,3 +309,27 @@ def encode_bound(n_chains: int, n_res: int, n_atoms: int, n_title: int, anchor_t
     """Same arithmetic as fcz_encode_bound (SURVEY.md Appendix A size formula)."""
     b = max(int(anchor_threshold), 1)
     return 97 * n_chains + 40 * (n_res // b + 2 * n_chains) + n_title + 6 * n_res + n_atoms
+
+
+@dataclass
+class HostTextBatch:
+    """Texts (PDB text per chain / extract output per blob), tightly concatenated, host memory."""
+
+    text_off: np.ndarray  # uint64 [n+1]
+    bytes: np.ndarray  # uint8 [cap]
+
+    @property
+    def n_chains(self) -> int:
+        return len(self.text_off) - 1
+
+    def text(self, c: int) -> bytes:
+        return bytes(self.bytes[int(self.text_off[c]) : int(self.text_off[c + 1])])
+
+    def as_struct(self) -> FczTextBatch:
+        s = FczTextBatch()
+        s.n_chains = self.n_chains
+        s.mem = FCZ_MEM_HOST
+        s.text_off = _ptr(self.text_off)
+        s.bytes = _ptr(self.bytes)
+        s.bytes_cap = len(self.bytes)
+        return s

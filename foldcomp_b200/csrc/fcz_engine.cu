@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "fcz_codec.h"
+#include "fcz_text.h"
 
 using namespace fcz;
 
@@ -941,6 +942,124 @@ __global__ void __launch_bounds__(256) k_plan_chunks(uint32_t n, uint32_t sub_re
     }
 }
 
+// ============================================================================================= text
+// PDB text of decoded chains (writeAtomCoordinatesToPDB, src/atom_coordinate.cpp:220-291) and the extract scans
+// (Foldcomp::extract, src/foldcomp.cpp:1260-1336).  Formatting itself is fcz_text.h (shared with the CPU model).
+//   k_pdb_plan  block per chain: residue -> first atom and residue -> first text byte (exact: over-long fields are
+//               measured), the chain's text bytes and its number of emit units;
+//   k_pdb_emit  block per unit of FCZ_PDB_UNIT_RES residues: thread per atom formats its 81-byte line into a
+//               shared-memory image that has the 16-byte phase of its destination, then 128-bit stores.
+// HBM-bound by the text written (81 B per atom against 12 B read).
+
+struct PdbArgs {
+    const uint32_t* res_off;
+    const uint64_t* atom_off;
+    const uint32_t* title_off;
+    const uint8_t* res_type;
+    const float* bfactor;
+    const float* xyz;
+    const char* titles;
+    const fcz_chain_meta* meta;
+    const TextTables* tt;
+    int32_t use_alt;
+    uint32_t n;
+    uint32_t* aoff;          // [n_res + n] workspace: chain c at res_off[c] + c
+    uint32_t* toff;          // same shape
+    uint32_t* text_bytes;    // [n] plan output
+    uint32_t* units;         // [n] plan output
+    const uint64_t* text_off;  // [n+1] scans of the two
+    const uint32_t* unit_off;
+    char* text;
+    uint32_t unit0;          // first unit of this launch (host-memory batches emit in slabs)
+};
+
+__device__ __forceinline__ PdbChain pdb_chain(const PdbArgs& a, uint32_t c) {
+    PdbChain ch;
+    const uint32_t r0 = a.res_off[c];
+    const uint64_t a0 = a.atom_off[c];
+    const uint32_t t0 = a.title_off[c];
+    ch.L = a.res_off[c + 1] - r0;
+    ch.A = (uint32_t)(a.atom_off[c + 1] - a0);
+    ch.title_len = a.title_off[c + 1] - t0;
+    ch.type = a.res_type + r0;
+    ch.bfac = a.bfactor + r0;
+    ch.X = a.xyz + 3u * a0;
+    ch.title = a.titles + t0;
+    ch.meta = a.meta + c;
+    ch.use_alt = a.use_alt;
+    ch.aoff = a.aoff + r0 + c;
+    ch.toff = a.toff + r0 + c;
+    return ch;
+}
+
+__global__ void __launch_bounds__(128) k_pdb_plan(PdbArgs a) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t scratch;
+    const uint32_t c = blockIdx.x;
+    DevCtx cx = block_ctx(wsum);
+    const PdbChain ch = pdb_chain(a, c);
+    const uint32_t total = pdb_plan_chain(cx, a.tt, ch, &scratch);
+    if (threadIdx.x == 0) {
+        a.text_bytes[c] = total;
+        a.units[c] = (ch.L + FCZ_PDB_UNIT_RES - 1u) / FCZ_PDB_UNIT_RES;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pdb_emit(PdbArgs a) {
+    __shared__ __align__(16) char stage[FCZ_PDB_STAGE_BYTES];
+    const uint32_t u = a.unit0 + blockIdx.x;
+    // chain of this unit: last c with unit_off[c] <= u (every thread searches; the array is L2-resident)
+    uint32_t lo = 0, hi = a.n;
+    while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a.unit_off + mid) <= u) lo = mid; else hi = mid;
+    }
+    const uint32_t c = lo;
+    DevCtx cx = block_ctx(nullptr);
+    const PdbChain ch = pdb_chain(a, c);
+    const uint32_t r_lo = (u - a.unit_off[c]) * FCZ_PDB_UNIT_RES;
+    const uint32_t r_hi = r_lo + FCZ_PDB_UNIT_RES < ch.L ? r_lo + FCZ_PDB_UNIT_RES : ch.L;
+    pdb_emit_unit(cx, a.tt, ch, r_lo, r_hi, a.text + a.text_off[c], stage);
+}
+
+struct ExtractArgs {
+    const uint64_t* blob_off;
+    const uint8_t* bytes;
+    const TextTables* tt;
+    int32_t type;
+    uint32_t digits;
+    uint32_t n;
+    uint32_t* text_bytes;      // [n] plan output
+    int32_t* status;           // [n]
+    const uint64_t* text_off;  // [n+1]
+    char* text;
+};
+// thread per blob: header check (Foldcomp::read, src/foldcomp.cpp:904-924) and output size
+__global__ void __launch_bounds__(256) k_extract_plan(ExtractArgs a) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n) return;
+    const uint8_t* blob = a.bytes + a.blob_off[c];
+    const uint64_t len = a.blob_off[c + 1] - a.blob_off[c];
+    int st = FCZ_OK;
+    uint32_t out = 0;
+    if (len < HDR_BYTES || blob[0] != 'F' || blob[1] != 'C' || blob[2] != 'M' || blob[3] != 'P') st = FCZ_E_MAGIC;
+    else {
+        const Layout y = make_layout(get_u16(blob + OFF_NRES), get_u32(blob + OFF_NSC), get_u32(blob + OFF_LENTITLE), blob[OFF_NANCHOR]);
+        if ((uint64_t)get_u32(blob + OFF_LENTITLE) > len || (uint64_t)get_u32(blob + OFF_NSC) > len || (uint64_t)y.size > len) st = FCZ_E_TRUNCATED;
+        else out = extract_len(y.L, a.type, a.digits);
+    }
+    a.text_bytes[c] = out;
+    a.status[c] = st;
+}
+__global__ void __launch_bounds__(128) k_extract(ExtractArgs a) {
+    const uint32_t c = blockIdx.x;
+    if (a.status[c] != FCZ_OK) return;
+    const uint8_t* blob = a.bytes + a.blob_off[c];
+    const Layout y = make_layout(get_u16(blob + OFF_NRES), get_u32(blob + OFF_NSC), get_u32(blob + OFF_LENTITLE), blob[OFF_NANCHOR]);
+    DevCtx cx = block_ctx(nullptr);
+    extract_chain(cx, a.tt, blob, y, a.type, a.digits, a.text + a.text_off[c]);
+}
+
 // ============================================================================================ scans
 // Exclusive scans of up to three per-chain u32 arrays into offsets (u32/u64), tile = 2048 chains.
 
@@ -1045,6 +1164,11 @@ struct fcz_engine {
     TierCfg enc_tier[FCZ_NTIER];
     int enc_occ[FCZ_NTIER];
     Tables* d_tables = nullptr;
+    TextTables* d_text_tables = nullptr;
+    // text emitter (fcz_pdb_text_plan -> fcz_pdb_text_batch)
+    DevBuf ws_aoff, ws_toff, d_unit_off, d_text_off, d_text;
+    struct PdbPlan { uint32_t n = 0; uint64_t total_bytes = 0; uint32_t total_units = 0; bool valid = false; } pdb;
+    std::vector<uint32_t> h_unit_off;
     // plan scratch
     DevBuf v0, v1, v2, v3, status, tier_list, partial;
     uint32_t* d_counters = nullptr;  // [FCZ_NTIER] counts, [FCZ_NTIER] tickets
@@ -1174,6 +1298,10 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     }
     Tables h;
     build_tables(&h);
+    TextTables ht;
+    build_text_tables(&ht);
+    ok &= cudaMalloc(&e->d_text_tables, sizeof(TextTables)) == cudaSuccess;
+    if (ok) ok &= cudaMemcpy(e->d_text_tables, &ht, sizeof(TextTables), cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMalloc(&e->d_tables, sizeof(Tables)) == cudaSuccess;
     ok &= cudaMalloc(&e->d_counters, sizeof(uint32_t) * (2 * FCZ_NTIER + 2)) == cudaSuccess;
     ok &= cudaMalloc(&e->d_totals, sizeof(uint64_t) * 4) == cudaSuccess;
@@ -1197,11 +1325,12 @@ void fcz_engine_destroy(fcz_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->v3, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
-                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets, &e->enc_gws,
+                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets, &e->enc_gws, &e->ws_aoff, &e->ws_toff, &e->d_unit_off, &e->d_text_off, &e->d_text,
                       &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (e->d_tables) cudaFree(e->d_tables);
+    if (e->d_text_tables) cudaFree(e->d_text_tables);
     if (e->d_counters) cudaFree(e->d_counters);
     if (e->d_totals) cudaFree(e->d_totals);
     if (e->h_counters) cudaFreeHost(e->h_counters);
@@ -1642,6 +1771,202 @@ extern "C" int fcz_encode_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_bl
     uint64_t total = 0;
     if (in->mem == FCZ_MEM_DEVICE) return encode_device(e, in, out, &total);
     return encode_host(e, in, out);
+}
+
+// --------------------------------------------------------------------------------------------- text
+
+// arrays of a chain batch on the device: the batch itself (device memory) or the engine's staging copy of a host batch
+struct DevChains {
+    const uint32_t* res_off; const uint64_t* atom_off; const uint32_t* title_off;
+    const uint8_t* res_type; const float* bfactor; const float* xyz; const char* titles; const fcz_chain_meta* meta;
+};
+
+static int upload_chains(fcz_engine* e, const fcz_chain_batch* in, DevChains* d) {
+    const uint32_t n = in->n_chains;
+    if (in->mem == FCZ_MEM_DEVICE) {
+        d->res_off = in->res_off; d->atom_off = in->atom_off; d->title_off = in->title_off; d->res_type = in->res_type;
+        d->bfactor = in->bfactor; d->xyz = in->xyz; d->titles = in->titles; d->meta = in->meta;
+        return FCZ_OK;
+    }
+    int rc;
+    const uint64_t n_res = in->res_off[n], n_atoms = in->atom_off[n], n_title = in->title_off[n];
+    H2D(e->d_res_off, in->res_off, 4ull * (n + 1));
+    H2D(e->d_atom_off, in->atom_off, 8ull * (n + 1));
+    H2D(e->d_title_off, in->title_off, 4ull * (n + 1));
+    H2D(e->d_res_type, in->res_type, n_res);
+    H2D(e->d_bfactor, in->bfactor, 4ull * n_res);
+    H2D(e->d_xyz, in->xyz, 12ull * n_atoms);
+    H2D(e->d_titles, in->titles, n_title);
+    H2D(e->d_meta, in->meta, sizeof(fcz_chain_meta) * (uint64_t)n);
+    d->res_off = (uint32_t*)e->d_res_off.p; d->atom_off = (uint64_t*)e->d_atom_off.p; d->title_off = (uint32_t*)e->d_title_off.p;
+    d->res_type = (uint8_t*)e->d_res_type.p; d->bfactor = (float*)e->d_bfactor.p; d->xyz = (float*)e->d_xyz.p;
+    d->titles = (char*)e->d_titles.p; d->meta = (fcz_chain_meta*)e->d_meta.p;
+    return FCZ_OK;
+}
+
+static void pdb_args(fcz_engine* e, const DevChains& d, uint32_t n, PdbArgs* a) {
+    memset(a, 0, sizeof *a);
+    a->res_off = d.res_off; a->atom_off = d.atom_off; a->title_off = d.title_off; a->res_type = d.res_type; a->bfactor = d.bfactor;
+    a->xyz = d.xyz; a->titles = d.titles; a->meta = d.meta;
+    a->tt = e->d_text_tables; a->use_alt = e->opts.use_alt_atom_order; a->n = n;
+    a->aoff = (uint32_t*)e->ws_aoff.p; a->toff = (uint32_t*)e->ws_toff.p;
+    a->text_bytes = (uint32_t*)e->v0.p; a->units = (uint32_t*)e->v1.p;
+    a->unit_off = (uint32_t*)e->d_unit_off.p;
+}
+
+extern "C" int fcz_pdb_text_plan(fcz_engine* e, const fcz_chain_batch* in, fcz_text_batch* out, uint64_t* total_bytes) {
+    if (!e || !in || !out || !total_bytes) return FCZ_E_ARG;
+    if (in->mem != out->mem) return fail(e, FCZ_E_ARG, "input and output batches must live in the same memory space");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    out->n_chains = n;
+    e->pdb.valid = false;
+    int rc;
+    DevChains d;
+    if ((rc = upload_chains(e, in, &d))) return rc;
+    const uint64_t n_res = in->mem == FCZ_MEM_HOST ? in->res_off[n] : in->res_cap;
+    if ((rc = plan_buffers(e, n))) return rc;
+    if ((rc = ensure(e, e->ws_aoff, 4ull * (n_res + n + 1)))) return rc;
+    if ((rc = ensure(e, e->ws_toff, 4ull * (n_res + n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_unit_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_text_off, 8ull * (n + 1)))) return rc;
+    PdbArgs a;
+    pdb_args(e, d, n, &a);
+    if (n) {
+        ProfSpan pk(e, FCZ_PROF_K_PDB_PLAN);
+        k_pdb_plan<<<n, 128, 0, e->stream>>>(a);
+        e->launches++;
+    }
+    uint64_t* d_text_off = in->mem == FCZ_MEM_DEVICE ? out->text_off : (uint64_t*)e->d_text_off.p;
+    ScanArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.n = n; sa.narr = 2;
+    sa.in[0] = a.text_bytes; sa.out[0] = d_text_off; sa.out64[0] = 1;
+    sa.in[1] = a.units; sa.out[1] = e->d_unit_off.p; sa.out64[1] = 0;
+    if ((rc = run_scan(e, sa))) return rc;
+    if (in->mem == FCZ_MEM_HOST) {
+        e->h_unit_off.resize((size_t)n + 1);
+        CK(cudaMemcpyAsync(out->text_off, d_text_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_unit_off.data(), e->d_unit_off.p, 4ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+    }
+    if ((rc = fetch_plan(e))) return rc;
+    e->pdb.n = n; e->pdb.total_bytes = e->h_totals[0]; e->pdb.total_units = (uint32_t)e->h_totals[1]; e->pdb.valid = true;
+    *total_bytes = e->pdb.total_bytes;
+    return FCZ_OK;
+}
+
+extern "C" int fcz_pdb_text_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_text_batch* out) {
+    if (!e || !in || !out) return FCZ_E_ARG;
+    if (in->mem != out->mem) return fail(e, FCZ_E_ARG, "input and output batches must live in the same memory space");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    if (!e->pdb.valid || e->pdb.n != n) return fail(e, FCZ_E_ARG, "fcz_pdb_text_batch needs a preceding fcz_pdb_text_plan on the same batch");
+    if (e->pdb.total_bytes > out->bytes_cap)
+        return fail(e, FCZ_E_CAPACITY, "text needs %llu bytes, capacity %llu", (unsigned long long)e->pdb.total_bytes, (unsigned long long)out->bytes_cap);
+    e->pdb.valid = false;
+    int rc;
+    DevChains d;
+    if (in->mem == FCZ_MEM_DEVICE) {
+        if ((rc = upload_chains(e, in, &d))) return rc;
+    } else {  // still resident in the staging buffers since the plan call
+        d.res_off = (uint32_t*)e->d_res_off.p; d.atom_off = (uint64_t*)e->d_atom_off.p; d.title_off = (uint32_t*)e->d_title_off.p;
+        d.res_type = (uint8_t*)e->d_res_type.p; d.bfactor = (float*)e->d_bfactor.p; d.xyz = (float*)e->d_xyz.p;
+        d.titles = (char*)e->d_titles.p; d.meta = (fcz_chain_meta*)e->d_meta.p;
+    }
+    PdbArgs a;
+    pdb_args(e, d, n, &a);
+    if (in->mem == FCZ_MEM_DEVICE) {
+        a.text_off = out->text_off; a.text = out->bytes; a.unit0 = 0;
+        if (e->pdb.total_units) {
+            ProfSpan pk(e, FCZ_PROF_K_PDB_EMIT);
+            k_pdb_emit<<<e->pdb.total_units, 128, 0, e->stream>>>(a);
+            e->launches++;
+        }
+        CK(cudaGetLastError());
+        return FCZ_OK;
+    }
+    // host memory: emit in slabs of ~64 MB of text so that the D2H copy of slab k overlaps the kernel of slab k+1
+    if ((rc = ensure(e, e->d_text, e->pdb.total_bytes + 64))) return rc;
+    a.text_off = (uint64_t*)e->d_text_off.p; a.text = (char*)e->d_text.p;
+    size_t evi = 0;
+    cudaEvent_t ev0 = pool_event(e, evi++);
+    CK(cudaEventRecord(ev0, e->stream));
+    CK(cudaStreamWaitEvent(e->s_out, ev0, 0));
+    uint32_t c0 = 0;
+    while (c0 < n) {
+        uint32_t c1 = c0;
+        while (c1 < n && out->text_off[c1] - out->text_off[c0] < (64ull << 20)) c1++;
+        const uint32_t u0 = e->h_unit_off[c0], u1 = e->h_unit_off[c1];
+        if (u1 > u0) {
+            a.unit0 = u0;
+            ProfSpan pk(e, FCZ_PROF_K_PDB_EMIT);
+            k_pdb_emit<<<u1 - u0, 128, 0, e->stream>>>(a);
+            e->launches++;
+        }
+        cudaEvent_t ev = pool_event(e, evi++);
+        CK(cudaEventRecord(ev, e->stream));
+        CK(cudaStreamWaitEvent(e->s_out, ev, 0));
+        const uint64_t b0 = out->text_off[c0], b1 = out->text_off[c1];
+        COPY(out->bytes + b0, (char*)e->d_text.p + b0, b1 - b0, cudaMemcpyDeviceToHost, e->s_out);
+        c0 = c1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->s_out));
+    CK(cudaStreamSynchronize(e->stream));
+    return FCZ_OK;
+}
+
+extern "C" int fcz_extract_batch(fcz_engine* e, const fcz_blob_batch* in, int32_t type, int32_t digits, fcz_text_batch* out, uint64_t* total_bytes) {
+    if (!e || !in || !out || !total_bytes) return FCZ_E_ARG;
+    if (type != 0 && type != 1) return fail(e, FCZ_E_ARG, "extract type must be 0 (plddt) or 1 (sequence)");
+    if (in->mem != out->mem) return fail(e, FCZ_E_ARG, "input and output batches must live in the same memory space");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    out->n_chains = n;
+    int rc;
+    if (digits < 1) digits = 1; else if (digits > 4) digits = 4;  // src/foldcomp.cpp:1265-1269
+    if ((rc = plan_buffers(e, n))) return rc;
+    ExtractArgs a;
+    memset(&a, 0, sizeof a);
+    const bool host = in->mem == FCZ_MEM_HOST;
+    if (host) {
+        const uint64_t nb = in->blob_off[n];
+        H2D(e->d_blob_off, in->blob_off, 8ull * (n + 1));
+        H2D(e->d_bytes, in->bytes, nb);
+        if ((rc = ensure(e, e->d_text_off, 8ull * (n + 1)))) return rc;
+        a.blob_off = (uint64_t*)e->d_blob_off.p; a.bytes = (uint8_t*)e->d_bytes.p;
+    } else {
+        a.blob_off = in->blob_off; a.bytes = in->bytes;
+    }
+    a.tt = e->d_text_tables; a.type = type; a.digits = (uint32_t)digits; a.n = n;
+    a.text_bytes = (uint32_t*)e->v0.p; a.status = (int32_t*)e->status.p;
+    uint64_t* d_text_off = host ? (uint64_t*)e->d_text_off.p : out->text_off;
+    if (n) {
+        k_extract_plan<<<(n + 255) / 256, 256, 0, e->stream>>>(a);
+        e->launches++;
+    }
+    ScanArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.n = n; sa.narr = 1;
+    sa.in[0] = a.text_bytes; sa.out[0] = d_text_off; sa.out64[0] = 1;
+    if ((rc = run_scan(e, sa))) return rc;
+    if ((rc = fetch_plan(e))) return rc;
+    const uint64_t total = e->h_totals[0];
+    *total_bytes = total;
+    if (total > out->bytes_cap) return fail(e, FCZ_E_CAPACITY, "extract needs %llu bytes, capacity %llu", (unsigned long long)total, (unsigned long long)out->bytes_cap);
+    if (host && (rc = ensure(e, e->d_text, total + 64))) return rc;
+    a.text_off = d_text_off; a.text = host ? (char*)e->d_text.p : out->bytes;
+    if (n) {
+        k_extract<<<n, 128, 0, e->stream>>>(a);
+        e->launches++;
+    }
+    CK(cudaGetLastError());
+    if (host) {
+        CK(cudaMemcpyAsync(out->text_off, d_text_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+        if (total) CK(cudaMemcpyAsync(out->bytes, e->d_text.p, total, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return FCZ_OK;
 }
 
 // ------------------------------------------------------------------------------------------- decode

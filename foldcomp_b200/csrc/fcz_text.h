@@ -15,7 +15,9 @@
 
 #include <stdint.h>
 
+#include "../../include/fcz_engine.h"
 #include "fcz_format.h"
+#include "fcz_math.h"
 #include "fcz_tables.h"
 
 namespace fcz {
@@ -221,6 +223,156 @@ FCZ_HD uint32_t put_title_lines(char* dst, const char* title, uint32_t T) {
     return (uint32_t)(p - dst);
 }
 
+// ------------------------------------------------------------------ chain-level plan and emit (any context)
+// Written against the same abstract execution context as fcz_codec.h (tid, nthr, sync(), excl_scan()): the CUDA
+// kernels instantiate them with a CTA, tests/emu/ with one host thread.
+
+#define FCZ_PDB_UNIT_RES 16u                                      // residues per emit unit (one CTA)
+#define FCZ_PDB_UNIT_ATOMS (FCZ_PDB_UNIT_RES * FCZ_MAX_ATOMS)     // 224 atoms at most
+#define FCZ_PDB_STAGE_BYTES (FCZ_PDB_UNIT_ATOMS * FCZ_PDB_LINE + 32u)
+
+struct PdbChain {
+    uint32_t L, A, title_len;
+    const uint8_t* type;   // [L] residue codes
+    const float* bfac;     // [L]
+    const float* X;        // [3A] atoms in the decoder's output order
+    const char* title;
+    const fcz_chain_meta* meta;
+    int use_alt;           // atoms are in the -a order: names follow TextTables::alt
+    uint32_t* aoff;        // [L+1] first atom of each residue, relative to the chain
+    uint32_t* toff;        // [L+1] text offset of each residue's first line, relative to the chain's text;
+                           //       toff[L] = where the OXT and TER lines start
+};
+
+FCZ_HD AtomRec pdb_atom_rec(const TextTables* tt, const PdbChain& ch, uint32_t r, uint32_t k, uint32_t atom) {
+    const unsigned code = ch.type[r];
+    AtomRec a;
+    a.serial = (uint32_t)ch.meta->idx_atom + atom;
+    a.resnum = (uint32_t)ch.meta->idx_residue + r;
+    a.name = tt->atom[code][ch.use_alt ? tt->alt[code][k] : k];
+    a.res3 = tt->name3[code];
+    a.chain = ch.meta->chain;
+    a.x = ch.X[3u * atom]; a.y = ch.X[3u * atom + 1u]; a.z = ch.X[3u * atom + 2u];
+    a.b = ch.bfac[r];
+    return a;
+}
+// the OXT record (Foldcomp::read, src/foldcomp.cpp:958-961: residue_index = nResidue) -- also the atom TER refers to
+FCZ_HD AtomRec pdb_oxt_rec(const TextTables* tt, const PdbChain& ch) {
+    AtomRec a;
+    a.serial = (uint32_t)ch.meta->idx_atom + ch.A;
+    a.resnum = ch.L;
+    a.name = (uint32_t)'O' | (uint32_t)'X' << 8 | (uint32_t)'T' << 16;
+    a.res3 = tt->name3[ch.type[ch.L - 1u]];
+    a.chain = ch.meta->chain;
+    a.x = ch.meta->oxt[0]; a.y = ch.meta->oxt[1]; a.z = ch.meta->oxt[2];
+    a.b = ch.bfac[ch.L - 1u];
+    return a;
+}
+FCZ_HD AtomRec pdb_last_rec(const TextTables* tt, const PdbChain& ch) {
+    if (ch.meta->has_oxt) return pdb_oxt_rec(tt, ch);
+    const uint32_t r = ch.L - 1u;
+    return pdb_atom_rec(tt, ch, r, ch.A - 1u - ch.aoff[r], ch.A - 1u);
+}
+
+// Plan: fills ch.aoff / ch.toff; returns the chain's text bytes (same value in every thread).
+// `scratch` is one word visible to all threads of the context.
+template <class Ctx>
+FCZ_HD uint32_t pdb_plan_chain(Ctx& cx, const TextTables* tt, const PdbChain& ch, uint32_t* scratch) {
+    const uint32_t L = ch.L;
+    if (L == 0u) return 0u;
+    const uint32_t chunk = (L + cx.nthr - 1) / cx.nthr;
+    uint32_t r0 = cx.tid * chunk; if (r0 > L) r0 = L;
+    uint32_t r1 = r0 + chunk; if (r1 > L) r1 = L;
+    uint32_t sum = 0;
+    for (uint32_t r = r0; r < r1; r++) sum += tt->natoms[ch.type[r]];
+    uint32_t base = cx.excl_scan(sum);
+    const uint32_t a_first = base;
+    for (uint32_t r = r0; r < r1; r++) { ch.aoff[r] = base; base += tt->natoms[ch.type[r]]; }
+    if (r1 == L) ch.aoff[L] = base;
+    cx.sync();
+    // bytes beyond 81 per residue (zero for ordinary coordinates)
+    uint32_t extra = 0, atom = a_first;
+    for (uint32_t r = r0; r < r1; r++) {
+        const uint32_t n = tt->natoms[ch.type[r]];
+        for (uint32_t k = 0; k < n; k++, atom++) extra += atom_line_extra(pdb_atom_rec(tt, ch, r, k, atom));
+    }
+    uint32_t ebase = cx.excl_scan(extra);
+    const uint32_t head = title_lines_len(ch.title_len);
+    atom = a_first;
+    for (uint32_t r = r0; r < r1; r++) {
+        ch.toff[r] = head + FCZ_PDB_LINE * atom + ebase;
+        const uint32_t n = tt->natoms[ch.type[r]];
+        for (uint32_t k = 0; k < n; k++, atom++) ebase += atom_line_extra(pdb_atom_rec(tt, ch, r, k, atom));
+    }
+    if (r1 == L) {
+        const uint32_t t_tail = head + FCZ_PDB_LINE * atom + ebase;
+        ch.toff[L] = t_tail;
+        uint32_t total = t_tail;
+        if (ch.meta->has_oxt) { const AtomRec o = pdb_oxt_rec(tt, ch); total += FCZ_PDB_LINE + atom_line_extra(o); }
+        total += ter_line_len(pdb_last_rec(tt, ch));
+        *scratch = total;
+    }
+    cx.sync();
+    const uint32_t total = *scratch;
+    cx.sync();
+    return total;
+}
+
+struct alignas(16) V16 { uint32_t w[4]; };
+// bytes from `src` to `dst` where both have the same 16-byte phase: 128-bit copies for the aligned interior
+template <class Ctx>
+FCZ_HD void copy_same_phase(Ctx& cx, char* dst, const char* src, uint32_t bytes) {
+    const uint32_t mis = (uint32_t)((uintptr_t)dst & 15u);
+    const uint32_t head = (16u - mis) & 15u;
+    const uint32_t hb = head < bytes ? head : bytes;
+    uint32_t body = 0;
+    if (bytes > head) body = (bytes - head) & ~15u;
+    for (uint32_t i = cx.tid; i < hb; i += cx.nthr) dst[i] = src[i];
+    const V16* s4 = reinterpret_cast<const V16*>(src + head);
+    V16* d4 = reinterpret_cast<V16*>(dst + head);
+    for (uint32_t i = cx.tid; i < (body >> 4); i += cx.nthr) d4[i] = s4[i];
+    for (uint32_t i = hb + body + cx.tid; i < bytes; i += cx.nthr) dst[i] = src[i];
+}
+
+// Emit the lines of residues [r_lo, r_hi) of a planned chain into its text (dst = first byte of the chain's
+// text); the first unit also writes the TITLE lines, the last one the OXT and TER lines.  `stage` is a buffer of
+// FCZ_PDB_STAGE_BYTES (16-byte aligned; shared memory on the device) through which uniform units -- every line
+// 81 bytes -- leave as 128-bit copies; a unit with an over-long line writes straight to dst.
+template <class Ctx>
+FCZ_HD void pdb_emit_unit(Ctx& cx, const TextTables* tt, const PdbChain& ch, uint32_t r_lo, uint32_t r_hi, char* dst, char* stage) {
+    const uint32_t a_lo = ch.aoff[r_lo], a_hi = ch.aoff[r_hi];
+    const uint32_t t_lo = ch.toff[r_lo], t_hi = ch.toff[r_hi];
+    const uint32_t n = a_hi - a_lo;
+    const bool uniform = (t_hi - t_lo) == FCZ_PDB_LINE * n;
+    char* g = dst + t_lo;
+    char* s = stage + ((uintptr_t)g & 15u);
+    for (uint32_t i = cx.tid; i < n; i += cx.nthr) {
+        const uint32_t atom = a_lo + i;
+        uint32_t r = r_lo;
+        while (r + 1u < r_hi && ch.aoff[r + 1u] <= atom) r++;
+        const uint32_t k = atom - ch.aoff[r];
+        const AtomRec a = pdb_atom_rec(tt, ch, r, k, atom);
+        if (uniform) {
+            put_atom_line(s + FCZ_PDB_LINE * i, a);
+        } else {
+            uint32_t off = ch.toff[r];
+            for (uint32_t j = 0; j < k; j++) off += FCZ_PDB_LINE + atom_line_extra(pdb_atom_rec(tt, ch, r, j, ch.aoff[r] + j));
+            put_atom_line(dst + off, a);
+        }
+    }
+    if (r_lo == 0u && cx.tid == 0) put_title_lines(dst, ch.title, ch.title_len);
+    if (r_hi == ch.L && cx.tid == cx.nthr - 1) {
+        char* p = dst + ch.toff[ch.L];
+        if (ch.meta->has_oxt) p += put_atom_line(p, pdb_oxt_rec(tt, ch));
+        put_ter_line(p, pdb_last_rec(tt, ch));
+    }
+    if (uniform) {
+        cx.sync();
+        copy_same_phase(cx, g, s, FCZ_PDB_LINE * n);
+        cx.sync();
+    }
+}
+
 // ---- Foldcomp::extract (src/foldcomp.cpp:1260-1336)
 // type 0: pLDDT (the continuised B-factor bytes) as `digits` characters per residue, comma separated when
 // digits > 1; type 1: the one-letter sequence.
@@ -252,6 +404,27 @@ FCZ_HD uint32_t put_plddt(char* dst, float v, uint32_t digits, bool zero_to_one)
     }
     if (digits == 4u) dst[n++] = (char)((int)(clamped * 100.0f) % 10) + '0';
     return n;
+}
+
+// One blob's extract output (thread per residue).  `y` is the blob's layout; dst receives extract_len() bytes.
+template <class Ctx>
+FCZ_HD void extract_chain(Ctx& cx, const TextTables* tt, const uint8_t* blob, const Layout& y, int type, uint32_t digits, char* dst) {
+    const uint32_t L = y.L;
+    if (type == 1) {
+        for (uint32_t r = cx.tid; r < L; r += cx.nthr) dst[r] = (char)tt->name1[blob[y.o_rec + 8u * r] >> 3];
+        return;
+    }
+    const float tmin = get_f32(blob + y.o_temp), tcont = get_f32(blob + y.o_temp + 4u);
+    // src/foldcomp.cpp:1290-1294: cont_f * (pow(2, 8) - 1) + min evaluated in double, compared as float
+    const float maxval = (float)((double)tcont * 255.0 + (double)tmin);
+    const bool z1 = maxval <= 1.0f && digits <= 2u;
+    const uint32_t stride = extract_plddt_stride(digits);
+    for (uint32_t i = cx.tid; i < L; i += cx.nthr) {
+        const float v = continuize((unsigned)blob[y.o_temp + 8u + i], tmin, tcont);
+        char* p = dst + i * stride;
+        const uint32_t n = put_plddt(p, v, digits, z1);
+        if (digits > 1u && i != L - 1u) p[n] = ',';
+    }
 }
 
 }  // namespace fcz

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import abi
 from ._lib import load
-from .abi import FczBlobBatch, FczChainBatch, FczOpts, FczSizes, HostBlobBatch, HostChainBatch
+from .abi import FczBlobBatch, FczChainBatch, FczOpts, FczSizes, FczTextBatch, HostBlobBatch, HostChainBatch, HostTextBatch
 
 
 class FczError(RuntimeError):
@@ -144,6 +144,29 @@ class DeviceBlobBatch:
         return s
 
 
+class DeviceTextBatch:
+    """Texts on one GPU: text_off (int64 holding uint64) and a byte buffer."""
+
+    def __init__(self, n_chains: int, cap: int, device):
+        torch = _torch()
+        self.n_chains = n_chains
+        self.text_off = torch.zeros(n_chains + 1, dtype=torch.int64, device=device)
+        self.bytes = torch.zeros(max(cap, 16), dtype=torch.uint8, device=device)
+
+    def as_struct(self) -> FczTextBatch:
+        s = FczTextBatch()
+        s.n_chains = self.n_chains
+        s.mem = abi.FCZ_MEM_DEVICE
+        s.text_off = self.text_off.data_ptr()
+        s.bytes = self.bytes.data_ptr()
+        s.bytes_cap = self.bytes.numel()
+        return s
+
+    def to_host(self) -> HostTextBatch:
+        off = self.text_off.cpu().numpy().view(np.uint64).copy()
+        return HostTextBatch(off, self.bytes[: int(off[-1])].cpu().numpy().copy())
+
+
 class Engine:
     """One engine per GPU (fcz_engine_create).  `stream` is a torch.cuda.Stream or None (engine-owned)."""
 
@@ -253,3 +276,36 @@ class Engine:
         if not with_titles:
             so.titles = None
         self._check(self.lib.fcz_decode_batch(self.h, C.byref(sin), C.byref(so)))
+
+    # ------------------------------------------------------------------ text
+    def pdb_text_host(self, chains: HostChainBatch) -> HostTextBatch:
+        """PDB text of every chain of a decoded host batch (writeAtomCoordinatesToPDB, src/atom_coordinate.cpp:220-291)."""
+        n = chains.n_chains
+        out = HostTextBatch(np.zeros(n + 1, np.uint64), np.zeros(0, np.uint8))
+        sin, so = chains.as_struct(), out.as_struct()
+        total = C.c_uint64()
+        self._check(self.lib.fcz_pdb_text_plan(self.h, C.byref(sin), C.byref(so), C.byref(total)))
+        out.bytes = np.zeros(total.value, np.uint8)
+        so = out.as_struct()
+        self._check(self.lib.fcz_pdb_text_batch(self.h, C.byref(sin), C.byref(so)))
+        return out
+
+    def pdb_text_plan_device(self, chains: DeviceChainBatch, out: "DeviceTextBatch") -> int:
+        sin, so = chains.as_struct(), out.as_struct()
+        total = C.c_uint64()
+        self._check(self.lib.fcz_pdb_text_plan(self.h, C.byref(sin), C.byref(so), C.byref(total)))
+        return int(total.value)
+
+    def pdb_text_device(self, chains: DeviceChainBatch, out: "DeviceTextBatch") -> None:
+        sin, so = chains.as_struct(), out.as_struct()
+        self._check(self.lib.fcz_pdb_text_batch(self.h, C.byref(sin), C.byref(so)))
+
+    def extract_host(self, blobs: HostBlobBatch, type_: int, digits: int = 2) -> HostTextBatch:
+        """Foldcomp::extract for every blob: type_ 0 = pLDDT (digits 1..4), 1 = sequence (src/foldcomp.cpp:1260-1336)."""
+        n = blobs.n_chains
+        nb = int(blobs.blob_off[-1]) if n else 0
+        out = HostTextBatch(np.zeros(n + 1, np.uint64), np.zeros(6 * nb // 8 + 64, np.uint8))  # <= 6 chars per residue, >= 8 blob bytes per residue
+        sin, so = blobs.as_struct(), out.as_struct()
+        total = C.c_uint64()
+        self._check(self.lib.fcz_extract_batch(self.h, C.byref(sin), int(type_), int(digits), C.byref(so), C.byref(total)))
+        return out

@@ -129,6 +129,33 @@ int fcz_decode_plan(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* ou
  * canonical slot order, or FCZ_ALT order when opts.use_alt_atom_order is set. */
 int fcz_decode_batch(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch* out);
 
+/* ---- text ------------------------------------------------------------------
+ * A batch of texts, tightly concatenated: PDB text per chain, or extract output per blob. */
+typedef struct fcz_text_batch {
+    uint32_t n_chains;
+    int32_t mem;
+    uint64_t* text_off;  /* [n_chains+1] byte offset of each chain's text in `bytes`              */
+    char* bytes;
+    uint64_t bytes_cap;  /* capacity of `bytes`                                                  */
+} fcz_text_batch;
+
+/* PDB text of every chain of a decoded batch, byte-identical to the reference's
+ * writeAtomCoordinatesToPDB (src/atom_coordinate.cpp:220-291; fast_ftoa 186-218) on the atoms that
+ * Foldcomp::decompress returns (src/foldcomp.cpp:779-902): TITLE lines, one ATOM line per atom (serials from
+ * meta.idx_atom, residue numbers from meta.idx_residue, the OXT record with residue number = nResidue as in
+ * src/foldcomp.cpp:958-961), TER.  Atom names follow opts.use_alt_atom_order, i.e. the order the decode call
+ * produced.  fcz_pdb_text_plan fills out->text_off and returns the total size (it synchronises the engine's
+ * stream); fcz_pdb_text_batch must follow it on the same batch with out->bytes of at least that capacity.
+ * For FCZ_MEM_DEVICE batches in->res_cap must be >= the batch's residue count. */
+int fcz_pdb_text_plan(fcz_engine* e, const fcz_chain_batch* in, fcz_text_batch* out, uint64_t* total_bytes);
+int fcz_pdb_text_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_text_batch* out);
+
+/* Foldcomp::extract (src/foldcomp.cpp:1260-1336) for every blob: type 0 = pLDDT with `digits` (1..4) characters
+ * per residue, comma separated when digits > 1; type 1 = one-letter amino-acid sequence.  A blob that fails the
+ * header check yields an empty text.  *total_bytes receives the size needed; FCZ_E_CAPACITY if out is smaller. */
+int fcz_extract_batch(fcz_engine* e, const fcz_blob_batch* in, int32_t type, int32_t digits, fcz_text_batch* out,
+                      uint64_t* total_bytes);
+
 /* Block until everything enqueued on the engine's stream has finished. */
 int fcz_engine_sync(fcz_engine* e);
 
@@ -146,6 +173,8 @@ uint64_t fcz_engine_launch_count(const fcz_engine* e);
 #define FCZ_PROF_K_DEC_FRONT 3   /* one k_dec_front launch (unpack + NeRF passes)                              */
 #define FCZ_PROF_K_DEC_STITCH 4  /* one k_dec_stitch_t launch (serial walk over anchor segments)               */
 #define FCZ_PROF_K_DEC_BACK 5    /* one k_dec_back launch (blend + side chains + copy-out)                     */
+#define FCZ_PROF_K_PDB_PLAN 6    /* one k_pdb_plan launch                                                      */
+#define FCZ_PROF_K_PDB_EMIT 7    /* one k_pdb_emit launch                                                      */
 #define FCZ_PROF_KINDS 8
 typedef struct fcz_profile {
     double encode_kernel_ms, decode_kernel_ms;

@@ -11,6 +11,7 @@
 #include "fcz_oracle.h"
 
 #include <math.h>
+#include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -537,4 +538,150 @@ int fcz_oracle_decode_batch(const fcz_blob_batch* in, fcz_chain_batch* out, int 
         if (out->status) out->status[c] = rc;
     }
     return FCZ_OK;
+}
+
+/* ------------------------------------------------------------------------------ text (section 8 f1/f4) */
+
+#include <stdio.h>
+
+/* src/atom_coordinate.cpp:173-183 itoa_pos_only */
+static void itoa_pos_only(int n, char* s) {
+    int i = 0;
+    do { s[i++] = (char)(n % 10 + '0'); } while ((n /= 10) > 0);
+    s[i] = 0;
+    for (int a = 0, b = i - 1; a < b; a++, b--) { char c = s[a]; s[a] = s[b]; s[b] = c; }
+}
+
+/* src/atom_coordinate.cpp:186-218 fast_ftoa<T,P>: float arithmetic throughout */
+static void fast_ftoa(float n, int T, int P, char* s) {
+    float rounded = n + ((n < 0) ? -(0.5f / (float)T) : (0.5f / (float)T));
+    int32_t integer = (int32_t)rounded;
+    int32_t decimal = (int32_t)((rounded - (float)integer) * (float)T);
+    char* data = s;
+    if (n < 0) {
+        integer = abs(integer);
+        decimal = abs(decimal);
+        *data++ = '-';
+    }
+    itoa_pos_only(integer, data);
+    data += strlen(data);
+    *data++ = '.';
+    char buffer[16];
+    itoa_pos_only(decimal, buffer);
+    int len = (int)strlen(buffer);
+    for (int i = 0; i < P - len; i++) *data++ = '0';
+    memcpy(data, buffer, (size_t)len);
+    data[len] = 0;
+}
+
+typedef struct { char* p; uint64_t cap, n; } sink_t;
+static void emit(sink_t* o, const char* s, size_t len) {
+    for (size_t i = 0; i < len; i++, o->n++)
+        if (o->n < o->cap) o->p[o->n] = s[i];
+}
+static void emitf(sink_t* o, const char* fmt, ...) {
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    int n = vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (n > 0) emit(o, buf, (size_t)(n < (int)sizeof buf ? n : (int)sizeof buf - 1));
+}
+
+/* src/atom_coordinate.cpp:246-275: one ATOM line; std::setw is a minimum width */
+static void atom_line(sink_t* o, int serial, const char* atom, const char* res3, char chain, int resnum,
+                      float x, float y, float z, float b) {
+    char fx[32], fy[32], fz[32], fb[32];
+    fast_ftoa(x, 1000, 3, fx);
+    fast_ftoa(y, 1000, 3, fy);
+    fast_ftoa(z, 1000, 3, fz);
+    fast_ftoa(b, 100, 2, fb);
+    if (strlen(atom) == 4) emitf(o, "ATOM  %5d %-4s %3s %c%4d    %8s%8s%8s  1.00%6s          %2c  \n", serial, atom, res3, chain, resnum, fx, fy, fz, fb, atom[0]);
+    else emitf(o, "ATOM  %5d  %-3s %3s %c%4d    %8s%8s%8s  1.00%6s          %2c  \n", serial, atom, res3, chain, resnum, fx, fy, fz, fb, atom[0]);
+}
+
+/* writeAtomCoordinatesToPDB (src/atom_coordinate.cpp:220-291) over a chain in the decoder's output layout,
+ * labelled as Foldcomp::decompress labels its atoms (serials from idxAtom, src/atom_coordinate.cpp:356-360;
+ * residue_index idxResidue + r; the OXT record with residue_index = nResidue, src/foldcomp.cpp:958-961).
+ * Returns the text length; at most cap bytes are written. */
+int64_t fcz_oracle_format_pdb(const uint8_t* res_type, uint32_t L, const float* xyz, const float* bfactor,
+                              const fcz_chain_meta* meta, const char* title, uint32_t title_len, int use_alt,
+                              char* out, uint64_t cap) {
+    sink_t o = {out, cap, 0};
+    if (title_len) { /* src/atom_coordinate.cpp:223-243 */
+        int remaining = (int)title_len;
+        emitf(&o, "TITLE     %.*s\n", remaining < 70 ? remaining : 70, title);
+        remaining -= 70;
+        int continuation = 2;
+        while (remaining > 0) {
+            emitf(&o, "TITLE  % 3d%.*s\n", continuation, remaining < 70 ? remaining : 70, title + ((int)title_len - remaining));
+            remaining -= 70;
+            continuation++;
+        }
+    }
+    int serial = meta->idx_atom;
+    uint64_t a = 0;
+    int last_serial = 0, last_resnum = 0;
+    const char* last_res3 = "";
+    int any = 0;
+    for (uint32_t r = 0; r < L; r++) {
+        const int code = res_type[r];
+        for (int k = 0; k < FCZ_NATOMS[code]; k++, a++) {
+            const char* name = FCZ_ATOM_NAME[code][use_alt ? FCZ_ALT[code][k] : k];
+            atom_line(&o, serial, name, FCZ_NAME3[code], (char)meta->chain, (int)meta->idx_residue + (int)r,
+                      xyz[3 * a], xyz[3 * a + 1], xyz[3 * a + 2], bfactor[r]);
+            last_serial = serial; last_resnum = (int)meta->idx_residue + (int)r; last_res3 = FCZ_NAME3[code]; any = 1;
+            serial++;
+        }
+    }
+    if (meta->has_oxt && L) {
+        const int code = res_type[L - 1];
+        atom_line(&o, serial, "OXT", FCZ_NAME3[code], (char)meta->chain, (int)L, meta->oxt[0], meta->oxt[1], meta->oxt[2], bfactor[L - 1]);
+        last_serial = serial; last_resnum = (int)L; last_res3 = FCZ_NAME3[code]; any = 1;
+    }
+    if (any) emitf(&o, "TER   %5d      %3s %c%4d\n", last_serial + 1, last_res3, (char)meta->chain, last_resnum);
+    return (int64_t)o.n;
+}
+
+/* Foldcomp::extract (src/foldcomp.cpp:1260-1336) */
+int64_t fcz_oracle_extract(const uint8_t* blob, uint64_t len, int type, int digits, char* out, uint64_t cap) {
+    view_t v;
+    int rc = parse(blob, len, &v);
+    if (rc) return rc;
+    sink_t o = {out, cap, 0};
+    if (type == 1) {
+        for (uint32_t r = 0; r < v.L; r++) { char ch = (char)code_to_char(v.records[8 * r] >> 3); emit(&o, &ch, 1); }
+        return (int64_t)o.n;
+    }
+    if (digits < 1) digits = 1; else if (digits > 4) digits = 4;
+    const float tmin = getf(v.temp), tcont = getf(v.temp + 4);
+    const float maxval = (float)((double)tcont * (pow(2, 8) - 1) + (double)tmin);
+    const int zero_to_one = (maxval <= 1.0f && digits <= 2);
+    for (uint32_t i = 0; i < v.L; i++) {
+        const float t = cont(v.temp[8 + i], tmin, tcont);
+        float clamped;
+        char d1, d2;
+        if (zero_to_one) {
+            clamped = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+            d1 = (char)((int)(clamped * 10.0f) % 10) + '0';
+            d2 = (char)((int)(clamped * 100.0f) % 10) + '0';
+        } else {
+            clamped = t < 0.0f ? 0.0f : (t > 100.0f ? 100.0f : t);
+            d1 = (char)(clamped / 10.0f) + '0';
+            d2 = (char)((int)clamped % 10) + '0';
+        }
+        emit(&o, &d1, 1);
+        if (digits > 1) emit(&o, &d2, 1);
+        if (digits >= 3) {
+            char d3 = (char)((int)(clamped * 10.0f) % 10) + '0';
+            emit(&o, ".", 1);
+            emit(&o, &d3, 1);
+        }
+        if (digits == 4) {
+            char d4 = (char)((int)(clamped * 100.0f) % 10) + '0';
+            emit(&o, &d4, 1);
+        }
+        if (digits > 1 && i != v.L - 1) emit(&o, ",", 1);
+    }
+    return (int64_t)o.n;
 }

@@ -40,6 +40,15 @@ int fcz_oracle_encode_batch(const fcz_chain_batch* in, fcz_blob_batch* out, int3
 int fcz_oracle_decode_plan(const fcz_blob_batch* in, fcz_chain_batch* out, fcz_sizes* totals);
 int fcz_oracle_decode_batch(const fcz_blob_batch* in, fcz_chain_batch* out, int use_alt, int n_threads);
 
+/* PDB text of one chain in the decoder's output layout: the reference's writeAtomCoordinatesToPDB
+ * (src/atom_coordinate.cpp:220-291) with fast_ftoa (186-218).  Returns the text length. */
+int64_t fcz_oracle_format_pdb(const uint8_t* res_type, uint32_t L, const float* xyz, const float* bfactor,
+                              const fcz_chain_meta* meta, const char* title, uint32_t title_len, int use_alt,
+                              char* out, uint64_t cap);
+
+/* Foldcomp::extract (src/foldcomp.cpp:1260-1336): type 0 = pLDDT with `digits` 1..4, type 1 = sequence. */
+int64_t fcz_oracle_extract(const uint8_t* blob, uint64_t len, int type, int digits, char* out, uint64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -207,6 +207,68 @@ int ref_roundtrip_batch(int n_chains, const uint32_t* res_off, const uint64_t* a
     return err;
 }
 
+// PDB text of one chain given in the decoder's output layout (canonical slot order, or the -a order when
+// use_alt), through the reference's own writeAtomCoordinatesToPDB (src/atom_coordinate.cpp:220-291).  The atoms
+// are labelled the way Foldcomp::decompress labels them: residue r has residue_index idx_res + r, atom serials
+// run from idx_atom, and the OXT record carries residue_index = nResidue (src/foldcomp.cpp:958-961).
+// Returns the text length (the text is truncated to cap).
+int64_t ref_format_pdb(const uint8_t* res_type, int L, const float* xyz, const float* bfac, int has_oxt,
+                       const float* oxt, int idx_res, int idx_atom, char chain, const char* title,
+                       int title_len, int use_alt, char* out, size_t cap) {
+    std::vector<AtomCoordinate> atoms;
+    std::string ch(1, chain);
+    int ai = idx_atom;
+    size_t a = 0;
+    for (int r = 0; r < L; r++) {
+        const TypeInfo& t = type_info(res_type[r]);
+        const std::vector<std::string>* names = &t.atoms;
+        auto it = aas().find(t.name3);
+        if (use_alt && it != aas().end() && !it->second.altAtoms.empty()) names = &it->second.altAtoms;
+        for (size_t k = 0; k < names->size(); k++, a++)
+            atoms.emplace_back((*names)[k], t.name3, ch, ai++, idx_res + r, xyz[3 * a], xyz[3 * a + 1], xyz[3 * a + 2], 1.0f, bfac[r]);
+    }
+    if (has_oxt) {
+        const TypeInfo& t = type_info(res_type[L - 1]);
+        atoms.emplace_back("OXT", t.name3, ch, ai++, L, oxt[0], oxt[1], oxt[2], 1.0f, bfac[L - 1]);
+    }
+    std::ostringstream oss;
+    writeAtomCoordinatesToPDB(atoms, std::string(title, title + title_len), oss);
+    const std::string s = oss.str();
+    memcpy(out, s.data(), s.size() < cap ? s.size() : cap);
+    return (int64_t)s.size();
+}
+
+// The same text straight from a blob: Foldcomp::read + decompress + writeAtomCoordinatesToPDB, i.e. what
+// `foldcomp decompress` writes (src/main.cpp:612-689).
+int64_t ref_decompress_to_pdb(const uint8_t* fcz, size_t len, int use_alt, char* out, size_t cap) {
+    std::vector<AtomCoordinate> atoms;
+    Foldcomp comp;
+    int rc;
+    try {
+        rc = decompress_one(fcz, len, use_alt, atoms, comp);
+    } catch (const std::exception&) {
+        return -3;
+    }
+    if (rc != 0) return rc;
+    std::ostringstream oss;
+    writeAtomCoordinatesToPDB(atoms, comp.strTitle, oss);
+    const std::string s = oss.str();
+    memcpy(out, s.data(), s.size() < cap ? s.size() : cap);
+    return (int64_t)s.size();
+}
+
+// Foldcomp::extract (src/foldcomp.cpp:1260-1336) on one blob: type 0 pLDDT with `digits`, type 1 sequence.
+int64_t ref_extract(const uint8_t* fcz, size_t len, int type, int digits, char* out, size_t cap) {
+    Foldcomp comp;
+    std::istringstream iss(std::string((const char*)fcz, len));
+    int rc = comp.read(iss);
+    if (rc != 0) return rc;
+    std::string data;
+    comp.extract(data, type, digits);
+    memcpy(out, data.data(), data.size() < cap ? data.size() : cap);
+    return (int64_t)data.size();
+}
+
 int ref_max_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

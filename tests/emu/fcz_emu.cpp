@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../foldcomp_b200/csrc/fcz_codec.h"
+#include "../../foldcomp_b200/csrc/fcz_text.h"
 
 using namespace fcz;
 
@@ -108,6 +109,44 @@ uint64_t emu_cos_deg_mismatches(const float* inner, const float* p, uint32_t n, 
     }
     *fallbacks = fb;
     return bad;
+}
+
+// PDB text of one chain through the product's plan + emit units (fcz_text.h), one host thread.
+int64_t emu_format_pdb(const uint8_t* res_type, uint32_t L, const float* xyz, const float* bfac, const fcz_chain_meta* meta,
+                       const char* title, uint32_t title_len, int use_alt, char* out, uint64_t cap) {
+    static TextTables tt;
+    static bool init = false;
+    if (!init) { build_text_tables(&tt); init = true; }
+    uint32_t A = 0;
+    for (uint32_t r = 0; r < L; r++) A += tt.natoms[res_type[r]];
+    std::vector<uint32_t> aoff(L + 1), toff(L + 1);
+    PdbChain ch;
+    ch.L = L; ch.A = A; ch.title_len = title_len; ch.type = res_type; ch.bfac = bfac; ch.X = xyz; ch.title = title; ch.meta = meta;
+    ch.use_alt = use_alt; ch.aoff = aoff.data(); ch.toff = toff.data();
+    HostCtx cx;
+    uint32_t scratch = 0;
+    const uint32_t total = pdb_plan_chain(cx, &tt, ch, &scratch);
+    if (!out || total > cap) return total;
+    std::vector<V16> stage(FCZ_PDB_STAGE_BYTES / 16 + 1);
+    memset(out, '#', total);  // every byte must be written by the emit units
+    for (uint32_t r = 0; r < L; r += FCZ_PDB_UNIT_RES)
+        pdb_emit_unit(cx, &tt, ch, r, r + FCZ_PDB_UNIT_RES < L ? r + FCZ_PDB_UNIT_RES : L, out, (char*)stage.data());
+    return total;
+}
+
+int64_t emu_extract(const uint8_t* blob, uint64_t len, int type, int digits, char* out, uint64_t cap) {
+    static TextTables tt;
+    static bool init = false;
+    if (!init) { build_text_tables(&tt); init = true; }
+    if (len < HDR_BYTES) return FCZ_E_MAGIC;
+    const Layout y = make_layout(get_u16(blob + OFF_NRES), get_u32(blob + OFF_NSC), get_u32(blob + OFF_LENTITLE), blob[OFF_NANCHOR]);
+    if (y.size > len) return FCZ_E_TRUNCATED;
+    if (digits < 1) digits = 1; else if (digits > 4) digits = 4;
+    const uint32_t n = extract_len(y.L, type, (uint32_t)digits);
+    if (!out || n > cap) return n;
+    HostCtx cx;
+    extract_chain(cx, &tt, blob, y, type, (uint32_t)digits, out);
+    return n;
 }
 
 }  // extern "C"

@@ -39,7 +39,7 @@ def build_oracle():
 
 def build_emu():
     src = os.path.join(ROOT, "tests", "emu", "fcz_emu.cpp")
-    deps = [src] + [os.path.join(ROOT, "foldcomp_b200", "csrc", f) for f in ("fcz_codec.h", "fcz_math.h", "fcz_format.h", "fcz_tables.h")]
+    deps = [src] + [os.path.join(ROOT, "foldcomp_b200", "csrc", f) for f in ("fcz_codec.h", "fcz_math.h", "fcz_format.h", "fcz_tables.h", "fcz_text.h")]
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMU_SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-o", EMU_SO, src])
 
@@ -313,3 +313,119 @@ def long_chain(L: int, seed: int = 0) -> HostChainBatch:
     meta = src.meta[:1].copy()
     meta["n_atom"] = np.uint16((A + int(meta["has_oxt"][0])) & 0xFFFF)  # the header field is 16 bits (src/foldcomp.h:118-131)
     return abi.concat_chains([(rt, src.bfactor[:L], xyz[:A], np.frombuffer(f"long_{L}".encode(), np.uint8), meta)])
+
+
+# --------------------------------------------------------------------------- text
+
+
+def _format_with(fn, b: HostChainBatch, c: int, use_alt: bool, via_ref: bool = False) -> bytes:
+    rt, bf, xyz, title, meta = b._slice(c)
+    rt = np.ascontiguousarray(rt)
+    bf = np.ascontiguousarray(bf)
+    xyz = np.ascontiguousarray(xyz)
+    tb = bytes(title)
+    cap = 128 + len(tb) * 2 + 120 * (len(xyz) + 2)
+    out = np.zeros(cap, np.uint8)
+    m = np.ascontiguousarray(meta)
+    if via_ref:
+        oxt = np.ascontiguousarray(m["oxt"][0], np.float32)
+        n = fn(rt.ctypes.data, len(rt), xyz.ctypes.data, bf.ctypes.data, int(m["has_oxt"][0]), oxt.ctypes.data, int(m["idx_residue"][0]),
+               int(m["idx_atom"][0]), bytes([int(m["chain"][0])]), tb, len(tb), int(use_alt), out.ctypes.data, cap)
+    else:
+        n = fn(rt.ctypes.data, len(rt), xyz.ctypes.data, bf.ctypes.data, m.ctypes.data, tb, len(tb), int(use_alt), out.ctypes.data, cap)
+    assert 0 <= n <= cap, n
+    return bytes(out[:n])
+
+
+def _text_protos(lib, prefix):
+    f = getattr(lib, prefix + "format_pdb")
+    f.restype = C.c_int64
+    f.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64]
+    e = getattr(lib, prefix + "extract")
+    e.restype = C.c_int64
+    e.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+    return f, e
+
+
+def oracle_format_pdb(b: HostChainBatch, c: int = 0, use_alt: bool = False) -> bytes:
+    f, _ = _text_protos(oracle(), "fcz_oracle_")
+    return _format_with(f, b, c, use_alt)
+
+
+def emu_format_pdb(b: HostChainBatch, c: int = 0, use_alt: bool = False) -> bytes:
+    f, _ = _text_protos(emu(), "emu_")
+    return _format_with(f, b, c, use_alt)
+
+
+def ref_format_pdb(b: HostChainBatch, c: int = 0, use_alt: bool = False) -> bytes:
+    lib = ref()
+    lib.ref_format_pdb.restype = C.c_int64
+    lib.ref_format_pdb.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_char, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    return _format_with(lib.ref_format_pdb, b, c, use_alt, via_ref=True)
+
+
+def ref_decompress_to_pdb(blob: bytes, use_alt: bool = False) -> bytes:
+    lib = ref()
+    lib.ref_decompress_to_pdb.restype = C.c_int64
+    lib.ref_decompress_to_pdb.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
+    cap = 1 << 24
+    out = np.zeros(cap, np.uint8)
+    n = lib.ref_decompress_to_pdb(blob, len(blob), int(use_alt), out.ctypes.data, cap)
+    assert 0 <= n <= cap, n
+    return bytes(out[:n])
+
+
+def _extract_with(fn, blob: bytes, type_: int, digits: int) -> bytes:
+    cap = 8 * len(blob) + 64
+    out = np.zeros(cap, np.uint8)
+    n = fn(blob, len(blob), type_, digits, out.ctypes.data, cap)
+    assert 0 <= n <= cap, n
+    return bytes(out[:n])
+
+
+def oracle_extract(blob: bytes, type_: int, digits: int = 2) -> bytes:
+    return _extract_with(_text_protos(oracle(), "fcz_oracle_")[1], blob, type_, digits)
+
+
+def emu_extract(blob: bytes, type_: int, digits: int = 2) -> bytes:
+    return _extract_with(_text_protos(emu(), "emu_")[1], blob, type_, digits)
+
+
+def ref_extract(blob: bytes, type_: int, digits: int = 2) -> bytes:
+    lib = ref()
+    lib.ref_extract.restype = C.c_int64
+    lib.ref_extract.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    return _extract_with(lib.ref_extract, blob, type_, digits)
+
+
+def decoded_as_batch(dec, title: bytes | None = None) -> HostChainBatch:
+    """A `Decoded` (oracle/emu decode of one blob; the OXT lives in meta) as a 1-chain batch in the engine's layout."""
+    meta = np.zeros(1, abi.META_DTYPE)
+    meta[0] = dec.meta
+    return abi.concat_chains([(dec.res_type, dec.bfactor, dec.xyz, np.frombuffer(dec.title if title is None else title, np.uint8), meta)])
+
+
+def extreme_text_chain(seed: int = 0) -> HostChainBatch:
+    """A chain whose fields overflow their PDB columns (std::setw is a minimum width): residue numbers beyond 9999,
+    serials beyond 99999, coordinates beyond 9999.999 / below -999.999, B-factors beyond 999.99, values that round
+    to -0.000, and a title long enough for continuation lines."""
+    from foldcomp_b200 import synth
+
+    b = synth.generate(1, 700, seed=900 + seed)
+    rng = np.random.default_rng(seed)
+    xyz = b.xyz.copy()
+    idx = rng.choice(len(xyz), 60, replace=False)
+    vals = np.array([12345.678, -1234.567, 99999.9996, -0.0004, -0.0005, 0.0004999, 9999.9995, -999.9995, 1e6, -1e6, 123456.7, 0.9995, -0.9995,
+                     2147480000.0, -2147480000.0], np.float32)
+    for j, i in enumerate(idx):
+        xyz[i, j % 3] = vals[j % len(vals)]
+    b.xyz = xyz
+    bf = b.bfactor.copy()
+    bf[:8] = [1000.0, 999.995, -100.0, -0.004, 0.005, 99.995, 12345.5, -99.994]
+    b.bfactor = bf
+    b.meta["idx_residue"] = 9700
+    b.meta["idx_atom"] = 65000
+    title = (b"a very long title " * 12)[:205]
+    b.titles = np.frombuffer(title, np.uint8).copy()
+    b.title_off = np.array([0, len(title)], np.uint32)
+    return b

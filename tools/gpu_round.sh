@@ -23,7 +23,14 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_encode|k_dec_front|k_dec_stitch_t|k_dec_back' -s 12 -c 4 \
       -o gpurun_out/prof_step -f python bench.py --kernels-only --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
 fi
+if [ "${TEXT:-1}" = "1" ]; then
+  timeout 300 python tools/bench_text.py > gpurun_out/bench_text.json 2> gpurun_out/bench_text.err
+  if [ "${NCU:-1}" = "1" ]; then
+    N_CHAINS=10000 STEPS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_pdb_emit|k_pdb_plan' -s 6 -c 2 \
+        -o gpurun_out/prof_text -f python tools/bench_text.py > gpurun_out/ncu_text.log 2>&1
+  fi
+fi
 if [ "${MIXED:-0}" = "1" ]; then
   timeout 600 python bench.py --lengths mixed --steps 10 --warmup 3 > gpurun_out/bench_mixed.json 2> gpurun_out/bench_mixed.err
 fi
-tail -6 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/pcie.json; python tools/summ.py; tail -3 gpurun_out/bench.err
+tail -6 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/pcie.json; python tools/summ.py; cat gpurun_out/bench_text.json; tail -2 gpurun_out/bench_text.err; tail -3 gpurun_out/bench.err
