@@ -59,11 +59,12 @@ def compress(name: str, pdb_content: str, *, anchor_residue_threshold: int = abi
 
 
 def decompress(fcz: bytes):
-    from .pdbio import format_pdb
-
     eng = _get_engine()
-    blobs = HostBlobBatch.from_blobs([bytes(fcz)])
-    out = eng.decode_host(blobs)
+    data = bytes(fcz)
+    blobs = HostBlobBatch.from_blobs([data])
+    out = eng.decode_to_pdb_host(blobs)  # decode + PDB text on the GPU (k_dec_* then k_pdb_*)
     if int(out.status[0]) != abi.FCZ_OK:
         raise error("Error decompressing.")
-    return out.title(0), format_pdb(out, 0)
+    tl = int.from_bytes(data[24:28], "little")  # CompressedFileHeader.lenTitle; the title follows the anchor indices
+    t0 = 76 + 4 * data[12]
+    return data[t0 : t0 + tl].decode("latin-1"), out.text(0).decode("latin-1")

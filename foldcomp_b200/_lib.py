@@ -24,6 +24,8 @@ SYMBOLS = [
     "fcz_decode_batch",
     "fcz_pdb_text_plan",
     "fcz_pdb_text_batch",
+    "fcz_decode_to_pdb_plan",
+    "fcz_decode_to_pdb_batch",
     "fcz_extract_batch",
     "fcz_engine_sync",
     "fcz_engine_launch_count",
@@ -73,6 +75,10 @@ def load() -> C.CDLL:
     lib.fcz_pdb_text_plan.argtypes = [C.c_void_p, P(abi.FczChainBatch), P(abi.FczTextBatch), P(C.c_uint64)]
     lib.fcz_pdb_text_batch.restype = C.c_int
     lib.fcz_pdb_text_batch.argtypes = [C.c_void_p, P(abi.FczChainBatch), P(abi.FczTextBatch)]
+    lib.fcz_decode_to_pdb_plan.restype = C.c_int
+    lib.fcz_decode_to_pdb_plan.argtypes = [C.c_void_p, P(abi.FczBlobBatch), P(abi.FczTextBatch), P(C.c_uint64)]
+    lib.fcz_decode_to_pdb_batch.restype = C.c_int
+    lib.fcz_decode_to_pdb_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), P(abi.FczTextBatch)]
     lib.fcz_extract_batch.restype = C.c_int
     lib.fcz_extract_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), C.c_int32, C.c_int32, P(abi.FczTextBatch), P(C.c_uint64)]
     lib.fcz_engine_sync.restype = C.c_int

@@ -91,6 +91,7 @@ class FczTextBatch(C.Structure):
         ("text_off", C.c_void_p),
         ("bytes", C.c_void_p),
         ("bytes_cap", C.c_uint64),
+        ("status", C.c_void_p),
     ]
 
 
@@ -317,6 +318,11 @@ class HostTextBatch:
 
     text_off: np.ndarray  # uint64 [n+1]
     bytes: np.ndarray  # uint8 [cap]
+    status: np.ndarray = field(default=None)  # int32 [n], written by decode_to_pdb
+
+    def __post_init__(self):
+        if self.status is None:
+            self.status = np.zeros(self.n_chains, np.int32)
 
     @property
     def n_chains(self) -> int:
@@ -332,4 +338,5 @@ class HostTextBatch:
         s.text_off = _ptr(self.text_off)
         s.bytes = _ptr(self.bytes)
         s.bytes_cap = len(self.bytes)
+        s.status = _ptr(self.status)
         return s

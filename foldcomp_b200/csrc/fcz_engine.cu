@@ -1007,6 +1007,7 @@ __global__ void __launch_bounds__(128) k_pdb_plan(PdbArgs a) {
 
 __global__ void __launch_bounds__(128) k_pdb_emit(PdbArgs a) {
     __shared__ __align__(16) char stage[FCZ_PDB_STAGE_BYTES];
+    __shared__ uint32_t us[2 * FCZ_PDB_UNIT_RES + 2];
     const uint32_t u = a.unit0 + blockIdx.x;
     // chain of this unit: last c with unit_off[c] <= u (every thread searches; the array is L2-resident)
     uint32_t lo = 0, hi = a.n;
@@ -1019,7 +1020,7 @@ __global__ void __launch_bounds__(128) k_pdb_emit(PdbArgs a) {
     const PdbChain ch = pdb_chain(a, c);
     const uint32_t r_lo = (u - a.unit_off[c]) * FCZ_PDB_UNIT_RES;
     const uint32_t r_hi = r_lo + FCZ_PDB_UNIT_RES < ch.L ? r_lo + FCZ_PDB_UNIT_RES : ch.L;
-    pdb_emit_unit(cx, a.tt, ch, r_lo, r_hi, a.text + a.text_off[c], stage);
+    pdb_emit_unit(cx, a.tt, ch, r_lo, r_hi, a.text + a.text_off[c], stage, us);
 }
 
 struct ExtractArgs {
@@ -1814,6 +1815,81 @@ static void pdb_args(fcz_engine* e, const DevChains& d, uint32_t n, PdbArgs* a) 
     a->unit_off = (uint32_t*)e->d_unit_off.p;
 }
 
+// plan over device-resident chains: fills d_text_off (device, [n+1]) and the engine's unit offsets; syncs; leaves the
+// totals in e->pdb.  host_text_off (may be null) receives a copy of the offsets, and the unit offsets come to the host too.
+static int pdb_plan_dev(fcz_engine* e, const DevChains& d, uint32_t n, uint64_t n_res_cap, uint64_t* d_text_off, uint64_t* host_text_off) {
+    int rc;
+    e->pdb.valid = false;
+    if ((rc = plan_buffers(e, n))) return rc;
+    if ((rc = ensure(e, e->ws_aoff, 4ull * (n_res_cap + n + 1)))) return rc;
+    if ((rc = ensure(e, e->ws_toff, 4ull * (n_res_cap + n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_unit_off, 4ull * (n + 1)))) return rc;
+    PdbArgs a;
+    pdb_args(e, d, n, &a);
+    if (n) {
+        ProfSpan pk(e, FCZ_PROF_K_PDB_PLAN);
+        k_pdb_plan<<<n, 128, 0, e->stream>>>(a);
+        e->launches++;
+    }
+    ScanArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.n = n; sa.narr = 2;
+    sa.in[0] = a.text_bytes; sa.out[0] = d_text_off; sa.out64[0] = 1;
+    sa.in[1] = a.units; sa.out[1] = e->d_unit_off.p; sa.out64[1] = 0;
+    if ((rc = run_scan(e, sa))) return rc;
+    if (host_text_off) {
+        e->h_unit_off.resize((size_t)n + 1);
+        CK(cudaMemcpyAsync(host_text_off, d_text_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_unit_off.data(), e->d_unit_off.p, 4ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+    }
+    if ((rc = fetch_plan(e))) return rc;
+    e->pdb.n = n; e->pdb.total_bytes = e->h_totals[0]; e->pdb.total_units = (uint32_t)e->h_totals[1]; e->pdb.valid = true;
+    return FCZ_OK;
+}
+
+// emit into the engine's text buffer in slabs of ~64 MB so that the D2H copy of slab k overlaps the kernel of slab k+1
+static int pdb_emit_to_host(fcz_engine* e, const DevChains& d, uint32_t n, const uint64_t* host_text_off, char* host_bytes) {
+    int rc;
+    if ((rc = ensure(e, e->d_text, e->pdb.total_bytes + 64))) return rc;
+    PdbArgs a;
+    pdb_args(e, d, n, &a);
+    a.text_off = (uint64_t*)e->d_text_off.p; a.text = (char*)e->d_text.p;
+    size_t evi = 0;
+    cudaEvent_t ev0 = pool_event(e, evi++);
+    CK(cudaEventRecord(ev0, e->stream));
+    CK(cudaStreamWaitEvent(e->s_out, ev0, 0));
+    uint32_t c0 = 0;
+    while (c0 < n) {
+        uint32_t c1 = c0;
+        while (c1 < n && host_text_off[c1] - host_text_off[c0] < (64ull << 20)) c1++;
+        const uint32_t u0 = e->h_unit_off[c0], u1 = e->h_unit_off[c1];
+        if (u1 > u0) {
+            a.unit0 = u0;
+            ProfSpan pk(e, FCZ_PROF_K_PDB_EMIT);
+            k_pdb_emit<<<u1 - u0, 128, 0, e->stream>>>(a);
+            e->launches++;
+        }
+        cudaEvent_t ev = pool_event(e, evi++);
+        CK(cudaEventRecord(ev, e->stream));
+        CK(cudaStreamWaitEvent(e->s_out, ev, 0));
+        const uint64_t b0 = host_text_off[c0], b1 = host_text_off[c1];
+        COPY(host_bytes + b0, (char*)e->d_text.p + b0, b1 - b0, cudaMemcpyDeviceToHost, e->s_out);
+        c0 = c1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->s_out));
+    CK(cudaStreamSynchronize(e->stream));
+    return FCZ_OK;
+}
+
+static DevChains staged_chains(fcz_engine* e) {
+    DevChains d;
+    d.res_off = (uint32_t*)e->d_res_off.p; d.atom_off = (uint64_t*)e->d_atom_off.p; d.title_off = (uint32_t*)e->d_title_off.p;
+    d.res_type = (uint8_t*)e->d_res_type.p; d.bfactor = (float*)e->d_bfactor.p; d.xyz = (float*)e->d_xyz.p;
+    d.titles = (char*)e->d_titles.p; d.meta = (fcz_chain_meta*)e->d_meta.p;
+    return d;
+}
+
 extern "C" int fcz_pdb_text_plan(fcz_engine* e, const fcz_chain_batch* in, fcz_text_batch* out, uint64_t* total_bytes) {
     if (!e || !in || !out || !total_bytes) return FCZ_E_ARG;
     if (in->mem != out->mem) return fail(e, FCZ_E_ARG, "input and output batches must live in the same memory space");
@@ -1824,33 +1900,10 @@ extern "C" int fcz_pdb_text_plan(fcz_engine* e, const fcz_chain_batch* in, fcz_t
     int rc;
     DevChains d;
     if ((rc = upload_chains(e, in, &d))) return rc;
-    const uint64_t n_res = in->mem == FCZ_MEM_HOST ? in->res_off[n] : in->res_cap;
-    if ((rc = plan_buffers(e, n))) return rc;
-    if ((rc = ensure(e, e->ws_aoff, 4ull * (n_res + n + 1)))) return rc;
-    if ((rc = ensure(e, e->ws_toff, 4ull * (n_res + n + 1)))) return rc;
-    if ((rc = ensure(e, e->d_unit_off, 4ull * (n + 1)))) return rc;
-    if ((rc = ensure(e, e->d_text_off, 8ull * (n + 1)))) return rc;
-    PdbArgs a;
-    pdb_args(e, d, n, &a);
-    if (n) {
-        ProfSpan pk(e, FCZ_PROF_K_PDB_PLAN);
-        k_pdb_plan<<<n, 128, 0, e->stream>>>(a);
-        e->launches++;
-    }
-    uint64_t* d_text_off = in->mem == FCZ_MEM_DEVICE ? out->text_off : (uint64_t*)e->d_text_off.p;
-    ScanArgs sa;
-    memset(&sa, 0, sizeof sa);
-    sa.n = n; sa.narr = 2;
-    sa.in[0] = a.text_bytes; sa.out[0] = d_text_off; sa.out64[0] = 1;
-    sa.in[1] = a.units; sa.out[1] = e->d_unit_off.p; sa.out64[1] = 0;
-    if ((rc = run_scan(e, sa))) return rc;
-    if (in->mem == FCZ_MEM_HOST) {
-        e->h_unit_off.resize((size_t)n + 1);
-        CK(cudaMemcpyAsync(out->text_off, d_text_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaMemcpyAsync(e->h_unit_off.data(), e->d_unit_off.p, 4ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
-    }
-    if ((rc = fetch_plan(e))) return rc;
-    e->pdb.n = n; e->pdb.total_bytes = e->h_totals[0]; e->pdb.total_units = (uint32_t)e->h_totals[1]; e->pdb.valid = true;
+    const bool host = in->mem == FCZ_MEM_HOST;
+    if (host && (rc = ensure(e, e->d_text_off, 8ull * (n + 1)))) return rc;
+    if ((rc = pdb_plan_dev(e, d, n, host ? in->res_off[n] : in->res_cap, host ? (uint64_t*)e->d_text_off.p : out->text_off,
+                           host ? out->text_off : nullptr))) return rc;
     *total_bytes = e->pdb.total_bytes;
     return FCZ_OK;
 }
@@ -1865,54 +1918,18 @@ extern "C" int fcz_pdb_text_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_
         return fail(e, FCZ_E_CAPACITY, "text needs %llu bytes, capacity %llu", (unsigned long long)e->pdb.total_bytes, (unsigned long long)out->bytes_cap);
     e->pdb.valid = false;
     int rc;
+    if (in->mem == FCZ_MEM_HOST) return pdb_emit_to_host(e, staged_chains(e), n, out->text_off, out->bytes);  // chains still staged since the plan
     DevChains d;
-    if (in->mem == FCZ_MEM_DEVICE) {
-        if ((rc = upload_chains(e, in, &d))) return rc;
-    } else {  // still resident in the staging buffers since the plan call
-        d.res_off = (uint32_t*)e->d_res_off.p; d.atom_off = (uint64_t*)e->d_atom_off.p; d.title_off = (uint32_t*)e->d_title_off.p;
-        d.res_type = (uint8_t*)e->d_res_type.p; d.bfactor = (float*)e->d_bfactor.p; d.xyz = (float*)e->d_xyz.p;
-        d.titles = (char*)e->d_titles.p; d.meta = (fcz_chain_meta*)e->d_meta.p;
-    }
+    if ((rc = upload_chains(e, in, &d))) return rc;
     PdbArgs a;
     pdb_args(e, d, n, &a);
-    if (in->mem == FCZ_MEM_DEVICE) {
-        a.text_off = out->text_off; a.text = out->bytes; a.unit0 = 0;
-        if (e->pdb.total_units) {
-            ProfSpan pk(e, FCZ_PROF_K_PDB_EMIT);
-            k_pdb_emit<<<e->pdb.total_units, 128, 0, e->stream>>>(a);
-            e->launches++;
-        }
-        CK(cudaGetLastError());
-        return FCZ_OK;
-    }
-    // host memory: emit in slabs of ~64 MB of text so that the D2H copy of slab k overlaps the kernel of slab k+1
-    if ((rc = ensure(e, e->d_text, e->pdb.total_bytes + 64))) return rc;
-    a.text_off = (uint64_t*)e->d_text_off.p; a.text = (char*)e->d_text.p;
-    size_t evi = 0;
-    cudaEvent_t ev0 = pool_event(e, evi++);
-    CK(cudaEventRecord(ev0, e->stream));
-    CK(cudaStreamWaitEvent(e->s_out, ev0, 0));
-    uint32_t c0 = 0;
-    while (c0 < n) {
-        uint32_t c1 = c0;
-        while (c1 < n && out->text_off[c1] - out->text_off[c0] < (64ull << 20)) c1++;
-        const uint32_t u0 = e->h_unit_off[c0], u1 = e->h_unit_off[c1];
-        if (u1 > u0) {
-            a.unit0 = u0;
-            ProfSpan pk(e, FCZ_PROF_K_PDB_EMIT);
-            k_pdb_emit<<<u1 - u0, 128, 0, e->stream>>>(a);
-            e->launches++;
-        }
-        cudaEvent_t ev = pool_event(e, evi++);
-        CK(cudaEventRecord(ev, e->stream));
-        CK(cudaStreamWaitEvent(e->s_out, ev, 0));
-        const uint64_t b0 = out->text_off[c0], b1 = out->text_off[c1];
-        COPY(out->bytes + b0, (char*)e->d_text.p + b0, b1 - b0, cudaMemcpyDeviceToHost, e->s_out);
-        c0 = c1;
+    a.text_off = out->text_off; a.text = out->bytes; a.unit0 = 0;
+    if (e->pdb.total_units) {
+        ProfSpan pk(e, FCZ_PROF_K_PDB_EMIT);
+        k_pdb_emit<<<e->pdb.total_units, 128, 0, e->stream>>>(a);
+        e->launches++;
     }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(e->s_out));
-    CK(cudaStreamSynchronize(e->stream));
     return FCZ_OK;
 }
 
@@ -2338,4 +2355,63 @@ extern "C" int fcz_decode_batch(fcz_engine* e, const fcz_blob_batch* in, fcz_cha
     if (in->mem == FCZ_MEM_DEVICE) return decode_device(e, in, out);
     (void)n; (void)rc;
     return decode_host(e, in, out);
+}
+
+// --------------------------------------------------------------------- fused decode -> PDB text (host blobs in, host text out)
+// What `foldcomp decompress` does per entry (src/main.cpp:612-689: read + decompress + writeAtomCoordinatesToPDB), for a
+// batch: blobs go up once, the decoded coordinates never leave the GPU, only the text comes back.
+extern "C" int fcz_decode_to_pdb_plan(fcz_engine* e, const fcz_blob_batch* in, fcz_text_batch* out, uint64_t* total_bytes) {
+    if (!e || !in || !out || !total_bytes) return FCZ_E_ARG;
+    if (in->mem != FCZ_MEM_HOST || out->mem != FCZ_MEM_HOST) return fail(e, FCZ_E_ARG, "fcz_decode_to_pdb_* take host-memory batches");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    out->n_chains = n;
+    e->pdb.valid = false;
+    int rc;
+    const uint64_t nb = in->blob_off[n];
+    H2D(e->d_blob_off, in->blob_off, 8ull * (n + 1));
+    H2D(e->d_bytes, in->bytes, nb);
+    if ((rc = ensure(e, e->d_res_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_atom_off, 8ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_title_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_status, 4ull * n + 4))) return rc;
+    if ((rc = ensure(e, e->d_text_off, 8ull * (n + 1)))) return rc;
+    fcz_blob_batch bin;
+    memset(&bin, 0, sizeof bin);
+    bin.n_chains = n; bin.mem = FCZ_MEM_DEVICE; bin.blob_off = (uint64_t*)e->d_blob_off.p; bin.bytes = (uint8_t*)e->d_bytes.p;
+    fcz_chain_batch cb;
+    memset(&cb, 0, sizeof cb);
+    cb.n_chains = n; cb.mem = FCZ_MEM_DEVICE;
+    cb.res_off = (uint32_t*)e->d_res_off.p; cb.atom_off = (uint64_t*)e->d_atom_off.p; cb.title_off = (uint32_t*)e->d_title_off.p;
+    cb.status = (int32_t*)e->d_status.p;
+    fcz_sizes tot;
+    if ((rc = decode_plan_device(e, &bin, &cb, &tot))) return rc;
+    if ((rc = ensure(e, e->d_res_type, tot.n_res + 16))) return rc;
+    if ((rc = ensure(e, e->d_bfactor, 4ull * tot.n_res + 16))) return rc;
+    if ((rc = ensure(e, e->d_xyz, 12ull * tot.n_atoms + 16))) return rc;
+    if ((rc = ensure(e, e->d_titles, tot.n_title_bytes + 16))) return rc;
+    if ((rc = ensure(e, e->d_meta, sizeof(fcz_chain_meta) * (uint64_t)n + 16))) return rc;
+    cb.res_type = (uint8_t*)e->d_res_type.p; cb.bfactor = (float*)e->d_bfactor.p; cb.xyz = (float*)e->d_xyz.p;
+    cb.titles = (char*)e->d_titles.p; cb.meta = (fcz_chain_meta*)e->d_meta.p;
+    cb.res_cap = tot.n_res; cb.atom_cap = tot.n_atoms; cb.title_cap = tot.n_title_bytes;
+    if ((rc = decode_device(e, &bin, &cb))) return rc;
+    if ((rc = pdb_plan_dev(e, staged_chains(e), n, tot.n_res, (uint64_t*)e->d_text_off.p, out->text_off))) return rc;
+    if (out->status) {
+        CK(cudaMemcpyAsync(out->status, e->d_status.p, 4ull * n, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    *total_bytes = e->pdb.total_bytes;
+    return FCZ_OK;
+}
+
+extern "C" int fcz_decode_to_pdb_batch(fcz_engine* e, const fcz_blob_batch* in, fcz_text_batch* out) {
+    if (!e || !in || !out) return FCZ_E_ARG;
+    if (in->mem != FCZ_MEM_HOST || out->mem != FCZ_MEM_HOST) return fail(e, FCZ_E_ARG, "fcz_decode_to_pdb_* take host-memory batches");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    if (!e->pdb.valid || e->pdb.n != n) return fail(e, FCZ_E_ARG, "fcz_decode_to_pdb_batch needs a preceding fcz_decode_to_pdb_plan on the same batch");
+    if (e->pdb.total_bytes > out->bytes_cap)
+        return fail(e, FCZ_E_CAPACITY, "text needs %llu bytes, capacity %llu", (unsigned long long)e->pdb.total_bytes, (unsigned long long)out->bytes_cap);
+    e->pdb.valid = false;
+    return pdb_emit_to_host(e, staged_chains(e), n, out->text_off, out->bytes);
 }

@@ -141,6 +141,107 @@ FCZ_HD uint32_t atom_line_extra(const AtomRec& a) {
     return ex;
 }
 
+// ---- the uniform (81-byte) line as 21 little-endian words: no loops, no per-character stores.
+// A line is uniform iff every field fits its column; that is decided from the same integers the formatter prints.
+FCZ_HD bool ftoa_fits(const FtoaParts& p, uint32_t ip_max_pos, uint32_t ip_max_neg, uint32_t dp_max) {
+    return p.ip <= (p.neg ? ip_max_neg : ip_max_pos) && p.dp <= dp_max;
+}
+FCZ_HD bool atom_line_uniform(const AtomRec& a) {
+    const float h3 = 0.5f / 1000.0f, h2 = 0.5f / 100.0f;
+    return a.serial <= 99999u && a.resnum <= 9999u && ftoa_fits(ftoa_parts(a.x, 1000.0f, h3), 9999u, 999u, 999u) &&
+           ftoa_fits(ftoa_parts(a.y, 1000.0f, h3), 9999u, 999u, 999u) && ftoa_fits(ftoa_parts(a.z, 1000.0f, h3), 9999u, 999u, 999u) &&
+           ftoa_fits(ftoa_parts(a.b, 100.0f, h2), 999u, 99u, 99u);
+}
+// v <= 9999 as four characters, right-aligned, blank-padded, with a '-' before the first digit when neg (v <= 999 then)
+FCZ_HD uint32_t digits4_right(uint32_t v, uint32_t neg) {
+    const uint32_t d3 = v / 1000u, r3 = v - d3 * 1000u, d2 = r3 / 100u, r2 = r3 - d2 * 100u, d1 = r2 / 10u, d0 = r2 - d1 * 10u;
+    const uint32_t D = 0x30303030u + (d3 | d2 << 8 | d1 << 16 | d0 << 24);
+    const uint32_t nd = 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u);
+    const uint32_t shift = 8u * (4u - nd);
+    const uint32_t mask = 0xFFFFFFFFu << shift;
+    uint32_t out = (D & mask) | (0x20202020u & ~mask);
+    if (neg) out ^= (uint32_t)(' ' ^ '-') << (shift - 8u);
+    return out;
+}
+// columns (0-based): 0-5 "ATOM  ", 6-10 serial, 11-12 blanks, 13-15 name, 16 blank, 17-19 residue, 20 blank, 21 chain,
+// 22-25 residue number, 26-29 blanks, 30-37 x, 38-45 y, 46-53 z, 54-59 "  1.00", 60-65 B, 66-76 blanks, 77 element,
+// 78-79 blanks, 80 newline; word j holds columns 4j..4j+3
+FCZ_HD void atom_line_words(uint32_t* w, const AtomRec& a) {
+    const float h3 = 0.5f / 1000.0f, h2 = 0.5f / 100.0f;
+    w[0] = (uint32_t)'A' | (uint32_t)'T' << 8 | (uint32_t)'O' << 16 | (uint32_t)'M' << 24;
+    {
+        const uint32_t hi = a.serial / 10000u, lo = a.serial - hi * 10000u;
+        uint32_t c0 = ' ', R;
+        if (hi) {
+            const uint32_t d3 = lo / 1000u, r3 = lo - d3 * 1000u, d2 = r3 / 100u, r2 = r3 - d2 * 100u, d1 = r2 / 10u, d0 = r2 - d1 * 10u;
+            c0 = '0' + hi;
+            R = 0x30303030u + (d3 | d2 << 8 | d1 << 16 | d0 << 24);
+        } else {
+            R = digits4_right(lo, 0u);
+        }
+        w[1] = 0x00002020u | c0 << 16 | (R & 0xFFu) << 24;
+        w[2] = (R >> 8) | (uint32_t)' ' << 24;
+    }
+    w[3] = (uint32_t)' ' | (a.name & 0xFFFFFFu) << 8;
+    w[4] = (uint32_t)' ' | (a.res3 & 0xFFFFFFu) << 8;
+    {
+        const uint32_t rn = digits4_right(a.resnum, 0u);
+        w[5] = (uint32_t)' ' | (uint32_t)a.chain << 8 | (rn & 0xFFFFu) << 16;
+        w[6] = (rn >> 16) | 0x20200000u;
+    }
+    uint32_t fl[3], fh[3];
+    const float xyz[3] = {a.x, a.y, a.z};
+    for (int k = 0; k < 3; k++) {
+        const FtoaParts p = ftoa_parts(xyz[k], 1000.0f, h3);
+        fl[k] = digits4_right(p.ip, p.neg);
+        const uint32_t e2 = p.dp / 100u, r2 = p.dp - e2 * 100u, e1 = r2 / 10u, e0 = r2 - e1 * 10u;
+        fh[k] = (uint32_t)'.' | ('0' + e2) << 8 | ('0' + e1) << 16 | ('0' + e0) << 24;
+    }
+    w[7] = 0x00002020u | fl[0] << 16;
+    w[8] = fl[0] >> 16 | fh[0] << 16;
+    w[9] = fh[0] >> 16 | fl[1] << 16;
+    w[10] = fl[1] >> 16 | fh[1] << 16;
+    w[11] = fh[1] >> 16 | fl[2] << 16;
+    w[12] = fl[2] >> 16 | fh[2] << 16;
+    w[13] = fh[2] >> 16 | 0x20200000u;
+    w[14] = (uint32_t)'1' | (uint32_t)'.' << 8 | (uint32_t)'0' << 16 | (uint32_t)'0' << 24;
+    {
+        const FtoaParts p = ftoa_parts(a.b, 100.0f, h2);
+        const uint32_t bi = digits4_right(p.ip, p.neg) >> 8;  // three columns
+        const uint32_t e1 = p.dp / 10u, e0 = p.dp - e1 * 10u;
+        w[15] = bi | (uint32_t)'.' << 24;
+        w[16] = ('0' + e1) | ('0' + e0) << 8 | 0x20200000u;
+    }
+    w[17] = 0x20202020u;
+    w[18] = 0x20202020u;
+    w[19] = (uint32_t)' ' | (a.name & 0xFFu) << 8 | 0x20200000u;
+    w[20] = (uint32_t)'\n';
+}
+// the low 32 bits of (hi:lo) >> s, 0 < s < 32
+FCZ_HD uint32_t shr64(uint32_t lo, uint32_t hi, uint32_t s) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, s);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> s);
+#endif
+}
+// store the 81 bytes held in w[0..20] at dst (any alignment): aligned 32-bit stores for the interior, bytes at the ends
+FCZ_HD void store_line81(char* dst, const uint32_t* w) {
+    const uint32_t m = (uint32_t)((uintptr_t)dst & 3u);
+    if (m == 0u) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        for (int k = 0; k < 20; k++) d[k] = w[k];
+        dst[80] = '\n';
+        return;
+    }
+    const uint32_t s = 8u * (4u - m);  // aligned word k (k >= 1) starts at line byte 4k - m
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst - m);
+    for (uint32_t b = 0; b < 4u - m; b++) dst[b] = (char)(w[0] >> (8u * b));
+    for (int k = 1; k < 20; k++) d[k] = shr64(w[k - 1], w[k], s);
+    const uint32_t tail = shr64(w[19], w[20], s);  // line bytes 80-m .. 80 (m + 1 of them)
+    for (uint32_t b = 0; b <= m; b++) dst[80u - m + b] = (char)(tail >> (8u * b));
+}
+
 // One ATOM line (src/atom_coordinate.cpp:246-275); returns its length.
 FCZ_HD uint32_t put_atom_line(char* dst, const AtomRec& a) {
     char* p = dst;
@@ -290,19 +391,27 @@ FCZ_HD uint32_t pdb_plan_chain(Ctx& cx, const TextTables* tt, const PdbChain& ch
     for (uint32_t r = r0; r < r1; r++) { ch.aoff[r] = base; base += tt->natoms[ch.type[r]]; }
     if (r1 == L) ch.aoff[L] = base;
     cx.sync();
-    // bytes beyond 81 per residue (zero for ordinary coordinates)
+    // bytes beyond 81 (zero for ordinary coordinates): the cheap fits-its-columns test per atom, the exact
+    // measurement only for the atoms that fail it
     uint32_t extra = 0, atom = a_first;
     for (uint32_t r = r0; r < r1; r++) {
         const uint32_t n = tt->natoms[ch.type[r]];
-        for (uint32_t k = 0; k < n; k++, atom++) extra += atom_line_extra(pdb_atom_rec(tt, ch, r, k, atom));
+        for (uint32_t k = 0; k < n; k++, atom++) {
+            const AtomRec a = pdb_atom_rec(tt, ch, r, k, atom);
+            if (!atom_line_uniform(a)) extra += atom_line_extra(a);
+        }
     }
     uint32_t ebase = cx.excl_scan(extra);
     const uint32_t head = title_lines_len(ch.title_len);
     atom = a_first;
-    for (uint32_t r = r0; r < r1; r++) {
-        ch.toff[r] = head + FCZ_PDB_LINE * atom + ebase;
-        const uint32_t n = tt->natoms[ch.type[r]];
-        for (uint32_t k = 0; k < n; k++, atom++) ebase += atom_line_extra(pdb_atom_rec(tt, ch, r, k, atom));
+    if (extra == 0u) {  // this thread's residues are uniform: offsets follow from the atom offsets alone
+        for (uint32_t r = r0; r < r1; r++) { ch.toff[r] = head + FCZ_PDB_LINE * atom + ebase; atom += tt->natoms[ch.type[r]]; }
+    } else {
+        for (uint32_t r = r0; r < r1; r++) {
+            ch.toff[r] = head + FCZ_PDB_LINE * atom + ebase;
+            const uint32_t n = tt->natoms[ch.type[r]];
+            for (uint32_t k = 0; k < n; k++, atom++) ebase += atom_line_extra(pdb_atom_rec(tt, ch, r, k, atom));
+        }
     }
     if (r1 == L) {
         const uint32_t t_tail = head + FCZ_PDB_LINE * atom + ebase;
@@ -339,24 +448,31 @@ FCZ_HD void copy_same_phase(Ctx& cx, char* dst, const char* src, uint32_t bytes)
 // FCZ_PDB_STAGE_BYTES (16-byte aligned; shared memory on the device) through which uniform units -- every line
 // 81 bytes -- leave as 128-bit copies; a unit with an over-long line writes straight to dst.
 template <class Ctx>
-FCZ_HD void pdb_emit_unit(Ctx& cx, const TextTables* tt, const PdbChain& ch, uint32_t r_lo, uint32_t r_hi, char* dst, char* stage) {
-    const uint32_t a_lo = ch.aoff[r_lo], a_hi = ch.aoff[r_hi];
-    const uint32_t t_lo = ch.toff[r_lo], t_hi = ch.toff[r_hi];
+FCZ_HD void pdb_emit_unit(Ctx& cx, const TextTables* tt, const PdbChain& ch, uint32_t r_lo, uint32_t r_hi, char* dst, char* stage,
+                          uint32_t* us /* [2 * FCZ_PDB_UNIT_RES + 2] words visible to all threads */) {
+    const uint32_t nr = r_hi - r_lo;
+    uint32_t* ut = us + FCZ_PDB_UNIT_RES + 1u;
+    for (uint32_t j = cx.tid; j <= nr; j += cx.nthr) { us[j] = ch.aoff[r_lo + j]; ut[j] = ch.toff[r_lo + j]; }
+    cx.sync();
+    const uint32_t a_lo = us[0], a_hi = us[nr];
+    const uint32_t t_lo = ut[0], t_hi = ut[nr];
     const uint32_t n = a_hi - a_lo;
     const bool uniform = (t_hi - t_lo) == FCZ_PDB_LINE * n;
     char* g = dst + t_lo;
     char* s = stage + ((uintptr_t)g & 15u);
     for (uint32_t i = cx.tid; i < n; i += cx.nthr) {
         const uint32_t atom = a_lo + i;
-        uint32_t r = r_lo;
-        while (r + 1u < r_hi && ch.aoff[r + 1u] <= atom) r++;
-        const uint32_t k = atom - ch.aoff[r];
+        uint32_t j = 0;
+        for (uint32_t q = 1; q < nr; q++) j += (us[q] <= atom) ? 1u : 0u;  // residue of this atom within the unit
+        const uint32_t r = r_lo + j, k = atom - us[j];
         const AtomRec a = pdb_atom_rec(tt, ch, r, k, atom);
         if (uniform) {
-            put_atom_line(s + FCZ_PDB_LINE * i, a);
+            uint32_t w[21];
+            atom_line_words(w, a);
+            store_line81(s + FCZ_PDB_LINE * i, w);
         } else {
-            uint32_t off = ch.toff[r];
-            for (uint32_t j = 0; j < k; j++) off += FCZ_PDB_LINE + atom_line_extra(pdb_atom_rec(tt, ch, r, j, ch.aoff[r] + j));
+            uint32_t off = ut[j];
+            for (uint32_t q = 0; q < k; q++) off += FCZ_PDB_LINE + atom_line_extra(pdb_atom_rec(tt, ch, r, q, us[j] + q));
             put_atom_line(dst + off, a);
         }
     }
@@ -369,8 +485,8 @@ FCZ_HD void pdb_emit_unit(Ctx& cx, const TextTables* tt, const PdbChain& ch, uin
     if (uniform) {
         cx.sync();
         copy_same_phase(cx, g, s, FCZ_PDB_LINE * n);
-        cx.sync();
     }
+    cx.sync();
 }
 
 // ---- Foldcomp::extract (src/foldcomp.cpp:1260-1336)

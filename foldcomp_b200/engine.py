@@ -160,6 +160,7 @@ class DeviceTextBatch:
         s.text_off = self.text_off.data_ptr()
         s.bytes = self.bytes.data_ptr()
         s.bytes_cap = self.bytes.numel()
+        s.status = None
         return s
 
     def to_host(self) -> HostTextBatch:
@@ -299,6 +300,21 @@ class Engine:
     def pdb_text_device(self, chains: DeviceChainBatch, out: "DeviceTextBatch") -> None:
         sin, so = chains.as_struct(), out.as_struct()
         self._check(self.lib.fcz_pdb_text_batch(self.h, C.byref(sin), C.byref(so)))
+
+    def decode_to_pdb_host(self, blobs: HostBlobBatch, out: HostTextBatch | None = None) -> HostTextBatch:
+        """FCZ blobs -> PDB text in one call (what `foldcomp decompress` does per entry, src/main.cpp:612-689): the decoded
+        coordinates stay on the GPU.  out.status holds the per-chain decode status (failed chains give empty text)."""
+        n = blobs.n_chains
+        if out is None:
+            out = HostTextBatch(np.zeros(n + 1, np.uint64), np.zeros(0, np.uint8))
+        sin, so = blobs.as_struct(), out.as_struct()
+        total = C.c_uint64()
+        self._check(self.lib.fcz_decode_to_pdb_plan(self.h, C.byref(sin), C.byref(so), C.byref(total)))
+        if len(out.bytes) < total.value:
+            out.bytes = np.zeros(total.value, np.uint8)
+        so = out.as_struct()
+        self._check(self.lib.fcz_decode_to_pdb_batch(self.h, C.byref(sin), C.byref(so)))
+        return out
 
     def extract_host(self, blobs: HostBlobBatch, type_: int, digits: int = 2) -> HostTextBatch:
         """Foldcomp::extract for every blob: type_ 0 = pLDDT (digits 1..4), 1 = sequence (src/foldcomp.cpp:1260-1336)."""

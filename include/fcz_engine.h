@@ -137,6 +137,7 @@ typedef struct fcz_text_batch {
     uint64_t* text_off;  /* [n_chains+1] byte offset of each chain's text in `bytes`              */
     char* bytes;
     uint64_t bytes_cap;  /* capacity of `bytes`                                                  */
+    int32_t* status;     /* [n_chains] per-chain status, written by fcz_decode_to_pdb_plan (may be NULL) */
 } fcz_text_batch;
 
 /* PDB text of every chain of a decoded batch, byte-identical to the reference's
@@ -149,6 +150,13 @@ typedef struct fcz_text_batch {
  * For FCZ_MEM_DEVICE batches in->res_cap must be >= the batch's residue count. */
 int fcz_pdb_text_plan(fcz_engine* e, const fcz_chain_batch* in, fcz_text_batch* out, uint64_t* total_bytes);
 int fcz_pdb_text_batch(fcz_engine* e, const fcz_chain_batch* in, fcz_text_batch* out);
+
+/* Decode and format in one go, host blobs in, host text out: what `foldcomp decompress` does per entry
+ * (src/main.cpp:612-689: Foldcomp::read + decompress + writeAtomCoordinatesToPDB).  The blobs go up once, the
+ * decoded coordinates stay on the GPU, only the text comes back (in slabs, overlapped with the emit kernel).
+ * Same plan/batch protocol as above; a blob that fails to decode yields an empty text and a status. */
+int fcz_decode_to_pdb_plan(fcz_engine* e, const fcz_blob_batch* in, fcz_text_batch* out, uint64_t* total_bytes);
+int fcz_decode_to_pdb_batch(fcz_engine* e, const fcz_blob_batch* in, fcz_text_batch* out);
 
 /* Foldcomp::extract (src/foldcomp.cpp:1260-1336) for every blob: type 0 = pLDDT with `digits` (1..4) characters
  * per residue, comma separated when digits > 1; type 1 = one-letter amino-acid sequence.  A blob that fails the

@@ -129,8 +129,9 @@ int64_t emu_format_pdb(const uint8_t* res_type, uint32_t L, const float* xyz, co
     if (!out || total > cap) return total;
     std::vector<V16> stage(FCZ_PDB_STAGE_BYTES / 16 + 1);
     memset(out, '#', total);  // every byte must be written by the emit units
+    uint32_t us[2 * FCZ_PDB_UNIT_RES + 2];
     for (uint32_t r = 0; r < L; r += FCZ_PDB_UNIT_RES)
-        pdb_emit_unit(cx, &tt, ch, r, r + FCZ_PDB_UNIT_RES < L ? r + FCZ_PDB_UNIT_RES : L, out, (char*)stage.data());
+        pdb_emit_unit(cx, &tt, ch, r, r + FCZ_PDB_UNIT_RES < L ? r + FCZ_PDB_UNIT_RES : L, out, (char*)stage.data(), us);
     return total;
 }
 

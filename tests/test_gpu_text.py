@@ -96,3 +96,30 @@ def test_extract_plddt_and_sequence(engine, golden):
         for c, blob in enumerate(blobs):
             want = H.oracle_extract(blob, t, d) if len(blob) > 4 else b""
             assert got.text(c) == want, (c, t, d)
+
+
+def test_decode_to_pdb_fused_and_python_decompress(engine, golden):
+    """fcz_decode_to_pdb_*: blobs in, text out; equals format(decode) of the separate calls, bad blobs give a status and
+    no text.  foldcomp_b200.decompress() -- the CPython module's decompress(bytes) -> (name, pdb) -- goes through it."""
+    import foldcomp_b200
+
+    blobs = golden.blobs(25) + [b"NOPE" + golden.blobs(25)[0][4:]] + list(golden.db_blobs[:5])
+    hb = HostBlobBatch.from_blobs(blobs)
+    got = engine.decode_to_pdb_host(hb)
+    dec = engine.decode_host(hb)
+    assert list(got.status) == list(dec.status) and got.status[len(golden.names)] == abi.FCZ_E_MAGIC
+    for c in range(hb.n_chains):
+        want = H.oracle_format_pdb(dec, c) if dec.status[c] == 0 else b""
+        assert got.text(c) == want, c
+    c = golden.names.index("test.pdb")
+    name, pdb = foldcomp_b200.decompress(blobs[c])
+    assert name == golden.batch.title(c) and pdb.encode("latin-1") == got.text(c)
+    # against the reference's own text of its own decode: same lines, coordinates within the decode tolerance
+    want = H.ref_decompress_to_pdb(blobs[c]).decode() if H.have_ref() else None
+    if want is not None:
+        gl, wl = pdb.splitlines(), want.splitlines()
+        assert len(gl) == len(wl)
+        for a, b in zip(gl, wl):
+            assert a[:30] == b[:30] and a[54:] == b[54:]
+            if a.startswith("ATOM"):
+                assert max(abs(float(a[30 + 8 * k : 38 + 8 * k]) - float(b[30 + 8 * k : 38 + 8 * k])) for k in range(3)) <= 0.051
