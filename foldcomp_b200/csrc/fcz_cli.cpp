@@ -10,6 +10,7 @@
 #include <iostream>
 #include <sstream>
 
+#include "fcz_db.h"
 #include "foldcomp_gpu.h"
 
 using namespace fczgpu;
@@ -39,29 +40,10 @@ static int read_pdb(const std::string& path, std::vector<AtomCoordinate>& atoms)
     return atoms.empty() ? 1 : 0;
 }
 
-static void write_pdb(std::ostream& os, const std::vector<AtomCoordinate>& atoms, const std::string& title) {
-    char buf[128];
-    if (!title.empty()) { snprintf(buf, sizeof buf, "TITLE     %.70s\n", title.c_str()); os << buf; }
-    for (size_t i = 0; i < atoms.size(); i++) {
-        const AtomCoordinate& a = atoms[i];
-        char name[8];
-        if (a.atom.size() == 4) snprintf(name, sizeof name, "%-4s", a.atom.c_str());
-        else snprintf(name, sizeof name, " %-3s", a.atom.c_str());
-        snprintf(buf, sizeof buf, "ATOM  %5d %s %3s %s%4d    %8.3f%8.3f%8.3f  1.00%6.2f          %2c  \n", a.atom_index, name,
-                 a.residue.c_str(), a.chain.c_str(), a.residue_index, a.coordinate.x, a.coordinate.y, a.coordinate.z, a.tempFactor,
-                 a.atom[0]);
-        os << buf;
-    }
-    if (!atoms.empty()) {
-        const AtomCoordinate& a = atoms.back();
-        snprintf(buf, sizeof buf, "TER   %5d      %3s %s%4d\n", a.atom_index + 1, a.residue.c_str(), a.chain.c_str(), a.residue_index);
-        os << buf;
-    }
-}
-
 int main(int argc, char** argv) {
     if (argc < 4) {
-        fprintf(stderr, "usage: fcz_cli compress [-b N] in.pdb out.fcz | decompress [-a] in.fcz out.pdb\n");
+        fprintf(stderr, "usage: fcz_cli compress [-b N] in.pdb out.fcz | decompress [-a] in.fcz out.pdb\n"
+                        "       fcz_cli compress-db [-b N] in_pdb_db out_fcz_db | decompress-db [-a] in_fcz_db out_pdb_db\n");
         return 2;
     }
     const std::string mode = argv[1];
@@ -77,6 +59,14 @@ int main(int argc, char** argv) {
     try {
         Engine eng(0);
         FoldcompGpu comp(eng);
+        if (mode == "compress-db" || mode == "decompress-db") {  // whole foldcomp databases, batched over the engine (fcz_db.h)
+            DbStats st;
+            const int rc = mode == "compress-db" ? compressDb(eng, in, out, b, &st) : decompressDb(eng, in, out, alt, &st);
+            if (rc) { fprintf(stderr, "[Error] %s: %s\n", mode.c_str(), fcz_strerror(rc)); return 1; }
+            fprintf(stderr, "%zu entries (%zu failed), %llu residues, %.3f s total, %.3f s in the engine\n", st.entries, st.failed,
+                    (unsigned long long)st.residues, st.seconds, st.seconds_engine);
+            return 0;
+        }
         if (mode == "compress") {
             std::vector<AtomCoordinate> atoms;
             int rc = read_pdb(in, atoms);
@@ -91,11 +81,11 @@ int main(int argc, char** argv) {
             std::ifstream is(in, std::ios::binary);
             if (!is || comp.read(is) != 0) { fprintf(stderr, "[Error] not an FCZ file\n"); return 1; }
             comp.useAltAtomOrder = alt;
-            std::vector<AtomCoordinate> atoms;
-            int rc = comp.decompress(atoms);
+            std::string text;
+            int rc = comp.decompressToPdb(text);  // decode + writeAtomCoordinatesToPDB-identical text, both on the GPU
             if (rc) { fprintf(stderr, "[Error] decompress: %s\n", fcz_strerror(rc)); return 1; }
-            std::ofstream os(out);
-            write_pdb(os, atoms, comp.strTitle);
+            std::ofstream os(out, std::ios::binary);
+            os.write(text.data(), (std::streamsize)text.size());
         } else return 2;
     } catch (const std::exception& ex) {
         fprintf(stderr, "[Error] %s\n", ex.what());

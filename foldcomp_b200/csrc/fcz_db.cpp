@@ -1,0 +1,459 @@
+// foldcomp_b200/csrc/fcz_db.cpp -- see fcz_db.h.  Host code (g++), no codec arithmetic.
+#include "fcz_db.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "fcz_tables.h"
+
+namespace fczgpu {
+
+// ------------------------------------------------------------------------------------------ parser
+
+// std::stof(line.substr(a, n)) of the reference = strtof on the field.  Fast path for the shape every PDB writer
+// produces -- optional blanks, optional sign, digits, optional '.', digits, at most 9 digits in all: the decimal
+// value m / 10^k is formed in double (m and 10^k are exact, one correctly rounded division) and rounded to float;
+// that equals strtof's correctly rounded result unless the double lands exactly on the midpoint of two floats, which
+// is detected from its low mantissa bits and sent to strtof.  Anything else goes to strtof as well.
+float parseFixedFloat(const char* s, size_t n) {
+    size_t i = 0;
+    while (i < n && (s[i] == ' ' || s[i] == '\t')) i++;
+    bool neg = false;
+    size_t j = i;
+    if (j < n && (s[j] == '-' || s[j] == '+')) { neg = s[j] == '-'; j++; }
+    uint64_t m = 0;
+    int nd = 0, frac = 0;
+    bool dot = false, ok = true;
+    for (; j < n; j++) {
+        const char ch = s[j];
+        if (ch >= '0' && ch <= '9') { m = m * 10 + (uint64_t)(ch - '0'); nd++; if (dot) frac++; }
+        else if (ch == '.' && !dot) dot = true;
+        else if (ch == ' ' || ch == '\t' || ch == '\r' || ch == 0) { break; }  // strtof stops here
+        else { ok = false; break; }
+    }
+    if (ok && nd > 0 && nd <= 9) {
+        static const double p10[10] = {1, 10, 100, 1000, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9};
+        const double d = (double)m / p10[frac];
+        uint64_t bits;
+        memcpy(&bits, &d, 8);
+        if ((bits & 0x1FFFFFFFull) != 0x10000000ull) {  // not a float midpoint: one more rounding is safe
+            const float f = (float)d;
+            return neg ? -f : f;
+        }
+    }
+    char buf[32];
+    const size_t k = n < sizeof buf - 1 ? n : sizeof buf - 1;
+    memcpy(buf, s, k);
+    buf[k] = 0;
+    return strtof(buf, nullptr);
+}
+
+static int parse_int_field(const char* s, size_t n) {  // std::stoi on the field: blanks, sign, digits
+    size_t i = 0;
+    while (i < n && (s[i] == ' ' || s[i] == '\t')) i++;
+    bool neg = false;
+    if (i < n && (s[i] == '-' || s[i] == '+')) { neg = s[i] == '-'; i++; }
+    long v = 0;
+    for (; i < n && s[i] >= '0' && s[i] <= '9'; i++) v = v * 10 + (s[i] - '0');
+    return (int)(neg ? -v : v);
+}
+
+struct RawAtom {
+    char name[5];
+    char res[4];
+    int serial, resnum;
+    float x, y, z, b;
+};
+
+static void trim_copy(char* dst, size_t cap, const char* s, size_t n) {  // trim(" \t") of the reference
+    size_t a = 0, b = n;
+    while (a < b && (s[a] == ' ' || s[a] == '\t')) a++;
+    while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\t')) b--;
+    size_t k = b - a < cap - 1 ? b - a : cap - 1;
+    memcpy(dst, s + a, k);
+    dst[k] = 0;
+}
+
+static int code_of3(const char* r) {
+    for (int c = 0; c < FCZ_NUM_CODES; c++)
+        if (!strcmp(FCZ_NAME3[c], r)) return FCZ_NATOMS[c] ? c : FCZ_CODE_UNK;
+    return FCZ_CODE_UNK;
+}
+
+int parsePdbChain(const char* text, size_t len, const std::string& title, CanonicalChain& out) {
+    out = CanonicalChain();
+    out.title = title;
+    std::vector<RawAtom> atoms;
+    atoms.reserve(len / 81 + 1);
+    char chain = 0;
+    bool have_chain = false;
+    size_t p = 0;
+    while (p < len) {
+        const char* line = text + p;
+        const char* nl = (const char*)memchr(line, '\n', len - p);
+        const size_t n = nl ? (size_t)(nl - line) : len - p;
+        p += n + 1;
+        if (n < 4 || memcmp(line, "ATOM", 4) != 0) continue;
+        if (n < 22) return 3;  // substr(21, 1) would throw
+        const char ch = line[21];
+        if (!have_chain) { chain = ch; have_chain = true; }
+        if (ch != chain) return 2;
+        if (n < 61) return 3;  // the B-factor column starts at 60
+        RawAtom a;
+        trim_copy(a.name, sizeof a.name, line + 12, 4);
+        trim_copy(a.res, sizeof a.res, line + 17, 3);
+        a.serial = parse_int_field(line + 6, 5);
+        a.resnum = parse_int_field(line + 22, 4);
+        a.x = parseFixedFloat(line + 30, 8);
+        a.y = parseFixedFloat(line + 38, 8);
+        a.z = parseFixedFloat(line + 46, 8);
+        a.b = parseFixedFloat(line + 60, n - 60 < 6 ? n - 60 : 6);
+        if (!atoms.empty() && !strcmp(atoms.back().name, a.name)) continue;  // removeAlternativePosition
+        atoms.push_back(a);
+    }
+    if (atoms.empty()) return 1;
+    const size_t n = atoms.size();
+    out.meta.n_atom = (uint16_t)n;
+    out.meta.idx_residue = (uint16_t)atoms[0].resnum;
+    out.meta.idx_atom = (uint16_t)atoms[0].serial;
+    out.meta.chain = (uint8_t)chain;
+    if (!strcmp(atoms[n - 1].name, "OXT")) {  // src/foldcomp.cpp:473-481
+        out.meta.has_oxt = 1;
+        out.meta.oxt[0] = atoms[n - 1].x; out.meta.oxt[1] = atoms[n - 1].y; out.meta.oxt[2] = atoms[n - 1].z;
+    }
+    size_t i = 0;
+    while (i < n) {  // splitAtomByResidue (src/atom_coordinate.cpp:304-328): the last atom joins the current residue
+        size_t j = i + 1;
+        while (j < n && (atoms[j].resnum == atoms[j - 1].resnum || j == n - 1)) j++;
+        const int code = code_of3(atoms[i].res);
+        out.res_type.push_back((uint8_t)code);
+        for (int k = 0; k < FCZ_NATOMS[code]; k++) {
+            const char* want = FCZ_ATOM_NAME[code][k];
+            float x = 0, y = 0, z = 0;  // findFirstAtomCoords: a missing atom reads as (0,0,0)
+            for (size_t a = i; a < j; a++)
+                if (!strcmp(atoms[a].name, want)) { x = atoms[a].x; y = atoms[a].y; z = atoms[a].z; break; }
+            out.xyz.push_back(x); out.xyz.push_back(y); out.xyz.push_back(z);
+        }
+        float bf = 0.f;
+        for (size_t a = i; a < j; a++)
+            if (!strcmp(atoms[a].name, "CA")) { bf = atoms[a].b; break; }
+        out.bfactor.push_back(bf);
+        i = j;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ reader
+
+DbReader::~DbReader() {
+    if (base_) munmap((void*)base_, bytes_);
+    if (fd_ >= 0) ::close(fd_);
+}
+
+static bool read_file(const std::string& path, std::string& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char buf[1 << 16];
+    size_t k;
+    out.clear();
+    while ((k = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, k);
+    fclose(f);
+    return true;
+}
+
+bool DbReader::open(const std::string& path) {
+    std::string idx;
+    if (!read_file(path + ".index", idx)) return false;
+    const char* p = idx.c_str();
+    while (*p) {
+        char* e;
+        const unsigned long k = strtoul(p, &e, 10);
+        if (e == p) break;
+        const unsigned long long off = strtoull(e, &e, 10), ln = strtoull(e, &e, 10);
+        keys_.push_back((uint32_t)k); offsets_.push_back(off); lengths_.push_back(ln);
+        p = e;
+        while (*p == '\n' || *p == '\r' || *p == ' ' || *p == '\t') p++;
+    }
+    fd_ = ::open(path.c_str(), O_RDONLY);
+    if (fd_ < 0) return false;
+    struct stat st;
+    if (fstat(fd_, &st) != 0) return false;
+    bytes_ = (size_t)st.st_size;
+    if (bytes_) {
+        void* m = mmap(nullptr, bytes_, PROT_READ, MAP_PRIVATE, fd_, 0);
+        if (m == MAP_FAILED) return false;
+        base_ = (const char*)m;
+    }
+    for (size_t i = 0; i < keys_.size(); i++)
+        if (offsets_[i] + lengths_[i] > bytes_) return false;
+    std::string lk;
+    if (read_file(path + ".lookup", lk)) {
+        names_.assign(keys_.size(), std::string());
+        std::vector<std::pair<uint32_t, std::string>> rows;
+        size_t a = 0;
+        while (a < lk.size()) {
+            size_t b = lk.find('\n', a);
+            if (b == std::string::npos) b = lk.size();
+            const size_t t1 = lk.find('\t', a);
+            if (t1 != std::string::npos && t1 < b) {
+                size_t t2 = lk.find('\t', t1 + 1);
+                if (t2 == std::string::npos || t2 > b) t2 = b;
+                rows.emplace_back((uint32_t)strtoul(lk.c_str() + a, nullptr, 10), lk.substr(t1 + 1, t2 - t1 - 1));
+            }
+            a = b + 1;
+        }
+        std::sort(rows.begin(), rows.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+        for (size_t i = 0; i < keys_.size(); i++) {
+            auto it = std::lower_bound(rows.begin(), rows.end(), keys_[i], [](const auto& x, uint32_t k) { return x.first < k; });
+            if (it != rows.end() && it->first == keys_[i]) names_[i] = it->second;
+        }
+    }
+    return true;
+}
+
+uint64_t DbReader::payload(size_t i) const {
+    const uint64_t n = lengths_[i];
+    return (n && base_[offsets_[i] + n - 1] == 0) ? n - 1 : n;
+}
+
+std::string DbReader::name(size_t i) const {
+    if (i < names_.size() && !names_[i].empty()) return names_[i];
+    return std::to_string(keys_[i]);
+}
+
+// ------------------------------------------------------------------------------------------ writer
+
+bool DbWriter::open(const std::string& path) {
+    path_ = path;
+    data_ = fopen(path.c_str(), "wb");
+    if (!data_) return false;
+    FILE* t = fopen((path + ".dbtype").c_str(), "wb");
+    if (!t) return false;
+    const int type = 12;  // generic dbtype, src/database_writer.cpp:51-55
+    fwrite(&type, sizeof type, 1, t);
+    fclose(t);
+    pos_ = 0;
+    return true;
+}
+
+bool DbWriter::append(const char* data, size_t len, uint32_t key, const std::string& name) {
+    if (!data_) return false;
+    if (len && fwrite(data, 1, len, data_) != len) return false;
+    const char nul = 0;
+    if (fwrite(&nul, 1, 1, data_) != 1) return false;
+    names_.push_back(name);
+    entries_.push_back({key, pos_, (uint64_t)len + 1, names_.size() - 1});
+    pos_ += len + 1;
+    return true;
+}
+
+bool DbWriter::close() {
+    if (!data_) return true;
+    fclose(data_);
+    data_ = nullptr;
+    std::stable_sort(entries_.begin(), entries_.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
+    FILE* idx = fopen((path_ + ".index").c_str(), "w");
+    FILE* lk = fopen((path_ + ".lookup").c_str(), "w");
+    if (!idx || !lk) return false;
+    for (const Entry& e : entries_) {
+        fprintf(idx, "%u\t%llu\t%llu\n", e.key, (unsigned long long)e.offset, (unsigned long long)e.length);
+        fprintf(lk, "%u\t%s\t0\n", e.key, names_[e.name].c_str());
+    }
+    fclose(idx);
+    fclose(lk);
+    entries_.clear();
+    return true;
+}
+
+// ------------------------------------------------------------------------------------- whole-db passes
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static std::string strip_ext(const std::string& n) {
+    const size_t d = n.find_last_of('.');
+    return d == std::string::npos ? n : n.substr(0, d);
+}
+
+int decompressDb(Engine& eng, const std::string& in_db, const std::string& out_db, bool altOrder, DbStats* stats) {
+    const double t0 = now_s();
+    DbReader rd;
+    if (!rd.open(in_db)) return FCZ_E_ARG;
+    DbWriter wr;
+    if (!wr.open(out_db)) return FCZ_E_ARG;
+    DbStats s;
+    fcz_opts o{25, altOrder ? 1 : 0, nullptr};
+    int rc = fcz_engine_set_opts(eng.get(), &o);
+    if (rc) return rc;
+    const size_t n_all = rd.size();
+    const uint64_t kBatchBytes = 16ull << 20;  // ~16 MB of FCZ per engine call (~650 MB of text)
+    std::vector<uint8_t> bytes;
+    std::vector<uint64_t> blob_off, text_off;
+    std::vector<int32_t> status;
+    std::vector<char> text;
+    size_t i0 = 0;
+    while (i0 < n_all) {
+        size_t i1 = i0;
+        uint64_t sum = 0;
+        while (i1 < n_all && (i1 == i0 || sum + rd.length(i1) <= kBatchBytes)) sum += rd.length(i1++);
+        const uint32_t n = (uint32_t)(i1 - i0);
+        blob_off.assign(n + 1, 0);
+        for (uint32_t c = 0; c < n; c++) blob_off[c + 1] = blob_off[c] + rd.length(i0 + c);
+        // entries of one database usually lie back to back: hand the mapped file to the engine as it is
+        bool contiguous = true;
+        for (uint32_t c = 0; c + 1 < n; c++) contiguous &= rd.offset(i0 + c) + rd.length(i0 + c) == rd.offset(i0 + c + 1);
+        const uint8_t* src = (const uint8_t*)rd.data(i0);
+        if (!contiguous) {
+            bytes.resize(blob_off[n] + 1);
+            for (uint32_t c = 0; c < n; c++) memcpy(bytes.data() + blob_off[c], rd.data(i0 + c), rd.length(i0 + c));
+            src = bytes.data();
+        }
+        fcz_blob_batch in{};
+        in.n_chains = n; in.mem = FCZ_MEM_HOST; in.blob_off = blob_off.data(); in.bytes = const_cast<uint8_t*>(src);
+        text_off.assign(n + 1, 0);
+        status.assign(n + 1, 0);
+        fcz_text_batch out{};
+        out.n_chains = n; out.mem = FCZ_MEM_HOST; out.text_off = text_off.data(); out.status = status.data();
+        uint64_t total = 0;
+        const double g0 = now_s();
+        if ((rc = fcz_decode_to_pdb_plan(eng.get(), &in, &out, &total))) return rc;
+        if (text.size() < total + 1) text.resize(total + 1);
+        out.bytes = text.data(); out.bytes_cap = text.size();
+        if ((rc = fcz_decode_to_pdb_batch(eng.get(), &in, &out))) return rc;
+        s.seconds_engine += now_s() - g0;
+        for (uint32_t c = 0; c < n; c++) {
+            s.entries++;
+            s.bytes_in += rd.length(i0 + c);
+            if (status[c] != FCZ_OK) { s.failed++; continue; }
+            const uint64_t tl = text_off[c + 1] - text_off[c];
+            const uint8_t* b = src + blob_off[c];
+            s.residues += (uint64_t)b[4] | (uint64_t)b[5] << 8;  // CompressedFileHeader.nResidue
+            s.bytes_out += tl;
+            if (!wr.append(text.data() + text_off[c], tl, rd.key(i0 + c), strip_ext(rd.name(i0 + c)) + ".pdb")) return FCZ_E_ARG;
+        }
+        i0 = i1;
+    }
+    if (!wr.close()) return FCZ_E_ARG;
+    s.seconds = now_s() - t0;
+    if (stats) *stats = s;
+    return FCZ_OK;
+}
+
+int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db, int anchorThreshold, DbStats* stats) {
+    const double t0 = now_s();
+    DbReader rd;
+    if (!rd.open(in_db)) return FCZ_E_ARG;
+    DbWriter wr;
+    if (!wr.open(out_db)) return FCZ_E_ARG;
+    DbStats s;
+    const size_t n_all = rd.size();
+    const uint64_t kBatchBytes = 512ull << 20;  // PDB text per engine call (~80 MB of coordinates)
+    size_t i0 = 0;
+    while (i0 < n_all) {
+        size_t i1 = i0;
+        uint64_t sum = 0;
+        while (i1 < n_all && (i1 == i0 || sum + rd.length(i1) <= kBatchBytes)) sum += rd.length(i1++);
+        const size_t n = i1 - i0;
+        std::vector<CanonicalChain> chains(n);
+        std::vector<int> flag(n, 0);
+#pragma omp parallel for schedule(dynamic, 8)
+        for (size_t c = 0; c < n; c++)
+            flag[c] = parsePdbChain(rd.data(i0 + c), rd.payload(i0 + c), strip_ext(rd.name(i0 + c)), chains[c]);
+        std::vector<CanonicalChain> good;
+        std::vector<size_t> which;
+        for (size_t c = 0; c < n; c++) {
+            s.entries++;
+            s.bytes_in += rd.length(i0 + c);
+            if (flag[c] == 0) { good.push_back(std::move(chains[c])); which.push_back(c); }
+            else s.failed++;
+        }
+        std::vector<std::string> blobs;
+        std::vector<int> st;
+        const double g0 = now_s();
+        int rc = FoldcompGpu::compressBatch(eng, good, anchorThreshold, blobs, st);
+        s.seconds_engine += now_s() - g0;
+        if (rc) return rc;
+        for (size_t g = 0; g < good.size(); g++) {
+            if (st[g] != FCZ_OK) { s.failed++; continue; }
+            s.residues += good[g].res_type.size();
+            s.bytes_out += blobs[g].size();
+            const size_t c = which[g];
+            if (!wr.append(blobs[g].data(), blobs[g].size(), rd.key(i0 + c), strip_ext(rd.name(i0 + c)) + ".fcz")) return FCZ_E_ARG;
+        }
+        i0 = i1;
+    }
+    if (!wr.close()) return FCZ_E_ARG;
+    s.seconds = now_s() - t0;
+    if (stats) *stats = s;
+    return FCZ_OK;
+}
+
+}  // namespace fczgpu
+
+using namespace fczgpu;
+
+extern "C" int fczgpu_parse_pdb(const char* text, size_t len, uint8_t* res_type, float* bfactor, float* xyz, fcz_chain_meta* meta,
+                                uint32_t* n_res, uint32_t* n_atoms, uint32_t cap_res, uint32_t cap_atoms) {
+    CanonicalChain c;
+    const int flag = parsePdbChain(text, len, "", c);
+    if (flag) return flag;
+    *n_res = (uint32_t)c.res_type.size();
+    *n_atoms = (uint32_t)(c.xyz.size() / 3);
+    if (*n_res > cap_res || *n_atoms > cap_atoms) return -1;
+    memcpy(res_type, c.res_type.data(), c.res_type.size());
+    memcpy(bfactor, c.bfactor.data(), 4 * c.bfactor.size());
+    memcpy(xyz, c.xyz.data(), 4 * c.xyz.size());
+    *meta = c.meta;
+    return 0;
+}
+
+static void put_stats(const DbStats& s, double* o) {
+    if (!o) return;
+    o[0] = (double)s.entries; o[1] = (double)s.failed; o[2] = (double)s.residues; o[3] = (double)s.bytes_in; o[4] = (double)s.bytes_out;
+    o[5] = s.seconds; o[6] = s.seconds_engine;
+}
+extern "C" int fczgpu_decompress_db(int device, const char* in_db, const char* out_db, int alt_order, double* stats7) {
+    try {
+        Engine eng(device);
+        DbStats s;
+        const int rc = decompressDb(eng, in_db, out_db, alt_order != 0, &s);
+        put_stats(s, stats7);
+        return rc;
+    } catch (const std::exception&) {
+        return FCZ_E_CUDA;
+    }
+}
+extern "C" int fczgpu_compress_db(int device, const char* in_db, const char* out_db, int anchor_threshold, double* stats7) {
+    try {
+        Engine eng(device);
+        DbStats s;
+        const int rc = compressDb(eng, in_db, out_db, anchor_threshold, &s);
+        put_stats(s, stats7);
+        return rc;
+    } catch (const std::exception&) {
+        return FCZ_E_CUDA;
+    }
+}
+
+// small hooks for bindings and tests
+extern "C" float fczgpu_parse_float(const char* s, size_t n) { return parseFixedFloat(s, n); }
+// read a database with DbReader and rewrite it with DbWriter (payloads kept, entries NUL-terminated, sorted by key)
+extern "C" int fczgpu_db_copy(const char* in_db, const char* out_db) {
+    DbReader rd;
+    if (!rd.open(in_db)) return FCZ_E_ARG;
+    DbWriter wr;
+    if (!wr.open(out_db)) return FCZ_E_ARG;
+    for (size_t i = 0; i < rd.size(); i++)
+        if (!wr.append(rd.data(i), rd.payload(i), rd.key(i), rd.name(i))) return FCZ_E_ARG;
+    return wr.close() ? (int)rd.size() : FCZ_E_ARG;
+}

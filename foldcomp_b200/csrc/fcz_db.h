@@ -1,0 +1,100 @@
+// foldcomp_b200/csrc/fcz_db.h -- host side of the batch path: a fixed-column ATOM
+// parser straight to the canonical slot layout, a foldcomp-db reader/writer, and whole-database compress /
+// decompress passes that feed the GPU engine with BATCHES of entries instead of one entry per OpenMP task.
+//
+// Reference pieces these stand in for:
+//   parsePdbChain   foldcomp/foldcomp.cxx:253-293 (fixed-column ATOM records, flag 1 = no ATOM line, flag 2 =
+//                   several chains) + removeAlternativePosition src/atom_coordinate.cpp:362-370 + the by-name atom
+//                   lookup of the encoder (see canonicalize() in foldcomp_gpu.h)
+//   DbReader        src/database_reader.cpp (index "key\toffset\tlength", lookup "key\tname\tfile", mmap'ed data)
+//   DbWriter        src/database_writer.cpp:36-96 (data + .index + .lookup + .dbtype, entries sorted by key on
+//                   close); entries are NUL-terminated (mmseqs convention)
+//   compressDb / decompressDb   the per-entry lambdas of src/main.cpp:438-536 / 612-689 under Processor::run
+//                   (src/input_processor.h:200-300), re-cut as batches over fcz_encode_batch / fcz_decode_to_pdb_*
+// Host code only; no arithmetic of the codec lives here.
+#ifndef FCZ_DB_H
+#define FCZ_DB_H
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "foldcomp_gpu.h"
+
+namespace fczgpu {
+
+// One single-chain PDB text -> canonical chain.  Returns 0, or the reference's flags: 1 no ATOM line, 2 more than
+// one chain; 3 = an ATOM line too short to hold its columns (the reference throws std::out_of_range there).
+int parsePdbChain(const char* text, size_t len, const std::string& title, CanonicalChain& out);
+
+// the reference's strtof-based field parse, with a certified fast path for plain fixed-point fields
+float parseFixedFloat(const char* s, size_t n);
+
+class DbReader {
+public:
+    DbReader() = default;
+    ~DbReader();
+    DbReader(const DbReader&) = delete;
+    DbReader& operator=(const DbReader&) = delete;
+    // data file `path`, index `path`.index, names from `path`.lookup when present.  Returns false on error.
+    bool open(const std::string& path);
+    size_t size() const { return keys_.size(); }
+    uint32_t key(size_t i) const { return keys_[i]; }
+    const char* data(size_t i) const { return base_ + offsets_[i]; }
+    uint64_t offset(size_t i) const { return offsets_[i]; }
+    uint64_t length(size_t i) const { return lengths_[i]; }  // as stored in the index (includes the trailing NUL if any)
+    // payload length: the index length minus one trailing NUL byte when the entry ends with one
+    uint64_t payload(size_t i) const;
+    std::string name(size_t i) const;
+
+private:
+    int fd_ = -1;
+    const char* base_ = nullptr;
+    size_t bytes_ = 0;
+    std::vector<uint32_t> keys_;
+    std::vector<uint64_t> offsets_, lengths_;
+    std::vector<std::string> names_;  // by entry, empty when there is no lookup file
+};
+
+class DbWriter {
+public:
+    DbWriter() = default;
+    ~DbWriter() { close(); }
+    bool open(const std::string& path);
+    // appends data + a NUL terminator; the index records length + 1
+    bool append(const char* data, size_t len, uint32_t key, const std::string& name);
+    bool close();  // writes .index / .lookup sorted by key (stable)
+
+private:
+    struct Entry { uint32_t key; uint64_t offset, length; size_t name; };
+    FILE* data_ = nullptr;
+    std::string path_;
+    uint64_t pos_ = 0;
+    std::vector<Entry> entries_;
+    std::vector<std::string> names_;
+};
+
+struct DbStats {
+    size_t entries = 0, failed = 0;
+    uint64_t residues = 0, bytes_in = 0, bytes_out = 0;
+    double seconds = 0, seconds_engine = 0;
+};
+
+// FCZ database -> PDB-text database (`foldcomp decompress --db`), entry names + ".pdb" like src/main.cpp:640-652
+int decompressDb(Engine& eng, const std::string& in_db, const std::string& out_db, bool altOrder, DbStats* stats);
+// PDB-text database -> FCZ database (`foldcomp compress --db`), titles = entry names without extension
+int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db, int anchorThreshold, DbStats* stats);
+
+}  // namespace fczgpu
+
+// C entry points over the above for bindings and tests (ctypes)
+extern "C" {
+// parse one PDB text; arrays must hold cap_res residues / cap_atoms atoms.  Returns the parser's flag, or -1 if too small.
+int fczgpu_parse_pdb(const char* text, size_t len, uint8_t* res_type, float* bfactor, float* xyz, fcz_chain_meta* meta,
+                     uint32_t* n_res, uint32_t* n_atoms, uint32_t cap_res, uint32_t cap_atoms);
+float fczgpu_parse_float(const char* s, size_t n);
+int fczgpu_db_copy(const char* in_db, const char* out_db);
+int fczgpu_decompress_db(int device, const char* in_db, const char* out_db, int alt_order, double* stats7);
+int fczgpu_compress_db(int device, const char* in_db, const char* out_db, int anchor_threshold, double* stats7);
+}
+#endif

@@ -201,6 +201,24 @@ int FoldcompGpu::read(std::istream& is) {
     return 0;
 }
 
+int FoldcompGpu::decompressToPdb(std::string& text) {
+    uint64_t blob_off[2] = {0, blob_.size()}, text_off[2] = {0, 0};
+    int32_t st[2] = {0, 0};
+    fcz_blob_batch in{};
+    in.n_chains = 1; in.mem = FCZ_MEM_HOST; in.blob_off = blob_off; in.bytes = (uint8_t*)&blob_[0];
+    fcz_text_batch out{};
+    out.n_chains = 1; out.mem = FCZ_MEM_HOST; out.text_off = text_off; out.status = st;
+    fcz_opts o{anchorThreshold, useAltAtomOrder ? 1 : 0, nullptr};
+    int rc = fcz_engine_set_opts(eng_.get(), &o);
+    if (rc) return rc;
+    uint64_t total = 0;
+    if ((rc = fcz_decode_to_pdb_plan(eng_.get(), &in, &out, &total))) return rc;
+    if (st[0]) return st[0];
+    text.assign(total, '\0');
+    out.bytes = &text[0]; out.bytes_cap = total;
+    return fcz_decode_to_pdb_batch(eng_.get(), &in, &out);
+}
+
 int FoldcompGpu::decompress(std::vector<AtomCoordinate>& atoms) {
     std::vector<CanonicalChain> ch;
     std::vector<int> st;

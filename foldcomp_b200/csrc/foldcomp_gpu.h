@@ -77,6 +77,8 @@ public:
     size_t getSize() const { return blob_.size(); }
     int read(std::istream& is);                               // 0 ok, -1 bad magic (src/foldcomp.cpp:911-915)
     int decompress(std::vector<AtomCoordinate>& atoms);       // 0 ok
+    // decompress + writeAtomCoordinatesToPDB (src/atom_coordinate.cpp:220-291) in one engine call: the PDB text
+    int decompressToPdb(std::string& text);
     const std::string& blob() const { return blob_; }
 
     // many chains per call

@@ -1,0 +1,99 @@
+"""Host side of the batch path (foldcomp_b200/csrc/fcz_db.{h,cpp}) -- no GPU:
+the fixed-column ATOM parser against the reference's CPython module (oracle/_ref/pyref, foldcomp/foldcomp.cxx:253-293)
+and the Python mirror in pdbio.py; the certified float-field fast path against strtof; the database reader/writer
+against plain-Python files and the reference's own reader."""
+import ctypes as C
+import ctypes.util
+import os
+
+import numpy as np
+import pytest
+
+import dbutil
+import helpers as H
+from foldcomp_b200 import abi, pdbio, synth
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return dbutil.gpu_host_lib()
+
+
+def cxx_parse(lib, text: bytes, title: str = "t"):
+    cap_r, cap_a = 70000, 70000 * 14
+    rt, bf, xyz = np.zeros(cap_r, np.uint8), np.zeros(cap_r, np.float32), np.zeros((cap_a, 3), np.float32)
+    meta = np.zeros(1, abi.META_DTYPE)
+    nr, na = C.c_uint32(), C.c_uint32()
+    flag = lib.fczgpu_parse_pdb(text, len(text), rt.ctypes.data, bf.ctypes.data, xyz.ctypes.data, meta.ctypes.data, C.byref(nr), C.byref(na), cap_r, cap_a)
+    if flag:
+        return flag
+    return abi.concat_chains([(rt[: nr.value], bf[: nr.value], xyz[: na.value], np.frombuffer(title.encode(), np.uint8), meta)])
+
+
+def _texts(golden):
+    out = [(n, H.oracle_format_pdb(golden.batch, c)) for c, n in enumerate(golden.names)]
+    b = synth.generate(6, np.array([2, 3, 17, 90, 350, 700]), seed=12)
+    out += [(f"syn{c}", H.oracle_format_pdb(b, c)) for c in range(b.n_chains)]
+    return out
+
+
+def test_parser_matches_python_mirror_and_reference_module(lib, golden):
+    ref = dbutil.reference_module()
+    for name, text in _texts(golden):
+        # noise the reference's parser skips or resolves: other record types, an alternate location, CRLF-free short lines
+        lines = text.split(b"\n")
+        atom_i = [i for i, l in enumerate(lines) if l.startswith(b"ATOM")]
+        noisy = lines[: atom_i[3]] + [lines[atom_i[2]].replace(b"  1.00", b"  0.50")] + lines[atom_i[3] :]
+        noisy = [b"HEADER    something", b"REMARK 1"] + noisy + [b"HETATM 9999  O   HOH A 999       1.000   2.000   3.000  1.00 20.00           O  ", b"END"]
+        for t in (text, b"\n".join(noisy)):
+            got = cxx_parse(lib, t, "x")
+            want = pdbio.parse_pdb_chain(t.decode("latin-1"), "x")
+            assert np.array_equal(got.res_type, want.res_type) and np.array_equal(got.xyz, want.xyz)
+            assert np.array_equal(got.bfactor, want.bfactor) and got.meta.tobytes() == want.meta.tobytes()
+            if ref is not None:
+                for b in (25, 200):
+                    theirs = ref.compress("x", t.decode("latin-1"), anchor_residue_threshold=b)
+                    assert H.masked(H.oracle_encode(got, 0, b)) == H.masked(theirs), (name, b)
+
+
+def test_parser_flags(lib):
+    assert cxx_parse(lib, b"HEADER x\nREMARK\n") == 1  # no ATOM line (foldcomp.cxx:288-290)
+    b = synth.generate(1, 5, seed=1)
+    text = H.oracle_format_pdb(b, 0)
+    two = text.replace(b" A   4 ", b" B   4 ")
+    assert cxx_parse(lib, two) == 2  # multiple chains (foldcomp.cxx:266-268)
+    assert cxx_parse(lib, text[:200] + b"\nATOM      9  N   GLY A\n") == 3  # a truncated ATOM record (the reference throws)
+
+
+def test_float_field_fast_path_is_strtof(lib):
+    libc = C.CDLL(ctypes.util.find_library("c"))
+    libc.strtof.restype = C.c_float
+    libc.strtof.argtypes = [C.c_char_p, C.c_void_p]
+    rng = np.random.default_rng(0)
+    fields = [b"   0.000", b"  -0.000", b"9999.999", b"-999.999", b"  12.5  ", b"1.5e3   ", b" .5     ", b"     nan", b"  +3.250", b"1234567.", b"16777217", b"99999999", b"0.000001"]
+    for _ in range(200000):
+        w = int(rng.integers(1, 9))
+        v = rng.uniform(-10 ** min(w, 4), 10 ** min(w, 5))
+        fields.append((b"%8.3f" % v)[:8] if rng.random() < 0.8 else (b"%8.*f" % (int(rng.integers(0, 7)), v))[:8])
+    for f in fields:
+        a, b = lib.fczgpu_parse_float(f, len(f)), libc.strtof(f, None)
+        assert (a == b) or (a != a and b != b), (f, a, b)
+
+
+def test_db_reader_writer_roundtrip(lib, golden, tmp_path):
+    entries = [(k, f"name_{k}.fcz", golden.db_blobs[i]) for i, k in enumerate([7, 3, 11, 0, 5])]
+    src = str(tmp_path / "src_db")
+    dbutil.write_db(src, entries, nul=False)  # `compress --db` of the reference writes no terminator
+    dst = str(tmp_path / "dst_db")
+    assert lib.fczgpu_db_copy(src.encode(), dst.encode()) == len(entries)
+    got = dbutil.read_db(dst)
+    assert got == sorted(entries)  # sorted by key on close; payloads intact; names kept
+    raw = open(dst, "rb").read()
+    assert sum(len(e[2]) + 1 for e in entries) == len(raw)  # every entry NUL-terminated
+    ref = dbutil.reference_module()
+    if ref is not None:  # the reference's own reader opens what we wrote and decodes every entry
+        with ref.open(dst) as db:
+            assert len(db) == len(entries)
+            for i, (k, name, blob) in enumerate(sorted(entries)):
+                n, pdb = db[i]
+                assert pdb == ref.decompress(blob)[1]

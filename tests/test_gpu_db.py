@@ -1,0 +1,87 @@
+"""Whole-database passes (foldcomp_b200/csrc/fcz_db.cpp: compressDb / decompressDb, the batched form of the
+per-entry lambdas of src/main.cpp:438-536 / 612-689) on the GPU, checked entry by entry against the oracle and --
+when oracle/_ref/pyref is present -- against the reference's own CPython module and database reader."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import dbutil
+import helpers as H
+from foldcomp_b200 import pdbio, synth
+from foldcomp_b200.abi import HostBlobBatch
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(H.ROOT, "foldcomp_b200", "csrc", "fcz_cli")
+
+
+def test_decompress_db_matches_engine_and_oracle(engine, golden, tmp_path):
+    lib = dbutil.gpu_host_lib()
+    blobs = list(golden.db_blobs) + golden.blobs(25) + [b"garbage entry"]
+    keys = list(range(100, 100 + len(blobs)))[::-1]  # written in descending key order: the writer must sort
+    entries = [(k, f"e{k}.fcz", b) for k, b in zip(keys, blobs)]
+    src, dst = str(tmp_path / "fcz_db"), str(tmp_path / "pdb_db")
+    dbutil.write_db(src, entries)
+    stats = (C.c_double * 7)()
+    assert lib.fczgpu_decompress_db(0, src.encode(), dst.encode(), 0, stats) == 0
+    assert int(stats[0]) == len(blobs) and int(stats[1]) == 1
+    got = dbutil.read_db(dst)
+    assert [g[0] for g in got] == sorted(keys)[1:]  # the garbage entry (largest key... first written) is dropped
+    dec = engine.decode_host(HostBlobBatch.from_blobs(blobs))
+    by_key = {k: c for c, k in enumerate(keys)}
+    ref = dbutil.reference_module()
+    for k, name, text in got:
+        c = by_key[k]
+        assert name == f"e{k}.pdb"
+        assert text == H.oracle_format_pdb(dec, c), k  # byte-identical to formatting the engine's decode
+        if ref is not None:  # the reference's text of its own decode: same records, coordinates within tolerance
+            theirs = ref.decompress(blobs[c])[1].encode("latin-1").split(b"\n")
+            ours = text.split(b"\n")
+            assert len(ours) == len(theirs)
+            for a, b in zip(ours, theirs):
+                assert a[:30] == b[:30] and a[54:] == b[54:], (k, a, b)
+                if a.startswith(b"ATOM"):
+                    assert max(abs(float(a[30 + 8 * j : 38 + 8 * j]) - float(b[30 + 8 * j : 38 + 8 * j])) for j in range(3)) <= 0.051
+
+
+def test_compress_db_matches_oracle_and_reference_module(engine, tmp_path):
+    lib = dbutil.gpu_host_lib()
+    lens = np.array([2, 5, 16, 33, 120, 350, 350, 900, 1400, 2100])
+    batch = synth.generate(len(lens), lens, seed=44)
+    texts = [H.oracle_format_pdb(batch, c) for c in range(batch.n_chains)]
+    entries = [(c, f"prot_{c}.pdb", t) for c, t in enumerate(texts)] + [(len(texts), "empty.pdb", b"HEADER nothing\n")]
+    src, dst = str(tmp_path / "pdb_db"), str(tmp_path / "fcz_db")
+    dbutil.write_db(src, entries)
+    stats = (C.c_double * 7)()
+    assert lib.fczgpu_compress_db(0, src.encode(), dst.encode(), 25, stats) == 0
+    assert int(stats[0]) == len(entries) and int(stats[1]) == 1 and int(stats[2]) == int(lens.sum())
+    got = dbutil.read_db(dst)
+    assert len(got) == len(texts)
+    ref = dbutil.reference_module()
+    for (k, name, blob), text in zip(got, texts):
+        assert name == f"prot_{k}.fcz"
+        parsed = pdbio.parse_pdb_chain(text.decode(), f"prot_{k}")
+        assert blob == H.oracle_encode(parsed, 0, 25), k
+        if ref is not None:
+            assert H.masked(blob) == H.masked(ref.compress(f"prot_{k}", text.decode())), k
+    if ref is not None:  # the reference's reader opens the database we wrote
+        with ref.open(dst) as db:
+            assert len(db) == len(texts)
+            n0, pdb0 = db[5]
+            back = pdbio.parse_pdb_chain(pdb0, "x")
+            assert np.abs(back.xyz - batch.chain(5).xyz).max() < 0.5
+
+
+def test_cli_db_subcommands(tmp_path, golden):
+    src = str(tmp_path / "in_db")
+    dbutil.write_db(src, [(i, f"d{i}.fcz", b) for i, b in enumerate(golden.db_blobs[:6])])
+    mid, back = str(tmp_path / "pdb_db"), str(tmp_path / "fcz_db")
+    subprocess.check_call([CLI, "decompress-db", src, mid])
+    subprocess.check_call([CLI, "compress-db", mid, back])
+    a, b = dbutil.read_db(src), dbutil.read_db(back)
+    assert [x[0] for x in a] == [x[0] for x in b] and [x[1] for x in a] == [x[1] for x in b]
+    for (_, _, x), (_, _, y) in zip(a, b):
+        dx, dy = H.oracle_decode(x), H.oracle_decode(y)
+        assert np.array_equal(dx.res_type, dy.res_type) and H.rmsd(dx.xyz, dy.xyz) < 0.2  # a second lossy generation
