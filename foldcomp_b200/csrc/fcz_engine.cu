@@ -969,6 +969,7 @@ struct PdbArgs {
     uint32_t* units;         // [n] plan output
     const uint64_t* text_off;  // [n+1] scans of the two
     const uint32_t* unit_off;
+    uint32_t* unit_chain;    // [total units] chain of every emit unit (k_pdb_unit_map)
     char* text;
     uint32_t unit0;          // first unit of this launch (host-memory batches emit in slabs)
 };
@@ -1009,18 +1010,19 @@ __global__ void __launch_bounds__(128) k_pdb_emit(PdbArgs a) {
     __shared__ __align__(16) char stage[FCZ_PDB_STAGE_BYTES];
     __shared__ uint32_t us[2 * FCZ_PDB_UNIT_RES + 2];
     const uint32_t u = a.unit0 + blockIdx.x;
-    // chain of this unit: last c with unit_off[c] <= u (every thread searches; the array is L2-resident)
-    uint32_t lo = 0, hi = a.n;
-    while (hi - lo > 1u) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(a.unit_off + mid) <= u) lo = mid; else hi = mid;
-    }
-    const uint32_t c = lo;
+    const uint32_t c = __ldg(a.unit_chain + u);
     DevCtx cx = block_ctx(nullptr);
     const PdbChain ch = pdb_chain(a, c);
     const uint32_t r_lo = (u - a.unit_off[c]) * FCZ_PDB_UNIT_RES;
     const uint32_t r_hi = r_lo + FCZ_PDB_UNIT_RES < ch.L ? r_lo + FCZ_PDB_UNIT_RES : ch.L;
     pdb_emit_unit(cx, a.tt, ch, r_lo, r_hi, a.text + a.text_off[c], stage, us);
+}
+
+// thread per chain: the chain index of each of its emit units (so that k_pdb_emit needs no search)
+__global__ void __launch_bounds__(256) k_pdb_unit_map(PdbArgs a) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n) return;
+    for (uint32_t u = a.unit_off[c]; u < a.unit_off[c + 1]; u++) a.unit_chain[u] = c;
 }
 
 struct ExtractArgs {
@@ -1167,7 +1169,7 @@ struct fcz_engine {
     Tables* d_tables = nullptr;
     TextTables* d_text_tables = nullptr;
     // text emitter (fcz_pdb_text_plan -> fcz_pdb_text_batch)
-    DevBuf ws_aoff, ws_toff, d_unit_off, d_text_off, d_text;
+    DevBuf ws_aoff, ws_toff, d_unit_off, d_unit_chain, d_text_off, d_text;
     struct PdbPlan { uint32_t n = 0; uint64_t total_bytes = 0; uint32_t total_units = 0; bool valid = false; } pdb;
     std::vector<uint32_t> h_unit_off;
     // plan scratch
@@ -1326,7 +1328,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->v3, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
-                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets, &e->enc_gws, &e->ws_aoff, &e->ws_toff, &e->d_unit_off, &e->d_text_off, &e->d_text,
+                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets, &e->enc_gws, &e->ws_aoff, &e->ws_toff, &e->d_unit_off, &e->d_unit_chain, &e->d_text_off, &e->d_text,
                       &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -1575,6 +1577,48 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
 // anyway) and processed in chunks so that the H2D copy of chunk k+1, the kernels of chunk k and the
 // D2H copy of chunk k-1 overlap on three streams (PCIe is full duplex; the kernels hide behind it).
 
+// Sum of table atom counts over L residue codes and whether any code has no table entry: the host-side twin of
+// k_enc_plan's per-residue loop.  32 residues per step with AVX2 (two 16-entry byte shuffles as the lookup table)
+// when the CPU has it; the planning of a host batch sits between its H2D copies and its kernels, so it is on the
+// end-to-end critical path.
+static void sum_natoms_scalar(const uint8_t* rt, uint32_t L, const uint8_t* lut, uint32_t* sum, uint32_t* bad) {
+    uint32_t s = 0, b = 0;
+    for (uint32_t r = 0; r < L; r++) { const uint32_t na = lut[rt[r]]; s += na; b |= (na == 0u); }
+    *sum += s; *bad |= b;
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void sum_natoms_avx2(const uint8_t* rt, uint32_t L, const uint8_t* lut, uint32_t* sum, uint32_t* bad) {
+    const __m128i lo128 = _mm_loadu_si128((const __m128i*)lut), hi128 = _mm_loadu_si128((const __m128i*)(lut + 16));
+    const __m256i lut_lo = _mm256_broadcastsi128_si256(lo128), lut_hi = _mm256_broadcastsi128_si256(hi128);
+    const __m256i m0f = _mm256_set1_epi8(0x0F), m10 = _mm256_set1_epi8(0x10), me0 = _mm256_set1_epi8((char)0xE0), zero = _mm256_setzero_si256();
+    __m256i acc = zero, anybad = zero;
+    uint32_t r = 0;
+    for (; r + 32u <= L; r += 32u) {
+        const __m256i v = _mm256_loadu_si256((const __m256i*)(rt + r));
+        const __m256i idx = _mm256_and_si256(v, m0f);
+        const __m256i is_hi = _mm256_cmpeq_epi8(_mm256_and_si256(v, m10), m10);
+        __m256i na = _mm256_blendv_epi8(_mm256_shuffle_epi8(lut_lo, idx), _mm256_shuffle_epi8(lut_hi, idx), is_hi);
+        const __m256i big = _mm256_cmpeq_epi8(_mm256_and_si256(v, me0), zero);  // 0xFF where the code is < 32
+        na = _mm256_and_si256(na, big);
+        anybad = _mm256_or_si256(anybad, _mm256_cmpeq_epi8(na, zero));
+        acc = _mm256_add_epi64(acc, _mm256_sad_epu8(na, zero));
+    }
+    uint64_t t[4];
+    _mm256_storeu_si256((__m256i*)t, acc);
+    *sum += (uint32_t)(t[0] + t[1] + t[2] + t[3]);
+    if (!_mm256_testz_si256(anybad, anybad)) *bad |= 1u;
+    sum_natoms_scalar(rt + r, L - r, lut, sum, bad);
+}
+#endif
+static void sum_natoms(const uint8_t* rt, uint32_t L, const uint8_t* lut, uint32_t* sum, uint32_t* bad) {
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool has_avx2 = __builtin_cpu_supports("avx2");
+    if (has_avx2) { sum_natoms_avx2(rt, L, lut, sum, bad); return; }
+#endif
+    sum_natoms_scalar(rt, L, lut, sum, bad);
+}
+
 static int host_pick_tier(const TierCfg* tiers, uint32_t L, uint64_t A, uint64_t blob, uint32_t nseg) {
     for (int i = 0; i < FCZ_NTIER; i++) {
         const TierCfg& t = tiers[i];
@@ -1689,7 +1733,7 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
         uint64_t size = 0;
         uint32_t sum = 0, bad = 0;
         const uint8_t* rt = in->res_type + r0;
-        for (uint32_t r = 0; r < L; r++) { const uint32_t na = nat_lut[rt[r]]; sum += na; bad |= (na == 0u); }
+        sum_natoms(rt, L, nat_lut, &sum, &bad);
         if (L < 2u || L > 65535u || b < 1) st = FCZ_E_LIMIT;
         else if (bad) st = FCZ_E_RESIDUE;
         else if ((uint64_t)sum != A) st = FCZ_E_ARG;
@@ -1813,6 +1857,7 @@ static void pdb_args(fcz_engine* e, const DevChains& d, uint32_t n, PdbArgs* a) 
     a->aoff = (uint32_t*)e->ws_aoff.p; a->toff = (uint32_t*)e->ws_toff.p;
     a->text_bytes = (uint32_t*)e->v0.p; a->units = (uint32_t*)e->v1.p;
     a->unit_off = (uint32_t*)e->d_unit_off.p;
+    a->unit_chain = (uint32_t*)e->d_unit_chain.p;
 }
 
 // plan over device-resident chains: fills d_text_off (device, [n+1]) and the engine's unit offsets; syncs; leaves the
@@ -1824,6 +1869,7 @@ static int pdb_plan_dev(fcz_engine* e, const DevChains& d, uint32_t n, uint64_t 
     if ((rc = ensure(e, e->ws_aoff, 4ull * (n_res_cap + n + 1)))) return rc;
     if ((rc = ensure(e, e->ws_toff, 4ull * (n_res_cap + n + 1)))) return rc;
     if ((rc = ensure(e, e->d_unit_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_unit_chain, 4ull * (n_res_cap / FCZ_PDB_UNIT_RES + n + 1)))) return rc;  // units <= residues/UNIT + chains
     PdbArgs a;
     pdb_args(e, d, n, &a);
     if (n) {
@@ -1837,6 +1883,10 @@ static int pdb_plan_dev(fcz_engine* e, const DevChains& d, uint32_t n, uint64_t 
     sa.in[0] = a.text_bytes; sa.out[0] = d_text_off; sa.out64[0] = 1;
     sa.in[1] = a.units; sa.out[1] = e->d_unit_off.p; sa.out64[1] = 0;
     if ((rc = run_scan(e, sa))) return rc;
+    if (n) {
+        k_pdb_unit_map<<<(n + 255) / 256, 256, 0, e->stream>>>(a);
+        e->launches++;
+    }
     if (host_text_off) {
         e->h_unit_off.resize((size_t)n + 1);
         CK(cudaMemcpyAsync(host_text_off, d_text_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));

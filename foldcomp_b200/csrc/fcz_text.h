@@ -328,8 +328,8 @@ FCZ_HD uint32_t put_title_lines(char* dst, const char* title, uint32_t T) {
 // Written against the same abstract execution context as fcz_codec.h (tid, nthr, sync(), excl_scan()): the CUDA
 // kernels instantiate them with a CTA, tests/emu/ with one host thread.
 
-#define FCZ_PDB_UNIT_RES 16u                                      // residues per emit unit (one CTA)
-#define FCZ_PDB_UNIT_ATOMS (FCZ_PDB_UNIT_RES * FCZ_MAX_ATOMS)     // 224 atoms at most
+#define FCZ_PDB_UNIT_RES 32u                                      // residues per emit unit (one CTA)
+#define FCZ_PDB_UNIT_ATOMS (FCZ_PDB_UNIT_RES * FCZ_MAX_ATOMS)     // 448 atoms at most
 #define FCZ_PDB_STAGE_BYTES (FCZ_PDB_UNIT_ATOMS * FCZ_PDB_LINE + 32u)
 
 struct PdbChain {
@@ -462,8 +462,11 @@ FCZ_HD void pdb_emit_unit(Ctx& cx, const TextTables* tt, const PdbChain& ch, uin
     char* s = stage + ((uintptr_t)g & 15u);
     for (uint32_t i = cx.tid; i < n; i += cx.nthr) {
         const uint32_t atom = a_lo + i;
-        uint32_t j = 0;
-        for (uint32_t q = 1; q < nr; q++) j += (us[q] <= atom) ? 1u : 0u;  // residue of this atom within the unit
+        uint32_t j = 0, hi = nr;  // residue of this atom within the unit: the last j with us[j] <= atom
+        while (hi - j > 1u) {
+            const uint32_t mid = (j + hi) >> 1;
+            if (us[mid] <= atom) j = mid; else hi = mid;
+        }
         const uint32_t r = r_lo + j, k = atom - us[j];
         const AtomRec a = pdb_atom_rec(tt, ch, r, k, atom);
         if (uniform) {

@@ -47,7 +47,7 @@ def test_pdb_text_of_decoded_goldens_matches_committed_reference_output(engine, 
 def test_pdb_text_mixed_lengths_and_extreme_fields(engine):
     rng = np.random.default_rng(8)
     lens = synth.mixed_lengths(rng, 300, lo=2, hi=1500)
-    lens[:6] = [2, 15, 16, 17, 32, 33]  # unit boundaries (16 residues per emit unit)
+    lens[:8] = [2, 15, 16, 31, 32, 33, 64, 65]  # unit boundaries (32 residues per emit unit)
     parts = [synth.generate(len(lens), lens, seed=81)] + [H.extreme_text_chain(s) for s in range(3)] + [H.long_chain(9000)]
     batch = abi.concat_batches(parts)
     # titles of every length around the continuation boundary, and an empty one

@@ -20,7 +20,7 @@ for ln in sec.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(\S.*?);", ln)
     if m and cur:
         line_of[int(m.group(1), 16)] = cur
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + __import__("os").environ.get("KNAME", ".*")], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]
