@@ -27,7 +27,7 @@ DEFAULT_ANCHOR_THRESHOLD = 25  # src/foldcomp.h:56
 
 
 class FczOpts(C.Structure):
-    _fields_ = [("anchor_threshold", C.c_int32), ("use_alt_atom_order", C.c_int32), ("stream", C.c_void_p)]
+    _fields_ = [("anchor_threshold", C.c_int32), ("use_alt_atom_order", C.c_int32), ("stream", C.c_void_p), ("terminate_blobs", C.c_int32)]
 
 
 class FczChainMeta(C.Structure):
@@ -309,7 +309,7 @@ class HostBlobBatch:
 def encode_bound(n_chains: int, n_res: int, n_atoms: int, n_title: int, anchor_threshold: int) -> int:
     """Same arithmetic as fcz_encode_bound (SURVEY.md Appendix A size formula)."""
     b = max(int(anchor_threshold), 1)
-    return 97 * n_chains + 40 * (n_res // b + 2 * n_chains) + n_title + 6 * n_res + n_atoms
+    return 98 * n_chains + 40 * (n_res // b + 2 * n_chains) + n_title + 6 * n_res + n_atoms
 
 
 @dataclass

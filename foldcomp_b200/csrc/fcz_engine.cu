@@ -264,6 +264,7 @@ struct EncArgs {
     const Tables* tables;
     int32_t b;
     TierCfg cfg;
+    uint32_t term;        // 1: one NUL byte follows every blob (fcz_opts.terminate_blobs)
     uint8_t* gws;         // k_encode_long: per-block workspace in global memory, gws_stride bytes each
     uint64_t gws_stride;
     uint32_t gws_max_res; // residues the workspace was sized for
@@ -293,7 +294,7 @@ __device__ __forceinline__ int pick_tier(const TierTable& tt, uint32_t L, uint32
 }
 
 __global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* atom_off, const uint32_t* title_off,
-                           const uint8_t* res_type, int32_t b, const Tables* tb, TierTable tt, PlanOut po) {
+                           const uint8_t* res_type, int32_t b, uint32_t term, const Tables* tb, TierTable tt, PlanOut po) {
     const uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= n) return;
@@ -323,7 +324,7 @@ __global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* 
         if (na > 255) status = FCZ_E_LIMIT;
         else {
             Layout y = make_layout(L, sum - 3u * L, T, (uint32_t)na);
-            size = y.size;
+            size = y.size + term;
             tier = pick_tier(tt, L, sum, size, (uint32_t)na - 1u);
             if (tier < 0) { status = FCZ_E_LIMIT; size = 0; }
         }
@@ -414,7 +415,9 @@ __global__ void __launch_bounds__(1024) k_encode(EncArgs a) {
         } else {
             encode_chain(cx, tb, ch);
         }
+        if (a.term && cx.tid == 0) (a.cfg.staged ? sB : gdst)[size - 1u] = 0;  // encode_chain ended with a barrier
         if (a.cfg.staged) {
+            if (a.term) __syncthreads();
             copy_out(cx, gdst, sB, size);
             cx.mark(4);
             cx.parity ^= 1u;
@@ -470,6 +473,7 @@ __global__ void __launch_bounds__(1024) k_encode_long(EncArgs a) {
         ch.type = a.res_type + r0;
         ch.B = a.bytes + a.blob_off[c];
         encode_chain(cx, tb, ch);
+        if (a.term && cx.tid == 0) ch.B[(uint32_t)(a.blob_off[c + 1] - a.blob_off[c]) - 1u] = 0;
         __syncthreads();
     }
 }
@@ -1255,6 +1259,7 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     e->opts.anchor_threshold = 25;
     e->opts.use_alt_atom_order = 0;
     e->opts.stream = nullptr;
+    e->opts.terminate_blobs = 0;
     if (opts) e->opts = *opts;
     if (e->opts.anchor_threshold < 1) e->opts.anchor_threshold = 25;
     if (cudaSetDevice(device) != cudaSuccess) { delete e; return nullptr; }
@@ -1358,6 +1363,7 @@ int fcz_engine_set_opts(fcz_engine* e, const fcz_opts* opts) {
     if (opts->anchor_threshold < 1) return fail(e, FCZ_E_ARG, "anchor_threshold must be >= 1");
     e->opts.anchor_threshold = opts->anchor_threshold;
     e->opts.use_alt_atom_order = opts->use_alt_atom_order;
+    e->opts.terminate_blobs = opts->terminate_blobs;
     if (opts->stream != e->opts.stream) {
         if (e->own_stream) {
             cudaStreamSynchronize(e->stream);
@@ -1377,7 +1383,7 @@ int fcz_engine_set_opts(fcz_engine* e, const fcz_opts* opts) {
 
 uint64_t fcz_encode_bound(uint64_t n_chains, uint64_t n_res, uint64_t n_atoms, uint64_t n_title_bytes, int32_t b) {
     if (b < 1) b = 1;
-    return 97ull * n_chains + 40ull * (n_res / (uint64_t)b + 2ull * n_chains) + n_title_bytes + 6ull * n_res + n_atoms;
+    return 98ull * n_chains + 40ull * (n_res / (uint64_t)b + 2ull * n_chains) + n_title_bytes + 6ull * n_res + n_atoms;  // 97 + a terminator
 }
 
 int fcz_engine_sync(fcz_engine* e) {
@@ -1528,7 +1534,7 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
     po.tier_list = (uint32_t*)e->tier_list.p;
     if (n) {
         k_enc_plan<<<(n + 7) / 8, 256, 0, e->stream>>>(n, in->res_off, in->atom_off, in->title_off, in->res_type,
-                                                       e->opts.anchor_threshold, e->d_tables, tt, po);
+                                                       e->opts.anchor_threshold, e->opts.terminate_blobs ? 1u : 0u, e->d_tables, tt, po);
         e->launches++;
     }
     ScanArgs sa;
@@ -1561,6 +1567,7 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
         a.ticket = e->d_counters + FCZ_NTIER + i;
         a.tables = e->d_tables;
         a.b = e->opts.anchor_threshold;
+        a.term = e->opts.terminate_blobs ? 1u : 0u;
         if ((rc = launch_encode(e, a, i, cnt, e->h_counters[2 * FCZ_NTIER], st))) return rc;
         if (fork) {
             CK(cudaEventRecord(e->ev_join[i], st));
@@ -1741,7 +1748,7 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
             const int na = anchor_count(L, b);
             if (na > 255) st = FCZ_E_LIMIT;
             else {
-                size = make_layout(L, sum - 3u * L, T, (uint32_t)na).size;
+                size = make_layout(L, sum - 3u * L, T, (uint32_t)na).size + (e->opts.terminate_blobs ? 1u : 0u);
                 const int t = host_pick_tier(e->enc_tier, L, sum, size, (uint32_t)na - 1u);
                 if (t < 0) { st = FCZ_E_LIMIT; size = 0; }
                 else {
@@ -1783,7 +1790,7 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
             a.list = (uint32_t*)e->d_list.p + ln.first;
             a.count = nullptr; a.count_val = ln.count;
             a.ticket = (uint32_t*)e->d_tickets.p + k * FCZ_NTIER + ln.tier;
-            a.tables = e->d_tables; a.b = b;
+            a.tables = e->d_tables; a.b = b; a.term = e->opts.terminate_blobs ? 1u : 0u;
             {
                 ProfSpan ps(e, FCZ_PROF_ENCODE);
                 if ((rc = launch_encode(e, a, (int)ln.tier, ln.count, long_max_res, e->stream))) return rc;

@@ -174,7 +174,7 @@ class Engine:
     def __init__(self, device: int = 0, anchor_threshold: int = abi.DEFAULT_ANCHOR_THRESHOLD, use_alt_atom_order: bool = False, stream=None):
         self.lib = load()
         self.device = int(device)
-        self._opts = FczOpts(int(anchor_threshold), int(bool(use_alt_atom_order)), None)
+        self._opts = FczOpts(int(anchor_threshold), int(bool(use_alt_atom_order)), None, 0)
         if stream is not None:
             self._opts.stream = stream.cuda_stream
         self._stream = stream
@@ -203,7 +203,9 @@ class Engine:
         if rc != abi.FCZ_OK:
             raise FczError(rc, (self.lib.fcz_last_error(self.h) or b"").decode() or self.lib.fcz_strerror(rc).decode())
 
-    def set_opts(self, anchor_threshold: int | None = None, use_alt_atom_order: bool | None = None):
+    def set_opts(self, anchor_threshold: int | None = None, use_alt_atom_order: bool | None = None, terminate_blobs: bool | None = None):
+        if terminate_blobs is not None:
+            self._opts.terminate_blobs = int(bool(terminate_blobs))
         if anchor_threshold is not None:
             self._opts.anchor_threshold = int(anchor_threshold)
         if use_alt_atom_order is not None:

@@ -59,6 +59,9 @@ typedef struct fcz_opts {
     int32_t anchor_threshold;   /* Foldcomp::anchorThreshold, CLI -b/--break; default 25 (src/foldcomp.h:56) */
     int32_t use_alt_atom_order; /* Foldcomp::useAltAtomOrder, CLI -a/--alt (decode only)          */
     void* stream;               /* cudaStream_t to enqueue on; NULL = engine-owned stream         */
+    int32_t terminate_blobs;    /* encode: one NUL byte after every blob (counted in blob_off), so that `bytes`
+                                   is a foldcomp-db data slab as it stands: entries NUL-terminated like
+                                   `decompress --db` and test/example_db (src/main.cpp:656-665) */
 } fcz_opts;
 
 /* Per-chain scalars that the reference keeps in Foldcomp members / CompressedFileHeader
@@ -109,7 +112,8 @@ void fcz_engine_destroy(fcz_engine* e);
 int fcz_engine_set_opts(fcz_engine* e, const fcz_opts* opts);
 
 /* Upper bound of the encoded size of a batch, from totals only (host arithmetic, no GPU work):
- * sum over chains of 97 + 40*nAnchor + lenTitle + 8*L + (atoms - 3*L) + L  (SURVEY.md Appendix A). */
+ * sum over chains of 97 + 40*nAnchor + lenTitle + 8*L + (atoms - 3*L) + L  (SURVEY.md Appendix A), plus one
+ * byte per chain for opts.terminate_blobs. */
 uint64_t fcz_encode_bound(uint64_t n_chains, uint64_t n_res, uint64_t n_atoms,
                           uint64_t n_title_bytes, int32_t anchor_threshold);
 

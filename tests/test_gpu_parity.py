@@ -360,3 +360,22 @@ def test_config3_542k_chain_db_decode(engine):
     assert rt_all <= 0.2, rt_all
     print(f"config3: {N_DB} chains, {n_res} residues decoded in {ms:.1f} ms wall ({n_res / ms / 1e6:.2f} G res/s incl. launch overheads); "
           f"all-atom round-trip RMSD vs input {rt_all:.3f} A")
+
+
+def test_terminated_blobs_are_a_db_slab(engine):
+    """opts.terminate_blobs: every blob is followed by one NUL that blob_off counts, so the output is a foldcomp-db
+    data slab as it stands; decode accepts the terminated entries unchanged."""
+    lens = np.array([2, 17, 64, 65, 350, 351, 1300, 3000])
+    batch = synth.generate(len(lens), lens, seed=88)
+    want = H.oracle_encode_batch(batch, 25)
+    engine.set_opts(terminate_blobs=True)
+    try:
+        got = engine.encode_host(batch)
+    finally:
+        engine.set_opts(terminate_blobs=False)
+    assert not got.status.any()
+    assert np.array_equal(np.diff(got.blob_off.astype(np.int64)), np.diff(want.blob_off.astype(np.int64)) + 1)
+    for c in range(batch.n_chains):
+        assert got.blob(c) == want.blob(c) + b"\0", c
+    dec = engine.decode_host(HostBlobBatch(got.blob_off, got.bytes))
+    _assert_decoded_close(dec, H.oracle_decode_batch(want))
