@@ -39,7 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_CHAINS, LENGTH, ANCHOR = 10000, 350, 25
-E2E_PARTS = int(os.environ.get("FCZ_E2E_PARTS", "4"))  # sub-batches per step on the end-to-end path
+E2E_PARTS = int(os.environ.get("FCZ_E2E_PARTS", "2"))  # sub-batches per step on the end-to-end path
 WORKLOAD_NOTE = ""
 METRIC = "residues/sec compress+decompress round-trip"
 UNIT = "residues/s"
@@ -337,8 +337,9 @@ def run_ours(args, rank, world, local_rank, out):
     # through in E2E_PARTS sub-batches on TWO engines driven by two host threads: one calls fcz_encode_batch,
     # the other fcz_decode_plan + fcz_decode_batch on the blobs the first produced, so the encode's H2D traffic
     # and the decode's D2H traffic share the full-duplex PCIe link (a compress job and a decompress job side
-    # by side, as the reference's CLI runs them under OpenMP).  Every step round-trips every chain; a blob
-    # buffer is reused only after its decode has finished.
+    # by side, as the reference's CLI runs them under OpenMP).  Every step round-trips every chain; the encode of one
+    # sub-batch (or of the next step's first one) runs while the previous one decodes, and a blob buffer is reused
+    # only after its decode has finished.
     import threading
 
     keep = []
@@ -366,23 +367,31 @@ def run_ours(args, rank, world, local_rank, out):
     bounds = [round(i * batch.n_chains / E2E_PARTS) for i in range(E2E_PARTS + 1)]
     parts = [batch.select(range(bounds[i], bounds[i + 1])) for i in range(E2E_PARTS)]
     h_in = [pinned_chain_batch(p) for p in parts]
-    h_blob = [pinned_blob_batch(p) for p in parts]
     h_out = [pinned_out_batch(p) for p in parts]
+    # blobs travel from the encode thread to the decode thread through a ring of at least two pinned buffers, so the
+    # encode of the next sub-batch (or of the next step's batch) never waits for the decode of the previous one
+    NB = max(2, E2E_PARTS)
+    big = max(parts, key=lambda p: p.n_atoms)
+    h_blob = [pinned_blob_batch(big) for _ in range(NB)]
     eng_enc = Engine(local_rank, anchor_threshold=ANCHOR)
     eng_dec = Engine(local_rank, anchor_threshold=ANCHOR)
 
+    def blob_view(slot, j):  # the ring slot, cut to sub-batch j's chain count
+        hb_, n_j = h_blob[slot], parts[j].n_chains
+        return HostBlobBatch(hb_.blob_off[: n_j + 1], hb_.bytes, hb_.status[:n_j])
+
     def e2e_run(steps):
-        ready = [threading.Semaphore(0) for _ in range(E2E_PARTS)]
-        free = [threading.Semaphore(1) for _ in range(E2E_PARTS)]
+        ready = [threading.Semaphore(0) for _ in range(NB)]
+        free = [threading.Semaphore(1) for _ in range(NB)]
         errs = []
 
         def enc_loop():
             try:
-                for _ in range(steps):
-                    for j in range(E2E_PARTS):
-                        free[j].acquire()
-                        eng_enc.encode_host(h_in[j], h_blob[j])
-                        ready[j].release()
+                for i in range(steps * E2E_PARTS):
+                    slot, j = i % NB, i % E2E_PARTS
+                    free[slot].acquire()
+                    eng_enc.encode_host(h_in[j], blob_view(slot, j))
+                    ready[slot].release()
             except Exception as ex:  # surface in the main thread
                 errs.append(ex)
                 for sem in ready:
@@ -390,13 +399,13 @@ def run_ours(args, rank, world, local_rank, out):
 
         def dec_loop():
             try:
-                for _ in range(steps):
-                    for j in range(E2E_PARTS):
-                        ready[j].acquire()
-                        if errs:
-                            return
-                        eng_dec.decode_host(h_blob[j], out=h_out[j])
-                        free[j].release()
+                for i in range(steps * E2E_PARTS):
+                    slot, j = i % NB, i % E2E_PARTS
+                    ready[slot].acquire()
+                    if errs:
+                        return
+                    eng_dec.decode_host(blob_view(slot, j), out=h_out[j])
+                    free[slot].release()
             except Exception as ex:
                 errs.append(ex)
                 for sem in free:

@@ -1643,11 +1643,13 @@ static cudaEvent_t pool_event(fcz_engine* e, size_t i) {
     return e->ev_pool[i];
 }
 
+#define FCZ_HOST_CHUNKS 32u  // chunks of a host-memory batch
+#define FCZ_H2D_DEPTH 2u     // input chunks queued ahead on the copy engine (see encode_host)
 // chain ranges of ~equal payload; chunk_c0 has nchunks+1 entries
 static void make_chunks(uint32_t n, const uint64_t* weight_prefix /* [n+1] */, std::vector<uint32_t>& chunk_c0) {
     const uint64_t total = weight_prefix[n] - weight_prefix[0];
-    uint32_t nchunks = (uint32_t)(total / (24ull << 20)) + 1u;  // ~24 MB of payload per chunk
-    if (nchunks > 16u) nchunks = 16u;
+    uint32_t nchunks = (uint32_t)(total / (12ull << 20)) + 1u;  // ~12 MB of payload per chunk
+    if (nchunks > FCZ_HOST_CHUNKS) nchunks = FCZ_HOST_CHUNKS;
     if (nchunks > n) nchunks = n ? n : 1u;
     chunk_c0.assign(1, 0u);
     uint32_t c = 0;
@@ -1695,14 +1697,16 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
     if ((rc = ensure(e, e->d_meta, sizeof(fcz_chain_meta) * (uint64_t)n + 16))) return rc;
     if ((rc = ensure(e, e->d_blob_off, 8ull * (n + 1)))) return rc;
     if ((rc = ensure(e, e->d_list, 4ull * n + 16))) return rc;
-    if ((rc = ensure(e, e->d_tickets, 4ull * 16 * FCZ_NTIER))) return rc;
+    if ((rc = ensure(e, e->d_tickets, 4ull * FCZ_HOST_CHUNKS * FCZ_NTIER))) return rc;
 
     fcz_engine::HostPlan plan;
     plan.n = n;
     make_chunks(n, in->atom_off, plan.chunk_c0);
     const uint32_t nchunks = (uint32_t)plan.chunk_c0.size() - 1u;
 
-    // 1. start moving the inputs (copy stream), chunk by chunk
+    // 1. start moving the inputs (copy stream), chunk by chunk.  Only FCZ_H2D_DEPTH chunks are queued ahead of the
+    // kernels: the H2D copy engine serves its queue in order, so a whole batch queued at once would hold up the
+    // small input copies of any other engine on the GPU (a decode running next to this encode) for milliseconds.
     size_t evi = 0;
     cudaEvent_t ev0 = pool_event(e, evi++);
     CK(cudaEventRecord(ev0, e->stream));
@@ -1713,7 +1717,8 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
     COPY(e->d_title_off.p, in->title_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
     COPY(e->d_meta.p, in->meta, sizeof(fcz_chain_meta) * (uint64_t)n, cudaMemcpyHostToDevice, e->s_in);
     std::vector<cudaEvent_t> ev_in(nchunks);
-    for (uint32_t k = 0; k < nchunks; k++) {
+    for (uint32_t k = 0; k < nchunks; k++) ev_in[k] = pool_event(e, evi++);
+    auto issue_chunk = [&](uint32_t k) -> int {
         const uint32_t c0 = plan.chunk_c0[k], c1 = plan.chunk_c0[k + 1];
         const uint64_t r0 = in->res_off[c0], r1 = in->res_off[c1], a0 = in->atom_off[c0], a1 = in->atom_off[c1];
         const uint64_t t0 = in->title_off[c0], t1 = in->title_off[c1];
@@ -1721,9 +1726,11 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
         COPY((float*)e->d_bfactor.p + r0, in->bfactor + r0, 4ull * (r1 - r0), cudaMemcpyHostToDevice, e->s_in);
         COPY((float*)e->d_xyz.p + 3ull * a0, in->xyz + 3ull * a0, 12ull * (a1 - a0), cudaMemcpyHostToDevice, e->s_in);
         COPY((char*)e->d_titles.p + t0, in->titles + t0, t1 - t0, cudaMemcpyHostToDevice, e->s_in);
-        ev_in[k] = pool_event(e, evi++);
         CK(cudaEventRecord(ev_in[k], e->s_in));
-    }
+        return FCZ_OK;
+    };
+    for (uint32_t k = 0; k < nchunks && k < FCZ_H2D_DEPTH; k++)
+        if ((rc = issue_chunk(k))) return rc;
 
     // 2. meanwhile plan on the host: validate (what k_enc_plan does on the device), sizes, offsets, tiers
     uint8_t nat_lut[256];
@@ -1773,12 +1780,16 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
     COPY(e->d_list.p, plan.list.data(), 4ull * plan.list.size(), cudaMemcpyHostToDevice, e->s_in);
     cudaEvent_t ev_plan = pool_event(e, evi++);
     CK(cudaEventRecord(ev_plan, e->s_in));
-    CK(cudaMemsetAsync(e->d_tickets.p, 0, 4ull * 16 * FCZ_NTIER, e->stream));
+    CK(cudaMemsetAsync(e->d_tickets.p, 0, 4ull * FCZ_HOST_CHUNKS * FCZ_NTIER, e->stream));
     CK(cudaStreamWaitEvent(e->stream, ev_plan, 0));
 
     // 3. kernels per chunk (main stream) and the blobs back (out stream)
     size_t li = 0;
     for (uint32_t k = 0; k < nchunks; k++) {
+        if (k + FCZ_H2D_DEPTH < nchunks) {  // chunk k has landed: queue the next one behind the one in flight
+            CK(cudaEventSynchronize(ev_in[k]));
+            if ((rc = issue_chunk(k + FCZ_H2D_DEPTH))) return rc;
+        }
         CK(cudaStreamWaitEvent(e->stream, ev_in[k], 0));
         for (; li < plan.launches.size() && plan.launches[li].chunk == k; li++) {
             const fcz_engine::Launch& ln = plan.launches[li];
