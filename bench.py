@@ -380,17 +380,22 @@ def run_ours(args, rank, world, local_rank, out):
         hb_, n_j = h_blob[slot], parts[j].n_chains
         return HostBlobBatch(hb_.blob_off[: n_j + 1], hb_.bytes, hb_.status[:n_j])
 
+    trace = []  # (leg, item, start, end) of every host call of the last run
+
     def e2e_run(steps):
         ready = [threading.Semaphore(0) for _ in range(NB)]
         free = [threading.Semaphore(1) for _ in range(NB)]
         errs = []
+        trace.clear()
 
         def enc_loop():
             try:
                 for i in range(steps * E2E_PARTS):
                     slot, j = i % NB, i % E2E_PARTS
                     free[slot].acquire()
+                    t_a = time.perf_counter()
                     eng_enc.encode_host(h_in[j], blob_view(slot, j))
+                    trace.append(("enc", i, t_a, time.perf_counter()))
                     ready[slot].release()
             except Exception as ex:  # surface in the main thread
                 errs.append(ex)
@@ -404,7 +409,9 @@ def run_ours(args, rank, world, local_rank, out):
                     ready[slot].acquire()
                     if errs:
                         return
+                    t_a = time.perf_counter()
                     eng_dec.decode_host(blob_view(slot, j), out=h_out[j])
+                    trace.append(("dec", i, t_a, time.perf_counter()))
                     free[slot].release()
             except Exception as ex:
                 errs.append(ex)
@@ -428,6 +435,10 @@ def run_ours(args, rank, world, local_rank, out):
     l1 = eng_enc.launch_count() + eng_dec.launch_count()
     dt_e = e2e_run(args.steps)
     e2e_launches = eng_enc.launch_count() + eng_dec.launch_count() - l1
+    if os.environ.get("FCZ_E2E_TRACE") and rank == 0:
+        t_base = min(t[2] for t in trace)
+        for leg, i, a, b in sorted(trace, key=lambda t: t[2])[: 6 * E2E_PARTS * 2]:
+            print(f"[e2e trace] {leg} item {i:3d}  {1e3 * (a - t_base):8.3f} -> {1e3 * (b - t_base):8.3f} ms  ({1e3 * (b - a):.3f} ms)", file=sys.stderr)
     barrier()
     ms_e = torch.tensor([dt_e * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:

@@ -1645,6 +1645,7 @@ static cudaEvent_t pool_event(fcz_engine* e, size_t i) {
 
 #define FCZ_HOST_CHUNKS 32u  // chunks of a host-memory batch
 #define FCZ_H2D_DEPTH 2u     // input chunks queued ahead on the copy engine (see encode_host)
+#define FCZ_DEC_H2D_PIECES 3u  // copies the blobs of a host-memory decode go up in (see decode_host)
 // chain ranges of ~equal payload; chunk_c0 has nchunks+1 entries
 static void make_chunks(uint32_t n, const uint64_t* weight_prefix /* [n+1] */, std::vector<uint32_t>& chunk_c0) {
     const uint64_t total = weight_prefix[n] - weight_prefix[0];
@@ -2273,12 +2274,20 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
     COPY(e->d_seg_off.p, plan.seg_off.data(), 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
     COPY(e->d_status.p, plan.status.data(), 4ull * n, cudaMemcpyHostToDevice, e->s_in);
     if (n) COPY(e->d_dec_list.p, plan.list.data(), 4ull * n, cudaMemcpyHostToDevice, e->s_in);
+    // The blobs are a seventh of the traffic of this call; they go up in at most FCZ_DEC_H2D_PIECES copies, not one per
+    // chunk: copies of one stream take turns with the copies of other engines on the H2D copy engine, so many small
+    // ones next to an encode's 12 MB chunks would each wait a full turn and stretch this call to the encode's length.
     std::vector<cudaEvent_t> ev_in(nchunks);
-    for (uint32_t k = 0; k < nchunks; k++) {
-        const uint64_t b0 = in->blob_off[plan.chunk_c0[k]], b1 = in->blob_off[plan.chunk_c0[k + 1]];
-        COPY((uint8_t*)e->d_bytes.p + b0, in->bytes + b0, b1 - b0, cudaMemcpyHostToDevice, e->s_in);
-        ev_in[k] = pool_event(e, evi++);
-        CK(cudaEventRecord(ev_in[k], e->s_in));
+    {
+        const uint32_t npieces = nchunks < FCZ_DEC_H2D_PIECES ? nchunks : FCZ_DEC_H2D_PIECES;
+        for (uint32_t p = 0; p < npieces; p++) {
+            const uint32_t k0 = (uint32_t)((uint64_t)nchunks * p / npieces), k1 = (uint32_t)((uint64_t)nchunks * (p + 1) / npieces);
+            const uint64_t b0 = in->blob_off[plan.chunk_c0[k0]], b1 = in->blob_off[plan.chunk_c0[k1]];
+            COPY((uint8_t*)e->d_bytes.p + b0, in->bytes + b0, b1 - b0, cudaMemcpyHostToDevice, e->s_in);
+            cudaEvent_t ev = pool_event(e, evi++);
+            CK(cudaEventRecord(ev, e->s_in));
+            for (uint32_t k = k0; k < k1; k++) ev_in[k] = ev;
+        }
     }
     TierTable tt;
     memset(&tt, 0, sizeof tt);
