@@ -39,7 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_CHAINS, LENGTH, ANCHOR = 10000, 350, 25
-E2E_PARTS = int(os.environ.get("FCZ_E2E_PARTS", "2"))  # sub-batches per step on the end-to-end path
+E2E_PARTS = int(os.environ.get("FCZ_E2E_PARTS", "4"))  # sub-batches per step on the end-to-end path
 WORKLOAD_NOTE = ""
 METRIC = "residues/sec compress+decompress round-trip"
 UNIT = "residues/s"

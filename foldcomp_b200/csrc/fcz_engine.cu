@@ -1153,6 +1153,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(ScanArgs a) {
 
 // ============================================================================================ engine
 
+#define FCZ_HOST_CHUNKS 32u  // chunks of a host-memory batch
+// Transfer shape of a host-memory batch, chosen from tools/e2e_sweep.py on a B200 (profiles/r01_v12_e2e_sweep.txt): two
+// engines (an encode next to a decode) reach 346 M residues/s with ONE coordinate copy per call of <= 96 MB, 305 M with
+// 12 MB chunks queued at once and 275-299 M with 12 MB chunks and a bounded queue.  Both knobs stay as environment
+// overrides (FCZ_CHUNK_MB, FCZ_H2D_QUEUE, FCZ_D2H_QUEUE); a depth of 0 queues every chunk at once.
+#define FCZ_CHUNK_BYTES (96ull << 20)
+#define FCZ_H2D_DEPTH 0u     // input chunks queued ahead on the copy engine (encode_host)
+#define FCZ_D2H_DEPTH 0u     // coordinate chunks queued ahead on the D2H copy engine (decode_host)
+#define FCZ_D2H_GROUP 4u     // encode: chunks whose blobs come back in one copy
+#define FCZ_DEC_H2D_PIECES 2u  // copies the blobs of a host-memory decode go up in (see decode_host)
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -1182,11 +1193,16 @@ struct fcz_engine {
     uint64_t* d_totals = nullptr;    // [3]
     uint32_t* h_counters = nullptr;  // pinned mirror
     uint64_t* h_totals = nullptr;
+    uint64_t chunk_bytes = FCZ_CHUNK_BYTES;  // coordinates per chunk of a host-memory batch (FCZ_CHUNK_MB)
+    uint32_t h2d_depth = FCZ_H2D_DEPTH, d2h_depth = FCZ_D2H_DEPTH;  // FCZ_H2D_QUEUE / FCZ_D2H_QUEUE, 0 = unlimited
     uint32_t dec_sub_res = FCZ_SUB_RESIDUES;  // residues per decode sub-batch (FCZ_DEC_SUB_RESIDUES overrides)
     uint32_t* h_bounds = nullptr;    // pinned: [0] nchunks, then chain / residue / segment-slot bounds of the decode sub-batches
     // staging for host-memory batches
     DevBuf d_res_off, d_atom_off, d_title_off, d_res_type, d_bfactor, d_xyz, d_titles, d_meta, d_blob_off, d_bytes, d_status;
-    DevBuf d_list, d_tickets, enc_gws;
+    DevBuf d_list, d_tickets, enc_gws, d_stage;
+    void* h_stage = nullptr;  // pinned staging for the per-chain arrays of a host-memory decode (one H2D copy)
+    size_t h_stage_cap = 0;
+    struct { uint64_t *blob_off, *atom_off; uint32_t *res_off, *title_off, *seg_off, *list; int32_t* status; } dh = {};
     DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax, d_dec_list;  // batch-wide decoder: segment offsets + L2-resident workspace
     // plan made on the host by fcz_decode_plan(host) for the following fcz_decode_batch(host)
     struct Launch { uint32_t chunk, tier, first, count; };
@@ -1294,6 +1310,9 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
         ok &= cudaFuncSetAttribute(k_dec_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         ok &= cudaFuncSetAttribute(k_dec_stitch_t, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
         if (const char* v = getenv("FCZ_DEC_SUB_RESIDUES")) { long q = atol(v); if (q > 0) e->dec_sub_res = (uint32_t)q; }
+        if (const char* v = getenv("FCZ_CHUNK_MB")) { long q = atol(v); if (q > 0) e->chunk_bytes = (uint64_t)q << 20; }
+        if (const char* v = getenv("FCZ_H2D_QUEUE")) e->h2d_depth = (uint32_t)atol(v);
+        if (const char* v = getenv("FCZ_D2H_QUEUE")) e->d2h_depth = (uint32_t)atol(v);
         // 64 registers per thread = 1024 threads per SM, shared between the CTAs the shared-memory footprint lets in
         int occ = 0;
         ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, 128, e->enc_tier[i].smem) == cudaSuccess;
@@ -1333,7 +1352,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->v3, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
-                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets, &e->enc_gws, &e->ws_aoff, &e->ws_toff, &e->d_unit_off, &e->d_unit_chain, &e->d_text_off, &e->d_text,
+                      &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets, &e->enc_gws, &e->d_stage, &e->ws_aoff, &e->ws_toff, &e->d_unit_off, &e->d_unit_chain, &e->d_text_off, &e->d_text,
                       &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -1344,6 +1363,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     if (e->h_counters) cudaFreeHost(e->h_counters);
     if (e->h_totals) cudaFreeHost(e->h_totals);
     if (e->h_bounds) cudaFreeHost(e->h_bounds);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
     for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto ev : e->free_events) cudaEventDestroy(ev);
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
@@ -1643,13 +1663,10 @@ static cudaEvent_t pool_event(fcz_engine* e, size_t i) {
     return e->ev_pool[i];
 }
 
-#define FCZ_HOST_CHUNKS 32u  // chunks of a host-memory batch
-#define FCZ_H2D_DEPTH 2u     // input chunks queued ahead on the copy engine (see encode_host)
-#define FCZ_DEC_H2D_PIECES 3u  // copies the blobs of a host-memory decode go up in (see decode_host)
 // chain ranges of ~equal payload; chunk_c0 has nchunks+1 entries
-static void make_chunks(uint32_t n, const uint64_t* weight_prefix /* [n+1] */, std::vector<uint32_t>& chunk_c0) {
+static void make_chunks(uint32_t n, const uint64_t* weight_prefix /* [n+1] atoms */, std::vector<uint32_t>& chunk_c0, uint64_t chunk_bytes) {
     const uint64_t total = weight_prefix[n] - weight_prefix[0];
-    uint32_t nchunks = (uint32_t)(total / (12ull << 20)) + 1u;  // ~12 MB of payload per chunk
+    uint32_t nchunks = (uint32_t)(total * 12ull / chunk_bytes) + 1u;  // coordinates (12 B per atom) per chunk
     if (nchunks > FCZ_HOST_CHUNKS) nchunks = FCZ_HOST_CHUNKS;
     if (nchunks > n) nchunks = n ? n : 1u;
     chunk_c0.assign(1, 0u);
@@ -1702,12 +1719,11 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
 
     fcz_engine::HostPlan plan;
     plan.n = n;
-    make_chunks(n, in->atom_off, plan.chunk_c0);
+    make_chunks(n, in->atom_off, plan.chunk_c0, e->chunk_bytes);
     const uint32_t nchunks = (uint32_t)plan.chunk_c0.size() - 1u;
 
-    // 1. start moving the inputs (copy stream), chunk by chunk.  Only FCZ_H2D_DEPTH chunks are queued ahead of the
-    // kernels: the H2D copy engine serves its queue in order, so a whole batch queued at once would hold up the
-    // small input copies of any other engine on the GPU (a decode running next to this encode) for milliseconds.
+    // 1. start moving the inputs (copy stream), chunk by chunk; with a non-zero h2d_depth only that many chunks are
+    // queued ahead of the kernels (the copy engine serves its queue in order, see the note at FCZ_CHUNK_BYTES).
     size_t evi = 0;
     cudaEvent_t ev0 = pool_event(e, evi++);
     CK(cudaEventRecord(ev0, e->stream));
@@ -1717,20 +1733,23 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
     COPY(e->d_atom_off.p, in->atom_off, 8ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
     COPY(e->d_title_off.p, in->title_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
     COPY(e->d_meta.p, in->meta, sizeof(fcz_chain_meta) * (uint64_t)n, cudaMemcpyHostToDevice, e->s_in);
+    // The per-residue side arrays (5 B/residue against 94 B/residue of coordinates) go up whole, ahead of the chunks:
+    // every copy has a fixed cost that grows when the other PCIe direction is busy (tools/pcie_matrix.py: 1 MB copies
+    // reach 29 GB/s each way, 12 MB copies 44 GB/s), so a chunk is ONE copy -- its coordinates.
+    COPY(e->d_res_type.p, in->res_type, n_res, cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_bfactor.p, in->bfactor, 4ull * n_res, cudaMemcpyHostToDevice, e->s_in);
+    COPY(e->d_titles.p, in->titles, n_title, cudaMemcpyHostToDevice, e->s_in);
     std::vector<cudaEvent_t> ev_in(nchunks);
     for (uint32_t k = 0; k < nchunks; k++) ev_in[k] = pool_event(e, evi++);
     auto issue_chunk = [&](uint32_t k) -> int {
         const uint32_t c0 = plan.chunk_c0[k], c1 = plan.chunk_c0[k + 1];
-        const uint64_t r0 = in->res_off[c0], r1 = in->res_off[c1], a0 = in->atom_off[c0], a1 = in->atom_off[c1];
-        const uint64_t t0 = in->title_off[c0], t1 = in->title_off[c1];
-        COPY((uint8_t*)e->d_res_type.p + r0, in->res_type + r0, r1 - r0, cudaMemcpyHostToDevice, e->s_in);
-        COPY((float*)e->d_bfactor.p + r0, in->bfactor + r0, 4ull * (r1 - r0), cudaMemcpyHostToDevice, e->s_in);
+        const uint64_t a0 = in->atom_off[c0], a1 = in->atom_off[c1];
         COPY((float*)e->d_xyz.p + 3ull * a0, in->xyz + 3ull * a0, 12ull * (a1 - a0), cudaMemcpyHostToDevice, e->s_in);
-        COPY((char*)e->d_titles.p + t0, in->titles + t0, t1 - t0, cudaMemcpyHostToDevice, e->s_in);
         CK(cudaEventRecord(ev_in[k], e->s_in));
         return FCZ_OK;
     };
-    for (uint32_t k = 0; k < nchunks && k < FCZ_H2D_DEPTH; k++)
+    const uint32_t h2d_depth = e->h2d_depth ? e->h2d_depth : nchunks;  // 0: everything queued at once
+    for (uint32_t k = 0; k < nchunks && k < h2d_depth; k++)
         if ((rc = issue_chunk(k))) return rc;
 
     // 2. meanwhile plan on the host: validate (what k_enc_plan does on the device), sizes, offsets, tiers
@@ -1787,9 +1806,9 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
     // 3. kernels per chunk (main stream) and the blobs back (out stream)
     size_t li = 0;
     for (uint32_t k = 0; k < nchunks; k++) {
-        if (k + FCZ_H2D_DEPTH < nchunks) {  // chunk k has landed: queue the next one behind the one in flight
+        if (k + h2d_depth < nchunks) {  // chunk k has landed: queue the next one behind the one in flight
             CK(cudaEventSynchronize(ev_in[k]));
-            if ((rc = issue_chunk(k + FCZ_H2D_DEPTH))) return rc;
+            if ((rc = issue_chunk(k + h2d_depth))) return rc;
         }
         CK(cudaStreamWaitEvent(e->stream, ev_in[k], 0));
         for (; li < plan.launches.size() && plan.launches[li].chunk == k; li++) {
@@ -1808,11 +1827,14 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
                 if ((rc = launch_encode(e, a, (int)ln.tier, ln.count, long_max_res, e->stream))) return rc;
             }
         }
-        cudaEvent_t ev_k = pool_event(e, evi++);
-        CK(cudaEventRecord(ev_k, e->stream));
-        CK(cudaStreamWaitEvent(e->s_out, ev_k, 0));
-        const uint64_t b0 = out->blob_off[plan.chunk_c0[k]], b1 = out->blob_off[plan.chunk_c0[k + 1]];
-        COPY(out->bytes + b0, (uint8_t*)e->d_bytes.p + b0, b1 - b0, cudaMemcpyDeviceToHost, e->s_out);
+        if ((k + 1u) % FCZ_D2H_GROUP == 0u || k + 1u == nchunks) {  // the blobs of the last few chunks, one copy
+            const uint32_t k0 = k - k % FCZ_D2H_GROUP;
+            cudaEvent_t ev_k = pool_event(e, evi++);
+            CK(cudaEventRecord(ev_k, e->stream));
+            CK(cudaStreamWaitEvent(e->s_out, ev_k, 0));
+            const uint64_t b0 = out->blob_off[plan.chunk_c0[k0]], b1 = out->blob_off[plan.chunk_c0[k + 1]];
+            COPY(out->bytes + b0, (uint8_t*)e->d_bytes.p + b0, b1 - b0, cudaMemcpyDeviceToHost, e->s_out);
+        }
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->s_out));
@@ -2204,7 +2226,7 @@ static int decode_plan_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_b
         out->title_off[c + 1] = out->title_off[c] + T;
         plan.seg_off[c + 1] = plan.seg_off[c] + na;
     }
-    make_chunks(n, out->atom_off, plan.chunk_c0);
+    make_chunks(n, out->atom_off, plan.chunk_c0, e->chunk_bytes);
     totals->n_res = out->res_off[n];
     totals->n_atoms = out->atom_off[n];
     totals->n_title_bytes = out->title_off[n];
@@ -2267,16 +2289,39 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
     CK(cudaEventRecord(ev0, e->stream));
     CK(cudaStreamWaitEvent(e->s_in, ev0, 0));
     CK(cudaStreamWaitEvent(e->s_out, ev0, 0));
-    COPY(e->d_blob_off.p, in->blob_off, 8ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
-    COPY(e->d_res_off.p, out->res_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
-    COPY(e->d_atom_off.p, out->atom_off, 8ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
-    COPY(e->d_title_off.p, out->title_off, 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
-    COPY(e->d_seg_off.p, plan.seg_off.data(), 4ull * (n + 1), cudaMemcpyHostToDevice, e->s_in);
-    COPY(e->d_status.p, plan.status.data(), 4ull * n, cudaMemcpyHostToDevice, e->s_in);
-    if (n) COPY(e->d_dec_list.p, plan.list.data(), 4ull * n, cudaMemcpyHostToDevice, e->s_in);
-    // The blobs are a seventh of the traffic of this call; they go up in at most FCZ_DEC_H2D_PIECES copies, not one per
-    // chunk: copies of one stream take turns with the copies of other engines on the H2D copy engine, so many small
-    // ones next to an encode's 12 MB chunks would each wait a full turn and stretch this call to the encode's length.
+    // Inputs go up in as FEW copies as possible: the seven per-chain arrays are packed into one pinned staging buffer
+    // (one copy), the blobs follow in FCZ_DEC_H2D_PIECES copies: every copy has a fixed cost that grows when the other
+    // PCIe direction is busy (tools/pcie_matrix.py).
+    uint8_t* dst_stage = nullptr;
+    {
+        const uint64_t n1 = (uint64_t)n + 1;
+        uint64_t off[8];
+        uint64_t o = 0;
+        const uint64_t sizes[7] = {8 * n1, 8 * n1, 4 * n1, 4 * n1, 4 * n1, 4ull * n, 4ull * n};
+        for (int i = 0; i < 7; i++) { off[i] = o; o += (sizes[i] + 15u) & ~15ull; }
+        off[7] = o;
+        if (o > e->h_stage_cap) {
+            if (e->h_stage) CK(cudaFreeHost(e->h_stage));
+            e->h_stage = nullptr; e->h_stage_cap = 0;
+            CK(cudaMallocHost(&e->h_stage, o + o / 4 + 4096));
+            e->h_stage_cap = o + o / 4 + 4096;
+        }
+        if ((rc = ensure(e, e->d_stage, o + 16))) return rc;
+        uint8_t* hs = (uint8_t*)e->h_stage;
+        memcpy(hs + off[0], in->blob_off, sizes[0]);
+        memcpy(hs + off[1], out->atom_off, sizes[1]);
+        memcpy(hs + off[2], out->res_off, sizes[2]);
+        memcpy(hs + off[3], out->title_off, sizes[3]);
+        memcpy(hs + off[4], plan.seg_off.data(), sizes[4]);
+        if (n) memcpy(hs + off[5], plan.status.data(), sizes[5]);
+        if (n) memcpy(hs + off[6], plan.list.data(), sizes[6]);
+        COPY(e->d_stage.p, hs, o, cudaMemcpyHostToDevice, e->s_in);
+        dst_stage = (uint8_t*)e->d_stage.p;
+        e->dh.blob_off = (uint64_t*)(dst_stage + off[0]); e->dh.atom_off = (uint64_t*)(dst_stage + off[1]);
+        e->dh.res_off = (uint32_t*)(dst_stage + off[2]); e->dh.title_off = (uint32_t*)(dst_stage + off[3]);
+        e->dh.seg_off = (uint32_t*)(dst_stage + off[4]); e->dh.status = (int32_t*)(dst_stage + off[5]);
+        e->dh.list = (uint32_t*)(dst_stage + off[6]);
+    }
     std::vector<cudaEvent_t> ev_in(nchunks);
     {
         const uint32_t npieces = nchunks < FCZ_DEC_H2D_PIECES ? nchunks : FCZ_DEC_H2D_PIECES;
@@ -2293,44 +2338,76 @@ static int decode_host(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batch*
     memset(&tt, 0, sizeof tt);
     PlanOut po;
     memset(&po, 0, sizeof po);
-    po.status = (int32_t*)e->d_status.p;
+    po.status = e->dh.status;
     Dec2Args a;
     memset(&a, 0, sizeof a);
-    a.blob_off = (uint64_t*)e->d_blob_off.p; a.bytes = (uint8_t*)e->d_bytes.p;
-    a.res_off = (uint32_t*)e->d_res_off.p; a.atom_off = (uint64_t*)e->d_atom_off.p; a.title_off = (uint32_t*)e->d_title_off.p;
-    a.seg_off = (uint32_t*)e->d_seg_off.p;
+    a.blob_off = e->dh.blob_off; a.bytes = (uint8_t*)e->d_bytes.p;
+    a.res_off = e->dh.res_off; a.atom_off = e->dh.atom_off; a.title_off = e->dh.title_off;
+    a.seg_off = e->dh.seg_off;
     a.res_type = (uint8_t*)e->d_res_type.p; a.bfactor = (float*)e->d_bfactor.p; a.xyz = (float*)e->d_xyz.p;
     a.titles = out->titles ? (char*)e->d_titles.p : nullptr; a.meta = (fcz_chain_meta*)e->d_meta.p;
-    a.status = (int32_t*)e->d_status.p; a.tables = e->d_tables; a.use_alt = e->opts.use_alt_atom_order;
+    a.status = e->dh.status; a.tables = e->d_tables; a.use_alt = e->opts.use_alt_atom_order;
+    static const bool trace = getenv("FCZ_TRACE_HOST") != nullptr;
+    std::vector<cudaEvent_t> tr_ev;  // debug timeline: start, then per chunk (kernels done, D2H done)
+    if (trace) {
+        tr_ev.resize(2 * nchunks + 2);
+        for (auto& ev : tr_ev) cudaEventCreate(&ev);
+        cudaEventRecord(tr_ev[0], e->stream);
+        cudaEventRecord(tr_ev[1], e->s_in);
+    }
+    // kernels of every chunk first (they only wait for the blobs), then the results back, with at most d2h_depth
+    // coordinate copies queued when that is non-zero (see the note at FCZ_CHUNK_BYTES).
+    std::vector<cudaEvent_t> ev_k(nchunks), ev_out(nchunks);
     for (uint32_t k = 0; k < nchunks; k++) {
         const uint32_t c0 = subs[k].c0, c1 = subs[k].c1;
         CK(cudaStreamWaitEvent(e->stream, ev_in[k], 0));
         if (c1 > c0) {
-            k_dec_plan<<<(c1 - c0 + 7) / 8, 256, 0, e->stream>>>(c0, c1, (uint64_t*)e->d_blob_off.p, (uint8_t*)e->d_bytes.p, e->d_tables, tt, po, 1);
+            k_dec_plan<<<(c1 - c0 + 7) / 8, 256, 0, e->stream>>>(c0, c1, e->dh.blob_off, (uint8_t*)e->d_bytes.p, e->d_tables, tt, po, 1);
             e->launches++;
             ProfSpan ps(e, FCZ_PROF_DECODE);
-            if ((rc = dec2_launch(e, a, subs[k], (const uint32_t*)e->d_dec_list.p))) return rc;
+            if ((rc = dec2_launch(e, a, subs[k], e->dh.list))) return rc;
         }
-        cudaEvent_t ev_k = pool_event(e, evi++);
-        CK(cudaEventRecord(ev_k, e->stream));
-        CK(cudaStreamWaitEvent(e->s_out, ev_k, 0));
-        const uint64_t r0 = out->res_off[c0], r1 = out->res_off[c1], a0 = out->atom_off[c0], a1 = out->atom_off[c1];
-        const uint64_t t0 = out->title_off[c0], t1 = out->title_off[c1];
+        ev_k[k] = pool_event(e, evi++);
+        ev_out[k] = pool_event(e, evi++);
+        CK(cudaEventRecord(ev_k[k], e->stream));
+        if (trace) cudaEventRecord(tr_ev[2 + 2 * k], e->stream);
+    }
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t c0 = subs[k].c0, c1 = subs[k].c1;
+        if (e->d2h_depth && k >= e->d2h_depth) CK(cudaEventSynchronize(ev_out[k - e->d2h_depth]));
+        CK(cudaStreamWaitEvent(e->s_out, ev_k[k], 0));
+        const uint64_t a0 = out->atom_off[c0], a1 = out->atom_off[c1];
         COPY(out->xyz + 3ull * a0, (float*)e->d_xyz.p + 3ull * a0, 12ull * (a1 - a0), cudaMemcpyDeviceToHost, e->s_out);
-        COPY(out->res_type + r0, (uint8_t*)e->d_res_type.p + r0, r1 - r0, cudaMemcpyDeviceToHost, e->s_out);
-        COPY(out->bfactor + r0, (float*)e->d_bfactor.p + r0, 4ull * (r1 - r0), cudaMemcpyDeviceToHost, e->s_out);
-        if (out->titles) COPY(out->titles + t0, (char*)e->d_titles.p + t0, t1 - t0, cudaMemcpyDeviceToHost, e->s_out);
-        COPY(out->meta + c0, (fcz_chain_meta*)e->d_meta.p + c0, sizeof(fcz_chain_meta) * (uint64_t)(c1 - c0), cudaMemcpyDeviceToHost, e->s_out);
+        CK(cudaEventRecord(ev_out[k], e->s_out));
+        if (k + 1u == nchunks) {  // the small per-residue / per-chain arrays come back whole, after the last chunk's kernels
+            COPY(out->res_type, e->d_res_type.p, n_res, cudaMemcpyDeviceToHost, e->s_out);
+            COPY(out->bfactor, e->d_bfactor.p, 4ull * n_res, cudaMemcpyDeviceToHost, e->s_out);
+            if (out->titles) COPY(out->titles, e->d_titles.p, n_title, cudaMemcpyDeviceToHost, e->s_out);
+            COPY(out->meta, e->d_meta.p, sizeof(fcz_chain_meta) * (uint64_t)n, cudaMemcpyDeviceToHost, e->s_out);
+        }
+        if (trace) cudaEventRecord(tr_ev[3 + 2 * k], e->s_out);
     }
     if (out->status) {
         cudaEvent_t ev_done = pool_event(e, evi++);
         CK(cudaEventRecord(ev_done, e->stream));
         CK(cudaStreamWaitEvent(e->s_out, ev_done, 0));
-        COPY(out->status, e->d_status.p, 4ull * n, cudaMemcpyDeviceToHost, e->s_out);
+        COPY(out->status, e->dh.status, 4ull * n, cudaMemcpyDeviceToHost, e->s_out);
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->s_out));
     CK(cudaStreamSynchronize(e->stream));
+    if (trace) {
+        float t_in = 0;
+        cudaEventElapsedTime(&t_in, tr_ev[0], tr_ev[1]);
+        fprintf(stderr, "[decode_host trace] %u chunks; inputs landed at %.3f ms\n", nchunks, t_in);
+        for (uint32_t k = 0; k < nchunks; k++) {
+            float tk = 0, td = 0;
+            cudaEventElapsedTime(&tk, tr_ev[0], tr_ev[2 + 2 * k]);
+            cudaEventElapsedTime(&td, tr_ev[0], tr_ev[3 + 2 * k]);
+            fprintf(stderr, "[decode_host trace] chunk %2u kernels done %.3f  d2h done %.3f\n", k, tk, td);
+        }
+        for (auto ev : tr_ev) cudaEventDestroy(ev);
+    }
     return FCZ_OK;
 }
 
