@@ -5,6 +5,8 @@ The Python surface mirrors the reference's CPython module for this path
 
     compress(name, pdb_content, *, anchor_residue_threshold=25) -> bytes     (foldcomp.cxx:295-328)
     decompress(fcz_bytes) -> (name, pdb_str)                                 (foldcomp.cxx:222-239)
+    open(path, *, ids=None, decompress=True, err_on_missing=False)           (foldcomp.cxx:333-433) -> FoldcompDatabase
+get_data() (a per-structure dump of the intermediate angles) is not provided.
 
 Both go through the CUDA engine (include/fcz_engine.h); text parsing/formatting is host code
 (pdbio.py).  Batch entry points live in `engine.Engine`.  There is no CPU fallback.
@@ -14,7 +16,7 @@ from __future__ import annotations
 from . import abi
 from .abi import HostBlobBatch, HostChainBatch
 
-__all__ = ["compress", "decompress", "error", "Engine", "HostChainBatch", "HostBlobBatch"]
+__all__ = ["compress", "decompress", "open", "FoldcompDatabase", "error", "Engine", "HostChainBatch", "HostBlobBatch"]
 
 
 class error(Exception):
@@ -38,6 +40,10 @@ def __getattr__(name):
         from .engine import Engine
 
         return Engine
+    if name in ("open", "FoldcompDatabase"):
+        from . import database
+
+        return getattr(database, name)
     raise AttributeError(name)
 
 

@@ -85,3 +85,40 @@ def test_cli_db_subcommands(tmp_path, golden):
     for (_, _, x), (_, _, y) in zip(a, b):
         dx, dy = H.oracle_decode(x), H.oracle_decode(y)
         assert np.array_equal(dx.res_type, dy.res_type) and H.rmsd(dx.xyz, dy.xyz) < 0.2  # a second lossy generation
+
+
+def test_python_open_mirrors_reference_database(golden, tmp_path):
+    """foldcomp_b200.open() against the reference's FoldcompDatabase (foldcomp.cxx:36-180, 333-433) on the same files."""
+    import foldcomp_b200
+
+    names = [f"d{i}x_" for i in range(len(golden.db_blobs))]
+    entries = [(i, names[i], b) for i, b in enumerate(golden.db_blobs)]
+    path = str(tmp_path / "db")
+    dbutil.write_db(path, entries)
+    ref = dbutil.reference_module()
+    with foldcomp_b200.open(path) as db:
+        assert len(db) == len(entries)
+        ours = [db[i] for i in range(len(db))]
+        assert db[-1] == ours[-1]
+        with pytest.raises(IndexError):
+            db[len(entries)]
+    for (title, pdb), blob in zip(ours, golden.db_blobs):
+        want = H.oracle_decode(blob)
+        assert title == want.title.decode()
+        back = pdbio.parse_pdb_chain(pdb, title)
+        assert np.array_equal(back.res_type, want.res_type) and np.abs(back.xyz - want.xyz).max() <= 0.05 + 0.0006
+    if ref is not None:
+        with ref.open(path) as rdb:
+            assert len(rdb) == len(ours)
+            for i in (0, 7, len(ours) - 1):
+                rname, rpdb = rdb[i]
+                assert rname == ours[i][0] and len(rpdb.splitlines()) == len(ours[i][1].splitlines())
+    sel = [names[5], "missing_one", names[2]]
+    with foldcomp_b200.open(path, ids=sel) as db:
+        assert len(db) == 2 and db[0] == ours[5] and db[1] == ours[2]
+    with pytest.raises(KeyError):
+        foldcomp_b200.open(path, ids=sel, err_on_missing=True)
+    with foldcomp_b200.open(path, decompress=False) as db:
+        assert db[3] == golden.db_blobs[3]
+    with pytest.raises(TypeError):
+        foldcomp_b200.open(path, ids="d1asha_")
