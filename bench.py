@@ -147,7 +147,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_id), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_id), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -261,7 +261,7 @@ def run_ours(args, rank, world, local_rank, out):
     ms_prof = ev2.elapsed_time(ev3)
     prof = eng.get_profile()
     eng.set_profiling(False)
-    clocks = sampler.stop()
+    clocks = sampler.stop()  # sampled over the device-resident timed passes only (the GPU idles between transfers later on)
     ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
