@@ -35,6 +35,7 @@ def build_oracle():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libfcz_oracle.so"])
     if os.path.isdir(os.path.join(REFERENCE_DIR, "src")):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+        subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "pyref"])
 
 
 def build_emu():
