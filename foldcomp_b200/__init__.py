@@ -6,7 +6,7 @@ The Python surface mirrors the reference's CPython module for this path
     compress(name, pdb_content, *, anchor_residue_threshold=25) -> bytes     (foldcomp.cxx:295-328)
     decompress(fcz_bytes) -> (name, pdb_str)                                 (foldcomp.cxx:222-239)
     open(path, *, ids=None, decompress=True, err_on_missing=False)           (foldcomp.cxx:333-433) -> FoldcompDatabase
-get_data() (a per-structure dump of the intermediate angles) is not provided.
+    get_data(fcz_bytes) -> dict                                              (foldcomp.cxx:497-640; FCZ input only)
 
 Both go through the CUDA engine (include/fcz_engine.h); text parsing/formatting is host code
 (pdbio.py).  Batch entry points live in `engine.Engine`.  There is no CPU fallback.
@@ -16,7 +16,7 @@ from __future__ import annotations
 from . import abi
 from .abi import HostBlobBatch, HostChainBatch
 
-__all__ = ["compress", "decompress", "open", "FoldcompDatabase", "error", "Engine", "HostChainBatch", "HostBlobBatch"]
+__all__ = ["compress", "decompress", "get_data", "open", "FoldcompDatabase", "error", "Engine", "HostChainBatch", "HostBlobBatch"]
 
 
 class error(Exception):
@@ -74,3 +74,38 @@ def decompress(fcz: bytes):
     tl = int.from_bytes(data[24:28], "little")  # CompressedFileHeader.lenTitle; the title follows the anchor indices
     t0 = 76 + 4 * data[12]
     return data[t0 : t0 + tl].decode("latin-1"), out.text(0).decode("latin-1")
+
+
+def get_data(input):  # noqa: A002 - the reference's parameter name
+    """foldcomp.get_data(fcz_bytes) -> dict with phi, psi, omega, torsion_angles, bond_angles, residues, b_factors,
+    coordinates (foldcomp/foldcomp.cxx:497-640, getDataFromFCZ): the continuised angles of the blob and its decoded
+    coordinates, both from the GPU engine.  PDB text input (the reference then runs its CPU encoder and returns the
+    angles before quantisation) is not supported: compress() it first."""
+    data = input.encode("latin-1") if isinstance(input, str) else bytes(input)
+    if len(data) == 0:
+        raise ValueError("Input is empty")
+    if data[:4] != b"FCMP":
+        raise ValueError("Input is not a FCZ file (foldcomp_b200.get_data takes FCZ bytes; compress() PDB text first)")
+    from .tables import NAME1
+
+    eng = _get_engine()
+    blobs = HostBlobBatch.from_blobs([data])
+    dec = eng.decode_host(blobs)
+    if int(dec.status[0]) != abi.FCZ_OK:
+        raise ValueError("Could not decompress FCZ file")
+    _, ang = eng.unpack_angles_host(blobs)
+    phi, psi, omega = ang[:, 0], ang[:, 1], ang[:, 2]
+    n_ca_c, ca_c_n, c_n_ca = ang[:, 3], ang[:, 4], ang[:, 5]
+    L = len(ang)
+    tors = [float(v) for i in range(L - 1) for v in (psi[i], omega[i], phi[i])]  # src/foldcomp.cpp:788-793
+    bond = [float(v) for i in range(L) for v in (ca_c_n[i], c_n_ca[i], n_ca_c[i])]  # src/foldcomp.cpp:799-804
+    coords = [tuple(float(x) for x in row) for row in dec.xyz]
+    m = dec.meta[0]
+    if int(m["has_oxt"]):
+        coords.append(tuple(float(x) for x in m["oxt"]))
+    return {
+        "phi": [float(v) for v in phi], "psi": [float(v) for v in psi], "omega": [float(v) for v in omega],
+        "torsion_angles": tors, "bond_angles": bond,
+        "residues": "".join(NAME1[int(c)] for c in dec.res_type),
+        "b_factors": [float(v) for v in dec.bfactor], "coordinates": coords,
+    }

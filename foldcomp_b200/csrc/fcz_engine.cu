@@ -1067,6 +1067,37 @@ __global__ void __launch_bounds__(128) k_extract(ExtractArgs a) {
     extract_chain(cx, a.tt, blob, y, a.type, a.digits, a.text + a.text_off[c]);
 }
 
+// Continuised backbone angles of every residue record (decompressBackboneChain, src/foldcomp.cpp:122-153 with
+// _continuize 155-158: q * cont_f + min, two float roundings): six floats per residue in header order
+// phi, psi, omega, N-CA-C, CA-C-N, C-N-CA.  What Foldcomp::decompress leaves in its phi / psi / omega / *_angle members
+// (src/foldcomp.cpp:783-804) and the CPython get_data() returns (foldcomp/foldcomp.cxx:497-560).  Thread per residue.
+struct AnglesArgs {
+    const uint64_t* blob_off;
+    const uint8_t* bytes;
+    const int32_t* status;
+    const uint64_t* res_off;  // [n+1] scan of the residue counts
+    float* angles;            // [6 * residues]
+    uint32_t n;
+};
+__global__ void __launch_bounds__(128) k_unpack_angles(AnglesArgs a) {
+    const uint32_t c = blockIdx.x;
+    if (a.status[c] != FCZ_OK) return;
+    const uint8_t* blob = a.bytes + a.blob_off[c];
+    const Layout y = make_layout(get_u16(blob + OFF_NRES), get_u32(blob + OFF_NSC), get_u32(blob + OFF_LENTITLE), blob[OFF_NANCHOR]);
+    float mins[6], cfs[6];
+    for (int k = 0; k < 6; k++) { mins[k] = get_f32(blob + OFF_MINS + 4 * k); cfs[k] = get_f32(blob + OFF_CONTFS + 4 * k); }
+    float* out = a.angles + 6u * a.res_off[c];
+    for (uint32_t r = threadIdx.x; r < y.L; r += blockDim.x) {
+        const Record q = unpack_record(blob + y.o_rec + 8u * r);
+        out[6u * r + 0u] = continuize(q.phi, mins[A_PHI], cfs[A_PHI]);
+        out[6u * r + 1u] = continuize(q.psi, mins[A_PSI], cfs[A_PSI]);
+        out[6u * r + 2u] = continuize(q.omg, mins[A_OMEGA], cfs[A_OMEGA]);
+        out[6u * r + 3u] = continuize(q.nca, mins[A_NCAC], cfs[A_NCAC]);
+        out[6u * r + 4u] = continuize(q.cac, mins[A_CACN], cfs[A_CACN]);
+        out[6u * r + 5u] = continuize(q.cnc, mins[A_CNCA], cfs[A_CNCA]);
+    }
+}
+
 // ============================================================================================ scans
 // Exclusive scans of up to three per-chain u32 arrays into offsets (u32/u64), tile = 2048 chains.
 
@@ -2568,4 +2599,56 @@ extern "C" int fcz_decode_to_pdb_batch(fcz_engine* e, const fcz_blob_batch* in, 
         return fail(e, FCZ_E_CAPACITY, "text needs %llu bytes, capacity %llu", (unsigned long long)e->pdb.total_bytes, (unsigned long long)out->bytes_cap);
     e->pdb.valid = false;
     return pdb_emit_to_host(e, staged_chains(e), n, out->text_off, out->bytes);
+}
+
+// ---------------------------------------------------------------------------------- continuised angles (get_data)
+extern "C" int fcz_unpack_angles_batch(fcz_engine* e, const fcz_blob_batch* in, uint64_t* res_off, float* angles, uint64_t res_cap,
+                                       uint64_t* total_res) {
+    if (!e || !in || !res_off || !total_res) return FCZ_E_ARG;
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    int rc;
+    if ((rc = plan_buffers(e, n))) return rc;
+    const bool host = in->mem == FCZ_MEM_HOST;
+    ExtractArgs x;
+    memset(&x, 0, sizeof x);
+    if (host) {
+        H2D(e->d_blob_off, in->blob_off, 8ull * (n + 1));
+        H2D(e->d_bytes, in->bytes, in->blob_off[n]);
+        if ((rc = ensure(e, e->d_text_off, 8ull * (n + 1)))) return rc;
+        x.blob_off = (uint64_t*)e->d_blob_off.p; x.bytes = (uint8_t*)e->d_bytes.p;
+    } else {
+        x.blob_off = in->blob_off; x.bytes = in->bytes;
+    }
+    x.tt = e->d_text_tables; x.type = 1; x.digits = 1; x.n = n;  // type 1 sizes = residues per blob
+    x.text_bytes = (uint32_t*)e->v0.p; x.status = (int32_t*)e->status.p;
+    uint64_t* d_res_off = host ? (uint64_t*)e->d_text_off.p : res_off;
+    if (n) {
+        k_extract_plan<<<(n + 255) / 256, 256, 0, e->stream>>>(x);
+        e->launches++;
+    }
+    ScanArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.n = n; sa.narr = 1;
+    sa.in[0] = x.text_bytes; sa.out[0] = d_res_off; sa.out64[0] = 1;
+    if ((rc = run_scan(e, sa))) return rc;
+    if ((rc = fetch_plan(e))) return rc;
+    const uint64_t total = e->h_totals[0];
+    *total_res = total;
+    if (!angles || total > res_cap) return total > res_cap && angles ? fail(e, FCZ_E_CAPACITY, "angles need %llu residues of capacity", (unsigned long long)total) : FCZ_OK;
+    if (host && (rc = ensure(e, e->d_text, 24ull * total + 64))) return rc;
+    AnglesArgs a;
+    a.blob_off = x.blob_off; a.bytes = x.bytes; a.status = x.status; a.res_off = d_res_off; a.n = n;
+    a.angles = host ? (float*)e->d_text.p : angles;
+    if (n) {
+        k_unpack_angles<<<n, 128, 0, e->stream>>>(a);
+        e->launches++;
+    }
+    CK(cudaGetLastError());
+    if (host) {
+        CK(cudaMemcpyAsync(res_off, d_res_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+        if (total) CK(cudaMemcpyAsync(angles, e->d_text.p, 24ull * total, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return FCZ_OK;
 }

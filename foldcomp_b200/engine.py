@@ -327,3 +327,14 @@ class Engine:
         total = C.c_uint64()
         self._check(self.lib.fcz_extract_batch(self.h, C.byref(sin), int(type_), int(digits), C.byref(so), C.byref(total)))
         return out
+
+    def unpack_angles_host(self, blobs: HostBlobBatch):
+        """(res_off [n+1], angles [R, 6]): continuised phi, psi, omega, N-CA-C, CA-C-N, C-N-CA of every residue record."""
+        n = blobs.n_chains
+        res_off = np.zeros(n + 1, np.uint64)
+        sin = blobs.as_struct()
+        total = C.c_uint64()
+        self._check(self.lib.fcz_unpack_angles_batch(self.h, C.byref(sin), res_off.ctypes.data, None, 0, C.byref(total)))
+        ang = np.zeros((total.value, 6), np.float32)
+        self._check(self.lib.fcz_unpack_angles_batch(self.h, C.byref(sin), res_off.ctypes.data, ang.ctypes.data, total.value, C.byref(total)))
+        return res_off, ang

@@ -168,6 +168,14 @@ int fcz_decode_to_pdb_batch(fcz_engine* e, const fcz_blob_batch* in, fcz_text_ba
 int fcz_extract_batch(fcz_engine* e, const fcz_blob_batch* in, int32_t type, int32_t digits, fcz_text_batch* out,
                       uint64_t* total_bytes);
 
+/* Continuised backbone angles of every residue record: six floats per residue, phi, psi, omega, N-CA-C, CA-C-N, C-N-CA
+ * -- decompressBackboneChain (src/foldcomp.cpp:122-153), i.e. what Foldcomp::decompress leaves in its phi / psi / omega /
+ * *_angle members (783-804) and the CPython get_data() returns (foldcomp/foldcomp.cxx:497-560).  Fills res_off[0..n]
+ * (residues before each blob; a blob that fails the header check counts 0) and, when `angles` is not NULL and
+ * res_cap is large enough, angles[6 * residues]; *total_res receives the residue total either way. */
+int fcz_unpack_angles_batch(fcz_engine* e, const fcz_blob_batch* in, uint64_t* res_off, float* angles, uint64_t res_cap,
+                            uint64_t* total_res);
+
 /* Block until everything enqueued on the engine's stream has finished. */
 int fcz_engine_sync(fcz_engine* e);
 

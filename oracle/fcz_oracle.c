@@ -685,3 +685,26 @@ int64_t fcz_oracle_extract(const uint8_t* blob, uint64_t len, int type, int digi
     }
     return (int64_t)o.n;
 }
+
+/* Continuised backbone angles per residue record: decompressBackboneChain (src/foldcomp.cpp:122-153) with _continuize
+ * (155-158).  out gets 6 floats per residue: phi, psi, omega, N-CA-C, CA-C-N, C-N-CA.  Returns the residue count. */
+int64_t fcz_oracle_unpack_angles(const uint8_t* blob, uint64_t len, float* out) {
+    view_t v;
+    int rc = parse(blob, len, &v);
+    if (rc) return rc;
+    float mins[6], cfs[6];
+    for (int k = 0; k < 6; k++) { mins[k] = getf(blob + 28 + 4 * k); cfs[k] = getf(blob + 52 + 4 * k); }
+    for (uint32_t r = 0; r < v.L; r++) {
+        const uint8_t* b = v.records + 8 * r; /* convertBytesToBackboneChain, src/foldcomp.cpp:60-77 */
+        unsigned omega = ((b[0] & 7u) << 8) | b[1];
+        unsigned psi = ((unsigned)b[2] << 4) | (b[3] >> 4);
+        unsigned phi = ((b[3] & 15u) << 8) | b[4];
+        out[6 * r + 0] = cont(phi, mins[0], cfs[0]);
+        out[6 * r + 1] = cont(psi, mins[1], cfs[1]);
+        out[6 * r + 2] = cont(omega, mins[2], cfs[2]);
+        out[6 * r + 3] = cont(b[7], mins[3], cfs[3]);
+        out[6 * r + 4] = cont(b[5], mins[4], cfs[4]);
+        out[6 * r + 5] = cont(b[6], mins[5], cfs[5]);
+    }
+    return (int64_t)v.L;
+}

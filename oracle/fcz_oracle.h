@@ -49,6 +49,10 @@ int64_t fcz_oracle_format_pdb(const uint8_t* res_type, uint32_t L, const float* 
 /* Foldcomp::extract (src/foldcomp.cpp:1260-1336): type 0 = pLDDT with `digits` 1..4, type 1 = sequence. */
 int64_t fcz_oracle_extract(const uint8_t* blob, uint64_t len, int type, int digits, char* out, uint64_t cap);
 
+/* Continuised angles of every residue record, 6 floats each (phi, psi, omega, N-CA-C, CA-C-N, C-N-CA):
+ * decompressBackboneChain, src/foldcomp.cpp:122-153.  Returns the residue count or a negative code. */
+int64_t fcz_oracle_unpack_angles(const uint8_t* blob, uint64_t len, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -430,3 +430,15 @@ def extreme_text_chain(seed: int = 0) -> HostChainBatch:
     b.titles = np.frombuffer(title, np.uint8).copy()
     b.title_off = np.array([0, len(title)], np.uint32)
     return b
+
+
+def oracle_unpack_angles(blob: bytes) -> np.ndarray:
+    """[L, 6] continuised phi, psi, omega, N-CA-C, CA-C-N, C-N-CA of every residue record (src/foldcomp.cpp:122-153)."""
+    lib = oracle()
+    lib.fcz_oracle_unpack_angles.restype = C.c_int64
+    lib.fcz_oracle_unpack_angles.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
+    L = int.from_bytes(blob[4:6], "little")
+    out = np.zeros((L, 6), np.float32)
+    n = lib.fcz_oracle_unpack_angles(blob, len(blob), out.ctypes.data)
+    assert n == L, n
+    return out

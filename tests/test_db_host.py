@@ -97,3 +97,21 @@ def test_db_reader_writer_roundtrip(lib, golden, tmp_path):
             for i, (k, name, blob) in enumerate(sorted(entries)):
                 n, pdb = db[i]
                 assert pdb == ref.decompress(blob)[1]
+
+
+def test_oracle_angles_match_reference_get_data(golden):
+    """The oracle's restatement of decompressBackboneChain against the reference's own get_data() (foldcomp.cxx:497-640)."""
+    ref = dbutil.reference_module()
+    if ref is None:
+        pytest.skip("oracle/_ref/pyref not built")
+    for blob in golden.blobs(25) + list(golden.db_blobs[:4]):
+        d = ref.get_data(blob)
+        ang = H.oracle_unpack_angles(blob)
+        L = len(ang)
+        f32 = lambda x: np.asarray(x, np.float32)
+        assert np.array_equal(f32(d["phi"]), ang[:, 0]) and np.array_equal(f32(d["psi"]), ang[:, 1]) and np.array_equal(f32(d["omega"]), ang[:, 2])
+        assert np.array_equal(f32(d["torsion_angles"]), ang[: L - 1][:, [1, 2, 0]].reshape(-1))
+        assert np.array_equal(f32(d["bond_angles"]), ang[:, [4, 5, 3]].reshape(-1))
+        dec = H.oracle_decode(blob)
+        assert np.array_equal(f32(d["b_factors"]), dec.bfactor)
+        assert d["residues"] == "".join("ARNDCQEGHILKMFPSTWYVBZ*X"[c] for c in dec.res_type)

@@ -122,3 +122,32 @@ def test_python_open_mirrors_reference_database(golden, tmp_path):
         assert db[3] == golden.db_blobs[3]
     with pytest.raises(TypeError):
         foldcomp_b200.open(path, ids="d1asha_")
+
+
+def test_python_get_data_matches_oracle_and_reference(golden):
+    """foldcomp_b200.get_data(fcz): angles, residues and B-factors exact, coordinates within the decode tolerance."""
+    import foldcomp_b200
+
+    ref = dbutil.reference_module()
+    for blob in golden.blobs(25)[:3] + list(golden.db_blobs[:3]):
+        d = foldcomp_b200.get_data(blob)
+        ang = H.oracle_unpack_angles(blob)
+        L = len(ang)
+        f32 = lambda x: np.asarray(x, np.float32)
+        assert np.array_equal(f32(d["phi"]), ang[:, 0]) and np.array_equal(f32(d["psi"]), ang[:, 1]) and np.array_equal(f32(d["omega"]), ang[:, 2])
+        assert np.array_equal(f32(d["torsion_angles"]), ang[: L - 1][:, [1, 2, 0]].reshape(-1))
+        assert np.array_equal(f32(d["bond_angles"]), ang[:, [4, 5, 3]].reshape(-1))
+        dec = H.oracle_decode(blob)
+        assert np.array_equal(f32(d["b_factors"]), dec.bfactor) and len(d["residues"]) == L
+        n_at = len(dec.xyz) + int(dec.meta["has_oxt"])
+        assert len(d["coordinates"]) == n_at
+        assert np.abs(f32(d["coordinates"])[: len(dec.xyz)] - dec.xyz).max() <= 0.05
+        if ref is not None:
+            r = ref.get_data(blob)
+            assert sorted(r.keys()) == sorted(d.keys())
+            for k in ("phi", "psi", "omega", "torsion_angles", "bond_angles", "b_factors", "residues"):
+                assert r[k] == d[k], k
+            assert len(r["coordinates"]) == len(d["coordinates"])
+            assert np.abs(f32(r["coordinates"]) - f32(d["coordinates"])).max() <= 0.05
+    with pytest.raises(ValueError):
+        foldcomp_b200.get_data("ATOM      1  N   GLY A   1 ...")

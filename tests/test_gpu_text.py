@@ -123,3 +123,13 @@ def test_decode_to_pdb_fused_and_python_decompress(engine, golden):
             assert a[:30] == b[:30] and a[54:] == b[54:]
             if a.startswith("ATOM"):
                 assert max(abs(float(a[30 + 8 * k : 38 + 8 * k]) - float(b[30 + 8 * k : 38 + 8 * k])) for k in range(3)) <= 0.051
+
+
+def test_text_entry_points_on_empty_batches(engine):
+    from foldcomp_b200.abi import HostChainBatch
+
+    assert engine.pdb_text_host(HostChainBatch.empty(0)).n_chains == 0
+    assert engine.decode_to_pdb_host(HostBlobBatch.from_blobs([])).n_chains == 0
+    assert engine.extract_host(HostBlobBatch.from_blobs([]), 1).n_chains == 0
+    off, ang = engine.unpack_angles_host(HostBlobBatch.from_blobs([]))
+    assert len(off) == 1 and ang.shape == (0, 6)
