@@ -409,10 +409,10 @@ FCZ_HD f3 blend(f3 fwd, f3 rev, float wf, float wr, float inv_n) {
     return mk3(fma_(rev.x, wr, fwd.x * wf) * inv_n, fma_(rev.y, wr, fwd.y * wf) * inv_n, fma_(rev.z, wr, fwd.z * wf) * inv_n);
 }
 
-// The decode of one chain is five phases.  decode_chain() runs them back to back inside one CTA (block
-// barriers in between); the batch-wide decoder of fcz_engine.cu runs each phase as its own kernel over all
-// chains of a sub-batch, with the workspace in global memory (L2-resident), so that the serial phases cost
-// their latency once per batch instead of once per CTA wave.
+// The decode of one chain is five phases.  decode_chain() runs them back to back inside one execution context (the
+// CPU model of tests/emu/ does); the engine (fcz_engine.cu) runs them as kernels over all chains of a length tier --
+// unpack + passes in k_dec_front, the stitch thread-per-chain in k_dec_stitch_t, blend + side chains in k_dec_back --
+// so that the serial stitch costs its latency once per batch instead of once per CTA.
 
 template <class Ctx>
 FCZ_HD void dec_unpack(Ctx& cx, const Tables* tb, const DecChain& ch) {

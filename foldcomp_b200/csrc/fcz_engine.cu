@@ -47,7 +47,7 @@ struct TierCfg {
 // last staged tier is smaller.  Tier 6 keeps chain data in global memory, tier 7 (up to the format's 65535
 // residues) its workspace as well.
 // Caps are chosen at the occupancy steps of the per-residue shared-memory footprint (encode ~172 B/residue,
-// 350-residue chains run 3 CTAs/SM).  Decode has no tiers: it is batch-wide (see below).
+// 350-residue chains run 3 CTAs/SM).  Decode has its own four length tiers (dec_tier_of, below).
 static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 296, 408, 632, 1280, 2720, 65535};
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -538,12 +538,12 @@ __global__ void k_dec_plan(uint32_t c0, uint32_t n, const uint64_t* blob_off, co
     }
 }
 
-// ============================================================================= batch-wide decode
-// The decoder that is used: each phase of fcz_codec.h's decode is its own kernel over all chains of a
-// sub-batch, workspace in global memory.  No shared-memory staging: the per-chain working set (~56 KB)
-// allows only two resident chains per SM, and a CTA that walks a chain through its serial phases (stitch:
-// one thread; passes: <= 2 lanes per segment) leaves the SM idle; run batch-wide, those phases cost their
-// latency once per sub-batch.  Sub-batches are sized so workspace + output stay L2-resident.
+// ================================================================================== decode kernels
+// Decode runs phase by phase over all chains of a length tier (fcz_codec.h: dec_unpack, dec_passes, dec_stitch_core,
+// dec_blend, dec_side), because a CTA that walks one chain through its serial phase (the stitch: one thread) would
+// leave its SM idle.  Two forms: the shared-memory pipeline k_dec_front -> k_dec_stitch_t -> k_dec_back (working set
+// of a chain in shared memory, hand-over through global scratch), and, for chains whose working set does not fit
+// 227 KB, one kernel per phase with the whole workspace in global memory (k_dec_unpack ... k_dec_side).
 
 struct Dec2Args {
     const uint64_t* blob_off;
@@ -1234,7 +1234,7 @@ struct fcz_engine {
     void* h_stage = nullptr;  // pinned staging for the per-chain arrays of a host-memory decode (one H2D copy)
     size_t h_stage_cap = 0;
     struct { uint64_t *blob_off, *atom_off; uint32_t *res_off, *title_off, *seg_off, *list; int32_t* status; } dh = {};
-    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax, d_dec_list;  // batch-wide decoder: segment offsets + L2-resident workspace
+    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax, d_dec_list;  // decoder: segment offsets + hand-over workspace between the phase kernels
     // plan made on the host by fcz_decode_plan(host) for the following fcz_decode_batch(host)
     struct Launch { uint32_t chunk, tier, first, count; };
     struct HostPlan {

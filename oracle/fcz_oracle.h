@@ -5,11 +5,13 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline leg.  The product path
  * (foldcomp_b200/) never links, imports or calls it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_ref.py checks this restatement against the
- * unmodified reference compiled in this container (oracle/_ref/libfoldcomp_ref.so): FCZ bytes
- * bit-identical (modulo the four uninitialised header padding bytes), decoded coordinates
- * bit-identical; tests/test_oracle_golden.py repeats it against committed fixtures
- * (tests/golden/) generated from the reference by tests/golden/make_golden.py.
+ * Parity status: PINNED.  tests/test_oracle.py checks this restatement against the unmodified
+ * reference compiled in this container (oracle/_ref/libfoldcomp_ref.so): FCZ bytes bit-identical
+ * (modulo the four uninitialised header padding bytes), decoded coordinates bit-identical, and
+ * repeats it against committed fixtures (tests/golden/golden.npz) generated from the reference by
+ * tests/golden/make_golden.py.  The text functions (PDB writer, extract, continuised angles) are
+ * pinned the same way by tests/test_text.py (tests/golden/text_golden.npz, make_text_golden.py) and
+ * tests/test_db_host.py (the reference's own CPython module, oracle/_ref/pyref).
  */
 #ifndef FCZ_ORACLE_H
 #define FCZ_ORACLE_H
