@@ -27,5 +27,10 @@ for c, name in enumerate(names):
         out[f"pdb_text_{name}"] = np.frombuffer(txt, np.uint8)
     for t, d in ((0, 1), (0, 2), (0, 3), (0, 4), (1, 0)):
         out[f"extract_{name}_{t}_{d}"] = np.frombuffer(H.ref_extract(blob, t, d), np.uint8)
+# the reference's own committed extract fixtures (test/test_af.fcz, test/test_af.plddt, test/test_af.plddt.tsv), verbatim
+REF_TEST = "/root/reference/test"
+out["upstream_test_af_fcz"] = np.frombuffer(open(os.path.join(REF_TEST, "test_af.fcz"), "rb").read(), np.uint8)
+out["upstream_test_af_plddt"] = np.frombuffer(open(os.path.join(REF_TEST, "test_af.plddt"), "rb").read(), np.uint8)
+out["upstream_test_af_plddt_tsv"] = np.frombuffer(open(os.path.join(REF_TEST, "test_af.plddt.tsv"), "rb").read(), np.uint8)
 np.savez_compressed(os.path.join(HERE, "text_golden.npz"), **out)
 print("wrote", len(out), "entries")

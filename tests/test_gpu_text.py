@@ -133,3 +133,19 @@ def test_text_entry_points_on_empty_batches(engine):
     assert engine.extract_host(HostBlobBatch.from_blobs([]), 1).n_chains == 0
     off, ang = engine.unpack_angles_host(HostBlobBatch.from_blobs([]))
     assert len(off) == 1 and ang.shape == (0, 6)
+
+
+def test_extract_matches_the_references_committed_fixtures(engine):
+    """The reference repository's own extract goldens (test/test_af.plddt, test/test_af.plddt.tsv) for its upstream-encoded
+    test/test_af.fcz, committed verbatim in tests/golden/text_golden.npz."""
+    tg = np.load(os.path.join(HERE, "golden", "text_golden.npz"))
+    blob = bytes(tg["upstream_test_af_fcz"])
+    digits1 = bytes(tg["upstream_test_af_plddt"]).split(b"\n")[1]
+    _, n_res, digits4 = bytes(tg["upstream_test_af_plddt_tsv"]).rstrip(b"\n").split(b"\t")
+    hb = HostBlobBatch.from_blobs([blob])
+    assert engine.extract_host(hb, 0, 1).text(0) == digits1
+    assert engine.extract_host(hb, 0, 4).text(0) == digits4
+    assert len(engine.extract_host(hb, 1).text(0)) == int(n_res)
+    # and the blob decodes (an upstream-encoded file, header floats differ in the last bit from a local encode)
+    dec = engine.decode_host(hb)
+    assert dec.status[0] == 0 and dec.n_res == int(n_res)

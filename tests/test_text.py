@@ -94,3 +94,16 @@ def test_oracle_text_matches_reference_live(golden):
         assert H.ref_decompress_to_pdb(blob, True) == H.oracle_format_pdb(alt, 0, True), name
         for t, d in ((0, 1), (0, 2), (0, 3), (0, 4), (1, 0)):
             assert H.ref_extract(blob, t, d) == H.oracle_extract(blob, t, d), (name, t, d)
+
+
+def test_extract_matches_the_references_committed_fixtures(text_golden):
+    """test/test_af.plddt (one digit per residue) and test/test_af.plddt.tsv (four digits) of the reference repository,
+    produced upstream from the upstream-encoded test/test_af.fcz."""
+    blob = bytes(text_golden["upstream_test_af_fcz"])
+    header, digits1 = bytes(text_golden["upstream_test_af_plddt"]).split(b"\n")[:2]
+    assert header.startswith(b">")
+    name, n_res, digits4 = bytes(text_golden["upstream_test_af_plddt_tsv"]).rstrip(b"\n").split(b"\t")
+    for fn in (H.oracle_extract, H.emu_extract):
+        assert fn(blob, 0, 1) == digits1
+        assert fn(blob, 0, 4) == digits4
+        assert len(fn(blob, 1, 0)) == int(n_res)
