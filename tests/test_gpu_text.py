@@ -149,3 +149,6 @@ def test_extract_matches_the_references_committed_fixtures(engine):
     # and the blob decodes (an upstream-encoded file, header floats differ in the last bit from a local encode)
     dec = engine.decode_host(hb)
     assert dec.status[0] == 0 and dec.n_res == int(n_res)
+    want = H.oracle_decode(blob)
+    assert np.array_equal(dec.res_type, want.res_type) and np.array_equal(dec.bfactor, want.bfactor)
+    assert H.max_dev(dec.xyz, want.xyz) <= 0.05
