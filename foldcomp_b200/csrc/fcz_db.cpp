@@ -68,24 +68,48 @@ static int parse_int_field(const char* s, size_t n) {  // std::stoi on the field
 }
 
 struct RawAtom {
-    char name[5];
-    char res[4];
+    uint32_t name;  // trimmed atom name, up to four characters packed little-endian (0-padded)
+    uint32_t res;   // trimmed residue name, same packing
     int serial, resnum;
     float x, y, z, b;
 };
 
-static void trim_copy(char* dst, size_t cap, const char* s, size_t n) {  // trim(" \t") of the reference
+// trim(" \t") of the reference, then the first four characters as one integer key
+static uint32_t trim_key(const char* s, size_t n) {
     size_t a = 0, b = n;
     while (a < b && (s[a] == ' ' || s[a] == '\t')) a++;
     while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\t')) b--;
-    size_t k = b - a < cap - 1 ? b - a : cap - 1;
-    memcpy(dst, s + a, k);
-    dst[k] = 0;
+    uint32_t k = 0;
+    for (size_t i = a; i < b && i < a + 4; i++) k |= (uint32_t)(uint8_t)s[i] << (8 * (i - a));
+    return k;
+}
+static uint32_t key_of(const char* z) {
+    uint32_t k = 0;
+    for (int i = 0; i < 4 && z[i]; i++) k |= (uint32_t)(uint8_t)z[i] << (8 * i);
+    return k;
+}
+struct NameKeys {
+    uint32_t atom[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
+    uint32_t res3[FCZ_NUM_CODES];
+    uint32_t ca, oxt;
+    NameKeys() {
+        for (int c = 0; c < FCZ_NUM_CODES; c++) {
+            res3[c] = key_of(FCZ_NAME3[c]);
+            for (int k = 0; k < FCZ_MAX_ATOMS; k++) atom[c][k] = key_of(FCZ_ATOM_NAME[c][k]);
+        }
+        ca = key_of("CA");
+        oxt = key_of("OXT");
+    }
+};
+static const NameKeys& name_keys() {
+    static const NameKeys k;
+    return k;
 }
 
-static int code_of3(const char* r) {
+static int code_of_key(uint32_t r) {
+    const NameKeys& nk = name_keys();
     for (int c = 0; c < FCZ_NUM_CODES; c++)
-        if (!strcmp(FCZ_NAME3[c], r)) return FCZ_NATOMS[c] ? c : FCZ_CODE_UNK;
+        if (nk.res3[c] == r) return FCZ_NATOMS[c] ? c : FCZ_CODE_UNK;
     return FCZ_CODE_UNK;
 }
 
@@ -109,24 +133,28 @@ int parsePdbChain(const char* text, size_t len, const std::string& title, Canoni
         if (ch != chain) return 2;
         if (n < 61) return 3;  // the B-factor column starts at 60
         RawAtom a;
-        trim_copy(a.name, sizeof a.name, line + 12, 4);
-        trim_copy(a.res, sizeof a.res, line + 17, 3);
+        a.name = trim_key(line + 12, 4);
+        a.res = trim_key(line + 17, 3);
         a.serial = parse_int_field(line + 6, 5);
         a.resnum = parse_int_field(line + 22, 4);
         a.x = parseFixedFloat(line + 30, 8);
         a.y = parseFixedFloat(line + 38, 8);
         a.z = parseFixedFloat(line + 46, 8);
         a.b = parseFixedFloat(line + 60, n - 60 < 6 ? n - 60 : 6);
-        if (!atoms.empty() && !strcmp(atoms.back().name, a.name)) continue;  // removeAlternativePosition
+        if (!atoms.empty() && atoms.back().name == a.name) continue;  // removeAlternativePosition
         atoms.push_back(a);
     }
     if (atoms.empty()) return 1;
     const size_t n = atoms.size();
+    out.xyz.reserve(3 * n + 64);
+    out.res_type.reserve(n / 4 + 8);
+    out.bfactor.reserve(n / 4 + 8);
     out.meta.n_atom = (uint16_t)n;
     out.meta.idx_residue = (uint16_t)atoms[0].resnum;
     out.meta.idx_atom = (uint16_t)atoms[0].serial;
     out.meta.chain = (uint8_t)chain;
-    if (!strcmp(atoms[n - 1].name, "OXT")) {  // src/foldcomp.cpp:473-481
+    const NameKeys& nk = name_keys();
+    if (atoms[n - 1].name == nk.oxt) {  // src/foldcomp.cpp:473-481
         out.meta.has_oxt = 1;
         out.meta.oxt[0] = atoms[n - 1].x; out.meta.oxt[1] = atoms[n - 1].y; out.meta.oxt[2] = atoms[n - 1].z;
     }
@@ -134,18 +162,28 @@ int parsePdbChain(const char* text, size_t len, const std::string& title, Canoni
     while (i < n) {  // splitAtomByResidue (src/atom_coordinate.cpp:304-328): the last atom joins the current residue
         size_t j = i + 1;
         while (j < n && (atoms[j].resnum == atoms[j - 1].resnum || j == n - 1)) j++;
-        const int code = code_of3(atoms[i].res);
+        const int code = code_of_key(atoms[i].res);
         out.res_type.push_back((uint8_t)code);
         for (int k = 0; k < FCZ_NATOMS[code]; k++) {
-            const char* want = FCZ_ATOM_NAME[code][k];
+            const uint32_t want = nk.atom[code][k];
             float x = 0, y = 0, z = 0;  // findFirstAtomCoords: a missing atom reads as (0,0,0)
-            for (size_t a = i; a < j; a++)
-                if (!strcmp(atoms[a].name, want)) { x = atoms[a].x; y = atoms[a].y; z = atoms[a].z; break; }
+            // the FIRST atom of that name in the residue; files written in table order hit it at position k, but an
+            // earlier duplicate name must still win, so the prefix is checked before the shortcut is taken
+            size_t hit = j;
+            if (i + k < j && atoms[i + k].name == want) {
+                hit = i + k;
+                for (size_t a = i; a < i + k; a++)
+                    if (atoms[a].name == want) { hit = a; break; }
+            } else {
+                for (size_t a = i; a < j; a++)
+                    if (atoms[a].name == want) { hit = a; break; }
+            }
+            if (hit < j) { x = atoms[hit].x; y = atoms[hit].y; z = atoms[hit].z; }
             out.xyz.push_back(x); out.xyz.push_back(y); out.xyz.push_back(z);
         }
         float bf = 0.f;
         for (size_t a = i; a < j; a++)
-            if (!strcmp(atoms[a].name, "CA")) { bf = atoms[a].b; break; }
+            if (atoms[a].name == nk.ca) { bf = atoms[a].b; break; }
         out.bfactor.push_back(bf);
         i = j;
     }
