@@ -3,7 +3,7 @@
 collective on the data path, ONE merged foldcomp database written by all ranks.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        tools/config4.py --chains-per-gpu 250000 --out /tmp/merged_db        # N = 8 -> 2 M chains, 700 M residues
+        tests/run_config4.py --chains-per-gpu 250000 --out /tmp/merged_db        # N = 8 -> 2 M chains, 700 M residues
 
 Every rank owns chains [rank * chains_per_gpu, (rank + 1) * chains_per_gpu): 10 000 synthetic chains (the bench.py
 generator, rank-specific seed offset) tiled on the device.  Encode runs with opts.terminate_blobs, so the rank's
