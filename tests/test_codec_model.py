@@ -74,3 +74,42 @@ def test_model_long_chains_up_to_format_maximum():
         do, de = H.oracle_decode(o), H.emu_decode(o)
         bb = H.backbone_mask(do.res_type)
         assert H.rmsd(de.xyz[bb], do.xyz[bb]) <= TOL_BB_RMSD and H.max_dev(de.xyz, do.xyz) <= TOL_MAX, (L, b)
+
+
+def test_model_encode_degenerate_inputs_match_oracle_and_reference():
+    """Inputs on which the reference's arithmetic leaves the beaten path -- constant B-factors (its discretiser divides
+    by zero and casts NaN), coincident atoms (NaN cosines), missing atoms at (0,0,0), collinear triples, NaN / inf
+    coordinates, integer-lattice coordinates (exact ties), two-valued B-factors: the product codec, the oracle and, when
+    present, the unmodified reference must still agree byte for byte."""
+    rng = np.random.default_rng(7)
+    for trial in range(120):
+        L = int(rng.integers(2, 60))
+        batch = synth.generate(1, L, seed=1000 + trial)
+        x, bf = batch.xyz.copy(), batch.bfactor.copy()
+        A, kind = len(x), trial % 10
+        if kind == 0:
+            bf[:] = 50.0
+        elif kind == 1:
+            x[rng.integers(0, A)] = x[rng.integers(0, A)]
+        elif kind == 2:
+            x[rng.integers(0, A, 3)] = 0.0
+        elif kind == 3:
+            x *= np.float32(100.0)
+        elif kind == 4:
+            x[2] = x[1] + (x[1] - x[0])
+        elif kind == 5:
+            x[rng.integers(0, A)] = np.nan
+        elif kind == 6:
+            bf[rng.integers(0, L)] = np.nan
+        elif kind == 7:
+            x[:] = np.round(x)
+        elif kind == 8:
+            x[rng.integers(0, A)] = np.inf
+        else:
+            bf[:] = rng.choice([0.0, 100.0], L)
+        batch.xyz, batch.bfactor = x, bf
+        for b in (25, 10):
+            o = H.oracle_encode(batch, 0, b)
+            assert H.emu_encode(batch, 0, b) == o, (kind, trial, b)
+            if H.have_ref():
+                assert H.masked(H.ref_encode(batch, 0, b)) == H.masked(o), (kind, trial, b)
