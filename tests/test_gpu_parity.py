@@ -256,6 +256,57 @@ def test_long_chains_up_to_format_maximum(engine, device_api):
             engine.set_opts(anchor_threshold=25)
 
 
+def test_degenerate_inputs(engine):
+    """Constant B-factors (the reference's discretiser divides by zero and casts NaN), coincident atoms (NaN cosines),
+    missing atoms at (0,0,0), collinear triples, NaN / inf coordinates, integer-lattice coordinates, two-valued
+    B-factors: byte-identical to the oracle (which test_codec_model.py pins to the unmodified reference on the same
+    inputs).  One known deviation, excluded here and documented in DESIGN.md section 5: a NaN in the FIRST B-factor makes
+    the header's tempMin / cont_f NaN, and a NaN PRODUCED by GPU arithmetic carries the canonical payload 0x7fffffff
+    where x86 propagates the operand's payload -- the blob has the same size and is equally meaningless in both."""
+    rng = np.random.default_rng(7)
+    parts, nan_first = [], []
+    for trial in range(120):
+        L = int(rng.integers(2, 60))
+        batch = synth.generate(1, L, seed=1000 + trial)
+        x, bf = batch.xyz.copy(), batch.bfactor.copy()
+        A, kind = len(x), trial % 10
+        if kind == 0:
+            bf[:] = 50.0
+        elif kind == 1:
+            x[rng.integers(0, A)] = x[rng.integers(0, A)]
+        elif kind == 2:
+            x[rng.integers(0, A, 3)] = 0.0
+        elif kind == 3:
+            x *= np.float32(100.0)
+        elif kind == 4:
+            x[2] = x[1] + (x[1] - x[0])
+        elif kind == 5:
+            x[rng.integers(0, A)] = np.nan
+        elif kind == 6:
+            bf[rng.integers(0, L)] = np.nan
+        elif kind == 7:
+            x[:] = np.round(x)
+        elif kind == 8:
+            x[rng.integers(0, A)] = np.inf
+        else:
+            bf[:] = rng.choice([0.0, 100.0], L)
+        batch.xyz, batch.bfactor = x, bf
+        parts.append(batch)
+        nan_first.append(bool(np.isnan(bf[0])))
+    big = abi.concat_batches(parts)
+    try:
+        for b in (25, 10):
+            engine.set_opts(anchor_threshold=b)
+            got = engine.encode_host(big)
+            want = H.oracle_encode_batch(big, b)
+            assert not got.status.any()
+            assert np.array_equal(got.blob_off, want.blob_off)
+            bad = [c for c in range(big.n_chains) if got.blob(c) != want.blob(c) and not nan_first[c]]
+            assert not bad, (b, bad)
+    finally:
+        engine.set_opts(anchor_threshold=25)
+
+
 # ------------------------------------------------------------------------------ full-size config 2
 
 
