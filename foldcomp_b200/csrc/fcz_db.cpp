@@ -221,6 +221,15 @@ bool DbReader::open(const std::string& path) {
         p = e;
         while (*p == '\n' || *p == '\r' || *p == ' ' || *p == '\t') p++;
     }
+    {   // entries by key, like the reference's reader (std::sort by id, src/database_reader.cpp:109); stable for equal keys
+        std::vector<size_t> perm(keys_.size());
+        for (size_t i = 0; i < perm.size(); i++) perm[i] = i;
+        std::stable_sort(perm.begin(), perm.end(), [&](size_t x, size_t y) { return keys_[x] < keys_[y]; });
+        std::vector<uint32_t> k2(keys_.size());
+        std::vector<uint64_t> o2(keys_.size()), l2(keys_.size());
+        for (size_t i = 0; i < perm.size(); i++) { k2[i] = keys_[perm[i]]; o2[i] = offsets_[perm[i]]; l2[i] = lengths_[perm[i]]; }
+        keys_.swap(k2); offsets_.swap(o2); lengths_.swap(l2);
+    }
     fd_ = ::open(path.c_str(), O_RDONLY);
     if (fd_ < 0) return false;
     struct stat st;

@@ -36,7 +36,8 @@ public:
     ~DbReader();
     DbReader(const DbReader&) = delete;
     DbReader& operator=(const DbReader&) = delete;
-    // data file `path`, index `path`.index, names from `path`.lookup when present.  Returns false on error.
+    // data file `path`, index `path`.index, names from `path`.lookup when present; entries are ordered by key like the
+    // reference's reader (src/database_reader.cpp:109).  Returns false on error.
     bool open(const std::string& path);
     size_t size() const { return keys_.size(); }
     uint32_t key(size_t i) const { return keys_[i]; }

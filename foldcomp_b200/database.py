@@ -37,6 +37,7 @@ class FoldcompDatabase:
         if not isinstance(err_on_missing, bool):
             raise TypeError("err_on_missing must be a boolean")
         rows = np.loadtxt(path + ".index", dtype=np.int64, ndmin=2) if os.path.getsize(path + ".index") else np.zeros((0, 3), np.int64)
+        rows = rows[np.argsort(rows[:, 0], kind="stable")]  # the reference's reader sorts its index by key (database_reader.cpp:109)
         self._keys, self._off, self._len = rows[:, 0], rows[:, 1], rows[:, 2]
         self._f = builtins.open(path, "rb")
         self._mm = mmap.mmap(self._f.fileno(), 0, access=mmap.ACCESS_READ) if os.path.getsize(path) else None

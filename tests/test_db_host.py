@@ -115,3 +115,45 @@ def test_oracle_angles_match_reference_get_data(golden):
         dec = H.oracle_decode(blob)
         assert np.array_equal(f32(d["b_factors"]), dec.bfactor)
         assert d["residues"] == "".join("ARNDCQEGHILKMFPSTWYVBZ*X"[c] for c in dec.res_type)
+
+
+def test_python_database_raw_mode_and_ids(golden, tmp_path):
+    """foldcomp_b200.open(..., decompress=False): the reference's raw mode (foldcomp.cxx:52-80) needs no GPU."""
+    import foldcomp_b200
+
+    entries = [(k, f"name_{k}", golden.db_blobs[i]) for i, k in enumerate([4, 9, 2, 7])]
+    path = str(tmp_path / "db")
+    dbutil.write_db(path, entries)
+    with foldcomp_b200.open(path, decompress=False) as db:
+        by_key = [e[2] for e in sorted(entries)]  # entries come in key order, as from the reference's reader
+        assert len(db) == 4 and [db[i] for i in range(4)] == by_key and db[-1] == by_key[-1]
+        with pytest.raises(IndexError):
+            db[4]
+    with foldcomp_b200.open(path, ids=["name_7", "nope", "name_4"], decompress=False) as db:
+        assert len(db) == 2 and db[0] == entries[3][2] and db[1] == entries[0][2]
+    with pytest.raises(KeyError):
+        foldcomp_b200.open(path, ids=["nope"], decompress=False, err_on_missing=True)
+    for bad in ({"ids": "name_4"}, {"decompress": 1}, {"err_on_missing": "yes"}):
+        with pytest.raises(TypeError):
+            foldcomp_b200.open(path, **bad)
+    ref = dbutil.reference_module()
+    if ref is not None:
+        with ref.open(path, decompress=False) as rdb, foldcomp_b200.open(path, decompress=False) as db:
+            assert len(rdb) == len(db) and all(rdb[i] == db[i] for i in range(len(db)))
+        with ref.open(path, ids=["name_7", "name_4"], decompress=False) as rdb:
+            assert [rdb[i] for i in range(len(rdb))] == [entries[3][2], entries[0][2]]
+
+
+def test_db_copy_handles_unsorted_and_gapped_files(lib, tmp_path):
+    """Entries out of key order in the index, gaps between entries, and no lookup file."""
+    src = str(tmp_path / "src")
+    blobs = {5: b"five", 1: b"one-one", 3: b""}
+    with open(src, "wb") as d:
+        d.write(b"XX" + blobs[5] + b"\0" + b"GAP" + blobs[1] + b"\0" + blobs[3] + b"\0")
+    with open(src + ".index", "w") as ix:
+        ix.write("5\t2\t5\n1\t10\t8\n3\t18\t1\n")
+    dst = str(tmp_path / "dst")
+    assert lib.fczgpu_db_copy(src.encode(), dst.encode()) == 3
+    got = dbutil.read_db(dst)
+    assert got == [(1, "1", b"one-one"), (3, "3", b""), (5, "5", b"five")]  # names default to the key
+    assert lib.fczgpu_db_copy((src + "_missing").encode(), dst.encode()) < 0
