@@ -339,7 +339,7 @@ int decompressDb(Engine& eng, const std::string& in_db, const std::string& out_d
     DbWriter wr;
     if (!wr.open(out_db)) return FCZ_E_ARG;
     DbStats s;
-    fcz_opts o{25, altOrder ? 1 : 0, nullptr};
+    fcz_opts o{25, altOrder ? 1 : 0, nullptr, 0};
     int rc = fcz_engine_set_opts(eng.get(), &o);
     if (rc) return rc;
     const size_t n_all = rd.size();

@@ -123,7 +123,7 @@ int FoldcompGpu::compressBatch(Engine& eng, const std::vector<CanonicalChain>& c
     fcz_blob_batch out{};
     out.n_chains = n; out.mem = FCZ_MEM_HOST; out.blob_off = blob_off.data(); out.bytes = bytes.data();
     out.status = st.data(); out.bytes_cap = cap;
-    fcz_opts o{anchorThreshold, 0, nullptr};
+    fcz_opts o{anchorThreshold, 0, nullptr, 0};
     int rc = fcz_engine_set_opts(eng.get(), &o);
     if (rc) return rc;
     rc = fcz_encode_batch(eng.get(), &in, &out);
@@ -149,7 +149,7 @@ int FoldcompGpu::decompressBatch(Engine& eng, const std::vector<std::string>& bl
     fcz_chain_batch out{};
     out.n_chains = n; out.mem = FCZ_MEM_HOST;
     out.res_off = res_off.data(); out.atom_off = atom_off.data(); out.title_off = title_off.data(); out.status = st.data();
-    fcz_opts o{25, altOrder ? 1 : 0, nullptr};
+    fcz_opts o{25, altOrder ? 1 : 0, nullptr, 0};
     int rc = fcz_engine_set_opts(eng.get(), &o);
     if (rc) return rc;
     fcz_sizes sz{};
@@ -208,7 +208,7 @@ int FoldcompGpu::decompressToPdb(std::string& text) {
     in.n_chains = 1; in.mem = FCZ_MEM_HOST; in.blob_off = blob_off; in.bytes = (uint8_t*)&blob_[0];
     fcz_text_batch out{};
     out.n_chains = 1; out.mem = FCZ_MEM_HOST; out.text_off = text_off; out.status = st;
-    fcz_opts o{anchorThreshold, useAltAtomOrder ? 1 : 0, nullptr};
+    fcz_opts o{anchorThreshold, useAltAtomOrder ? 1 : 0, nullptr, 0};
     int rc = fcz_engine_set_opts(eng_.get(), &o);
     if (rc) return rc;
     uint64_t total = 0;
