@@ -151,3 +151,23 @@ def test_python_get_data_matches_oracle_and_reference(golden):
             assert np.abs(f32(r["coordinates"]) - f32(d["coordinates"])).max() <= 0.05
     with pytest.raises(ValueError):
         foldcomp_b200.get_data("ATOM      1  N   GLY A   1 ...")
+
+
+def test_python_compress_matches_oracle_and_reference_module(golden):
+    """foldcomp_b200.compress(name, pdb_text) -- the CPython module's compress (foldcomp.cxx:253-328) -- byte for byte."""
+    import foldcomp_b200
+
+    ref = dbutil.reference_module()
+    for c in (golden.names.index("test_af.pdb"), golden.names.index("test.pdb")):
+        text = H.oracle_format_pdb(golden.batch, c).decode("latin-1")
+        for b in (25, 50):
+            blob = foldcomp_b200.compress("entry", text, anchor_residue_threshold=b)
+            assert blob == H.oracle_encode(pdbio.parse_pdb_chain(text, "entry"), 0, b)
+            if ref is not None:
+                assert H.masked(blob) == H.masked(ref.compress("entry", text, anchor_residue_threshold=b))
+        name, pdb = foldcomp_b200.decompress(blob)
+        assert name == "entry" and pdb.count("\nATOM") + pdb.startswith("ATOM") == text.count("\nATOM") + text.startswith("ATOM")
+    with pytest.raises(foldcomp_b200.error):
+        foldcomp_b200.compress("x", "HEADER nothing here\n")
+    with pytest.raises(TypeError):
+        foldcomp_b200.compress("x", text, anchor_residue_threshold="25")
