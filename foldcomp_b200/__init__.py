@@ -48,10 +48,16 @@ def __getattr__(name):
 
 
 def compress(name: str, pdb_content: str, *, anchor_residue_threshold: int = abi.DEFAULT_ANCHOR_THRESHOLD) -> bytes:
-    from .pdbio import PdbError, parse_pdb_chain
+    from . import pdbnative
+    from .pdbio import PdbError
 
     if not isinstance(anchor_residue_threshold, int):
         raise TypeError("anchor_residue_threshold must be an integer")
+    # host-side text parsing: the C++ parser of the batch path when it is built, its Python mirror otherwise
+    if pdbnative.available():
+        parse_pdb_chain = pdbnative.parse_pdb_chain
+    else:
+        from .pdbio import parse_pdb_chain
     try:
         batch = parse_pdb_chain(pdb_content, name)
     except PdbError as e:

@@ -1,0 +1,51 @@
+"""The C++ fixed-column ATOM parser (foldcomp_b200/csrc/fcz_db.cpp: parsePdbChain) behind ctypes: what compress() uses to
+turn PDB text into a canonical chain (~0.5 ms per 350-residue chain instead of ~60 ms in pdbio.py's Python mirror).
+Same flags as the reference's parser (foldcomp/foldcomp.cxx:253-293): 1 = no ATOM line, 2 = several chains."""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import os
+
+import numpy as np
+
+from .abi import META_DTYPE, HostChainBatch, concat_chains
+from .pdbio import PdbError
+
+_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libfoldcomp_gpu.so")
+
+
+@functools.lru_cache(maxsize=1)
+def _lib():
+    lib = C.CDLL(_SO)
+    lib.fczgpu_parse_pdb.restype = C.c_int
+    lib.fczgpu_parse_pdb.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32),
+                                     C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32]
+    return lib
+
+
+def available() -> bool:
+    return os.path.exists(_SO)
+
+
+def parse_pdb_chain(pdb_text: str, title: str) -> HostChainBatch:
+    data = pdb_text.encode("latin-1") if isinstance(pdb_text, str) else bytes(pdb_text)
+    n_lines = data.count(b"\n") + 1
+    cap_a = n_lines + 16          # one ATOM line per atom at most ...
+    cap_r = n_lines + 16          # ... and every residue has at least one; missing atoms only add slots:
+    cap_a = 14 * cap_r            # a residue owns up to 14 table slots whatever the file lists
+    rt = np.zeros(cap_r, np.uint8)
+    bf = np.zeros(cap_r, np.float32)
+    xyz = np.zeros((cap_a, 3), np.float32)
+    meta = np.zeros(1, META_DTYPE)
+    nr, na = C.c_uint32(), C.c_uint32()
+    flag = _lib().fczgpu_parse_pdb(data, len(data), rt.ctypes.data, bf.ctypes.data, xyz.ctypes.data, meta.ctypes.data,
+                                   C.byref(nr), C.byref(na), cap_r, cap_a)
+    if flag == 1:
+        raise PdbError("No ATOM lines found")
+    if flag == 2:
+        raise PdbError("Multiple chains found")
+    if flag != 0:
+        raise PdbError("Malformed ATOM record")
+    tbytes = np.frombuffer(title.encode("latin-1"), np.uint8)
+    return concat_chains([(rt[: nr.value].copy(), bf[: nr.value].copy(), xyz[: na.value].copy(), tbytes, meta)])

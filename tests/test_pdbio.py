@@ -70,3 +70,22 @@ def test_format_roundtrips_through_parser(golden):
     assert np.array_equal(back.res_type, dec.res_type)
     assert np.abs(back.xyz - dec.xyz).max() <= 0.00051
     assert back.meta[0]["has_oxt"] == 1
+
+
+def test_native_parser_face_equals_python_mirror(golden):
+    """foldcomp_b200.pdbnative (ctypes over the C++ parser, what compress() uses) against pdbio on texts with noise."""
+    from foldcomp_b200 import pdbnative
+
+    assert pdbnative.available()
+    for c in range(len(golden.names)):
+        text = H.oracle_format_pdb(golden.batch, c).decode("latin-1")
+        a, b = pdbnative.parse_pdb_chain(text, "t"), pdbio.parse_pdb_chain(text, "t")
+        for f in ("res_off", "atom_off", "title_off", "res_type", "bfactor", "xyz", "titles"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), (c, f)
+        assert a.meta.tobytes() == b.meta.tobytes()
+    a, b = pdbnative.parse_pdb_chain(PDB, "tiny"), pdbio.parse_pdb_chain(PDB, "tiny")
+    assert np.array_equal(a.xyz, b.xyz) and a.meta.tobytes() == b.meta.tobytes() and a.n_atoms == 9
+    with pytest.raises(pdbio.PdbError, match="No ATOM"):
+        pdbnative.parse_pdb_chain("HEADER x\n", "t")
+    with pytest.raises(pdbio.PdbError, match="Multiple chains"):
+        pdbnative.parse_pdb_chain(PDB.replace("ALA A   6", "ALA B   6"), "t")
