@@ -27,6 +27,7 @@ SYMBOLS = [
     "fcz_decode_to_pdb_plan",
     "fcz_decode_to_pdb_batch",
     "fcz_extract_batch",
+    "fcz_check_batch",
     "fcz_unpack_angles_batch",
     "fcz_engine_sync",
     "fcz_engine_launch_count",
@@ -82,6 +83,8 @@ def load() -> C.CDLL:
     lib.fcz_decode_to_pdb_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), P(abi.FczTextBatch)]
     lib.fcz_extract_batch.restype = C.c_int
     lib.fcz_extract_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), C.c_int32, C.c_int32, P(abi.FczTextBatch), P(C.c_uint64)]
+    lib.fcz_check_batch.restype = C.c_int
+    lib.fcz_check_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), C.c_void_p, C.c_void_p]
     lib.fcz_unpack_angles_batch.restype = C.c_int
     lib.fcz_unpack_angles_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), C.c_void_p, C.c_void_p, C.c_uint64, P(C.c_uint64)]
     lib.fcz_engine_sync.restype = C.c_int

@@ -25,6 +25,27 @@ FCZ_E_ARG = -7
 
 DEFAULT_ANCHOR_THRESHOLD = 25  # src/foldcomp.h:56
 
+# ValidityError classes (src/foldcomp.h:59-67) as fcz_check_batch reports them, with printValidityError's messages
+# (src/foldcomp.cpp:1534-1561)
+VALIDITY = (
+    "SUCCESS",
+    "E_BACKBONE_COUNT_MISMATCH",
+    "E_SIDECHAIN_COUNT_MISMATCH",
+    "E_TEMP_FACTOR_COUNT_MISMATCH",
+    "E_EMPTY_BACKBONE_ANGLE",
+    "E_EMPTY_SIDECHAIN_ANGLE",
+    "E_EMPTY_TEMP_FACTOR",
+)
+VALIDITY_MESSAGE = (
+    "",
+    "[Error] Number of backbone angles does not match header: ",
+    "[Error] Number of sidechain angles does not match header: ",
+    "[Error] Number of temperature factors does not match header: ",
+    "[Error] All backbone angles are empty: ",
+    "[Error] All sidechain angles are empty: ",
+    "[Error] All temperature factors are empty: ",
+)
+
 
 class FczOpts(C.Structure):
     _fields_ = [("anchor_threshold", C.c_int32), ("use_alt_atom_order", C.c_int32), ("stream", C.c_void_p), ("terminate_blobs", C.c_int32)]

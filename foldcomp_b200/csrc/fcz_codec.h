@@ -24,18 +24,23 @@
 
 namespace fcz {
 
-// Device-friendly copy of the residue tables (built once from fcz_tables.h).
+// Device-friendly copy of the residue tables (built once from fcz_tables.h).  FCZ_CODE_ROWS = 32 rows: a record's
+// residue field has five bits, and the reference maps every value its switch does not know (24..31) to UNK
+// (convertIntToOneLetterCode / convertIntToThreeLetterCode default branch, src/utility.cpp:297-377, 461-), so rows
+// 24..31 repeat the UNK row: a raw code from an untrusted blob indexes these tables safely and decodes as the
+// reference decodes it.  Encode INPUT codes must be < FCZ_NUM_CODES (the plans check).
+// (FCZ_CODE_ROWS and norm_code live in fcz_format.h.)
 struct Tables {
-    uint8_t natoms[FCZ_NUM_CODES];
-    uint8_t name1[FCZ_NUM_CODES];  // one-letter codes (header firstResidue / lastResidue)
-    uint8_t alt[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
-    uint16_t pred[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
+    uint8_t natoms[FCZ_CODE_ROWS];
+    uint8_t name1[FCZ_CODE_ROWS];  // one-letter codes (header firstResidue / lastResidue)
+    uint8_t alt[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];
+    uint16_t pred[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];
     // side-chain byte as a step function of cos(torsion) (see build_tables), both tables increasing:
     // non-negated torsion: byte = 127 + #{i: -c >= sc_pos[i]};  negated torsion: byte = #{i: c >= sc_neg[i]}
     float sc_pos[128];
     float sc_neg[128];
-    float blen[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
-    cs bang[FCZ_NUM_CODES][FCZ_MAX_ATOMS];  // (cos, sin) of the table bond angle
+    float blen[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];
+    cs bang[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];  // (cos, sin) of the table bond angle
     cs sc_tor[256];  // (cos, sin) of every side-chain torsion byte: FixedAngleDiscretizer(255).continuize(b)
 };
 
@@ -94,16 +99,17 @@ inline void build_tables(Tables* t) {
             }
         }
     }
-    for (int c = 0; c < FCZ_NUM_CODES; c++) {
-        t->natoms[c] = FCZ_NATOMS[c];
-        t->name1[c] = (uint8_t)FCZ_NAME1[c];
+    for (int row = 0; row < FCZ_CODE_ROWS; row++) {
+        const int c = (int)norm_code((unsigned)row);
+        t->natoms[row] = FCZ_NATOMS[c];
+        t->name1[row] = (uint8_t)FCZ_NAME1[c];
         for (int k = 0; k < FCZ_MAX_ATOMS; k++) {
-            t->alt[c][k] = FCZ_ALT[c][k];
-            t->pred[c][k] = FCZ_PRED[c][k];
-            t->blen[c][k] = FCZ_BLEN[c][k];
+            t->alt[row][k] = FCZ_ALT[c][k];
+            t->pred[row][k] = FCZ_PRED[c][k];
+            t->blen[row][k] = FCZ_BLEN[c][k];
             float r = (float)((double)FCZ_BANG[c][k] * M_PI / 180.0);
-            t->bang[c][k].c = cosf(r);
-            t->bang[c][k].s = sinf(r);
+            t->bang[row][k].c = cosf(r);
+            t->bang[row][k].s = sinf(r);
         }
     }
     for (int b = 0; b < 256; b++) {  // src/foldcomp.cpp:338-369 + src/nerf.cpp:64,66-70
@@ -168,6 +174,25 @@ FCZ_HD uint8_t sc_byte_fast(const Tables* tb, DotParts dp, bool neg) {
 FCZ_HD f3 bb_atom(const EncChain& ch, uint32_t j) {  // j-th backbone atom (N,CA,C = slots 0..2)
     uint32_t r = j / 3u, k = j - 3u * r;
     return ld3(ch.X + 3u * (ch.aoff[r] + k));
+}
+
+// The NaN an x86-64 build of the reference leaves in a bond angle at backbone atom m (angle(), src/float3d.h:55-65, over
+// getCosineTheta 36-43 and the library acos) -- needed only when that angle is the FIRST of its array, because then it
+// becomes the header's min / cont_f and reaches the file (src/discretizer.cpp:27-32).  SSE arithmetic returns a NaN
+// operand quieted (payload and sign kept); an invalid operation on non-NaN operands (0/0 for coincident atoms,
+// inf - inf, inf/inf for infinite coordinates) returns the default NaN 0xFFC00000; conversions float <-> double and
+// glibc's acos ((x-x)/(x-x)) keep both.  So: the quieted first NaN among the nine input floats, else the default NaN.
+// (With several DIFFERENT NaN payloads among the nine inputs the winner depends on the compiler's operand order --
+// two builds of the reference disagree with each other there; the scan order below is one valid choice.)
+FCZ_HD float x86_angle_nan(const EncChain& ch, uint32_t m) {
+    const uint32_t order[3] = {m - 1u, m, m + 1u};
+    for (int i = 0; i < 3; i++) {
+        const f3 p = bb_atom(ch, order[i]);
+        if (p.x != p.x) return u2f(f2u(p.x) | 0x00400000u);
+        if (p.y != p.y) return u2f(f2u(p.y) | 0x00400000u);
+        if (p.z != p.z) return u2f(f2u(p.z) | 0x00400000u);
+    }
+    return u2f(0xFFC00000u);
 }
 
 template <class Ctx>
@@ -297,12 +322,25 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
                 hi = max_ignore_nan(hi, ch.red[w * 14 + 7 + k]);
             }
             float first = (k < 6) ? ch.ang[k * L] : ch.bfac[0];
-            if (first != first) { lo = first; hi = first; }  // min_element/max_element keep a NaN first element
+            if (first != first) {  // min_element/max_element keep a NaN first element
+                // A bond angle that came out NaN: WHICH NaN is hardware business (see x86_angle_nan); B-factors are input
+                // and are copied bit for bit (this->min = *std::min_element(...) is a plain move).
+                if (k >= 3 && k < 6) first = x86_angle_nan(ch, k == A_CACN ? 2u : (k == A_CNCA ? 3u : 4u));
+                lo = first; hi = first;
+            }
             unsigned nb = (k < 6) ? n_bins(k) : 255u;
             float* prm = res + 14 + 3 * k;
             prm[0] = lo;
             prm[1] = disc_factor(lo, hi, nb);
             prm[2] = cont_factor(lo, hi, nb);
+            if (prm[2] != prm[2]) {
+                // (max - min) is NaN: x86 propagates the quieted NaN operand (min = max = the NaN first element) through
+                // the subtraction and the division, and produces its default NaN (negative, 0xFFC00000) for inf - inf;
+                // a GPU would put its canonical 0x7FFFFFFF into the header instead (src/discretizer.cpp:27-32).
+                const float nanv = u2f(lo != lo ? (f2u(lo) | 0x00400000u) : 0xFFC00000u);
+                prm[1] = nanv;
+                prm[2] = nanv;
+            }
         }
         cx.sync();
         cx.mark(2);  // E_MINMAX
@@ -449,7 +487,7 @@ FCZ_HD void dec_unpack(Ctx& cx, const Tables* tb, const DecChain& ch) {
         const float tmin = get_f32(blob + y.o_temp), tcf = get_f32(blob + y.o_temp + 4);
         for (uint32_t r = cx.tid; r < L; r += cx.nthr) {
             Record q = unpack_record(rec + 8u * r);
-            ch.out_type[r] = (uint8_t)q.res;
+            ch.out_type[r] = (uint8_t)norm_code(q.res);  // 24..31 decode as UNK (see Tables)
             ch.out_bfac[r] = continuize(blob[y.o_temp + 8u + r], tmin, tcf);  // src/foldcomp.cpp:884-886
             if (r + 1u < L) {
                 ch.tor[3u * r + 0u] = cossin_deg(continuize(q.psi, mins[A_PSI], cfs[A_PSI]));

@@ -240,8 +240,8 @@ bool DbReader::open(const std::string& path) {
         if (m == MAP_FAILED) return false;
         base_ = (const char*)m;
     }
-    for (size_t i = 0; i < keys_.size(); i++)
-        if (offsets_[i] + lengths_[i] > bytes_) return false;
+    for (size_t i = 0; i < keys_.size(); i++)  // no sum: offset + length of a malformed row may wrap
+        if (lengths_[i] > bytes_ || offsets_[i] > bytes_ - lengths_[i]) return false;
     std::string lk;
     if (read_file(path + ".lookup", lk)) {
         names_.assign(keys_.size(), std::string());
@@ -284,10 +284,10 @@ bool DbWriter::open(const std::string& path) {
     data_ = fopen(path.c_str(), "wb");
     if (!data_) return false;
     FILE* t = fopen((path + ".dbtype").c_str(), "wb");
-    if (!t) return false;
+    if (!t) { fclose(data_); data_ = nullptr; return false; }
     const int type = 12;  // generic dbtype, src/database_writer.cpp:51-55
-    fwrite(&type, sizeof type, 1, t);
-    fclose(t);
+    const bool ok = fwrite(&type, sizeof type, 1, t) == 1;
+    if (fclose(t) != 0 || !ok) { fclose(data_); data_ = nullptr; return false; }
     pos_ = 0;
     return true;
 }
@@ -305,20 +305,24 @@ bool DbWriter::append(const char* data, size_t len, uint32_t key, const std::str
 
 bool DbWriter::close() {
     if (!data_) return true;
-    fclose(data_);
+    bool ok = fclose(data_) == 0;  // a full disk shows up here at the latest: never report a truncated database as written
     data_ = nullptr;
     std::stable_sort(entries_.begin(), entries_.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
     FILE* idx = fopen((path_ + ".index").c_str(), "w");
     FILE* lk = fopen((path_ + ".lookup").c_str(), "w");
-    if (!idx || !lk) return false;
-    for (const Entry& e : entries_) {
-        fprintf(idx, "%u\t%llu\t%llu\n", e.key, (unsigned long long)e.offset, (unsigned long long)e.length);
-        fprintf(lk, "%u\t%s\t0\n", e.key, names_[e.name].c_str());
+    if (!idx || !lk) {
+        if (idx) fclose(idx);
+        if (lk) fclose(lk);
+        return false;
     }
-    fclose(idx);
-    fclose(lk);
+    for (const Entry& e : entries_) {
+        ok &= fprintf(idx, "%u\t%llu\t%llu\n", e.key, (unsigned long long)e.offset, (unsigned long long)e.length) > 0;
+        ok &= fprintf(lk, "%u\t%s\t0\n", e.key, names_[e.name].c_str()) > 0;
+    }
+    ok &= fclose(idx) == 0;
+    ok &= fclose(lk) == 0;
     entries_.clear();
-    return true;
+    return ok;
 }
 
 // ------------------------------------------------------------------------------------- whole-db passes

@@ -1067,6 +1067,54 @@ __global__ void __launch_bounds__(128) k_extract(ExtractArgs a) {
     extract_chain(cx, a.tt, blob, y, a.type, a.digits, a.text + a.text_off[c]);
 }
 
+// Foldcomp::read + checkValidity (src/foldcomp.cpp:904-1036, 1492-1532) for every blob: one warp per blob scans the
+// record, side-chain and B-factor sections for a non-zero entry (see fcz_check_batch in include/fcz_engine.h).
+struct CheckArgs {
+    const uint64_t* blob_off;
+    const uint8_t* bytes;
+    uint32_t n;
+    int32_t* read_status;  // may be null
+    int32_t* validity;     // may be null
+};
+__global__ void __launch_bounds__(256) k_check(CheckArgs a) {
+    const uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31u;
+    if (c >= a.n) return;
+    const uint8_t* blob = a.bytes + a.blob_off[c];
+    const uint64_t len = a.blob_off[c + 1] - a.blob_off[c];
+    int st = FCZ_OK, v = FCZ_V_SUCCESS;
+    if (len < 4u || blob[0] != 'F' || blob[1] != 'C' || blob[2] != 'M' || blob[3] != 'P') st = FCZ_E_MAGIC;
+    else if (len < HDR_BYTES) { st = FCZ_E_TRUNCATED; v = FCZ_V_BACKBONE_COUNT_MISMATCH; }
+    else {
+        const Layout y = make_layout(get_u16(blob + OFF_NRES), get_u32(blob + OFF_NSC), get_u32(blob + OFF_LENTITLE), blob[OFF_NANCHOR]);
+        // sections in file order; 64-bit sums: lenTitle and nSideChainTorsion are 32-bit fields of an untrusted header
+        const uint64_t e_rec = (uint64_t)HDR_BYTES + 40ull * y.n_anchor + y.title_len + 13ull + 8ull * y.L;
+        const uint64_t e_sc = e_rec + y.n_sc, e_tmp = e_sc + 8ull + y.L;
+        if (e_rec > len) { st = FCZ_E_TRUNCATED; v = FCZ_V_BACKBONE_COUNT_MISMATCH; }
+        else if (e_sc > len) { st = FCZ_E_TRUNCATED; v = FCZ_V_SIDECHAIN_COUNT_MISMATCH; }
+        else if (e_tmp > len) { st = FCZ_E_TRUNCATED; v = FCZ_V_TEMP_FACTOR_COUNT_MISMATCH; }
+        else {
+            uint32_t any_bb = 0, any_sc = 0, any_t = 0;
+            const uint8_t* rec = blob + y.o_rec;
+            // phi | psi | omega non-zero <=> (byte0 & 7) | byte1 | byte2 | byte3 | byte4 (convertBytesToBackboneChain, 60-77)
+            for (uint32_t r = lane; r < y.L; r += 32u) {
+                const uint8_t* p = rec + 8u * r;
+                any_bb |= (uint32_t)(p[0] & 7u) | p[1] | p[2] | p[3] | p[4];
+            }
+            for (uint32_t i = lane; i < y.n_sc; i += 32u) any_sc |= blob[y.o_sc + i];
+            for (uint32_t i = lane; i < y.L; i += 32u) any_t |= blob[y.o_temp + 8u + i];
+            any_bb = __any_sync(0xffffffffu, any_bb != 0u);
+            any_sc = __any_sync(0xffffffffu, any_sc != 0u);
+            any_t = __any_sync(0xffffffffu, any_t != 0u);
+            v = !any_bb ? FCZ_V_EMPTY_BACKBONE_ANGLE : (!any_sc ? FCZ_V_EMPTY_SIDECHAIN_ANGLE : (!any_t ? FCZ_V_EMPTY_TEMP_FACTOR : FCZ_V_SUCCESS));
+        }
+    }
+    if (lane == 0) {
+        if (a.read_status) a.read_status[c] = st;
+        if (a.validity) a.validity[c] = v;
+    }
+}
+
 // Continuised backbone angles of every residue record (decompressBackboneChain, src/foldcomp.cpp:122-153 with
 // _continuize 155-158: q * cont_f + min, two float roundings): six floats per residue in header order
 // phi, psi, omega, N-CA-C, CA-C-N, C-N-CA.  What Foldcomp::decompress leaves in its phi / psi / omega / *_angle members
@@ -2648,6 +2696,38 @@ extern "C" int fcz_unpack_angles_batch(fcz_engine* e, const fcz_blob_batch* in, 
     if (host) {
         CK(cudaMemcpyAsync(res_off, d_res_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
         if (total) CK(cudaMemcpyAsync(angles, e->d_text.p, 24ull * total, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return FCZ_OK;
+}
+
+// ---------------------------------------------------------------------------------- check (Foldcomp::checkValidity)
+extern "C" int fcz_check_batch(fcz_engine* e, const fcz_blob_batch* in, int32_t* read_status, int32_t* validity) {
+    if (!e || !in) return FCZ_E_ARG;
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    int rc;
+    const bool host = in->mem == FCZ_MEM_HOST;
+    CheckArgs a;
+    memset(&a, 0, sizeof a);
+    a.n = n;
+    if (host) {
+        H2D(e->d_blob_off, in->blob_off, 8ull * (n + 1));
+        H2D(e->d_bytes, in->bytes, in->blob_off[n]);
+        if ((rc = ensure(e, e->d_status, 8ull * n + 8))) return rc;
+        a.blob_off = (uint64_t*)e->d_blob_off.p; a.bytes = (uint8_t*)e->d_bytes.p;
+        a.read_status = (int32_t*)e->d_status.p; a.validity = (int32_t*)e->d_status.p + n;
+    } else {
+        a.blob_off = in->blob_off; a.bytes = in->bytes; a.read_status = read_status; a.validity = validity;
+    }
+    if (n) {
+        k_check<<<(n + 7) / 8, 256, 0, e->stream>>>(a);
+        e->launches++;
+    }
+    CK(cudaGetLastError());
+    if (host) {
+        if (read_status && n) CK(cudaMemcpyAsync(read_status, a.read_status, 4ull * n, cudaMemcpyDeviceToHost, e->stream));
+        if (validity && n) CK(cudaMemcpyAsync(validity, a.validity, 4ull * n, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
     }
     return FCZ_OK;

@@ -27,6 +27,10 @@ enum {
     HDR_BYTES = 76
 };
 
+// rows of the device-side residue tables (5-bit code space) and the reference's mapping of unknown codes to UNK
+#define FCZ_CODE_ROWS 32
+FCZ_HD unsigned norm_code(unsigned code) { return code < (unsigned)FCZ_NUM_CODES ? code : (unsigned)FCZ_CODE_UNK; }
+
 // header order of the six backbone arrays
 enum { A_PHI = 0, A_PSI = 1, A_OMEGA = 2, A_NCAC = 3, A_CACN = 4, A_CNCA = 5 };
 

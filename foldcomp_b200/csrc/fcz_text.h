@@ -27,19 +27,20 @@ namespace fcz {
 
 // Names as the emitter needs them: residue names and atom names packed little-endian into 32-bit words, atom
 // names already left-justified in 3 columns (std::setw(3) << std::left, src/atom_coordinate.cpp:253-255).
-struct TextTables {
-    uint32_t name3[FCZ_NUM_CODES];                 // 'A' | 'L' << 8 | 'A' << 16
-    uint32_t atom[FCZ_NUM_CODES][FCZ_MAX_ATOMS];   // "CA " etc; byte 0 is also the element column (atom[0])
-    uint8_t natoms[FCZ_NUM_CODES];
-    uint8_t alt[FCZ_NUM_CODES][FCZ_MAX_ATOMS];
-    uint8_t name1[FCZ_NUM_CODES];
+struct TextTables {  // FCZ_CODE_ROWS rows: 24..31 repeat UNK (see Tables in fcz_codec.h)
+    uint32_t name3[FCZ_CODE_ROWS];                 // 'A' | 'L' << 8 | 'A' << 16
+    uint32_t atom[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];   // "CA " etc; byte 0 is also the element column (atom[0])
+    uint8_t natoms[FCZ_CODE_ROWS];
+    uint8_t alt[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];
+    uint8_t name1[FCZ_CODE_ROWS];
 };
 
 inline void build_text_tables(TextTables* t) {
-    for (int c = 0; c < FCZ_NUM_CODES; c++) {
-        t->name3[c] = (uint32_t)(uint8_t)FCZ_NAME3[c][0] | (uint32_t)(uint8_t)FCZ_NAME3[c][1] << 8 | (uint32_t)(uint8_t)FCZ_NAME3[c][2] << 16;
-        t->natoms[c] = FCZ_NATOMS[c];
-        t->name1[c] = (uint8_t)FCZ_NAME1[c];
+    for (int row = 0; row < FCZ_CODE_ROWS; row++) {
+        const int c = (int)norm_code((unsigned)row);
+        t->name3[row] = (uint32_t)(uint8_t)FCZ_NAME3[c][0] | (uint32_t)(uint8_t)FCZ_NAME3[c][1] << 8 | (uint32_t)(uint8_t)FCZ_NAME3[c][2] << 16;
+        t->natoms[row] = FCZ_NATOMS[c];
+        t->name1[row] = (uint8_t)FCZ_NAME1[c];
         for (int k = 0; k < FCZ_MAX_ATOMS; k++) {
             uint32_t w = 0;
             bool end = false;
@@ -48,8 +49,8 @@ inline void build_text_tables(TextTables* t) {
                 if (ch == 0) { end = true; ch = ' '; }
                 w |= (uint32_t)(uint8_t)ch << (8 * j);
             }
-            t->atom[c][k] = w;
-            t->alt[c][k] = FCZ_ALT[c][k];
+            t->atom[row][k] = w;
+            t->alt[row][k] = FCZ_ALT[c][k];
         }
     }
 }
@@ -346,7 +347,7 @@ struct PdbChain {
 };
 
 FCZ_HD AtomRec pdb_atom_rec(const TextTables* tt, const PdbChain& ch, uint32_t r, uint32_t k, uint32_t atom) {
-    const unsigned code = ch.type[r];
+    const unsigned code = ch.type[r] & 31u;  // tables have FCZ_CODE_ROWS rows
     AtomRec a;
     a.serial = (uint32_t)ch.meta->idx_atom + atom;
     a.resnum = (uint32_t)ch.meta->idx_residue + r;
@@ -363,7 +364,7 @@ FCZ_HD AtomRec pdb_oxt_rec(const TextTables* tt, const PdbChain& ch) {
     a.serial = (uint32_t)ch.meta->idx_atom + ch.A;
     a.resnum = ch.L;
     a.name = (uint32_t)'O' | (uint32_t)'X' << 8 | (uint32_t)'T' << 16;
-    a.res3 = tt->name3[ch.type[ch.L - 1u]];
+    a.res3 = tt->name3[ch.type[ch.L - 1u] & 31u];
     a.chain = ch.meta->chain;
     a.x = ch.meta->oxt[0]; a.y = ch.meta->oxt[1]; a.z = ch.meta->oxt[2];
     a.b = ch.bfac[ch.L - 1u];
@@ -385,17 +386,17 @@ FCZ_HD uint32_t pdb_plan_chain(Ctx& cx, const TextTables* tt, const PdbChain& ch
     uint32_t r0 = cx.tid * chunk; if (r0 > L) r0 = L;
     uint32_t r1 = r0 + chunk; if (r1 > L) r1 = L;
     uint32_t sum = 0;
-    for (uint32_t r = r0; r < r1; r++) sum += tt->natoms[ch.type[r]];
+    for (uint32_t r = r0; r < r1; r++) sum += tt->natoms[ch.type[r] & 31u];
     uint32_t base = cx.excl_scan(sum);
     const uint32_t a_first = base;
-    for (uint32_t r = r0; r < r1; r++) { ch.aoff[r] = base; base += tt->natoms[ch.type[r]]; }
+    for (uint32_t r = r0; r < r1; r++) { ch.aoff[r] = base; base += tt->natoms[ch.type[r] & 31u]; }
     if (r1 == L) ch.aoff[L] = base;
     cx.sync();
     // bytes beyond 81 (zero for ordinary coordinates): the cheap fits-its-columns test per atom, the exact
     // measurement only for the atoms that fail it
     uint32_t extra = 0, atom = a_first;
     for (uint32_t r = r0; r < r1; r++) {
-        const uint32_t n = tt->natoms[ch.type[r]];
+        const uint32_t n = tt->natoms[ch.type[r] & 31u];
         for (uint32_t k = 0; k < n; k++, atom++) {
             const AtomRec a = pdb_atom_rec(tt, ch, r, k, atom);
             if (!atom_line_uniform(a)) extra += atom_line_extra(a);
@@ -405,11 +406,11 @@ FCZ_HD uint32_t pdb_plan_chain(Ctx& cx, const TextTables* tt, const PdbChain& ch
     const uint32_t head = title_lines_len(ch.title_len);
     atom = a_first;
     if (extra == 0u) {  // this thread's residues are uniform: offsets follow from the atom offsets alone
-        for (uint32_t r = r0; r < r1; r++) { ch.toff[r] = head + FCZ_PDB_LINE * atom + ebase; atom += tt->natoms[ch.type[r]]; }
+        for (uint32_t r = r0; r < r1; r++) { ch.toff[r] = head + FCZ_PDB_LINE * atom + ebase; atom += tt->natoms[ch.type[r] & 31u]; }
     } else {
         for (uint32_t r = r0; r < r1; r++) {
             ch.toff[r] = head + FCZ_PDB_LINE * atom + ebase;
-            const uint32_t n = tt->natoms[ch.type[r]];
+            const uint32_t n = tt->natoms[ch.type[r] & 31u];
             for (uint32_t k = 0; k < n; k++, atom++) ebase += atom_line_extra(pdb_atom_rec(tt, ch, r, k, atom));
         }
     }

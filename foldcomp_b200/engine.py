@@ -328,6 +328,15 @@ class Engine:
         self._check(self.lib.fcz_extract_batch(self.h, C.byref(sin), int(type_), int(digits), C.byref(so), C.byref(total)))
         return out
 
+    def check_host(self, blobs: HostBlobBatch):
+        """(read_status [n], validity [n]): Foldcomp::read + checkValidity for every blob (src/foldcomp.cpp:904-1036,
+        1492-1532): read_status 0 / FCZ_E_MAGIC / FCZ_E_TRUNCATED, validity = ValidityError class 0..6 (abi.VALIDITY)."""
+        n = blobs.n_chains
+        rs, va = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        sin = blobs.as_struct()
+        self._check(self.lib.fcz_check_batch(self.h, C.byref(sin), rs.ctypes.data, va.ctypes.data))
+        return rs, va
+
     def unpack_angles_host(self, blobs: HostBlobBatch):
         """(res_off [n+1], angles [R, 6]): continuised phi, psi, omega, N-CA-C, CA-C-N, C-N-CA of every residue record."""
         n = blobs.n_chains

@@ -36,8 +36,12 @@ def _atom_records(pdb_text: str):
             chain = ch
         if ch != chain:
             raise PdbError("Multiple chains found")  # foldcomp.cxx:266-268 (flag 2)
-        out.append(
-            (
+        # a short line or a blank / non-numeric fixed-column field is flag 3 of the C++ parser (parsePdbChain,
+        # foldcomp_b200/csrc/fcz_db.cpp: n < 22, n < 61, failed numeric field): the same error here
+        if len(line) < 61:
+            raise PdbError("Malformed ATOM record")
+        try:
+            rec = (
                 line[12:16].strip(" \t"),
                 line[17:20].strip(" \t"),
                 ch,
@@ -48,7 +52,9 @@ def _atom_records(pdb_text: str):
                 np.float32(line[46:54]),
                 np.float32(line[60:66]),
             )
-        )
+        except ValueError:
+            raise PdbError("Malformed ATOM record") from None
+        out.append(rec)
     if not out:
         raise PdbError("No ATOM lines found")  # foldcomp.cxx:288-290 (flag 1)
     # removeAlternativePosition: drop an atom whose name equals its predecessor's

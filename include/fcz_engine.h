@@ -168,6 +168,26 @@ int fcz_decode_to_pdb_batch(fcz_engine* e, const fcz_blob_batch* in, fcz_text_ba
 int fcz_extract_batch(fcz_engine* e, const fcz_blob_batch* in, int32_t type, int32_t digits, fcz_text_batch* out,
                       uint64_t* total_bytes);
 
+/* Foldcomp::read (src/foldcomp.cpp:904-1036) followed by Foldcomp::checkValidity (src/foldcomp.cpp:1492-1532; classes
+ * ValidityError src/foldcomp.h:59-67) for every blob: what `foldcomp check` (src/main.cpp:910-928) and `decompress
+ * --check` (630-636) run per entry.
+ *   read_status[c]  0, or FCZ_E_MAGIC where read() returns -1; FCZ_E_TRUNCATED where the blob ends before the sections its
+ *                   header announces (the reference reads past the end of its stream there and checks whatever its
+ *                   buffers held; here that is an error of its own)
+ *   validity[c]     the ValidityError class, FCZ_V_*; for a truncated blob the COUNT_MISMATCH class of the first section
+ *                   that falls short; FCZ_V_SUCCESS for a blob that fails the magic check (nothing was read)
+ * Order of the checks as in the reference: backbone (every record has phi = psi = omega = 0), side chain (every byte 0 --
+ * and, std::all_of over an empty range being true, a chain WITHOUT side-chain torsions), B-factors (every byte 0).
+ * Both arrays live in the memory space of `in`, n_chains entries each; either may be NULL. */
+#define FCZ_V_SUCCESS 0
+#define FCZ_V_BACKBONE_COUNT_MISMATCH 1
+#define FCZ_V_SIDECHAIN_COUNT_MISMATCH 2
+#define FCZ_V_TEMP_FACTOR_COUNT_MISMATCH 3
+#define FCZ_V_EMPTY_BACKBONE_ANGLE 4
+#define FCZ_V_EMPTY_SIDECHAIN_ANGLE 5
+#define FCZ_V_EMPTY_TEMP_FACTOR 6
+int fcz_check_batch(fcz_engine* e, const fcz_blob_batch* in, int32_t* read_status, int32_t* validity);
+
 /* Continuised backbone angles of every residue record: six floats per residue, phi, psi, omega, N-CA-C, CA-C-N, C-N-CA
  * -- decompressBackboneChain (src/foldcomp.cpp:122-153), i.e. what Foldcomp::decompress leaves in its phi / psi / omega /
  * *_angle members (783-804) and the CPython get_data() returns (foldcomp/foldcomp.cxx:497-560).  Fills res_off[0..n]

@@ -154,7 +154,10 @@ static int anchors(uint32_t L, int32_t b, int32_t* idx /* may be NULL */) {
     return n_all;
 }
 
-static int code_to_char(int code) { return FCZ_NAME1[code]; }
+/* convertIntToOneLetterCode / convertIntToThreeLetterCode, src/utility.cpp:297-377, 461-: the 5-bit field can hold
+ * 24..31, which fall into the switch's default branch = UNK ('X'). */
+static int norm_code(int code) { return (code >= 0 && code < FCZ_NUM_CODES) ? code : FCZ_CODE_UNK; }
+static int code_to_char(int code) { return FCZ_NAME1[norm_code(code)]; }
 static int char_to_code(int ch) {
     for (int i = 0; i < FCZ_NUM_CODES; i++)
         if (FCZ_NAME1[i] == ch) return i;
@@ -322,7 +325,7 @@ int fcz_oracle_peek(const uint8_t* blob, uint64_t len, uint32_t* L, uint64_t* n_
     if (rc) return rc;
     uint64_t na = 0, nsc = 0;
     for (uint32_t r = 0; r < v.L; r++) {
-        int c = v.records[8 * r] >> 3;
+        int c = norm_code(v.records[8 * r] >> 3);
         if (FCZ_NATOMS[c] == 0) return FCZ_E_RESIDUE;
         na += FCZ_NATOMS[c];
         nsc += FCZ_NATOMS[c] - 3;
@@ -350,7 +353,7 @@ int fcz_oracle_decode_chain(const uint8_t* blob, uint64_t len, int use_alt, uint
     rec_t* rec = (rec_t*)malloc(sizeof(rec_t) * L);
     for (uint32_t i = 0; i < L; i++) {
         const uint8_t* b = v.records + 8 * i;
-        unsigned res = b[0] >> 3;
+        unsigned res = (unsigned)norm_code(b[0] >> 3);
         unsigned omg = ((b[0] & 7u) << 8) | b[1];
         unsigned psi = ((unsigned)b[2] << 4) | (b[3] >> 4);
         unsigned phi = ((b[3] & 0xFu) << 8) | b[4];
@@ -707,4 +710,38 @@ int64_t fcz_oracle_unpack_angles(const uint8_t* blob, uint64_t len, float* out) 
         out[6 * r + 5] = cont(b[6], mins[5], cfs[5]);
     }
     return (int64_t)v.L;
+}
+
+/* Foldcomp::read (src/foldcomp.cpp:904-1036) + Foldcomp::checkValidity (src/foldcomp.cpp:1492-1532).  read() sizes its
+ * three vectors from the header (compressedBackBone.resize(nResidue) 979-984, nSideChainTorsion push_backs 1010-1014,
+ * nResidue push_backs 1027-1031), so the three COUNT_MISMATCH classes cannot occur on a blob that is complete; they
+ * are used here for a blob that ends before the section (the reference reads past the end of its stream there and
+ * checks whatever its buffers held).  Then, in this order: every record has phi = psi = omega = 0 (1499-1505), every
+ * side-chain byte is 0 (1506-1510; std::all_of is true on an empty range), every B-factor byte is 0 (1511-1515).
+ * Returns the read status (0, FCZ_E_MAGIC, FCZ_E_TRUNCATED); *validity receives the class 0..6. */
+int fcz_oracle_check(const uint8_t* b, uint64_t len, int* validity) {
+    *validity = 0;
+    if (len < 4 || memcmp(b, "FCMP", 4) != 0) return FCZ_E_MAGIC;
+    if (len < FCZ_HDR) { *validity = 1; return FCZ_E_TRUNCATED; }
+    const uint32_t L = get16(b + 4), n_anchor = b[12], n_sc = get32(b + 16), title_len = get32(b + 24);
+    uint64_t o = FCZ_HDR + 4ull * n_anchor + title_len + 36ull * n_anchor + 13;
+    const uint8_t* rec = b + o;
+    o += 8ull * L;
+    if (o > len) { *validity = 1; return FCZ_E_TRUNCATED; }
+    const uint8_t* sc = b + o;
+    o += n_sc;
+    if (o > len) { *validity = 2; return FCZ_E_TRUNCATED; }
+    const uint8_t* temp = b + o + 8;
+    o += 8ull + L;
+    if (o > len) { *validity = 3; return FCZ_E_TRUNCATED; }
+    int empty_bb = 1, empty_sc = 1, empty_t = 1;
+    for (uint32_t r = 0; r < L; r++) {
+        const uint8_t* p = rec + 8 * r;
+        unsigned omg = ((p[0] & 7u) << 8) | p[1], psi = ((unsigned)p[2] << 4) | (p[3] >> 4), phi = ((p[3] & 0xFu) << 8) | p[4];
+        if (phi || psi || omg) empty_bb = 0;
+    }
+    for (uint32_t i = 0; i < n_sc; i++) if (sc[i]) empty_sc = 0;
+    for (uint32_t i = 0; i < L; i++) if (temp[i]) empty_t = 0;
+    *validity = empty_bb ? 4 : (empty_sc ? 5 : (empty_t ? 6 : 0));
+    return FCZ_OK;
 }

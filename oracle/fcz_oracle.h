@@ -55,6 +55,10 @@ int64_t fcz_oracle_extract(const uint8_t* blob, uint64_t len, int type, int digi
  * decompressBackboneChain, src/foldcomp.cpp:122-153.  Returns the residue count or a negative code. */
 int64_t fcz_oracle_unpack_angles(const uint8_t* blob, uint64_t len, float* out);
 
+/* Foldcomp::read + checkValidity (src/foldcomp.cpp:904-1036, 1492-1532): returns the read status, *validity = the
+ * ValidityError class (src/foldcomp.h:59-67). */
+int fcz_oracle_check(const uint8_t* blob, uint64_t len, int* validity);
+
 #ifdef __cplusplus
 }
 #endif

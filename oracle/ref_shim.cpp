@@ -269,6 +269,18 @@ int64_t ref_extract(const uint8_t* fcz, size_t len, int type, int digits, char* 
     return (int64_t)data.size();
 }
 
+// Foldcomp::read + Foldcomp::checkValidity (src/foldcomp.cpp:904-1036, 1492-1532) on one blob, as `foldcomp check` runs
+// them (src/main.cpp:910-928): returns read()'s code; *validity = the ValidityError class.
+int ref_check(const uint8_t* fcz, size_t len, int* validity) {
+    Foldcomp comp;
+    std::istringstream iss(std::string((const char*)fcz, len));
+    *validity = 0;
+    int rc = comp.read(iss);
+    if (rc != 0) return rc;
+    *validity = (int)comp.checkValidity();
+    return 0;
+}
+
 int ref_max_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

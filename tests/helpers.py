@@ -442,3 +442,218 @@ def oracle_unpack_angles(blob: bytes) -> np.ndarray:
     n = lib.fcz_oracle_unpack_angles(blob, len(blob), out.ctypes.data)
     assert n == L, n
     return out
+
+
+# --------------------------------------------------------------------------- degenerate inputs (shared generator)
+
+
+def _nanf(bits: int) -> np.float32:
+    return np.array([bits], np.uint32).view(np.float32)[0]
+
+
+def degenerate_chains():
+    """[(kind, HostChainBatch of one chain)]: inputs on which the reference's arithmetic leaves the beaten path.
+    Kinds 0-9 (120 chains, the round-1 set): constant B-factors (the discretiser divides by zero and casts NaN), coincident
+    atoms, missing atoms at (0,0,0), scaled, collinear triple, NaN coordinate, NaN B-factor, integer lattice, inf
+    coordinate, two-valued B-factors.  Kinds 10-14 aim at the FIRST element of every array, whose NaN reaches the
+    header floats (std::min_element keeps a NaN first element, src/discretizer.cpp:27-28): NaN / inf in each of the
+    first six backbone atoms, neighbouring backbone atoms coincident (0/0), NaN first B-factors of several payloads
+    and signs, all-infinite B-factors, two different NaN payloads among the first atoms."""
+    from foldcomp_b200 import synth
+
+    rng = np.random.default_rng(7)
+    out = []
+    for trial in range(120):
+        L = int(rng.integers(2, 60))
+        batch = synth.generate(1, L, seed=1000 + trial)
+        x, bf = batch.xyz.copy(), batch.bfactor.copy()
+        A, kind = len(x), trial % 10
+        if kind == 0:
+            bf[:] = 50.0
+        elif kind == 1:
+            x[rng.integers(0, A)] = x[rng.integers(0, A)]
+        elif kind == 2:
+            x[rng.integers(0, A, 3)] = 0.0
+        elif kind == 3:
+            x *= np.float32(100.0)
+        elif kind == 4:
+            x[2] = x[1] + (x[1] - x[0])
+        elif kind == 5:
+            x[rng.integers(0, A)] = np.nan
+        elif kind == 6:
+            bf[rng.integers(0, L)] = np.nan
+        elif kind == 7:
+            x[:] = np.round(x)
+        elif kind == 8:
+            x[rng.integers(0, A)] = np.inf
+        else:
+            bf[:] = rng.choice([0.0, 100.0], L)
+        batch.xyz, batch.bfactor = x, bf
+        out.append((kind, batch))
+
+    nat = tables().natoms
+    seed = [2000]
+
+    def fresh(L=None):
+        seed[0] += 1
+        b = synth.generate(1, L if L else int(rng.integers(3, 40)), seed=seed[0])
+        b.xyz, b.bfactor = b.xyz.copy(), b.bfactor.copy()
+        n0 = int(nat[int(b.res_type[0])])
+        return b, [0, 1, 2, n0, n0 + 1, n0 + 2]  # atom indices of the first six backbone atoms
+
+    for j in range(6):  # kind 10: NaN in one component / all components of backbone atom j
+        for comp in (0, 1, 2, None):
+            b, bbi = fresh()
+            if comp is None:
+                b.xyz[bbi[j]] = np.nan
+            else:
+                b.xyz[bbi[j], comp] = np.nan
+            out.append((10, b))
+    for j in range(6):  # kind 11: +inf / -inf
+        for v in (np.inf, -np.inf):
+            b, bbi = fresh()
+            b.xyz[bbi[j], int(rng.integers(0, 3))] = v
+            out.append((11, b))
+        b, bbi = fresh()
+        b.xyz[bbi[j]] = np.inf
+        out.append((11, b))
+    for j in range(5):  # kind 12: backbone atoms j and j+1 coincide (zero bond vector: 0/0)
+        b, bbi = fresh()
+        b.xyz[bbi[j + 1]] = b.xyz[bbi[j]]
+        out.append((12, b))
+    for first in (_nanf(0x7FC00000), _nanf(0xFFC00000), _nanf(0x7F812345), _nanf(0xFFA00001), np.float32(np.inf), np.float32(-np.inf)):
+        b, _ = fresh()  # kind 13: first B-factor NaN (quiet, negative, signalling payloads) or infinite
+        b.bfactor[0] = first
+        out.append((13, b))
+    for v in (np.inf, -np.inf):  # ... and every B-factor infinite (max - min = inf - inf)
+        b, _ = fresh()
+        b.bfactor[:] = v
+        out.append((13, b))
+    return out
+
+
+def has_collinear_backbone(b: HostChainBatch, c: int = 0, eps: float = 1e-6) -> bool:
+    """True when three consecutive backbone atoms of chain c are collinear to within eps (sine of their angle), or a
+    bond vector vanishes: the geometry on which Nerf::place_atom's frame (src/nerf.cpp:52-85) is undefined."""
+    a0, a1 = int(b.atom_off[c]), int(b.atom_off[c + 1])
+    r0, r1 = int(b.res_off[c]), int(b.res_off[c + 1])
+    p = b.xyz[a0:a1][backbone_mask(b.res_type[r0:r1])].astype(np.float64)
+    u, v = p[:-2] - p[1:-1], p[2:] - p[1:-1]
+    with np.errstate(all="ignore"):
+        s = np.linalg.norm(np.cross(u, v), axis=1) / (np.linalg.norm(u, axis=1) * np.linalg.norm(v, axis=1))
+    s = s[np.isfinite(s)]
+    return bool(len(s) and s.min() < eps)
+
+
+def decode_mismatch(got: np.ndarray, want: np.ndarray, res_type: np.ndarray, tol_bb_rmsd: float, tol_max: float):
+    """None when two decodes of one chain agree: identical NaN / inf masks, finite atoms within the tolerances."""
+    ng, nw = np.isnan(got), np.isnan(want)
+    if not np.array_equal(ng, nw):
+        return f"NaN masks differ ({int(ng.sum())} vs {int(nw.sum())})"
+    with np.errstate(all="ignore"):
+        if not np.array_equal(np.isinf(got), np.isinf(want)) or not np.array_equal(got[np.isinf(want)], want[np.isinf(want)]):
+            return "inf masks differ"
+        fin = np.isfinite(want).all(axis=1)
+        if not fin.any():
+            return None
+        d = np.sqrt(((got[fin].astype(np.float64) - want[fin].astype(np.float64)) ** 2).sum(axis=1))
+    if d.max() > tol_max:
+        return f"max deviation {d.max():.3e}"
+    bb = backbone_mask(res_type)[fin]
+    if bb.any() and np.sqrt((d[bb] ** 2).mean()) > tol_bb_rmsd:
+        return f"backbone rmsd {np.sqrt((d[bb] ** 2).mean()):.3e}"
+    return None
+
+
+# --------------------------------------------------------------------------- check (Foldcomp::checkValidity)
+
+
+def oracle_check(blob: bytes):
+    """(read status, ValidityError class) of the oracle's restatement of read + checkValidity."""
+    lib = oracle()
+    lib.fcz_oracle_check.restype = C.c_int
+    lib.fcz_oracle_check.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+    buf = np.frombuffer(blob, np.uint8) if len(blob) else np.zeros(1, np.uint8)
+    v = C.c_int()
+    rc = lib.fcz_oracle_check(buf.ctypes.data, len(blob), C.byref(v))
+    return int(rc), int(v.value)
+
+
+def ref_check(blob: bytes):
+    lib = ref()
+    lib.ref_check.restype = C.c_int
+    lib.ref_check.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+    buf = np.frombuffer(blob, np.uint8) if len(blob) else np.zeros(1, np.uint8)
+    v = C.c_int()
+    rc = lib.ref_check(buf.ctypes.data, len(blob), C.byref(v))
+    return int(rc), int(v.value)
+
+
+def blob_sections(blob: bytes):
+    """(o_rec, o_sc, o_temp, size, L, n_sc) of an FCZ blob."""
+    import struct
+
+    L, = struct.unpack_from("<H", blob, 4)
+    na = blob[12]
+    n_sc, = struct.unpack_from("<I", blob, 16)
+    T, = struct.unpack_from("<I", blob, 24)
+    o_rec = 76 + 4 * na + T + 36 * na + 13
+    o_sc = o_rec + 8 * L
+    o_temp = o_sc + n_sc
+    return o_rec, o_sc, o_temp, o_temp + 8 + L, L, n_sc
+
+
+def unk_chain(L: int = 30, seed: int = 5) -> HostChainBatch:
+    """One chain of L residues that are all UNK (backbone only): no side-chain torsions at all."""
+    from foldcomp_b200 import synth
+
+    b = synth.generate(1, L, seed=seed)
+    xyz = b.xyz[backbone_mask(b.res_type)].copy()
+    meta = b.meta.copy()
+    meta["n_atom"] = 3 * L
+    meta["has_oxt"] = 0
+    return HostChainBatch(res_off=np.array([0, L], np.uint32), atom_off=np.array([0, 3 * L], np.uint64), title_off=b.title_off,
+                          res_type=np.full(L, 23, np.uint8), bfactor=b.bfactor, xyz=xyz, titles=b.titles, meta=meta,
+                          status=np.zeros(1, np.int32))
+
+
+def check_cases():
+    """[(label, blob)] for read + checkValidity: good blobs, each section zeroed (alone and together), a chain without
+    side-chain torsions, bad magic, empty input, blobs cut inside every section."""
+    from foldcomp_b200 import synth
+
+    out = []
+    for i in range(3):
+        out.append((f"good{i}", oracle_encode(synth.generate(1, 20 + 40 * i, seed=300 + i), 0, 25)))
+    base = out[1][1]
+    o_rec, o_sc, o_temp, size, L, n_sc = blob_sections(base)
+
+    def zero_bb(b):
+        b = bytearray(b)
+        for r in range(L):
+            b[o_rec + 8 * r] &= 0xF8
+            b[o_rec + 8 * r + 1 : o_rec + 8 * r + 5] = bytes(4)
+        return bytes(b)
+
+    def zero_sc(b):
+        b = bytearray(b)
+        b[o_sc : o_sc + n_sc] = bytes(n_sc)
+        return bytes(b)
+
+    def zero_t(b):
+        b = bytearray(b)
+        b[o_temp + 8 : o_temp + 8 + L] = bytes(L)
+        return bytes(b)
+
+    out += [("zero_bb", zero_bb(base)), ("zero_sc", zero_sc(base)), ("zero_t", zero_t(base)),
+            ("zero_bb_sc", zero_sc(zero_bb(base))), ("zero_sc_t", zero_t(zero_sc(base))), ("zero_all", zero_t(zero_sc(zero_bb(base))))]
+    nz = bytearray(zero_bb(base))
+    nz[o_rec + 8 * (L - 1) + 4] = 1  # a single non-zero phi bit in the last record
+    out.append(("one_phi_bit", bytes(nz)))
+    out.append(("all_unk", oracle_encode(unk_chain(), 0, 25)))
+    out.append(("bad_magic", b"FCMQ" + base[4:]))
+    out.append(("zeros", bytes(len(base))))
+    out.append(("empty", b""))
+    for cut in (3, 40, o_rec - 1, o_rec + 5, o_sc - 1, o_sc + 1, o_temp - 1, o_temp + 3, size - 1):
+        out.append((f"cut{cut}", base[:cut]))
+    return out
