@@ -11,7 +11,8 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfcz_engine.so")
+# FCZ_ENGINE_LIB: another build of the SAME library (A/B experiments of tools/kernel_ab.py); there is still no fallback
+LIB_PATH = os.environ.get("FCZ_ENGINE_LIB") or os.path.join(_HERE, "csrc", "libfcz_engine.so")
 
 # every symbol include/fcz_engine.h declares
 SYMBOLS = [

@@ -124,6 +124,17 @@ inline void build_tables(Tables* t) {
 // scratch floats needed by the min/max reduction: per-warp partials + results + discretiser params
 #define FCZ_RED_FLOATS(nwarps) ((nwarps) * 14 + 14 + 21)
 
+// Scratch words of the float-first backbone path (EncChain::fl):
+//   [FL_N]      number of list entries appended (may exceed the capacity: then the chain takes the exact path)
+//   [FL_BAD]    != 0: degenerate geometry seen, the chain takes the exact path
+//   [FL_BND+4a .. +3]  array a (header order), as ordered ints: min and max over the items of (x - eps), min and max of (x + eps)
+//   [FL_EX+2a, +1]     exact min / max over the re-evaluated items of array a (a = 6: the B-factors)
+//   [FL_DER+6a .. +5]  floats derived from the bounds for pass B: mU, mL, ML, f_lo, f_hi, unused
+// The list of undecided values (EncChain::list, value index a * L + r) and their exact values (EncChain::xe) hold
+// list_cap entries each: about 3 % of a chain's 6 (L-1) values end up there, enc_list_cap leaves a factor ~1.5.
+enum { FL_N = 0, FL_BAD = 1, FL_BND = 2, FL_EX = 26, FL_DER = 40, FCZ_FL_WORDS = 76 };
+FCZ_HD uint32_t enc_list_cap(uint32_t max_res) { return max_res <= 1024u ? 256u : (max_res + 3u) / 4u; }
+
 struct EncChain {
     uint32_t L, A, title_len;
     int32_t b;               // anchor threshold
@@ -136,39 +147,47 @@ struct EncChain {
     // workspace
     uint32_t* aoff;          // [L+1] first atom of each residue, relative to the chain
     uint16_t* sres;          // [A-3L] residue of each side-chain atom (= side-chain torsion)
-    float* ang;              // [6*L] the six backbone arrays, header order, stride L
+    float* ang;              // [6*L] the six backbone arrays, header order, stride L: angles, then (in place) their quantised values
     float* red;              // [FCZ_RED_FLOATS(nwarps)]
+    uint32_t* fl;            // [FCZ_FL_WORDS]
+    uint32_t* list;          // [list_cap] undecided values of the float-first path
+    float* xe;               // [list_cap] their exact values
+    uint32_t list_cap;
 };
 
-// Side-chain byte from the parts of cos(torsion) and the torsion's sign (see encode_chain phase 2).
-// The count of thresholds <= z is found from a cheap estimate (a 4-term arccosine, good to 0.003 degrees,
-// run through the reference's own byte formula) corrected against the table, so it is exact whatever the
-// estimate's quality; the table lookup is certified against the error G of the single-precision cosine.
-FCZ_HD uint8_t sc_byte_fast(const Tables* tb, DotParts dp, bool neg) {
-    const float G = 5e-7f;  // > 4 ulp of a cosine: bound on |inner * rsqrt(p) - reference cosine|
-    float c = dp.inner * rsqrt_(dp.p);
+// The side-chain byte for an EXACT cosine c (the reference's float): count of thresholds in cos-space, found from a
+// cheap estimate corrected against the table (exact whatever the estimate's quality).
+FCZ_HD uint8_t sc_byte_exact(const Tables* tb, float c, bool neg) {
     const float* tz = neg ? tb->sc_neg : tb->sc_pos;
-    bool ok = dp.p >= 1e-30f && dp.p <= 1e30f;
-    int n = 0;
-    for (int pass = 0; pass < 2; pass++) {
-        if (c != c) c = 2.0f;  // NaN cosine: the reference's acos is NaN and c < 0 is false -> 0 degrees
-        c = c > 2.0f ? 2.0f : (c < -2.0f ? -2.0f : c);  // |c| > 1 all take the NaN branch: the table spans [-2, 2]
-        const float z = neg ? c : -c;
-        // estimate (Abramowitz & Stegun 4.4.45): acos(x) ~ sqrt(1-x) (a0 + a1 x + a2 x^2 + a3 x^3), 0 <= x <= 1
-        const float x = fminf(fabsf(c), 1.0f);
-        float a = sqrtf(1.0f - x) * (1.5707288f + x * (-0.2121144f + x * (0.0742610f + x * -0.0187293f))) * 57.29578f;
-        if (c < 0.0f) a = 180.0f - a;
-        n = (int)(((neg ? -a : a) + 180.0f) * sc_disc_f()) - (neg ? 0 : 127);
-        n = n < 0 ? 0 : (n > 128 ? 128 : n);
-        while (n > 0 && !(z >= tz[n - 1])) n--;   // exact count of thresholds <= z (tables increase)
-        while (n < 128 && z >= tz[n]) n++;
-        if (ok && n > 0 && !(z - G >= tz[n - 1])) ok = false;
-        if (ok && n < 128 && !(z + G < tz[n])) ok = false;
-        if (ok) break;
-        c = cos_exact_slow(dp.inner, dp.p);  // the reference's own sequence; the second pass needs no guard
-        ok = true;
-    }
+    if (c != c) c = 2.0f;  // NaN cosine: the reference's acos is NaN and c < 0 is false -> 0 degrees
+    c = c > 2.0f ? 2.0f : (c < -2.0f ? -2.0f : c);  // |c| > 1 all take the NaN branch: the table spans [-2, 2]
+    const float z = neg ? c : -c;
+    // estimate (Abramowitz & Stegun 4.4.45): acos(x) ~ sqrt(1-x) (a0 + a1 x + a2 x^2 + a3 x^3), 0 <= x <= 1
+    const float x = fminf(fabsf(c), 1.0f);
+    float a = sqrtf(1.0f - x) * (1.5707288f + x * (-0.2121144f + x * (0.0742610f + x * -0.0187293f))) * 57.29578f;
+    if (c < 0.0f) a = 180.0f - a;
+    int n = (int)(((neg ? -a : a) + 180.0f) * sc_disc_f()) - (neg ? 0 : 127);
+    n = n < 0 ? 0 : (n > 128 ? 128 : n);
+    while (n > 0 && !(z >= tz[n - 1])) n--;   // exact count of thresholds <= z (tables increase)
+    while (n < 128 && z >= tz[n]) n++;
     return (uint8_t)(neg ? n : 127 + n);
+}
+static FCZ_HD_SLOW uint8_t sc_byte_slow(const Tables* tb, float inner, float p, bool neg) {
+    return sc_byte_exact(tb, cos_exact_slow(inner, p), neg);
+}
+// Side-chain byte from the parts of cos(torsion) and the torsion's sign (see encode_chain phase 2): the reference stores
+// (unsigned)((t - (-180.f)) * (255 / 360.f)) -- float add, float multiply, truncation (src/discretizer.cpp:55-57 via
+// src/foldcomp.cpp:532-538).  Both are monotone, so the float-first estimate x of t with |x - t| <= eps brackets the
+// product; when both ends truncate to the same integer that is the reference's byte, otherwise (an estimate within
+// eps of a byte boundary: ~2e-4 of the items) the reference's exact cosine goes through the threshold table.
+FCZ_HD uint8_t sc_byte_fast(const Tables* tb, DotParts dp, bool neg) {
+    uint32_t bad = 0;
+    const float x = ang_fast(dp, true, neg, bad);
+    const float e = ang_eps(x);
+    const float t_lo = ((x - e) + 180.0f) * sc_disc_f(), t_hi = ((x + e) + 180.0f) * sc_disc_f();
+    const int n_lo = (int)t_lo, n_hi = (int)t_hi;
+    if (!bad && n_lo == n_hi) return (uint8_t)n_lo;
+    return sc_byte_slow(tb, dp.inner, dp.p, neg);
 }
 
 FCZ_HD f3 bb_atom(const EncChain& ch, uint32_t j) {  // j-th backbone atom (N,CA,C = slots 0..2)
@@ -195,12 +214,132 @@ FCZ_HD float x86_angle_nan(const EncChain& ch, uint32_t m) {
     return u2f(0xFFC00000u);
 }
 
+// Discretiser parameters (min, disc_f, cont_f) of one array from its extremes and its first element
+// (Discretizer::Discretizer, src/discretizer.cpp:22-33), k = array index (6 = B-factors).
+FCZ_HD void enc_params(const EncChain& ch, int k, float lo, float hi, float first, float* prm) {
+    if (first != first) {  // min_element/max_element keep a NaN first element
+        // A bond angle that came out NaN: WHICH NaN is hardware business (see x86_angle_nan); B-factors are input
+        // and are copied bit for bit (this->min = *std::min_element(...) is a plain move).
+        if (k >= 3 && k < 6) first = x86_angle_nan(ch, k == A_CACN ? 2u : (k == A_CNCA ? 3u : 4u));
+        lo = first; hi = first;
+    }
+    const unsigned nb = (k < 6) ? n_bins(k) : 255u;
+    prm[0] = lo;
+    prm[1] = disc_factor(lo, hi, nb);
+    prm[2] = cont_factor(lo, hi, nb);
+    if (prm[2] != prm[2]) {
+        // (max - min) is NaN: x86 propagates the quieted NaN operand (min = max = the NaN first element) through
+        // the subtraction and the division, and produces its default NaN (negative, 0xFFC00000) for inf - inf;
+        // a GPU would put its canonical 0x7FFFFFFF into the header instead (src/discretizer.cpp:27-32).
+        const float nanv = u2f(lo != lo ? (f2u(lo) | 0x00400000u) : 0xFFC00000u);
+        prm[1] = nanv;
+        prm[2] = nanv;
+    }
+}
+
+// One backbone value by the reference's exact sequence: array a (header order) at index r -- the torsion over backbone
+// atoms 3r+k .. 3r+k+3 or the bond angle at backbone atom 3r+k+2, k = 0 (psi, CA-C-N), 1 (omega, C-N-CA), 2 (phi, N-CA-C)
+// (src/torsion_angle.cpp:49-94, src/nerf.cpp:495-508, split src/foldcomp.cpp:488-505).
+FCZ_HD void bb_item_atoms(const EncChain& ch, uint32_t r, uint32_t k, f3& p0, f3& p1, f3& p2, f3& p3) {
+    const uint32_t a0 = ch.aoff[r], a1 = ch.aoff[r + 1u];
+    // backbone atoms j .. j+3 = (r,k) (r,k+1) ... wrapping into residue r+1
+    const uint32_t i0 = a0 + k, i1 = (k < 2u) ? a0 + k + 1u : a1, i2 = (k < 1u) ? a0 + 2u : a1 + (k - 1u), i3 = a1 + k;
+    p0 = ld3(ch.X + 3u * i0); p1 = ld3(ch.X + 3u * i1); p2 = ld3(ch.X + 3u * i2); p3 = ld3(ch.X + 3u * i3);
+}
+FCZ_HD uint32_t bb_array_k(uint32_t a) { return (a == A_PSI || a == A_CACN) ? 0u : ((a == A_OMEGA || a == A_CNCA) ? 1u : 2u); }
+static FCZ_HD_SLOW float bb_value_exact(const EncChain& ch, uint32_t a, uint32_t r) {
+    const uint32_t k = bb_array_k(a);
+    const bool is_tor = a < 3u;
+    f3 p0, p1, p2, p3;
+    bb_item_atoms(ch, r, k, p0, p1, p2, p3);
+    const f3 d2 = sub3(p2, p1), d3 = sub3(p3, p2);
+    f3 v1, v2;
+    bool neg = false;
+    if (is_tor) {
+        const f3 d1 = sub3(p1, p0);
+        v1 = cross3(d1, d2);
+        v2 = cross3(d2, d3);
+        const f3 pb = cross3(v2, d2);
+        neg = (v1.x * pb.x) + (v1.y * pb.y) + (v1.z * pb.z) < 0;
+    } else {
+        v1 = sub3(p1, p2);
+        v2 = d3;
+    }
+    const float c = cos_ref(dot_parts(v1, v2));
+    float deg;
+    if (!acos_deg_certified(c, &deg)) deg = angle_deg_slow(c, is_tor);  // ~2e-6 of items, and |c| > 1
+    return (is_tor && neg) ? -deg : deg;
+}
+
+// q = floor(t + 0.5) as the reference's (unsigned)((double)t + 0.5) gives it for 0 <= t < 2^23, in exact float steps
+FCZ_HD uint32_t round_half_up(float t) {
+    const int n = (int)t;
+    return (uint32_t)n + ((t - (float)n) >= 0.5f ? 1u : 0u);
+}
+
+// ---- the backbone arrays by the reference's exact sequence for EVERY item (the fallback of the float-first path:
+// degenerate geometry, or more undecided items than the list holds): phase 3 computes all 6(L-1) values, phase 4
+// reduces them, then they are quantised in place.
+template <class Ctx>
+FCZ_HD void enc_backbone_exact(Ctx& cx, const EncChain& ch) {
+    const uint32_t L = ch.L;
+    {
+        const uint32_t nV = 6u * (L - 1u);
+        for (uint32_t w = cx.tid; w < nV; w += cx.nthr) {
+            const uint32_t a = w / (L - 1u), r = w - a * (L - 1u);
+            ch.ang[a * L + r] = bb_value_exact(ch, a, r);
+        }
+    }
+    cx.sync();
+    {
+        float mn[6], mx[6];
+        for (int k = 0; k < 6; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+        for (uint32_t i = cx.tid; i + 1u < L; i += cx.nthr) {
+            for (int k = 0; k < 6; k++) {
+                float v = ch.ang[k * L + i];
+                mn[k] = min_ignore_nan(mn[k], v);
+                mx[k] = max_ignore_nan(mx[k], v);
+            }
+        }
+        for (int k = 0; k < 6; k++) {
+            mn[k] = cx.wmin(mn[k]);
+            mx[k] = cx.wmax(mx[k]);
+        }
+        if (cx.lane == 0) {
+            for (int k = 0; k < 6; k++) {
+                ch.red[cx.warp * 14 + k] = mn[k];
+                ch.red[cx.warp * 14 + 7 + k] = mx[k];
+            }
+        }
+        cx.sync();
+        float* res = ch.red + cx.nwarps * 14;  // [14] unused, then [21] (min, disc_f, cont_f) x 7
+        for (int k = cx.tid; k < 6; k += cx.nthr) {
+            float lo = INFINITY, hi = -INFINITY;
+            for (int w = 0; w < cx.nwarps; w++) {
+                lo = min_ignore_nan(lo, ch.red[w * 14 + k]);
+                hi = max_ignore_nan(hi, ch.red[w * 14 + 7 + k]);
+            }
+            enc_params(ch, k, lo, hi, ch.ang[k * L], res + 14 + 3 * k);
+        }
+        cx.sync();
+    }
+    const float* prm = ch.red + cx.nwarps * 14 + 14;
+    uint32_t* q = reinterpret_cast<uint32_t*>(ch.ang);
+    for (uint32_t w = cx.tid; w < 6u * (L - 1u); w += cx.nthr) {
+        const uint32_t a = w / (L - 1u), r = w - a * (L - 1u);
+        q[a * L + r] = disc_round(ch.ang[a * L + r], prm[3 * a], prm[3 * a + 1]);
+    }
+}
+
 template <class Ctx>
 FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
     const uint32_t L = ch.L, A = ch.A;
     const int n_anchor = anchor_count(L, ch.b);
     const Layout y = make_layout(L, A - 3u * L, ch.title_len, (uint32_t)n_anchor);
     uint8_t* B = ch.B;
+    uint32_t* fl = ch.fl;
+    int32_t* fli = reinterpret_cast<int32_t*>(ch.fl);
+    float* flf = reinterpret_cast<float*>(ch.fl);
 
     // ---- phase 1: residue -> first atom (exclusive scan of table atom counts), side-chain atom -> residue
     {
@@ -217,17 +356,24 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
             base += n;
         }
         if (r1 == L) ch.aoff[L] = base;
+        // scratch of the float-first path: counters, bounds (ordered ints), exact extremes
+        for (uint32_t i = cx.tid; i < (uint32_t)FL_DER; i += cx.nthr) {
+            uint32_t v = 0u;
+            if (i >= (uint32_t)FL_BND && i < (uint32_t)FL_EX) {
+                const uint32_t w = (i - FL_BND) & 3u;  // min(x-eps), max(x-eps), min(x+eps), max(x+eps)
+                v = (uint32_t)ford((w & 1u) ? -INFINITY : INFINITY);
+            } else if (i >= (uint32_t)FL_EX) {
+                v = (uint32_t)ford(((i - FL_EX) & 1u) ? -INFINITY : INFINITY);
+            }
+            fl[i] = v;
+        }
     }
     cx.stage_wait();  // coordinates staged by the caller are now visible
     cx.sync();
     cx.mark(0);  // E_SCAN
 
     // ---- phase 2: side-chain bytes, one dihedral per side-chain atom (src/sidechain.cpp:149-168 +
-    // FixedAngleDiscretizer, src/foldcomp.cpp:532-538).  The stored byte is a monotone step function of
-    // cos(torsion), so it is read off a 128-entry threshold table in cos-space (Tables::sc_pos/sc_neg, built
-    // with the host's libm exactly as the reference evaluates it): no acos at all.  The cosine itself is
-    // first taken in single precision (inner * rsqrt(p), within 4 ulp of the reference's float); only when
-    // that lands within the error of a threshold is the reference's exact double sqrt/divide evaluated.
+    // FixedAngleDiscretizer, src/foldcomp.cpp:532-538), float first (sc_byte_fast).
     {
         const uint32_t S = A - 3u * L;
         for (uint32_t t = cx.tid; t < S; t += cx.nthr) {
@@ -246,106 +392,156 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
         }
     }
     cx.mark(1);  // E_SIDE (no barrier: timing only)
-    // ---- phase 3: backbone torsions j = 0 .. 3L-4 (src/torsion_angle.cpp:49-94; j%3 = 0 psi, 1 omega,
-    // 2 phi of residue j/3, src/foldcomp.cpp:488-492) and bond angles at backbone atoms m = 2 .. 3L-2
-    // (src/nerf.cpp:495-508; m%3 = 2 CA-C-N[m/3], 0 C-N-CA[m/3-1], 1 N-CA-C[m/3-1], src/foldcomp.cpp:496-505)
-    // in ONE loop, so that the double-precision tail (cosine, acos, degrees) exists once.
+
+    // ---- phase 3: backbone, float first.  One item = residue pair (r, r+1) and k in {0,1,2}: the torsion over the four
+    // backbone atoms 3r+k .. 3r+k+3 (psi, omega, phi of record r: src/torsion_angle.cpp:49-94, src/foldcomp.cpp:488-492)
+    // AND the bond angle at the third of them (CA-C-N, C-N-CA, N-CA-C of record r: src/nerf.cpp:495-508,
+    // src/foldcomp.cpp:496-505), which share their bond vectors.  Every value is stored as a float estimate x (ang_fast);
+    // per array the extremes of x - eps and x + eps are gathered (thread, warp, then integer atomics on ordered floats).
+    // k is uniform over a warp when the warps come in threes.
     {
-        const uint32_t nT = 3u * L - 3u;
-        for (uint32_t w = cx.tid; w < 2u * nT; w += cx.nthr) {
-            f3 v1, v2;
-            bool neg = false;
-            const bool is_tor = w < nT;
-            uint32_t dst;
-            if (is_tor) {
-                const uint32_t r = w / 3u, k = w - 3u * r;
-                const uint32_t a0 = ch.aoff[r], a1 = ch.aoff[r + 1u];
-                // backbone atoms j .. j+3 = (r,k) (r,k+1) ... wrapping into residue r+1
-                const uint32_t i0 = a0 + k, i1 = (k < 2u) ? a0 + k + 1u : a1, i2 = (k < 1u) ? a0 + 2u : a1 + (k - 1u), i3 = a1 + k;
-                const f3 p0 = ld3(ch.X + 3u * i0), p1 = ld3(ch.X + 3u * i1), p2 = ld3(ch.X + 3u * i2), p3 = ld3(ch.X + 3u * i3);
+        const int kstep = (cx.nwarps % 3 == 0) ? 3 : 1;
+        const uint32_t rstart = (uint32_t)cx.lane + (uint32_t)cx.wsize * (uint32_t)(kstep == 3 ? cx.warp / 3 : cx.warp);
+        const uint32_t rstep = (uint32_t)cx.wsize * (uint32_t)(kstep == 3 ? cx.nwarps / 3 : cx.nwarps);
+        uint32_t bad = 0;
+        for (uint32_t k = (kstep == 3) ? (uint32_t)(cx.warp % 3) : 0u; k < 3u; k += (uint32_t)kstep) {
+            const uint32_t at = (k == 0u) ? (uint32_t)A_PSI : (k == 1u ? (uint32_t)A_OMEGA : (uint32_t)A_PHI);
+            const uint32_t ab = (k == 0u) ? (uint32_t)A_CACN : (k == 1u ? (uint32_t)A_CNCA : (uint32_t)A_NCAC);
+            float tlo_mn = INFINITY, tlo_mx = -INFINITY, thi_mn = INFINITY, thi_mx = -INFINITY;
+            float blo_mn = INFINITY, blo_mx = -INFINITY, bhi_mn = INFINITY, bhi_mx = -INFINITY;
+            for (uint32_t r = rstart; r + 1u < L; r += rstep) {
+                f3 p0, p1, p2, p3;
+                bb_item_atoms(ch, r, k, p0, p1, p2, p3);
                 const f3 d1 = sub3(p1, p0), d2 = sub3(p2, p1), d3 = sub3(p3, p2);
-                v1 = cross3(d1, d2);
-                v2 = cross3(d2, d3);
-                const f3 pb = cross3(v2, d2);
-                neg = (v1.x * pb.x) + (v1.y * pb.y) + (v1.z * pb.z) < 0;
-                dst = (k == 0u ? (uint32_t)A_PSI : (k == 1u ? (uint32_t)A_OMEGA : (uint32_t)A_PHI)) * L + r;
-            } else {
-                const uint32_t m = 2u + (w - nT);
-                const uint32_t q = m / 3u, k = m - 3u * q;
-                const f3 pm = bb_atom(ch, m);
-                v1 = sub3(bb_atom(ch, m - 1u), pm);
-                v2 = sub3(bb_atom(ch, m + 1u), pm);
-                dst = (k == 2u) ? (uint32_t)A_CACN * L + q : (k == 0u ? (uint32_t)A_CNCA * L + q - 1u : (uint32_t)A_NCAC * L + q - 1u);
+                const f3 u1 = cross3(d1, d2), u2 = cross3(d2, d3);
+                const f3 pb = cross3(u2, d2);
+                const bool neg = (u1.x * pb.x) + (u1.y * pb.y) + (u1.z * pb.z) < 0;
+                const float xt = ang_fast(dot_parts(u1, u2), true, neg, bad);
+                // bond angle at p2 between p1 - p2 = -d2 and p3 - p2 = d3: negation is exact, so the reference's
+                // products and sums (src/float3d.h:36-43) are these with the sign flipped
+                DotParts da;
+                da.inner = -((d2.x * d3.x) + (d2.y * d3.y) + (d2.z * d3.z));
+                da.p = (d2.x * d2.x + d2.y * d2.y + d2.z * d2.z) * (d3.x * d3.x + d3.y * d3.y + d3.z * d3.z);
+                const float xb = ang_fast(da, false, false, bad);
+                ch.ang[at * L + r] = xt;
+                ch.ang[ab * L + r] = xb;
+                const float et = ang_eps(xt), eb = ang_eps(xb);
+                const float tl = xt - et, th = xt + et, bl = xb - eb, bh = xb + eb;
+                tlo_mn = fminf(tlo_mn, tl); tlo_mx = fmaxf(tlo_mx, tl); thi_mn = fminf(thi_mn, th); thi_mx = fmaxf(thi_mx, th);
+                blo_mn = fminf(blo_mn, bl); blo_mx = fmaxf(blo_mx, bl); bhi_mn = fminf(bhi_mn, bh); bhi_mx = fmaxf(bhi_mx, bh);
             }
-            const float c = cos_ref(dot_parts(v1, v2));
-            float deg;
-            if (!acos_deg_certified(c, &deg)) deg = angle_deg_slow(c, is_tor);  // ~2e-6 of items, and |c| > 1
-            if (is_tor && neg) deg = -deg;
-            ch.ang[dst] = deg;
+            int32_t v[8] = {ford(tlo_mn), ford(tlo_mx), ford(thi_mn), ford(thi_mx), ford(blo_mn), ford(blo_mx), ford(bhi_mn), ford(bhi_mx)};
+            for (int i = 0; i < 8; i++) v[i] = (i & 1) ? cx.wmax_i(v[i]) : cx.wmin_i(v[i]);
+            if (cx.lane == 0) {
+                for (int i = 0; i < 8; i++) {
+                    int32_t* dst = fli + FL_BND + 4 * (i < 4 ? at : ab) + (i & 3);
+                    if (i & 1) cx.atomic_max_i(dst, v[i]); else cx.atomic_min_i(dst, v[i]);
+                }
+            }
+        }
+        if (bad) fl[FL_BAD] = 1u;
+        // B-factors: exact extremes (they are input)
+        {
+            float mn = INFINITY, mx = -INFINITY;
+            for (uint32_t i = cx.tid; i < L; i += cx.nthr) {
+                const float v = ch.bfac[i];
+                mn = min_ignore_nan(mn, v);
+                mx = max_ignore_nan(mx, v);
+            }
+            const int32_t imn = cx.wmin_i(ford(mn)), imx = cx.wmax_i(ford(mx));
+            if (cx.lane == 0) {
+                cx.atomic_min_i(fli + FL_EX + 12, imn);
+                cx.atomic_max_i(fli + FL_EX + 13, imx);
+            }
         }
     }
     cx.sync();
+    cx.mark(2);
 
-    // ---- phase 4: min / max of the six arrays (L-1 values) and of the B-factors (L values)
-    // (Discretizer::Discretizer, src/discretizer.cpp:22-33)
-    {
-        float mn[7], mx[7];
-        for (int k = 0; k < 7; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
-        for (uint32_t i = cx.tid; i < L; i += cx.nthr) {
-            if (i + 1u < L) {
-                for (int k = 0; k < 6; k++) {
-                    float v = ch.ang[k * L + i];
-                    mn[k] = min_ignore_nan(mn[k], v);
-                    mx[k] = max_ignore_nan(mx[k], v);
+    float* prm = ch.red + cx.nwarps * 14 + 14;  // [21] (min, disc_f, cont_f) x 7
+    if (cx.tid == 6 % cx.nthr) enc_params(ch, 6, funord(fli[FL_EX + 12]), funord(fli[FL_EX + 13]), ch.bfac[0], prm + 18);
+    bool exact_path = fl[FL_BAD] != 0u;
+    if (!exact_path) {
+        // ---- phase 4a: what pass B needs of the bounds, per array.  The true min lies in [mL, mU] = [min(x-eps), min(x+eps)],
+        // the true max in [ML, MU]; disc_f = RN(nb / RN(max - min)) is monotone in both, so IEEE float operations on
+        // the interval ends bracket it without any slop.
+        for (int a = cx.tid; a < 6; a += cx.nthr) {
+            const float mL = funord(fli[FL_BND + 4 * a]), ML = funord(fli[FL_BND + 4 * a + 1]);
+            const float mU = funord(fli[FL_BND + 4 * a + 2]), MU = funord(fli[FL_BND + 4 * a + 3]);
+            const float nb = (float)n_bins(a);
+            float* d = flf + FL_DER + 6 * a;
+            d[0] = mU; d[1] = mL; d[2] = ML;
+            d[3] = nb / (MU - mL);  // f_lo
+            d[4] = nb / (ML - mU);  // f_hi (inf / negative / NaN when the bounds cross: then every item is undecided)
+        }
+        cx.sync();
+        // ---- phase 4b: decide every value from its estimate.  x in [x-eps, x+eps], min in [mL, mU], f in [f_lo, f_hi]:
+        // RN(x - min) * f is bracketed by t_lo = RN(RN(lo - mU) * f_lo) and t_hi = RN(RN(hi - mL) * f_hi) (monotone IEEE
+        // operations on non-negative values).  Same rounded integer at both ends and no chance of being the array's
+        // min or max: that integer is the reference's; otherwise the value goes on the list.
+        {
+            const uint32_t W = (uint32_t)cx.wsize, Lp = (L - 1u + W - 1u) / W * W;
+            uint32_t* q = reinterpret_cast<uint32_t*>(ch.ang);
+            for (uint32_t v = cx.tid; v < 6u * Lp; v += cx.nthr) {
+                const uint32_t a = v / Lp, r = v - a * Lp;
+                if (r + 1u >= L) continue;
+                const float* d = flf + FL_DER + 6 * a;
+                const float x = ch.ang[a * L + r];
+                const float e = ang_eps(x);
+                const float lo = x - e, hi = x + e;
+                const float t_lo = (lo - d[0]) * d[3], t_hi = (hi - d[1]) * d[4];
+                uint32_t q_lo = 0u;
+                bool decided = false;
+                if (lo > d[0] && hi < d[2] && t_lo >= 0.0f && t_hi < 65536.0f) {
+                    q_lo = round_half_up(t_lo);
+                    decided = q_lo == round_half_up(t_hi);
+                }
+                if (decided) {
+                    q[a * L + r] = q_lo;
+                } else {
+                    const uint32_t j = cx.atomic_add(&fl[FL_N], 1u);
+                    if (j < ch.list_cap) ch.list[j] = a * L + r;
                 }
             }
-            float v = ch.bfac[i];
-            mn[6] = min_ignore_nan(mn[6], v);
-            mx[6] = max_ignore_nan(mx[6], v);
-        }
-        for (int k = 0; k < 7; k++) {
-            mn[k] = cx.wmin(mn[k]);
-            mx[k] = cx.wmax(mx[k]);
-        }
-        if (cx.lane == 0) {
-            for (int k = 0; k < 7; k++) {
-                ch.red[cx.warp * 14 + k] = mn[k];
-                ch.red[cx.warp * 14 + 7 + k] = mx[k];
-            }
         }
         cx.sync();
-        float* res = ch.red + cx.nwarps * 14;  // [14] min/max, then [21] (min, disc_f, cont_f) x 7
-        for (int k = cx.tid; k < 7; k += cx.nthr) {
-            float lo = INFINITY, hi = -INFINITY;
-            for (int w = 0; w < cx.nwarps; w++) {
-                lo = min_ignore_nan(lo, ch.red[w * 14 + k]);
-                hi = max_ignore_nan(hi, ch.red[w * 14 + 7 + k]);
-            }
-            float first = (k < 6) ? ch.ang[k * L] : ch.bfac[0];
-            if (first != first) {  // min_element/max_element keep a NaN first element
-                // A bond angle that came out NaN: WHICH NaN is hardware business (see x86_angle_nan); B-factors are input
-                // and are copied bit for bit (this->min = *std::min_element(...) is a plain move).
-                if (k >= 3 && k < 6) first = x86_angle_nan(ch, k == A_CACN ? 2u : (k == A_CNCA ? 3u : 4u));
-                lo = first; hi = first;
-            }
-            unsigned nb = (k < 6) ? n_bins(k) : 255u;
-            float* prm = res + 14 + 3 * k;
-            prm[0] = lo;
-            prm[1] = disc_factor(lo, hi, nb);
-            prm[2] = cont_factor(lo, hi, nb);
-            if (prm[2] != prm[2]) {
-                // (max - min) is NaN: x86 propagates the quieted NaN operand (min = max = the NaN first element) through
-                // the subtraction and the division, and produces its default NaN (negative, 0xFFC00000) for inf - inf;
-                // a GPU would put its canonical 0x7FFFFFFF into the header instead (src/discretizer.cpp:27-32).
-                const float nanv = u2f(lo != lo ? (f2u(lo) | 0x00400000u) : 0xFFC00000u);
-                prm[1] = nanv;
-                prm[2] = nanv;
-            }
-        }
-        cx.sync();
-        cx.mark(2);  // E_MINMAX
+        exact_path = fl[FL_N] > ch.list_cap;
     }
-    const float* prm = ch.red + cx.nwarps * 14 + 14;
+    if (!exact_path) {
+        // ---- phase 4c: the undecided values by the reference's exact sequence; their extremes are the arrays' extremes
+        const uint32_t n = fl[FL_N];
+        for (uint32_t j = cx.tid; j < n; j += cx.nthr) {
+            const uint32_t v = ch.list[j], a = v / L, r = v - a * L;
+            const float x = bb_value_exact(ch, a, r);
+            ch.xe[j] = x;
+            if (x == x) {
+                cx.atomic_min_i(fli + FL_EX + 2 * a, ford(x));
+                cx.atomic_max_i(fli + FL_EX + 2 * a + 1, ford(x));
+            } else {
+                fl[FL_BAD] = 1u;  // cannot happen (a NaN bond angle sets `bad` in phase 3); belt and braces
+            }
+        }
+        cx.sync();
+        exact_path = fl[FL_BAD] != 0u;
+    }
+    if (!exact_path) {
+        for (int a = cx.tid; a < 6; a += cx.nthr) {
+            const float lo = funord(fli[FL_EX + 2 * a]), hi = funord(fli[FL_EX + 2 * a + 1]);
+            enc_params(ch, a, lo, hi, lo, prm + 3 * a);  // no NaN on this path: the first element plays no role
+        }
+        cx.sync();
+        const uint32_t n = fl[FL_N];
+        uint32_t* q = reinterpret_cast<uint32_t*>(ch.ang);
+        for (uint32_t j = cx.tid; j < n; j += cx.nthr) {
+            const uint32_t v = ch.list[j], a = v / L;
+            q[v] = disc_round(ch.xe[j], prm[3 * a], prm[3 * a + 1]);
+        }
+    } else {
+        cx.sync();  // (phase-4 scratch reads above are done)
+        enc_backbone_exact(cx, ch);
+    }
+    cx.sync();
+    cx.mark(2);  // E_MINMAX
 
     // ---- phase 5: serialise (src/foldcomp.cpp:1038-1109)
     if (cx.tid == 0) {
@@ -384,13 +580,16 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
         put_f32(B + y.o_anchor + 4u * e, ch.X[3u * ch.aoff[r] + w]);
     }
     // backbone records (src/foldcomp.cpp:581-602) and B-factor bytes (src/foldcomp.cpp:1102-1107)
-    for (uint32_t r = cx.tid; r < L; r += cx.nthr) {
-        unsigned q[6] = {0, 0, 0, 0, 0, 0};
-        if (r + 1u < L) {
-            for (int k = 0; k < 6; k++) q[k] = disc_round(ch.ang[k * L + r], prm[3 * k], prm[3 * k + 1]);
+    {
+        const uint32_t* qv = reinterpret_cast<const uint32_t*>(ch.ang);
+        for (uint32_t r = cx.tid; r < L; r += cx.nthr) {
+            unsigned q[6] = {0, 0, 0, 0, 0, 0};
+            if (r + 1u < L) {
+                for (int k = 0; k < 6; k++) q[k] = qv[k * L + r];
+            }
+            pack_record(B + y.o_rec + 8u * r, ch.type[r], q[A_PHI], q[A_PSI], q[A_OMEGA], q[A_NCAC], q[A_CACN], q[A_CNCA]);
+            B[y.o_temp + 8u + r] = (uint8_t)disc_round(ch.bfac[r], prm[18], prm[19]);
         }
-        pack_record(B + y.o_rec + 8u * r, ch.type[r], q[A_PHI], q[A_PSI], q[A_OMEGA], q[A_NCAC], q[A_CACN], q[A_CNCA]);
-        B[y.o_temp + 8u + r] = (uint8_t)disc_round(ch.bfac[r], prm[18], prm[19]);
     }
     cx.sync();
     cx.mark(3);  // E_PACK

@@ -34,7 +34,8 @@ struct TierCfg {
     uint32_t max_atoms;  // atoms
     uint32_t max_blob;   // blob bytes
     uint32_t max_seg;    // anchor segments (decode)
-    uint32_t staged;     // 1: chain data staged in smem; 0: large tier, data stays in global memory
+    uint32_t staged;     // 1: blob (and residue types) staged in smem; 0: large tier, the blob is written to global memory directly
+    uint32_t stage_x;    // 1: the chain's coordinates are staged in smem by a bulk copy; 0: read from global memory (L1 / L2)
     uint32_t gws;        // 1: the workspace (atom offsets, angle arrays) lives in global memory too (k_encode_long)
     uint32_t threads;
     uint32_t smem;       // dynamic shared memory bytes
@@ -54,7 +55,7 @@ __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15
 
 // ---- shared memory carve-up (offsets are computed identically on host and device)
 struct EncSmem {
-    uint32_t o_tab, o_misc, o_red, o_type, o_aoff, o_ares, o_ang, o_x, o_b, total;
+    uint32_t o_tab, o_misc, o_red, o_fl, o_list, o_type, o_aoff, o_ares, o_ang, o_x, o_b, total;
 };
 __host__ __device__ inline EncSmem enc_smem(const TierCfg& t) {
     EncSmem s;
@@ -62,11 +63,13 @@ __host__ __device__ inline EncSmem enc_smem(const TierCfg& t) {
     s.o_tab = o;  o += align16((uint32_t)offsetof(Tables, blen));
     s.o_misc = o; o += 256;  // mbarrier, ticket, warp sums
     s.o_red = o;  o += align16(4u * FCZ_RED_FLOATS(32));
+    s.o_fl = o;   o += align16(4u * FCZ_FL_WORDS);
+    s.o_list = o; o += t.gws ? 0u : align16(8u * enc_list_cap(t.max_res));  // undecided values + their exact values
     s.o_type = o; o += t.staged ? align16(t.max_res) : 0u;
     s.o_aoff = o; o += t.gws ? 0u : align16(4u * (t.max_res + 1u));
     s.o_ares = o; o += t.gws ? 0u : align16(2u * t.max_atoms);
     s.o_ang = o;  o += t.gws ? 0u : align16(24u * t.max_res);
-    s.o_x = o;    o += t.staged ? align16(12u * t.max_atoms) + 32u : 0u;
+    s.o_x = o;    o += t.stage_x ? align16(12u * t.max_atoms) + 32u : 0u;
     s.o_b = o;    o += t.staged ? align16(t.max_blob) + 32u : 0u;
     s.total = o;
     return s;
@@ -75,6 +78,7 @@ static TierCfg make_tier(uint32_t max_res, bool staged, bool gws) {
     TierCfg t;
     t.max_res = max_res;
     t.staged = staged ? 1u : 0u;
+    t.stage_x = t.staged;
     t.gws = gws ? 1u : 0u;
     t.max_atoms = 9u * max_res;
     t.max_blob = 17u * max_res + 1280u;
@@ -199,6 +203,11 @@ struct DevCtx {
         for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
         return v;
     }
+    // integer warp reductions (REDUX.MIN / REDUX.MAX) and shared / global atomics: floats go through fcz::ford
+    __device__ __forceinline__ int32_t wmin_i(int32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+    __device__ __forceinline__ int32_t wmax_i(int32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+    __device__ __forceinline__ void atomic_min_i(int32_t* p, int32_t v) { atomicMin(p, v); }
+    __device__ __forceinline__ void atomic_max_i(int32_t* p, int32_t v) { atomicMax(p, v); }
 };
 
 // Stage `bytes` bytes starting at global address `src` into shared memory so that the copy has
@@ -340,7 +349,10 @@ __global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* 
     }
 }
 
-__global__ void __launch_bounds__(1024) k_encode(EncArgs a) {
+#ifndef FCZ_ENC_MAXREG
+#define FCZ_ENC_MAXREG 72  // 864 threads per SM (3 CTAs of 288) fit the register file
+#endif
+__global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncSmem so = enc_smem(a.cfg);
     Tables* tb = reinterpret_cast<Tables*>(smem + so.o_tab);
@@ -385,11 +397,23 @@ __global__ void __launch_bounds__(1024) k_encode(EncArgs a) {
         ch.sres = reinterpret_cast<uint16_t*>(smem + so.o_ares);
         ch.ang = reinterpret_cast<float*>(smem + so.o_ang);
         ch.red = reinterpret_cast<float*>(smem + so.o_red);
+        ch.fl = reinterpret_cast<uint32_t*>(smem + so.o_fl);
+        ch.list_cap = enc_list_cap(a.cfg.max_res);
+        ch.list = reinterpret_cast<uint32_t*>(smem + so.o_list);
+        ch.xe = reinterpret_cast<float*>(smem + so.o_list) + ch.list_cap;
         uint8_t* gdst = a.bytes + b0;
         uint8_t* sB = nullptr;
         if (a.cfg.staged) {
-            const uint8_t* gx = reinterpret_cast<const uint8_t*>(a.xyz + 3u * a0);
-            ch.X = reinterpret_cast<const float*>(stage_in(cx, smem + so.o_x, gx, 12u * A));
+            if (a.cfg.stage_x) {
+                const uint8_t* gx = reinterpret_cast<const uint8_t*>(a.xyz + 3u * a0);
+                ch.X = reinterpret_cast<const float*>(stage_in(cx, smem + so.o_x, gx, 12u * A));
+            } else {
+                // coordinates stay in global memory: pull the chain towards L2 while phase 1 runs (one line per thread and trip)
+                ch.X = a.xyz + 3u * a0;
+                const char* gx = reinterpret_cast<const char*>(ch.X);
+                for (uint32_t off = cx.tid * 128u; off < 12u * A; off += cx.nthr * 128u) prefetch_l2(gx + off);
+                cx.staged = false;
+            }
             uint8_t* st = smem + so.o_type;
             for (uint32_t i = cx.tid; i < L; i += cx.nthr) st[i] = a.res_type[r0 + i];
             ch.type = st;
@@ -407,20 +431,30 @@ __global__ void __launch_bounds__(1024) k_encode(EncArgs a) {
         __builtin_assume(__isShared(ch.sres));
         __builtin_assume(__isShared(ch.ang));
         __builtin_assume(__isShared(ch.red));
-        if (a.cfg.staged) {
+        __builtin_assume(__isShared(ch.fl));
+        __builtin_assume(__isShared(ch.list));
+        __builtin_assume(__isShared(ch.xe));
+        if (a.cfg.staged && a.cfg.stage_x) {
             __builtin_assume(__isShared(ch.X));
             __builtin_assume(__isShared(ch.type));
             __builtin_assume(__isShared(ch.B));
             encode_chain(cx, tb, ch);
-        } else {
+        } else if (a.cfg.staged) {
+            __builtin_assume(__isGlobal(ch.X));
+            __builtin_assume(__isShared(ch.type));
+            __builtin_assume(__isShared(ch.B));
             encode_chain(cx, tb, ch);
+        } else {
+#ifndef FCZ_ANALYSE_STAGED_ONLY  // (tools/sass_static.py: count one copy of the codec)
+            encode_chain(cx, tb, ch);
+#endif
         }
         if (a.term && cx.tid == 0) (a.cfg.staged ? sB : gdst)[size - 1u] = 0;  // encode_chain ended with a barrier
         if (a.cfg.staged) {
             if (a.term) __syncthreads();
             copy_out(cx, gdst, sB, size);
             cx.mark(4);
-            cx.parity ^= 1u;
+            if (a.cfg.stage_x) cx.parity ^= 1u;
             cx.staged = false;
         }
         __syncthreads();  // shared buffers free for the next chain
@@ -430,7 +464,8 @@ __global__ void __launch_bounds__(1024) k_encode(EncArgs a) {
 // The long tier (2721 .. 65535 residues): chain data AND workspace stay in global memory (per-block slices of
 // a.gws, sized for the tier's longest chain); otherwise the same persistent ticket loop as k_encode.
 __host__ __device__ inline uint64_t enc_gws_bytes(uint32_t max_res) {
-    return (uint64_t)align16(4u * (max_res + 1u)) + align16(2u * (FCZ_MAX_ATOMS - 3u) * max_res) + align16(24u * max_res);
+    return (uint64_t)align16(4u * (max_res + 1u)) + align16(2u * (FCZ_MAX_ATOMS - 3u) * max_res) + align16(24u * max_res) +
+           align16(8u * enc_list_cap(max_res));
 }
 __global__ void __launch_bounds__(1024) k_encode_long(EncArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -469,6 +504,10 @@ __global__ void __launch_bounds__(1024) k_encode_long(EncArgs a) {
         ch.sres = reinterpret_cast<uint16_t*>(ws + align16(4u * (a.gws_max_res + 1u)));
         ch.ang = reinterpret_cast<float*>(ws + align16(4u * (a.gws_max_res + 1u)) + align16(2u * (FCZ_MAX_ATOMS - 3u) * a.gws_max_res));
         ch.red = reinterpret_cast<float*>(smem + so.o_red);
+        ch.fl = reinterpret_cast<uint32_t*>(smem + so.o_fl);
+        ch.list_cap = enc_list_cap(a.gws_max_res);
+        ch.list = reinterpret_cast<uint32_t*>(ws + align16(4u * (a.gws_max_res + 1u)) + align16(2u * (FCZ_MAX_ATOMS - 3u) * a.gws_max_res) + align16(24u * a.gws_max_res));
+        ch.xe = reinterpret_cast<float*>(ch.list) + ch.list_cap;
         ch.X = a.xyz + 3u * a0;
         ch.type = a.res_type + r0;
         ch.B = a.bytes + a.blob_off[c];
@@ -1368,6 +1407,11 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
         e->own_stream = true;
     }
     make_tiers(e->enc_tier);
+    // experiment knobs (A/B runs, tools/kernel_ab.py): FCZ_ENC_XGLOBAL=1 reads coordinates from global memory instead of staging
+    // them (smaller footprint, more CTAs per SM); FCZ_ENC_THREADS fixes the block size of the staged tiers
+    if (const char* v = getenv("FCZ_ENC_XGLOBAL")) {
+        if (atoi(v)) for (int i = 0; i < FCZ_NTIER; i++) { e->enc_tier[i].stage_x = 0; e->enc_tier[i].smem = enc_smem(e->enc_tier[i]).total; }
+    }
     bool ok = true;
     ok &= cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) == cudaSuccess;
     ok &= cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -1396,11 +1440,13 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
         int occ = 0;
         ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, 128, e->enc_tier[i].smem) == cudaSuccess;
         if (occ < 1) occ = 1;
-        uint32_t thr = (1024u / (uint32_t)occ) & ~31u;
-        e->enc_tier[i].threads = thr < 128u ? 128u : thr;
+        uint32_t thr = (1024u / (uint32_t)occ) / 96u * 96u;  // whole triples of warps: phase 3's k is uniform over a warp
+        if (const char* v = getenv("FCZ_ENC_THREADS")) { const long q = atol(v); if (q >= 32 && e->enc_tier[i].staged) thr = (uint32_t)q; }
+        if (thr > 768u) thr = 768u;  // k_encode's launch bound
+        e->enc_tier[i].threads = thr < 96u ? 96u : thr;
         ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, (int)e->enc_tier[i].threads, e->enc_tier[i].smem) == cudaSuccess;
         e->enc_occ[i] = occ > 0 ? occ : 1;
-        if (e->enc_tier[i].gws) { e->enc_tier[i].threads = 1024u; e->enc_occ[i] = 1; }  // one wide block per SM walks a long chain
+        if (e->enc_tier[i].gws) { e->enc_tier[i].threads = 960u; e->enc_occ[i] = 1; }  // one wide block per SM walks a long chain
     }
     Tables h;
     build_tables(&h);

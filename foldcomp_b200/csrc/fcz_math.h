@@ -9,6 +9,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define FCZ_HD __host__ __device__ __forceinline__
@@ -27,6 +28,53 @@ namespace fcz {
 struct f3 {
     float x, y, z;
 };
+
+FCZ_HD float fma_(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+// Approximate reciprocal square root / reciprocal: MUFU.RSQ / MUFU.RCP on the device (rsqrt.approx / rcp.approx: <= 2 ulp, CUDA C
+// Programming Guide, mathematical functions appendix), IEEE operations on the host.  Every use sits behind an error
+// bound that covers several ulp either way.  FCZ_EMU_PERTURB (tests only, tests/emu) pushes the host results off by
+// up to +-3 ulp, pseudo-randomly per argument, so that the CPU tests exercise those bounds and not just the
+// correctly rounded special case.
+#if !defined(__CUDA_ARCH__) && defined(FCZ_EMU_PERTURB)
+inline float emu_perturb_(float v, float x) {
+    uint32_t h, u;
+    memcpy(&h, &x, 4);
+    h = (h ^ (h >> 15)) * 0x2c1b3c6du; h ^= h >> 12;
+    const int k = (int)(h % 7u) - 3;
+    memcpy(&u, &v, 4);
+    if ((u & 0x7f800000u) != 0x7f800000u && (u & 0x7fffffffu) > 8u) u = (uint32_t)((int32_t)u + k);
+    memcpy(&v, &u, 4);
+    return v;
+}
+#endif
+FCZ_HD float rsqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;  // one MUFU.RSQ: rsqrtf() wraps it in denormal scaling that no caller needs (arguments are >= 1e-30 or rejected)
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#elif defined(FCZ_EMU_PERTURB)
+    return emu_perturb_(1.0f / sqrtf(x), x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+FCZ_HD float rcp_(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;  // one MUFU.RCP
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#elif defined(FCZ_EMU_PERTURB)
+    return emu_perturb_(1.0f / x, x);
+#else
+    return 1.0f / x;
+#endif
+}
 
 FCZ_HD f3 mk3(float x, float y, float z) {
     f3 r;
@@ -154,6 +202,88 @@ static FCZ_HD_SLOW float angle_deg_slow(float c, bool is_torsion) {
     return (float)(ac * 180.0 / M_PI);
 }
 
+// ---- single-precision arccosine in degrees with a proven error bound: the FLOAT-FIRST path of the encoder.
+// The exact sequence above is needed only for the few items whose quantised value (or min / max candidacy) a float
+// estimate cannot decide; everything else is decided from acosdeg_f and the bound FCZ_ACOS_E0.
+//   asin(s) [deg] = s (K + z P(z)),  z = s^2 <= 1/4,  P a degree-4 fit (4.9e-7 deg);  |c| <= 1/2: 90 - asin(c);
+//   |c| > 1/2: 2 asin(sqrt((1-|c|)/2)), mirrored for c < 0.  `rs` is an approximation of 1/sqrt((1-|c|)/2) that may be
+//   off by a few ulp (MUFU.RSQ on the device, 1/sqrtf on the host); only IEEE operations otherwise, so host and device
+//   agree bit for bit given the same rs.
+// FCZ_ACOS_E0 bounds |acosdeg_f(c, rs) - (float)(acos((double)c) * 180.0 / M_PI)| over EVERY float c in [-1, 1] and every
+// rs within 4 ulp of the true value (exhaustive sweep: tests/test_fastpath.py::test_float_acos_bound, measured 3.82e-5).
+#define FCZ_ACOS_E0 8.0e-5f
+FCZ_HD float acosdeg_f(float c, float rs) {
+    const float ax = fabsf(c);
+    const bool big = ax > 0.5f;
+    const float zb = (1.0f - ax) * 0.5f;  // exact for 1/2 <= |c| <= 1
+    const float z = big ? zb : c * c;
+    const float s = big ? zb * rs : ax;
+    float p = 0x1.1833680000000p+1f;
+    p = fma_(p, z, 0x1.849c500000000p+0f);
+    p = fma_(p, z, 0x1.4a1a280000000p+1f);
+    p = fma_(p, z, 0x1.12f9e00000000p+2f);
+    p = fma_(p, z, 0x1.3193de0000000p+3f);
+    const float r = fma_(s * z, p, s * 57.29577951308232f);  // asin(s) in degrees
+    if (big) return c < 0.0f ? fma_(-2.0f, r, 180.0f) : 2.0f * r;
+    return c < 0.0f ? 90.0f + r : 90.0f - r;
+}
+
+// An angle (bond angle, or torsion with its sign) as the float-first path sees it: the value the reference would
+// store is within ang_eps(x) of the returned x.
+//   * cosine from ONE MUFU.RSQ and a multiply: |c - c_ref| <= 4.5e-7 |c| (2 ulp + two roundings + the reference's own);
+//   * where that is not good enough -- |c| > FCZ_COS_HARD, i.e. within 0.81 degrees of 0 / 180, where the reference's
+//     angle is a coarse staircase of its float cosine -- the reference's EXACT cosine (cos_ref: certified double
+//     sequence) is taken, so the only error left is acosdeg_f's;
+//   * |c_ref| > 1: the reference's acos is NaN; torsions then take 0 / 180 (src/torsion_angle.cpp:74-79) -- exact
+//     here too; a NaN bond angle, a NaN cosine or a squared-length product outside [1e-30, 1e30] sets `bad`: the chain
+//     leaves the float-first path altogether (degenerate input).
+#define FCZ_COS_HARD 0.9999f   // acos = 0.81029 degrees
+#define FCZ_DEG_HARD 0.81f     // an x closer than this to 0 / 180 was computed from the exact cosine
+#define FCZ_ANG_E1 2.5e-3f     // >= 57.2958 * 4.5e-7 * 90 (1 + margin): cosine error over sin(theta) >= d / 90
+FCZ_HD float ang_fast(DotParts dp, bool is_tor, bool neg, uint32_t& bad) {
+    float c = dp.inner * rsqrt_(dp.p);
+    if (!(dp.p >= 1e-30f && dp.p <= 1e30f)) bad |= 1u;
+    if (!(fabsf(c) <= FCZ_COS_HARD)) {
+        c = cos_ref(dp);
+        if (!(fabsf(c) <= 1.0f)) {
+            if (!is_tor) bad |= 1u;
+            const float t = c < 0.0f ? 180.0f : 0.0f;
+            return neg ? -t : t;
+        }
+    }
+    const float zb = (1.0f - fabsf(c)) * 0.5f;
+    const float x = acosdeg_f(c, rsqrt_(fmaxf(zb, 1e-30f)));
+    return (is_tor && neg) ? -x : x;
+}
+// bound on |x - reference value| for an x returned by ang_fast (a function of x alone, so that later passes can
+// recompute it from the stored value): d = distance to 0 / 180 degrees
+FCZ_HD float ang_eps(float x) {
+    const float ax = fabsf(x);
+    const float d = fminf(ax, 180.0f - ax);
+    return d >= FCZ_DEG_HARD ? fma_(FCZ_ANG_E1, rcp_(d), FCZ_ACOS_E0) : FCZ_ACOS_E0;
+}
+// monotone map float -> int32 (for non-NaN values): integer min / max / atomics on floats
+FCZ_HD int32_t ford(float f) {
+    uint32_t u;
+#if defined(__CUDA_ARCH__)
+    u = __float_as_uint(f);
+#else
+    memcpy(&u, &f, 4);
+#endif
+    const int32_t i = (int32_t)u;
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+FCZ_HD float funord(int32_t i) {
+    const uint32_t u = (uint32_t)(i ^ ((i >> 31) & 0x7fffffff));
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
 // reference: angle, src/float3d.h:55-65 -- bond angle at a2 in degrees (double acos).
 FCZ_HD float bond_angle_deg(f3 a1, f3 a2, f3 a3) {
     float c = cos_theta(sub3(a1, a2), sub3(a3, a2));
@@ -182,20 +312,6 @@ FCZ_HD float dihedral_deg(f3 a1, f3 a2, f3 a3, f3 a4) {
 // the BASELINE.md tolerance instead and is free to use fused multiply-adds, rsqrt and a propagated
 // frame.  Everything below is exact-arithmetic equivalent to Nerf::place_atom (src/nerf.cpp:39-104).
 
-FCZ_HD float fma_(float a, float b, float c) {
-#if defined(__CUDA_ARCH__)
-    return __fmaf_rn(a, b, c);
-#else
-    return fmaf(a, b, c);
-#endif
-}
-FCZ_HD float rsqrt_(float x) {
-#if defined(__CUDA_ARCH__)
-    return rsqrtf(x);
-#else
-    return 1.0f / sqrtf(x);
-#endif
-}
 FCZ_HD float dotf(f3 a, f3 b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
 FCZ_HD f3 crossf(f3 a, f3 b) {
     return mk3(fma_(a.y, b.z, -(b.y * a.z)), fma_(a.z, b.x, -(b.z * a.x)), fma_(a.x, b.y, -(b.x * a.y)));

@@ -22,6 +22,10 @@ struct HostCtx {
     float wmin(float v) { return v; }
     float wmax(float v) { return v; }
     uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+    int32_t wmin_i(int32_t v) { return v; }
+    int32_t wmax_i(int32_t v) { return v; }
+    void atomic_min_i(int32_t* p, int32_t v) { if (v < *p) *p = v; }
+    void atomic_max_i(int32_t* p, int32_t v) { if (v > *p) *p = v; }
 };
 
 static const Tables* tables() {
@@ -30,6 +34,8 @@ static const Tables* tables() {
     if (!init) { build_tables(&t); init = true; }
     return &t;
 }
+
+static thread_local uint32_t g_last_list = 0, g_last_bad = 0, g_last_cap = 0, g_last_by_array[6] = {0, 0, 0, 0, 0, 0};
 
 extern "C" {
 
@@ -49,13 +55,26 @@ int64_t emu_encode_chain(const uint8_t* res_type, uint32_t L, const float* xyz, 
     std::vector<uint32_t> aoff(L + 1);
     std::vector<uint16_t> ares(A);
     std::vector<float> ang(6 * (size_t)L), red(FCZ_RED_FLOATS(1));
+    std::vector<uint32_t> fl(FCZ_FL_WORDS), list(enc_list_cap(L));
+    std::vector<float> xe(enc_list_cap(L));
     EncChain ch;
     ch.L = L; ch.A = A; ch.title_len = title_len; ch.b = b;
     ch.type = res_type; ch.bfac = bfac; ch.X = xyz; ch.title = title; ch.meta = meta; ch.B = out;
-    ch.aoff = aoff.data(); ch.sres = ares.data(); ch.ang = ang.data(); ch.red = red.data();
+    ch.aoff = aoff.data(); ch.sres = ares.data(); ch.ang = ang.data(); ch.red = red.data(); ch.fl = fl.data();
+    ch.list = list.data(); ch.xe = xe.data(); ch.list_cap = enc_list_cap(L);
     HostCtx cx;
     encode_chain(cx, tb, ch);
+    g_last_list = fl[FL_N]; g_last_bad = fl[FL_BAD];
+    for (int a = 0; a < 6; a++) g_last_by_array[a] = 0;
+    for (uint32_t j = 0; j < fl[FL_N] && j < ch.list_cap; j++) g_last_by_array[list[j] / L]++;
+    g_last_cap = ch.list_cap;
     return y.size;
+}
+// float-first path of the last emu_encode_chain on this thread: values re-evaluated exactly, and whether the chain
+// fell back to the all-exact path (degenerate geometry or list overflow)
+void emu_last_stats(uint32_t* out) {
+    out[0] = g_last_list; out[1] = (g_last_bad || g_last_list > g_last_cap) ? 1u : 0u;
+    for (int a = 0; a < 6; a++) out[2 + a] = g_last_by_array[a];
 }
 
 int emu_decode_chain(const uint8_t* blob, uint64_t len, int use_alt, uint8_t* res_type, float* bfac,
@@ -194,4 +213,30 @@ extern "C" long emu_cossin_check(double lo, double hi, uint64_t n) {
         if (e > worst) worst = e;
     }
     return (long)(worst * 1e9);
+}
+
+// acosdeg_f (the encoder's float-first arccosine) against the reference's float (float)(acos((double)c) * 180.0 / M_PI)
+// over the floats in [-1, 1] (stride 1 = all of them), with the reciprocal square root it is handed perturbed by
+// -4 .. +4 ulp: returns the largest absolute deviation in degrees.
+extern "C" double emu_acosdeg_f_check(uint32_t stride) {
+    double worst = 0;
+    const uint32_t one = 0x3f800000u;
+#pragma omp parallel for reduction(max : worst) schedule(static)
+    for (int64_t k = 0; k <= (int64_t)one; k += stride) {
+        for (int sgn = 0; sgn < 2; sgn++) {
+            uint32_t u = (uint32_t)k | (sgn ? 0x80000000u : 0u);
+            float c;
+            memcpy(&c, &u, 4);
+            const float want = (float)(acos((double)c) * 180.0 / M_PI);
+            const float zb = (1.0f - fabsf(c)) * 0.5f;
+            const float rs0 = (float)(1.0 / sqrt((double)(zb > 1e-30f ? zb : 1e-30f)));
+            for (int d = -4; d <= 4; d += 4) {
+                float rs = rs0;
+                for (int i = 0; i < (d < 0 ? -d : d); i++) rs = nextafterf(rs, d < 0 ? 0.0f : INFINITY);
+                const double e = fabs((double)fcz::acosdeg_f(c, rs) - (double)want);
+                if (e > worst) worst = e;
+            }
+        }
+    }
+    return worst;
 }

@@ -38,11 +38,18 @@ def build_oracle():
         subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "pyref"])
 
 
-def build_emu():
+EMU_PERTURB_SO = os.path.join(ROOT, "tests", "emu", "libfcz_emu_perturb.so")
+
+
+def build_emu(perturb: bool = False):
+    """perturb=True: the variant whose approximate reciprocal (square root) is pushed off by up to +-3 ulp, like a GPU's
+    MUFU results may be (fcz_math.h: FCZ_EMU_PERTURB) -- the certified shortcuts must not care."""
     src = os.path.join(ROOT, "tests", "emu", "fcz_emu.cpp")
+    so = EMU_PERTURB_SO if perturb else EMU_SO
     deps = [src] + [os.path.join(ROOT, "foldcomp_b200", "csrc", f) for f in ("fcz_codec.h", "fcz_math.h", "fcz_format.h", "fcz_tables.h", "fcz_text.h")]
-    if not os.path.exists(EMU_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMU_SO) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-o", EMU_SO, src])
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17"]
+                              + (["-DFCZ_EMU_PERTURB"] if perturb else []) + ["-o", so, src])
 
 
 _cache = {}
@@ -89,16 +96,25 @@ def ref():
     return _cache["ref"]
 
 
-def emu():
-    if "emu" not in _cache:
-        build_emu()
-        lib = C.CDLL(EMU_SO)
+def emu(perturb: bool = False):
+    key = "emu_perturb" if perturb else "emu"
+    if key not in _cache:
+        build_emu(perturb)
+        lib = C.CDLL(EMU_PERTURB_SO if perturb else EMU_SO)
         lib.emu_encode_chain.restype = C.c_int64
         lib.emu_encode_chain.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_uint64]
         lib.emu_decode_chain.restype = C.c_int
         lib.emu_decode_chain.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        _cache["emu"] = lib
-    return _cache["emu"]
+        lib.emu_last_stats.argtypes = [C.c_void_p]
+        _cache[key] = lib
+    return _cache[key]
+
+
+def emu_last_stats(perturb: bool = False):
+    """(values re-evaluated exactly, fell back to the all-exact path) of the last emu_encode on this thread."""
+    out = np.zeros(8, np.uint32)
+    emu(perturb).emu_last_stats(out.ctypes.data)
+    return int(out[0]), bool(out[1]), out[2:].copy()  # ... and the list entries per array (phi psi omega N-CA-C CA-C-N C-N-CA)
 
 
 # --------------------------------------------------------------------------- per-chain convenience
@@ -130,8 +146,8 @@ def oracle_encode(b: HostChainBatch, c: int = 0, anchor: int = 25):
     return _encode_with(oracle().fcz_oracle_encode_chain, b, c, anchor)
 
 
-def emu_encode(b: HostChainBatch, c: int = 0, anchor: int = 25):
-    return _encode_with(emu().emu_encode_chain, b, c, anchor)
+def emu_encode(b: HostChainBatch, c: int = 0, anchor: int = 25, perturb: bool = False):
+    return _encode_with(emu(perturb).emu_encode_chain, b, c, anchor)
 
 
 def ref_encode(b: HostChainBatch, c: int = 0, anchor: int = 25):

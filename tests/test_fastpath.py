@@ -5,12 +5,13 @@ take over), and on degenerate inputs.  Runs the product header through the one-t
 import ctypes as C
 
 import numpy as np
+import pytest
 
 import helpers as H
 
 
-def _lib():
-    lib = H.emu()
+def _lib(perturb=False):
+    lib = H.emu(perturb)
     lib.emu_sc_bytes.argtypes = [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_void_p]
     lib.emu_thresholds.argtypes = [C.c_void_p, C.c_void_p]
     lib.emu_cos_deg_mismatches.restype = C.c_uint64
@@ -28,8 +29,12 @@ def _sc(lib, inner, p, neg):
     return fast, exact
 
 
-def test_side_chain_bytes_random():
-    lib = _lib()
+PERTURB = pytest.mark.parametrize("perturb", [False, True], ids=["ieee", "perturbed"])
+
+
+@PERTURB
+def test_side_chain_bytes_random(perturb):
+    lib = _lib(perturb)
     rng = np.random.default_rng(0)
     n = 2_000_000
     # cosines spread over [-1,1] incl. the ill-conditioned ends; p over many magnitudes
@@ -42,8 +47,9 @@ def test_side_chain_bytes_random():
     assert len(np.unique(exact)) == 256  # every byte value occurs
 
 
-def test_side_chain_bytes_on_every_threshold():
-    lib = _lib()
+@PERTURB
+def test_side_chain_bytes_on_every_threshold(perturb):
+    lib = _lib(perturb)
     pos = np.zeros(128, np.float32)
     neg_t = np.zeros(128, np.float32)
     lib.emu_thresholds(pos.ctypes.data, neg_t.ctypes.data)
@@ -65,8 +71,9 @@ def test_side_chain_bytes_on_every_threshold():
         assert np.array_equal(fast, exact), scale
 
 
-def test_side_chain_bytes_degenerate():
-    lib = _lib()
+@PERTURB
+def test_side_chain_bytes_degenerate(perturb):
+    lib = _lib(perturb)
     inner = np.array([0, 0, 1, -1, 1e-20, 5, -5, np.nan, 1, 1.0000001, -1.0000001], np.float32)
     p = np.array([0, 1, 0, 0, 1e-40, 1, 1, 1, np.inf, 1, 1], np.float32)
     for flag in (0, 1):
@@ -100,6 +107,60 @@ def test_fast_acos_sampled():
     assert e <= -46000, e
     assert wrong.value == 0
     assert unc.value < 2000
+
+
+def test_float_acos_bound():
+    """acosdeg_f (the float-first arccosine of the encoder) against the reference's float over every 97th float of
+    [-1, 1], with the reciprocal square root it is handed off by up to +-4 ulp: the deviation must stay below
+    FCZ_ACOS_E0 = 8e-5 degrees, the constant every certification in fcz_codec.h builds on.  (stride 1 = all 2^31 floats,
+    run once by hand: 3.8147e-05.)"""
+    lib = _lib()
+    lib.emu_acosdeg_f_check.restype = C.c_double
+    lib.emu_acosdeg_f_check.argtypes = [C.c_uint32]
+    worst = lib.emu_acosdeg_f_check(97)
+    assert 1e-6 < worst <= 4.0e-5, worst
+
+
+@PERTURB
+def test_float_first_backbone_path_is_exercised_and_exact(perturb):
+    """The float-first path must (a) carry the synthetic chains -- no fall-back to the all-exact path, a few dozen
+    re-evaluated values per 350-residue chain -- and (b) give the oracle's bytes, also when the approximate
+    reciprocals it starts from are off by a few ulp (the perturbed build stands in for the GPU's MUFU results)."""
+    from foldcomp_b200 import synth
+
+    batch = synth.generate(120, 350, seed=4242)
+    want = H.oracle_encode_batch(batch, 25)
+    n_list = []
+    for c in range(batch.n_chains):
+        assert H.emu_encode(batch, c, 25, perturb=perturb) == want.blob(c), c
+        n, fell_back, _ = H.emu_last_stats(perturb)
+        assert not fell_back, c
+        n_list.append(n)
+    assert 10 <= np.mean(n_list) <= 120 and max(n_list) <= 256, (np.mean(n_list), max(n_list))
+    mixed = synth.generate(60, synth.mixed_lengths(np.random.default_rng(3), 60), seed=99)
+    for b in (10, 25, 50, 200):
+        want = H.oracle_encode_batch(mixed, b)
+        for c in range(mixed.n_chains):
+            assert H.emu_encode(mixed, c, b, perturb=perturb) == want.blob(c), (b, c)
+
+
+def test_float_first_path_on_tight_geometry():
+    """Arrays with a tiny range (every residue the same conformation: disc_f is huge, every value sits next to a bin
+    edge) and ideal helices: the undecided list overflows or the bounds cross, the chain takes the all-exact path,
+    bytes still equal the oracle's."""
+    from foldcomp_b200 import synth
+
+    base = synth.generate(1, 80, seed=12)
+    # repeat one residue pair's geometry: build by copying the oracle-decoded coordinates of a constant-angle chain is
+    # overkill -- scaling the chain towards a line (x *= 1e-3 in two axes) gives near-degenerate, tightly ranged angles
+    for scale in (1e-2, 1e-4):
+        b = synth.generate(1, 80, seed=13)
+        b.xyz = b.xyz.copy()
+        b.xyz[:, 1:] *= np.float32(scale)
+        for anchor in (25, 10):
+            o = H.oracle_encode(b, 0, anchor)
+            for pert in (False, True):
+                assert H.emu_encode(b, 0, anchor, perturb=pert) == o, (scale, anchor, pert)
 
 
 def test_decode_cossin_deg():

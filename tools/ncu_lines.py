@@ -42,7 +42,7 @@ srcs = {}
 for (f, l), n in agg.most_common(top):
     if f not in srcs:
         try:
-            srcs[f] = open("/root/repo/foldcomp_b200/csrc/" + f).read().splitlines()
+            srcs[f] = open(__import__("os").environ.get("SRCDIR", "/root/repo/foldcomp_b200/csrc/") + f).read().splitlines()
         except OSError:
             srcs[f] = []
     text = srcs[f][l - 1].strip()[:90] if 0 < l <= len(srcs[f]) else ""
