@@ -31,10 +31,11 @@ namespace fcz {
 // reference decodes it.  Encode INPUT codes must be < FCZ_NUM_CODES (the plans check).
 // (FCZ_CODE_ROWS and norm_code live in fcz_format.h.)
 struct Tables {
+    // (the encode kernel keeps a copy of the fields up to `alt` in shared memory: natoms, name1, pred)
     uint8_t natoms[FCZ_CODE_ROWS];
     uint8_t name1[FCZ_CODE_ROWS];  // one-letter codes (header firstResidue / lastResidue)
-    uint8_t alt[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];
     uint16_t pred[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];
+    uint8_t alt[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];
     // side-chain byte as a step function of cos(torsion) (see build_tables), both tables increasing:
     // non-negated torsion: byte = 127 + #{i: -c >= sc_pos[i]};  negated torsion: byte = #{i: c >= sc_neg[i]}
     float sc_pos[128];
@@ -129,10 +130,11 @@ inline void build_tables(Tables* t) {
 //   [FL_BAD]    != 0: degenerate geometry seen, the chain takes the exact path
 //   [FL_BND+4a .. +3]  array a (header order), as ordered ints: min and max over the items of (x - eps), min and max of (x + eps)
 //   [FL_EX+2a, +1]     exact min / max over the re-evaluated items of array a (a = 6: the B-factors)
-//   [FL_DER+6a .. +5]  floats derived from the bounds for pass B: mU, mL, ML, f_lo, f_hi, unused
 // The list of undecided values (EncChain::list, value index a * L + r) and their exact values (EncChain::xe) hold
 // list_cap entries each: about 3 % of a chain's 6 (L-1) values end up there, enc_list_cap leaves a factor ~1.5.
-enum { FL_N = 0, FL_BAD = 1, FL_BND = 2, FL_EX = 26, FL_DER = 40, FCZ_FL_WORDS = 76 };
+// Both may alias EncChain::sres, which is dead once phase 2 is over (the list is first touched after the barrier
+// that ends phase 3).
+enum { FL_N = 0, FL_BAD = 1, FL_BND = 2, FL_EX = 26, FCZ_FL_WORDS = 40 };
 FCZ_HD uint32_t enc_list_cap(uint32_t max_res) { return max_res <= 1024u ? 256u : (max_res + 3u) / 4u; }
 
 struct EncChain {
@@ -150,6 +152,7 @@ struct EncChain {
     float* ang;              // [6*L] the six backbone arrays, header order, stride L: angles, then (in place) their quantised values
     float* red;              // [FCZ_RED_FLOATS(nwarps)]
     uint32_t* fl;            // [FCZ_FL_WORDS]
+    const Tables* tbg;       // the complete tables (global memory): threshold tables of the exact side-chain path
     uint32_t* list;          // [list_cap] undecided values of the float-first path
     float* xe;               // [list_cap] their exact values
     uint32_t list_cap;
@@ -357,7 +360,7 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
         }
         if (r1 == L) ch.aoff[L] = base;
         // scratch of the float-first path: counters, bounds (ordered ints), exact extremes
-        for (uint32_t i = cx.tid; i < (uint32_t)FL_DER; i += cx.nthr) {
+        for (uint32_t i = cx.tid; i < (uint32_t)FCZ_FL_WORDS; i += cx.nthr) {
             uint32_t v = 0u;
             if (i >= (uint32_t)FL_BND && i < (uint32_t)FL_EX) {
                 const uint32_t w = (i - FL_BND) & 3u;  // min(x-eps), max(x-eps), min(x+eps), max(x+eps)
@@ -388,11 +391,12 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
             const f3 u1 = cross3(d1, d2), u2 = cross3(d2, d3);
             const f3 pb = cross3(u2, d2);  // torsion_angle.cpp:87-92
             const bool neg = (u1.x * pb.x) + (u1.y * pb.y) + (u1.z * pb.z) < 0;
-            B[y.o_sc + t] = sc_byte_fast(tb, dot_parts(u1, u2), neg);
+            B[y.o_sc + t] = sc_byte_fast(ch.tbg, dot_parts(u1, u2), neg);
         }
     }
     cx.mark(1);  // E_SIDE (no barrier: timing only)
 
+#if !defined(FCZ_ENC_BACKBONE_PAIR)  // (FCZ_ENC_BACKBONE_PAIR: experiment build with one item per residue pair, libfcz_engine_pair.so)
     // ---- phase 3: backbone, float first.  One item = residue pair (r, r+1) and k in {0,1,2}: the torsion over the four
     // backbone atoms 3r+k .. 3r+k+3 (psi, omega, phi of record r: src/torsion_angle.cpp:49-94, src/foldcomp.cpp:488-492)
     // AND the bond angle at the third of them (CA-C-N, C-N-CA, N-CA-C of record r: src/nerf.cpp:495-508,
@@ -439,6 +443,72 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
                 }
             }
         }
+#else
+    // ---- phase 3: backbone, float first.  One item = one residue pair (r, r+1): the three torsions over its six
+    // backbone atoms (psi, omega, phi of record r: src/torsion_angle.cpp:49-94, src/foldcomp.cpp:488-492) and the three bond
+    // angles at C, N', CA' (CA-C-N, C-N-CA, N-CA-C of record r: src/nerf.cpp:495-508, src/foldcomp.cpp:496-505) share five
+    // bond vectors and four cross products.  Every value is stored as a float estimate x (ang_fast); per array the
+    // extremes of x - eps and x + eps are gathered (warp reduction on ordered integers, then shared-memory atomics).
+    {
+        uint32_t bad = 0;
+        for (uint32_t r0 = 0; r0 + 1u < L; r0 += (uint32_t)cx.nthr) {
+            const uint32_t r = r0 + (uint32_t)cx.tid;
+            const bool on = r + 1u < L;
+            float x[6];  // header order: phi psi omega N-CA-C CA-C-N C-N-CA
+            if (on) {
+                const uint32_t a0 = ch.aoff[r], a1 = ch.aoff[r + 1u];
+                const f3 n0 = ld3(ch.X + 3u * a0), ca0 = ld3(ch.X + 3u * a0 + 3u), c0 = ld3(ch.X + 3u * a0 + 6u);
+                const f3 n1 = ld3(ch.X + 3u * a1), ca1 = ld3(ch.X + 3u * a1 + 3u), c1 = ld3(ch.X + 3u * a1 + 6u);
+                const f3 d0 = sub3(ca0, n0), d1 = sub3(c0, ca0), d2 = sub3(n1, c0), d3 = sub3(ca1, n1), d4 = sub3(c1, ca1);
+                const f3 c01 = cross3(d0, d1), c12 = cross3(d1, d2), c23 = cross3(d2, d3), c34 = cross3(d3, d4);
+                const float s01 = c01.x * c01.x + c01.y * c01.y + c01.z * c01.z, s12 = c12.x * c12.x + c12.y * c12.y + c12.z * c12.z;
+                const float s23 = c23.x * c23.x + c23.y * c23.y + c23.z * c23.z, s34 = c34.x * c34.x + c34.y * c34.y + c34.z * c34.z;
+                DotParts dp;
+                {   // psi: atoms N CA C N'
+                    const f3 pb = cross3(c12, d1);
+                    const bool neg = (c01.x * pb.x) + (c01.y * pb.y) + (c01.z * pb.z) < 0;
+                    dp.inner = (c01.x * c12.x) + (c01.y * c12.y) + (c01.z * c12.z); dp.p = s01 * s12;
+                    x[A_PSI] = ang_fast(dp, true, neg, bad);
+                }
+                {   // omega: atoms CA C N' CA'
+                    const f3 pb = cross3(c23, d2);
+                    const bool neg = (c12.x * pb.x) + (c12.y * pb.y) + (c12.z * pb.z) < 0;
+                    dp.inner = (c12.x * c23.x) + (c12.y * c23.y) + (c12.z * c23.z); dp.p = s12 * s23;
+                    x[A_OMEGA] = ang_fast(dp, true, neg, bad);
+                }
+                {   // phi: atoms C N' CA' C'
+                    const f3 pb = cross3(c34, d3);
+                    const bool neg = (c23.x * pb.x) + (c23.y * pb.y) + (c23.z * pb.z) < 0;
+                    dp.inner = (c23.x * c34.x) + (c23.y * c34.y) + (c23.z * c34.z); dp.p = s23 * s34;
+                    x[A_PHI] = ang_fast(dp, true, neg, bad);
+                }
+                // bond angle at atom b between a - b and c - b, i.e. between -d and d': negation is exact, so the
+                // reference's products and sums (src/float3d.h:36-43) are these with the sign flipped
+                const float q1 = d1.x * d1.x + d1.y * d1.y + d1.z * d1.z, q2 = d2.x * d2.x + d2.y * d2.y + d2.z * d2.z;
+                const float q3 = d3.x * d3.x + d3.y * d3.y + d3.z * d3.z, q4 = d4.x * d4.x + d4.y * d4.y + d4.z * d4.z;
+                dp.inner = -((d1.x * d2.x) + (d1.y * d2.y) + (d1.z * d2.z)); dp.p = q1 * q2;
+                x[A_CACN] = ang_fast(dp, false, false, bad);
+                dp.inner = -((d2.x * d3.x) + (d2.y * d3.y) + (d2.z * d3.z)); dp.p = q2 * q3;
+                x[A_CNCA] = ang_fast(dp, false, false, bad);
+                dp.inner = -((d3.x * d4.x) + (d3.y * d4.y) + (d3.z * d4.z)); dp.p = q3 * q4;
+                x[A_NCAC] = ang_fast(dp, false, false, bad);
+                for (int a = 0; a < 6; a++) ch.ang[a * L + r] = x[a];
+            }
+            for (int a = 0; a < 6; a++) {
+                float lo = INFINITY, hi = -INFINITY;  // an idle lane changes no extreme
+                float lo2 = -INFINITY, hi2 = INFINITY;
+                if (on) {
+                    const float e = ang_eps(x[a]);
+                    lo = x[a] - e; hi = x[a] + e; lo2 = lo; hi2 = hi;
+                }
+                const int32_t v0 = cx.wmin_i(ford(lo)), v1 = cx.wmax_i(ford(lo2)), v2 = cx.wmin_i(ford(hi2)), v3 = cx.wmax_i(ford(hi));
+                if (cx.lane == 0) {
+                    int32_t* dst = fli + FL_BND + 4 * a;
+                    cx.atomic_min_i(dst, v0); cx.atomic_max_i(dst + 1, v1); cx.atomic_min_i(dst + 2, v2); cx.atomic_max_i(dst + 3, v3);
+                }
+            }
+        }
+#endif
         if (bad) fl[FL_BAD] = 1u;
         // B-factors: exact extremes (they are input)
         {
@@ -456,59 +526,54 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
         }
     }
     cx.sync();
-    cx.mark(2);
+    cx.mark(2);  // E_BACKBONE
 
     float* prm = ch.red + cx.nwarps * 14 + 14;  // [21] (min, disc_f, cont_f) x 7
     if (cx.tid == 6 % cx.nthr) enc_params(ch, 6, funord(fli[FL_EX + 12]), funord(fli[FL_EX + 13]), ch.bfac[0], prm + 18);
     bool exact_path = fl[FL_BAD] != 0u;
     if (!exact_path) {
-        // ---- phase 4a: what pass B needs of the bounds, per array.  The true min lies in [mL, mU] = [min(x-eps), min(x+eps)],
-        // the true max in [ML, MU]; disc_f = RN(nb / RN(max - min)) is monotone in both, so IEEE float operations on
-        // the interval ends bracket it without any slop.
-        for (int a = cx.tid; a < 6; a += cx.nthr) {
-            const float mL = funord(fli[FL_BND + 4 * a]), ML = funord(fli[FL_BND + 4 * a + 1]);
-            const float mU = funord(fli[FL_BND + 4 * a + 2]), MU = funord(fli[FL_BND + 4 * a + 3]);
-            const float nb = (float)n_bins(a);
-            float* d = flf + FL_DER + 6 * a;
-            d[0] = mU; d[1] = mL; d[2] = ML;
-            d[3] = nb / (MU - mL);  // f_lo
-            d[4] = nb / (ML - mU);  // f_hi (inf / negative / NaN when the bounds cross: then every item is undecided)
-        }
-        cx.sync();
-        // ---- phase 4b: decide every value from its estimate.  x in [x-eps, x+eps], min in [mL, mU], f in [f_lo, f_hi]:
-        // RN(x - min) * f is bracketed by t_lo = RN(RN(lo - mU) * f_lo) and t_hi = RN(RN(hi - mL) * f_hi) (monotone IEEE
-        // operations on non-negative values).  Same rounded integer at both ends and no chance of being the array's
-        // min or max: that integer is the reference's; otherwise the value goes on the list.
+        // ---- phase 4a: decide every value from its estimate.  The true min of an array lies in [mL, mU] = [min(x-eps),
+        // min(x+eps)], its max in [ML, MU]; disc_f = RN(nb / RN(max - min)) is monotone in both, so it lies between
+        // f_lo <= RN(nb / RN(MU - mL)) and f_hi >= RN(nb / RN(ML - mU)) -- taken from ONE MUFU.RCP each, widened by 1e-6
+        // (rcp_ is good to 2 ulp, the product to half an ulp; every thread derives them itself: no extra pass).
+        // x in [x-eps, x+eps]: RN(x - min) * disc_f is bracketed by t_lo = RN(RN(lo - mU) * f_lo) and
+        // t_hi = RN(RN(hi - mL) * f_hi) (monotone IEEE operations on non-negative values).  Same rounded integer at both
+        // ends and no chance of being the array's min or max: that integer is the reference's; otherwise the value
+        // goes on the list.  (Crossed bounds give a negative or infinite f_hi: nothing is decided, the list overflows.)
         {
-            const uint32_t W = (uint32_t)cx.wsize, Lp = (L - 1u + W - 1u) / W * W;
             uint32_t* q = reinterpret_cast<uint32_t*>(ch.ang);
-            for (uint32_t v = cx.tid; v < 6u * Lp; v += cx.nthr) {
-                const uint32_t a = v / Lp, r = v - a * Lp;
-                if (r + 1u >= L) continue;
-                const float* d = flf + FL_DER + 6 * a;
-                const float x = ch.ang[a * L + r];
-                const float e = ang_eps(x);
-                const float lo = x - e, hi = x + e;
-                const float t_lo = (lo - d[0]) * d[3], t_hi = (hi - d[1]) * d[4];
-                uint32_t q_lo = 0u;
-                bool decided = false;
-                if (lo > d[0] && hi < d[2] && t_lo >= 0.0f && t_hi < 65536.0f) {
-                    q_lo = round_half_up(t_lo);
-                    decided = q_lo == round_half_up(t_hi);
-                }
-                if (decided) {
-                    q[a * L + r] = q_lo;
-                } else {
-                    const uint32_t j = cx.atomic_add(&fl[FL_N], 1u);
-                    if (j < ch.list_cap) ch.list[j] = a * L + r;
+            const uint32_t n1 = L - 1u;
+            for (uint32_t a = 0; a < 6u; a++) {
+                const float mL = funord(fli[FL_BND + 4 * a]), ML = funord(fli[FL_BND + 4 * a + 1]);
+                const float mU = funord(fli[FL_BND + 4 * a + 2]), MU = funord(fli[FL_BND + 4 * a + 3]);
+                const float nb = (float)n_bins((int)a);
+                const float f_lo = (nb * rcp_(MU - mL)) * (1.0f - 1e-6f), f_hi = (nb * rcp_(ML - mU)) * (1.0f + 1e-6f);
+                for (uint32_t r = cx.tid; r < n1; r += cx.nthr) {
+                    const float x = ch.ang[a * L + r];
+                    const float e = ang_eps(x);
+                    const float lo = x - e, hi = x + e;
+                    const float t_lo = (lo - mU) * f_lo, t_hi = (hi - mL) * f_hi;
+                    uint32_t q_lo = 0u;
+                    bool decided = false;
+                    if (lo > mU && hi < ML && t_lo >= 0.0f && t_hi < 65536.0f) {
+                        q_lo = round_half_up(t_lo);
+                        decided = q_lo == round_half_up(t_hi);
+                    }
+                    if (decided) {
+                        q[a * L + r] = q_lo;
+                    } else {
+                        const uint32_t j = cx.atomic_add(&fl[FL_N], 1u);
+                        if (j < ch.list_cap) ch.list[j] = a * L + r;
+                    }
                 }
             }
         }
         cx.sync();
+        cx.mark(5);  // E_DECIDE
         exact_path = fl[FL_N] > ch.list_cap;
     }
     if (!exact_path) {
-        // ---- phase 4c: the undecided values by the reference's exact sequence; their extremes are the arrays' extremes
+        // ---- phase 4b: the undecided values by the reference's exact sequence; their extremes are the arrays' extremes
         const uint32_t n = fl[FL_N];
         for (uint32_t j = cx.tid; j < n; j += cx.nthr) {
             const uint32_t v = ch.list[j], a = v / L, r = v - a * L;
@@ -522,26 +587,33 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
             }
         }
         cx.sync();
+        cx.mark(6);  // E_LIST
         exact_path = fl[FL_BAD] != 0u;
     }
     if (!exact_path) {
-        for (int a = cx.tid; a < 6; a += cx.nthr) {
-            const float lo = funord(fli[FL_EX + 2 * a]), hi = funord(fli[FL_EX + 2 * a + 1]);
-            enc_params(ch, a, lo, hi, lo, prm + 3 * a);  // no NaN on this path: the first element plays no role
-        }
-        cx.sync();
+        // ---- phase 4c: the discretiser parameters from the exact extremes (no NaN on this path: the first element plays no
+        // role), by every thread that needs them -- the list's threads for their value, thread 0 for the header
         const uint32_t n = fl[FL_N];
         uint32_t* q = reinterpret_cast<uint32_t*>(ch.ang);
         for (uint32_t j = cx.tid; j < n; j += cx.nthr) {
             const uint32_t v = ch.list[j], a = v / L;
-            q[v] = disc_round(ch.xe[j], prm[3 * a], prm[3 * a + 1]);
+            const float lo = funord(fli[FL_EX + 2 * a]), hi = funord(fli[FL_EX + 2 * a + 1]);
+            float pa[3];
+            enc_params(ch, (int)a, lo, hi, lo, pa);
+            q[v] = disc_round(ch.xe[j], pa[0], pa[1]);
+        }
+        if (cx.tid == 0) {
+            for (int a = 0; a < 6; a++) {
+                const float lo = funord(fli[FL_EX + 2 * a]), hi = funord(fli[FL_EX + 2 * a + 1]);
+                enc_params(ch, a, lo, hi, lo, prm + 3 * a);
+            }
         }
     } else {
         cx.sync();  // (phase-4 scratch reads above are done)
         enc_backbone_exact(cx, ch);
     }
     cx.sync();
-    cx.mark(2);  // E_MINMAX
+    cx.mark(7);  // E_QUANT
 
     // ---- phase 5: serialise (src/foldcomp.cpp:1038-1109)
     if (cx.tid == 0) {

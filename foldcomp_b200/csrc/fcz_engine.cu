@@ -49,30 +49,34 @@ struct TierCfg {
 // residues) its workspace as well.
 // Caps are chosen at the occupancy steps of the per-residue shared-memory footprint (encode ~172 B/residue,
 // 350-residue chains run 3 CTAs/SM).  Decode has its own four length tiers (dec_tier_of, below).
-static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 296, 408, 632, 1280, 2720, 65535};
+static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 256, 384, 640, 1280, 2720, 65535};
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 // ---- shared memory carve-up (offsets are computed identically on host and device)
 struct EncSmem {
-    uint32_t o_tab, o_misc, o_red, o_fl, o_list, o_type, o_aoff, o_ares, o_ang, o_x, o_b, total;
+    uint32_t o_tab, o_misc, o_red, o_fl, o_type, o_aoff, o_ares, o_ang, o_x, o_b, total;
 };
 __host__ __device__ inline EncSmem enc_smem(const TierCfg& t) {
     EncSmem s;
     uint32_t o = 0;
-    s.o_tab = o;  o += align16((uint32_t)offsetof(Tables, blen));
+    s.o_tab = o;  o += align16((uint32_t)offsetof(Tables, alt));  // natoms, name1, pred
     s.o_misc = o; o += 256;  // mbarrier, ticket, warp sums
-    s.o_red = o;  o += align16(4u * FCZ_RED_FLOATS(32));
+    s.o_red = o;  o += align16(4u * FCZ_RED_FLOATS(24));  // blocks have at most 768 threads
     s.o_fl = o;   o += align16(4u * FCZ_FL_WORDS);
-    s.o_list = o; o += t.gws ? 0u : align16(8u * enc_list_cap(t.max_res));  // undecided values + their exact values
     s.o_type = o; o += t.staged ? align16(t.max_res) : 0u;
     s.o_aoff = o; o += t.gws ? 0u : align16(4u * (t.max_res + 1u));
-    s.o_ares = o; o += t.gws ? 0u : align16(2u * t.max_atoms);
+    s.o_ares = o; o += t.gws ? 0u : align16(2u * t.max_atoms);  // side-chain atom -> residue; later the undecided-value list (enc_tier_list_cap)
     s.o_ang = o;  o += t.gws ? 0u : align16(24u * t.max_res);
     s.o_x = o;    o += t.stage_x ? align16(12u * t.max_atoms) + 32u : 0u;
     s.o_b = o;    o += t.staged ? align16(t.max_blob) + 32u : 0u;
     s.total = o;
     return s;
+}
+// entries of the undecided-value list + exact values (8 bytes each) that fit the side-chain map they alias
+__host__ __device__ inline uint32_t enc_tier_list_cap(const TierCfg& t) {
+    const uint32_t fit = align16(2u * t.max_atoms) / 8u, want = enc_list_cap(t.max_res);
+    return want < fit ? want : fit;
 }
 static TierCfg make_tier(uint32_t max_res, bool staged, bool gws) {
     TierCfg t;
@@ -367,16 +371,19 @@ __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.tables);
         uint32_t* dst = reinterpret_cast<uint32_t*>(tb);
-        for (uint32_t i = cx.tid; i < (uint32_t)offsetof(Tables, blen) / 4u; i += cx.nthr) dst[i] = src[i];
+        for (uint32_t i = cx.tid; i < (uint32_t)offsetof(Tables, alt) / 4u; i += cx.nthr) dst[i] = src[i];
     }
     if (cx.tid == 0) mbar_init(bar, 1);
     __syncthreads();
     const uint32_t count = a.count ? *a.count : a.count_val;
-    for (;;) {
-        if (cx.tid == 0) *s_ticket = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const uint32_t t = *s_ticket;
-        if (t >= count) break;
+    // Tickets run one chain ahead: while chain t is encoded, thread 0 already holds the ticket of the block's next chain
+    // (slots alternate, so a slot is rewritten two barriers after its last reader), and the next chain's coordinates
+    // are pulled towards L2 -- the bulk copy (or the first loads) of the next trip then find them there.
+    if (cx.tid == 0) s_ticket[0] = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    uint32_t t = s_ticket[0];
+    for (uint32_t trip = 0; t < count; trip++) {
+        if (cx.tid == 0) s_ticket[(trip + 1u) & 1u] = atomicAdd(a.ticket, 1u);
 #ifdef FCZ_PHASE_TIMING
         cx.t_last = clock64();
 #endif
@@ -398,9 +405,10 @@ __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
         ch.ang = reinterpret_cast<float*>(smem + so.o_ang);
         ch.red = reinterpret_cast<float*>(smem + so.o_red);
         ch.fl = reinterpret_cast<uint32_t*>(smem + so.o_fl);
-        ch.list_cap = enc_list_cap(a.cfg.max_res);
-        ch.list = reinterpret_cast<uint32_t*>(smem + so.o_list);
-        ch.xe = reinterpret_cast<float*>(smem + so.o_list) + ch.list_cap;
+        ch.tbg = a.tables;
+        ch.list_cap = enc_tier_list_cap(a.cfg);
+        ch.list = reinterpret_cast<uint32_t*>(smem + so.o_ares);
+        ch.xe = reinterpret_cast<float*>(smem + so.o_ares) + ch.list_cap;
         uint8_t* gdst = a.bytes + b0;
         uint8_t* sB = nullptr;
         if (a.cfg.staged) {
@@ -408,10 +416,13 @@ __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
                 const uint8_t* gx = reinterpret_cast<const uint8_t*>(a.xyz + 3u * a0);
                 ch.X = reinterpret_cast<const float*>(stage_in(cx, smem + so.o_x, gx, 12u * A));
             } else {
-                // coordinates stay in global memory: pull the chain towards L2 while phase 1 runs (one line per thread and trip)
+                // coordinates stay in global memory (L1 / L2): the block's first chain is pulled towards L2 here, every
+                // later one was prefetched a trip ahead (below)
                 ch.X = a.xyz + 3u * a0;
-                const char* gx = reinterpret_cast<const char*>(ch.X);
-                for (uint32_t off = cx.tid * 128u; off < 12u * A; off += cx.nthr * 128u) prefetch_l2(gx + off);
+                if (trip == 0u) {
+                    const char* gx = reinterpret_cast<const char*>(ch.X);
+                    for (uint32_t off = cx.tid * 128u; off < 12u * A; off += cx.nthr * 128u) prefetch_l2(gx + off);
+                }
                 cx.staged = false;
             }
             uint8_t* st = smem + so.o_type;
@@ -419,7 +430,22 @@ __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
             ch.type = st;
             sB = smem + so.o_b + ((uintptr_t)gdst & 15u);
             ch.B = sB;
-            __syncthreads();  // staged types visible before phase 1
+            __syncthreads();  // staged types (and the next ticket) visible before phase 1
+            {
+                const uint32_t tn = s_ticket[(trip + 1u) & 1u];
+                if (tn < count) {
+                    const uint32_t cn = a.list[tn];
+                    const uint64_t an = a.atom_off[cn];
+                    const uint32_t bytes = 12u * (uint32_t)(a.atom_off[cn + 1] - an);
+                    const char* gx = reinterpret_cast<const char*>(a.xyz + 3u * an);
+                    for (uint32_t off = cx.tid * 128u; off < bytes; off += cx.nthr * 128u) prefetch_l2(gx + off);
+                    if (cx.tid < 32u) {
+                        const uint32_t rn = a.res_off[cn], Ln = a.res_off[cn + 1] - rn;
+                        for (uint32_t off = cx.tid * 128u; off < Ln; off += 32u * 128u) prefetch_l2(a.res_type + rn + off);
+                        for (uint32_t off = cx.tid * 128u; off < 4u * Ln; off += 32u * 128u) prefetch_l2(reinterpret_cast<const char*>(a.bfactor + rn) + off);
+                    }
+                }
+            }
         } else {
             ch.X = a.xyz + 3u * a0;
             ch.type = a.res_type + r0;
@@ -434,16 +460,21 @@ __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
         __builtin_assume(__isShared(ch.fl));
         __builtin_assume(__isShared(ch.list));
         __builtin_assume(__isShared(ch.xe));
+        // Three instances of the codec, by the address space of the coordinates and of the blob.  The coordinate pointer
+        // of the global-memory instance is re-derived from the kernel parameter instead of being given an assumption (two
+        // different address-space assumptions on one SSA value leaked across the branches: LDG on a shared address).
         if (a.cfg.staged && a.cfg.stage_x) {
             __builtin_assume(__isShared(ch.X));
             __builtin_assume(__isShared(ch.type));
             __builtin_assume(__isShared(ch.B));
             encode_chain(cx, tb, ch);
         } else if (a.cfg.staged) {
-            __builtin_assume(__isGlobal(ch.X));
+#ifndef FCZ_ANALYSE_STAGED_ONLY
+            ch.X = a.xyz + 3u * a0;  // kernel parameter: known to be global memory
             __builtin_assume(__isShared(ch.type));
             __builtin_assume(__isShared(ch.B));
             encode_chain(cx, tb, ch);
+#endif
         } else {
 #ifndef FCZ_ANALYSE_STAGED_ONLY  // (tools/sass_static.py: count one copy of the codec)
             encode_chain(cx, tb, ch);
@@ -458,6 +489,7 @@ __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
             cx.staged = false;
         }
         __syncthreads();  // shared buffers free for the next chain
+        t = s_ticket[(trip + 1u) & 1u];
     }
 }
 
@@ -480,7 +512,7 @@ __global__ void __launch_bounds__(1024) k_encode_long(EncArgs a) {
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.tables);
         uint32_t* dst = reinterpret_cast<uint32_t*>(tb);
-        for (uint32_t i = cx.tid; i < (uint32_t)offsetof(Tables, blen) / 4u; i += cx.nthr) dst[i] = src[i];
+        for (uint32_t i = cx.tid; i < (uint32_t)offsetof(Tables, alt) / 4u; i += cx.nthr) dst[i] = src[i];
     }
     __syncthreads();
     uint8_t* ws = a.gws + (uint64_t)blockIdx.x * a.gws_stride;
@@ -505,6 +537,7 @@ __global__ void __launch_bounds__(1024) k_encode_long(EncArgs a) {
         ch.ang = reinterpret_cast<float*>(ws + align16(4u * (a.gws_max_res + 1u)) + align16(2u * (FCZ_MAX_ATOMS - 3u) * a.gws_max_res));
         ch.red = reinterpret_cast<float*>(smem + so.o_red);
         ch.fl = reinterpret_cast<uint32_t*>(smem + so.o_fl);
+        ch.tbg = a.tables;
         ch.list_cap = enc_list_cap(a.gws_max_res);
         ch.list = reinterpret_cast<uint32_t*>(ws + align16(4u * (a.gws_max_res + 1u)) + align16(2u * (FCZ_MAX_ATOMS - 3u) * a.gws_max_res) + align16(24u * a.gws_max_res));
         ch.xe = reinterpret_cast<float*>(ch.list) + ch.list_cap;
@@ -1409,8 +1442,12 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     make_tiers(e->enc_tier);
     // experiment knobs (A/B runs, tools/kernel_ab.py): FCZ_ENC_XGLOBAL=1 reads coordinates from global memory instead of staging
     // them (smaller footprint, more CTAs per SM); FCZ_ENC_THREADS fixes the block size of the staged tiers
-    if (const char* v = getenv("FCZ_ENC_XGLOBAL")) {
-        if (atoi(v)) for (int i = 0; i < FCZ_NTIER; i++) { e->enc_tier[i].stage_x = 0; e->enc_tier[i].smem = enc_smem(e->enc_tier[i]).total; }
+    {
+        // Coordinates are read from global memory by default: without the 12 bytes per atom of staging a 384-residue
+        // block needs 29 KB of shared memory instead of 71 KB, seven blocks share an SM instead of three, and the measured
+        // kernel time is lower (profiles/r02_*ab*.json); FCZ_ENC_XGLOBAL=0 restores the bulk-copy staging.
+        const char* v = getenv("FCZ_ENC_XGLOBAL");
+        if (!v || atoi(v)) for (int i = 0; i < FCZ_NTIER; i++) { e->enc_tier[i].stage_x = 0; e->enc_tier[i].smem = enc_smem(e->enc_tier[i]).total; }
     }
     bool ok = true;
     ok &= cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) == cudaSuccess;
@@ -1440,10 +1477,13 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
         int occ = 0;
         ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, 128, e->enc_tier[i].smem) == cudaSuccess;
         if (occ < 1) occ = 1;
-        uint32_t thr = (1024u / (uint32_t)occ) / 96u * 96u;  // whole triples of warps: phase 3's k is uniform over a warp
+        // block size: as many threads as the register file leaves each of the `occ` blocks (whole warps)
+        uint32_t lim = (FCZ_ENC_MAXREG <= 64 ? 1024u : 65536u / FCZ_ENC_MAXREG) / (uint32_t)occ;
+        uint32_t thr = lim & ~31u;
+        if (thr < 96u) thr = 96u;
         if (const char* v = getenv("FCZ_ENC_THREADS")) { const long q = atol(v); if (q >= 32 && e->enc_tier[i].staged) thr = (uint32_t)q; }
-        if (thr > 768u) thr = 768u;  // k_encode's launch bound
-        e->enc_tier[i].threads = thr < 96u ? 96u : thr;
+        if (thr > 768u) thr = 768u;
+        e->enc_tier[i].threads = thr < 64u ? 64u : thr;
         ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, (int)e->enc_tier[i].threads, e->enc_tier[i].smem) == cudaSuccess;
         e->enc_occ[i] = occ > 0 ? occ : 1;
         if (e->enc_tier[i].gws) { e->enc_tier[i].threads = 960u; e->enc_occ[i] = 1; }  // one wide block per SM walks a long chain

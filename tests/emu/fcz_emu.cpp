@@ -61,7 +61,7 @@ int64_t emu_encode_chain(const uint8_t* res_type, uint32_t L, const float* xyz, 
     ch.L = L; ch.A = A; ch.title_len = title_len; ch.b = b;
     ch.type = res_type; ch.bfac = bfac; ch.X = xyz; ch.title = title; ch.meta = meta; ch.B = out;
     ch.aoff = aoff.data(); ch.sres = ares.data(); ch.ang = ang.data(); ch.red = red.data(); ch.fl = fl.data();
-    ch.list = list.data(); ch.xe = xe.data(); ch.list_cap = enc_list_cap(L);
+    ch.list = list.data(); ch.xe = xe.data(); ch.list_cap = enc_list_cap(L); ch.tbg = tb;
     HostCtx cx;
     encode_chain(cx, tb, ch);
     g_last_list = fl[FL_N]; g_last_bad = fl[FL_BAD];
