@@ -278,6 +278,7 @@ struct EncArgs {
     int32_t b;
     TierCfg cfg;
     uint32_t term;        // 1: one NUL byte follows every blob (fcz_opts.terminate_blobs)
+    uint32_t prefetch_next;  // 1: pull the block's next chain towards L2 while the current one is encoded
     uint8_t* gws;         // k_encode_long: per-block workspace in global memory, gws_stride bytes each
     uint64_t gws_stride;
     uint32_t gws_max_res; // residues the workspace was sized for
@@ -419,7 +420,7 @@ __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
                 // coordinates stay in global memory (L1 / L2): the block's first chain is pulled towards L2 here, every
                 // later one was prefetched a trip ahead (below)
                 ch.X = a.xyz + 3u * a0;
-                if (trip == 0u) {
+                if (trip == 0u || !a.prefetch_next) {
                     const char* gx = reinterpret_cast<const char*>(ch.X);
                     for (uint32_t off = cx.tid * 128u; off < 12u * A; off += cx.nthr * 128u) prefetch_l2(gx + off);
                 }
@@ -433,7 +434,7 @@ __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
             __syncthreads();  // staged types (and the next ticket) visible before phase 1
             {
                 const uint32_t tn = s_ticket[(trip + 1u) & 1u];
-                if (tn < count) {
+                if (a.prefetch_next && tn < count) {
                     const uint32_t cn = a.list[tn];
                     const uint64_t an = a.atom_off[cn];
                     const uint32_t bytes = 12u * (uint32_t)(a.atom_off[cn + 1] - an);
@@ -517,6 +518,7 @@ __global__ void __launch_bounds__(1024) k_encode_long(EncArgs a) {
     __syncthreads();
     uint8_t* ws = a.gws + (uint64_t)blockIdx.x * a.gws_stride;
     const uint32_t count = a.count ? *a.count : a.count_val;
+    if (blockDim.x > 768u) __trap();  // FCZ_RED_FLOATS(24)
     for (;;) {
         if (cx.tid == 0) *s_ticket = atomicAdd(a.ticket, 1u);
         __syncthreads();
@@ -1332,6 +1334,8 @@ struct fcz_engine {
     int num_sms = 148;
     TierCfg enc_tier[FCZ_NTIER];
     int enc_occ[FCZ_NTIER];
+    uint32_t enc_prefetch_next = 0;  // FCZ_ENC_PREFETCH_NEXT=1: pull the next chain towards L2 a trip ahead (measured 4 % SLOWER on the headline batch)
+    uint32_t enc_pad = 0;            // FCZ_ENC_PAD_KB: extra dynamic shared memory per block, i.e. fewer blocks per SM (A/B)
     Tables* d_tables = nullptr;
     TextTables* d_text_tables = nullptr;
     // text emitter (fcz_pdb_text_plan -> fcz_pdb_text_batch)
@@ -1448,6 +1452,11 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
         // kernel time is lower (profiles/r02_*ab*.json); FCZ_ENC_XGLOBAL=0 restores the bulk-copy staging.
         const char* v = getenv("FCZ_ENC_XGLOBAL");
         if (!v || atoi(v)) for (int i = 0; i < FCZ_NTIER; i++) { e->enc_tier[i].stage_x = 0; e->enc_tier[i].smem = enc_smem(e->enc_tier[i]).total; }
+        if (const char* q = getenv("FCZ_ENC_PREFETCH_NEXT")) e->enc_prefetch_next = atoi(q) ? 1u : 0u;
+        if (const char* q = getenv("FCZ_ENC_PAD_KB")) {
+            e->enc_pad = (uint32_t)atoi(q) * 1024u;
+            for (int i = 0; i < FCZ_NTIER - 2; i++) if (e->enc_tier[i].smem + e->enc_pad <= 227u * 1024u) e->enc_tier[i].smem += e->enc_pad;
+        }
     }
     bool ok = true;
     ok &= cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) == cudaSuccess;
@@ -1486,7 +1495,7 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
         e->enc_tier[i].threads = thr < 64u ? 64u : thr;
         ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_encode, (int)e->enc_tier[i].threads, e->enc_tier[i].smem) == cudaSuccess;
         e->enc_occ[i] = occ > 0 ? occ : 1;
-        if (e->enc_tier[i].gws) { e->enc_tier[i].threads = 960u; e->enc_occ[i] = 1; }  // one wide block per SM walks a long chain
+        if (e->enc_tier[i].gws) { e->enc_tier[i].threads = 768u; e->enc_occ[i] = 1; }  // one wide block per SM walks a long chain (24 warps: FCZ_RED_FLOATS(24))
     }
     Tables h;
     build_tables(&h);
@@ -1687,6 +1696,7 @@ static int fetch_plan(fcz_engine* e) {
 static int launch_encode(fcz_engine* e, EncArgs& a, int tier, uint32_t cnt, uint32_t long_max_res, cudaStream_t st) {
     a.cfg = e->enc_tier[tier];
     a.gws = nullptr; a.gws_stride = 0; a.gws_max_res = 0;
+    a.prefetch_next = e->enc_prefetch_next;
     uint32_t grid = (uint32_t)(e->num_sms * e->enc_occ[tier]);
     if (grid > cnt) grid = cnt;
     ProfSpan pk(e, FCZ_PROF_K_ENCODE, st);
