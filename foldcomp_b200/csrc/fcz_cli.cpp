@@ -43,7 +43,8 @@ static int read_pdb(const std::string& path, std::vector<AtomCoordinate>& atoms)
 int main(int argc, char** argv) {
     if (argc < 4) {
         fprintf(stderr, "usage: fcz_cli compress [-b N] in.pdb out.fcz | decompress [-a] in.fcz out.pdb\n"
-                        "       fcz_cli compress-db [-b N] in_pdb_db out_fcz_db | decompress-db [-a] in_fcz_db out_pdb_db\n");
+                        "       fcz_cli compress-db [-b N] in_pdb_db out_fcz_db | decompress-db [-a] in_fcz_db out_pdb_db\n"
+                        "       fcz_cli compress-tar [-b N] in.pdb out.tar | extract-plddt | extract-fasta | check  in.fcz out.txt\n");
         return 2;
     }
     const std::string mode = argv[1];
@@ -86,6 +87,30 @@ int main(int argc, char** argv) {
             if (rc) { fprintf(stderr, "[Error] decompress: %s\n", fcz_strerror(rc)); return 1; }
             std::ofstream os(out, std::ios::binary);
             os.write(text.data(), (std::streamsize)text.size());
+        } else if (mode == "compress-tar") {  // one-member archive: Foldcomp::writeTar (src/main.cpp:518-523)
+            std::vector<AtomCoordinate> atoms;
+            int rc = read_pdb(in, atoms);
+            if (rc) { fprintf(stderr, "[Error] %s\n", rc == 2 ? "multiple chains" : "no atoms found"); return 1; }
+            std::string base = in.substr(in.find_last_of('/') == std::string::npos ? 0 : in.find_last_of('/') + 1);
+            base = base.substr(0, base.find_last_of('.'));
+            comp.strTitle = base;
+            comp.anchorThreshold = b;
+            if ((rc = comp.compress(atoms))) { fprintf(stderr, "[Error] compress: %s\n", fcz_strerror(rc)); return 1; }
+            std::ofstream os(out, std::ios::binary);
+            if (comp.writeTar(os, base + ".fcz") || FoldcompGpu::writeTarEnd(os)) return 1;
+        } else if (mode == "extract-plddt" || mode == "extract-fasta" || mode == "check") {
+            std::ifstream is(in, std::ios::binary);
+            if (!is || comp.read(is) != 0) { fprintf(stderr, "[Error] File is not a valid fcz file\n"); return 1; }
+            std::ofstream os(out, std::ios::binary);
+            if (mode == "check") {
+                const int v = comp.checkValidity();  // ValidityError class (src/foldcomp.h:59-67)
+                os << v << "\n";
+            } else {
+                std::string data;
+                const int rc = comp.extract(data, mode == "extract-fasta" ? 1 : 0, 1);
+                if (rc) { fprintf(stderr, "[Error] extract: %s\n", fcz_strerror(rc)); return 1; }
+                os << ">" << in << "\n" << data << "\n";  // Foldcomp::writeFASTALike (src/foldcomp.cpp:1223-1231)
+            }
         } else return 2;
     } catch (const std::exception& ex) {
         fprintf(stderr, "[Error] %s\n", ex.what());

@@ -208,9 +208,11 @@ static bool read_file(const std::string& path, std::string& out) {
     return true;
 }
 
-bool DbReader::open(const std::string& path) {
+bool DbReader::open(const std::string& path) { return open(path, path + ".index", true); }
+
+bool DbReader::open(const std::string& path, const std::string& index_path, bool with_data) {
     std::string idx;
-    if (!read_file(path + ".index", idx)) return false;
+    if (!read_file(index_path, idx)) return false;
     const char* p = idx.c_str();
     while (*p) {
         char* e;
@@ -230,18 +232,20 @@ bool DbReader::open(const std::string& path) {
         for (size_t i = 0; i < perm.size(); i++) { k2[i] = keys_[perm[i]]; o2[i] = offsets_[perm[i]]; l2[i] = lengths_[perm[i]]; }
         keys_.swap(k2); offsets_.swap(o2); lengths_.swap(l2);
     }
-    fd_ = ::open(path.c_str(), O_RDONLY);
-    if (fd_ < 0) return false;
-    struct stat st;
-    if (fstat(fd_, &st) != 0) return false;
-    bytes_ = (size_t)st.st_size;
-    if (bytes_) {
-        void* m = mmap(nullptr, bytes_, PROT_READ, MAP_PRIVATE, fd_, 0);
-        if (m == MAP_FAILED) return false;
-        base_ = (const char*)m;
+    if (with_data) {  // (without: index / lookup queries only, the reference's reader without DB_READER_USE_DATA)
+        fd_ = ::open(path.c_str(), O_RDONLY);
+        if (fd_ < 0) return false;
+        struct stat st;
+        if (fstat(fd_, &st) != 0) return false;
+        bytes_ = (size_t)st.st_size;
+        if (bytes_) {
+            void* m = mmap(nullptr, bytes_, PROT_READ, MAP_PRIVATE, fd_, 0);
+            if (m == MAP_FAILED) return false;
+            base_ = (const char*)m;
+        }
+        for (size_t i = 0; i < keys_.size(); i++)  // no sum: offset + length of a malformed row may wrap
+            if (lengths_[i] > bytes_ || offsets_[i] > bytes_ - lengths_[i]) return false;
     }
-    for (size_t i = 0; i < keys_.size(); i++)  // no sum: offset + length of a malformed row may wrap
-        if (lengths_[i] > bytes_ || offsets_[i] > bytes_ - lengths_[i]) return false;
     std::string lk;
     if (read_file(path + ".lookup", lk)) {
         names_.assign(keys_.size(), std::string());
@@ -279,8 +283,11 @@ std::string DbReader::name(size_t i) const {
 
 // ------------------------------------------------------------------------------------------ writer
 
-bool DbWriter::open(const std::string& path) {
+bool DbWriter::open(const std::string& path) { return open(path, path + ".index"); }
+
+bool DbWriter::open(const std::string& path, const std::string& index_path) {
     path_ = path;
+    index_path_ = index_path;
     data_ = fopen(path.c_str(), "wb");
     if (!data_) return false;
     FILE* t = fopen((path + ".dbtype").c_str(), "wb");
@@ -303,12 +310,21 @@ bool DbWriter::append(const char* data, size_t len, uint32_t key, const std::str
     return true;
 }
 
+bool DbWriter::appendRaw(const char* data, size_t len, uint32_t key, const std::string& name) {
+    if (!data_) return false;
+    if (len && fwrite(data, 1, len, data_) != len) return false;
+    names_.push_back(name);
+    entries_.push_back({key, pos_, (uint64_t)len, names_.size() - 1});
+    pos_ += len;
+    return true;
+}
+
 bool DbWriter::close() {
     if (!data_) return true;
     bool ok = fclose(data_) == 0;  // a full disk shows up here at the latest: never report a truncated database as written
     data_ = nullptr;
     std::stable_sort(entries_.begin(), entries_.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
-    FILE* idx = fopen((path_ + ".index").c_str(), "w");
+    FILE* idx = fopen(index_path_.c_str(), "w");
     FILE* lk = fopen((path_ + ".lookup").c_str(), "w");
     if (!idx || !lk) {
         if (idx) fclose(idx);
@@ -507,4 +523,68 @@ extern "C" int fczgpu_db_copy(const char* in_db, const char* out_db) {
     for (size_t i = 0; i < rd.size(); i++)
         if (!wr.append(rd.data(i), rd.payload(i), rd.key(i), rd.name(i))) return FCZ_E_ARG;
     return wr.close() ? (int)rd.size() : FCZ_E_ARG;
+}
+
+// ------------------------------------------------------------------ the reference's C-style database handles
+// src/database_reader.h:11-27 / src/database_writer.h:12-15 over DbReader / DbWriter (C++ linkage, like the reference's).
+namespace {
+struct ReaderHandle {
+    fczgpu::DbReader rd;
+    std::vector<std::pair<std::string, uint32_t>> by_name;  // sorted by name
+    bool lookup = false;
+};
+}  // namespace
+
+void* make_reader(const char* data_name, const char* index_name, int32_t data_mode) {
+    if (!data_name || !index_name) return nullptr;
+    ReaderHandle* h = new ReaderHandle;
+    if (!h->rd.open(data_name, index_name, (data_mode & 1) != 0)) { delete h; return nullptr; }
+    h->lookup = (data_mode & (4 | 8)) != 0 && h->rd.hasLookup();
+    if (h->lookup) {
+        for (size_t i = 0; i < h->rd.size(); i++) h->by_name.emplace_back(h->rd.name(i), h->rd.key(i));
+        std::sort(h->by_name.begin(), h->by_name.end());
+    }
+    return h;
+}
+void free_reader(void* r) { delete (ReaderHandle*)r; }
+int64_t reader_get_size(void* r) { return r ? (int64_t)((ReaderHandle*)r)->rd.size() : -1; }
+int64_t reader_get_id(void* r, uint32_t key) {
+    if (!r) return -1;
+    const fczgpu::DbReader& rd = ((ReaderHandle*)r)->rd;
+    size_t lo = 0, hi = rd.size();
+    while (lo < hi) { const size_t mid = (lo + hi) / 2; if (rd.key(mid) < key) lo = mid + 1; else hi = mid; }
+    return (lo < rd.size() && rd.key(lo) == key) ? (int64_t)lo : -1;
+}
+static bool in_range(void* r, int64_t id) { return r && id >= 0 && id < (int64_t)((ReaderHandle*)r)->rd.size(); }
+const char* reader_get_data(void* r, int64_t id) { return in_range(r, id) && ((ReaderHandle*)r)->rd.hasData() ? ((ReaderHandle*)r)->rd.data((size_t)id) : nullptr; }
+uint32_t reader_get_key(void* r, int64_t id) { return in_range(r, id) ? ((ReaderHandle*)r)->rd.key((size_t)id) : UINT32_MAX; }
+int64_t reader_get_length(void* r, int64_t id) { return in_range(r, id) ? (int64_t)((ReaderHandle*)r)->rd.length((size_t)id) : -1; }
+int64_t reader_get_offset(void* r, int64_t id) { return in_range(r, id) ? (int64_t)((ReaderHandle*)r)->rd.offset((size_t)id) : -1; }
+uint32_t reader_lookup_entry(void* r, const char* name) {
+    ReaderHandle* h = (ReaderHandle*)r;
+    if (!h || !h->lookup || !name) return UINT32_MAX;
+    const std::string n(name);
+    auto it = std::lower_bound(h->by_name.begin(), h->by_name.end(), n, [](const std::pair<std::string, uint32_t>& a, const std::string& b) { return a.first < b; });
+    return (it != h->by_name.end() && it->first == n) ? it->second : UINT32_MAX;
+}
+const char* reader_lookup_name_alloc(void* r, uint32_t key) {
+    ReaderHandle* h = (ReaderHandle*)r;
+    if (!h || !h->lookup) return "";
+    const int64_t id = reader_get_id(r, key);
+    if (id < 0) return "";
+    return strdup(h->rd.name((size_t)id).c_str());
+}
+void* make_writer(const char* data_name, const char* index_name) {
+    if (!data_name || !index_name) return nullptr;
+    fczgpu::DbWriter* w = new fczgpu::DbWriter;
+    if (!w->open(data_name, index_name)) { delete w; return nullptr; }
+    return w;
+}
+void free_writer(void* w) {
+    if (!w) return;
+    ((fczgpu::DbWriter*)w)->close();
+    delete (fczgpu::DbWriter*)w;
+}
+bool writer_append(void* w, const char* data, size_t length, uint32_t key, const char* name) {
+    return w && ((fczgpu::DbWriter*)w)->appendRaw(data, length, key, name ? name : "");
 }

@@ -39,6 +39,10 @@ public:
     // data file `path`, index `path`.index, names from `path`.lookup when present; entries are ordered by key like the
     // reference's reader (src/database_reader.cpp:109).  Returns false on error.
     bool open(const std::string& path);
+    // explicit index file; with_data = false maps no data file (index / lookup queries only)
+    bool open(const std::string& path, const std::string& index_path, bool with_data);
+    bool hasLookup() const { return !names_.empty(); }
+    bool hasData() const { return base_ != nullptr; }
     size_t size() const { return keys_.size(); }
     uint32_t key(size_t i) const { return keys_[i]; }
     const char* data(size_t i) const { return base_ + offsets_[i]; }
@@ -62,14 +66,17 @@ public:
     DbWriter() = default;
     ~DbWriter() { close(); }
     bool open(const std::string& path);
+    bool open(const std::string& path, const std::string& index_path);
     // appends data + a NUL terminator; the index records length + 1
     bool append(const char* data, size_t len, uint32_t key, const std::string& name);
+    // appends data as it is (the reference's writer_append: its callers put the NUL into the data themselves)
+    bool appendRaw(const char* data, size_t len, uint32_t key, const std::string& name);
     bool close();  // writes .index / .lookup sorted by key (stable)
 
 private:
     struct Entry { uint32_t key; uint64_t offset, length; size_t name; };
     FILE* data_ = nullptr;
-    std::string path_;
+    std::string path_, index_path_;
     uint64_t pos_ = 0;
     std::vector<Entry> entries_;
     std::vector<std::string> names_;
@@ -87,6 +94,25 @@ int decompressDb(Engine& eng, const std::string& in_db, const std::string& out_d
 int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db, int anchorThreshold, DbStats* stats);
 
 }  // namespace fczgpu
+
+// The reference's C-style database handles (src/database_reader.h:11-27, src/database_writer.h:12-15), same names,
+// signatures and return conventions, over DbReader / DbWriter: foldcomp/foldcomp.cxx:333-435 (FoldcompDatabase) and
+// src/main.cpp (--db output, DatabaseProcessor input) bind to them unchanged.  `data_mode` bits as in the reference:
+// 1 map the data file, 2 index cache (accepted, ignored: the index is parsed every time), 4 / 8 read the .lookup file.
+// Not thread-safe, like the reference's (its callers wrap them in `omp critical`).
+void* make_reader(const char* data_name, const char* index_name, int32_t data_mode);
+void free_reader(void* reader);
+int64_t reader_get_id(void* reader, uint32_t key);       // position in the key-sorted index, -1 when absent
+const char* reader_get_data(void* reader, int64_t id);   // NULL when out of range
+uint32_t reader_get_key(void* reader, int64_t id);
+int64_t reader_get_length(void* reader, int64_t id);     // as in the index (includes a trailing NUL)
+int64_t reader_get_offset(void* reader, int64_t id);
+int64_t reader_get_size(void* reader);
+uint32_t reader_lookup_entry(void* reader, const char* name);          // key of a name, UINT32_MAX when absent
+const char* reader_lookup_name_alloc(void* reader, uint32_t key);      // strdup'ed name (caller frees), "" when absent
+void* make_writer(const char* data_name, const char* index_name);
+void free_writer(void* writer);                                        // sorts by key (stable), writes index + lookup
+bool writer_append(void* writer, const char* data, size_t length, uint32_t key, const char* name);
 
 // C entry points over the above for bindings and tests (ctypes)
 extern "C" {

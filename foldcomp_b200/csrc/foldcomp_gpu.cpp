@@ -1,7 +1,9 @@
 // foldcomp_b200/csrc/foldcomp_gpu.cpp -- see foldcomp_gpu.h.  Host-side data marshalling only.
 #include "foldcomp_gpu.h"
 
+#include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <istream>
 #include <iterator>
 #include <ostream>
@@ -230,6 +232,67 @@ int FoldcompGpu::decompress(std::vector<AtomCoordinate>& atoms) {
     to_atoms(ch[0], useAltAtomOrder, atoms);
     nAtom = (int)atoms.size();
     return 0;
+}
+
+int FoldcompGpu::write(const std::string& filename) const {  // Foldcomp::write, src/foldcomp.cpp:1111-1119
+    std::ofstream out(filename, std::ios::out | std::ios::binary);
+    if (!out) return -1;
+    return writeStream(out);
+}
+
+// Foldcomp::writeTar (src/foldcomp.cpp:1122-1187) appends the entry to an open microtar archive; here the same record
+// goes to a stream: the 512-byte header exactly as mtar_write_file_header + mtar_write_header build it
+// (lib/microtar/microtar.c:186-220: name, mode 644, owner 0, size and mtime in unpadded octal, type '0', checksum
+// "%06o" NUL ' '), the blob, zero padding to a 512-byte boundary.  writeTarEnd writes the two closing zero records
+// (mtar_finalize).
+int FoldcompGpu::writeTar(std::ostream& tar, const std::string& filename) const {
+    char h[512];
+    memset(h, 0, sizeof h);
+    if (filename.size() >= 100) return -1;
+    memcpy(h, filename.c_str(), filename.size());
+    snprintf(h + 100, 8, "%o", 0644u);
+    snprintf(h + 108, 8, "%o", 0u);
+    snprintf(h + 116, 12, "%o", (unsigned)blob_.size());
+    snprintf(h + 128, 12, "%o", 0u);
+    h[148 + 8] = '0';  // type, right after the 8-byte checksum field at offset 148
+    unsigned sum = 256;
+    for (int i = 0; i < 148; i++) sum += (unsigned char)h[i];
+    for (int i = 156; i < 512; i++) sum += (unsigned char)h[i];
+    snprintf(h + 148, 8, "%06o", sum);
+    h[155] = ' ';
+    tar.write(h, 512);
+    tar.write(blob_.data(), (std::streamsize)blob_.size());
+    static const char zeros[512] = {0};
+    const size_t pad = (512 - blob_.size() % 512) % 512;
+    tar.write(zeros, (std::streamsize)pad);
+    return tar ? 0 : -1;
+}
+int FoldcompGpu::writeTarEnd(std::ostream& tar) {
+    static const char zeros[1024] = {0};
+    tar.write(zeros, 1024);
+    return tar ? 0 : -1;
+}
+
+int FoldcompGpu::extract(std::string& data, int type, int digits) {  // Foldcomp::extract, src/foldcomp.cpp:1260-1336
+    uint64_t blob_off[2] = {0, blob_.size()}, text_off[2] = {0, 0}, total = 0;
+    fcz_blob_batch in{};
+    in.n_chains = 1; in.mem = FCZ_MEM_HOST; in.blob_off = blob_off; in.bytes = (uint8_t*)&blob_[0];
+    std::string out(blob_.size() + 64, '\0');  // <= 6 characters per residue, >= 9 blob bytes per residue
+    fcz_text_batch tb{};
+    tb.n_chains = 1; tb.mem = FCZ_MEM_HOST; tb.text_off = text_off; tb.bytes = &out[0]; tb.bytes_cap = out.size();
+    const int rc = fcz_extract_batch(eng_.get(), &in, type, digits, &tb, &total);
+    if (rc) return rc;
+    data.append(out.data(), (size_t)total);
+    return 0;
+}
+
+int FoldcompGpu::checkValidity() {  // Foldcomp::checkValidity, src/foldcomp.cpp:1492-1532: the ValidityError class 0..6
+    uint64_t blob_off[2] = {0, blob_.size()};
+    fcz_blob_batch in{};
+    in.n_chains = 1; in.mem = FCZ_MEM_HOST; in.blob_off = blob_off; in.bytes = (uint8_t*)&blob_[0];
+    int32_t rs = 0, v = 0;
+    const int rc = fcz_check_batch(eng_.get(), &in, &rs, &v);
+    return rc ? rc : v;
 }
 
 }  // namespace fczgpu

@@ -9,6 +9,12 @@
 //     compRes.read(is);  (0 / -1 / -2)          compRes.read(is);                   // src/foldcomp.cpp:904
 //     compRes.useAltAtomOrder = alt;            compRes.useAltAtomOrder = alt;
 //     compRes.decompress(atoms);                compRes.decompress(atoms);          // src/foldcomp.cpp:779
+//     compRes.write(file) / writeTar(tar, ..)   compRes.write(file) / writeTar(os, name)  // src/foldcomp.cpp:1111, 1122
+//     compRes.extract(data, type, digits)       compRes.extract(data, type, digits) // src/foldcomp.cpp:1260
+//     compRes.checkValidity()                   compRes.checkValidity()             // src/foldcomp.cpp:1492
+//
+// (integration/foldcomp_on_engine.cpp goes one step further: it implements the reference's class Foldcomp ITSELF on
+// the engine, so that src/main.cpp and foldcomp/foldcomp.cxx link against it without a single changed line.)
 //
 // so that the CLI lambdas (src/main.cpp:438-536, 612-689) and the CPython module
 // (foldcomp/foldcomp.cxx:197-220, 253-293) change only at those call sites.  The batch forms
@@ -74,6 +80,11 @@ public:
 
     int compress(const std::vector<AtomCoordinate>& atoms);  // 0 ok, else FCZ_E_*
     int writeStream(std::ostream& os) const;
+    int write(const std::string& filename) const;                          // src/foldcomp.h:377
+    int writeTar(std::ostream& tar, const std::string& filename) const;     // src/foldcomp.h:382 (one archive member)
+    static int writeTarEnd(std::ostream& tar);                              // the archive's closing records
+    int extract(std::string& data, int type, int digits);                  // src/foldcomp.h:394: 0 pLDDT, 1 sequence
+    int checkValidity();                                                    // src/foldcomp.h:401: ValidityError class, FCZ_V_*
     size_t getSize() const { return blob_.size(); }
     int read(std::istream& is);                               // 0 ok, -1 bad magic (src/foldcomp.cpp:911-915)
     int decompress(std::vector<AtomCoordinate>& atoms);       // 0 ok

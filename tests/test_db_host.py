@@ -5,6 +5,7 @@ against plain-Python files and the reference's own reader."""
 import ctypes as C
 import ctypes.util
 import os
+import struct
 
 import numpy as np
 import pytest
@@ -157,3 +158,62 @@ def test_db_copy_handles_unsorted_and_gapped_files(lib, tmp_path):
     got = dbutil.read_db(dst)
     assert got == [(1, "1", b"one-one"), (3, "3", b""), (5, "5", b"five")]  # names default to the key
     assert lib.fczgpu_db_copy((src + "_missing").encode(), dst.encode()) < 0
+
+
+def test_reference_style_db_handles(tmp_path):
+    """make_reader ... writer_append (src/database_reader.h:11-27, src/database_writer.h:12-15) exported by
+    libfoldcomp_gpu.so over DbReader / DbWriter: same signatures (C++ linkage, as in the reference) and conventions --
+    ids are positions in the key-sorted index, lengths include the entry's NUL, lookups by name and by key, absent ->
+    -1 / UINT32_MAX / "", writer_append stores the data as given and free_writer sorts by key."""
+    import ctypes as C
+
+    lib = C.CDLL(dbutil.GPU_SO)
+    f = lambda name, res, args: (setattr(getattr(lib, name), "restype", res), setattr(getattr(lib, name), "argtypes", args), getattr(lib, name))[2]
+    make_reader = f("_Z11make_readerPKcS0_i", C.c_void_p, [C.c_char_p, C.c_char_p, C.c_int32])
+    free_reader = f("_Z11free_readerPv", None, [C.c_void_p])
+    get_id = f("_Z13reader_get_idPvj", C.c_int64, [C.c_void_p, C.c_uint32])
+    get_data = f("_Z15reader_get_dataPvl", C.c_void_p, [C.c_void_p, C.c_int64])
+    get_key = f("_Z14reader_get_keyPvl", C.c_uint32, [C.c_void_p, C.c_int64])
+    get_len = f("_Z17reader_get_lengthPvl", C.c_int64, [C.c_void_p, C.c_int64])
+    get_off = f("_Z17reader_get_offsetPvl", C.c_int64, [C.c_void_p, C.c_int64])
+    get_size = f("_Z15reader_get_sizePv", C.c_int64, [C.c_void_p])
+    lookup_entry = f("_Z19reader_lookup_entryPvPKc", C.c_uint32, [C.c_void_p, C.c_char_p])
+    lookup_name = f("_Z24reader_lookup_name_allocPvj", C.c_char_p, [C.c_void_p, C.c_uint32])
+    make_writer = f("_Z11make_writerPKcS0_", C.c_void_p, [C.c_char_p, C.c_char_p])
+    free_writer = f("_Z11free_writerPv", None, [C.c_void_p])
+    append = f("_Z13writer_appendPvPKcmjS1_", C.c_bool, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint32, C.c_char_p])
+
+    db = str(tmp_path / "db")
+    w = make_writer(db.encode(), (db + ".index").encode())
+    entries = [(7, "gamma", b"third entry\0"), (2, "alpha", b"first\0"), (5, "beta", b"second one\0")]  # keys out of order
+    for k, n, d in entries:
+        assert append(w, d, len(d), k, n.encode())
+    free_writer(w)
+    assert open(db + ".dbtype", "rb").read() == struct.pack("<i", 12)
+    assert [l.split("\t")[0] for l in open(db + ".index").read().splitlines()] == ["2", "5", "7"]
+    assert open(db + ".lookup").read().splitlines() == ["2\talpha\t0", "5\tbeta\t0", "7\tgamma\t0"]
+    assert open(db, "rb").read() == b"".join(d for _, _, d in entries)  # data in append order, nothing added
+
+    r = make_reader(db.encode(), (db + ".index").encode(), 1 | 4 | 8)
+    assert r and get_size(r) == 3
+    by_key = {k: (n, d) for k, n, d in entries}
+    for pos, k in enumerate((2, 5, 7)):
+        assert get_id(r, k) == pos and get_key(r, pos) == k
+        n, d = by_key[k]
+        assert get_len(r, pos) == len(d)
+        assert C.string_at(get_data(r, pos), get_len(r, pos)) == d
+        assert open(db, "rb").read()[get_off(r, pos):get_off(r, pos) + len(d)] == d
+        assert lookup_entry(r, n.encode()) == k and lookup_name(r, k) == n.encode()
+    assert get_id(r, 3) == -1 and get_data(r, 9) is None and get_len(r, -1) == -1
+    assert lookup_entry(r, b"delta") == 0xFFFFFFFF and lookup_name(r, 3) == b""
+    free_reader(r)
+    r = make_reader(db.encode(), (db + ".index").encode(), 0)  # no data, no lookup
+    assert get_size(r) == 3 and get_data(r, 0) is None and lookup_entry(r, b"alpha") == 0xFFFFFFFF
+    free_reader(r)
+    assert make_reader((db + "_missing").encode(), (db + "_missing.index").encode(), 1) is None
+    # the reference's own reader (its CPython module) opens what the handle API wrote
+    ref = dbutil.reference_module()
+    if ref is not None:
+        with ref.open(db, decompress=False) as d2:
+            assert len(d2) == 3 and [bytes(x).rstrip(b"\0") if not isinstance(x, str) else x.rstrip("\0") for x in d2] in (
+                [b"first", b"second one", b"third entry"], ["first", "second one", "third entry"])

@@ -40,3 +40,26 @@ def test_cli_rejects_garbage(tmp_path):
     bad.write_bytes(b"not an fcz file")
     r = subprocess.run([CLI, "decompress", str(bad), str(tmp_path / "x.pdb")], capture_output=True)
     assert r.returncode == 1 and b"not an FCZ" in r.stderr
+
+
+def test_cli_tar_extract_check(golden, tmp_path):
+    """FoldcompGpu::writeTar / extract / checkValidity (mirrors of src/foldcomp.h:382, 394, 401) through fcz_cli: the
+    archive is a valid tar whose member is the oracle's blob; extract and check agree with the oracle."""
+    import tarfile
+
+    ch = golden.batch.chain(golden.names.index("test_af.pdb"))
+    pdb_in = tmp_path / "in.pdb"
+    pdb_in.write_text(pdbio.format_pdb(ch, 0))
+    subprocess.check_call([CLI, "compress-tar", str(pdb_in), str(tmp_path / "out.tar")])
+    want = H.oracle_encode(pdbio.parse_pdb_chain(pdb_in.read_text(), "in"), 0, 25)
+    with tarfile.open(tmp_path / "out.tar") as t:
+        members = t.getmembers()
+        assert [m.name for m in members] == ["in.fcz"] and members[0].size == len(want)
+        assert t.extractfile(members[0]).read() == want
+    (tmp_path / "in.fcz").write_bytes(want)
+    for mode, type_ in (("extract-plddt", 0), ("extract-fasta", 1)):
+        subprocess.check_call([CLI, mode, str(tmp_path / "in.fcz"), str(tmp_path / "x.txt")])
+        lines = (tmp_path / "x.txt").read_bytes().split(b"\n")
+        assert lines[1] == H.oracle_extract(want, type_, 1)
+    subprocess.check_call([CLI, "check", str(tmp_path / "in.fcz"), str(tmp_path / "c.txt")])
+    assert int((tmp_path / "c.txt").read_text()) == H.oracle_check(want)[1] == 0
