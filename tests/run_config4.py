@@ -5,13 +5,13 @@ collective on the data path, ONE merged foldcomp database written by all ranks.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         tests/run_config4.py --chains-per-gpu 250000 --out /tmp/merged_db        # N = 8 -> 2 M chains, 700 M residues
 
-Every rank owns chains [rank * chains_per_gpu, (rank + 1) * chains_per_gpu): 10 000 synthetic chains (the bench.py
-generator, rank-specific seed offset) tiled on the device.  Encode runs with opts.terminate_blobs, so the rank's
+Every rank owns chains [rank * chains_per_gpu, (rank + 1) * chains_per_gpu), every one of them DISTINCT: generated on the
+device (foldcomp_b200/synth_device.py) from the chain's global index.  Encode runs with opts.terminate_blobs, so the rank's
 output IS its slab of the data file; the only exchange is the all_gather of one int64 per rank (the exclusive scan
 of slab sizes, foldcomp_b200/shard.py).  Each rank pwrite()s its slab at its offset and sends its index rows to
-rank 0, which writes .index / .lookup / .dbtype in key order.  Checks: blobs of every replica identical to the first
-one's, the first 10 000 spot-checked against the oracle when it is present, decode round trip within the loss of the
-format, the merged file re-read through its index.  Prints one JSON line (rank 0)."""
+rank 0, which writes .index / .lookup / .dbtype in key order.  Checks: every chain's status and round trip against its
+own input (on the device), the oracle on every 1000th chain of every rank (FCZ bytes identical, decode within tolerance),
+the merged file re-read through its index.  Prints one JSON line (rank 0)."""
 import argparse
 import json
 import os
@@ -25,12 +25,11 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from foldcomp_b200 import abi, shard, synth  # noqa: E402
+from foldcomp_b200 import abi, shard, synth, synth_device  # noqa: E402
 from foldcomp_b200.engine import DeviceBlobBatch, DeviceChainBatch, Engine  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--chains-per-gpu", type=int, default=250000)
-ap.add_argument("--base", type=int, default=10000, help="distinct synthetic chains per rank (tiled up to chains-per-gpu)")
 ap.add_argument("--out", default="/tmp/fcz_merged_db")
 ap.add_argument("--steps", type=int, default=3)
 args = ap.parse_args()
@@ -39,40 +38,28 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-n, nb = args.chains_per_gpu, min(args.base, args.chains_per_gpu)
-reps = (n + nb - 1) // nb
-base = synth.generate(nb, 350, seed=synth.SEED, first_index=rank * nb)
+n = args.chains_per_gpu
 L = 350
 stream = torch.cuda.Stream(device=dev)
 eng = Engine(local, anchor_threshold=25, stream=stream)
 eng.set_opts(terminate_blobs=True)
 
-
-def tile_offsets(off, unit_total, dtype):
-    o = torch.from_numpy(off[:-1].astype(np.int64)).to(dev)
-    full = (o[None, :] + unit_total * torch.arange(reps, device=dev, dtype=torch.int64)[:, None]).reshape(-1)[:n]
-    last = n - (reps - 1) * nb
-    end = unit_total * (reps - 1) + int(off[last])
-    return torch.cat([full, torch.tensor([end], device=dev, dtype=torch.int64)]).to(dtype), end
-
-
+# every chain DISTINCT: the synthetic generator on the device (foldcomp_b200/synth_device.py), keyed by the chain's
+# global index (rank * chains_per_gpu + i)
+t_gen = time.perf_counter()
 with torch.cuda.stream(stream):
+    g = synth_device.generate_device(n, L, synth.SEED, rank * n, dev)
     d = DeviceChainBatch(n, 1, 1, 1, dev)
-    d.res_off, n_res = tile_offsets(base.res_off, base.n_res, torch.int32)
-    d.atom_off, n_atoms = tile_offsets(base.atom_off, base.n_atoms, torch.int64)
-    d.title_off, n_title = tile_offsets(base.title_off, len(base.titles), torch.int32)
-    last = n - (reps - 1) * nb
-    d.res_type = torch.from_numpy(base.res_type).to(dev).repeat(reps)[:n_res].contiguous()
-    d.bfactor = torch.from_numpy(base.bfactor).to(dev).repeat(reps)[:n_res].contiguous()
-    d.xyz = torch.from_numpy(base.xyz).to(dev).repeat(reps, 1)[:n_atoms].contiguous()
-    d.titles = torch.from_numpy(base.titles).to(dev).repeat(reps)[:n_title].contiguous()
-    d.meta = torch.from_numpy(base.meta.view(np.uint8).reshape(nb, -1)).to(dev).repeat(reps, 1)[:n].contiguous()
+    d.res_off, d.atom_off, d.title_off = g["res_off"], g["atom_off"], g["title_off"]
+    d.res_type, d.bfactor, d.xyz, d.titles, d.meta = g["res_type"], g["bfactor"], g["xyz"], g["titles"], g["meta"]
     d.status = torch.zeros(n, dtype=torch.int32, device=dev)
+    n_res, n_atoms, n_title = int(d.res_off[-1].item()), int(d.atom_off[-1].item()), int(d.title_off[-1].item())
     d.n_res, d.n_atoms, d.n_title = n_res, n_atoms, n_title
     cap = abi.encode_bound(n, n_res, n_atoms, n_title, 25)
     dblob = DeviceBlobBatch(n, cap, dev)
     dout = DeviceChainBatch(n, n_res, n_atoms, n_title, dev)
 stream.synchronize()
+t_gen = time.perf_counter() - t_gen
 
 
 def step():
@@ -100,29 +87,42 @@ ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, dev
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 
-# ---- checks on the device result
+# ---- checks on the device result: every chain's status, every chain's round trip against its own input (on the device),
+# and the oracle on every 1000th chain: FCZ bytes identical, decoded coordinates within the tolerance
 assert int(dblob.status.count_nonzero().item()) == 0 and int(dout.status.count_nonzero().item()) == 0
 boff = dblob.blob_off
 slab_bytes = int(boff[-1].item())
-unit = int(boff[nb].item()) if n > nb else slab_bytes
-for k in range(1, reps):
-    nk = nb if k < reps - 1 else last
-    lo, hi = int(boff[k * nb].item()), int(boff[k * nb + nk].item())
-    assert hi - lo == int(boff[nk].item()) and torch.equal(dblob.bytes[lo:hi], dblob.bytes[: hi - lo]), k
-first = abi.HostBlobBatch(boff[: nb + 1].cpu().numpy().view(np.uint64).copy(), dblob.bytes[:unit].cpu().numpy().copy())
-oracle_checked = 0
-try:
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import helpers as H
+assert torch.equal(dout.res_type[:n_res], d.res_type) and torch.equal(dout.atom_off.to(torch.int64), d.atom_off.to(torch.int64))
+d2 = ((dout.xyz[:n_atoms].double() - d.xyz.double()) ** 2).sum(1)
+rt_rmsd = float(torch.sqrt(d2.mean()).item())
+chain_of_atom = torch.repeat_interleave(torch.arange(n, device=dev), (d.atom_off[1:] - d.atom_off[:-1]).to(torch.int64))
+per_chain = torch.sqrt(torch.zeros(n, device=dev, dtype=torch.float64).index_add_(0, chain_of_atom, d2) / (d.atom_off[1:] - d.atom_off[:-1]).double())
+worst_chain_rmsd = float(per_chain.max().item())
+assert rt_rmsd < 0.1 and worst_chain_rmsd < 0.5, (rt_rmsd, worst_chain_rmsd)
+oracle_checked, oracle_bb, oracle_max = 0, 0.0, 0.0
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers as H  # the checker (oracle/), test infrastructure
 
-    for c in range(0, nb, 1000):
-        assert first.blob(c) == H.oracle_encode(base, c, 25) + b"\0", c
-        oracle_checked += 1
-except ImportError:
-    pass
-got_xyz = dout.xyz[: base.n_atoms].cpu().numpy()
-rt_rmsd = float(np.sqrt(((got_xyz - base.xyz) ** 2).sum(1).mean()))
-assert rt_rmsd < 0.2, rt_rmsd
+sample = list(range(0, n, 1000))
+h_res_off, h_atom_off = d.res_off.cpu().numpy(), d.atom_off.cpu().numpy()
+h_boff = boff.cpu().numpy().view(np.uint64).astype(np.int64)
+for c in sample:
+    r0, r1, a0, a1 = int(h_res_off[c]), int(h_res_off[c + 1]), int(h_atom_off[c]), int(h_atom_off[c + 1])
+    one = abi.HostChainBatch(
+        res_off=np.array([0, r1 - r0], np.uint32), atom_off=np.array([0, a1 - a0], np.uint64), title_off=np.array([0, 11], np.uint32),
+        res_type=d.res_type[r0:r1].cpu().numpy(), bfactor=d.bfactor[r0:r1].cpu().numpy(), xyz=d.xyz[a0:a1].cpu().numpy(),
+        titles=d.titles[11 * c : 11 * c + 11].cpu().numpy(), meta=d.meta[c : c + 1].cpu().numpy().view(abi.META_DTYPE).reshape(-1))
+    want = H.oracle_encode(one, 0, 25)
+    got = bytes(dblob.bytes[int(h_boff[c]) : int(h_boff[c + 1])].cpu().numpy())
+    assert got == want + b"\0", (rank, c)
+    ref = H.oracle_decode(want)
+    mine = dout.xyz[a0:a1].cpu().numpy()
+    bbm = H.backbone_mask(ref.res_type)
+    oracle_bb = max(oracle_bb, H.rmsd(mine[bbm], ref.xyz[bbm]))
+    oracle_max = max(oracle_max, H.max_dev(mine, ref.xyz))
+    oracle_checked += 1
+assert oracle_bb <= 0.01 and oracle_max <= 0.05, (oracle_bb, oracle_max)
+first3 = [bytes(dblob.bytes[int(h_boff[c]) : int(h_boff[c + 1])].cpu().numpy()) for c in range(3)]
 
 # ---- merged database: exclusive scan of slab sizes, every rank writes its slab at its offset
 t0 = time.perf_counter()
@@ -169,14 +169,15 @@ if rank == 0:
         k = r * n + 7
         key, off, ln = allrows[k]
         assert key == k and data[off + ln - 1] == 0 and bytes(data[off : off + 4]) == b"FCMP"
-    mine = allrows[:3]
-    for key, off, ln in mine:
-        assert bytes(data[off : off + ln]) == first.blob(int(key))
+    for (key, off, ln), blob in zip(allrows[:3], first3):
+        assert bytes(data[off : off + ln]) == blob
     line = {
         "config": f"BASELINE.json configs[3]: {world * n} synthetic 350-residue chains, round trip sharded over {world} GPU(s), merged db",
         "n_gpus": world, "chains": world * n, "residues": world * n * L, "ms_per_round_trip": float(ms.item()),
         "residues_per_s": world * n * L / (float(ms.item()) * 1e-3), "fcz_bytes_total": int(total), "db_write_s": write_s,
-        "roundtrip_rmsd_vs_input": rt_rmsd, "replicas_identical": True, "oracle_spot_checks": oracle_checked,
+        "distinct_chains": True, "generator_s": t_gen, "roundtrip_rmsd_vs_input_all_atoms": rt_rmsd, "worst_chain_rmsd_vs_input": worst_chain_rmsd,
+        "oracle_checks_per_rank": oracle_checked, "oracle_fcz_bytes_identical": True, "decode_vs_oracle_bb_rmsd_max": oracle_bb,
+        "decode_vs_oracle_max_dev": oracle_max,
         "exchange": "one all_gather of an int64 per rank (slab sizes) + index rows to rank 0; no data-path collective",
     }
     print(json.dumps(line), flush=True)
