@@ -252,8 +252,8 @@ int FoldcompGpu::writeTar(std::ostream& tar, const std::string& filename) const 
     memcpy(h, filename.c_str(), filename.size());
     snprintf(h + 100, 8, "%o", 0644u);
     snprintf(h + 108, 8, "%o", 0u);
-    snprintf(h + 116, 12, "%o", (unsigned)blob_.size());
-    snprintf(h + 128, 12, "%o", 0u);
+    snprintf(h + 124, 12, "%o", (unsigned)blob_.size());  // (116: the group field, left zero as microtar leaves it)
+    snprintf(h + 136, 12, "%o", 0u);
     h[148 + 8] = '0';  // type, right after the 8-byte checksum field at offset 148
     unsigned sum = 256;
     for (int i = 0; i < 148; i++) sum += (unsigned char)h[i];

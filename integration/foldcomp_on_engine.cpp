@@ -73,7 +73,7 @@ struct Lease {
 std::string& blob_of(Foldcomp& f) { return f.strMetadata[kBlobKey]; }
 
 // header + the members the callers (and writeTar / get_data) look at, from an encoded chain
-int parse_into(Foldcomp& f, const std::string& b) {
+int parse_into(Foldcomp& f, std::string& b) {
     if (b.size() < 4 || memcmp(b.data(), MAGICNUMBER, MAGICNUMBER_LENGTH) != 0) return -1;  // src/foldcomp.cpp:911-915
     if (b.size() < 4 + sizeof(CompressedFileHeader)) return -1;
     memcpy(&f.header, b.data() + 4, sizeof(CompressedFileHeader));
@@ -83,7 +83,15 @@ int parse_into(Foldcomp& f, const std::string& b) {
     f.lenTitle = f.header.lenTitle; f.nBackbone = 3 * f.nResidue;
     size_t o = 4 + sizeof(CompressedFileHeader);
     const size_t need = o + 4ull * f.nAllAnchor + f.lenTitle + 36ull * f.nAllAnchor + 13 + 8ull * f.nResidue + f.nSideChainTorsion + 8 + f.nResidue;
-    if (b.size() < need) return -1;
+    if (b.size() < need) {
+        // A blob that stops inside its last section (the B-factor bytes): `foldcomp compress --db` stores entries without
+        // a terminator (src/main.cpp:510-517) while FoldcompDatabase strips one byte from every entry
+        // (foldcomp/foldcomp.cxx:65,73), so the reference's own Python reader hands read() blobs that are one byte
+        // short; read() (src/foldcomp.cpp:1024-1031) then decodes whatever its uninitialised buffer held there.  Here
+        // the missing bytes are zeros.  Anything shorter is not a readable entry.
+        if (b.size() + (size_t)f.nResidue < need) return -1;
+        b.resize(need, '\0');
+    }
     f.anchorIndices.resize(f.nAllAnchor);
     memcpy(f.anchorIndices.data(), b.data() + o, 4ull * f.nAllAnchor); o += 4ull * f.nAllAnchor;
     f.strTitle.assign(b.data() + o, f.lenTitle); o += f.lenTitle;
