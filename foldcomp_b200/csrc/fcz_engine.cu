@@ -24,6 +24,7 @@
 
 #include "fcz_codec.h"
 #include "fcz_text.h"
+#include "fcz_parse.h"
 
 using namespace fcz;
 
@@ -210,6 +211,8 @@ struct DevCtx {
     // integer warp reductions (REDUX.MIN / REDUX.MAX) and shared / global atomics: floats go through fcz::ford
     __device__ __forceinline__ int32_t wmin_i(int32_t v) { return __reduce_min_sync(0xffffffffu, v); }
     __device__ __forceinline__ int32_t wmax_i(int32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+    __device__ __forceinline__ void atomic_min_u(uint32_t* p, uint32_t v) { atomicMin(p, v); }
+    __device__ __forceinline__ void atomic_or_u(uint32_t* p, uint32_t v) { atomicOr(p, v); }
     __device__ __forceinline__ void atomic_min_i(int32_t* p, int32_t v) { atomicMin(p, v); }
     __device__ __forceinline__ void atomic_max_i(int32_t* p, int32_t v) { atomicMax(p, v); }
 };
@@ -1220,6 +1223,84 @@ __global__ void __launch_bounds__(128) k_unpack_angles(AnglesArgs a) {
     }
 }
 
+// ============================================================================================ PDB text in
+// fcz_parse.h on the GPU: k_parse_lines counts the lines of every entry (sizes the workspace), k_parse_plan (block per
+// entry) finds and parses the ATOM records, drops alternative positions and splits residues, k_parse_emit (block per
+// entry) fills the canonical layout.
+struct ParseArgs {
+    const uint64_t* text_off;
+    const char* text;
+    uint32_t n;
+    const ParseTables* pt;
+    uint32_t* n_lines;          // [n] lines per entry (k_parse_lines)
+    const uint64_t* line_off;   // [n+1] their scan: workspace slots
+    uint32_t* lines;            // [total_lines + n]
+    uint32_t* rstart;           // [total_lines + n]
+    RawAtom* raw;               // [2 * total_lines]
+    uint32_t* scratch;          // [8 * n]
+    uint32_t* v_res;            // [n] residues per entry (plan output)
+    uint32_t* v_atoms;          // [n] table slots per entry
+    int32_t* status;            // [n]
+    const uint32_t* res_off;    // [n+1]
+    const uint64_t* atom_off;   // [n+1]
+    uint8_t* res_type;
+    float* bfactor;
+    float* xyz;
+    fcz_chain_meta* meta;
+};
+__global__ void __launch_bounds__(256) k_parse_lines(ParseArgs a) {
+    __shared__ uint32_t s_cnt;
+    const uint32_t c = blockIdx.x;
+    const char* t = a.text + a.text_off[c];
+    const uint64_t len = a.text_off[c + 1] - a.text_off[c];
+    if (threadIdx.x == 0) s_cnt = 0u;
+    __syncthreads();
+    uint32_t cnt = 0;
+    for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) cnt += t[i] == '\n';
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) a.n_lines[c] = s_cnt + ((len && t[len - 1] != '\n') ? 1u : 0u);
+}
+__device__ __forceinline__ ParseEntry parse_entry_of(const ParseArgs& a, uint32_t c) {
+    ParseEntry e;
+    e.text = a.text + a.text_off[c];
+    e.len = (uint32_t)(a.text_off[c + 1] - a.text_off[c]);
+    const uint64_t l0 = a.line_off[c];
+    e.max_lines = (uint32_t)(a.line_off[c + 1] - l0);
+    e.lines = a.lines + l0 + c;
+    e.rstart = a.rstart + l0 + c;
+    e.raw = a.raw + 2ull * l0;
+    e.scratch = a.scratch + 8ull * c;
+    return e;
+}
+__global__ void __launch_bounds__(256) k_parse_plan(ParseArgs a) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t c = blockIdx.x;
+    DevCtx cx = block_ctx(wsum);
+    const ParseEntry e = parse_entry_of(a, c);
+    if (e.max_lines == 0u || (a.text_off[c + 1] - a.text_off[c]) >= 0xFFFFFFFFull) {  // empty text (or one beyond 4 GB)
+        if (threadIdx.x == 0) { a.v_res[c] = 0u; a.v_atoms[c] = 0u; a.status[c] = FCZ_E_PARSE_NOATOM; e.scratch[PS_FLAG] = 1u; }
+        return;
+    }
+    parse_entry_plan(cx, a.pt, e);
+    if (threadIdx.x == 0) {
+        const uint32_t f = e.scratch[PS_FLAG];
+        a.status[c] = f == 0u ? FCZ_OK : (f == 1u ? FCZ_E_PARSE_NOATOM : (f == 2u ? FCZ_E_PARSE_CHAINS : (f == 3u ? FCZ_E_PARSE_RECORD : FCZ_E_PARSE_NUMBER)));
+        a.v_res[c] = f ? 0u : e.scratch[PS_NRES];
+        a.v_atoms[c] = f ? 0u : e.scratch[PS_NSLOT];
+    }
+}
+__global__ void __launch_bounds__(256) k_parse_emit(ParseArgs a) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t c = blockIdx.x;
+    if (a.status[c] != FCZ_OK) return;
+    DevCtx cx = block_ctx(wsum);
+    const ParseEntry e = parse_entry_of(a, c);
+    parse_entry_emit(cx, a.pt, e, a.res_type + a.res_off[c], a.bfactor + a.res_off[c], a.xyz + 3ull * a.atom_off[c], a.meta + c);
+}
+
 // ============================================================================================ scans
 // Exclusive scans of up to three per-chain u32 arrays into offsets (u32/u64), tile = 2048 chains.
 
@@ -1342,6 +1423,11 @@ struct fcz_engine {
     DevBuf ws_aoff, ws_toff, d_unit_off, d_unit_chain, d_text_off, d_text;
     struct PdbPlan { uint32_t n = 0; uint64_t total_bytes = 0; uint32_t total_units = 0; bool valid = false; } pdb;
     std::vector<uint32_t> h_unit_off;
+    // PDB text parser (fcz_parse_pdb_plan -> fcz_parse_pdb_batch): tables, per-line workspace
+    ParseTables* d_parse_tables = nullptr;
+    DevBuf p_line_off, p_lines, p_rstart, p_raw, p_scratch;
+    struct ParsePlan { uint32_t n = 0; uint64_t n_res = 0, n_atoms = 0; int32_t* status = nullptr; bool valid = false; } parse;
+    std::vector<int32_t> h_parse_status;
     // plan scratch
     DevBuf v0, v1, v2, v3, status, tier_list, partial;
     uint32_t* d_counters = nullptr;  // [FCZ_NTIER] counts, [FCZ_NTIER] tickets
@@ -1527,11 +1613,13 @@ void fcz_engine_destroy(fcz_engine* e) {
     DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->v3, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
                       &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets, &e->enc_gws, &e->d_stage, &e->ws_aoff, &e->ws_toff, &e->d_unit_off, &e->d_unit_chain, &e->d_text_off, &e->d_text,
-                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list};
+                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list,
+                      &e->p_line_off, &e->p_lines, &e->p_rstart, &e->p_raw, &e->p_scratch};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (e->d_tables) cudaFree(e->d_tables);
     if (e->d_text_tables) cudaFree(e->d_text_tables);
+    if (e->d_parse_tables) cudaFree(e->d_parse_tables);
     if (e->d_counters) cudaFree(e->d_counters);
     if (e->d_totals) cudaFree(e->d_totals);
     if (e->h_counters) cudaFreeHost(e->h_counters);
@@ -1634,6 +1722,10 @@ const char* fcz_strerror(int code) {
         case FCZ_E_CAPACITY: return "output buffer too small";
         case FCZ_E_CUDA: return "CUDA error";
         case FCZ_E_ARG: return "bad argument";
+        case FCZ_E_PARSE_NOATOM: return "No ATOM lines found";
+        case FCZ_E_PARSE_CHAINS: return "Multiple chains found";
+        case FCZ_E_PARSE_RECORD: return "Malformed ATOM record";
+        case FCZ_E_PARSE_NUMBER: return "numeric field outside the fixed-point grammar";
         default: return "unknown error";
     }
 }
@@ -2826,5 +2918,161 @@ extern "C" int fcz_check_batch(fcz_engine* e, const fcz_blob_batch* in, int32_t*
         if (validity && n) CK(cudaMemcpyAsync(validity, a.validity, 4ull * n, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
     }
+    return FCZ_OK;
+}
+
+// ---------------------------------------------------------------------------------- PDB text in (section 8 f3)
+static void parse_args(fcz_engine* e, const uint64_t* text_off, const char* text, uint32_t n, ParseArgs* a) {
+    memset(a, 0, sizeof *a);
+    a->text_off = text_off; a->text = text; a->n = n; a->pt = e->d_parse_tables;
+    a->n_lines = (uint32_t*)e->v0.p; a->line_off = (uint64_t*)e->p_line_off.p;
+    a->lines = (uint32_t*)e->p_lines.p; a->rstart = (uint32_t*)e->p_rstart.p; a->raw = (RawAtom*)e->p_raw.p;
+    a->scratch = (uint32_t*)e->p_scratch.p;
+    a->v_res = (uint32_t*)e->v1.p; a->v_atoms = (uint32_t*)e->v2.p;
+}
+
+// lines -> workspace -> per-entry plan -> offsets; two stream syncs (the workspace and the outputs are sized by the text)
+static int parse_plan_dev(fcz_engine* e, const uint64_t* d_text_off, const char* d_text, uint32_t n, uint32_t* d_res_off,
+                          uint64_t* d_atom_off, int32_t* d_status, fcz_sizes* totals) {
+    int rc;
+    e->parse.valid = false;
+    if (!e->d_parse_tables) {
+        ParseTables h;
+        build_parse_tables(&h);
+        CK(cudaMalloc(&e->d_parse_tables, sizeof(ParseTables)));
+        CK(cudaMemcpyAsync(e->d_parse_tables, &h, sizeof(ParseTables), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));  // h is a stack object
+    }
+    if ((rc = plan_buffers(e, n))) return rc;
+    if ((rc = ensure(e, e->p_line_off, 8ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->p_scratch, 32ull * n + 32))) return rc;
+    ParseArgs a;
+    parse_args(e, d_text_off, d_text, n, &a);
+    if (n) {
+        k_parse_lines<<<n, 256, 0, e->stream>>>(a);
+        e->launches++;
+    }
+    ScanArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.n = n; sa.narr = 1;
+    sa.in[0] = a.n_lines; sa.out[0] = e->p_line_off.p; sa.out64[0] = 1;
+    if ((rc = run_scan(e, sa))) return rc;
+    if ((rc = fetch_plan(e))) return rc;
+    const uint64_t total_lines = e->h_totals[0];
+    if ((rc = ensure(e, e->p_lines, 4ull * (total_lines + n + 1)))) return rc;
+    if ((rc = ensure(e, e->p_rstart, 4ull * (total_lines + n + 1)))) return rc;
+    if ((rc = ensure(e, e->p_raw, 2ull * sizeof(RawAtom) * total_lines + 64))) return rc;
+    parse_args(e, d_text_off, d_text, n, &a);
+    a.status = d_status;
+    if (n) {
+        k_parse_plan<<<n, 256, 0, e->stream>>>(a);
+        e->launches++;
+    }
+    memset(&sa, 0, sizeof sa);
+    sa.n = n; sa.narr = 2;
+    sa.in[0] = a.v_res; sa.out[0] = d_res_off; sa.out64[0] = 0;
+    sa.in[1] = a.v_atoms; sa.out[1] = d_atom_off; sa.out64[1] = 1;
+    if ((rc = run_scan(e, sa))) return rc;
+    if ((rc = fetch_plan(e))) return rc;
+    if (e->h_totals[0] > 0xFFFFFFFFull) return fail(e, FCZ_E_LIMIT, "a parsed batch holds %llu residues (the canonical layout indexes residues with 32 bits)", (unsigned long long)e->h_totals[0]);
+    if (totals) { totals->n_res = e->h_totals[0]; totals->n_atoms = e->h_totals[1]; totals->n_title_bytes = 0; totals->n_blob_bytes = 0; }
+    e->parse.n = n; e->parse.n_res = e->h_totals[0]; e->parse.n_atoms = e->h_totals[1]; e->parse.status = d_status; e->parse.valid = true;
+    return FCZ_OK;
+}
+
+static int parse_emit_dev(fcz_engine* e, const uint64_t* d_text_off, const char* d_text, uint32_t n, const uint32_t* d_res_off,
+                          const uint64_t* d_atom_off, uint8_t* res_type, float* bfactor, float* xyz, fcz_chain_meta* meta) {
+    ParseArgs a;
+    parse_args(e, d_text_off, d_text, n, &a);
+    a.status = e->parse.status;
+    a.res_off = d_res_off; a.atom_off = d_atom_off; a.res_type = res_type; a.bfactor = bfactor; a.xyz = xyz; a.meta = meta;
+    if (n) {
+        k_parse_emit<<<n, 256, 0, e->stream>>>(a);
+        e->launches++;
+    }
+    CK(cudaGetLastError());
+    return FCZ_OK;
+}
+
+extern "C" int fcz_parse_pdb_plan(fcz_engine* e, const fcz_text_batch* in, fcz_chain_batch* out, fcz_sizes* totals) {
+    if (!e || !in || !out || !totals) return FCZ_E_ARG;
+    if (in->mem != FCZ_MEM_DEVICE || out->mem != FCZ_MEM_DEVICE) return fail(e, FCZ_E_ARG, "fcz_parse_pdb_plan works on device memory (fcz_encode_pdb_text_batch takes host text)");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    out->n_chains = n;
+    int rc;
+    int32_t* st = out->status;
+    if (!st) { if ((rc = ensure(e, e->d_status, 4ull * n + 4))) return rc; st = (int32_t*)e->d_status.p; }
+    return parse_plan_dev(e, in->text_off, in->bytes, n, out->res_off, out->atom_off, st, totals);
+}
+
+extern "C" int fcz_parse_pdb_batch(fcz_engine* e, const fcz_text_batch* in, fcz_chain_batch* out) {
+    if (!e || !in || !out) return FCZ_E_ARG;
+    if (in->mem != FCZ_MEM_DEVICE || out->mem != FCZ_MEM_DEVICE) return fail(e, FCZ_E_ARG, "fcz_parse_pdb_batch works on device memory");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    if (!e->parse.valid || e->parse.n != n) return fail(e, FCZ_E_ARG, "fcz_parse_pdb_batch needs a preceding fcz_parse_pdb_plan on the same batch");
+    if (e->parse.n_res > out->res_cap || e->parse.n_atoms > out->atom_cap)
+        return fail(e, FCZ_E_CAPACITY, "parsed batch needs %llu residues / %llu atoms of capacity", (unsigned long long)e->parse.n_res, (unsigned long long)e->parse.n_atoms);
+    e->parse.valid = false;
+    return parse_emit_dev(e, in->text_off, in->bytes, n, out->res_off, out->atom_off, out->res_type, out->bfactor, out->xyz, out->meta);
+}
+
+extern "C" int fcz_encode_pdb_text_batch(fcz_engine* e, const fcz_text_batch* in, const uint32_t* title_off, const char* titles,
+                                         fcz_blob_batch* out, uint64_t* total_bytes) {
+    if (!e || !in || !out || !total_bytes || !title_off) return FCZ_E_ARG;
+    if (in->mem != FCZ_MEM_HOST || out->mem != FCZ_MEM_HOST) return fail(e, FCZ_E_ARG, "fcz_encode_pdb_text_batch takes host text and returns host blobs");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    out->n_chains = n;
+    int rc;
+    const uint64_t n_text = in->text_off[n], n_title = title_off[n];
+    // text up: the offsets first (the line count needs them), the bytes in one copy
+    H2D(e->d_text_off, in->text_off, 8ull * (n + 1));
+    H2D(e->d_text, in->bytes, n_text);
+    H2D(e->d_title_off, title_off, 4ull * (n + 1));
+    H2D(e->d_titles, titles, n_title);
+    if ((rc = ensure(e, e->d_res_off, 4ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_atom_off, 8ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_status, 8ull * n + 8))) return rc;
+    if ((rc = ensure(e, e->d_meta, sizeof(fcz_chain_meta) * (uint64_t)n + 32))) return rc;
+    int32_t* d_pstat = (int32_t*)e->d_status.p;       // parser status
+    int32_t* d_estat = (int32_t*)e->d_status.p + n;   // encoder status
+    fcz_sizes tot;
+    if ((rc = parse_plan_dev(e, (const uint64_t*)e->d_text_off.p, (const char*)e->d_text.p, n, (uint32_t*)e->d_res_off.p,
+                             (uint64_t*)e->d_atom_off.p, d_pstat, &tot))) return rc;
+    if ((rc = ensure(e, e->d_res_type, tot.n_res + 16))) return rc;
+    if ((rc = ensure(e, e->d_bfactor, 4ull * tot.n_res + 16))) return rc;
+    if ((rc = ensure(e, e->d_xyz, 12ull * tot.n_atoms + 16))) return rc;
+    if (n) CK(cudaMemsetAsync(e->d_meta.p, 0, sizeof(fcz_chain_meta) * (uint64_t)n, e->stream));  // entries that failed to parse
+    e->parse.valid = false;
+    if ((rc = parse_emit_dev(e, (const uint64_t*)e->d_text_off.p, (const char*)e->d_text.p, n, (uint32_t*)e->d_res_off.p,
+                             (uint64_t*)e->d_atom_off.p, (uint8_t*)e->d_res_type.p, (float*)e->d_bfactor.p, (float*)e->d_xyz.p,
+                             (fcz_chain_meta*)e->d_meta.p))) return rc;
+    // encode the device-resident chains
+    const uint64_t bound = fcz_encode_bound(n, tot.n_res, tot.n_atoms, n_title, e->opts.anchor_threshold);
+    if ((rc = ensure(e, e->d_blob_off, 8ull * (n + 1)))) return rc;
+    if ((rc = ensure(e, e->d_bytes, bound + 64))) return rc;
+    fcz_chain_batch cb;
+    memset(&cb, 0, sizeof cb);
+    cb.n_chains = n; cb.mem = FCZ_MEM_DEVICE;
+    cb.res_off = (uint32_t*)e->d_res_off.p; cb.atom_off = (uint64_t*)e->d_atom_off.p; cb.title_off = (uint32_t*)e->d_title_off.p;
+    cb.res_type = (uint8_t*)e->d_res_type.p; cb.bfactor = (float*)e->d_bfactor.p; cb.xyz = (float*)e->d_xyz.p;
+    cb.titles = (char*)e->d_titles.p; cb.meta = (fcz_chain_meta*)e->d_meta.p;
+    fcz_blob_batch bb;
+    memset(&bb, 0, sizeof bb);
+    bb.n_chains = n; bb.mem = FCZ_MEM_DEVICE;
+    bb.blob_off = (uint64_t*)e->d_blob_off.p; bb.bytes = (uint8_t*)e->d_bytes.p; bb.status = d_estat; bb.bytes_cap = bound;
+    uint64_t total = 0;
+    if ((rc = encode_device(e, &cb, &bb, &total))) return rc;
+    *total_bytes = total;
+    if (total > out->bytes_cap) return fail(e, FCZ_E_CAPACITY, "encode needs %llu bytes, capacity %llu", (unsigned long long)total, (unsigned long long)out->bytes_cap);
+    CK(cudaMemcpyAsync(out->blob_off, e->d_blob_off.p, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
+    if (total) CK(cudaMemcpyAsync(out->bytes, e->d_bytes.p, total, cudaMemcpyDeviceToHost, e->stream));
+    e->h_parse_status.resize(2ull * n + 2);
+    if (n) CK(cudaMemcpyAsync(e->h_parse_status.data(), e->d_status.p, 8ull * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (out->status)
+        for (uint32_t c = 0; c < n; c++) out->status[c] = e->h_parse_status[c] ? e->h_parse_status[c] : e->h_parse_status[n + c];
     return FCZ_OK;
 }

@@ -52,6 +52,11 @@ extern "C" {
 #define FCZ_E_CAPACITY (-5)      /* an output buffer is too small                                 */
 #define FCZ_E_CUDA (-6)          /* CUDA runtime error (see fcz_last_error)                       */
 #define FCZ_E_ARG (-7)           /* bad argument                                                  */
+/* PDB text (fcz_parse_pdb_*, fcz_encode_pdb_text_batch), per entry; the reference's parser flags (foldcomp/foldcomp.cxx:262-291) */
+#define FCZ_E_PARSE_NOATOM (-11) /* no ATOM record ("No ATOM lines found", flag 1)                 */
+#define FCZ_E_PARSE_CHAINS (-12) /* ATOM records of more than one chain ("Multiple chains", flag 2) */
+#define FCZ_E_PARSE_RECORD (-13) /* an ATOM record too short for its columns (the reference throws std::out_of_range) */
+#define FCZ_E_PARSE_NUMBER (-14) /* a numeric field that is not a plain fixed-point number (see fcz_parse_pdb_plan)   */
 
 typedef struct fcz_engine fcz_engine;
 
@@ -187,6 +192,29 @@ int fcz_extract_batch(fcz_engine* e, const fcz_blob_batch* in, int32_t type, int
 #define FCZ_V_EMPTY_SIDECHAIN_ANGLE 5
 #define FCZ_V_EMPTY_TEMP_FACTOR 6
 int fcz_check_batch(fcz_engine* e, const fcz_blob_batch* in, int32_t* read_status, int32_t* validity);
+
+/* ---- PDB text in ----------------------------------------------------------------------------
+ * The fixed-column ATOM parser of the reference's CPython compress() (foldcomp/foldcomp.cxx:253-293: atom 12-15, residue
+ * 17-19, chain 21, serial 6-10, residue number 22-25, x y z 30-53, B-factor 60-65; removeAlternativePosition
+ * src/atom_coordinate.cpp:362-370) followed by the encoder's by-name bookkeeping (residue split src/atom_coordinate.cpp:304-328,
+ * first atom of every table name src/sidechain.cpp:140-147, CA B-factor src/foldcomp.cpp:543-547, OXT 473-481), for a
+ * batch of single-chain PDB texts on the GPU: `in` = texts tightly concatenated (text_off[n+1], bytes), DEVICE memory;
+ * `out` = the canonical chain batch in DEVICE memory.  fcz_parse_pdb_plan fills out->res_off, out->atom_off, out->status
+ * (0 or FCZ_E_PARSE_*: such an entry has no residues) and `totals` (it synchronises the engine's stream);
+ * fcz_parse_pdb_batch must follow on the same batch and fills res_type, bfactor, xyz, meta.  Titles are the caller's
+ * (entry names): title_off / titles are not touched.  Numeric fields are converted exactly like the reference's
+ * std::stof when they are plain fixed-point numbers of at most nine digits (what every PDB writer emits); any other shape
+ * (exponent, hex float, nan) makes the entry FCZ_E_PARSE_NUMBER. */
+int fcz_parse_pdb_plan(fcz_engine* e, const fcz_text_batch* in, fcz_chain_batch* out, fcz_sizes* totals);
+int fcz_parse_pdb_batch(fcz_engine* e, const fcz_text_batch* in, fcz_chain_batch* out);
+
+/* PDB texts in HOST memory -> FCZ blobs in HOST memory in one call: what `foldcomp compress` does per entry
+ * (src/main.cpp:438-536) for a batch.  The text goes up once, parsing and encoding stay on the GPU, only the blobs come
+ * back.  title_off[n+1] / titles: the entries' titles (host).  out->blob_off, out->bytes (capacity out->bytes_cap),
+ * out->status (parser or encoder status per entry; a failed entry gets an empty blob).  *total_bytes receives the size
+ * needed; FCZ_E_CAPACITY when out->bytes is smaller. */
+int fcz_encode_pdb_text_batch(fcz_engine* e, const fcz_text_batch* in, const uint32_t* title_off, const char* titles,
+                              fcz_blob_batch* out, uint64_t* total_bytes);
 
 /* Continuised backbone angles of every residue record: six floats per residue, phi, psi, omega, N-CA-C, CA-C-N, C-N-CA
  * -- decompressBackboneChain (src/foldcomp.cpp:122-153), i.e. what Foldcomp::decompress leaves in its phi / psi / omega /

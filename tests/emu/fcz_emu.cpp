@@ -9,6 +9,7 @@
 
 #include "../../foldcomp_b200/csrc/fcz_codec.h"
 #include "../../foldcomp_b200/csrc/fcz_text.h"
+#include "../../foldcomp_b200/csrc/fcz_parse.h"
 
 using namespace fcz;
 
@@ -24,6 +25,8 @@ struct HostCtx {
     uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
     int32_t wmin_i(int32_t v) { return v; }
     int32_t wmax_i(int32_t v) { return v; }
+    void atomic_min_u(uint32_t* p, uint32_t v) { if (v < *p) *p = v; }
+    void atomic_or_u(uint32_t* p, uint32_t v) { *p |= v; }
     void atomic_min_i(int32_t* p, int32_t v) { if (v < *p) *p = v; }
     void atomic_max_i(int32_t* p, int32_t v) { if (v > *p) *p = v; }
 };
@@ -239,4 +242,44 @@ extern "C" double emu_acosdeg_f_check(uint32_t stride) {
         }
     }
     return worst;
+}
+
+// The GPU parser's per-entry algorithm (fcz_parse.h) on one host thread: returns the parser's flag (0 ok), or -1 when
+// the output arrays are too small.
+extern "C" int emu_parse_pdb(const char* text, uint32_t len, uint8_t* res_type, float* bfac, float* xyz, fcz_chain_meta* meta,
+                             uint32_t* n_res, uint32_t* n_atoms, uint32_t cap_res, uint32_t cap_atoms) {
+    static ParseTables pt;
+    static bool init = false;
+    if (!init) { build_parse_tables(&pt); init = true; }
+    uint32_t max_lines = 1;
+    for (uint32_t i = 0; i < len; i++) max_lines += text[i] == '\n';
+    std::vector<uint32_t> lines(max_lines + 1), rstart(max_lines + 1), scratch(8);
+    std::vector<RawAtom> raw(2 * (size_t)max_lines);
+    ParseEntry e;
+    e.text = text; e.len = len; e.max_lines = max_lines; e.lines = lines.data(); e.raw = raw.data(); e.rstart = rstart.data(); e.scratch = scratch.data();
+    HostCtx cx;
+    parse_entry_plan(cx, &pt, e);
+    if (scratch[PS_FLAG]) return (int)scratch[PS_FLAG];
+    *n_res = scratch[PS_NRES]; *n_atoms = scratch[PS_NSLOT];
+    if (*n_res > cap_res || *n_atoms > cap_atoms) return -1;
+    parse_entry_emit(cx, &pt, e, res_type, bfac, xyz, meta);
+    return 0;
+}
+// parse_fixed_float against strtof on n fields of width w (concatenated): returns the number of mismatches; *rejected = fields
+// the fast shape does not cover
+extern "C" uint64_t emu_parse_float_check(const char* fields, uint32_t w, uint64_t n, uint64_t* rejected) {
+    uint64_t bad = 0, rej = 0;
+#pragma omp parallel for reduction(+ : bad, rej) schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        char buf[40];
+        memcpy(buf, fields + (size_t)i * w, w);
+        buf[w] = 0;
+        bool ok;
+        const float got = parse_fixed_float(buf, w, &ok);
+        if (!ok) { rej++; continue; }
+        const float want = strtof(buf, nullptr);
+        if (memcmp(&got, &want, 4) != 0) bad++;
+    }
+    *rejected = rej;
+    return bad;
 }
