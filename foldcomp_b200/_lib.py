@@ -29,7 +29,12 @@ SYMBOLS = [
     "fcz_decode_to_pdb_batch",
     "fcz_extract_batch",
     "fcz_check_batch",
+    "fcz_parse_pdb_plan",
+    "fcz_parse_pdb_batch",
+    "fcz_encode_pdb_text_batch",
     "fcz_unpack_angles_batch",
+    "fcz_host_alloc",
+    "fcz_host_free",
     "fcz_engine_sync",
     "fcz_engine_launch_count",
     "fcz_engine_set_profiling",
@@ -86,8 +91,18 @@ def load() -> C.CDLL:
     lib.fcz_extract_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), C.c_int32, C.c_int32, P(abi.FczTextBatch), P(C.c_uint64)]
     lib.fcz_check_batch.restype = C.c_int
     lib.fcz_check_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), C.c_void_p, C.c_void_p]
+    lib.fcz_parse_pdb_plan.restype = C.c_int
+    lib.fcz_parse_pdb_plan.argtypes = [C.c_void_p, P(abi.FczTextBatch), P(abi.FczChainBatch), P(abi.FczSizes)]
+    lib.fcz_parse_pdb_batch.restype = C.c_int
+    lib.fcz_parse_pdb_batch.argtypes = [C.c_void_p, P(abi.FczTextBatch), P(abi.FczChainBatch)]
+    lib.fcz_encode_pdb_text_batch.restype = C.c_int
+    lib.fcz_encode_pdb_text_batch.argtypes = [C.c_void_p, P(abi.FczTextBatch), C.c_void_p, C.c_void_p, P(abi.FczBlobBatch), P(C.c_uint64)]
     lib.fcz_unpack_angles_batch.restype = C.c_int
     lib.fcz_unpack_angles_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), C.c_void_p, C.c_void_p, C.c_uint64, P(C.c_uint64)]
+    lib.fcz_host_alloc.restype = C.c_void_p
+    lib.fcz_host_alloc.argtypes = [C.c_size_t]
+    lib.fcz_host_free.restype = None
+    lib.fcz_host_free.argtypes = [C.c_void_p]
     lib.fcz_engine_sync.restype = C.c_int
     lib.fcz_engine_sync.argtypes = [C.c_void_p]
     lib.fcz_engine_launch_count.restype = C.c_uint64

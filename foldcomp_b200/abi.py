@@ -22,6 +22,11 @@ FCZ_E_LIMIT = -4
 FCZ_E_CAPACITY = -5
 FCZ_E_CUDA = -6
 FCZ_E_ARG = -7
+# PDB text parser, per entry (the flags of foldcomp/foldcomp.cxx:262-291 plus the two shapes the reference throws on)
+FCZ_E_PARSE_NOATOM = -11
+FCZ_E_PARSE_CHAINS = -12
+FCZ_E_PARSE_RECORD = -13
+FCZ_E_PARSE_NUMBER = -14
 
 DEFAULT_ANCHOR_THRESHOLD = 25  # src/foldcomp.h:56
 

@@ -417,6 +417,10 @@ int decompressDb(Engine& eng, const std::string& in_db, const std::string& out_d
 }
 
 int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db, int anchorThreshold, DbStats* stats) {
+    // PDB text goes to the GPU as it is: the ATOM parser (fcz_parse.h, k_parse_*) and the encoder run there, only the FCZ
+    // blobs (about 1/40 of the text) come back.  The host's share is one parallel copy of the mapped text into a pinned
+    // buffer -- without each entry's NUL terminator -- and the database writer.  FCZ_HOST_PARSER=1 restores the
+    // per-entry host parser (parsePdbChain under OpenMP) for A/B runs.
     const double t0 = now_s();
     DbReader rd;
     if (!rd.open(in_db)) return FCZ_E_ARG;
@@ -424,38 +428,118 @@ int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db,
     if (!wr.open(out_db)) return FCZ_E_ARG;
     DbStats s;
     const size_t n_all = rd.size();
+    const char* hp = getenv("FCZ_HOST_PARSER");
+    const bool host_parser = hp && atoi(hp) != 0;
+    fcz_opts o{anchorThreshold, 0, nullptr, 0};
+    int rc = fcz_engine_set_opts(eng.get(), &o);
+    if (rc) return rc;
     const uint64_t kBatchBytes = 512ull << 20;  // PDB text per engine call (~80 MB of coordinates)
+    char* pin_text = nullptr;
+    uint8_t* pin_blob = nullptr;
+    uint64_t pin_text_cap = 0, pin_blob_cap = 0;
+    struct Free { char*& a; uint8_t*& b; ~Free() { if (a) fcz_host_free(a); if (b) fcz_host_free(b); } } guard{pin_text, pin_blob};
     size_t i0 = 0;
     while (i0 < n_all) {
         size_t i1 = i0;
         uint64_t sum = 0;
         while (i1 < n_all && (i1 == i0 || sum + rd.length(i1) <= kBatchBytes)) sum += rd.length(i1++);
         const size_t n = i1 - i0;
-        std::vector<CanonicalChain> chains(n);
-        std::vector<int> flag(n, 0);
-#pragma omp parallel for schedule(dynamic, 8)
-        for (size_t c = 0; c < n; c++)
-            flag[c] = parsePdbChain(rd.data(i0 + c), rd.payload(i0 + c), strip_ext(rd.name(i0 + c)), chains[c]);
-        std::vector<CanonicalChain> good;
+        std::vector<std::string> blobs_host;     // host-parser path / entries the GPU grammar rejected
+        std::vector<int> st_host;
         std::vector<size_t> which;
+        if (host_parser) {
+            std::vector<CanonicalChain> chains(n);
+            std::vector<int> flag(n, 0);
+#pragma omp parallel for schedule(dynamic, 8)
+            for (size_t c = 0; c < n; c++)
+                flag[c] = parsePdbChain(rd.data(i0 + c), rd.payload(i0 + c), strip_ext(rd.name(i0 + c)), chains[c]);
+            std::vector<CanonicalChain> good;
+            for (size_t c = 0; c < n; c++) {
+                s.entries++;
+                s.bytes_in += rd.length(i0 + c);
+                if (flag[c] == 0) { good.push_back(std::move(chains[c])); which.push_back(c); }
+                else s.failed++;
+            }
+            const double g0 = now_s();
+            rc = FoldcompGpu::compressBatch(eng, good, anchorThreshold, blobs_host, st_host);
+            s.seconds_engine += now_s() - g0;
+            if (rc) return rc;
+            for (size_t g = 0; g < good.size(); g++) {
+                if (st_host[g] != FCZ_OK) { s.failed++; continue; }
+                s.residues += good[g].res_type.size();
+                s.bytes_out += blobs_host[g].size();
+                const size_t c = which[g];
+                if (!wr.append(blobs_host[g].data(), blobs_host[g].size(), rd.key(i0 + c), strip_ext(rd.name(i0 + c)) + ".fcz")) return FCZ_E_ARG;
+            }
+            i0 = i1;
+            continue;
+        }
+        // ---- GPU parser: texts and titles tightly concatenated
+        std::vector<uint64_t> text_off(n + 1, 0), blob_off(n + 1, 0);
+        std::vector<uint32_t> title_off(n + 1, 0);
+        std::vector<std::string> names(n);
+        std::string titles;
+        for (size_t c = 0; c < n; c++) {
+            text_off[c + 1] = text_off[c] + rd.payload(i0 + c);
+            names[c] = strip_ext(rd.name(i0 + c));
+            titles += names[c];
+            title_off[c + 1] = (uint32_t)titles.size();
+        }
+        if (text_off[n] + 16 > pin_text_cap) {
+            if (pin_text) fcz_host_free(pin_text);
+            pin_text_cap = text_off[n] + text_off[n] / 8 + 4096;
+            pin_text = (char*)fcz_host_alloc(pin_text_cap);
+            if (!pin_text) return FCZ_E_CUDA;
+        }
+        const uint64_t blob_cap = text_off[n] / 16 + 512 * n + titles.size() + 4096;  // FCZ is ~1/40 of its text; retried when short
+        if (blob_cap > pin_blob_cap) {
+            if (pin_blob) fcz_host_free(pin_blob);
+            pin_blob_cap = blob_cap + blob_cap / 8;
+            pin_blob = (uint8_t*)fcz_host_alloc(pin_blob_cap);
+            if (!pin_blob) return FCZ_E_CUDA;
+        }
+#pragma omp parallel for schedule(static)
+        for (size_t c = 0; c < n; c++) memcpy(pin_text + text_off[c], rd.data(i0 + c), text_off[c + 1] - text_off[c]);
+        std::vector<int32_t> status(n + 1, 0);
+        fcz_text_batch in{};
+        in.n_chains = (uint32_t)n; in.mem = FCZ_MEM_HOST; in.text_off = text_off.data(); in.bytes = pin_text; in.bytes_cap = text_off[n];
+        fcz_blob_batch out{};
+        out.n_chains = (uint32_t)n; out.mem = FCZ_MEM_HOST; out.blob_off = blob_off.data(); out.bytes = pin_blob; out.bytes_cap = pin_blob_cap;
+        out.status = status.data();
+        uint64_t total = 0;
+        const double g0 = now_s();
+        rc = fcz_encode_pdb_text_batch(eng.get(), &in, title_off.data(), titles.data(), &out, &total);
+        if (rc == FCZ_E_CAPACITY) {
+            fcz_host_free(pin_blob);
+            pin_blob_cap = total + 4096;
+            pin_blob = (uint8_t*)fcz_host_alloc(pin_blob_cap);
+            if (!pin_blob) return FCZ_E_CUDA;
+            out.bytes = pin_blob; out.bytes_cap = pin_blob_cap;
+            rc = fcz_encode_pdb_text_batch(eng.get(), &in, title_off.data(), titles.data(), &out, &total);
+        }
+        s.seconds_engine += now_s() - g0;
+        if (rc) return rc;
+        // entries with a numeric field outside the GPU grammar (exponents, hex floats: no PDB writer emits them) take the
+        // host parser, which goes through strtof
+        std::vector<CanonicalChain> odd;
+        for (size_t c = 0; c < n; c++) {
+            if (status[c] != FCZ_E_PARSE_NUMBER) continue;
+            CanonicalChain ch;
+            if (parsePdbChain(rd.data(i0 + c), rd.payload(i0 + c), names[c], ch) == 0) { odd.push_back(std::move(ch)); which.push_back(c); }
+        }
+        if (!odd.empty() && (rc = FoldcompGpu::compressBatch(eng, odd, anchorThreshold, blobs_host, st_host))) return rc;
+        size_t w = 0;
         for (size_t c = 0; c < n; c++) {
             s.entries++;
             s.bytes_in += rd.length(i0 + c);
-            if (flag[c] == 0) { good.push_back(std::move(chains[c])); which.push_back(c); }
-            else s.failed++;
-        }
-        std::vector<std::string> blobs;
-        std::vector<int> st;
-        const double g0 = now_s();
-        int rc = FoldcompGpu::compressBatch(eng, good, anchorThreshold, blobs, st);
-        s.seconds_engine += now_s() - g0;
-        if (rc) return rc;
-        for (size_t g = 0; g < good.size(); g++) {
-            if (st[g] != FCZ_OK) { s.failed++; continue; }
-            s.residues += good[g].res_type.size();
-            s.bytes_out += blobs[g].size();
-            const size_t c = which[g];
-            if (!wr.append(blobs[g].data(), blobs[g].size(), rd.key(i0 + c), strip_ext(rd.name(i0 + c)) + ".fcz")) return FCZ_E_ARG;
+            const char* data = (const char*)pin_blob + blob_off[c];
+            size_t len = (size_t)(blob_off[c + 1] - blob_off[c]);
+            int32_t stc = status[c];
+            if (w < which.size() && which[w] == c) { data = blobs_host[w].data(); len = blobs_host[w].size(); stc = st_host[w]; w++; }
+            if (stc != FCZ_OK || len < 6) { s.failed++; continue; }
+            s.residues += (uint64_t)(uint8_t)data[4] | (uint64_t)(uint8_t)data[5] << 8;  // CompressedFileHeader.nResidue
+            s.bytes_out += len;
+            if (!wr.append(data, len, rd.key(i0 + c), names[c] + ".fcz")) return FCZ_E_ARG;
         }
         i0 = i1;
     }

@@ -1668,6 +1668,14 @@ uint64_t fcz_encode_bound(uint64_t n_chains, uint64_t n_res, uint64_t n_atoms, u
     return 98ull * n_chains + 40ull * (n_res / (uint64_t)b + 2ull * n_chains) + n_title_bytes + 6ull * n_res + n_atoms;  // 97 + a terminator
 }
 
+void* fcz_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void fcz_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int fcz_engine_sync(fcz_engine* e) {
     if (!e) return FCZ_E_ARG;
     CK(cudaStreamSynchronize(e->stream));

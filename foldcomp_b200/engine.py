@@ -328,6 +328,41 @@ class Engine:
         self._check(self.lib.fcz_extract_batch(self.h, C.byref(sin), int(type_), int(digits), C.byref(so), C.byref(total)))
         return out
 
+    # ------------------------------------------------------------------ PDB text in
+    def parse_pdb_device(self, texts: "DeviceTextBatch") -> DeviceChainBatch:
+        """Single-chain PDB texts on the GPU -> canonical chains on the GPU (fcz_parse_pdb_plan + fcz_parse_pdb_batch: the
+        ATOM parser of foldcomp/foldcomp.cxx:253-293).  status[c] is 0 or FCZ_E_PARSE_*; titles are left empty."""
+        n = texts.n_chains
+        plan = DeviceChainBatch(n, 0, 0, 0, texts.bytes.device)
+        sin, sp = texts.as_struct(), plan.as_struct()
+        sizes = FczSizes()
+        self._check(self.lib.fcz_parse_pdb_plan(self.h, C.byref(sin), C.byref(sp), C.byref(sizes)))
+        out = DeviceChainBatch(n, int(sizes.n_res), int(sizes.n_atoms), 0, texts.bytes.device)
+        out.res_off, out.atom_off, out.status = plan.res_off, plan.atom_off, plan.status
+        so = out.as_struct()
+        self._check(self.lib.fcz_parse_pdb_batch(self.h, C.byref(sin), C.byref(so)))
+        return out
+
+    def encode_pdb_text_host(self, texts: HostTextBatch, titles) -> HostBlobBatch:
+        """PDB texts (host) -> FCZ blobs (host) in one call, parser and encoder on the GPU (what `foldcomp compress` does per
+        entry, src/main.cpp:438-536).  titles: one bytes object per entry.  out.status: parser or encoder status."""
+        n = texts.n_chains
+        title_off = np.zeros(n + 1, np.uint32)
+        title_off[1:] = np.cumsum([len(t) for t in titles], dtype=np.uint64).astype(np.uint32) if n else 0
+        tbytes = np.frombuffer(b"".join(titles) + b"\0", np.uint8).copy()
+        n_text = int(texts.text_off[-1]) if n else 0
+        # FCZ is about 1/40 of its PDB text (15.9 of 634 bytes per residue at -b 25); retry once with the exact size
+        out = HostBlobBatch.empty(n, n_text // 16 + 512 * n + int(title_off[-1]) + 1024)
+        total = C.c_uint64()
+        sin, so = texts.as_struct(), out.as_struct()
+        rc = self.lib.fcz_encode_pdb_text_batch(self.h, C.byref(sin), title_off.ctypes.data, tbytes.ctypes.data, C.byref(so), C.byref(total))
+        if rc == abi.FCZ_E_CAPACITY:
+            out = HostBlobBatch.empty(n, int(total.value) + 64)
+            so = out.as_struct()
+            rc = self.lib.fcz_encode_pdb_text_batch(self.h, C.byref(sin), title_off.ctypes.data, tbytes.ctypes.data, C.byref(so), C.byref(total))
+        self._check(rc)
+        return out
+
     def check_host(self, blobs: HostBlobBatch):
         """(read_status [n], validity [n]): Foldcomp::read + checkValidity for every blob (src/foldcomp.cpp:904-1036,
         1492-1532): read_status 0 / FCZ_E_MAGIC / FCZ_E_TRUNCATED, validity = ValidityError class 0..6 (abi.VALIDITY)."""

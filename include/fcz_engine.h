@@ -224,6 +224,12 @@ int fcz_encode_pdb_text_batch(fcz_engine* e, const fcz_text_batch* in, const uin
 int fcz_unpack_angles_batch(fcz_engine* e, const fcz_blob_batch* in, uint64_t* res_off, float* angles, uint64_t res_cap,
                             uint64_t* total_res);
 
+/* Page-locked host memory for the buffers of FCZ_MEM_HOST batches (cudaHostAlloc / cudaFreeHost): copies from and to such
+ * memory run at the full link rate and asynchronously; pageable memory works everywhere too, at roughly half the rate.
+ * For host code that does not link the CUDA runtime itself (foldcomp_b200/csrc/fcz_db.cpp, bindings in other languages). */
+void* fcz_host_alloc(size_t bytes);
+void fcz_host_free(void* p);
+
 /* Block until everything enqueued on the engine's stream has finished. */
 int fcz_engine_sync(fcz_engine* e);
 

@@ -49,13 +49,13 @@ def test_parser_model_matches_host_parser_on_written_text():
         assert got[0] == 0 and np.array_equal(got[1], batch.chain(c).res_type) and np.array_equal(got[3], batch.chain(c).xyz)
 
 
-def test_parser_model_on_messy_text(golden):
+def messy_variants(golden):
     """Other records between the atoms, CRLF, alternative positions, atoms out of table order, a missing atom, an
     unknown residue, a last atom that is not OXT, short B-factor column, no trailing newline."""
     base = pdbio.format_pdb(golden.batch.chain(golden.names.index("test_af.pdb")), 0)
     lines = base.splitlines()
     atoms = [l for l in lines if l.startswith("ATOM")]
-    variants = {
+    return {
         "plain": base,
         "crlf": base.replace("\n", "\r\n"),
         "no_final_newline": base.rstrip("\n"),
@@ -72,6 +72,10 @@ def test_parser_model_on_messy_text(golden):
         "empty": "",
         "short_record": "\n".join(atoms[:4] + [atoms[4][:40]] + atoms[5:]) + "\n",
     }
+
+
+def test_parser_model_on_messy_text(golden):
+    variants = messy_variants(golden)
     for name, text in variants.items():
         a, b = _emu_parse(text.encode()), _host_parse(text.encode())
         _same(a, b)

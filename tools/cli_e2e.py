@@ -56,11 +56,15 @@ if not args.skip_ours:
         blobs = eng.encode_host(hb)
     dbutil.write_db(P("fcz_db"), [(c, "syn_%07d" % c, blobs.blob(c)) for c in range(args.chains)])
     del g, hb
-    # 2. ours: FCZ db -> PDB-text db (GPU decode + text emitter), then PDB-text db -> FCZ db (host parser + GPU encode)
+    # 2. ours: FCZ db -> PDB-text db (GPU decode + text emitter), then PDB-text db -> FCZ db (GPU parser + GPU encode)
     dt, r = timed([OURS, "decompress-db", P("fcz_db"), P("pdb_db")])
     out["ours_decompress_db"] = {"seconds": dt, "residues_per_s": args.chains * L / dt, "stderr": r.stderr.strip()[-200:]}
     dt, r = timed([OURS, "compress-db", P("pdb_db"), P("fcz_db_ours")])
     out["ours_compress_db"] = {"seconds": dt, "residues_per_s": args.chains * L / dt, "stderr": r.stderr.strip()[-200:]}
+    os.environ["FCZ_HOST_PARSER"] = "1"  # A/B: the per-entry host parser (OpenMP) instead of the GPU parser
+    dt, r = timed([OURS, "compress-db", P("pdb_db"), P("fcz_db_ours_hostparse")])
+    del os.environ["FCZ_HOST_PARSER"]
+    out["ours_compress_db_host_parser"] = {"seconds": dt, "residues_per_s": args.chains * L / dt, "stderr": r.stderr.strip()[-200:]}
     out["pdb_text_db_bytes"] = db_bytes(P("pdb_db"))
     out["fcz_db_bytes"] = db_bytes(P("fcz_db"))
 # 3. the reference CLI on the same two databases, all host threads
