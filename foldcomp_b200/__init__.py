@@ -6,7 +6,7 @@ The Python surface mirrors the reference's CPython module for this path
     compress(name, pdb_content, *, anchor_residue_threshold=25) -> bytes     (foldcomp.cxx:295-328)
     decompress(fcz_bytes) -> (name, pdb_str)                                 (foldcomp.cxx:222-239)
     open(path, *, ids=None, decompress=True, err_on_missing=False)           (foldcomp.cxx:333-433) -> FoldcompDatabase
-    get_data(fcz_bytes) -> dict                                              (foldcomp.cxx:497-640; FCZ input only)
+    get_data(fcz_bytes | pdb_text) -> dict                                   (foldcomp.cxx:497-671)
 
 Both go through the CUDA engine (include/fcz_engine.h); text parsing/formatting is host code
 (pdbio.py).  Batch entry points live in `engine.Engine`.  There is no CPU fallback.
@@ -82,16 +82,41 @@ def decompress(fcz: bytes):
     return data[t0 : t0 + tl].decode("latin-1"), out.text(0).decode("latin-1")
 
 
+def _get_data_from_pdb(text: str):
+    """getDataFromPDB (foldcomp/foldcomp.cxx:633-671): every ATOM record goes in (no chain check, alternative positions
+    kept), Foldcomp::compress runs, and the dict holds the angles BEFORE quantisation plus the input coordinates."""
+    from .pdbio import PdbError, _atom_records, canonicalize
+    from .tables import NAME1
+
+    try:
+        recs = _atom_records(text, one_chain=False, dedup_alt=False)
+    except PdbError as e:
+        raise ValueError(str(e) + " in PDB file") from None
+    batch = canonicalize(recs, "")
+    eng = _get_engine()
+    ang = eng.backbone_angles_host(batch)  # k_raw_angles: the encoder's own arithmetic, before quantisation
+    L = len(ang)
+    tors = ang[: L - 1, :3].reshape(-1)
+    bond = ang[:, 3:].reshape(-1)[1 : 3 * L - 1]
+    return {
+        "phi": [float(v) for v in tors[2::3]], "psi": [float(v) for v in tors[0::3]], "omega": [float(v) for v in tors[1::3]],
+        "torsion_angles": [float(v) for v in tors], "bond_angles": [float(v) for v in bond],
+        "residues": "".join(NAME1[int(c)] for c in batch.res_type),
+        "b_factors": [float(v) for v in batch.bfactor],
+        "coordinates": [(float(r[5]), float(r[6]), float(r[7])) for r in recs],
+    }
+
+
 def get_data(input):  # noqa: A002 - the reference's parameter name
-    """foldcomp.get_data(fcz_bytes) -> dict with phi, psi, omega, torsion_angles, bond_angles, residues, b_factors,
-    coordinates (foldcomp/foldcomp.cxx:497-640, getDataFromFCZ): the continuised angles of the blob and its decoded
-    coordinates, both from the GPU engine.  PDB text input (the reference then runs its CPU encoder and returns the
-    angles before quantisation) is not supported: compress() it first."""
+    """foldcomp.get_data(input) -> dict with phi, psi, omega, torsion_angles, bond_angles, residues, b_factors,
+    coordinates (foldcomp/foldcomp.cxx:497-640).  FCZ bytes: the continuised angles of the blob and its decoded
+    coordinates (getDataFromFCZ); PDB text: the encoder's angles before quantisation and the input coordinates
+    (getDataFromPDB, 633-671).  Both from the GPU engine."""
     data = input.encode("latin-1") if isinstance(input, str) else bytes(input)
     if len(data) == 0:
         raise ValueError("Input is empty")
     if data[:4] != b"FCMP":
-        raise ValueError("Input is not a FCZ file (foldcomp_b200.get_data takes FCZ bytes; compress() PDB text first)")
+        return _get_data_from_pdb(data.decode("latin-1"))
     from .tables import NAME1
 
     eng = _get_engine()

@@ -33,6 +33,7 @@ SYMBOLS = [
     "fcz_parse_pdb_batch",
     "fcz_encode_pdb_text_batch",
     "fcz_unpack_angles_batch",
+    "fcz_backbone_angles_batch",
     "fcz_host_alloc",
     "fcz_host_free",
     "fcz_engine_sync",
@@ -99,6 +100,8 @@ def load() -> C.CDLL:
     lib.fcz_encode_pdb_text_batch.argtypes = [C.c_void_p, P(abi.FczTextBatch), C.c_void_p, C.c_void_p, P(abi.FczBlobBatch), P(C.c_uint64)]
     lib.fcz_unpack_angles_batch.restype = C.c_int
     lib.fcz_unpack_angles_batch.argtypes = [C.c_void_p, P(abi.FczBlobBatch), C.c_void_p, C.c_void_p, C.c_uint64, P(C.c_uint64)]
+    lib.fcz_backbone_angles_batch.restype = C.c_int
+    lib.fcz_backbone_angles_batch.argtypes = [C.c_void_p, P(abi.FczChainBatch), C.c_void_p]
     lib.fcz_host_alloc.restype = C.c_void_p
     lib.fcz_host_alloc.argtypes = [C.c_size_t]
     lib.fcz_host_free.restype = None

@@ -250,11 +250,8 @@ FCZ_HD void bb_item_atoms(const EncChain& ch, uint32_t r, uint32_t k, f3& p0, f3
     p0 = ld3(ch.X + 3u * i0); p1 = ld3(ch.X + 3u * i1); p2 = ld3(ch.X + 3u * i2); p3 = ld3(ch.X + 3u * i3);
 }
 FCZ_HD uint32_t bb_array_k(uint32_t a) { return (a == A_PSI || a == A_CACN) ? 0u : ((a == A_OMEGA || a == A_CNCA) ? 1u : 2u); }
-static FCZ_HD_SLOW float bb_value_exact(const EncChain& ch, uint32_t a, uint32_t r) {
-    const uint32_t k = bb_array_k(a);
-    const bool is_tor = a < 3u;
-    f3 p0, p1, p2, p3;
-    bb_item_atoms(ch, r, k, p0, p1, p2, p3);
+// torsion over p0..p3 (is_tor) or bond angle at p2 over p1, p2, p3, by the reference's exact sequence
+static FCZ_HD_SLOW float bb_value_of_atoms(bool is_tor, f3 p0, f3 p1, f3 p2, f3 p3) {
     const f3 d2 = sub3(p2, p1), d3 = sub3(p3, p2);
     f3 v1, v2;
     bool neg = false;
@@ -272,6 +269,39 @@ static FCZ_HD_SLOW float bb_value_exact(const EncChain& ch, uint32_t a, uint32_t
     float deg;
     if (!acos_deg_certified(c, &deg)) deg = angle_deg_slow(c, is_tor);  // ~2e-6 of items, and |c| > 1
     return (is_tor && neg) ? -deg : deg;
+}
+static FCZ_HD_SLOW float bb_value_exact(const EncChain& ch, uint32_t a, uint32_t r) {
+    f3 p0, p1, p2, p3;
+    bb_item_atoms(ch, r, bb_array_k(a), p0, p1, p2, p3);
+    return bb_value_of_atoms(a < 3u, p0, p1, p2, p3);
+}
+
+// Backbone angles of one chain BEFORE quantisation, six floats per residue r: the torsions over backbone atoms 3r+j ..
+// 3r+j+3 (psi_r, omega_r, phi_r+1; zero for the last residue) and the bond angles at backbone atoms 3r, 3r+1, 3r+2 (zero
+// at the chain's first and last atom) -- Foldcomp::preprocess's backboneTorsionAngles (getTorsionFromXYZ,
+// src/torsion_angle.cpp:46-96) and backboneBondAngles (Nerf::getBondAngles, src/nerf.cpp:495-508), src/foldcomp.cpp:484-496;
+// what the CPython get_data(pdb_text) returns (foldcomp/foldcomp.cxx:633-671).  ch needs L, X and aoff.
+template <class Ctx>
+FCZ_HD void enc_raw_angles(Ctx& cx, const EncChain& ch, float* out) {
+    const uint32_t L = ch.L;
+    for (uint32_t e = (uint32_t)cx.tid; e < 6u * L; e += (uint32_t)cx.nthr) {
+        const uint32_t r = e / 6u, j = e - 6u * r;
+        float v = 0.0f;
+        if (j < 3u) {
+            if (r + 1u < L) v = bb_value_exact(ch, j == 0u ? A_PSI : (j == 1u ? A_OMEGA : A_PHI), r);
+        } else {
+            const uint32_t m = 3u * r + (j - 3u);  // backbone atom the angle sits at
+            if (m == 1u) {
+                const uint32_t a0 = ch.aoff[0];
+                const f3 z = {0.f, 0.f, 0.f};
+                v = bb_value_of_atoms(false, z, ld3(ch.X + 3u * a0), ld3(ch.X + 3u * (a0 + 1u)), ld3(ch.X + 3u * (a0 + 2u)));
+            } else if (m >= 2u && m + 1u < 3u * L) {
+                const uint32_t k = (m - 2u) % 3u;
+                v = bb_value_exact(ch, k == 0u ? A_CACN : (k == 1u ? A_CNCA : A_NCAC), (m - 2u) / 3u);
+            }
+        }
+        out[e] = v;
+    }
 }
 
 // q = floor(t + 0.5) as the reference's (unsigned)((double)t + 0.5) gives it for 0 <= t < 2^23, in exact float steps

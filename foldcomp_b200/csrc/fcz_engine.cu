@@ -1223,6 +1223,41 @@ __global__ void __launch_bounds__(128) k_unpack_angles(AnglesArgs a) {
     }
 }
 
+// Backbone angles before quantisation (enc_raw_angles): block per chain; the residue -> atom offsets are scanned into a
+// global workspace first (any chain length), then one thread per value.
+struct RawAnglesArgs {
+    const uint32_t* res_off;
+    const uint64_t* atom_off;
+    const uint8_t* res_type;
+    const float* xyz;
+    const Tables* tables;
+    uint32_t* aoff;   // [n_res + n] workspace
+    float* angles;    // [6 * n_res]
+    uint32_t n;
+};
+__global__ void __launch_bounds__(128) k_raw_angles(RawAnglesArgs a) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t c = blockIdx.x;
+    DevCtx cx = block_ctx(wsum);
+    const uint32_t r0 = a.res_off[c], L = a.res_off[c + 1] - r0;
+    if (L == 0u) return;
+    uint32_t* aoff = a.aoff + r0 + c;
+    const uint8_t* type = a.res_type + r0;
+    const uint32_t chunk = (L + blockDim.x - 1u) / blockDim.x;
+    uint32_t b0 = threadIdx.x * chunk; if (b0 > L) b0 = L;
+    uint32_t b1 = b0 + chunk; if (b1 > L) b1 = L;
+    uint32_t sum = 0;
+    for (uint32_t r = b0; r < b1; r++) sum += a.tables->natoms[type[r] & 31u];
+    uint32_t base = cx.excl_scan(sum);
+    for (uint32_t r = b0; r < b1; r++) { aoff[r] = base; base += a.tables->natoms[type[r] & 31u]; }
+    if (b1 == L && b0 < L) aoff[L] = base;
+    __syncthreads();
+    EncChain ch;
+    memset(&ch, 0, sizeof ch);
+    ch.L = L; ch.X = a.xyz + 3ull * a.atom_off[c]; ch.aoff = aoff; ch.type = type;
+    enc_raw_angles(cx, ch, a.angles + 6ull * r0);
+}
+
 // ============================================================================================ PDB text in
 // fcz_parse.h on the GPU: k_parse_lines counts the lines of every entry (sizes the workspace), k_parse_plan (block per
 // entry) finds and parses the ATOM records, drops alternative positions and splits residues, k_parse_emit (block per
@@ -2892,6 +2927,40 @@ extern "C" int fcz_unpack_angles_batch(fcz_engine* e, const fcz_blob_batch* in, 
     if (host) {
         CK(cudaMemcpyAsync(res_off, d_res_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, e->stream));
         if (total) CK(cudaMemcpyAsync(angles, e->d_text.p, 24ull * total, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return FCZ_OK;
+}
+
+// ---------------------------------------------------------------------------------- backbone angles before quantisation
+extern "C" int fcz_backbone_angles_batch(fcz_engine* e, const fcz_chain_batch* in, float* angles) {
+    if (!e || !in || !angles) return FCZ_E_ARG;
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = in->n_chains;
+    int rc;
+    DevChains d;
+    const bool host = in->mem == FCZ_MEM_HOST;
+    uint64_t n_res = in->res_cap;
+    if (host) {
+        n_res = in->res_off[n];
+        H2D(e->d_res_off, in->res_off, 4ull * (n + 1));
+        H2D(e->d_atom_off, in->atom_off, 8ull * (n + 1));
+        H2D(e->d_res_type, in->res_type, n_res);
+        H2D(e->d_xyz, in->xyz, 12ull * in->atom_off[n]);
+        d = staged_chains(e);
+        if ((rc = ensure(e, e->d_text, 24ull * n_res + 64))) return rc;
+    } else if ((rc = upload_chains(e, in, &d))) return rc;
+    if ((rc = ensure(e, e->ws_aoff, 4ull * (n_res + n + 1)))) return rc;
+    RawAnglesArgs a;
+    a.res_off = d.res_off; a.atom_off = d.atom_off; a.res_type = d.res_type; a.xyz = d.xyz; a.tables = e->d_tables;
+    a.aoff = (uint32_t*)e->ws_aoff.p; a.angles = host ? (float*)e->d_text.p : angles; a.n = n;
+    if (n) {
+        k_raw_angles<<<n, 128, 0, e->stream>>>(a);
+        e->launches++;
+    }
+    CK(cudaGetLastError());
+    if (host) {
+        if (n_res) CK(cudaMemcpyAsync(angles, e->d_text.p, 24ull * n_res, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
     }
     return FCZ_OK;

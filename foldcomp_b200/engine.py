@@ -363,6 +363,14 @@ class Engine:
         self._check(rc)
         return out
 
+    def backbone_angles_host(self, chains: HostChainBatch) -> np.ndarray:
+        """[R, 6] per residue: psi, omega, next phi, then the bond angles at N, CA, C -- the encoder's angles before
+        quantisation (Foldcomp::preprocess, src/foldcomp.cpp:484-496), zero where the chain end leaves none."""
+        out = np.zeros((chains.n_res, 6), np.float32)
+        sin = chains.as_struct()
+        self._check(self.lib.fcz_backbone_angles_batch(self.h, C.byref(sin), out.ctypes.data))
+        return out
+
     def check_host(self, blobs: HostBlobBatch):
         """(read_status [n], validity [n]): Foldcomp::read + checkValidity for every blob (src/foldcomp.cpp:904-1036,
         1492-1532): read_status 0 / FCZ_E_MAGIC / FCZ_E_TRUNCATED, validity = ValidityError class 0..6 (abi.VALIDITY)."""

@@ -24,8 +24,9 @@ class PdbError(ValueError):
     pass
 
 
-def _atom_records(pdb_text: str):
-    """(atom, residue, chain, serial, resnum, x, y, z, bfac) for ATOM lines of ONE chain."""
+def _atom_records(pdb_text: str, one_chain: bool = True, dedup_alt: bool = True):
+    """(atom, residue, chain, serial, resnum, x, y, z, bfac) for ATOM lines of ONE chain (compress, foldcomp.cxx:253-293);
+    one_chain = dedup_alt = False is get_data's reading of a PDB text (getDataFromPDB, foldcomp.cxx:633-656)."""
     out = []
     chain = None
     for line in pdb_text.splitlines():
@@ -34,7 +35,7 @@ def _atom_records(pdb_text: str):
         ch = line[21:22]
         if chain is None:
             chain = ch
-        if ch != chain:
+        if one_chain and ch != chain:
             raise PdbError("Multiple chains found")  # foldcomp.cxx:266-268 (flag 2)
         # a short line or a blank / non-numeric fixed-column field is flag 3 of the C++ parser (parsePdbChain,
         # foldcomp_b200/csrc/fcz_db.cpp: n < 22, n < 61, failed numeric field): the same error here
@@ -57,6 +58,8 @@ def _atom_records(pdb_text: str):
         out.append(rec)
     if not out:
         raise PdbError("No ATOM lines found")  # foldcomp.cxx:288-290 (flag 1)
+    if not dedup_alt:
+        return out
     # removeAlternativePosition: drop an atom whose name equals its predecessor's
     dedup = [out[0]]
     for rec in out[1:]:

@@ -224,6 +224,15 @@ int fcz_encode_pdb_text_batch(fcz_engine* e, const fcz_text_batch* in, const uin
 int fcz_unpack_angles_batch(fcz_engine* e, const fcz_blob_batch* in, uint64_t* res_off, float* angles, uint64_t res_cap,
                             uint64_t* total_res);
 
+/* Backbone angles BEFORE quantisation, six floats per residue r of every chain: the torsions over backbone atoms 3r+j ..
+ * 3r+j+3, j = 0..2 (psi_r, omega_r, phi_r+1; zero for a chain's last residue), then the bond angles at backbone atoms 3r,
+ * 3r+1, 3r+2 (zero at a chain's first and last atom) -- what Foldcomp::preprocess leaves in backboneTorsionAngles
+ * (getTorsionFromXYZ, src/torsion_angle.cpp:46-96) and backboneBondAngles (Nerf::getBondAngles, src/nerf.cpp:495-508) at
+ * src/foldcomp.cpp:484-496, bit for bit; the CPython get_data(pdb_text) returns them (foldcomp/foldcomp.cxx:633-671).
+ * `angles` [6 * n_res] lives in the memory space of `in`; a residue code outside the table reads as UNK has no atoms:
+ * chains must have passed an encode (or come from the parser).  Device batches need in->res_cap >= n_res. */
+int fcz_backbone_angles_batch(fcz_engine* e, const fcz_chain_batch* in, float* angles);
+
 /* Page-locked host memory for the buffers of FCZ_MEM_HOST batches (cudaHostAlloc / cudaFreeHost): copies from and to such
  * memory run at the full link rate and asynchronously; pageable memory works everywhere too, at roughly half the rate.
  * For host code that does not link the CUDA runtime itself (foldcomp_b200/csrc/fcz_db.cpp, bindings in other languages). */

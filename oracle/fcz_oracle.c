@@ -164,6 +164,32 @@ static int char_to_code(int ch) {
     return FCZ_CODE_UNK;
 }
 
+/* ------------------------------------------------------------------- backbone angles before quantisation */
+/* What Foldcomp::preprocess leaves in backboneTorsionAngles (getTorsionFromXYZ over the backbone, src/torsion_angle.cpp:
+ * 46-96; src/foldcomp.cpp:484-485) and backboneBondAngles (Nerf::getBondAngles, src/nerf.cpp:495-508; src/foldcomp.cpp:494-
+ * 495), the lists the CPython get_data(pdb_text) returns (foldcomp/foldcomp.cxx:633-671), re-cut per residue r as six
+ * floats: torsions 3r, 3r+1, 3r+2 of the list (zero for the last residue), then the bond angles AT backbone atoms 3r,
+ * 3r+1, 3r+2 (list index atom-1; zero at the chain's first and last atom).  Pinned to the reference's get_data() by
+ * tests/test_oracle.py (oracle/_ref/pyref) and tests/golden/getdata_golden.npz. */
+int fcz_oracle_backbone_angles(const uint8_t* res_type, uint32_t L, const float* xyz, float* out) {
+    const f3* at = (const f3*)xyz;
+    if (L < 1) return FCZ_E_LIMIT;
+    f3* bb = (f3*)malloc(sizeof(f3) * 3 * L);
+    uint64_t a = 0;
+    for (uint32_t r = 0; r < L; r++) {
+        int c = res_type[r];
+        if (c >= FCZ_NUM_CODES || FCZ_NATOMS[c] == 0) { free(bb); return FCZ_E_RESIDUE; }
+        for (int k = 0; k < 3; k++) bb[3 * r + k] = at[a + k];
+        a += FCZ_NATOMS[c];
+    }
+    const uint32_t n = 3 * L;
+    for (uint32_t e = 0; e < 6 * L; e++) out[e] = 0.0f;
+    for (uint32_t i = 0; i + 3 < n; i++) out[6 * (i / 3) + i % 3] = dihedral(bb[i], bb[i + 1], bb[i + 2], bb[i + 3]);
+    for (uint32_t m = 1; m + 1 < n; m++) out[6 * (m / 3) + 3 + m % 3] = angle3(bb[m - 1], bb[m], bb[m + 1]);
+    free(bb);
+    return 0;
+}
+
 /* ---------------------------------------------------------------------------------------- encode */
 
 int64_t fcz_oracle_encode_chain(const uint8_t* res_type, uint32_t L, const float* xyz,

@@ -54,6 +54,8 @@ int64_t fcz_oracle_extract(const uint8_t* blob, uint64_t len, int type, int digi
 /* Continuised angles of every residue record, 6 floats each (phi, psi, omega, N-CA-C, CA-C-N, C-N-CA):
  * decompressBackboneChain, src/foldcomp.cpp:122-153.  Returns the residue count or a negative code. */
 int64_t fcz_oracle_unpack_angles(const uint8_t* blob, uint64_t len, float* out);
+/* backbone angles before quantisation, out[6 * L] (see fcz_oracle.c) */
+int fcz_oracle_backbone_angles(const uint8_t* res_type, uint32_t L, const float* xyz, float* out);
 
 /* Foldcomp::read + checkValidity (src/foldcomp.cpp:904-1036, 1492-1532): returns the read status, *validity = the
  * ValidityError class (src/foldcomp.h:59-67). */

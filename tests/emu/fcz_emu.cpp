@@ -283,3 +283,15 @@ extern "C" uint64_t emu_parse_float_check(const char* fields, uint32_t w, uint64
     *rejected = rej;
     return bad;
 }
+
+// enc_raw_angles (the body of k_raw_angles) on one host thread
+extern "C" int emu_backbone_angles(const uint8_t* res_type, uint32_t L, const float* xyz, float* out) {
+    std::vector<uint32_t> aoff(L + 1, 0);
+    for (uint32_t r = 0; r < L; r++) aoff[r + 1] = aoff[r] + (uint32_t)FCZ_NATOMS[res_type[r] < FCZ_NUM_CODES ? res_type[r] : FCZ_CODE_UNK];
+    EncChain ch;
+    memset(&ch, 0, sizeof ch);
+    ch.L = L; ch.X = xyz; ch.aoff = aoff.data(); ch.type = res_type;
+    HostCtx cx;
+    enc_raw_angles(cx, ch, out);
+    return 0;
+}

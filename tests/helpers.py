@@ -460,6 +460,38 @@ def oracle_unpack_angles(blob: bytes) -> np.ndarray:
     return out
 
 
+def oracle_backbone_angles(b: HostChainBatch, c: int = 0) -> np.ndarray:
+    """[L, 6] per residue: psi, omega, next phi, bond angles at N, CA, C -- before quantisation (src/foldcomp.cpp:484-496)."""
+    lib = oracle()
+    lib.fcz_oracle_backbone_angles.restype = C.c_int
+    lib.fcz_oracle_backbone_angles.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    r0, r1, a0, a1 = int(b.res_off[c]), int(b.res_off[c + 1]), int(b.atom_off[c]), int(b.atom_off[c + 1])
+    rt, xyz = np.ascontiguousarray(b.res_type[r0:r1]), np.ascontiguousarray(b.xyz[a0:a1])
+    out = np.zeros((r1 - r0, 6), np.float32)
+    rc = lib.fcz_oracle_backbone_angles(rt.ctypes.data, r1 - r0, xyz.ctypes.data, out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+def emu_backbone_angles(b: HostChainBatch, c: int = 0) -> np.ndarray:
+    lib = emu()
+    lib.emu_backbone_angles.restype = C.c_int
+    lib.emu_backbone_angles.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    r0, r1, a0, a1 = int(b.res_off[c]), int(b.res_off[c + 1]), int(b.atom_off[c]), int(b.atom_off[c + 1])
+    rt, xyz = np.ascontiguousarray(b.res_type[r0:r1]), np.ascontiguousarray(b.xyz[a0:a1])
+    out = np.zeros((r1 - r0, 6), np.float32)
+    assert lib.emu_backbone_angles(rt.ctypes.data, r1 - r0, xyz.ctypes.data, out.ctypes.data) == 0
+    return out
+
+
+def get_data_lists(ang: np.ndarray):
+    """(torsion_angles, bond_angles, phi, psi, omega) as the reference's get_data(pdb_text) lists them, from the [L, 6] layout."""
+    L = len(ang)
+    tors = ang[: L - 1, :3].reshape(-1)
+    bond = ang[:, 3:].reshape(-1)[1 : 3 * L - 1]
+    return tors, bond, tors[2::3], tors[0::3], tors[1::3]
+
+
 # --------------------------------------------------------------------------- degenerate inputs (shared generator)
 
 

@@ -80,8 +80,9 @@ if not args.skip_ours:
     # same answers: the FCZ databases hold the same blobs (padding bytes masked), the text databases the same entries
     import helpers as H
 
-    a = {n: b for _, n, b in dbutil.read_db(P("fcz_db_ours"))}
-    b = {n.replace(".pdb", ""): x for _, n, x in dbutil.read_db(P("fcz_db_ref"))}
+    stem = lambda n: n.split(".")[0]
+    a = {stem(n): b for _, n, b in dbutil.read_db(P("fcz_db_ours"))}
+    b = {stem(n): x for _, n, x in dbutil.read_db(P("fcz_db_ref"))}
     same = sum(1 for k in a if k in b and H.masked(a[k]) == H.masked(b[k]))
     out["compress_outputs_identical"] = f"{same} of {len(a)} entries (reference has {len(b)})"
     out["speedup_compress"] = out["ours_compress_db"]["residues_per_s"] / out["reference_compress_db"]["residues_per_s"]
