@@ -3,6 +3,9 @@
 // file <-> one .fcz file.  ATOM records are read with the fixed columns the reference's CPython module
 // uses (foldcomp/foldcomp.cxx:253-293) and written like writeAtomCoordinatesToPDB
 // (src/atom_coordinate.cpp:220-291).  Host text I/O only; the codec runs on the GPU.
+#include <unistd.h>
+
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,15 +61,18 @@ int main(int argc, char** argv) {
     if (ai + 2 > argc) return 2;
     const std::string in = argv[ai], out = argv[ai + 1];
     try {
+        const auto t_start = std::chrono::steady_clock::now();
         Engine eng(0);
         FoldcompGpu comp(eng);
+        const double init_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
         if (mode == "compress-db" || mode == "decompress-db") {  // whole foldcomp databases, batched over the engine (fcz_db.h)
             DbStats st;
             const int rc = mode == "compress-db" ? compressDb(eng, in, out, b, &st) : decompressDb(eng, in, out, alt, &st);
             if (rc) { fprintf(stderr, "[Error] %s: %s\n", mode.c_str(), fcz_strerror(rc)); return 1; }
-            fprintf(stderr, "%zu entries (%zu failed), %llu residues, %.3f s total, %.3f s in the engine\n", st.entries, st.failed,
-                    (unsigned long long)st.residues, st.seconds, st.seconds_engine);
-            return 0;
+            fprintf(stderr, "%zu entries (%zu failed), %llu residues, %.3f s total, %.3f s in the engine, %.3f s CUDA context + engine start\n",
+                    st.entries, st.failed, (unsigned long long)st.residues, st.seconds, st.seconds_engine, init_s);
+            fflush(nullptr);
+            _exit(0);  // the outputs are closed: skip unmapping the inputs and tearing down the CUDA context
         }
         if (mode == "compress") {
             std::vector<AtomCoordinate> atoms;

@@ -7,6 +7,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <thread>
+#include <future>
+#include <cerrno>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -288,41 +291,94 @@ bool DbWriter::open(const std::string& path) { return open(path, path + ".index"
 bool DbWriter::open(const std::string& path, const std::string& index_path) {
     path_ = path;
     index_path_ = index_path;
-    data_ = fopen(path.c_str(), "wb");
-    if (!data_) return false;
+    fd_ = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd_ < 0) return false;
     FILE* t = fopen((path + ".dbtype").c_str(), "wb");
-    if (!t) { fclose(data_); data_ = nullptr; return false; }
+    if (!t) { ::close(fd_); fd_ = -1; return false; }
     const int type = 12;  // generic dbtype, src/database_writer.cpp:51-55
     const bool ok = fwrite(&type, sizeof type, 1, t) == 1;
-    if (fclose(t) != 0 || !ok) { fclose(data_); data_ = nullptr; return false; }
+    if (fclose(t) != 0 || !ok) { ::close(fd_); fd_ = -1; return false; }
     pos_ = 0;
+    buf_.clear();
+    buf_.reserve(4u << 20);
     return true;
 }
 
-bool DbWriter::append(const char* data, size_t len, uint32_t key, const std::string& name) {
-    if (!data_) return false;
-    if (len && fwrite(data, 1, len, data_) != len) return false;
-    const char nul = 0;
-    if (fwrite(&nul, 1, 1, data_) != 1) return false;
-    names_.push_back(name);
-    entries_.push_back({key, pos_, (uint64_t)len + 1, names_.size() - 1});
-    pos_ += len + 1;
+static bool pwrite_all(int fd, const char* p, size_t n, uint64_t at) {
+    while (n) {
+        const ssize_t w = ::pwrite(fd, p, n, (off_t)at);
+        if (w < 0) { if (errno == EINTR) continue; return false; }
+        p += w; n -= (size_t)w; at += (uint64_t)w;
+    }
     return true;
 }
 
-bool DbWriter::appendRaw(const char* data, size_t len, uint32_t key, const std::string& name) {
-    if (!data_) return false;
-    if (len && fwrite(data, 1, len, data_) != len) return false;
-    names_.push_back(name);
-    entries_.push_back({key, pos_, (uint64_t)len, names_.size() - 1});
+bool DbWriter::flush() {
+    if (buf_.empty()) return true;
+    const bool ok = pwrite_all(fd_, buf_.data(), buf_.size(), pos_ - buf_.size());
+    buf_.clear();
+    return ok;
+}
+
+bool DbWriter::put(const char* data, size_t len) {
+    if (len >= (1u << 20)) {  // large payloads go straight to the file
+        if (!flush() || !pwrite_all(fd_, data, len, pos_)) return false;
+        pos_ += len;
+        return true;
+    }
+    if (buf_.size() + len > (4u << 20) && !flush()) return false;
+    buf_.insert(buf_.end(), data, data + len);
     pos_ += len;
     return true;
 }
 
+bool DbWriter::append(const char* data, size_t len, uint32_t key, const std::string& name) {
+    if (fd_ < 0) return false;
+    const uint64_t at = pos_;
+    const char nul = 0;
+    if (!put(data, len) || !put(&nul, 1)) return false;
+    names_.push_back(name);
+    entries_.push_back({key, at, (uint64_t)len + 1, names_.size() - 1});
+    return true;
+}
+
+bool DbWriter::appendRaw(const char* data, size_t len, uint32_t key, const std::string& name) {
+    if (fd_ < 0) return false;
+    const uint64_t at = pos_;
+    if (!put(data, len)) return false;
+    names_.push_back(name);
+    entries_.push_back({key, at, (uint64_t)len, names_.size() - 1});
+    return true;
+}
+
+bool DbWriter::appendBatch(const char* base, const uint64_t* off, size_t n, const uint32_t* keys, const std::string* names, const uint8_t* skip) {
+    if (fd_ < 0 || !flush()) return false;
+    std::vector<uint64_t> at(n + 1);
+    at[0] = pos_;
+    for (size_t c = 0; c < n; c++) at[c + 1] = at[c] + ((skip && skip[c]) ? 0 : off[c + 1] - off[c] + 1);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(| : bad)
+    for (size_t c = 0; c < n; c++) {
+        if (skip && skip[c]) continue;
+        const size_t len = (size_t)(off[c + 1] - off[c]);
+        const char nul = 0;
+        if (!pwrite_all(fd_, base + off[c], len, at[c]) || !pwrite_all(fd_, &nul, 1, at[c] + len)) bad |= 1;
+    }
+    if (bad) return false;
+    for (size_t c = 0; c < n; c++) {
+        if (skip && skip[c]) continue;
+        names_.push_back(names[c]);
+        entries_.push_back({keys[c], at[c], at[c + 1] - at[c], names_.size() - 1});
+    }
+    pos_ = at[n];
+    return true;
+}
+
 bool DbWriter::close() {
-    if (!data_) return true;
-    bool ok = fclose(data_) == 0;  // a full disk shows up here at the latest: never report a truncated database as written
-    data_ = nullptr;
+    if (fd_ < 0) return true;
+    bool ok = flush();
+    ok &= ::close(fd_) == 0;  // a full disk shows up here at the latest: never report a truncated database as written
+    fd_ = -1;
     std::stable_sort(entries_.begin(), entries_.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
     FILE* idx = fopen(index_path_.c_str(), "w");
     FILE* lk = fopen((path_ + ".lookup").c_str(), "w");
@@ -353,6 +409,8 @@ static std::string strip_ext(const std::string& n) {
 }
 
 int decompressDb(Engine& eng, const std::string& in_db, const std::string& out_db, bool altOrder, DbStats* stats) {
+    // Per batch: blobs up, decode + text on the GPU, text back into one of two pinned buffers; while the GPU works on the
+    // next batch a writer thread puts the previous one into the data file with all host cores (DbWriter::appendBatch).
     const double t0 = now_s();
     DbReader rd;
     if (!rd.open(in_db)) return FCZ_E_ARG;
@@ -363,17 +421,29 @@ int decompressDb(Engine& eng, const std::string& in_db, const std::string& out_d
     int rc = fcz_engine_set_opts(eng.get(), &o);
     if (rc) return rc;
     const size_t n_all = rd.size();
-    const uint64_t kBatchBytes = 16ull << 20;  // ~16 MB of FCZ per engine call (~650 MB of text)
+    const uint64_t kBatchBytes = 8ull << 20;  // ~8 MB of FCZ per engine call (~330 MB of text)
+    struct Slot {
+        char* text = nullptr; uint64_t cap = 0;
+        std::vector<uint64_t> text_off;
+        std::vector<uint32_t> keys;
+        std::vector<std::string> names;
+        std::vector<uint8_t> skip;
+        std::thread writer;
+        bool ok = true;
+    } slot[2];
+    struct Free { Slot* s; ~Free() { for (int i = 0; i < 2; i++) { if (s[i].writer.joinable()) s[i].writer.join(); if (s[i].text) fcz_host_free(s[i].text); } } } guard{slot};
     std::vector<uint8_t> bytes;
-    std::vector<uint64_t> blob_off, text_off;
+    std::vector<uint64_t> blob_off;
     std::vector<int32_t> status;
-    std::vector<char> text;
     size_t i0 = 0;
-    while (i0 < n_all) {
+    for (int k = 0; i0 < n_all; k ^= 1) {
         size_t i1 = i0;
         uint64_t sum = 0;
         while (i1 < n_all && (i1 == i0 || sum + rd.length(i1) <= kBatchBytes)) sum += rd.length(i1++);
         const uint32_t n = (uint32_t)(i1 - i0);
+        Slot& sl = slot[k];
+        if (sl.writer.joinable()) sl.writer.join();  // the batch that used this buffer two rounds ago
+        if (!sl.ok) return FCZ_E_ARG;
         blob_off.assign(n + 1, 0);
         for (uint32_t c = 0; c < n; c++) blob_off[c + 1] = blob_off[c] + rd.length(i0 + c);
         // entries of one database usually lie back to back: hand the mapped file to the engine as it is
@@ -387,28 +457,43 @@ int decompressDb(Engine& eng, const std::string& in_db, const std::string& out_d
         }
         fcz_blob_batch in{};
         in.n_chains = n; in.mem = FCZ_MEM_HOST; in.blob_off = blob_off.data(); in.bytes = const_cast<uint8_t*>(src);
-        text_off.assign(n + 1, 0);
+        sl.text_off.assign(n + 1, 0);
         status.assign(n + 1, 0);
         fcz_text_batch out{};
-        out.n_chains = n; out.mem = FCZ_MEM_HOST; out.text_off = text_off.data(); out.status = status.data();
+        out.n_chains = n; out.mem = FCZ_MEM_HOST; out.text_off = sl.text_off.data(); out.status = status.data();
         uint64_t total = 0;
         const double g0 = now_s();
         if ((rc = fcz_decode_to_pdb_plan(eng.get(), &in, &out, &total))) return rc;
-        if (text.size() < total + 1) text.resize(total + 1);
-        out.bytes = text.data(); out.bytes_cap = text.size();
+        if (sl.cap < total + 1) {
+            if (sl.text) fcz_host_free(sl.text);
+            sl.cap = total + total / 8 + 4096;
+            sl.text = (char*)fcz_host_alloc(sl.cap);
+            if (!sl.text) return FCZ_E_CUDA;
+        }
+        out.bytes = sl.text; out.bytes_cap = sl.cap;
         if ((rc = fcz_decode_to_pdb_batch(eng.get(), &in, &out))) return rc;
         s.seconds_engine += now_s() - g0;
+        sl.keys.resize(n); sl.names.resize(n); sl.skip.assign(n, 0);
         for (uint32_t c = 0; c < n; c++) {
             s.entries++;
             s.bytes_in += rd.length(i0 + c);
-            if (status[c] != FCZ_OK) { s.failed++; continue; }
-            const uint64_t tl = text_off[c + 1] - text_off[c];
+            sl.keys[c] = rd.key(i0 + c);
+            sl.names[c] = strip_ext(rd.name(i0 + c)) + ".pdb";
+            if (status[c] != FCZ_OK) { s.failed++; sl.skip[c] = 1; continue; }
             const uint8_t* b = src + blob_off[c];
             s.residues += (uint64_t)b[4] | (uint64_t)b[5] << 8;  // CompressedFileHeader.nResidue
-            s.bytes_out += tl;
-            if (!wr.append(text.data() + text_off[c], tl, rd.key(i0 + c), strip_ext(rd.name(i0 + c)) + ".pdb")) return FCZ_E_ARG;
+            s.bytes_out += sl.text_off[c + 1] - sl.text_off[c];
         }
+        // batches are appended in order: the previous writer (other slot) must be done before this one starts
+        Slot& prev = slot[k ^ 1];
+        if (prev.writer.joinable()) prev.writer.join();
+        if (!prev.ok) return FCZ_E_ARG;
+        sl.writer = std::thread([&wr, &sl, n]() { sl.ok = wr.appendBatch(sl.text, sl.text_off.data(), n, sl.keys.data(), sl.names.data(), sl.skip.data()); });
         i0 = i1;
+    }
+    for (int k = 0; k < 2; k++) {
+        if (slot[k].writer.joinable()) slot[k].writer.join();
+        if (!slot[k].ok) return FCZ_E_ARG;
     }
     if (!wr.close()) return FCZ_E_ARG;
     s.seconds = now_s() - t0;
@@ -419,8 +504,8 @@ int decompressDb(Engine& eng, const std::string& in_db, const std::string& out_d
 int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db, int anchorThreshold, DbStats* stats) {
     // PDB text goes to the GPU as it is: the ATOM parser (fcz_parse.h, k_parse_*) and the encoder run there, only the FCZ
     // blobs (about 1/40 of the text) come back.  The host's share is one parallel copy of the mapped text into a pinned
-    // buffer -- without each entry's NUL terminator -- and the database writer.  FCZ_HOST_PARSER=1 restores the
-    // per-entry host parser (parsePdbChain under OpenMP) for A/B runs.
+    // buffer -- without each entry's NUL terminator; the copy of batch k+1 runs while the GPU works on batch k -- and
+    // the database writer.  FCZ_HOST_PARSER=1 restores the per-entry host parser (parsePdbChain under OpenMP) for A/B runs.
     const double t0 = now_s();
     DbReader rd;
     if (!rd.open(in_db)) return FCZ_E_ARG;
@@ -433,76 +518,106 @@ int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db,
     fcz_opts o{anchorThreshold, 0, nullptr, 0};
     int rc = fcz_engine_set_opts(eng.get(), &o);
     if (rc) return rc;
-    const uint64_t kBatchBytes = 512ull << 20;  // PDB text per engine call (~80 MB of coordinates)
-    char* pin_text = nullptr;
-    uint8_t* pin_blob = nullptr;
-    uint64_t pin_text_cap = 0, pin_blob_cap = 0;
-    struct Free { char*& a; uint8_t*& b; ~Free() { if (a) fcz_host_free(a); if (b) fcz_host_free(b); } } guard{pin_text, pin_blob};
-    size_t i0 = 0;
-    while (i0 < n_all) {
-        size_t i1 = i0;
-        uint64_t sum = 0;
-        while (i1 < n_all && (i1 == i0 || sum + rd.length(i1) <= kBatchBytes)) sum += rd.length(i1++);
-        const size_t n = i1 - i0;
-        std::vector<std::string> blobs_host;     // host-parser path / entries the GPU grammar rejected
-        std::vector<int> st_host;
-        std::vector<size_t> which;
-        if (host_parser) {
+    if (host_parser) {
+        const uint64_t kBatchBytes = 512ull << 20;  // PDB text per engine call (~80 MB of coordinates)
+        size_t i0 = 0;
+        while (i0 < n_all) {
+            size_t i1 = i0;
+            uint64_t sum = 0;
+            while (i1 < n_all && (i1 == i0 || sum + rd.length(i1) <= kBatchBytes)) sum += rd.length(i1++);
+            const size_t n = i1 - i0;
             std::vector<CanonicalChain> chains(n);
             std::vector<int> flag(n, 0);
 #pragma omp parallel for schedule(dynamic, 8)
             for (size_t c = 0; c < n; c++)
                 flag[c] = parsePdbChain(rd.data(i0 + c), rd.payload(i0 + c), strip_ext(rd.name(i0 + c)), chains[c]);
             std::vector<CanonicalChain> good;
+            std::vector<size_t> which;
             for (size_t c = 0; c < n; c++) {
                 s.entries++;
                 s.bytes_in += rd.length(i0 + c);
                 if (flag[c] == 0) { good.push_back(std::move(chains[c])); which.push_back(c); }
                 else s.failed++;
             }
+            std::vector<std::string> blobs;
+            std::vector<int> st;
             const double g0 = now_s();
-            rc = FoldcompGpu::compressBatch(eng, good, anchorThreshold, blobs_host, st_host);
+            rc = FoldcompGpu::compressBatch(eng, good, anchorThreshold, blobs, st);
             s.seconds_engine += now_s() - g0;
             if (rc) return rc;
             for (size_t g = 0; g < good.size(); g++) {
-                if (st_host[g] != FCZ_OK) { s.failed++; continue; }
+                if (st[g] != FCZ_OK) { s.failed++; continue; }
                 s.residues += good[g].res_type.size();
-                s.bytes_out += blobs_host[g].size();
+                s.bytes_out += blobs[g].size();
                 const size_t c = which[g];
-                if (!wr.append(blobs_host[g].data(), blobs_host[g].size(), rd.key(i0 + c), strip_ext(rd.name(i0 + c)) + ".fcz")) return FCZ_E_ARG;
+                if (!wr.append(blobs[g].data(), blobs[g].size(), rd.key(i0 + c), strip_ext(rd.name(i0 + c)) + ".fcz")) return FCZ_E_ARG;
             }
             i0 = i1;
-            continue;
         }
-        // ---- GPU parser: texts and titles tightly concatenated
-        std::vector<uint64_t> text_off(n + 1, 0), blob_off(n + 1, 0);
+        if (!wr.close()) return FCZ_E_ARG;
+        s.seconds = now_s() - t0;
+        if (stats) *stats = s;
+        return FCZ_OK;
+    }
+    // ---- GPU parser, two pinned text buffers
+    const uint64_t kBatchBytes = 256ull << 20;  // PDB text per engine call
+    struct Slot {
+        char* text = nullptr; uint64_t cap = 0;
+        size_t i0 = 0, i1 = 0;
+        std::vector<uint64_t> text_off;
+        std::thread copier;
+    } slot[2];
+    uint8_t* pin_blob = nullptr;
+    uint64_t pin_blob_cap = 0;
+    struct Free { Slot* s; uint8_t*& b; ~Free() { for (int i = 0; i < 2; i++) { if (s[i].copier.joinable()) s[i].copier.join(); if (s[i].text) fcz_host_free(s[i].text); } if (b) fcz_host_free(b); } } guard{slot, pin_blob};
+    // stage(k, i0): picks the entries of the batch that starts at i0, sizes the buffer, starts the copy; returns false on error
+    auto stage = [&](Slot& sl, size_t i0) -> bool {
+        size_t i1 = i0;
+        uint64_t sum = 0;
+        while (i1 < n_all && (i1 == i0 || sum + rd.length(i1) <= kBatchBytes)) sum += rd.length(i1++);
+        sl.i0 = i0; sl.i1 = i1;
+        const size_t n = i1 - i0;
+        sl.text_off.assign(n + 1, 0);
+        for (size_t c = 0; c < n; c++) sl.text_off[c + 1] = sl.text_off[c] + rd.payload(i0 + c);
+        if (sl.text_off[n] + 16 > sl.cap) {
+            if (sl.text) fcz_host_free(sl.text);
+            sl.cap = std::max<uint64_t>(sl.text_off[n] + sl.text_off[n] / 16 + 4096, kBatchBytes + (kBatchBytes >> 4));
+            sl.text = (char*)fcz_host_alloc(sl.cap);
+            if (!sl.text) return false;
+        }
+        sl.copier = std::thread([&rd, &sl, n]() {
+#pragma omp parallel for schedule(static)
+            for (size_t c = 0; c < n; c++) memcpy(sl.text + sl.text_off[c], rd.data(sl.i0 + c), sl.text_off[c + 1] - sl.text_off[c]);
+        });
+        return true;
+    };
+    if (n_all && !stage(slot[0], 0)) return FCZ_E_CUDA;
+    for (int k = 0; n_all && slot[k].i0 < n_all; k ^= 1) {
+        Slot& sl = slot[k];
+        sl.copier.join();
+        const size_t i0 = sl.i0, i1 = sl.i1, n = i1 - i0;
+        if (i1 < n_all) { if (!stage(slot[k ^ 1], i1)) return FCZ_E_CUDA; }
+        else slot[k ^ 1].i0 = n_all;
+        std::vector<uint64_t> blob_off(n + 1, 0);
         std::vector<uint32_t> title_off(n + 1, 0);
         std::vector<std::string> names(n);
         std::string titles;
         for (size_t c = 0; c < n; c++) {
-            text_off[c + 1] = text_off[c] + rd.payload(i0 + c);
             names[c] = strip_ext(rd.name(i0 + c));
             titles += names[c];
             title_off[c + 1] = (uint32_t)titles.size();
         }
-        if (text_off[n] + 16 > pin_text_cap) {
-            if (pin_text) fcz_host_free(pin_text);
-            pin_text_cap = text_off[n] + text_off[n] / 8 + 4096;
-            pin_text = (char*)fcz_host_alloc(pin_text_cap);
-            if (!pin_text) return FCZ_E_CUDA;
-        }
-        const uint64_t blob_cap = text_off[n] / 16 + 512 * n + titles.size() + 4096;  // FCZ is ~1/40 of its text; retried when short
+        const uint64_t n_text = sl.text_off[n];
+        const uint64_t blob_cap = n_text / 16 + 512 * n + titles.size() + 4096;  // FCZ is ~1/40 of its text; retried when short
         if (blob_cap > pin_blob_cap) {
             if (pin_blob) fcz_host_free(pin_blob);
             pin_blob_cap = blob_cap + blob_cap / 8;
             pin_blob = (uint8_t*)fcz_host_alloc(pin_blob_cap);
             if (!pin_blob) return FCZ_E_CUDA;
         }
-#pragma omp parallel for schedule(static)
-        for (size_t c = 0; c < n; c++) memcpy(pin_text + text_off[c], rd.data(i0 + c), text_off[c + 1] - text_off[c]);
         std::vector<int32_t> status(n + 1, 0);
         fcz_text_batch in{};
-        in.n_chains = (uint32_t)n; in.mem = FCZ_MEM_HOST; in.text_off = text_off.data(); in.bytes = pin_text; in.bytes_cap = text_off[n];
+        in.n_chains = (uint32_t)n; in.mem = FCZ_MEM_HOST; in.text_off = sl.text_off.data(); in.bytes = sl.text; in.bytes_cap = n_text;
         fcz_blob_batch out{};
         out.n_chains = (uint32_t)n; out.mem = FCZ_MEM_HOST; out.blob_off = blob_off.data(); out.bytes = pin_blob; out.bytes_cap = pin_blob_cap;
         out.status = status.data();
@@ -522,6 +637,9 @@ int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db,
         // entries with a numeric field outside the GPU grammar (exponents, hex floats: no PDB writer emits them) take the
         // host parser, which goes through strtof
         std::vector<CanonicalChain> odd;
+        std::vector<size_t> which;
+        std::vector<std::string> blobs_host;
+        std::vector<int> st_host;
         for (size_t c = 0; c < n; c++) {
             if (status[c] != FCZ_E_PARSE_NUMBER) continue;
             CanonicalChain ch;
@@ -541,7 +659,6 @@ int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db,
             s.bytes_out += len;
             if (!wr.append(data, len, rd.key(i0 + c), names[c] + ".fcz")) return FCZ_E_ARG;
         }
-        i0 = i1;
     }
     if (!wr.close()) return FCZ_E_ARG;
     s.seconds = now_s() - t0;

@@ -71,13 +71,19 @@ public:
     bool append(const char* data, size_t len, uint32_t key, const std::string& name);
     // appends data as it is (the reference's writer_append: its callers put the NUL into the data themselves)
     bool appendRaw(const char* data, size_t len, uint32_t key, const std::string& name);
+    // n entries of one slab at once, entry c = base[off[c] .. off[c+1]) + a NUL terminator, written by all host threads
+    // (pwrite at precomputed positions: the page-cache copy is what bounds a text database); skip[c] != 0 leaves c out
+    bool appendBatch(const char* base, const uint64_t* off, size_t n, const uint32_t* keys, const std::string* names, const uint8_t* skip);
     bool close();  // writes .index / .lookup sorted by key (stable)
 
 private:
     struct Entry { uint32_t key; uint64_t offset, length; size_t name; };
-    FILE* data_ = nullptr;
+    bool put(const char* data, size_t len);  // buffered sequential write at pos_
+    bool flush();
+    int fd_ = -1;
+    std::vector<char> buf_;
     std::string path_, index_path_;
-    uint64_t pos_ = 0;
+    uint64_t pos_ = 0;       // logical end of the data file (buffered bytes included)
     std::vector<Entry> entries_;
     std::vector<std::string> names_;
 };

@@ -8,7 +8,7 @@ nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 timeout 600 $TR bench.py --gpus $N --steps ${STEPS:-10} --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
 echo "bench exit $?" >> gpurun_out/bench_n$N.err
-FCZ_BIND=0 timeout 600 $TR bench.py --gpus $N --steps ${STEPS:-10} --warmup 3 > gpurun_out/bench_n${N}_nobind.json 2> gpurun_out/bench_n${N}_nobind.err
+[ "${NOBIND:-0}" = "1" ] && FCZ_BIND=0 timeout 600 $TR bench.py --gpus $N --steps ${STEPS:-10} --warmup 3 > gpurun_out/bench_n${N}_nobind.json 2> gpurun_out/bench_n${N}_nobind.err
 timeout 900 $TR tests/run_config4.py --chains-per-gpu ${CHAINS:-250000} --out /tmp/fcz_merged_db > gpurun_out/config4_n$N.json 2> gpurun_out/config4_n$N.err
 echo "config4 exit $?" >> gpurun_out/config4_n$N.err
 ls -la /tmp/fcz_merged_db* >> gpurun_out/config4_n$N.err 2>&1
