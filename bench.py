@@ -348,15 +348,18 @@ def run_ours(args, rank, world, local_rank, out):
     kms = kernels[kname]["ms_per_launch"]
     kbytes = kalg[kname] / max(kernels[kname]["launches_per_step"], 1.0)
     achieved = kbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
-    traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kname]
+    traffic, traffic_src = None, None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel: STATIC, from the committed ncu --set full capture of
+        # this workload (hardware counters cannot be read by the run itself); traffic_source names the capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        t = tj[kname]
         traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+        traffic_src = "static, not measured by this run: " + tj.get("source", "profiles/ncu_traffic.json")
     except Exception:
         pass
     roofline = {
         "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src, "ms_per_launch": kms, "algorithmic_bytes_per_launch": kbytes,
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "ms_per_launch": kms, "algorithmic_bytes_per_launch": kbytes,
         "kernels": kernels, "round_trip_bytes_per_residue": (enc_bytes + dec_bytes) / n_res,
         "round_trip_frac": (enc_bytes + dec_bytes) * args.steps / (ms * 1e-3) / 1e9 / peak,
         "ms_per_step_with_kernel_events": ms_prof / args.steps,

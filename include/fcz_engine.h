@@ -25,8 +25,13 @@
  * All pointers inside a batch live in ONE memory space, named by `mem`:
  *   FCZ_MEM_HOST    host memory (pageable or pinned); the call copies in/out and returns when the
  *                   results are on the host.
- *   FCZ_MEM_DEVICE  device memory of the engine's GPU; the call only enqueues work on the
- *                   engine's stream and returns (results are valid after the stream syncs).
+ *   FCZ_MEM_DEVICE  device memory of the engine's GPU; the call enqueues its kernels on the engine's
+ *                   stream and returns without waiting for them (results are valid after the stream
+ *                   syncs).  Calls that size something from the data wait for ONE small plan result
+ *                   first: fcz_encode_batch (bytes per length tier, total size against bytes_cap),
+ *                   the *_plan calls and fcz_extract_batch / fcz_unpack_angles_batch (their totals);
+ *                   fcz_decode_batch, fcz_pdb_text_batch and fcz_parse_pdb_batch after their plan,
+ *                   fcz_check_batch and fcz_backbone_angles_batch never wait.
  * Buffers are caller-owned; the engine owns its stream-ordered scratch.  One engine per GPU; calls
  * on one engine must be serialised by the caller, different engines are independent.
  */
