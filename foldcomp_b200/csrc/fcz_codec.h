@@ -731,6 +731,7 @@ struct DecChain {
     uint16_t* order;      // [L] residues sorted by atom count (side chains), with bins[32] u32 of scratch; or NULL
     uint32_t* bins;
     const uint8_t* codes;  // [L] residue codes when a copy is at hand (else read from the records), or NULL
+    const uint8_t* sc;     // [A - 3L] side-chain torsion bytes when a copy is at hand (else read from the blob), or NULL
 };
 
 // y = R x + t, T = rows of R (9) then t (3)
@@ -1085,7 +1086,7 @@ FCZ_HD void dec_side(Ctx& cx, const Tables* tb, const DecChain& ch) {
     // are lower slots of the same residue).  Nerf::reconstructAminoAcid src/nerf.cpp:106-155; torsion =
     // FixedAngleDiscretizer(255).continuize(byte), src/foldcomp.cpp:338-369, read from a 256-entry table.
     {
-        const uint8_t* sc = blob + y.o_sc;
+        const uint8_t* sc = ch.sc ? ch.sc : blob + y.o_sc;
         // Residues sorted by atom count (counting sort, longest first) so that the lanes of a warp -- and the two
         // residues of a pair -- run the same number of placements: a warp costs its longest lane.
         const uint16_t* ord = nullptr;

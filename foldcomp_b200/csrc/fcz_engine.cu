@@ -671,7 +671,7 @@ __device__ __forceinline__ bool dec2_chain(const Dec2Args& a, uint32_t c, DecCha
     ch.ang = a.ang + 3u * (size_t)rr;
     ch.rev = a.rev + 9u * (size_t)rr;
     ch.loc = nullptr;
-    ch.order = nullptr; ch.bins = nullptr; ch.codes = nullptr;
+    ch.order = nullptr; ch.bins = nullptr; ch.codes = nullptr; ch.sc = nullptr;
     ch.seg = a.seg + (size_t)(a.seg_off[c] - a.s_base) * FCZ_SEG_FLOATS;
     return true;
 }
@@ -737,7 +737,7 @@ __host__ __device__ inline FrontSmem front_smem(uint32_t max_L, uint32_t max_anc
     o.total = p;
     return o;
 }
-struct BackSmem { uint32_t o_seg, o_aoff, o_segid, o_codes, o_order, o_out, total; };
+struct BackSmem { uint32_t o_seg, o_aoff, o_segid, o_codes, o_order, o_sc, o_out, total; };
 __host__ __device__ inline BackSmem back_smem(uint32_t max_L, uint32_t max_anchor, uint32_t max_atoms) {
     BackSmem o;
     uint32_t p = 0;
@@ -746,6 +746,7 @@ __host__ __device__ inline BackSmem back_smem(uint32_t max_L, uint32_t max_ancho
     o.o_segid = p; p += up16(max_L);
     o.o_codes = p; p += up16(max_L);
     o.o_order = p; p += up16(2u * max_L) + 128u;  // sorted residues + 32 bins
+    o.o_sc = p; p += up16(max_atoms - 3u * (max_atoms / FCZ_MAX_ATOMS)) + 16u;  // side-chain bytes (at most atoms - 3 per residue)
     o.o_out = p; p += up16(12u * max_atoms) + 32u;
     o.total = p;
     return o;
@@ -791,7 +792,7 @@ __global__ void __launch_bounds__(1024) k_dec_front(Dec2Args a) {
     ch.rev = a.rev + 9u * (size_t)rr;
     ch.out_xyz = a.loc + 9u * (size_t)rr;  // forward atoms of residue r at 9r: see the offsets below
     ch.loc = nullptr;
-    ch.order = nullptr; ch.bins = nullptr; ch.codes = nullptr;
+    ch.order = nullptr; ch.bins = nullptr; ch.codes = nullptr; ch.sc = nullptr;
     __builtin_assume(__isShared(ch.blob));
     __builtin_assume(__isShared(ch.aoff));
     __builtin_assume(__isShared(ch.segid));
@@ -926,6 +927,12 @@ __global__ void __launch_bounds__(1024) k_dec_back(Dec2Args a) {
         const uint8_t* gtype = a.res_type + r0;  // written by the front kernel
         for (uint32_t r = cx.tid; r < L; r += cx.nthr) codes[r] = gtype[r];
         ch.codes = codes;
+        // side-chain torsion bytes of the chain: one coalesced pass instead of a dependent byte load per placement
+        uint8_t* ssc = smem + so.o_sc;
+        const uint8_t* gsc = blob + ch.y.o_sc;
+        const uint32_t nsc = A - 3u * L;
+        for (uint32_t i = cx.tid; i < nsc; i += cx.nthr) ssc[i] = gsc[i];
+        ch.sc = ssc;
         cp_async_wait_all();
     }
     __syncthreads();

@@ -52,8 +52,19 @@ def write_db(path, entries, nul=True):
         t.write(struct.pack("<i", 12))
 
 
+def fcz_size(blob: bytes) -> int:
+    """Size of an FCZ blob from its header (Foldcomp::getSize, src/foldcomp.cpp:1190-1214), 0 if it is not one."""
+    if len(blob) < 76 or blob[:4] != b"FCMP":
+        return 0
+    L, n_anchor = int.from_bytes(blob[4:6], "little"), blob[12]
+    n_sc, title_len = int.from_bytes(blob[16:20], "little"), int.from_bytes(blob[24:28], "little")
+    return 76 + 40 * n_anchor + title_len + 13 + 8 * L + n_sc + 8 + L
+
+
 def read_db(path):
-    """-> list of (key, name, payload bytes) in index order; a trailing NUL is stripped."""
+    """-> list of (key, name, payload bytes) in index order; a trailing NUL terminator is stripped -- for an FCZ entry only
+    when the header says the blob is one byte shorter (`foldcomp compress --db` writes its blobs WITHOUT a terminator,
+    src/main.cpp:510-517, and a blob may end in a zero B-factor byte)."""
     data = open(path, "rb").read()
     names = {}
     if os.path.exists(path + ".lookup"):
@@ -64,7 +75,7 @@ def read_db(path):
     for line in open(path + ".index"):
         k, o, n = (int(x) for x in line.split())
         blob = data[o : o + n]
-        if blob.endswith(b"\0"):
+        if blob.endswith(b"\0") and (blob[:4] != b"FCMP" or fcz_size(blob) == len(blob) - 1):
             blob = blob[:-1]
         out.append((k, names.get(k, str(k)), blob))
     return out

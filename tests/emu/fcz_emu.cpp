@@ -97,7 +97,7 @@ int emu_decode_chain(const uint8_t* blob, uint64_t len, int use_alt, uint8_t* re
     ch.out_xyz = xyz; ch.out_type = res_type; ch.out_bfac = bfac; ch.out_meta = meta; ch.out_title = title;
     ch.aoff = aoff.data(); ch.tor = tor.data(); ch.ang = ang.data(); ch.seg = seg.data(); ch.rev = rev.data(); ch.segid = segid.data(); ch.loc = nullptr;
     std::vector<uint16_t> order(L); std::vector<uint32_t> bins(32);
-    ch.order = order.data(); ch.bins = bins.data(); ch.codes = nullptr;
+    ch.order = order.data(); ch.bins = bins.data(); ch.codes = nullptr; ch.sc = nullptr;
     HostCtx cx;
     decode_chain(cx, tb, ch);
     return FCZ_OK;

@@ -217,3 +217,31 @@ def test_reference_style_db_handles(tmp_path):
         with ref.open(db, decompress=False) as d2:
             assert len(d2) == 3 and [bytes(x).rstrip(b"\0") if not isinstance(x, str) else x.rstrip("\0") for x in d2] in (
                 [b"first", b"second one", b"third entry"], ["first", "second one", "third entry"])
+
+
+def test_writer_batch_append_both_modes(tmp_path, monkeypatch):
+    """DbWriter::appendBatch (the text side of decompress-db): entries of one slab written by all host threads, through a
+    shared mapping or by pwrite, between ordinary appends -- every entry NUL-terminated, index in key order, skipped
+    entries absent."""
+    import ctypes as C
+
+    lib = dbutil.gpu_host_lib()
+    lib.fczgpu_db_write_batch.restype = C.c_int
+    lib.fczgpu_db_write_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    rng = np.random.default_rng(4)
+    lens = rng.integers(0, 70000, 300)
+    lens[:4] = [0, 1, 4095, 4096]
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    slab = rng.integers(1, 255, int(off[-1]), dtype=np.uint8).tobytes()
+    skip = (rng.random(len(lens)) < 0.1).astype(np.uint8)
+    for mode in ("mmap", "pwrite"):
+        monkeypatch.setenv("FCZ_DB_WRITE", mode)
+        path = str(tmp_path / f"db_{mode}")
+        assert lib.fczgpu_db_write_batch(path.encode(), slab, off.ctypes.data, len(lens), skip.ctypes.data) == 0
+        got = dbutil.read_db(path)
+        want = [(1, "head", b"head"), (2, "tail", b"tail")] + [
+            (100 + c, f"e{c}", slab[int(off[c]) : int(off[c + 1])]) for c in range(len(lens)) if not skip[c]
+        ]
+        assert got == want, mode
+        assert os.path.getsize(path) == sum(len(b) + 1 for _, _, b in want)

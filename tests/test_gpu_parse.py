@@ -89,10 +89,12 @@ def test_text_to_fcz_in_one_call_matches_oracle_and_reference(engine, golden):
             continue
         assert blobs.status[c] == 0, (name, blobs.status[c])
         assert blobs.blob(c) == H.oracle_encode(one, 0, 25), name
-        # "shuffled": the reference's backbone is the N / CA / C atoms in INPUT order (filterBackbone, src/atom_coordinate.cpp:
-        # 135-143) while the canonical layout stores every atom in its table slot, so a residue whose backbone atoms come
-        # out of order is encoded as if they were in order -- a documented property of the slot layout
-        if ref is not None and len(rt) >= 3 and name != "shuffled":
+        # "shuffled", "missing_atom" (a CA): the reference's backbone is the atoms named N / CA / C in INPUT order, however many
+        # there are (filterBackbone, src/atom_coordinate.cpp:135-143), while the canonical layout stores every atom in its
+        # table slot: backbone atoms out of order are encoded as if in order, a missing one reads (0,0,0) like a missing
+        # side-chain atom does in the reference too (findFirstAtomCoords) -- a documented property of the slot layout
+        # (DESIGN.md section 2); a missing SIDE-CHAIN atom is the same in both ("missing_sidechain_atom")
+        if ref is not None and len(rt) >= 3 and name not in ("shuffled", "missing_atom"):
             try:
                 want = ref.compress(name, t.decode())
             except Exception:

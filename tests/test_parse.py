@@ -63,6 +63,7 @@ def messy_variants(golden):
         "altloc": "\n".join(atoms[:5] + [atoms[4]] + [atoms[4][:30] + "   9.999   9.999   9.999" + atoms[4][54:]] + atoms[5:]) + "\n",
         "shuffled": "\n".join(atoms[:3][::-1] + atoms[3:]) + "\n",
         "missing_atom": "\n".join(atoms[:1] + atoms[2:]) + "\n",
+        "missing_sidechain_atom": "\n".join(atoms[:4] + atoms[5:]) + "\n",
         "unknown_residue": "\n".join(l[:17] + "XYZ" + l[20:] if 8 <= i < 16 else l for i, l in enumerate(atoms)) + "\n",
         "no_oxt": "\n".join(atoms[:-1]) + "\n",
         "short_b": "\n".join(l[:64] for l in atoms) + "\n",
