@@ -50,7 +50,10 @@ struct TierCfg {
 // residues) its workspace as well.
 // Caps are chosen at the occupancy steps of the per-residue shared-memory footprint (encode ~172 B/residue,
 // 350-residue chains run 3 CTAs/SM).  Decode has its own four length tiers (dec_tier_of, below).
-static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 256, 384, 640, 1280, 2720, 65535};
+#ifndef FCZ_ENC_TIER3
+#define FCZ_ENC_TIER3 384  // (A/B knob: the cap of the tier that takes 350-residue chains)
+#endif
+static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 256, FCZ_ENC_TIER3, 640, 1280, 2720, 65535};
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
@@ -737,7 +740,7 @@ __host__ __device__ inline FrontSmem front_smem(uint32_t max_L, uint32_t max_anc
     o.total = p;
     return o;
 }
-struct BackSmem { uint32_t o_seg, o_aoff, o_segid, o_codes, o_order, o_sc, o_out, total; };
+struct BackSmem { uint32_t o_seg, o_aoff, o_segid, o_codes, o_order, o_out, total; };
 __host__ __device__ inline BackSmem back_smem(uint32_t max_L, uint32_t max_anchor, uint32_t max_atoms) {
     BackSmem o;
     uint32_t p = 0;
@@ -746,7 +749,6 @@ __host__ __device__ inline BackSmem back_smem(uint32_t max_L, uint32_t max_ancho
     o.o_segid = p; p += up16(max_L);
     o.o_codes = p; p += up16(max_L);
     o.o_order = p; p += up16(2u * max_L) + 128u;  // sorted residues + 32 bins
-    o.o_sc = p; p += up16(max_atoms - 3u * (max_atoms / FCZ_MAX_ATOMS)) + 16u;  // side-chain bytes (at most atoms - 3 per residue)
     o.o_out = p; p += up16(12u * max_atoms) + 32u;
     o.total = p;
     return o;
@@ -927,12 +929,9 @@ __global__ void __launch_bounds__(1024) k_dec_back(Dec2Args a) {
         const uint8_t* gtype = a.res_type + r0;  // written by the front kernel
         for (uint32_t r = cx.tid; r < L; r += cx.nthr) codes[r] = gtype[r];
         ch.codes = codes;
-        // side-chain torsion bytes of the chain: one coalesced pass instead of a dependent byte load per placement
-        uint8_t* ssc = smem + so.o_sc;
-        const uint8_t* gsc = blob + ch.y.o_sc;
-        const uint32_t nsc = A - 3u * L;
-        for (uint32_t i = cx.tid; i < nsc; i += cx.nthr) ssc[i] = gsc[i];
-        ch.sc = ssc;
+        // (staging the side-chain bytes here as well was measured: 2.5 KB more shared memory per block costs the fifth
+        // block per SM, 0.260 -> 0.327 ms on the headline batch)
+        ch.sc = nullptr;
         cp_async_wait_all();
     }
     __syncthreads();
@@ -2454,57 +2453,66 @@ static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb, const uint3
         if (sb.tier[t].count) ntier++;
     if (!ntier) return FCZ_OK;  // no valid chain
     // Each tier is its own three-kernel pipeline; tiers run side by side on their own streams (a tier of long
-    // chains has few, long-running blocks): fork from the engine's stream, join at the end.
-    const bool fork = ntier > 1;
+    // chains has few, long-running blocks): fork from the engine's stream, join at the end.  A tier with many chains
+    // runs as TWO such pipelines over the halves of its list (streams t and 4 + t): the serial stitch of one half -- one
+    // wave of latency-bound threads -- then overlaps the front / back kernels of the other half, and the tail of one
+    // kernel fills with the head of the next.  The workspace is indexed per chain, so the halves share nothing.
+    static const uint32_t split_min = [] { const char* v = getenv("FCZ_DEC_SPLIT_MIN"); return v ? (uint32_t)atol(v) : 4096u; }();
+    bool fork = ntier > 1;
+    for (int t = 0; t < FCZ_DEC_TIERS; t++) fork |= sb.tier[t].count >= split_min && sb.tier[t].smem;
     if (fork) CK(cudaEventRecord(e->ev_fork, e->stream));
     for (int t = 0; t < FCZ_DEC_TIERS; t++) {
         const Dec2Tier& tr = sb.tier[t];
         if (!tr.count) continue;
-        cudaStream_t st = fork ? e->s_tier[t] : e->stream;
-        if (fork) CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
-        a.list = list + tr.list_off; a.count = tr.count;
+        const int halves = (tr.smem && tr.count >= split_min) ? 2 : 1;
         a.max_L = tr.max_L; a.max_anchor = tr.max_anchor; a.max_blob = tr.max_blob; a.max_atoms = tr.max_atoms;
-        // stitch: one wave when it fits -- chains per block = ceil(chains / SMs), bounded by shared memory
-        const uint32_t cbytes = stitch_chain_bytes(tr.max_anchor);
-        uint32_t G = (tr.count + (uint32_t)e->num_sms - 1u) / (uint32_t)e->num_sms;
-        const uint32_t gmax = (FCZ_SMEM_LIMIT - 1024u) / cbytes;
-        if (G > gmax) G = gmax;
-        if (G > 1024u) G = 1024u;
-        if (G < 1u) G = 1u;
-        a.stitch_group = G;
-        uint32_t sthr = 32u * G;  // enough warps to gather the group's scratch with deep queues
-        sthr = sthr < 256u ? 256u : (sthr > 1024u ? 1024u : sthr);
-        if (tr.smem) {
-            // front: three lanes per segment and direction -- enough warps that the passes take one trip
-            uint32_t thr = (6u * tr.max_anchor + 31u) & ~31u;
-            thr = thr < 128u ? 128u : (thr > 1024u ? 1024u : thr);
-            {
-                ProfSpan pk(e, FCZ_PROF_K_DEC_FRONT, st);
-                k_dec_front<<<tr.count, thr, front_smem(tr.max_L, tr.max_anchor, tr.max_blob).total, st>>>(a);
+        for (int h = 0; h < halves; h++) {
+            cudaStream_t st = fork ? e->s_tier[t + 4 * h] : e->stream;
+            if (fork) CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
+            const uint32_t first = h ? tr.count / 2u : 0u, cnt = halves == 2 ? (h ? tr.count - tr.count / 2u : tr.count / 2u) : tr.count;
+            a.list = list + tr.list_off + first; a.count = cnt;
+            // stitch: one wave when it fits -- chains per block = ceil(chains / SMs), bounded by shared memory
+            const uint32_t cbytes = stitch_chain_bytes(tr.max_anchor);
+            uint32_t G = (cnt + (uint32_t)e->num_sms - 1u) / (uint32_t)e->num_sms;
+            const uint32_t gmax = (FCZ_SMEM_LIMIT - 1024u) / cbytes;
+            if (G > gmax) G = gmax;
+            if (G > 1024u) G = 1024u;
+            if (G < 1u) G = 1u;
+            a.stitch_group = G;
+            uint32_t sthr = 32u * G;  // enough warps to gather the group's scratch with deep queues
+            sthr = sthr < 256u ? 256u : (sthr > 1024u ? 1024u : sthr);
+            if (tr.smem) {
+                // front: three lanes per segment and direction -- enough warps that the passes take one trip
+                uint32_t thr = (6u * tr.max_anchor + 31u) & ~31u;
+                thr = thr < 128u ? 128u : (thr > 1024u ? 1024u : thr);
+                {
+                    ProfSpan pk(e, FCZ_PROF_K_DEC_FRONT, st);
+                    k_dec_front<<<cnt, thr, front_smem(tr.max_L, tr.max_anchor, tr.max_blob).total, st>>>(a);
+                }
+                {
+                    ProfSpan pk(e, FCZ_PROF_K_DEC_STITCH, st);
+                    k_dec_stitch_t<<<(cnt + G - 1u) / G, sthr, G * cbytes, st>>>(a);
+                }
+                // back: about one thread per two residues (side chains take two trips), whole warps
+                thr = ((tr.max_L * 35u) / 64u + 31u) & ~31u;
+                thr = thr < 192u ? 192u : (thr > 1024u ? 1024u : thr);
+                {
+                    ProfSpan pk(e, FCZ_PROF_K_DEC_BACK, st);
+                    k_dec_back<<<cnt, thr, back_smem(tr.max_L, tr.max_anchor, tr.max_atoms).total, st>>>(a);
+                }
+                e->launches += 3;
+            } else {
+                k_dec_unpack<<<cnt, 256, 0, st>>>(a);
+                k_dec_passes<<<cnt, 128, 0, st>>>(a);
+                k_dec_stitch_t<<<(cnt + G - 1u) / G, sthr, G * cbytes, st>>>(a);
+                k_dec_blend<<<cnt, 128, 0, st>>>(a);
+                k_dec_side<<<cnt, 192, 0, st>>>(a);
+                e->launches += 5;
             }
-            {
-                ProfSpan pk(e, FCZ_PROF_K_DEC_STITCH, st);
-                k_dec_stitch_t<<<(tr.count + G - 1u) / G, sthr, G * cbytes, st>>>(a);
+            if (fork) {
+                CK(cudaEventRecord(e->ev_join[t + 4 * h], st));
+                CK(cudaStreamWaitEvent(e->stream, e->ev_join[t + 4 * h], 0));
             }
-            // back: about one thread per two residues (side chains take two trips), whole warps
-            thr = ((tr.max_L * 35u) / 64u + 31u) & ~31u;
-            thr = thr < 192u ? 192u : (thr > 1024u ? 1024u : thr);
-            {
-                ProfSpan pk(e, FCZ_PROF_K_DEC_BACK, st);
-                k_dec_back<<<tr.count, thr, back_smem(tr.max_L, tr.max_anchor, tr.max_atoms).total, st>>>(a);
-            }
-            e->launches += 3;
-        } else {
-            k_dec_unpack<<<tr.count, 256, 0, st>>>(a);
-            k_dec_passes<<<tr.count, 128, 0, st>>>(a);
-            k_dec_stitch_t<<<(tr.count + G - 1u) / G, sthr, G * cbytes, st>>>(a);
-            k_dec_blend<<<tr.count, 128, 0, st>>>(a);
-            k_dec_side<<<tr.count, 192, 0, st>>>(a);
-            e->launches += 5;
-        }
-        if (fork) {
-            CK(cudaEventRecord(e->ev_join[t], st));
-            CK(cudaStreamWaitEvent(e->stream, e->ev_join[t], 0));
         }
     }
     return FCZ_OK;

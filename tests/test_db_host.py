@@ -236,7 +236,7 @@ def test_writer_batch_append_both_modes(tmp_path, monkeypatch):
     slab = rng.integers(1, 255, int(off[-1]), dtype=np.uint8).tobytes()
     skip = (rng.random(len(lens)) < 0.1).astype(np.uint8)
     for mode in ("mmap", "pwrite"):
-        monkeypatch.setenv("FCZ_DB_WRITE", mode)
+        monkeypatch.setenv("FCZ_DB_WRITE", mode)  # mmap is the opt-in
         path = str(tmp_path / f"db_{mode}")
         assert lib.fczgpu_db_write_batch(path.encode(), slab, off.ctypes.data, len(lens), skip.ctypes.data) == 0
         got = dbutil.read_db(path)

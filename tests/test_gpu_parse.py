@@ -94,7 +94,9 @@ def test_text_to_fcz_in_one_call_matches_oracle_and_reference(engine, golden):
         # table slot: backbone atoms out of order are encoded as if in order, a missing one reads (0,0,0) like a missing
         # side-chain atom does in the reference too (findFirstAtomCoords) -- a documented property of the slot layout
         # (DESIGN.md section 2); a missing SIDE-CHAIN atom is the same in both ("missing_sidechain_atom")
-        if ref is not None and len(rt) >= 3 and name not in ("shuffled", "missing_atom"):
+        # "unknown_residue": the reference's compress() dies on an uncaught std::out_of_range (AAS.at, src/sidechain.cpp:177)
+        # and takes the process with it; here such a residue is encoded as UNK, like a decode of codes 24..31
+        if ref is not None and len(rt) >= 3 and name not in ("shuffled", "missing_atom", "unknown_residue"):
             try:
                 want = ref.compress(name, t.decode())
             except Exception:
