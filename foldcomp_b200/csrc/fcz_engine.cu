@@ -2457,7 +2457,10 @@ static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb, const uint3
     // runs as TWO such pipelines over the halves of its list (streams t and 4 + t): the serial stitch of one half -- one
     // wave of latency-bound threads -- then overlaps the front / back kernels of the other half, and the tail of one
     // kernel fills with the head of the next.  The workspace is indexed per chain, so the halves share nothing.
-    static const uint32_t split_min = [] { const char* v = getenv("FCZ_DEC_SPLIT_MIN"); return v ? (uint32_t)atol(v) : 4096u; }();
+    // Measured on the B200 (profiles/r02_v15_ab.jsonl): decode span 0.457 ms split against 0.463 ms whole on the headline
+    // batch, 0.831 against 0.824 ms on mixed lengths -- no gain worth the overlapped per-kernel timings, so it is OFF
+    // unless FCZ_DEC_SPLIT_MIN names a chain count.
+    static const uint32_t split_min = [] { const char* v = getenv("FCZ_DEC_SPLIT_MIN"); return v ? (uint32_t)atol(v) : 0xFFFFFFFFu; }();
     bool fork = ntier > 1;
     for (int t = 0; t < FCZ_DEC_TIERS; t++) fork |= sb.tier[t].count >= split_min && sb.tier[t].smem;
     if (fork) CK(cudaEventRecord(e->ev_fork, e->stream));

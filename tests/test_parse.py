@@ -67,7 +67,7 @@ def messy_variants(golden):
         "unknown_residue": "\n".join(l[:17] + "XYZ" + l[20:] if 8 <= i < 16 else l for i, l in enumerate(atoms)) + "\n",
         "no_oxt": "\n".join(atoms[:-1]) + "\n",
         "short_b": "\n".join(l[:64] for l in atoms) + "\n",
-        "negative_numbers": "\n".join(l[:22] + " -12" + l[26:] if i < 7 else l for i, l in enumerate(atoms)) + "\n",
+        "negative_numbers": "\n".join(l[:22] + " -12" + l[26:] if l[22:26] == atoms[0][22:26] else l for l in atoms) + "\n",  # the whole first residue
         "two_chains": "\n".join(atoms[:10] + [l[:21] + "B" + l[22:] for l in atoms[10:20]]) + "\n",
         "no_atoms": "HEADER\nREMARK\nEND\n",
         "empty": "",
