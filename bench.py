@@ -141,44 +141,65 @@ def run_reference(args, rank, world, out):
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU while the timed passes run: NVML polled every 2 ms from a thread of this
+    process (nvidia_ml_py; an `nvidia-smi -lms` child needs longer to start than the timed region lasts).  The sampler is
+    started before the warm-up steps; stop() keeps the samples taken between mark_begin() and mark_end() -- the timed and
+    the per-kernel-event passes -- and says how many there were."""
 
-    def __init__(self, gpu_id):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, gpu_uuid, index):
+        import threading
+
+        self.rows, self.err, self._stop = [], None, threading.Event()
+        self.t0 = self.t1 = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_id), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(gpu_uuid.encode() if isinstance(gpu_uuid, str) else gpu_uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = f"NVML unavailable: {e}"
+            return
+
+        def run():
+            while not self._stop.is_set():
+                try:
+                    self.rows.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                      int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.002)
+
+        self.th = threading.Thread(target=run, daemon=True)
+        self.th.start()
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(nm)
-            except (ValueError, IndexError):
-                pass
-        if not sm:
+        if self.err:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err]}
+        self._stop.set()
+        self.th.join(timeout=2)
+        rows = [r for r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        window = "timed passes"
+        if len(rows) < 3:  # a region shorter than a few polls: the warm-up steps before it ran the same kernels
+            rows, window = [r for r in self.rows if self.t1 is None or r[0] <= self.t1], "warm-up + timed passes"
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(nm for nm, m in self.REASONS if bits & m), "samples": len(rows), "window": window}
 
 
 # --------------------------------------------------------------------------------------- ours
@@ -264,17 +285,18 @@ def run_ours(args, rank, world, local_rank, out):
         if dist is not None:
             dist.barrier()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    # ---- timed region: kernels with HBM-resident inputs
     try:
         gpu_id = str(torch.cuda.get_device_properties(local_rank).uuid)
         if not gpu_id.startswith("GPU-"):
             gpu_id = "GPU-" + gpu_id
     except Exception:
         gpu_id = str(local_rank)
-    sampler = ClockSampler(gpu_id)
+    sampler = ClockSampler(gpu_id, local_rank)  # polls from here on: the warm-up steps run the same kernels
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # ---- timed region: kernels with HBM-resident inputs
+    sampler.mark_begin()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -297,6 +319,7 @@ def run_ours(args, rank, world, local_rank, out):
     ms_prof = ev2.elapsed_time(ev3)
     prof = eng.get_profile()
     eng.set_profiling(False)
+    sampler.mark_end()
     clocks = sampler.stop()  # sampled over the device-resident timed passes only (the GPU idles between transfers later on)
     ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:

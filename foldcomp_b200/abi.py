@@ -27,6 +27,7 @@ FCZ_E_PARSE_NOATOM = -11
 FCZ_E_PARSE_CHAINS = -12
 FCZ_E_PARSE_RECORD = -13
 FCZ_E_PARSE_NUMBER = -14
+FCZ_E_PARSE_GAPS = -15
 
 DEFAULT_ANCHOR_THRESHOLD = 25  # src/foldcomp.h:56
 

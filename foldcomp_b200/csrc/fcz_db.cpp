@@ -75,6 +75,7 @@ struct RawAtom {
     uint32_t res;   // trimmed residue name, same packing
     int serial, resnum;
     float x, y, z, b;
+    char chain;
 };
 
 // trim(" \t") of the reference, then the first four characters as one integer key
@@ -116,10 +117,13 @@ static int code_of_key(uint32_t r) {
     return FCZ_CODE_UNK;
 }
 
-int parsePdbChain(const char* text, size_t len, const std::string& title, CanonicalChain& out) {
-    out = CanonicalChain();
-    out.title = title;
-    std::vector<RawAtom> atoms;
+static std::string strip_ext(const std::string& n);
+
+// ATOM records of a text in file order, alternative positions dropped (an atom named like its predecessor,
+// removeAlternativePosition src/atom_coordinate.cpp:362-370).  one_chain: stop with flag 2 at a second chain id
+// (foldcomp/foldcomp.cxx:266-268); otherwise every chain is read (the CLI's reader).  0, or 2 / 3 as parsePdbChain.
+static int read_atom_records(const char* text, size_t len, bool one_chain, std::vector<RawAtom>& atoms) {
+    atoms.clear();
     atoms.reserve(len / 81 + 1);
     char chain = 0;
     bool have_chain = false;
@@ -133,7 +137,7 @@ int parsePdbChain(const char* text, size_t len, const std::string& title, Canoni
         if (n < 22) return 3;  // substr(21, 1) would throw
         const char ch = line[21];
         if (!have_chain) { chain = ch; have_chain = true; }
-        if (ch != chain) return 2;
+        if (one_chain && ch != chain) return 2;
         if (n < 61) return 3;  // the B-factor column starts at 60
         RawAtom a;
         a.name = trim_key(line + 12, 4);
@@ -144,18 +148,24 @@ int parsePdbChain(const char* text, size_t len, const std::string& title, Canoni
         a.y = parseFixedFloat(line + 38, 8);
         a.z = parseFixedFloat(line + 46, 8);
         a.b = parseFixedFloat(line + 60, n - 60 < 6 ? n - 60 : 6);
+        a.chain = ch;
         if (!atoms.empty() && atoms.back().name == a.name) continue;  // removeAlternativePosition
         atoms.push_back(a);
     }
-    if (atoms.empty()) return 1;
-    const size_t n = atoms.size();
+    return 0;
+}
+
+// atoms[0..n) of ONE chain / fragment -> canonical slot layout (what Foldcomp::compress sees of them)
+static void canonicalize_records(const RawAtom* atoms, size_t n, const std::string& title, CanonicalChain& out) {
+    out = CanonicalChain();
+    out.title = title;
     out.xyz.reserve(3 * n + 64);
     out.res_type.reserve(n / 4 + 8);
     out.bfactor.reserve(n / 4 + 8);
     out.meta.n_atom = (uint16_t)n;
     out.meta.idx_residue = (uint16_t)atoms[0].resnum;
     out.meta.idx_atom = (uint16_t)atoms[0].serial;
-    out.meta.chain = (uint8_t)chain;
+    out.meta.chain = (uint8_t)atoms[0].chain;
     const NameKeys& nk = name_keys();
     if (atoms[n - 1].name == nk.oxt) {  // src/foldcomp.cpp:473-481
         out.meta.has_oxt = 1;
@@ -190,7 +200,96 @@ int parsePdbChain(const char* text, size_t len, const std::string& title, Canoni
         out.bfactor.push_back(bf);
         i = j;
     }
+}
+
+int parsePdbChain(const char* text, size_t len, const std::string& title, CanonicalChain& out) {
+    out = CanonicalChain();
+    out.title = title;
+    std::vector<RawAtom> atoms;
+    const int flag = read_atom_records(text, len, true, atoms);
+    if (flag) return flag;
+    if (atoms.empty()) return 1;
+    canonicalize_records(atoms.data(), atoms.size(), title, out);
     return 0;
+}
+
+// The title `foldcomp compress` gives the chains of one PDB text (src/main.cpp:466-467 over StructureReader::updateStructure,
+// src/structure_reader.cpp:31-46, over gemmi's record reader, lib/gemmi/pdb.hpp:483-498): the HEADER record's idCode
+// (columns 63-66) when the line is long enough and the code is not blank; else the text of the TITLE records (from column
+// 11 on, right-trimmed, continuation lines appended as they stand); else the file name -- and a title equal to the file name
+// becomes the name without its extension.  Records after the first ATOM / HETATM line are not looked at (gemmi would).
+std::string pdbTitle(const char* text, size_t len, const std::string& base_name) {
+    std::string entry_id, title;
+    size_t p = 0;
+    auto rtrim = [](std::string v) {
+        const size_t last = v.find_last_not_of(" \r\n\t");
+        return v.substr(0, last == std::string::npos ? 0 : last + 1);
+    };
+    while (p < len) {
+        const char* line = text + p;
+        const char* nl = (const char*)memchr(line, '\n', len - p);
+        const size_t n = nl ? (size_t)(nl - line) : len - p;  // without the newline
+        const size_t glen = n + (nl ? 1 : 0);                  // gemmi's `len` counts the newline it copied
+        p += n + 1;
+        if (n >= 4 && (memcmp(line, "ATOM", 4) == 0 || memcmp(line, "HETA", 4) == 0)) break;
+        if (n >= 6 && memcmp(line, "HEADER", 6) == 0) {
+            if (glen > 66) { const std::string id = rtrim(std::string(line + 62, 4)); if (!id.empty()) entry_id = id; }
+        } else if (n >= 5 && memcmp(line, "TITLE", 5) == 0) {
+            if (glen > 10) title += rtrim(std::string(line + 10, glen - 10 - 1));
+        }
+    }
+    std::string t = !entry_id.empty() ? entry_id : (!title.empty() ? title : base_name);
+    if (t == base_name) t = strip_ext(base_name);
+    return t;
+}
+
+int parsePdbUnits(const char* text, size_t len, const std::string& title, std::vector<CanonicalChain>& units) {
+    units.clear();
+    std::vector<RawAtom> atoms;
+    const int flag = read_atom_records(text, len, false, atoms);
+    if (flag) return flag;
+    if (atoms.empty()) return 1;
+    const NameKeys& nk = name_keys();
+    const uint32_t kN = key_of("N");
+    (void)nk;
+    const size_t n = atoms.size();
+    // identifyChains (src/atom_coordinate.cpp:469-497): a new chain starts where the chain id changes -- at that atom when
+    // it is an N, else at the next N atom (the atoms in between belong to nobody).  (Without any further N atom the
+    // reference never leaves its loop; here the rest of the text is dropped.)
+    std::vector<std::pair<size_t, size_t>> chains;
+    size_t start = 0;
+    for (size_t i = 1; i < n; i++) {
+        if (atoms[i].chain == atoms[i - 1].chain) continue;
+        size_t j = i;
+        while (j < n && atoms[j].name != kN) j++;
+        chains.emplace_back(start, i);
+        start = j;
+        if (j >= n) break;
+        i = j;
+    }
+    if (start < n) chains.emplace_back(start, n);
+    for (const auto& ch : chains) {
+        // identifyDiscontinousResInd (src/atom_coordinate.cpp:506-530): fragments start at N atoms; a fragment ends where
+        // the next N atom's residue number exceeds the previous N atom's by more than one.  The first fragment starts at
+        // the chain's first N atom.  (A chain without N atoms is undefined behaviour there; here it stays one fragment.)
+        size_t fstart = ch.first;
+        bool have = false;
+        int prev = 0;
+        std::vector<std::pair<size_t, size_t>> frags;
+        for (size_t i = ch.first; i < ch.second; i++) {
+            if (atoms[i].name != kN) continue;
+            if (!have) { fstart = i; have = true; }
+            else if (atoms[i].resnum - prev > 1) { frags.emplace_back(fstart, i); fstart = i; }
+            prev = atoms[i].resnum;
+        }
+        frags.emplace_back(fstart, ch.second);
+        for (const auto& f : frags) {
+            if (f.second <= f.first) continue;
+            units.emplace_back();
+            canonicalize_records(atoms.data() + f.first, f.second - f.first, title, units.back());
+        }
+    }
+    return units.empty() ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------ reader
@@ -542,6 +641,10 @@ int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db,
     const size_t n_all = rd.size();
     const char* hp = getenv("FCZ_HOST_PARSER");
     const bool host_parser = hp && atoi(hp) != 0;
+    // Outputs like the reference CLI's (src/main.cpp:438-536): an entry whose ATOM records hold several chains or breaks in
+    // the residue numbering yields one FCZ entry per chain / fragment; every output carries the entry's base name (no
+    // extension, 448-449) and the next key of a running counter (514-517; there in completion order, here in input order).
+    uint32_t next_key = 0;
     fcz_opts o{anchorThreshold, 0, nullptr, 0};
     int rc = fcz_engine_set_opts(eng.get(), &o);
     if (rc) return rc;
@@ -553,18 +656,18 @@ int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db,
             uint64_t sum = 0;
             while (i1 < n_all && (i1 == i0 || sum + rd.length(i1) <= kBatchBytes)) sum += rd.length(i1++);
             const size_t n = i1 - i0;
-            std::vector<CanonicalChain> chains(n);
+            std::vector<std::vector<CanonicalChain>> units(n);
             std::vector<int> flag(n, 0);
 #pragma omp parallel for schedule(dynamic, 8)
             for (size_t c = 0; c < n; c++)
-                flag[c] = parsePdbChain(rd.data(i0 + c), rd.payload(i0 + c), strip_ext(rd.name(i0 + c)), chains[c]);
+                flag[c] = parsePdbUnits(rd.data(i0 + c), rd.payload(i0 + c), pdbTitle(rd.data(i0 + c), rd.payload(i0 + c), rd.name(i0 + c)), units[c]);
             std::vector<CanonicalChain> good;
             std::vector<size_t> which;
             for (size_t c = 0; c < n; c++) {
                 s.entries++;
                 s.bytes_in += rd.length(i0 + c);
-                if (flag[c] == 0) { good.push_back(std::move(chains[c])); which.push_back(c); }
-                else s.failed++;
+                if (flag[c] != 0) { s.failed++; continue; }
+                for (auto& u : units[c]) { good.push_back(std::move(u)); which.push_back(c); }
             }
             std::vector<std::string> blobs;
             std::vector<int> st;
@@ -576,8 +679,7 @@ int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db,
                 if (st[g] != FCZ_OK) { s.failed++; continue; }
                 s.residues += good[g].res_type.size();
                 s.bytes_out += blobs[g].size();
-                const size_t c = which[g];
-                if (!wr.append(blobs[g].data(), blobs[g].size(), rd.key(i0 + c), strip_ext(rd.name(i0 + c)) + ".fcz")) return FCZ_E_ARG;
+                if (!wr.appendRaw(blobs[g].data(), blobs[g].size(), next_key++, strip_ext(rd.name(i0 + which[g])))) return FCZ_E_ARG;
             }
             i0 = i1;
         }
@@ -629,9 +731,12 @@ int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db,
         std::vector<uint32_t> title_off(n + 1, 0);
         std::vector<std::string> names(n);
         std::string titles;
+        std::vector<std::string> title_of(n);
+#pragma omp parallel for schedule(static)
+        for (size_t c = 0; c < n; c++) title_of[c] = pdbTitle(rd.data(i0 + c), rd.payload(i0 + c), rd.name(i0 + c));
         for (size_t c = 0; c < n; c++) {
             names[c] = strip_ext(rd.name(i0 + c));
-            titles += names[c];
+            titles += title_of[c];
             title_off[c + 1] = (uint32_t)titles.size();
         }
         const uint64_t n_text = sl.text_off[n];
@@ -661,30 +766,42 @@ int compressDb(Engine& eng, const std::string& in_db, const std::string& out_db,
         }
         s.seconds_engine += now_s() - g0;
         if (rc) return rc;
-        // entries with a numeric field outside the GPU grammar (exponents, hex floats: no PDB writer emits them) take the
-        // host parser, which goes through strtof
+        // What the GPU parser hands back to the host: entries with several chains or fragments (the units are cut here,
+        // parsePdbUnits) and entries with a numeric field outside the GPU grammar (exponents, hex floats: no PDB writer
+        // emits them; the host parser goes through strtof).  Their blobs are made by one more engine call.
         std::vector<CanonicalChain> odd;
         std::vector<size_t> which;
         std::vector<std::string> blobs_host;
         std::vector<int> st_host;
         for (size_t c = 0; c < n; c++) {
-            if (status[c] != FCZ_E_PARSE_NUMBER) continue;
-            CanonicalChain ch;
-            if (parsePdbChain(rd.data(i0 + c), rd.payload(i0 + c), names[c], ch) == 0) { odd.push_back(std::move(ch)); which.push_back(c); }
+            if (status[c] != FCZ_E_PARSE_NUMBER && status[c] != FCZ_E_PARSE_CHAINS && status[c] != FCZ_E_PARSE_GAPS) continue;
+            std::vector<CanonicalChain> units;
+            if (parsePdbUnits(rd.data(i0 + c), rd.payload(i0 + c), title_of[c], units) != 0) continue;
+            for (auto& u : units) { odd.push_back(std::move(u)); which.push_back(c); }
         }
         if (!odd.empty() && (rc = FoldcompGpu::compressBatch(eng, odd, anchorThreshold, blobs_host, st_host))) return rc;
         size_t w = 0;
         for (size_t c = 0; c < n; c++) {
             s.entries++;
             s.bytes_in += rd.length(i0 + c);
+            if (w < which.size() && which[w] == c) {
+                bool any = false;
+                for (; w < which.size() && which[w] == c; w++) {
+                    if (st_host[w] != FCZ_OK) continue;
+                    any = true;
+                    s.residues += odd[w].res_type.size();
+                    s.bytes_out += blobs_host[w].size();
+                    if (!wr.appendRaw(blobs_host[w].data(), blobs_host[w].size(), next_key++, names[c])) return FCZ_E_ARG;
+                }
+                if (!any) s.failed++;
+                continue;
+            }
             const char* data = (const char*)pin_blob + blob_off[c];
-            size_t len = (size_t)(blob_off[c + 1] - blob_off[c]);
-            int32_t stc = status[c];
-            if (w < which.size() && which[w] == c) { data = blobs_host[w].data(); len = blobs_host[w].size(); stc = st_host[w]; w++; }
-            if (stc != FCZ_OK || len < 6) { s.failed++; continue; }
+            const size_t len = (size_t)(blob_off[c + 1] - blob_off[c]);
+            if (status[c] != FCZ_OK || len < 6) { s.failed++; continue; }
             s.residues += (uint64_t)(uint8_t)data[4] | (uint64_t)(uint8_t)data[5] << 8;  // CompressedFileHeader.nResidue
             s.bytes_out += len;
-            if (!wr.appendRaw(data, len, rd.key(i0 + c), names[c] + ".fcz")) return FCZ_E_ARG;  // no terminator, like `foldcomp compress --db` (src/main.cpp:510-517)
+            if (!wr.appendRaw(data, len, next_key++, names[c])) return FCZ_E_ARG;  // no terminator, like `foldcomp compress --db` (src/main.cpp:510-517)
         }
     }
     if (!wr.close()) return FCZ_E_ARG;
@@ -724,6 +841,38 @@ extern "C" int fczgpu_db_write_batch(const char* path, const char* base, const u
     if (!wr.appendBatch(base, off, n, keys.data(), names.data(), skip)) return FCZ_E_ARG;
     if (!wr.append("tail", 4, 2, "tail")) return FCZ_E_ARG;
     return wr.close() ? FCZ_OK : FCZ_E_ARG;
+}
+
+extern "C" int fczgpu_pdb_title(const char* text, size_t len, const char* base_name, char* out, size_t cap) {
+    const std::string t = pdbTitle(text, len, base_name);
+    if (t.size() + 1 > cap) return -1;
+    memcpy(out, t.c_str(), t.size() + 1);
+    return (int)t.size();
+}
+
+// parsePdbUnits for bindings and tests: the units of one text, concatenated (res_off / atom_off [n_units + 1]).  Returns
+// the parser's flag, or -1 when a capacity is too small; *n_units is set either way when the flag is 0.
+extern "C" int fczgpu_parse_pdb_units(const char* text, size_t len, uint32_t* n_units, uint32_t* res_off, uint64_t* atom_off,
+                                      uint8_t* res_type, float* bfactor, float* xyz, fcz_chain_meta* meta, uint32_t cap_units,
+                                      uint32_t cap_res, uint64_t cap_atoms) {
+    std::vector<CanonicalChain> units;
+    const int flag = parsePdbUnits(text, len, "", units);
+    if (flag) return flag;
+    *n_units = (uint32_t)units.size();
+    if (units.size() > cap_units) return -1;
+    uint64_t r = 0, a = 0;
+    for (size_t u = 0; u < units.size(); u++) {
+        res_off[u] = (uint32_t)r; atom_off[u] = a;
+        const CanonicalChain& c = units[u];
+        if (r + c.res_type.size() > cap_res || a + c.xyz.size() / 3 > cap_atoms) return -1;
+        memcpy(res_type + r, c.res_type.data(), c.res_type.size());
+        memcpy(bfactor + r, c.bfactor.data(), 4 * c.bfactor.size());
+        memcpy(xyz + 3 * a, c.xyz.data(), 4 * c.xyz.size());
+        meta[u] = c.meta;
+        r += c.res_type.size(); a += c.xyz.size() / 3;
+    }
+    res_off[units.size()] = (uint32_t)r; atom_off[units.size()] = a;
+    return 0;
 }
 
 static void put_stats(const DbStats& s, double* o) {

@@ -27,6 +27,16 @@ namespace fczgpu {
 // one chain; 3 = an ATOM line too short to hold its columns (the reference throws std::out_of_range there).
 int parsePdbChain(const char* text, size_t len, const std::string& title, CanonicalChain& out);
 
+// One PDB text -> the units `foldcomp compress` encodes one by one (src/main.cpp:466-484): ATOM records of every chain,
+// alternative positions dropped, cut into chains (identifyChains, src/atom_coordinate.cpp:469-497) and each chain into
+// fragments of continuous residue numbering (identifyDiscontinousResInd, 506-530), in file order.  0, 1 (no ATOM record)
+// or 3 (malformed record).
+int parsePdbUnits(const char* text, size_t len, const std::string& title, std::vector<CanonicalChain>& units);
+
+// title of the chains of one PDB text as `foldcomp compress` sets it: HEADER idCode, else TITLE records, else the file name
+// (without extension); see fcz_db.cpp
+std::string pdbTitle(const char* text, size_t len, const std::string& base_name);
+
 // the reference's strtof-based field parse, with a certified fast path for plain fixed-point fields
 float parseFixedFloat(const char* s, size_t n);
 
@@ -125,6 +135,8 @@ extern "C" {
 // parse one PDB text; arrays must hold cap_res residues / cap_atoms atoms.  Returns the parser's flag, or -1 if too small.
 int fczgpu_parse_pdb(const char* text, size_t len, uint8_t* res_type, float* bfactor, float* xyz, fcz_chain_meta* meta,
                      uint32_t* n_res, uint32_t* n_atoms, uint32_t cap_res, uint32_t cap_atoms);
+int fczgpu_parse_pdb_units(const char* text, size_t len, uint32_t* n_units, uint32_t* res_off, uint64_t* atom_off, uint8_t* res_type,
+                           float* bfactor, float* xyz, fcz_chain_meta* meta, uint32_t cap_units, uint32_t cap_res, uint64_t cap_atoms);
 float fczgpu_parse_float(const char* s, size_t n);
 int fczgpu_db_copy(const char* in_db, const char* out_db);
 int fczgpu_decompress_db(int device, const char* in_db, const char* out_db, int alt_order, double* stats7);

@@ -1328,7 +1328,7 @@ __global__ void __launch_bounds__(256) k_parse_plan(ParseArgs a) {
     parse_entry_plan(cx, a.pt, e);
     if (threadIdx.x == 0) {
         const uint32_t f = e.scratch[PS_FLAG];
-        a.status[c] = f == 0u ? FCZ_OK : (f == 1u ? FCZ_E_PARSE_NOATOM : (f == 2u ? FCZ_E_PARSE_CHAINS : (f == 3u ? FCZ_E_PARSE_RECORD : FCZ_E_PARSE_NUMBER)));
+        a.status[c] = f == 0u ? FCZ_OK : (f == 1u ? FCZ_E_PARSE_NOATOM : (f == 2u ? FCZ_E_PARSE_CHAINS : (f == 3u ? FCZ_E_PARSE_RECORD : (f == 4u ? FCZ_E_PARSE_NUMBER : FCZ_E_PARSE_GAPS))));
         a.v_res[c] = f ? 0u : e.scratch[PS_NRES];
         a.v_atoms[c] = f ? 0u : e.scratch[PS_NSLOT];
     }
@@ -1775,6 +1775,7 @@ const char* fcz_strerror(int code) {
         case FCZ_E_PARSE_CHAINS: return "Multiple chains found";
         case FCZ_E_PARSE_RECORD: return "Malformed ATOM record";
         case FCZ_E_PARSE_NUMBER: return "numeric field outside the fixed-point grammar";
+        case FCZ_E_PARSE_GAPS: return "discontinuous residue numbering (the chain splits into fragments)";
         default: return "unknown error";
     }
 }

@@ -29,7 +29,7 @@ struct ParseTables {
     uint32_t atom[FCZ_NUM_CODES][FCZ_MAX_ATOMS];  // atom names of the table slots, up to four characters packed little-endian
     uint32_t res3[FCZ_NUM_CODES];
     uint8_t natoms[FCZ_NUM_CODES];
-    uint32_t ca, oxt;
+    uint32_t ca, oxt, n;
 };
 inline uint32_t name_key4(const char* z) {
     uint32_t k = 0;
@@ -44,6 +44,7 @@ inline void build_parse_tables(ParseTables* t) {
     }
     t->ca = name_key4("CA");
     t->oxt = name_key4("OXT");
+    t->n = name_key4("N");
 }
 
 // trim(" \t") of the reference, then the first four characters as one integer key
@@ -261,7 +262,30 @@ FCZ_HD void parse_entry_plan(Ctx& cx, const ParseTables* pt, const ParseEntry& e
     for (uint32_t j = a0; j < a1; j++)
         if (j == 0u || (dense[j].resnum != dense[j - 1u].resnum && j != n_atoms - 1u)) e.rstart[rbase++] = j;
     if (a1 == n_atoms && cx.tid == cx.nthr - 1) { e.scratch[PS_NRES] = rbase; e.rstart[rbase] = n_atoms; }
+    // fragments (identifyDiscontinousResInd, src/atom_coordinate.cpp:506-530; src/main.cpp:469-484): the reference CLI cuts a
+    // chain where the residue number of an N atom exceeds that of the previous N atom by more than one, and starts its
+    // first fragment at the chain's first N atom.  Such an entry is not ONE chain for `foldcomp compress`: flag 5 (the batch
+    // front end splits it on the host, fczgpu::parsePdbUnits).
+    {
+        uint32_t gap = 0;
+        bool have = false;
+        int32_t prevn = 0;
+        for (uint32_t j = a0; j > 0u && a0 < a1; j--)  // the last N atom before this thread's range
+            if (dense[j - 1u].name == pt->n) { have = true; prevn = dense[j - 1u].resnum; break; }
+        for (uint32_t j = a0; j < a1; j++) {
+            if (dense[j].name != pt->n) continue;
+            if (have && dense[j].resnum - prevn > 1) gap = 1u;
+            have = true; prevn = dense[j].resnum;
+        }
+        if (cx.tid == 0 && dense[0].name != pt->n) gap = 1u;
+        if (gap) cx.atomic_or_u(&e.scratch[PS_BITS], 16u);
+    }
     cx.sync();
+    if (e.scratch[PS_BITS] & 16u) {
+        if (cx.tid == 0) e.scratch[PS_FLAG] = 5u;
+        cx.sync();
+        return;
+    }
     // ---- pass 5: table slots of every residue (the canonical atom count)
     const uint32_t n_res = e.scratch[PS_NRES];
     uint32_t slots = 0;

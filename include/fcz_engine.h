@@ -62,6 +62,11 @@ extern "C" {
 #define FCZ_E_PARSE_CHAINS (-12) /* ATOM records of more than one chain ("Multiple chains", flag 2) */
 #define FCZ_E_PARSE_RECORD (-13) /* an ATOM record too short for its columns (the reference throws std::out_of_range) */
 #define FCZ_E_PARSE_NUMBER (-14) /* a numeric field that is not a plain fixed-point number (see fcz_parse_pdb_plan)   */
+#define FCZ_E_PARSE_GAPS (-15)   /* the residue number of an N atom exceeds the previous N atom's by more than one, or the
+                                    text does not start at an N atom: `foldcomp compress` cuts such a chain into fragments
+                                    (identifyDiscontinousResInd, src/atom_coordinate.cpp:506-530; src/main.cpp:469-484)
+                                    and encodes each on its own -- the entry is not ONE chain (the CPython compress() does
+                                    not cut, and stores anchors picked by residue NUMBER, src/foldcomp.cpp:756-760)      */
 
 typedef struct fcz_engine fcz_engine;
 

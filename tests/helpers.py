@@ -46,7 +46,7 @@ def build_emu(perturb: bool = False):
     MUFU results may be (fcz_math.h: FCZ_EMU_PERTURB) -- the certified shortcuts must not care."""
     src = os.path.join(ROOT, "tests", "emu", "fcz_emu.cpp")
     so = EMU_PERTURB_SO if perturb else EMU_SO
-    deps = [src] + [os.path.join(ROOT, "foldcomp_b200", "csrc", f) for f in ("fcz_codec.h", "fcz_math.h", "fcz_format.h", "fcz_tables.h", "fcz_text.h")]
+    deps = [src] + [os.path.join(ROOT, "foldcomp_b200", "csrc", f) for f in ("fcz_codec.h", "fcz_math.h", "fcz_format.h", "fcz_tables.h", "fcz_text.h", "fcz_parse.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17"]
                               + (["-DFCZ_EMU_PERTURB"] if perturb else []) + ["-o", so, src])

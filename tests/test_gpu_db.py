@@ -10,7 +10,7 @@ import pytest
 
 import dbutil
 import helpers as H
-from foldcomp_b200 import pdbio, synth
+from foldcomp_b200 import abi, pdbio, synth
 from foldcomp_b200.abi import HostBlobBatch
 
 pytestmark = pytest.mark.gpu
@@ -61,7 +61,7 @@ def test_compress_db_matches_oracle_and_reference_module(engine, tmp_path):
     assert len(got) == len(texts)
     ref = dbutil.reference_module()
     for (k, name, blob), text in zip(got, texts):
-        assert name == f"prot_{k}.fcz"
+        assert name == f"prot_{k}"  # the entry's base name without extension, like the reference CLI (src/main.cpp:448-449)
         parsed = pdbio.parse_pdb_chain(text.decode(), f"prot_{k}")
         assert blob == H.oracle_encode(parsed, 0, 25), k
         if ref is not None:
@@ -171,3 +171,45 @@ def test_python_compress_matches_oracle_and_reference_module(golden):
         foldcomp_b200.compress("x", "HEADER nothing here\n")
     with pytest.raises(TypeError):
         foldcomp_b200.compress("x", text, anchor_residue_threshold="25")
+
+
+def test_compress_db_splits_chains_and_fragments_like_the_reference_cli(engine, tmp_path):
+    """Entries with several chains or breaks in the residue numbering: `foldcomp compress --db` writes one FCZ entry per chain
+    / fragment under the entry's name (src/main.cpp:466-517).  compress-db does the same (the GPU parser flags such entries,
+    the host cuts them: parsePdbUnits); the two databases hold the same blobs per name."""
+    import subprocess
+
+    from test_parse import _host_units
+
+    ref_cli = os.path.join(H.ROOT, "integration", "_build", "foldcomp_ref")
+    batch = synth.generate(6, [40, 60, 80, 30, 50, 70], seed=91)
+    t = [pdbio.format_pdb(batch.chain(c), 0) for c in range(6)]
+    atoms = lambda c, ch=None, shift=0, cut=None: [
+        l[:21] + (ch or l[21]) + "%4d" % (int(l[22:26]) + (shift if cut is not None and int(l[22:26]) > cut else 0)) + l[26:]
+        for l in t[c].splitlines() if l.startswith("ATOM")]
+    texts = {
+        "single": t[0],
+        "two_chains": "\n".join(atoms(1, "A") + atoms(2, "B")) + "\nEND\n",
+        "gap": "\n".join(atoms(3, None, 4, 12)) + "\nEND\n",
+        "chains_and_gaps": "\n".join(atoms(4, "X", 9, 20) + atoms(5, "Y", 3, 33)) + "\nEND\n",
+        "plain_again": t[1],
+    }
+    src, dst = str(tmp_path / "pdb_db"), str(tmp_path / "fcz_db")
+    dbutil.write_db(src, [(i, n + ".pdb", x.encode()) for i, (n, x) in enumerate(texts.items())])
+    stats = (C.c_double * 7)()
+    assert dbutil.gpu_host_lib().fczgpu_compress_db(0, src.encode(), dst.encode(), 25, stats) == 0
+    got = dbutil.read_db(dst)
+    assert [k for k, _, _ in got] == list(range(len(got)))  # a running key per output
+    want = []
+    for n, x in texts.items():
+        for rt, bf, xyz, meta in _host_units(x.encode()):
+            one = abi.concat_chains([(rt, bf, xyz, np.frombuffer(n.encode(), np.uint8), np.array([meta]))])
+            want.append((n, H.oracle_encode(one, 0, 25)))
+    assert [(n, b) for _, n, b in got] == want
+    assert len(want) == 1 + 2 + 2 + 4 + 1 and int(stats[1]) == 0
+    if os.path.exists(ref_cli):
+        rdst = str(tmp_path / "fcz_ref")
+        r = subprocess.run([ref_cli, "compress", "-t", "1", "-y", "--db", src, rdst], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (r.stdout[-300:], r.stderr[-300:])
+        theirs = sorted((n, H.masked(b)) for _, n, b in dbutil.read_db(rdst))
+        assert theirs == sorted((n, H.masked(b)) for n, b in want)

@@ -10,11 +10,18 @@ import helpers as H
 from foldcomp_b200 import abi, pdbio, synth
 from foldcomp_b200.abi import HostTextBatch
 from foldcomp_b200.engine import DeviceTextBatch
-from test_parse import _host_parse, messy_variants
+from test_parse import _host_parse, cli_fragments, messy_variants
 
 pytestmark = pytest.mark.gpu
 
-FLAG_TO_STATUS = {0: 0, 1: abi.FCZ_E_PARSE_NOATOM, 2: abi.FCZ_E_PARSE_CHAINS, 3: abi.FCZ_E_PARSE_RECORD, 4: abi.FCZ_E_PARSE_NUMBER}
+FLAG_TO_STATUS = {0: 0, 1: abi.FCZ_E_PARSE_NOATOM, 2: abi.FCZ_E_PARSE_CHAINS, 3: abi.FCZ_E_PARSE_RECORD, 4: abi.FCZ_E_PARSE_NUMBER,
+                  5: abi.FCZ_E_PARSE_GAPS}
+
+
+def _want_flag(text: bytes, host_flag: int) -> int:
+    """The GPU parser's flag from the single-chain host parser's: the same, plus 5 where `foldcomp compress` would cut the
+    chain into fragments (the host side of that is parsePdbUnits)."""
+    return 5 if host_flag == 0 and cli_fragments(text) else host_flag
 
 
 def _texts_batch(texts):
@@ -59,9 +66,10 @@ def test_device_parser_matches_host_parser(engine, golden):
         if name == "exponent":  # strtof reads it, the GPU grammar rejects it -- never mis-parses it
             assert status[c] == abi.FCZ_E_PARSE_NUMBER and want[0] == 0
             continue
-        assert status[c] == FLAG_TO_STATUS[want[0]], (name, status[c], want[0])
+        flag = _want_flag(t, want[0])
+        assert status[c] == FLAG_TO_STATUS[flag], (name, status[c], flag)
         r0, r1, a0, a1 = int(hb.res_off[c]), int(hb.res_off[c + 1]), int(hb.atom_off[c]), int(hb.atom_off[c + 1])
-        if want[0]:
+        if flag:
             assert r1 == r0 and a1 == a0, name
             continue
         assert np.array_equal(hb.res_type[r0:r1], want[1]), name
@@ -80,6 +88,7 @@ def test_text_to_fcz_in_one_call_matches_oracle_and_reference(engine, golden):
         if name == "exponent":
             assert blobs.status[c] == abi.FCZ_E_PARSE_NUMBER and blobs.blob(c) == b""
             continue
+        flag = _want_flag(t, flag)
         if flag:
             assert blobs.status[c] == FLAG_TO_STATUS[flag] and blobs.blob(c) == b"", name
             continue
