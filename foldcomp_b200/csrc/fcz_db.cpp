@@ -458,7 +458,7 @@ bool DbWriter::appendBatch(const char* base, const uint64_t* off, size_t n, cons
     int bad = 0;
     // Buffered write()s to ONE file are serialised by the file system (the inode lock), so pwrite from many threads runs
     // at little more than the speed of one; stores through a shared mapping fault their pages in concurrently but pay a
-    // fault per page -- measured on the B200 box's ext4 volume (profiles/r02_v14_cli_e2e_50k.json): 11 GB of text in
+    // fault per page -- measured on the B200 box's ext4 volume (profiles/r02_v14b_cli_e2e_50k.json): 11 GB of text in
     // 3.8 s by pwrite, 4.2 s through the mapping.  pwrite stays the default; FCZ_DB_WRITE=mmap selects the mapping.
     const char* wmode = getenv("FCZ_DB_WRITE");
     const bool use_mmap = wmode && strcmp(wmode, "mmap") == 0;

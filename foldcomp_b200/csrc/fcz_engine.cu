@@ -50,8 +50,11 @@ struct TierCfg {
 // residues) its workspace as well.
 // Caps are chosen at the occupancy steps of the per-residue shared-memory footprint (encode ~172 B/residue,
 // 350-residue chains run 3 CTAs/SM).  Decode has its own four length tiers (dec_tier_of, below).
+// Tier 3's cap is where EIGHT blocks of 128 threads still fit an SM's shared memory (8 x (26.5 KB + 1 KB) <= 228 KB) now
+// that k_encode runs in 64 registers: measured against cap 384 / 72 registers / 7 blocks, k_encode 0.4131 -> 0.4025 ms on
+// the 350-residue batch and 0.570 -> 0.559 ms per step on mixed lengths (profiles/r02_v15_ab.jsonl, r02_v16_ab_mixed.jsonl).
 #ifndef FCZ_ENC_TIER3
-#define FCZ_ENC_TIER3 384  // (A/B knob: the cap of the tier that takes 350-residue chains)
+#define FCZ_ENC_TIER3 352
 #endif
 static const uint32_t kEncTierRes[FCZ_NTIER] = {64, 128, 256, FCZ_ENC_TIER3, 640, 1280, 2720, 65535};
 
@@ -361,7 +364,7 @@ __global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* 
 }
 
 #ifndef FCZ_ENC_MAXREG
-#define FCZ_ENC_MAXREG 72  // 864 threads per SM (3 CTAs of 288) fit the register file
+#define FCZ_ENC_MAXREG 64  // 1024 threads per SM: eight blocks of 128 (96 bytes of spill stores; 72 registers = seven blocks, measured slower)
 #endif
 __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];

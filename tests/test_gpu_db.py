@@ -62,10 +62,13 @@ def test_compress_db_matches_oracle_and_reference_module(engine, tmp_path):
     ref = dbutil.reference_module()
     for (k, name, blob), text in zip(got, texts):
         assert name == f"prot_{k}"  # the entry's base name without extension, like the reference CLI (src/main.cpp:448-449)
-        parsed = pdbio.parse_pdb_chain(text.decode(), f"prot_{k}")
+        # the title is the text's TITLE record, as in the reference CLI (pdbTitle; src/structure_reader.cpp:31-46)
+        title = batch.title(k)
+        assert f"TITLE     {title}".encode() in text
+        parsed = pdbio.parse_pdb_chain(text.decode(), title)
         assert blob == H.oracle_encode(parsed, 0, 25), k
         if ref is not None:
-            assert H.masked(blob) == H.masked(ref.compress(f"prot_{k}", text.decode())), k
+            assert H.masked(blob) == H.masked(ref.compress(title, text.decode())), k
     if ref is not None:  # the reference's reader opens the database we wrote
         with ref.open(dst) as db:
             assert len(db) == len(texts)

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 nproc > gpurun_out/nproc.txt
 if [ "${TESTS:-1}" = "1" ]; then
-  timeout 1500 python -m pytest tests -m gpu -x -q -rA ${PYTEST_ARGS:-} 2>&1 | tail -120 > gpurun_out/pytest_gpu.log
+  timeout 1500 python -m pytest tests -m gpu -q -rA ${PYTEST_ARGS:-} 2>&1 | tail -120 > gpurun_out/pytest_gpu.log
   echo "pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
   echo "smoke exit: $?" >> gpurun_out/smoke.log
