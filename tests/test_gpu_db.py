@@ -84,7 +84,7 @@ def test_cli_db_subcommands(tmp_path, golden):
     subprocess.check_call([CLI, "decompress-db", src, mid])
     subprocess.check_call([CLI, "compress-db", mid, back])
     a, b = dbutil.read_db(src), dbutil.read_db(back)
-    assert [x[0] for x in a] == [x[0] for x in b] and [x[1] for x in a] == [x[1] for x in b]
+    assert [x[0] for x in a] == [x[0] for x in b] and [x[1].rsplit(".", 1)[0] for x in a] == [x[1] for x in b]  # base names, like the reference CLI
     for (_, _, x), (_, _, y) in zip(a, b):
         dx, dy = H.oracle_decode(x), H.oracle_decode(y)
         assert np.array_equal(dx.res_type, dy.res_type) and H.rmsd(dx.xyz, dy.xyz) < 0.2  # a second lossy generation
@@ -203,10 +203,16 @@ def test_compress_db_splits_chains_and_fragments_like_the_reference_cli(engine, 
     assert dbutil.gpu_host_lib().fczgpu_compress_db(0, src.encode(), dst.encode(), 25, stats) == 0
     got = dbutil.read_db(dst)
     assert [k for k, _, _ in got] == list(range(len(got)))  # a running key per output
+    lib = dbutil.gpu_host_lib()
+    lib.fczgpu_pdb_title.restype = C.c_int
+    lib.fczgpu_pdb_title.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_size_t]
     want = []
     for n, x in texts.items():
+        buf = C.create_string_buffer(1024)  # the CLI's title rule (TITLE record of the two whole texts, else the entry name)
+        tl = lib.fczgpu_pdb_title(x.encode(), len(x.encode()), (n + ".pdb").encode(), buf, 1024)
+        title = buf.raw[:tl]
         for rt, bf, xyz, meta in _host_units(x.encode()):
-            one = abi.concat_chains([(rt, bf, xyz, np.frombuffer(n.encode(), np.uint8), np.array([meta]))])
+            one = abi.concat_chains([(rt, bf, xyz, np.frombuffer(title, np.uint8), np.array([meta]))])
             want.append((n, H.oracle_encode(one, 0, 25)))
     assert [(n, b) for _, n, b in got] == want
     assert len(want) == 1 + 2 + 2 + 4 + 1 and int(stats[1]) == 0
