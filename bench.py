@@ -293,8 +293,13 @@ def run_ours(args, rank, world, local_rank, out):
     except Exception:
         gpu_id = str(local_rank)
     sampler = ClockSampler(gpu_id, local_rank)  # polls from here on: the warm-up steps run the same kernels
-    for _ in range(max(args.warmup, 3)):
+    # warm-up: the W steps asked for (at least 3), then on until the GPU has been busy for 100 ms -- an idle B200 sits at
+    # 120 MHz and a 3 ms warm-up can end before the SM clock has ramped up (seen with eight ranks starting at once)
+    n_warm = 0
+    t_w = time.perf_counter()
+    while n_warm < max(args.warmup, 3) or (time.perf_counter() - t_w < 0.1 and n_warm < 400):
         step()
+        n_warm += 1
     barrier()
     # ---- timed region: kernels with HBM-resident inputs
     sampler.mark_begin()
@@ -323,7 +328,11 @@ def run_ours(args, rank, world, local_rank, out):
     sampler.mark_end()
     clocks = sampler.stop()  # sampled over the device-resident timed passes only (the GPU idles between transfers later on)
     ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ms_all = [ms]
     if dist is not None:
+        gathered = [torch.zeros_like(ms_t) for _ in range(world)]
+        dist.all_gather(gathered, ms_t)
+        ms_all = [float(g.item()) for g in gathered]
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_max = float(ms_t.item())
     value = world * n_res * args.steps / (ms_max * 1e-3)
@@ -596,6 +605,7 @@ def run_ours(args, rank, world, local_rank, out):
                     "serial_one_engine": {"value": world * e2e_serial, "unit": UNIT,
                                           "how": "one engine, fcz_encode_batch then fcz_decode_batch on the whole batch, no overlap"}},
             "gpu_launches": launches, "fcz_bytes_per_step": fcz_bytes, "roundtrip_rmsd_vs_input": dev_rt,
+            "warmup_steps_run": n_warm, "ms_per_step_by_rank": [m / args.steps for m in ms_all],
         }
         print(json.dumps(line), file=out, flush=True)
     if dist is not None:
