@@ -115,3 +115,29 @@ def generate_device(n_chains: int, length: int, seed: int, first_index: int, dev
         "res_type": torch.cat(out["res_type"]), "bfactor": torch.cat(out["bfactor"]), "xyz": torch.cat(out["xyz"]),
         "titles": torch.from_numpy(titles.copy()).to(dev), "meta": torch.cat(out["meta"]),
     }
+
+
+def generate_device_mixed(lengths, counts, seed: int, device, first_index: int = 0):
+    """Chains of several lengths, every one DISTINCT: counts[i] chains of lengths[i] residues each, generated length by
+    length (generate_device) and concatenated in that order.  Same dict as generate_device."""
+    dev = torch.device(device)
+    parts, first = [], int(first_index)
+    for L, n in zip(lengths, counts):
+        n, L = int(n), int(L)
+        if n <= 0:
+            continue
+        parts.append(generate_device(n, L, seed, first, dev, chunk=max(64, 6_000_000 // L)))
+        first += n
+
+    def offsets(key, dt):
+        out, base = [torch.zeros(1, dtype=torch.int64, device=dev)], 0
+        for p in parts:
+            o = p[key].to(torch.int64)
+            out.append(o[1:] + base)
+            base += int(o[-1].item())
+        return torch.cat(out).to(dt)
+
+    return {
+        "res_off": offsets("res_off", torch.int32), "atom_off": offsets("atom_off", torch.int64), "title_off": offsets("title_off", torch.int32),
+        **{k: torch.cat([p[k] for p in parts]) for k in ("res_type", "bfactor", "xyz", "titles", "meta")},
+    }
