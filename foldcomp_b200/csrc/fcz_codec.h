@@ -1117,10 +1117,18 @@ FCZ_HD void dec_side(Ctx& cx, const Tables* tb, const DecChain& ch) {
             const uint32_t o = ch.aoff[r], n = ch.aoff[r + 1u] - o;
             float* R = ch.out_xyz + 3u * o;
             const uint8_t* sb = sc + (o - 3u * r);
+            // the table entries of placement k+1 are fetched while placement k is computed (they depend on the residue code
+            // and the stored byte only): the dependent look-ups were the kernel's hottest line
+            unsigned pp_n = 0;
+            float len_n = 0.f;
+            cs ang_n = {0.f, 0.f}, tor_n = {0.f, 0.f};
+            if (n > 3u) { pp_n = tb->pred[code][3]; len_n = tb->blen[code][3]; ang_n = tb->bang[code][3]; tor_n = tb->sc_tor[sb[0]]; }
             for (uint32_t k = 3u; k < n; k++) {
-                const unsigned pp = tb->pred[code][k];
-                st3(R + 3u * k, place_from(ld3(R + 3u * (pp & 15u)), ld3(R + 3u * ((pp >> 4) & 15u)), ld3(R + 3u * ((pp >> 8) & 15u)),
-                                           tb->blen[code][k], tb->bang[code][k], tb->sc_tor[sb[k - 3u]]));
+                const unsigned pp = pp_n;
+                const float len = len_n;
+                const cs ang = ang_n, tor = tor_n;
+                if (k + 1u < n) { pp_n = tb->pred[code][k + 1u]; len_n = tb->blen[code][k + 1u]; ang_n = tb->bang[code][k + 1u]; tor_n = tb->sc_tor[sb[k - 2u]]; }
+                st3(R + 3u * k, place_from(ld3(R + 3u * (pp & 15u)), ld3(R + 3u * ((pp >> 4) & 15u)), ld3(R + 3u * ((pp >> 8) & 15u)), len, ang, tor));
             }
         }
         cx.sync();

@@ -144,3 +144,17 @@ def _roundtrip_batch(engine, texts, batch):
     hb = got.to_host()
     hb.title_off, hb.titles = batch.title_off, batch.titles
     return hb
+
+
+def test_text_entry_points_on_empty_and_all_failed_batches(engine):
+    """No entries at all, and a batch in which no entry parses: empty blobs, statuses, no fault."""
+    import torch
+
+    empty = engine.encode_pdb_text_host(_texts_batch([]), [])
+    assert empty.n_chains == 0 and int(empty.blob_off[-1]) == 0
+    texts = [b"", b"HEADER only\n", b"ATOM  short\n"]
+    out = engine.encode_pdb_text_host(_texts_batch(texts), [b"a", b"b", b"c"])
+    assert list(out.status) == [abi.FCZ_E_PARSE_NOATOM, abi.FCZ_E_PARSE_NOATOM, abi.FCZ_E_PARSE_RECORD] and int(out.blob_off[-1]) == 0
+    got = engine.parse_pdb_device(_device_texts(texts, torch.device("cuda", engine.device)))
+    engine.sync()
+    assert int(got.res_off[-1].item()) == 0 and int(got.atom_off[-1].item()) == 0
