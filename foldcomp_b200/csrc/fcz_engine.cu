@@ -22,9 +22,6 @@
 #include <new>
 #include <vector>
 
-#include <atomic>
-#include <chrono>
-
 #include "fcz_codec.h"
 #include "fcz_text.h"
 #include "fcz_parse.h"
@@ -1363,13 +1360,6 @@ struct ScanArgs {
     int out64[4];       // 1: uint64 output, 0: uint32
     uint64_t* partial;  // [ntiles*4]
     uint64_t* totals;   // [4]
-    // k_scan_one only, optional: publish the plan to PINNED HOST memory and raise a flag there, so that the host can pick
-    // it up by polling instead of a copy + stream synchronisation (fetch_plan)
-    const uint32_t* pub_counters;  // device counters to copy (2 * FCZ_NTIER + 2 words), or null
-    uint32_t* pub_h_counters;
-    uint64_t* pub_h_totals;
-    volatile uint32_t* pub_flag;
-    uint32_t pub_seq;
 };
 
 __device__ __forceinline__ uint64_t block_sum64(uint64_t v, uint64_t* sh) {
@@ -1439,54 +1429,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(ScanArgs a) {
     }
 }
 
-// One block for batches of up to SCAN_ONE_MAX chains (the usual case): every array in the same two passes -- per-thread sums of
-// a contiguous run of chains, one block scan of all the arrays' sums together, then the running offsets -- instead of two
-// launches that walk the arrays one after the other (measured under ncu on 10 000 chains: 22 us -> one launch of a few us).
-#define SCAN_ONE_THREADS 1024
-#define SCAN_ONE_MAX (SCAN_ONE_THREADS * 64u)
-__global__ void __launch_bounds__(SCAN_ONE_THREADS) k_scan_one(ScanArgs a) {
-    __shared__ uint64_t sh[4][32];
-    const uint32_t per = (a.n + SCAN_ONE_THREADS - 1u) / SCAN_ONE_THREADS;
-    const uint32_t b0 = min(threadIdx.x * per, a.n), b1 = min(b0 + per, a.n);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t s[4] = {0, 0, 0, 0};
-    for (int j = 0; j < a.narr; j++)
-        for (uint32_t i = b0; i < b1; i++) s[j] += a.in[j][i];
-    uint64_t x[4];
-    for (int j = 0; j < 4; j++) {
-        x[j] = s[j];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t y = __shfl_up_sync(0xffffffffu, x[j], o);
-            if (lane >= o) x[j] += y;
-        }
-        if (lane == 31) sh[j][warp] = x[j];
-    }
-    __syncthreads();
-    for (int j = 0; j < a.narr; j++) {
-        uint64_t wb = 0, total = 0;
-        for (int w = 0; w < SCAN_ONE_THREADS / 32; w++) { const uint64_t v = sh[j][w]; if (w < warp) wb += v; total += v; }
-        uint64_t off = wb + x[j] - s[j];
-        for (uint32_t i = b0; i < b1; i++) {
-            if (a.out64[j]) ((uint64_t*)a.out[j])[i] = off;
-            else ((uint32_t*)a.out[j])[i] = (uint32_t)off;
-            off += a.in[j][i];
-        }
-        if (threadIdx.x == 0) {
-            if (a.out64[j]) ((uint64_t*)a.out[j])[a.n] = total;
-            else ((uint32_t*)a.out[j])[a.n] = (uint32_t)total;
-            a.totals[j] = total;
-            if (a.pub_flag) a.pub_h_totals[j] = total;
-        }
-    }
-    if (a.pub_flag) {
-        if (threadIdx.x < 2 * FCZ_NTIER + 2) a.pub_h_counters[threadIdx.x] = a.pub_counters[threadIdx.x];
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) { *a.pub_flag = a.pub_seq; __threadfence_system(); }
-    }
-}
-
 // ============================================================================================ engine
 
 #define FCZ_HOST_CHUNKS 32u  // chunks of a host-memory batch
@@ -1536,9 +1478,6 @@ struct fcz_engine {
     uint64_t* d_totals = nullptr;    // [3]
     uint32_t* h_counters = nullptr;  // pinned mirror
     uint64_t* h_totals = nullptr;
-    volatile uint32_t* h_flag = nullptr;  // pinned: sequence number of the last plan k_scan_one published (see fetch_plan)
-    uint32_t plan_seq = 0;
-    bool plan_published = false;     // the scan just enqueued publishes counters + totals itself
     uint64_t chunk_bytes = FCZ_CHUNK_BYTES;  // coordinates per chunk of a host-memory batch (FCZ_CHUNK_MB)
     uint32_t h2d_depth = FCZ_H2D_DEPTH, d2h_depth = FCZ_D2H_DEPTH;  // FCZ_H2D_QUEUE / FCZ_D2H_QUEUE, 0 = unlimited
     uint32_t dec_sub_res = FCZ_SUB_RESIDUES;  // residues per decode sub-batch (FCZ_DEC_SUB_RESIDUES overrides)
@@ -1699,7 +1638,6 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     ok &= cudaMalloc(&e->d_totals, sizeof(uint64_t) * 4) == cudaSuccess;
     ok &= cudaMallocHost(&e->h_counters, sizeof(uint32_t) * (2 * FCZ_NTIER + 2)) == cudaSuccess;
     ok &= cudaMallocHost(&e->h_totals, sizeof(uint64_t) * 4) == cudaSuccess;
-    { void* f = nullptr; ok &= cudaMallocHost(&f, 64) == cudaSuccess; e->h_flag = (volatile uint32_t*)f; if (f) *e->h_flag = 0u; }
     ok &= cudaMallocHost(&e->h_bounds, sizeof(uint32_t) * ((3 + 5 * FCZ_DEC_TIERS) * (FCZ_MAX_CHUNKS + 1) + 1)) == cudaSuccess;
     if (ok) ok &= cudaMemcpy(e->d_tables, &h, sizeof(Tables), cudaMemcpyHostToDevice) == cudaSuccess;
     ok &= cudaMalloc(&e->d_submax.p, sizeof(uint32_t) * (5 * FCZ_DEC_TIERS * FCZ_MAX_CHUNKS + 1)) == cudaSuccess;  // k_plan_chunks keeps it zero
@@ -1730,7 +1668,6 @@ void fcz_engine_destroy(fcz_engine* e) {
     if (e->d_totals) cudaFree(e->d_totals);
     if (e->h_counters) cudaFreeHost(e->h_counters);
     if (e->h_totals) cudaFreeHost(e->h_totals);
-    if (e->h_flag) cudaFreeHost((void*)e->h_flag);
     if (e->h_bounds) cudaFreeHost(e->h_bounds);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
@@ -1878,26 +1815,11 @@ static int plan_buffers(fcz_engine* e, uint32_t n) {
     return FCZ_OK;
 }
 
-static int run_scan(fcz_engine* e, ScanArgs& sa, bool publish = false) {
-    e->plan_published = false;
+static int run_scan(fcz_engine* e, ScanArgs& sa) {
     uint32_t ntiles = (sa.n + SCAN_TILE - 1) / SCAN_TILE;
     if (ntiles == 0) ntiles = 1;
     sa.partial = (uint64_t*)e->partial.p;
     sa.totals = e->d_totals;
-    static const bool two_pass = getenv("FCZ_SCAN_TWO_PASS") != nullptr;  // (A/B knob: the tiled two-kernel scan for every size)
-    if (sa.n <= SCAN_ONE_MAX && !two_pass) {
-        static const bool spin = [] { const char* v = getenv("FCZ_PLAN_SPIN"); return !v || atoi(v) != 0; }();
-        if (publish && spin) {
-            sa.pub_counters = e->d_counters; sa.pub_h_counters = e->h_counters; sa.pub_h_totals = e->h_totals;
-            sa.pub_flag = e->h_flag; sa.pub_seq = ++e->plan_seq;
-            if (sa.pub_seq == 0u) sa.pub_seq = ++e->plan_seq;
-            e->plan_published = true;
-        }
-        k_scan_one<<<1, SCAN_ONE_THREADS, 0, e->stream>>>(sa);
-        e->launches += 1;
-        CK(cudaGetLastError());
-        return FCZ_OK;
-    }
     k_scan_partials<<<ntiles, SCAN_THREADS, 0, e->stream>>>(sa);
     k_scan_final<<<ntiles, SCAN_THREADS, 0, e->stream>>>(sa);
     e->launches += 2;
@@ -1907,16 +1829,6 @@ static int run_scan(fcz_engine* e, ScanArgs& sa, bool publish = false) {
 
 // counters + totals -> pinned host, then wait for them
 static int fetch_plan(fcz_engine* e) {
-    if (e->plan_published) {
-        // the scan kernel wrote counters and totals into pinned memory and raised the flag: poll it (a kernel that failed
-        // never raises it: after 2 s fall through to the synchronising path, which reports the error)
-        e->plan_published = false;
-        const auto t0 = std::chrono::steady_clock::now();
-        for (uint32_t spins = 0;; spins++) {
-            if (*e->h_flag == e->plan_seq) { std::atomic_thread_fence(std::memory_order_acquire); return FCZ_OK; }
-            if ((spins & 0xFFFu) == 0xFFFu && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) break;
-        }
-    }
     CK(cudaMemcpyAsync(e->h_counters, e->d_counters, sizeof(uint32_t) * (2 * FCZ_NTIER + 2), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(e->h_totals, e->d_totals, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1969,7 +1881,7 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
     memset(&sa, 0, sizeof sa);
     sa.n = n; sa.narr = 1;
     sa.in[0] = po.v0; sa.out[0] = out->blob_off; sa.out64[0] = 1;
-    if ((rc = run_scan(e, sa, true))) return rc;  // nothing else is enqueued between the scan and the wait
+    if ((rc = run_scan(e, sa))) return rc;
     if ((rc = fetch_plan(e))) return rc;
     *total_bytes = e->h_totals[0];
     if (*total_bytes > out->bytes_cap) return fail(e, FCZ_E_CAPACITY, "encode needs %llu bytes, capacity %llu",
