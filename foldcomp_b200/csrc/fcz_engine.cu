@@ -251,19 +251,37 @@ __device__ __forceinline__ uint8_t* stage_in(DevCtx& cx, uint8_t* buf, const uin
     return dst0;
 }
 
-// Copy `bytes` bytes from shared (same 16-byte phase as dst, see stage buffers) to global with
-// 128-bit stores for the aligned interior.
+// Copy `bytes` bytes from shared (same 16-byte phase as dst, see stage buffers) to global: the 16-byte aligned interior by
+// ONE bulk async copy shared -> global (cp.async.bulk.global.shared::cta, SASS UBLKCP.G.S, issued by thread 0 after every
+// thread has fenced its generic-proxy writes towards the async proxy), the <16-byte head and tail by plain stores.  Every
+// thread of the block must call it; when it returns the image has been READ (thread 0 waited for the bulk group), so a
+// barrier after it frees the buffer.  FCZ_BULK_STORE=0 builds the loop of 128-bit stores instead (A/B).
+#ifndef FCZ_BULK_STORE
+#define FCZ_BULK_STORE 1
+#endif
 __device__ __forceinline__ void copy_out(const DevCtx& cx, uint8_t* dst, const uint8_t* src, uint32_t bytes) {
     const uint32_t mis = (uint32_t)((uintptr_t)dst & 15u);
     const uint32_t head = (16u - mis) & 15u;
     const uint32_t hb = head < bytes ? head : bytes;
     uint32_t body = 0;
     if (bytes > head) body = (bytes - head) & ~15u;
+#if FCZ_BULK_STORE
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (cx.tid == 0 && body) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head), "r"(smem_u32(src + head)), "r"(body) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    for (uint32_t i = cx.tid; i < hb; i += cx.nthr) dst[i] = src[i];
+    for (uint32_t i = hb + body + cx.tid; i < bytes; i += cx.nthr) dst[i] = src[i];
+    if (cx.tid == 0 && body) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#else
     for (uint32_t i = cx.tid; i < hb; i += cx.nthr) dst[i] = src[i];
     const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
     uint4* d4 = reinterpret_cast<uint4*>(dst + head);
     for (uint32_t i = cx.tid; i < (body >> 4); i += cx.nthr) d4[i] = s4[i];
     for (uint32_t i = hb + body + cx.tid; i < bytes; i += cx.nthr) dst[i] = src[i];
+#endif
 }
 
 // ========================================================================================== encode
