@@ -217,6 +217,7 @@ struct DevCtx {
     // integer warp reductions (REDUX.MIN / REDUX.MAX) and shared / global atomics: floats go through fcz::ford
     __device__ __forceinline__ int32_t wmin_i(int32_t v) { return __reduce_min_sync(0xffffffffu, v); }
     __device__ __forceinline__ int32_t wmax_i(int32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+    __device__ __forceinline__ void copy_out_same_phase(char* dst, const char* src, uint32_t bytes) const;  // = copy_out (below)
     __device__ __forceinline__ void atomic_min_u(uint32_t* p, uint32_t v) { atomicMin(p, v); }
     __device__ __forceinline__ void atomic_or_u(uint32_t* p, uint32_t v) { atomicOr(p, v); }
     __device__ __forceinline__ void atomic_min_i(int32_t* p, int32_t v) { atomicMin(p, v); }
@@ -282,6 +283,10 @@ __device__ __forceinline__ void copy_out(const DevCtx& cx, uint8_t* dst, const u
     for (uint32_t i = cx.tid; i < (body >> 4); i += cx.nthr) d4[i] = s4[i];
     for (uint32_t i = hb + body + cx.tid; i < bytes; i += cx.nthr) dst[i] = src[i];
 #endif
+}
+
+__device__ __forceinline__ void DevCtx::copy_out_same_phase(char* dst, const char* src, uint32_t bytes) const {
+    copy_out(*this, reinterpret_cast<uint8_t*>(dst), reinterpret_cast<const uint8_t*>(src), bytes);
 }
 
 // ========================================================================================== encode

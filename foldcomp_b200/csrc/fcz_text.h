@@ -488,7 +488,7 @@ FCZ_HD void pdb_emit_unit(Ctx& cx, const TextTables* tt, const PdbChain& ch, uin
     }
     if (uniform) {
         cx.sync();
-        copy_same_phase(cx, g, s, FCZ_PDB_LINE * n);
+        cx.copy_out_same_phase(g, s, FCZ_PDB_LINE * n);  // device: one bulk async copy shared -> global; host model: copy_same_phase
     }
     cx.sync();
 }

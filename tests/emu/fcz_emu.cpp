@@ -25,6 +25,7 @@ struct HostCtx {
     uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
     int32_t wmin_i(int32_t v) { return v; }
     int32_t wmax_i(int32_t v) { return v; }
+    void copy_out_same_phase(char* dst, const char* src, uint32_t bytes) { copy_same_phase(*this, dst, src, bytes); }
     void atomic_min_u(uint32_t* p, uint32_t v) { if (v < *p) *p = v; }
     void atomic_or_u(uint32_t* p, uint32_t v) { *p |= v; }
     void atomic_min_i(int32_t* p, int32_t v) { if (v < *p) *p = v; }
