@@ -515,8 +515,7 @@ __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
         }
         if (a.term && cx.tid == 0) (a.cfg.staged ? sB : gdst)[size - 1u] = 0;  // encode_chain ended with a barrier
         if (a.cfg.staged) {
-            if (a.term) __syncthreads();
-            copy_out(cx, gdst, sB, size);
+            copy_out(cx, gdst, sB, size);  // (synchronises the block first: the terminator is in)
             cx.mark(4);
             if (a.cfg.stage_x) cx.parity ^= 1u;
             cx.staged = false;
@@ -838,11 +837,11 @@ __global__ void __launch_bounds__(1024) k_dec_front(Dec2Args a) {
     __syncthreads();
     cx.mark(8);
     dec_passes(cx, a.tables, ch);
-    __syncthreads();
     cx.mark(9);
-    float4* gseg = reinterpret_cast<float4*>(a.seg + (size_t)(g0 - a.s_base) * FCZ_SEG_FLOATS);
-    const float4* sseg = reinterpret_cast<const float4*>(ch.seg);
-    for (uint32_t e = cx.tid; e < nA * (FCZ_SEG_FLOATS / 4u); e += cx.nthr) gseg[e] = sseg[e];
+    // (copy_out fences every thread's writes and synchronises the block before the copy is issued)
+    // the segment scratch (352 bytes per segment, 16-byte aligned on both sides) leaves by one bulk async copy
+    copy_out(cx, reinterpret_cast<uint8_t*>(a.seg + (size_t)(g0 - a.s_base) * FCZ_SEG_FLOATS), reinterpret_cast<const uint8_t*>(ch.seg),
+             nA * FCZ_SEG_FLOATS * 4u);
     cx.mark(14);
 }
 
@@ -971,9 +970,8 @@ __global__ void __launch_bounds__(1024) k_dec_back(Dec2Args a) {
     __syncthreads();
     cx.mark(11);
     dec_side(cx, a.tables, ch);
-    __syncthreads();
     cx.mark(12);
-    copy_out(cx, gdst, sdst, 12u * A);
+    copy_out(cx, gdst, sdst, 12u * A);  // (fences every thread's writes and synchronises the block first)
     cx.mark(14);
 }
 
