@@ -43,6 +43,9 @@ struct Tables {
     float blen[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];
     cs bang[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];  // (cos, sin) of the table bond angle
     cs sc_tor[256];  // (cos, sin) of every side-chain torsion byte: FixedAngleDiscretizer(255).continuize(b)
+    // one 16-byte entry per (residue code, slot) for the decoder's side-chain placement: predecessors, bond length and
+    // (cos, sin) of the bond angle come with ONE 128-bit load instead of three look-ups
+    struct alignas(16) ScEntry { uint32_t pred; float blen; cs bang; } sc_ent[FCZ_CODE_ROWS][FCZ_MAX_ATOMS];
 };
 
 // The side-chain byte the reference stores for a torsion whose cosine is the float c
@@ -111,6 +114,9 @@ inline void build_tables(Tables* t) {
             float r = (float)((double)FCZ_BANG[c][k] * M_PI / 180.0);
             t->bang[row][k].c = cosf(r);
             t->bang[row][k].s = sinf(r);
+            t->sc_ent[row][k].pred = FCZ_PRED[c][k];
+            t->sc_ent[row][k].blen = t->blen[row][k];
+            t->sc_ent[row][k].bang = t->bang[row][k];
         }
     }
     for (int b = 0; b < 256; b++) {  // src/foldcomp.cpp:338-369 + src/nerf.cpp:64,66-70
@@ -1119,16 +1125,16 @@ FCZ_HD void dec_side(Ctx& cx, const Tables* tb, const DecChain& ch) {
             const uint8_t* sb = sc + (o - 3u * r);
             // the table entries of placement k+1 are fetched while placement k is computed (they depend on the residue code
             // and the stored byte only): the dependent look-ups were the kernel's hottest line
-            unsigned pp_n = 0;
-            float len_n = 0.f;
-            cs ang_n = {0.f, 0.f}, tor_n = {0.f, 0.f};
-            if (n > 3u) { pp_n = tb->pred[code][3]; len_n = tb->blen[code][3]; ang_n = tb->bang[code][3]; tor_n = tb->sc_tor[sb[0]]; }
+            const Tables::ScEntry* ent = tb->sc_ent[code];
+            Tables::ScEntry e_n = ent[3];
+            cs tor_n = {0.f, 0.f};
+            if (n > 3u) tor_n = tb->sc_tor[sb[0]];
             for (uint32_t k = 3u; k < n; k++) {
-                const unsigned pp = pp_n;
-                const float len = len_n;
-                const cs ang = ang_n, tor = tor_n;
-                if (k + 1u < n) { pp_n = tb->pred[code][k + 1u]; len_n = tb->blen[code][k + 1u]; ang_n = tb->bang[code][k + 1u]; tor_n = tb->sc_tor[sb[k - 2u]]; }
-                st3(R + 3u * k, place_from(ld3(R + 3u * (pp & 15u)), ld3(R + 3u * ((pp >> 4) & 15u)), ld3(R + 3u * ((pp >> 8) & 15u)), len, ang, tor));
+                const Tables::ScEntry e = e_n;
+                const cs tor = tor_n;
+                if (k + 1u < n) { e_n = ent[k + 1u]; tor_n = tb->sc_tor[sb[k - 2u]]; }
+                const unsigned pp = e.pred;
+                st3(R + 3u * k, place_from(ld3(R + 3u * (pp & 15u)), ld3(R + 3u * ((pp >> 4) & 15u)), ld3(R + 3u * ((pp >> 8) & 15u)), e.blen, e.bang, tor));
             }
         }
         cx.sync();
