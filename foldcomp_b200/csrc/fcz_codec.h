@@ -17,6 +17,7 @@
 #ifndef FCZ_CODEC_H
 #define FCZ_CODEC_H
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/fcz_engine.h"
@@ -106,6 +107,7 @@ inline void build_tables(Tables* t) {
     for (int row = 0; row < FCZ_CODE_ROWS; row++) {
         const int c = (int)norm_code((unsigned)row);
         t->natoms[row] = FCZ_NATOMS[c];
+        if (natoms_packed((unsigned)row) != (uint32_t)FCZ_NATOMS[c]) abort();  // the packed constants of fcz_format.h went stale
         t->name1[row] = (uint8_t)FCZ_NAME1[c];
         for (int k = 0; k < FCZ_MAX_ATOMS; k++) {
             t->alt[row][k] = FCZ_ALT[c][k];
@@ -386,11 +388,11 @@ FCZ_HD void encode_chain(Ctx& cx, const Tables* tb, const EncChain& ch) {
         uint32_t r0 = cx.tid * chunk; if (r0 > L) r0 = L;
         uint32_t r1 = r0 + chunk; if (r1 > L) r1 = L;
         uint32_t sum = 0;
-        for (uint32_t r = r0; r < r1; r++) sum += tb->natoms[ch.type[r]];
+        for (uint32_t r = r0; r < r1; r++) sum += natoms_packed(ch.type[r]);
         uint32_t base = cx.excl_scan(sum);
         for (uint32_t r = r0; r < r1; r++) {
             ch.aoff[r] = base;
-            uint32_t n = tb->natoms[ch.type[r]];
+            uint32_t n = natoms_packed(ch.type[r]);
             for (uint32_t k = 3u; k < n; k++) ch.sres[base - 3u * r + (k - 3u)] = (uint16_t)r;
             base += n;
         }
@@ -784,12 +786,12 @@ FCZ_HD void dec_unpack(Ctx& cx, const Tables* tb, const DecChain& ch) {
         uint32_t r1 = r0 + chunk; if (r1 > L) r1 = L;
         uint32_t sum = 0;
         for (uint32_t r = r0; r < r1; r++) {
-            sum += tb->natoms[rec[8u * r] >> 3];
+            sum += natoms_packed(rec[8u * r] >> 3);
         }
         uint32_t base = cx.excl_scan(sum);
         for (uint32_t r = r0; r < r1; r++) {
             ch.aoff[r] = base;
-            base += tb->natoms[rec[8u * r] >> 3];
+            base += natoms_packed(rec[8u * r] >> 3);
         }
         if (r1 == L) ch.aoff[L] = base;
         const float tmin = get_f32(blob + y.o_temp), tcf = get_f32(blob + y.o_temp + 4);

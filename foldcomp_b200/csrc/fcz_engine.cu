@@ -351,7 +351,7 @@ __global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* 
     uint32_t sum = 0, bad = 0;
     for (uint32_t r = lane; r < L; r += 32) {
         uint32_t code = res_type[r0 + r];
-        uint32_t na = code < FCZ_NUM_CODES ? tb->natoms[code] : 0u;
+        uint32_t na = code < FCZ_NUM_CODES ? natoms_packed(code) : 0u;
         bad |= (na == 0u);
         sum += na;
     }
@@ -609,7 +609,7 @@ __global__ void k_dec_plan(uint32_t c0, uint32_t n, const uint64_t* blob_off, co
         } else {
             uint32_t sum = 0, bad = 0;
             for (uint32_t r = lane; r < L; r += 32) {
-                uint32_t nat = tb->natoms[blob[y.o_rec + 8u * r] >> 3];
+                uint32_t nat = natoms_packed(blob[y.o_rec + 8u * r] >> 3);
                 bad |= (nat == 0u);
                 sum += nat;
             }
@@ -1277,9 +1277,9 @@ __global__ void __launch_bounds__(128) k_raw_angles(RawAnglesArgs a) {
     uint32_t b0 = threadIdx.x * chunk; if (b0 > L) b0 = L;
     uint32_t b1 = b0 + chunk; if (b1 > L) b1 = L;
     uint32_t sum = 0;
-    for (uint32_t r = b0; r < b1; r++) sum += a.tables->natoms[type[r] & 31u];
+    for (uint32_t r = b0; r < b1; r++) sum += natoms_packed(type[r] & 31u);
     uint32_t base = cx.excl_scan(sum);
-    for (uint32_t r = b0; r < b1; r++) { aoff[r] = base; base += a.tables->natoms[type[r] & 31u]; }
+    for (uint32_t r = b0; r < b1; r++) { aoff[r] = base; base += natoms_packed(type[r] & 31u); }
     if (b1 == L && b0 < L) aoff[L] = base;
     __syncthreads();
     EncChain ch;

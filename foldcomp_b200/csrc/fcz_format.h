@@ -30,6 +30,12 @@ enum {
 // rows of the device-side residue tables (5-bit code space) and the reference's mapping of unknown codes to UNK
 #define FCZ_CODE_ROWS 32
 FCZ_HD unsigned norm_code(unsigned code) { return code < (unsigned)FCZ_NUM_CODES ? code : (unsigned)FCZ_CODE_UNK; }
+// Table atom count of a 5-bit residue code (rows 24..31 = UNK, like Tables::natoms) from two 64-bit constants, four bits per
+// code: pure arithmetic where a table look-up would be a dependent load (build_tables checks it against FCZ_NATOMS).
+FCZ_HD uint32_t natoms_packed(unsigned code5) {
+    const unsigned long long k = (code5 & 16u) ? 0x3333333330007ce7ull : 0x67b8988a499688b5ull;
+    return (uint32_t)(k >> (4u * (code5 & 15u))) & 15u;
+}
 
 // header order of the six backbone arrays
 enum { A_PHI = 0, A_PSI = 1, A_OMEGA = 2, A_NCAC = 3, A_CACN = 4, A_CNCA = 5 };

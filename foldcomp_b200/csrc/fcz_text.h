@@ -386,17 +386,17 @@ FCZ_HD uint32_t pdb_plan_chain(Ctx& cx, const TextTables* tt, const PdbChain& ch
     uint32_t r0 = cx.tid * chunk; if (r0 > L) r0 = L;
     uint32_t r1 = r0 + chunk; if (r1 > L) r1 = L;
     uint32_t sum = 0;
-    for (uint32_t r = r0; r < r1; r++) sum += tt->natoms[ch.type[r] & 31u];
+    for (uint32_t r = r0; r < r1; r++) sum += natoms_packed(ch.type[r] & 31u);
     uint32_t base = cx.excl_scan(sum);
     const uint32_t a_first = base;
-    for (uint32_t r = r0; r < r1; r++) { ch.aoff[r] = base; base += tt->natoms[ch.type[r] & 31u]; }
+    for (uint32_t r = r0; r < r1; r++) { ch.aoff[r] = base; base += natoms_packed(ch.type[r] & 31u); }
     if (r1 == L) ch.aoff[L] = base;
     cx.sync();
     // bytes beyond 81 (zero for ordinary coordinates): the cheap fits-its-columns test per atom, the exact
     // measurement only for the atoms that fail it
     uint32_t extra = 0, atom = a_first;
     for (uint32_t r = r0; r < r1; r++) {
-        const uint32_t n = tt->natoms[ch.type[r] & 31u];
+        const uint32_t n = natoms_packed(ch.type[r] & 31u);
         for (uint32_t k = 0; k < n; k++, atom++) {
             const AtomRec a = pdb_atom_rec(tt, ch, r, k, atom);
             if (!atom_line_uniform(a)) extra += atom_line_extra(a);
@@ -406,11 +406,11 @@ FCZ_HD uint32_t pdb_plan_chain(Ctx& cx, const TextTables* tt, const PdbChain& ch
     const uint32_t head = title_lines_len(ch.title_len);
     atom = a_first;
     if (extra == 0u) {  // this thread's residues are uniform: offsets follow from the atom offsets alone
-        for (uint32_t r = r0; r < r1; r++) { ch.toff[r] = head + FCZ_PDB_LINE * atom + ebase; atom += tt->natoms[ch.type[r] & 31u]; }
+        for (uint32_t r = r0; r < r1; r++) { ch.toff[r] = head + FCZ_PDB_LINE * atom + ebase; atom += natoms_packed(ch.type[r] & 31u); }
     } else {
         for (uint32_t r = r0; r < r1; r++) {
             ch.toff[r] = head + FCZ_PDB_LINE * atom + ebase;
-            const uint32_t n = tt->natoms[ch.type[r] & 31u];
+            const uint32_t n = natoms_packed(ch.type[r] & 31u);
             for (uint32_t k = 0; k < n; k++, atom++) ebase += atom_line_extra(pdb_atom_rec(tt, ch, r, k, atom));
         }
     }
