@@ -650,7 +650,21 @@ __global__ void k_dec_plan(uint32_t c0, uint32_t n, const uint64_t* blob_off, co
 // of a chain in shared memory, hand-over through global scratch), and, for chains whose working set does not fit
 // 227 KB, one kernel per phase with the whole workspace in global memory (k_dec_unpack ... k_dec_side).
 
+// Everything the decode kernels need to know about a chain before they touch its data, gathered by k_plan_chunks at the
+// chain's position in the tier list: one 64-byte load where the kernels would chase list -> six offset arrays (two
+// dependent round trips at the start of every block).
+struct alignas(16) DecDesc {
+    uint32_t c, r0, L, A;
+    uint32_t t0, T, g0, nA;
+    uint64_t a0, b0;
+    uint32_t blob_len;
+    int32_t status;
+    uint32_t pad[2];
+};
+static_assert(sizeof(DecDesc) == 64, "DecDesc is four 16-byte words");
+
 struct Dec2Args {
+    const DecDesc* desc;      // per position of `list` (device-planned batches), or null: the kernels read the offset arrays
     const uint64_t* blob_off;
     const uint8_t* bytes;
     const uint32_t* res_off;
@@ -781,15 +795,23 @@ __host__ __device__ inline BackSmem back_smem(uint32_t max_L, uint32_t max_ancho
 
 __global__ void __launch_bounds__(1024) k_dec_front(Dec2Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t c = a.list[blockIdx.x];
-    // everything about the chain from the offset arrays (independent loads, one round trip): the plan has
-    // already checked them against the blob header
-    const int32_t st = a.status[c];
-    const uint64_t b0 = a.blob_off[c], b1 = a.blob_off[c + 1];
-    const uint32_t r0 = a.res_off[c], L = a.res_off[c + 1] - r0;
-    const uint32_t A = (uint32_t)(a.atom_off[c + 1] - a.atom_off[c]);
-    const uint32_t t0 = a.title_off[c], T = a.title_off[c + 1] - t0;
-    const uint32_t g0 = a.seg_off[c], nA = a.seg_off[c + 1] - g0;
+    // everything about the chain: from its descriptor (one load), else from the offset arrays (list, then independent
+    // loads: two round trips); the plan has already checked them against the blob header
+    uint32_t c, r0, L, A, t0, T, g0, nA;
+    uint64_t b0, b1;
+    int32_t st;
+    if (a.desc) {
+        const DecDesc q = a.desc[blockIdx.x];
+        c = q.c; r0 = q.r0; L = q.L; A = q.A; t0 = q.t0; T = q.T; g0 = q.g0; nA = q.nA; b0 = q.b0; b1 = q.b0 + q.blob_len; st = q.status;
+    } else {
+        c = a.list[blockIdx.x];
+        st = a.status[c];
+        b0 = a.blob_off[c]; b1 = a.blob_off[c + 1];
+        r0 = a.res_off[c]; L = a.res_off[c + 1] - r0;
+        A = (uint32_t)(a.atom_off[c + 1] - a.atom_off[c]);
+        t0 = a.title_off[c]; T = a.title_off[c + 1] - t0;
+        g0 = a.seg_off[c]; nA = a.seg_off[c + 1] - g0;
+    }
     if (st != FCZ_OK) return;
     const FrontSmem so = front_smem(a.max_L, a.max_anchor, a.max_blob);
     DevCtx cx = block_ctx(reinterpret_cast<uint32_t*>(smem + 64));
@@ -855,8 +877,9 @@ __global__ void __launch_bounds__(1024) k_dec_stitch_t(Dec2Args a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (uint32_t j = warp; j < G; j += nwarps) {
         if (ib + j >= a.count) continue;
-        const uint32_t c = a.list[ib + j];
-        const uint32_t s0 = a.seg_off[c], nA = a.seg_off[c + 1] - s0;
+        uint32_t s0, nA;
+        if (a.desc) { s0 = a.desc[ib + j].g0; nA = a.desc[ib + j].nA; }
+        else { const uint32_t c = a.list[ib + j]; s0 = a.seg_off[c]; nA = a.seg_off[c + 1] - s0; }
         const float* src = a.seg + (size_t)(s0 - a.s_base) * FCZ_SEG_FLOATS;
         float* dst = sm + (size_t)j * cstride;
         const uint32_t ne = nA * SegPacked::N;
@@ -879,14 +902,17 @@ __global__ void __launch_bounds__(1024) k_dec_stitch_t(Dec2Args a) {
     }
     __syncthreads();
     if (threadIdx.x < G && ib + threadIdx.x < a.count) {
-        const uint32_t c = a.list[ib + threadIdx.x];
-        dec_stitch_core<SegPacked>(sm + (size_t)threadIdx.x * cstride, 1, (int)(a.seg_off[c + 1] - a.seg_off[c]) - 1);
+        uint32_t nA;
+        if (a.desc) nA = a.desc[ib + threadIdx.x].nA;
+        else { const uint32_t c = a.list[ib + threadIdx.x]; nA = a.seg_off[c + 1] - a.seg_off[c]; }
+        dec_stitch_core<SegPacked>(sm + (size_t)threadIdx.x * cstride, 1, (int)nA - 1);
     }
     __syncthreads();
     for (uint32_t j = warp; j < G; j += nwarps) {
         if (ib + j >= a.count) continue;
-        const uint32_t c = a.list[ib + j];
-        const uint32_t s0 = a.seg_off[c], nA = a.seg_off[c + 1] - s0;
+        uint32_t s0, nA;
+        if (a.desc) { s0 = a.desc[ib + j].g0; nA = a.desc[ib + j].nA; }
+        else { const uint32_t c = a.list[ib + j]; s0 = a.seg_off[c]; nA = a.seg_off[c + 1] - s0; }
         float* out = a.seg + (size_t)(s0 - a.s_base) * FCZ_SEG_FLOATS;
         const float* srcp = sm + (size_t)j * cstride;
         for (uint32_t e = lane; e < nA * 21u; e += 32) {  // S[9] T[12] are adjacent in the full layout
@@ -899,14 +925,22 @@ __global__ void __launch_bounds__(1024) k_dec_stitch_t(Dec2Args a) {
 __global__ void __launch_bounds__(1024) k_dec_back(Dec2Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t wsum[32];
-    const uint32_t c = a.list[blockIdx.x];
-    const int32_t st = a.status[c];
-    const uint64_t b0 = a.blob_off[c];
-    const uint32_t r0 = a.res_off[c], L = a.res_off[c + 1] - r0;
-    const uint64_t a0 = a.atom_off[c];
-    const uint32_t A = (uint32_t)(a.atom_off[c + 1] - a0);
-    const uint32_t T = a.title_off[c + 1] - a.title_off[c];
-    const uint32_t g0 = a.seg_off[c], nA = a.seg_off[c + 1] - g0;
+    uint32_t c, r0, L, A, T, g0, nA;
+    uint64_t b0, a0;
+    int32_t st;
+    if (a.desc) {
+        const DecDesc q = a.desc[blockIdx.x];
+        c = q.c; r0 = q.r0; L = q.L; A = q.A; T = q.T; g0 = q.g0; nA = q.nA; b0 = q.b0; a0 = q.a0; st = q.status;
+    } else {
+        c = a.list[blockIdx.x];
+        st = a.status[c];
+        b0 = a.blob_off[c];
+        r0 = a.res_off[c]; L = a.res_off[c + 1] - r0;
+        a0 = a.atom_off[c];
+        A = (uint32_t)(a.atom_off[c + 1] - a0);
+        T = a.title_off[c + 1] - a.title_off[c];
+        g0 = a.seg_off[c]; nA = a.seg_off[c + 1] - g0;
+    }
     if (st != FCZ_OK) return;
     const BackSmem so = back_smem(a.max_L, a.max_anchor, a.max_atoms);
     DevCtx cx = block_ctx(wsum);
@@ -987,7 +1021,7 @@ __host__ __device__ inline uint32_t dec_tier_of(uint32_t L) { return L <= 384u ?
 
 __global__ void __launch_bounds__(256) k_plan_chunks(uint32_t n, uint32_t sub_res, const uint32_t* res_off, const uint32_t* seg_off,
                                                      const uint64_t* atom_off, const uint64_t* blob_off, const int32_t* status,
-                                                     uint32_t* list, uint32_t* dmax, uint32_t* out) {
+                                                     uint32_t* list, uint32_t* dmax, uint32_t* out, const uint32_t* title_off, DecDesc* desc) {
     __shared__ uint32_t s_last;
     const uint64_t R = res_off[n];
     uint64_t per64 = n ? ((uint64_t)sub_res * n + (R ? R - 1 : 0)) / (R ? R : 1) : 1;
@@ -1016,6 +1050,7 @@ __global__ void __launch_bounds__(256) k_plan_chunks(uint32_t n, uint32_t sub_re
         m[3] = (uint32_t)(atom_off[c + 1] - atom_off[c]);
         t = dec_tier_of(m[0]);
     }
+    size_t li = 0;  // the chain's position in the tier lists
     // a block whose chains all sit in one sub-batch (the usual case) aggregates in shared memory first
     const uint32_t cf = blockIdx.x * blockDim.x, cl = (cf + blockDim.x < n ? cf + blockDim.x : n) - 1u;
     if (cf < n && cf / per == cl / per) {
@@ -1034,12 +1069,23 @@ __global__ void __launch_bounds__(256) k_plan_chunks(uint32_t n, uint32_t sub_re
             for (int j = 0; j < 4; j++) atomicMax(&d[1 + j], s_agg[threadIdx.x][1 + j]);
         }
         __syncthreads();
-        if (valid) list[(size_t)t * n + (size_t)k * per + s_agg[t][5] + pos] = c;
+        if (valid) li = (size_t)t * n + (size_t)k * per + s_agg[t][5] + pos;
     } else if (valid) {
         uint32_t* d = dmax + 5u * (FCZ_DEC_TIERS * k + t);
         const uint32_t pos = atomicAdd(&d[0], 1u);
-        list[(size_t)t * n + (size_t)k * per + pos] = c;
+        li = (size_t)t * n + (size_t)k * per + pos;
         for (int j = 0; j < 4; j++) atomicMax(&d[1 + j], m[j]);
+    }
+    if (valid) {
+        list[li] = c;
+        if (desc) {
+            DecDesc q;
+            q.c = c; q.r0 = res_off[c]; q.L = m[0]; q.A = m[3];
+            q.t0 = title_off[c]; q.T = title_off[c + 1] - q.t0; q.g0 = seg_off[c]; q.nA = m[1];
+            q.a0 = atom_off[c]; q.b0 = blob_off[c]; q.blob_len = m[2]; q.status = FCZ_OK;
+            q.pad[0] = 0u; q.pad[1] = 0u;
+            desc[li] = q;
+        }
     }
     __threadfence();
     __syncthreads();
@@ -1501,6 +1547,7 @@ struct fcz_engine {
     uint64_t* h_totals = nullptr;
     uint64_t chunk_bytes = FCZ_CHUNK_BYTES;  // coordinates per chunk of a host-memory batch (FCZ_CHUNK_MB)
     uint32_t h2d_depth = FCZ_H2D_DEPTH, d2h_depth = FCZ_D2H_DEPTH;  // FCZ_H2D_QUEUE / FCZ_D2H_QUEUE, 0 = unlimited
+    bool dec_desc_valid = false;  // the last decode plan filled d_dec_desc (device-planned batches)
     uint32_t dec_sub_res = FCZ_SUB_RESIDUES;  // residues per decode sub-batch (FCZ_DEC_SUB_RESIDUES overrides)
     uint32_t* h_bounds = nullptr;    // pinned: [0] nchunks, then chain / residue / segment-slot bounds of the decode sub-batches
     // staging for host-memory batches
@@ -1509,7 +1556,7 @@ struct fcz_engine {
     void* h_stage = nullptr;  // pinned staging for the per-chain arrays of a host-memory decode (one H2D copy)
     size_t h_stage_cap = 0;
     struct { uint64_t *blob_off, *atom_off; uint32_t *res_off, *title_off, *seg_off, *list; int32_t* status; } dh = {};
-    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax, d_dec_list;  // decoder: segment offsets + hand-over workspace between the phase kernels
+    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax, d_dec_list, d_dec_desc;  // decoder: segment offsets + hand-over workspace between the phase kernels
     // plan made on the host by fcz_decode_plan(host) for the following fcz_decode_batch(host)
     struct Launch { uint32_t chunk, tier, first, count; };
     struct HostPlan {
@@ -1678,7 +1725,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->v3, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
                       &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets, &e->enc_gws, &e->d_stage, &e->ws_aoff, &e->ws_toff, &e->d_unit_off, &e->d_unit_chain, &e->d_text_off, &e->d_text,
-                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list,
+                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list, &e->d_dec_desc,
                       &e->p_line_off, &e->p_lines, &e->p_rstart, &e->p_raw, &e->p_scratch};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -2466,7 +2513,7 @@ static int dec2_workspace(fcz_engine* e, Dec2Sub* subs, size_t nsub) {
 }
 
 // the phase kernels over one sub-batch (a carries the batch pointers, list = device chain list)
-static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb, const uint32_t* list) {
+static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb, const uint32_t* list, const DecDesc* desc = nullptr) {
     const uint32_t nch = sb.c1 - sb.c0;
     if (!nch) return FCZ_OK;
     a.c0 = sb.c0; a.c1 = sb.c1; a.r_base = sb.r0; a.s_base = sb.s0;
@@ -2499,6 +2546,7 @@ static int dec2_launch(fcz_engine* e, Dec2Args a, const Dec2Sub& sb, const uint3
             if (fork) CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
             const uint32_t first = h ? tr.count / 2u : 0u, cnt = halves == 2 ? (h ? tr.count - tr.count / 2u : tr.count / 2u) : tr.count;
             a.list = list + tr.list_off + first; a.count = cnt;
+            a.desc = desc ? desc + tr.list_off + first : nullptr;
             // stitch: one wave when it fits -- chains per block = ceil(chains / SMs), bounded by shared memory
             const uint32_t cbytes = stitch_chain_bytes(tr.max_anchor);
             uint32_t G = (cnt + (uint32_t)e->num_sms - 1u) / (uint32_t)e->num_sms;
@@ -2789,8 +2837,12 @@ static int decode_plan_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain
     sa.in[3] = po.v3; sa.out[3] = e->d_seg_off.p; sa.out64[3] = 0;
     if ((rc = run_scan(e, sa))) return rc;
     if ((rc = ensure(e, e->d_dec_list, 4ull * FCZ_DEC_TIERS * n + 16))) return rc;
+    static const bool use_desc = [] { const char* v = getenv("FCZ_DEC_DESC"); return !v || atoi(v) != 0; }();  // (A/B knob)
+    if (use_desc && (rc = ensure(e, e->d_dec_desc, sizeof(DecDesc) * (size_t)FCZ_DEC_TIERS * n + 64))) return rc;
+    e->dec_desc_valid = use_desc;
     k_plan_chunks<<<n / 256 + 1, 256, 0, e->stream>>>(n, e->dec_sub_res, out->res_off, (uint32_t*)e->d_seg_off.p, out->atom_off, in->blob_off,
-                                                  po.status, (uint32_t*)e->d_dec_list.p, (uint32_t*)e->d_submax.p, e->h_bounds);
+                                                  po.status, (uint32_t*)e->d_dec_list.p, (uint32_t*)e->d_submax.p, e->h_bounds, out->title_off,
+                                                  use_desc ? (DecDesc*)e->d_dec_desc.p : nullptr);
     e->launches++;
     if ((rc = fetch_plan(e))) return rc;
     totals->n_res = e->h_totals[0];
@@ -2832,7 +2884,7 @@ static int decode_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain_batc
     {
         ProfSpan ps(e, FCZ_PROF_DECODE);
         for (uint32_t k = 0; k < nsub; k++)
-            if ((rc = dec2_launch(e, a, subs[k], (const uint32_t*)e->d_dec_list.p))) return rc;
+            if ((rc = dec2_launch(e, a, subs[k], (const uint32_t*)e->d_dec_list.p, e->dec_desc_valid ? (const DecDesc*)e->d_dec_desc.p : nullptr))) return rc;
     }
     CK(cudaGetLastError());
     return FCZ_OK;
