@@ -291,6 +291,15 @@ __device__ __forceinline__ void DevCtx::copy_out_same_phase(char* dst, const cha
 
 // ========================================================================================== encode
 
+// What k_encode needs to know about a chain before it touches its data, written by k_enc_plan at the chain's position in
+// its tier list (one 48-byte load instead of list -> three offset arrays at the top of every trip).
+struct alignas(16) EncDesc {
+    uint32_t c, r0, L, A;
+    uint32_t t0, T, pad0, pad1;
+    uint64_t a0, pad2;
+};
+static_assert(sizeof(EncDesc) == 48, "EncDesc is three 16-byte words");
+
 struct EncArgs {
     const uint32_t* res_off;
     const uint64_t* atom_off;
@@ -302,6 +311,7 @@ struct EncArgs {
     const fcz_chain_meta* meta;
     const uint64_t* blob_off;
     uint8_t* bytes;
+    const struct EncDesc* desc;  // per position of `list` (device-planned batches), or null: the kernel reads the offset arrays
     const uint32_t* list;   // chains of this tier
     const uint32_t* count;  // their number (device-planned batches) ...
     uint32_t count_val;     // ... or by value when count == nullptr (host-planned batches)
@@ -325,6 +335,7 @@ struct PlanOut {
     int32_t* status;       // per-chain status (engine copy)
     uint32_t* tier_count;  // [FCZ_NTIER]
     uint32_t* tier_list;   // [FCZ_NTIER][n]
+    EncDesc* enc_desc;     // [FCZ_NTIER][n] or null (encode plan only)
 };
 
 struct TierTable {
@@ -381,6 +392,11 @@ __global__ void k_enc_plan(uint32_t n, const uint32_t* res_off, const uint64_t* 
         if (tier >= 0) {
             uint32_t pos = atomicAdd(&po.tier_count[tier], 1u);
             po.tier_list[(size_t)tier * n + pos] = c;
+            if (po.enc_desc) {
+                EncDesc q;
+                q.c = c; q.r0 = r0; q.L = L; q.A = sum; q.t0 = title_off[c]; q.T = T; q.pad0 = 0u; q.pad1 = 0u; q.a0 = atom_off[c]; q.pad2 = 0ull;
+                po.enc_desc[(size_t)tier * n + pos] = q;
+            }
             if (tt.t[tier].gws) atomicMax(&po.tier_count[2 * FCZ_NTIER], L);  // sizes the long tier's global workspace
         }
     }
@@ -420,11 +436,18 @@ __global__ void __maxnreg__(FCZ_ENC_MAXREG) k_encode(EncArgs a) {
 #ifdef FCZ_PHASE_TIMING
         cx.t_last = clock64();
 #endif
-        const uint32_t c = a.list[t];
-        const uint32_t r0 = a.res_off[c], L = a.res_off[c + 1] - r0;
-        const uint64_t a0 = a.atom_off[c];
-        const uint32_t A = (uint32_t)(a.atom_off[c + 1] - a0);
-        const uint32_t t0 = a.title_off[c], T = a.title_off[c + 1] - t0;
+        uint32_t c, r0, L, A, t0, T;
+        uint64_t a0;
+        if (a.desc) {
+            const EncDesc q = a.desc[t];
+            c = q.c; r0 = q.r0; L = q.L; A = q.A; t0 = q.t0; T = q.T; a0 = q.a0;
+        } else {
+            c = a.list[t];
+            r0 = a.res_off[c]; L = a.res_off[c + 1] - r0;
+            a0 = a.atom_off[c];
+            A = (uint32_t)(a.atom_off[c + 1] - a0);
+            t0 = a.title_off[c]; T = a.title_off[c + 1] - t0;
+        }
         const uint64_t b0 = a.blob_off[c];
         const uint32_t size = (uint32_t)(a.blob_off[c + 1] - b0);
 
@@ -1556,7 +1579,7 @@ struct fcz_engine {
     void* h_stage = nullptr;  // pinned staging for the per-chain arrays of a host-memory decode (one H2D copy)
     size_t h_stage_cap = 0;
     struct { uint64_t *blob_off, *atom_off; uint32_t *res_off, *title_off, *seg_off, *list; int32_t* status; } dh = {};
-    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax, d_dec_list, d_dec_desc;  // decoder: segment offsets + hand-over workspace between the phase kernels
+    DevBuf d_seg_off, sc_aoff, sc_segid, sc_tor, sc_ang, sc_rev, sc_seg, sc_loc, d_submax, d_dec_list, d_dec_desc, d_enc_desc;  // decoder: segment offsets + hand-over workspace between the phase kernels
     // plan made on the host by fcz_decode_plan(host) for the following fcz_decode_batch(host)
     struct Launch { uint32_t chunk, tier, first, count; };
     struct HostPlan {
@@ -1725,7 +1748,7 @@ void fcz_engine_destroy(fcz_engine* e) {
     DevBuf* bufs[] = {&e->v0, &e->v1, &e->v2, &e->v3, &e->status, &e->tier_list, &e->partial, &e->d_res_off, &e->d_atom_off,
                       &e->d_title_off, &e->d_res_type, &e->d_bfactor, &e->d_xyz, &e->d_titles, &e->d_meta,
                       &e->d_blob_off, &e->d_bytes, &e->d_status, &e->d_list, &e->d_tickets, &e->enc_gws, &e->d_stage, &e->ws_aoff, &e->ws_toff, &e->d_unit_off, &e->d_unit_chain, &e->d_text_off, &e->d_text,
-                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list, &e->d_dec_desc,
+                      &e->d_seg_off, &e->sc_aoff, &e->sc_segid, &e->sc_tor, &e->sc_ang, &e->sc_rev, &e->sc_seg, &e->sc_loc, &e->d_submax, &e->d_dec_list, &e->d_dec_desc, &e->d_enc_desc,
                       &e->p_line_off, &e->p_lines, &e->p_rstart, &e->p_raw, &e->p_scratch};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -1940,6 +1963,9 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
     po.status = out->status ? out->status : (int32_t*)e->status.p;
     po.tier_count = e->d_counters;
     po.tier_list = (uint32_t*)e->tier_list.p;
+    static const bool use_desc = [] { const char* v = getenv("FCZ_ENC_DESC"); return !v || atoi(v) != 0; }();  // (A/B knob)
+    if (use_desc && (rc = ensure(e, e->d_enc_desc, sizeof(EncDesc) * (size_t)FCZ_NTIER * n + 64))) return rc;
+    po.enc_desc = use_desc ? (EncDesc*)e->d_enc_desc.p : nullptr;
     if (n) {
         k_enc_plan<<<(n + 7) / 8, 256, 0, e->stream>>>(n, in->res_off, in->atom_off, in->title_off, in->res_type,
                                                        e->opts.anchor_threshold, e->opts.terminate_blobs ? 1u : 0u, e->d_tables, tt, po);
@@ -1970,6 +1996,7 @@ static int encode_device(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batc
         a.res_type = in->res_type; a.bfactor = in->bfactor; a.xyz = in->xyz; a.titles = in->titles; a.meta = in->meta;
         a.blob_off = out->blob_off; a.bytes = out->bytes;
         a.list = (uint32_t*)e->tier_list.p + (size_t)i * n;
+        a.desc = po.enc_desc ? po.enc_desc + (size_t)i * n : nullptr;
         a.count = e->d_counters + i;
         a.count_val = 0;
         a.ticket = e->d_counters + FCZ_NTIER + i;
@@ -2207,6 +2234,7 @@ static int encode_host(fcz_engine* e, const fcz_chain_batch* in, fcz_blob_batch*
             a.titles = (char*)e->d_titles.p; a.meta = (fcz_chain_meta*)e->d_meta.p;
             a.blob_off = (uint64_t*)e->d_blob_off.p; a.bytes = (uint8_t*)e->d_bytes.p;
             a.list = (uint32_t*)e->d_list.p + ln.first;
+            a.desc = nullptr;  // host-planned: the kernel reads the offset arrays
             a.count = nullptr; a.count_val = ln.count;
             a.ticket = (uint32_t*)e->d_tickets.p + k * FCZ_NTIER + ln.tier;
             a.tables = e->d_tables; a.b = b; a.term = e->opts.terminate_blobs ? 1u : 0u;
@@ -2824,6 +2852,7 @@ static int decode_plan_device(fcz_engine* e, const fcz_blob_batch* in, fcz_chain
     po.status = out->status ? out->status : (int32_t*)e->status.p;
     po.tier_count = e->d_counters;
     po.tier_list = (uint32_t*)e->tier_list.p;
+    po.enc_desc = nullptr;
     if (n) {
         k_dec_plan<<<(n + 7) / 8, 256, 0, e->stream>>>(0u, n, in->blob_off, in->bytes, e->d_tables, tt, po, 0);
         e->launches++;
