@@ -75,15 +75,37 @@ int main(int argc, char** argv) {
             _exit(0);  // the outputs are closed: skip unmapping the inputs and tearing down the CUDA context
         }
         if (mode == "compress") {
-            std::vector<AtomCoordinate> atoms;
-            int rc = read_pdb(in, atoms);
-            if (rc) { fprintf(stderr, "[Error] %s\n", rc == 2 ? "multiple chains" : "no atoms found"); return 1; }
-            std::string base = out.substr(out.find_last_of('/') == std::string::npos ? 0 : out.find_last_of('/') + 1);
-            comp.strTitle = base.substr(0, base.find_last_of('.'));  // main.cpp:451-465: output basename without extension
-            comp.anchorThreshold = b;
-            if ((rc = comp.compress(atoms))) { fprintf(stderr, "[Error] compress: %s\n", fcz_strerror(rc)); return 1; }
-            std::ofstream os(out, std::ios::binary);
-            comp.writeStream(os);
+            // one PDB file like the reference CLI's single-file mode (src/main.cpp:438-530): the title by its rule (HEADER id,
+            // TITLE records, else the OUTPUT's name without extension, 451-467); one .fcz per chain and fragment of continuous
+            // numbering, named <out><chain>_<fragment>.fcz when there are several (494-509)
+            std::ifstream f(in, std::ios::binary);
+            if (!f) { fprintf(stderr, "[Error] cannot read %s\n", in.c_str()); return 1; }
+            std::stringstream ss;
+            ss << f.rdbuf();
+            const std::string text = ss.str();
+            const std::string in_base = in.substr(in.find_last_of('/') == std::string::npos ? 0 : in.find_last_of('/') + 1);
+            const std::string in_stem = in_base.substr(0, in_base.find_last_of('.'));
+            const size_t dot = out.find_last_of('.'), slash = out.find_last_of('/');
+            const bool has_ext = dot != std::string::npos && (slash == std::string::npos || dot > slash);
+            const std::string out_stem = has_ext ? out.substr(0, dot) : out, out_ext = has_ext ? out.substr(dot) : std::string(".fcz");
+            std::string title = pdbTitle(text.data(), text.size(), in_base);
+            if (title == in_stem) title = out_stem;  // the reader fell back to the file name: single-file mode takes getFileParts(output).first,
+                                                     // i.e. the output path as given without its extension (src/utility.cpp:118-126)
+            std::vector<CanonicalChain> units;
+            std::vector<UnitLabel> labels;
+            int rc = parsePdbUnits(text.data(), text.size(), title, units, &labels);
+            if (rc) { fprintf(stderr, "[Error] %s\n", rc == 1 ? "no atoms found" : "malformed ATOM record"); return 1; }
+            std::vector<std::string> blobs;
+            std::vector<int> st;
+            if ((rc = FoldcompGpu::compressBatch(eng, units, b, blobs, st))) { fprintf(stderr, "[Error] compress: %s\n", fcz_strerror(rc)); return 1; }
+            for (size_t u = 0; u < units.size(); u++) {
+                if (st[u] != FCZ_OK) { fprintf(stderr, "[Error] compress: %s\n", fcz_strerror(st[u])); return 1; }
+                std::string name = out_stem;
+                if (labels[u].n_chains > 1) name += labels[u].chain;
+                if (labels[u].n_frags > 1) name += "_" + std::to_string(labels[u].frag);
+                std::ofstream os(name + out_ext, std::ios::binary);
+                os.write(blobs[u].data(), (std::streamsize)blobs[u].size());
+            }
         } else if (mode == "decompress") {
             std::ifstream is(in, std::ios::binary);
             if (!is || comp.read(is) != 0) { fprintf(stderr, "[Error] not an FCZ file\n"); return 1; }

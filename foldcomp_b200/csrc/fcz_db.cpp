@@ -243,8 +243,9 @@ std::string pdbTitle(const char* text, size_t len, const std::string& base_name)
     return t;
 }
 
-int parsePdbUnits(const char* text, size_t len, const std::string& title, std::vector<CanonicalChain>& units) {
+int parsePdbUnits(const char* text, size_t len, const std::string& title, std::vector<CanonicalChain>& units, std::vector<UnitLabel>* labels) {
     units.clear();
+    if (labels) labels->clear();
     std::vector<RawAtom> atoms;
     const int flag = read_atom_records(text, len, false, atoms);
     if (flag) return flag;
@@ -283,10 +284,14 @@ int parsePdbUnits(const char* text, size_t len, const std::string& title, std::v
             prev = atoms[i].resnum;
         }
         frags.emplace_back(fstart, ch.second);
+        int j = 0;
         for (const auto& f : frags) {
-            if (f.second <= f.first) continue;
-            units.emplace_back();
-            canonicalize_records(atoms.data() + f.first, f.second - f.first, title, units.back());
+            if (f.second > f.first) {
+                units.emplace_back();
+                canonicalize_records(atoms.data() + f.first, f.second - f.first, title, units.back());
+                if (labels) labels->push_back({atoms[ch.first].chain, j, (int)frags.size(), (int)chains.size()});
+            }
+            j++;
         }
     }
     return units.empty() ? 1 : 0;

@@ -31,7 +31,9 @@ int parsePdbChain(const char* text, size_t len, const std::string& title, Canoni
 // alternative positions dropped, cut into chains (identifyChains, src/atom_coordinate.cpp:469-497) and each chain into
 // fragments of continuous residue numbering (identifyDiscontinousResInd, 506-530), in file order.  0, 1 (no ATOM record)
 // or 3 (malformed record).
-int parsePdbUnits(const char* text, size_t len, const std::string& title, std::vector<CanonicalChain>& units);
+struct UnitLabel { char chain; int frag, n_frags, n_chains; };  // which chain / fragment a unit is (the CLI's output file names)
+int parsePdbUnits(const char* text, size_t len, const std::string& title, std::vector<CanonicalChain>& units,
+                  std::vector<UnitLabel>* labels = nullptr);
 
 // title of the chains of one PDB text as `foldcomp compress` sets it: HEADER idCode, else TITLE records, else the file name
 // (without extension); see fcz_db.cpp

@@ -20,8 +20,9 @@ def test_cli_roundtrip_matches_oracle(golden, tmp_path, name):
     pdb_in = tmp_path / "in.pdb"
     pdb_in.write_text(pdbio.format_pdb(ch, 0))
     fcz = tmp_path / "out.fcz"
-    subprocess.check_call([CLI, "compress", str(pdb_in), str(fcz)])
-    # what the reference would produce for this text input (title = output basename, main.cpp:451-465)
+    subprocess.check_call([CLI, "compress", "in.pdb", "out.fcz"], cwd=tmp_path)
+    # what the reference would produce for this text input: a text without HEADER id / TITLE record is named after the output
+    # path as given, without its extension (main.cpp:451-467, getFileParts)
     parsed = pdbio.parse_pdb_chain(pdb_in.read_text(), "out")
     want = H.oracle_encode(parsed, 0, 25)
     assert fcz.read_bytes() == want
@@ -63,3 +64,36 @@ def test_cli_tar_extract_check(golden, tmp_path):
         assert lines[1] == H.oracle_extract(want, type_, 1)
     subprocess.check_call([CLI, "check", str(tmp_path / "in.fcz"), str(tmp_path / "c.txt")])
     assert int((tmp_path / "c.txt").read_text()) == H.oracle_check(want)[1] == 0
+
+
+def test_cli_compress_like_the_reference_cli_on_chains_fragments_and_titles(tmp_path):
+    """`fcz_cli compress` on one file against the reference's own CLI (integration/_build/foldcomp_ref): a TITLE record
+    becomes the title, several chains and numbering gaps give one .fcz per chain and fragment with the reference's file
+    names (src/main.cpp:466-509)."""
+    from foldcomp_b200 import synth
+
+    ref_cli = os.path.join(H.ROOT, "integration", "_build", "foldcomp_ref")
+    if not os.path.exists(ref_cli):
+        pytest.skip("integration/_build/foldcomp_ref not built")
+    batch = synth.generate(3, [40, 55, 30], seed=17)
+    t = [pdbio.format_pdb(batch.chain(c), 0) for c in range(3)]
+    atoms = lambda c, ch, shift=0, cut=None: [
+        l[:21] + ch + "%4d" % (int(l[22:26]) + (shift if cut is not None and int(l[22:26]) > cut else 0)) + l[26:]
+        for l in t[c].splitlines() if l.startswith("ATOM")]
+    cases = {
+        "titled": t[0],                                                                      # TITLE record present
+        "plain": "\n".join(atoms(0, "A")) + "\nEND\n",                                      # no TITLE: named after the output
+        "multi": "TITLE     TWO CHAINS AND A GAP\n" + "\n".join(atoms(1, "A", 6, 20) + atoms(2, "B")) + "\nEND\n",
+    }
+    for name, text in cases.items():
+        (tmp_path / f"{name}.pdb").write_text(text)
+        for tag, cli in (("ours", CLI), ("ref", ref_cli)):
+            d = tmp_path / f"{tag}_{name}"
+            d.mkdir()
+            args = [cli, "compress"] + (["-y"] if tag == "ref" else []) + [f"../{name}.pdb", "o.fcz"]
+            r = subprocess.run(args, cwd=d, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, (tag, name, r.stdout[-300:], r.stderr[-300:])
+        ours = {f: H.masked((tmp_path / f"ours_{name}" / f).read_bytes()) for f in sorted(os.listdir(tmp_path / f"ours_{name}"))}
+        ref = {f: H.masked((tmp_path / f"ref_{name}" / f).read_bytes()) for f in sorted(os.listdir(tmp_path / f"ref_{name}"))}
+        assert ours == ref, (name, sorted(ours), sorted(ref))
+    assert len(os.listdir(tmp_path / "ours_multi")) == 3  # oA_0.fcz, oA_1.fcz, oB.fcz
