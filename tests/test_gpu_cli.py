@@ -21,19 +21,20 @@ def test_cli_roundtrip_matches_oracle(golden, tmp_path, name):
     pdb_in.write_text(pdbio.format_pdb(ch, 0))
     fcz = tmp_path / "out.fcz"
     subprocess.check_call([CLI, "compress", "in.pdb", "out.fcz"], cwd=tmp_path)
-    # what the reference would produce for this text input: a text without HEADER id / TITLE record is named after the output
-    # path as given, without its extension (main.cpp:451-467, getFileParts)
-    parsed = pdbio.parse_pdb_chain(pdb_in.read_text(), "out")
+    # what the reference CLI would produce for this text input: the title is the text's TITLE record; a text without HEADER id /
+    # TITLE record is named after the output path as given, without its extension (main.cpp:451-467, getFileParts)
+    title = ch.title(0) or "out"
+    parsed = pdbio.parse_pdb_chain(pdb_in.read_text(), title)
     want = H.oracle_encode(parsed, 0, 25)
     assert fcz.read_bytes() == want
     pdb_out = tmp_path / "back.pdb"
     subprocess.check_call([CLI, "decompress", str(fcz), str(pdb_out)])
-    back = pdbio.parse_pdb_chain(pdb_out.read_text(), "out")
+    back = pdbio.parse_pdb_chain(pdb_out.read_text(), title)
     ref = H.oracle_decode(want)
     assert np.array_equal(back.res_type, ref.res_type)
     assert np.abs(back.xyz - ref.xyz).max() <= 0.05 + 0.0006  # tolerance + 3-decimal text rounding
     assert H.rmsd(back.xyz, ref.xyz) <= 0.01 + 0.0006
-    assert pdb_out.read_text().startswith("TITLE     out\nATOM ")
+    assert pdb_out.read_text().startswith(f"TITLE     {title}\nATOM ")
 
 
 def test_cli_rejects_garbage(tmp_path):
