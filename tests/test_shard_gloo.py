@@ -73,3 +73,18 @@ def test_shard_helpers():
     assert sorted(np.concatenate(bins).tolist()) == list(range(7))
     loads = [int(lens[b].sum()) for b in bins]
     assert abs(loads[0] - loads[1]) <= 200
+
+
+def test_bench_clock_sampler_without_nvml():
+    """bench.py's clock sampler on a box without a GPU: no exception, the JSON object says why there are no samples."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler("GPU-00000000-0000-0000-0000-000000000000", 0)
+    s.mark_begin()
+    s.mark_end()
+    out = s.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"} and (out["sm_mhz"] is None or out["sm_mhz"] > 0)
