@@ -1668,9 +1668,9 @@ fcz_engine* fcz_engine_create(int device, const fcz_opts* opts) {
     // experiment knobs (A/B runs, tools/kernel_ab.py): FCZ_ENC_XGLOBAL=1 reads coordinates from global memory instead of staging
     // them (smaller footprint, more CTAs per SM); FCZ_ENC_THREADS fixes the block size of the staged tiers
     {
-        // Coordinates are read from global memory by default: without the 12 bytes per atom of staging a 384-residue
-        // block needs 29 KB of shared memory instead of 71 KB, seven blocks share an SM instead of three, and the measured
-        // kernel time is lower (profiles/r02_*ab*.json); FCZ_ENC_XGLOBAL=0 restores the bulk-copy staging.
+        // Coordinates are read from global memory by default: without the 12 bytes per atom of staging a 352-residue
+        // block needs 26.5 KB of shared memory instead of 71 KB, eight blocks share an SM instead of three, and the
+        // measured kernel time is lower; FCZ_ENC_XGLOBAL=0 restores the bulk-copy staging.
         const char* v = getenv("FCZ_ENC_XGLOBAL");
         if (!v || atoi(v)) for (int i = 0; i < FCZ_NTIER; i++) { e->enc_tier[i].stage_x = 0; e->enc_tier[i].smem = enc_smem(e->enc_tier[i]).total; }
         if (const char* q = getenv("FCZ_ENC_PREFETCH_NEXT")) e->enc_prefetch_next = atoi(q) ? 1u : 0u;
