@@ -7,6 +7,7 @@ The Python surface mirrors the reference's CPython module for this path
     decompress(fcz_bytes) -> (name, pdb_str)                                 (foldcomp.cxx:222-239)
     open(path, *, ids=None, decompress=True, err_on_missing=False)           (foldcomp.cxx:333-433) -> FoldcompDatabase
     get_data(fcz_bytes | pdb_text) -> dict                                   (foldcomp.cxx:497-671)
+    split_pdb_by_chain(pdb_text) -> [pdb_text per chain]                     (foldcomp/util.py:1-18)
 
 Both go through the CUDA engine (include/fcz_engine.h); text parsing/formatting is host code
 (pdbio.py).  Batch entry points live in `engine.Engine`.  There is no CPU fallback.
@@ -16,7 +17,8 @@ from __future__ import annotations
 from . import abi
 from .abi import HostBlobBatch, HostChainBatch
 
-__all__ = ["compress", "decompress", "get_data", "open", "FoldcompDatabase", "error", "Engine", "HostChainBatch", "HostBlobBatch"]
+__all__ = ["compress", "decompress", "get_data", "open", "FoldcompDatabase", "error", "split_pdb_by_chain", "Engine", "HostChainBatch",
+           "HostBlobBatch"]
 
 
 class error(Exception):
@@ -40,6 +42,10 @@ def __getattr__(name):
         from .engine import Engine
 
         return Engine
+    if name == "split_pdb_by_chain":  # pure text helper of the reference package (foldcomp/util.py), same behaviour
+        from .pdbio import split_pdb_by_chain
+
+        return split_pdb_by_chain
     if name in ("open", "FoldcompDatabase"):
         from . import database
 

@@ -36,7 +36,7 @@ def _atom_records(pdb_text: str, one_chain: bool = True, dedup_alt: bool = True)
         if chain is None:
             chain = ch
         if one_chain and ch != chain:
-            raise PdbError("Multiple chains found")  # foldcomp.cxx:266-268 (flag 2)
+            raise PdbError("Multiple chains found. Please provide a single chain using 'foldcomp.split_pdb_by_chain'")  # foldcomp.cxx:266-268 (flag 2)
         # a short line or a blank / non-numeric fixed-column field is flag 3 of the C++ parser (parsePdbChain,
         # foldcomp_b200/csrc/fcz_db.cpp: n < 22, n < 61, failed numeric field): the same error here
         if len(line) < 61:
@@ -172,3 +172,14 @@ def _atom_line(rec, chain: str) -> str:
     return "ATOM  %5d %s %3s %s%4d    %8s%8s%8s  1.00%6s          %2s  \n" % (
         serial, nm, res, chain, resnum, _ftoa(x, 1000, 3), _ftoa(y, 1000, 3), _ftoa(z, 1000, 3), _ftoa(b, 100, 2), name[0],
     )
+
+
+def split_pdb_by_chain(pdb_str: str):
+    """foldcomp.split_pdb_by_chain (/root/reference/foldcomp/util.py:1-18): the ATOM records of a PDB text grouped into one
+    text per run of equal chain ids (column 22), in file order; every other record is dropped.  A text without ATOM records
+    gives one empty string, like the reference."""
+    import itertools
+
+    atom_lines = [line for line in pdb_str.splitlines() if line.startswith("ATOM")]
+    runs = ["".join(l + "\n" for l in grp) for _, grp in itertools.groupby(atom_lines, key=lambda l: l[21])]
+    return runs or [""]

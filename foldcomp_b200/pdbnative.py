@@ -44,7 +44,7 @@ def parse_pdb_chain(pdb_text: str, title: str) -> HostChainBatch:
     if flag == 1:
         raise PdbError("No ATOM lines found")
     if flag == 2:
-        raise PdbError("Multiple chains found")
+        raise PdbError("Multiple chains found. Please provide a single chain using 'foldcomp.split_pdb_by_chain'")
     if flag != 0:
         raise PdbError("Malformed ATOM record")
     tbytes = np.frombuffer(title.encode("latin-1"), np.uint8)

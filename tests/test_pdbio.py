@@ -89,3 +89,26 @@ def test_native_parser_face_equals_python_mirror(golden):
         pdbnative.parse_pdb_chain("HEADER x\n", "t")
     with pytest.raises(pdbio.PdbError, match="Multiple chains"):
         pdbnative.parse_pdb_chain(PDB.replace("ALA A   6", "ALA B   6"), "t")
+
+
+def test_split_pdb_by_chain_like_the_reference_helper():
+    """foldcomp_b200.split_pdb_by_chain against the reference package's pure-Python helper (foldcomp/util.py) where it is at
+    hand, and against spelled-out expectations everywhere."""
+    import importlib.util
+    import os
+
+    import foldcomp_b200
+
+    a = "ATOM      1  N   MET A   1      -1.000   2.000   3.000  1.00 50.00           N  "
+    b = a[:21] + "B" + a[22:]
+    text = "HEADER x\n" + a + "\n" + a + "\nTER\n" + b + "\nHETATM junk\n" + a + "\nEND\n"
+    want = [a + "\n" + a + "\n", b + "\n", a + "\n"]
+    assert foldcomp_b200.split_pdb_by_chain(text) == want
+    assert foldcomp_b200.split_pdb_by_chain("HEADER only\n") == [""] and foldcomp_b200.split_pdb_by_chain("") == [""]
+    ref_util = "/root/reference/foldcomp/util.py"
+    if os.path.exists(ref_util):
+        spec = importlib.util.spec_from_file_location("ref_util", ref_util)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        for t in (text, "HEADER only\n", "", a, a + "\n" + b):
+            assert foldcomp_b200.split_pdb_by_chain(t) == m.split_pdb_by_chain(t), t
