@@ -33,3 +33,4 @@ if [ -n "${EXTRA:-}" ]; then
 fi
 tail -8 gpurun_out/pytest_gpu.log 2>/dev/null; tail -2 gpurun_out/smoke.log 2>/dev/null; cat gpurun_out/bench.json 2>/dev/null | cut -c1-1500; tail -3 gpurun_out/bench.err 2>/dev/null
 cat gpurun_out/ab.jsonl 2>/dev/null | cut -c1-600; tail -3 gpurun_out/ab.err 2>/dev/null
+exit 0
