@@ -8,7 +8,10 @@ Files are the reference's (src/database_reader.cpp): `path` (data), `path.index`
 `path.lookup` (key, name, file).  Entries are decoded in BATCHES: reading entry i decodes entries i .. i+batch-1 with one
 fcz_decode_to_pdb call and keeps the texts until the window moves, so that iterating a database runs the GPU on
 hundreds of chains per launch instead of one.  Like the reference, one byte (the NUL terminator) is dropped from every
-entry's indexed length (foldcomp.cxx:66,73)."""
+entry's indexed length when the raw bytes are handed out (decompress=False; foldcomp.cxx:66,73).  For decoding the entry
+goes to the engine at its full indexed length: an FCZ blob carries its own size in its header, so a terminator is ignored
+and a database written WITHOUT terminators -- what `foldcomp compress --db` and `fcz_cli compress-db` write
+(src/main.cpp:510-517) -- decodes completely (the reference drops the last B-factor byte of such entries)."""
 from __future__ import annotations
 
 import builtins
@@ -71,9 +74,9 @@ class FoldcompDatabase:
     def __len__(self):
         return len(self._order) if self._order is not None else len(self._keys)
 
-    def _entry(self, pos: int) -> bytes:
+    def _entry(self, pos: int, full: bool = False) -> bytes:
         i = self._order[pos] if self._order is not None else pos
-        n = max(int(self._len[i]), 1) - 1
+        n = int(self._len[i]) if full else max(int(self._len[i]), 1) - 1
         o = int(self._off[i])
         return self._mm[o : o + n]
 
@@ -88,7 +91,7 @@ class FoldcompDatabase:
         first, count, texts, blobs = self._win
         if texts is None or not (first <= index < first + count):
             first, count = index, min(self._batch, n - index)
-            blobs = [self._entry(p) for p in range(first, first + count)]
+            blobs = [self._entry(p, full=True) for p in range(first, first + count)]
             texts = self._engine.decode_to_pdb_host(HostBlobBatch.from_blobs(blobs))
             self._win = (first, count, texts, blobs)
         j = index - first

@@ -245,3 +245,33 @@ def test_writer_batch_append_both_modes(tmp_path, monkeypatch):
         ]
         assert got == want, mode
         assert os.path.getsize(path) == sum(len(b) + 1 for _, _, b in want)
+
+
+def test_python_database_hands_full_entries_to_the_decoder(golden, tmp_path, monkeypatch):
+    """decompress=True: every entry reaches the engine at its full indexed length -- with its terminator when the database
+    has them (the decoder sizes a blob from its header), complete when it has none (`foldcomp compress --db` and
+    `fcz_cli compress-db` write none); raw mode keeps the reference's one-byte strip.  The engine is a stub here: the
+    decoding itself is tests/test_gpu_db.py's business."""
+    import foldcomp_b200
+    from foldcomp_b200 import abi, database
+
+    seen = []
+
+    class StubEngine:
+        def decode_to_pdb_host(self, blobs):
+            seen.append(blobs.blobs())
+            n = blobs.n_chains
+            return abi.HostTextBatch(np.arange(n + 1, dtype=np.uint64), np.frombuffer(b"x" * n, np.uint8).copy(), np.zeros(n, np.int32))
+
+    monkeypatch.setattr(foldcomp_b200, "_get_engine", lambda: StubEngine())
+    blobs = list(golden.db_blobs[:3])
+    for nul in (True, False):
+        path = str(tmp_path / f"db_{int(nul)}")
+        dbutil.write_db(path, [(k, f"n{k}", b) for k, b in enumerate(blobs)], nul=nul)
+        seen.clear()
+        with database.FoldcompDatabase(path) as db:
+            name, text = db[1]
+            assert text == "x" and isinstance(name, str)
+        assert seen and seen[0] == [b + (b"\0" if nul else b"") for b in blobs[1:]]  # the window opens at the entry asked for
+        with foldcomp_b200.open(path, decompress=False) as db:
+            assert [db[i] for i in range(3)] == [(b if nul else b[:-1]) for b in blobs]
